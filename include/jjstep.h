@@ -1,0 +1,128 @@
+/*
+ * jjstep.h - C ABI of the B200 time-evolution engine (libjjstep.so).
+ *
+ * Drop-in boundary for ONE hot path of pyjjasim: the implicit RCSJ stepping loop
+ *   time_evolution_core(problem, th_store_mask, I_store_mask) -> (th_out, I_out)
+ *   (reference: /root/reference/time_evolution.py:461-582)
+ * The reference has no FFI layer (it is pure Python); the seam is the Python call
+ * TimeEvolutionProblem.compute() -> time_evolution() -> time_evolution_core()
+ * (reference: time_evolution.py:303-307, :422-458, :461). Each entry point below cites the part of
+ * that function it replaces. Plain pointers and sizes only; every host pointer is BORROWED for the
+ * duration of the call and copied to the device inside it; outputs are copied into caller-allocated
+ * buffers. All functions return 0 on success and a negative JJ_E* code on failure;
+ * jj_last_error() returns a message. There is NO CPU fallback: without a CUDA device jj_create fails.
+ *
+ * Face indices crossing this interface are in the PERMUTED numbering chosen by the host-side
+ * nested dissection (the permutation never needs to be undone on the device because all stored
+ * outputs are per junction).
+ *
+ * Layouts: host arrays named (Nj, W) are C-ordered with the problem index minor, as in the reference.
+ */
+#ifndef JJSTEP_H
+#define JJSTEP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct JJHandle JJHandle;
+
+enum { JJ_OK = 0, JJ_ECUDA = -1, JJ_EINVAL = -2, JJ_ESTATE = -3, JJ_ENOMEM = -4, JJ_ENONFINITE = -5 };
+
+/* which per-step input a source call refers to (reference: time_evolution.py:524-531) */
+enum { JJ_SRC_IS = 0, JJ_SRC_F = 1, JJ_SRC_VS = 2, JJ_SRC_T = 3 };
+/* device forms of an input (see pyjjasim_b200/sources.py) */
+enum { JJ_KIND_ZERO = 0, JJ_KIND_RANK1 = 1, JJ_KIND_DENSE = 2 };
+/* step engines */
+enum { JJ_ENGINE_AUTO = 0,      /* pick RESIDENT when the problem fits, else STREAMING */
+       JJ_ENGINE_STREAMING = 1, /* problem-minor (Nj, W) arrays in HBM, one kernel per phase */
+       JJ_ENGINE_RESIDENT = 2   /* persistent kernel: a thread-block cluster owns a tile of problems for the
+                                   whole time loop, right-hand sides live in shared memory */ };
+
+/* One sweep (forward or backward) of the compiled solve program, see pyjjasim_b200/factor.py.
+ * Replaces the two SuperLU triangular sweeps per step (reference: time_evolution.py:506, :560-569). */
+typedef struct {
+    int32_t n_levels;
+    const int32_t *level_ptr;    /* [n_levels+1] -> groups */
+    const int32_t *group_ptr;    /* [n_groups+1] -> tiles; tiles of a group are processed in order */
+    int32_t n_tiles;
+    const int32_t *tile_row0;    /* first output row (permuted face index) */
+    const int32_t *tile_nrows;   /* 1..32 */
+    const int32_t *tile_lpr;     /* lanes per row; (32 / lpr) >= nrows */
+    const int32_t *tile_nsteps;  /* columns = nsteps * lpr */
+    const int32_t *tile_flags;   /* bit0: add src[row]; bit1: staged (block spans several tiles) */
+    const int64_t *tile_col_off; /* into cols */
+    const int64_t *tile_val_off; /* into vals */
+    int64_t n_cols;  const int32_t *cols;
+    int64_t n_vals;  const double  *vals;   /* [tile][step][32 lanes] */
+    int32_t stage_rows;
+} JJSweep;
+
+/* Circuit constants, per junction, precomputed on the host in float64 exactly as the reference does
+ * (reference: time_evolution.py:470-478): Rv = 1/(dt R), Cv = C/dt^2, c0 = Rv+Cv, c1 = -Rv-2Cv, c2 = Cv. */
+typedef struct {
+    int32_t Nj, Nf;
+    const int32_t *face_ptr;    /* [Nf+1] CSR rows of the cycle matrix A, permuted face order */
+    const int32_t *face_junc;   /* junction index per entry */
+    const int8_t  *face_sign;   /* +1 / -1 */
+    const int32_t *junc_face;   /* [Nj*2] the (at most two) faces of each junction, -1 if none */
+    const int8_t  *junc_sign;   /* [Nj*2] */
+    const double *Ic, *c0, *c1, *c2;   /* [Nj] */
+    int32_t cpr_harmonics;      /* M >= 1; Icp = Ic * sum_{m<=M} a[m] cos(m th) + b[m] sin(m th) */
+    const double *cpr_a, *cpr_b; /* [M+1]; DefaultCPR is M=1, a={0,0}, b={0,1} (reference: static_problem.py:77-85) */
+} JJCircuit;
+
+/* create / destroy an engine bound to one CUDA device */
+int  jj_create(int device, JJHandle **out);
+void jj_destroy(JJHandle *h);
+const char *jj_last_error(const JJHandle *h);   /* h may be NULL: error of the last failed jj_create */
+
+/* setup (reference: time_evolution.py:466-519) */
+int jj_set_circuit(JJHandle *h, const JJCircuit *c);
+int jj_set_solver(JJHandle *h, const JJSweep *fwd, const JJSweep *bwd);
+/* W problems, time step dt, Philox seed, index of this shard's first problem in the global batch
+ * (keeps noise identical however the batch is sharded over GPUs; must be a multiple of 4) */
+int jj_set_problem(JJHandle *h, int32_t W, double dt, uint64_t seed, int64_t problem_offset, int32_t engine);
+/* theta(-1), theta(-2): (Nj, W) host arrays (reference: time_evolution.py:480,490; config_at_minus_1/2) */
+int jj_set_state(JJHandle *h, const double *theta_m1, const double *theta_m2);
+int jj_get_state(JJHandle *h, double *theta_m1, double *theta_m2);
+
+/* per-step inputs (reference: time_evolution.py:342-356, :524-531).
+ * RANK1: value(e,w,i) = base[e] * amp[i - i0][w];  DENSE: value = table[i - i0][e][w].
+ * is_static != 0: a single row/plane valid for all steps. For JJ_SRC_T the host passes
+ * base = sqrt(2 * Tbase * Rv) and amp = sqrt(Tamp) (RANK1) so that the device multiplies once;
+ * for JJ_SRC_VS (RANK1) amp is the running sum of Vs*dt BEFORE step i (reference: :579-580). */
+int jj_set_source(JJHandle *h, int32_t which, int32_t kind, int32_t is_static, const double *base /* [N] or NULL */);
+int jj_upload_source(JJHandle *h, int32_t which, int64_t i0, int32_t K, const double *table /* (K,W) or (K,N,W) */);
+/* standard-normal draws to use instead of the Philox generator for steps [i0, i0+K): (K, Nj, W); K = 0 disables */
+int jj_upload_noise(JJHandle *h, int64_t i0, int32_t K, const double *Z);
+
+/* output planes kept on the device: theta and current snapshots, (plane, Nj, W) */
+int jj_alloc_outputs(JJHandle *h, int64_t n_theta_planes, int64_t n_current_planes);
+/* Run steps [i0, i0+n) (reference: time_evolution.py:523-580). th_plane[k] / I_plane[k] >= 0: store
+ * theta / current of step i0+k into that plane; -1: do not store. */
+int jj_run(JJHandle *h, int64_t i0, int32_t n, const int64_t *th_plane, const int64_t *I_plane);
+int jj_fetch_theta(JJHandle *h, int64_t plane0, int64_t n_planes, double *dst /* (n_planes, Nj, W) */);
+int jj_fetch_current(JJHandle *h, int64_t plane0, int64_t n_planes, double *dst);
+/* device generator check: the standard normal draws the device would use at one step, (Nj, W) */
+int jj_debug_noise(JJHandle *h, int64_t step, double *dst);
+/* one solve J = S^-1 b through the compiled program, (Nf, W) host arrays in permuted face order */
+int jj_debug_solve(JJHandle *h, const double *b, double *J);
+
+typedef struct {
+    int32_t engine;             /* engine actually used */
+    int32_t cluster_size, tile_problems;
+    int64_t steps_done;
+    int64_t kernel_launches;    /* launches of OUR kernels since jj_set_problem */
+    double  step_ms;            /* device time of the last jj_run (CUDA events on the run stream) */
+    int64_t device_bytes;       /* device memory held */
+    int32_t non_finite;         /* 1 if a non-finite phase was seen */
+} JJStats;
+int jj_stats(JJHandle *h, JJStats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

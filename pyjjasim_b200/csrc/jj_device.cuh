@@ -1,0 +1,115 @@
+// Device helpers shared by the streaming and the resident step engines (sm_100a).
+//
+// Arithmetic contract (reference: /root/reference/time_evolution.py:533-580), per junction j, problem w:
+//   theta_n   = (y - x) / c0                                   y = (A^T J)[j]
+//   X         = Ic * cpr(2 theta_n - theta_{n-1}) + c1 theta_n + c2 theta_{n-1}
+//   x'        = (noise - Is) + X                               noise = sqrt(2 T Rv) * Z,  Z ~ N(0,1)
+//   b[f]      = sum_j A[f,j] (x'_j / c0_j - theta_s_j) - 2 pi f_f
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace jj {
+
+enum { KIND_ZERO = 0, KIND_RANK1 = 1, KIND_DENSE = 2 };
+
+// One per-step input on the device. `table` rows are indexed by (step - i0), or 0 when is_static.
+struct Source {
+    int kind;
+    int is_static;
+    long long i0;
+    int K;
+    const double* base;    // [N]           (RANK1)
+    const double* table;   // [K][ld]       (RANK1: ld = Wp)   or [K][N][ld] (DENSE)
+};
+
+__device__ __forceinline__ long long source_row(const Source& s, long long step) {
+    return s.is_static ? 0 : (step - s.i0);
+}
+
+// value(e, w..w+3, step) for four consecutive problems
+__device__ __forceinline__ void source_eval4(const Source& s, long long step, int e, int N, int ld, int w,
+                                             double out[4]) {
+    if (s.kind == KIND_ZERO) { out[0] = out[1] = out[2] = out[3] = 0.0; return; }
+    long long r = source_row(s, step);
+    if (s.kind == KIND_RANK1) {
+        double b = s.base[e];
+        const double2* t = reinterpret_cast<const double2*>(s.table + r * ld + w);
+        double2 a0 = t[0], a1 = t[1];
+        out[0] = b * a0.x; out[1] = b * a0.y; out[2] = b * a1.x; out[3] = b * a1.y;
+    } else {
+        const double2* t = reinterpret_cast<const double2*>(s.table + (r * N + e) * (long long)ld + w);
+        double2 a0 = t[0], a1 = t[1];
+        out[0] = a0.x; out[1] = a0.y; out[2] = a1.x; out[3] = a1.y;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Counter-based noise: Philox4x32-10 (Salmon et al., SC'11), key = seed, counter = (junction,
+// problem group = w/4, step lo, step hi). The four 32-bit outputs make two Box-Muller pairs, i.e. the
+// four standard normals of problems 4g..4g+3 at this junction and step. Single precision
+// transcendentals are enough for thermal noise (relative error 1e-6 on a random number) and keep the
+// FP64 pipe free for the phase update. Replaces np.random.randn (reference: time_evolution.py:533-538).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t out[4]) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
+    // u in (0, 1]: all 32 bits are kept where it matters (small a is exact in float -> 6.7 sigma tail);
+    // angle in [0, 2pi)
+    float u = fminf((float(a) + 0.5f) * 2.3283064365386963e-10f, 1.0f);
+    float v = float(b >> 8) * (1.0f / 16777216.0f);
+    float r = sqrtf(-2.0f * __logf(u));
+    float s, c;
+    __sincosf(6.283185307179586f * v, &s, &c);
+    z0 = r * c;
+    z1 = r * s;
+}
+
+__device__ __forceinline__ void normal4(uint64_t seed, int junction, long long group, long long step, double z[4]) {
+    uint32_t o[4];
+    philox4x32_10((uint32_t)junction, (uint32_t)group, (uint32_t)step, (uint32_t)((unsigned long long)step >> 32),
+                  (uint32_t)seed, (uint32_t)(seed >> 32), o);
+    float a, b, c, d;
+    box_muller(o[0], o[1], a, b);
+    box_muller(o[2], o[3], c, d);
+    z[0] = a; z[1] = b; z[2] = c; z[3] = d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Current-phase relation Ic * g(theta), g a trigonometric polynomial (DefaultCPR: g = sin).
+// (reference: static_problem.py:34-85; custom relations are fitted on the host, current_phase_relation.py)
+// ---------------------------------------------------------------------------------------------
+struct Cpr {
+    int M;
+    double a[17], b[17];
+};
+
+template <bool DEFAULT>
+__device__ __forceinline__ double cpr_eval(const Cpr& c, double th) {
+    if (DEFAULT) return sin(th);
+    double s, co;
+    sincos(th, &s, &co);
+    double acc = c.a[0] + c.a[1] * co + c.b[1] * s;
+    double cm = co, sm = s;
+    for (int m = 2; m <= c.M; ++m) {
+        double cn = cm * co - sm * s;
+        double sn = sm * co + cm * s;
+        cm = cn; sm = sn;
+        acc += c.a[m] * cm + c.b[m] * sm;
+    }
+    return acc;
+}
+
+}  // namespace jj

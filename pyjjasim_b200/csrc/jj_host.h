@@ -1,0 +1,94 @@
+// Host-side engine state behind the opaque JJHandle (see include/jjstep.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/jjstep.h"
+#include "jj_device.cuh"
+
+namespace jj {
+
+struct SweepDev {
+    int n_levels = 0, n_tiles = 0, n_groups = 0, stage_rows = 0;
+    std::vector<int> level_ptr, group_ptr;      // host copies for launch configuration
+    std::vector<int> tile_row0_h, tile_nrows_h, tile_flags_h;
+    int *group_ptr_d = nullptr;
+    int *tile_row0 = nullptr, *tile_nrows = nullptr, *tile_lpr = nullptr, *tile_nsteps = nullptr, *tile_flags = nullptr;
+    long long *tile_col_off = nullptr, *tile_val_off = nullptr;
+    int *cols = nullptr;
+    double *vals = nullptr;
+    long long n_cols = 0, n_vals = 0;
+};
+
+// kernel-side view of a sweep
+struct SweepView {
+    const int *group_ptr, *tile_row0, *tile_nrows, *tile_lpr, *tile_nsteps, *tile_flags;
+    const long long *tile_col_off, *tile_val_off;
+    const int *cols;
+    const double *vals;
+};
+
+struct CircuitDev {
+    int Nj = 0, Nf = 0;
+    int *face_ptr = nullptr, *face_junc = nullptr;
+    signed char *face_sign = nullptr;
+    int *junc_face = nullptr;
+    signed char *junc_sign = nullptr;
+    double *Ic = nullptr, *c0 = nullptr, *c1 = nullptr, *c2 = nullptr;
+    Cpr cpr;
+    bool default_cpr = true;
+    int max_face_len = 0;
+};
+
+struct SourceHost {
+    Source dev{};            // device view (pointers are device pointers)
+    double *base_buf = nullptr, *table_buf = nullptr;
+    size_t table_cap = 0;    // bytes
+    int N = 0;
+};
+
+}  // namespace jj
+
+struct JJHandle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    jj::CircuitDev cir;
+    jj::SweepDev fwd, bwd;
+    bool have_circuit = false, have_solver = false, have_problem = false, have_state = false;
+    // problem
+    int W = 0, Wp = 0;
+    double dt = 0.0;
+    uint64_t seed = 0;
+    long long problem_offset = 0;
+    int engine_req = 0, engine = 0;
+    // state (streaming engine): problem-minor [Nj][Wp]
+    double *th1 = nullptr, *th2 = nullptr, *x = nullptr, *thetas = nullptr, *v = nullptr;
+    jj::SourceHost src[4];
+    // injected noise
+    double *noise_buf = nullptr; size_t noise_cap = 0; long long noise_i0 = 0; int noise_K = 0;
+    // outputs
+    double *th_out = nullptr, *I_out = nullptr; long long n_th_planes = 0, n_I_planes = 0;
+    int *flag_d = nullptr;
+    // resident engine (see jj_resident.cu)
+    void *resident = nullptr;
+    // stats
+    long long steps_done = 0, launches = 0, device_bytes = 0;
+    double last_ms = 0.0;
+    int non_finite = 0;
+};
+
+namespace jj {
+// implemented in jj_resident.cu
+int resident_supported(JJHandle* h, std::string& why_not);
+int resident_prepare(JJHandle* h);
+int resident_run(JJHandle* h, long long i0, int n, const long long* th_plane, const long long* I_plane);
+int resident_set_state(JJHandle* h, const double* t1, const double* t2);
+int resident_get_state(JJHandle* h, double* t1, double* t2);
+void resident_free(JJHandle* h);
+int dev_alloc(JJHandle* h, void** p, size_t bytes);
+void dev_free(JJHandle* h, void* p, size_t bytes);
+}

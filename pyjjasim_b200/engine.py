@@ -1,0 +1,453 @@
+"""
+Host driver of the device time-evolution core.
+
+``device_time_evolution_core(problem, th_store_mask, I_store_mask)`` has the contract of the
+reference's ``time_evolution_core`` (reference: time_evolution.py:461-582): it returns ``th_out`` and
+``I_out`` of shape (Nj, W, n_stored + 2) whose first two planes are the initial conditions
+theta(-2), theta(-1) (and their supercurrents). Everything inside the reference's ``for`` loop runs
+on the GPU through the C ABI of include/jjstep.h; the host only
+
+  * builds the circuit tables and the compiled solve program once (``CircuitTables``),
+  * classifies the four per-step inputs (sources.py) and uploads their tables chunk by chunk,
+  * shards the problem axis over the requested devices (one host thread per GPU, no collective on
+    the step path) and gathers the stored planes at the end.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+import scipy.sparse
+
+from . import _lib
+from .current_phase_relation import harmonics
+from .factor import build_solve_program, system_matrix
+from .sources import classify_source, nonnegative_factors, ZERO, RANK1, DENSE
+
+__all__ = ["device_time_evolution_core", "CircuitTables", "DeviceEngine", "last_run_stats"]
+
+_TABLE_BYTES = 64 << 20      # budget for one chunk of rank-one amplitude tables
+_DENSE_BYTES = 256 << 20     # budget for one chunk of dense tables / injected noise
+last_run_stats = {}          # filled by device_time_evolution_core (per device), for benchmarks and tests
+
+
+class CircuitTables:
+    """
+    Everything the device needs that depends only on (circuit, dt): coefficient vectors
+    (reference: time_evolution.py:470-478), CSR form of A in the permuted face order, the two faces of
+    every junction, and the compiled solve program of A (L + 1/(Cv+Rv)) A^T (reference: :504-506).
+    """
+
+    def __init__(self, circuit, dt, leaf_size=None):
+        A = scipy.sparse.csr_matrix(circuit.get_cycle_matrix())
+        A.sum_duplicates()
+        A.eliminate_zeros()
+        A.sort_indices()
+        Nf, Nj = A.shape
+        self.Nj, self.Nf, self.dt = Nj, Nf, dt
+        R = np.asarray(circuit._R(), dtype=np.double)
+        Cc = np.asarray(circuit._C(), dtype=np.double)
+        self.Rv = 1 / (dt * R)
+        self.Cv = Cc / (dt ** 2)
+        self.c0 = 1.0 * self.Rv + 1.0 * self.Cv
+        self.c1 = -1.0 * self.Rv + -2.0 * self.Cv
+        self.c2 = 0.0 * self.Rv + 1.0 * self.Cv
+        self.Ic = np.ascontiguousarray(circuit._Ic(), dtype=np.double)
+        if leaf_size is None:
+            leaf_size = int(os.environ.get("JJ_LEAF_SIZE", "8"))
+        if Nf > 0:
+            S = system_matrix(A, circuit._L(), self.Rv, self.Cv)
+            if hasattr(circuit, "get_face_centroids"):
+                cx, cy = circuit.get_face_centroids()
+            else:
+                cx, cy = _centroids_from_matrix(circuit, A)
+            self.program = build_solve_program(S, cx, cy, leaf_size=leaf_size)
+            perm = self.program.perm.astype(np.int64)
+        else:
+            self.program = None
+            perm = np.zeros(0, dtype=np.int64)
+        self.perm = perm
+        inv = np.empty(Nf, dtype=np.int64)
+        inv[perm] = np.arange(Nf)
+        self.inv_perm = inv
+        Ap = A[perm] if Nf else A
+        Ap.sort_indices()                       # ascending junction index inside a face, like the reference's CSC product
+        self.face_ptr = Ap.indptr.astype(np.int32)
+        self.face_junc = Ap.indices.astype(np.int32)
+        self.face_sign = Ap.data.astype(np.int8)
+        # the (at most two) faces of each junction, in ascending ORIGINAL face order like the reference's A^T product
+        At = scipy.sparse.csr_matrix(A.T)
+        At.sort_indices()
+        cnt = np.diff(At.indptr)
+        if cnt.size and cnt.max() > 2:
+            raise ValueError("a junction borders more than two faces; the circuit is not a planar embedding")
+        jf = np.full((Nj, 2), -1, dtype=np.int32)
+        js = np.zeros((Nj, 2), dtype=np.int8)
+        rows = np.repeat(np.arange(Nj), cnt)
+        slot = np.arange(At.indices.size) - At.indptr[rows]
+        jf[rows, slot] = inv[At.indices]
+        js[rows, slot] = At.data
+        self.junc_face, self.junc_sign = jf, js
+
+
+def _centroids_from_matrix(circuit, A):
+    x, y = circuit.get_node_coordinates()
+    n1, n2 = circuit.get_junction_nodes()
+    jx, jy = 0.5 * (x[n1] + x[n2]), 0.5 * (y[n1] + y[n2])
+    B = abs(A)
+    deg = np.asarray(B.sum(axis=1)).ravel()
+    return (B @ jx) / deg, (B @ jy) / deg
+
+
+_tables_cache = {}
+
+
+def _tables_for(circuit, dt):
+    """Cache per circuit object, invalidated when component values change."""
+    L = circuit._L()
+    key = (id(circuit), float(dt), hash(np.asarray(circuit._R()).tobytes()), hash(np.asarray(circuit._C()).tobytes()),
+           hash(np.asarray(circuit._Ic()).tobytes()), hash(L.data.tobytes()) ^ hash(L.indices.tobytes()),
+           os.environ.get("JJ_LEAF_SIZE", "8"))
+    hit = _tables_cache.get(id(circuit))
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    tab = CircuitTables(circuit, dt)
+    _tables_cache[id(circuit)] = (key, tab)
+    return tab
+
+
+class DeviceEngine:
+    """One GPU, one shard of the problem axis. Thin object wrapper over the C ABI."""
+
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        self.h = C.c_void_p()
+        rc = self.lib.jj_create(int(device), C.byref(self.h))
+        if rc != 0:
+            raise RuntimeError("jj_create failed: " + self.lib.jj_last_error(None).decode())
+        self.device = device
+        self._keep = []
+
+    def close(self):
+        if self.h:
+            self.lib.jj_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            msg = self.lib.jj_last_error(self.h).decode()
+            if rc == _lib.JJ_ENONFINITE:
+                raise FloatingPointError(msg)
+            raise (ValueError if rc == -2 else RuntimeError)(f"libjjstep error {rc}: {msg}")
+
+    # --- setup -----------------------------------------------------------------------------
+    def set_circuit(self, tab: CircuitTables, cpr):
+        a, b = harmonics(cpr)
+        a, b = _lib.c_f64(a), _lib.c_f64(b)
+        c = _lib.JJCircuit()
+        c.Nj, c.Nf = tab.Nj, tab.Nf
+        keep = [tab.face_ptr, tab.face_junc, tab.face_sign, np.ascontiguousarray(tab.junc_face),
+                np.ascontiguousarray(tab.junc_sign), tab.Ic, _lib.c_f64(tab.c0), _lib.c_f64(tab.c1),
+                _lib.c_f64(tab.c2), a, b]
+        c.face_ptr, c.face_junc, c.face_sign = _lib.i32(keep[0]), _lib.i32(keep[1]), _lib.i8(keep[2])
+        c.junc_face, c.junc_sign = _lib.i32(keep[3]), _lib.i8(keep[4])
+        c.Ic, c.c0, c.c1, c.c2 = _lib.f64(keep[5]), _lib.f64(keep[6]), _lib.f64(keep[7]), _lib.f64(keep[8])
+        c.cpr_harmonics = len(a) - 1
+        c.cpr_a, c.cpr_b = _lib.f64(a), _lib.f64(b)
+        self._ck(self.lib.jj_set_circuit(self.h, C.byref(c)))
+        sweeps = []
+        for name in ("fwd", "bwd"):
+            sw = tab.program.sweeps[name] if tab.program is not None else _empty_sweep()
+            s = _lib.JJSweep()
+            s.n_levels = len(sw["level_ptr"]) - 1
+            s.level_ptr, s.group_ptr = _lib.i32(sw["level_ptr"]), _lib.i32(sw["group_ptr"])
+            s.n_tiles = len(sw["tile_row0"])
+            s.tile_row0, s.tile_nrows = _lib.i32(sw["tile_row0"]), _lib.i32(sw["tile_nrows"])
+            s.tile_lpr, s.tile_nsteps = _lib.i32(sw["tile_lpr"]), _lib.i32(sw["tile_nsteps"])
+            s.tile_flags = _lib.i32(sw["tile_flags"])
+            s.tile_col_off, s.tile_val_off = _lib.i64(sw["tile_col_off"]), _lib.i64(sw["tile_val_off"])
+            s.n_cols, s.cols = sw["cols"].size, _lib.i32(sw["cols"])
+            s.n_vals, s.vals = sw["vals"].size, _lib.f64(sw["vals"])
+            s.stage_rows = sw["stage_rows"]
+            sweeps.append(s)
+        self._ck(self.lib.jj_set_solver(self.h, C.byref(sweeps[0]), C.byref(sweeps[1])))
+        self.tab = tab
+
+    def set_problem(self, W, dt, seed=0, problem_offset=0, engine=_lib.JJ_ENGINE_AUTO):
+        self.W = W
+        self._ck(self.lib.jj_set_problem(self.h, W, float(dt), int(seed) & (2 ** 64 - 1), int(problem_offset), engine))
+
+    def set_state(self, th_m1, th_m2):
+        a, b = _lib.c_f64(th_m1), _lib.c_f64(th_m2)
+        assert a.shape == (self.tab.Nj, self.W) and b.shape == (self.tab.Nj, self.W)
+        self._ck(self.lib.jj_set_state(self.h, _lib.f64(a), _lib.f64(b)))
+
+    def get_state(self):
+        a = np.empty((self.tab.Nj, self.W)); b = np.empty((self.tab.Nj, self.W))
+        self._ck(self.lib.jj_get_state(self.h, _lib.f64(a), _lib.f64(b)))
+        return a, b
+
+    def set_source(self, which, kind, is_static, base=None):
+        basep = _lib.f64(_lib.c_f64(base)) if base is not None else None
+        self._ck(self.lib.jj_set_source(self.h, which, kind, int(is_static), basep))
+
+    def upload_source(self, which, i0, table):
+        t = _lib.c_f64(table)
+        self._ck(self.lib.jj_upload_source(self.h, which, int(i0), int(t.shape[0]), _lib.f64(t)))
+
+    def upload_noise(self, i0, Z):
+        if Z is None:
+            self._ck(self.lib.jj_upload_noise(self.h, 0, 0, None))
+            return
+        z = _lib.c_f64(Z)
+        self._ck(self.lib.jj_upload_noise(self.h, int(i0), int(z.shape[0]), _lib.f64(z)))
+
+    def alloc_outputs(self, n_th, n_I):
+        self._ck(self.lib.jj_alloc_outputs(self.h, int(n_th), int(n_I)))
+
+    def run(self, i0, n, th_plane=None, I_plane=None):
+        tp = np.ascontiguousarray(th_plane if th_plane is not None else -np.ones(n), dtype=np.int64)
+        ip = np.ascontiguousarray(I_plane if I_plane is not None else -np.ones(n), dtype=np.int64)
+        self._ck(self.lib.jj_run(self.h, int(i0), int(n), _lib.i64(tp), _lib.i64(ip)))
+
+    def fetch_theta(self, p0, n):
+        out = np.empty((n, self.tab.Nj, self.W))
+        self._ck(self.lib.jj_fetch_theta(self.h, int(p0), int(n), _lib.f64(out)))
+        return out
+
+    def fetch_current(self, p0, n):
+        out = np.empty((n, self.tab.Nj, self.W))
+        self._ck(self.lib.jj_fetch_current(self.h, int(p0), int(n), _lib.f64(out)))
+        return out
+
+    def debug_noise(self, step):
+        out = np.empty((self.tab.Nj, self.W))
+        self._ck(self.lib.jj_debug_noise(self.h, int(step), _lib.f64(out)))
+        return out
+
+    def debug_solve(self, b):
+        """Solve S J = b on the device; b, J are (Nf, W) in ORIGINAL face numbering."""
+        bp = _lib.c_f64(np.asarray(b)[self.tab.perm])
+        Jp = np.empty_like(bp)
+        self._ck(self.lib.jj_debug_solve(self.h, _lib.f64(bp), _lib.f64(Jp)))
+        J = np.empty_like(Jp)
+        J[self.tab.perm] = Jp
+        return J
+
+    def stats(self):
+        s = _lib.JJStats()
+        self._ck(self.lib.jj_stats(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in s._fields_}
+
+
+def _empty_sweep():
+    z32, z64 = np.zeros(1, np.int32), np.zeros(1, np.int64)
+    return dict(level_ptr=z32, group_ptr=z32, tile_row0=z32[:0], tile_nrows=z32[:0], tile_lpr=z32[:0],
+                tile_nsteps=z32[:0], tile_flags=z32[:0], tile_col_off=z64[:0], tile_val_off=z64[:0],
+                cols=z32[:0], vals=np.zeros(0), stage_rows=0)
+
+
+# ----------------------------------------------------------------------------------------------
+class _ShardInputs:
+    """The four classified inputs restricted to problems [w0, w1)."""
+
+    def __init__(self, specs, w0, w1):
+        self.specs, self.w0, self.w1 = specs, w0, w1
+
+    def amp(self, name, i0, i1):
+        return self.specs[name].amp_chunk(i0, i1)[:, self.w0:self.w1]
+
+    def dense(self, name, i0, i1):
+        return self.specs[name].dense_chunk(i0, i1)[:, :, self.w0:self.w1]
+
+
+def _classify_all(problem, tab):
+    Nj, Nf, W, Nt = tab.Nj, tab.Nf, problem.get_problem_count(), problem._Nt()
+    raw = getattr(problem, "_raw_sources", None)
+    if raw is None:       # a reference-style problem object: use its stored inputs
+        raw = dict(f=problem.external_flux, Is=problem.current_sources, Vs=problem.voltage_sources,
+                   T=problem.temperature)
+    specs = dict(Is=classify_source(raw["Is"], Nj, W, Nt), f=classify_source(raw["f"], Nf, W, Nt),
+                 Vs=classify_source(raw["Vs"], Nj, W, Nt),
+                 T=nonnegative_factors(classify_source(raw["T"], Nj, W, Nt)))
+    return specs
+
+
+def _chunk_length(specs, tab, W, Nt, has_replay):
+    K = Nt
+    for name, s in specs.items():
+        if s.kind == ZERO or (s.static and not (name == "Vs" and s.kind == RANK1)):
+            continue
+        N = tab.Nf if name == "f" else tab.Nj
+        per = W * 8 if s.kind == RANK1 else N * W * 8
+        K = min(K, max(1, (_TABLE_BYTES if s.kind == RANK1 else _DENSE_BYTES) // per))
+    if has_replay:
+        K = min(K, max(1, _DENSE_BYTES // (tab.Nj * W * 8)))
+    return max(1, K)
+
+
+_WHICH = dict(Is=_lib.JJ_SRC_IS, f=_lib.JJ_SRC_F, Vs=_lib.JJ_SRC_VS, T=_lib.JJ_SRC_T)
+
+
+def _run_shard(problem, tab, specs, dev, w0, w1, th_mask, I_mask, th_host, I_host, engine_kind, stats_out):
+    """Integrate problems [w0, w1) on one device and write stored planes into th_host / I_host
+    (plane-major (n_planes + 2, Nj, W) arrays, planes 0 and 1 are the initial conditions)."""
+    Nj, Nf, Nt, dt = tab.Nj, tab.Nf, problem._Nt(), problem._dt()
+    W = w1 - w0
+    eng = DeviceEngine(dev)
+    try:
+        eng.set_circuit(tab, problem.current_phase_relation)
+        seed = problem.noise_seed if getattr(problem, "noise_seed", None) is not None else 0
+        eng.set_problem(W, dt, seed=seed, problem_offset=w0, engine=engine_kind)
+        eng.set_state(problem.config_at_minus_1[:, w0:w1], problem.config_at_minus_2[:, w0:w1])
+        sh = _ShardInputs(specs, w0, w1)
+        replay = getattr(problem, "noise_replay", None)
+        # static parts
+        vs_cum = np.zeros(W)          # running sum of Vs amplitude * dt (rank-one voltage sources)
+        for name, s in specs.items():
+            which = _WHICH[name]
+            if s.kind == ZERO:
+                eng.set_source(which, _lib.JJ_KIND_ZERO, True)
+                continue
+            if s.kind == RANK1:
+                base = s.base
+                if name == "T":
+                    base = np.sqrt(2.0 * s.base * tab.Rv)
+                elif name == "f":
+                    base = s.base[tab.perm]
+                static = s.static and name != "Vs"
+                eng.set_source(which, _lib.JJ_KIND_RANK1, static, base)
+                if static:
+                    amp = sh.amp(name, 0, 1)
+                    eng.upload_source(which, 0, np.sqrt(amp) if name == "T" else amp)
+            else:
+                eng.set_source(which, _lib.JJ_KIND_DENSE, s.static)
+                if s.static:
+                    eng.upload_source(which, 0, _dense_for_device(name, sh.dense(name, 0, 1), tab))
+        K = _chunk_length(specs, tab, W, Nt, replay is not None)
+        th_idx = np.cumsum(th_mask) - 1      # plane index (without the +2 offset) of each stored step
+        I_idx = np.cumsum(I_mask) - 1
+        total_ms = 0.0
+        for i0 in range(0, Nt, K):
+            i1 = min(Nt, i0 + K)
+            n = i1 - i0
+            for name, s in specs.items():
+                which = _WHICH[name]
+                if s.kind == ZERO:
+                    continue
+                if s.kind == RANK1:
+                    if name == "Vs":
+                        amp = sh.amp(name, i0, i1)
+                        if s.static:
+                            amp = np.broadcast_to(amp, (n, W))
+                        cum = vs_cum[None, :] + np.concatenate((np.zeros((1, W)), np.cumsum(amp * dt, axis=0)[:-1]), axis=0)
+                        vs_cum = vs_cum + np.sum(amp * dt, axis=0)
+                        eng.upload_source(which, i0, cum)
+                    elif not s.static:
+                        amp = sh.amp(name, i0, i1)
+                        eng.upload_source(which, i0, np.sqrt(amp) if name == "T" else amp)
+                elif not s.static:
+                    eng.upload_source(which, i0, _dense_for_device(name, sh.dense(name, i0, i1), tab))
+            if replay is not None and specs["T"].kind != ZERO:
+                if callable(replay):
+                    Z = np.stack([np.asarray(replay(i))[:, w0:w1] for i in range(i0, i1)])
+                else:
+                    Z = np.asarray(replay)[i0:i1, :, w0:w1]
+                eng.upload_noise(i0, Z)
+            tm, im = th_mask[i0:i1], I_mask[i0:i1]
+            n_th, n_I = int(tm.sum()), int(im.sum())
+            eng.alloc_outputs(n_th, n_I)
+            tp = np.where(tm, np.cumsum(tm) - 1, -1)
+            ip = np.where(im, np.cumsum(im) - 1, -1)
+            eng.run(i0, n, tp, ip)
+            total_ms += eng.stats()["step_ms"]
+            if n_th:
+                first = th_idx[i0:i1][tm][0]
+                th_host[2 + first: 2 + first + n_th, :, w0:w1] = eng.fetch_theta(0, n_th)
+            if n_I:
+                first = I_idx[i0:i1][im][0]
+                I_host[2 + first: 2 + first + n_I, :, w0:w1] = eng.fetch_current(0, n_I)
+        st = eng.stats()
+        st["total_ms"] = total_ms
+        st["problems"] = W
+        stats_out[dev] = st
+    finally:
+        eng.close()
+
+
+def _dense_for_device(name, table, tab):
+    """(K, N, W) host values -> what the device expects for a DENSE input."""
+    if name == "T":
+        return np.sqrt(2.0 * table * tab.Rv[None, :, None])     # noise amplitude sqrt(2 T Rv)
+    if name == "f":
+        return table[:, tab.perm, :]
+    return table
+
+
+def device_time_evolution_core(problem, th_store_mask, I_store_mask, engine=None):
+    """
+    Device replacement of time_evolution_core (reference: time_evolution.py:461-582), stencil width 3.
+    Returns th_out, I_out of shape (Nj, W, n_stored + 2).
+    """
+    if getattr(problem, "stencil_width", 3) != 3:
+        raise NotImplementedError("only stencil_width=3 is supported")
+    circuit = problem.get_circuit()
+    tab = _tables_for(circuit, problem._dt())
+    Nj, W = tab.Nj, problem.get_problem_count()
+    th_mask = np.asarray(th_store_mask, dtype=bool)
+    I_mask = np.asarray(I_store_mask, dtype=bool)
+    specs = _classify_all(problem, tab)
+    th_host = np.zeros((int(th_mask.sum()) + 2, Nj, W))
+    I_host = np.zeros((int(I_mask.sum()) + 2, Nj, W))
+    th_host[1] = problem.config_at_minus_1
+    th_host[0] = problem.config_at_minus_2
+    I_host[1] = problem._cp(problem.config_at_minus_1)
+    I_host[0] = problem._cp(problem.config_at_minus_2)
+    devices = getattr(problem, "devices", None)
+    if devices is None:
+        env = os.environ.get("JJ_DEVICES")
+        devices = [int(d) for d in env.split(",")] if env else [0]
+    if engine is None:
+        engine = {"auto": _lib.JJ_ENGINE_AUTO, "streaming": _lib.JJ_ENGINE_STREAMING,
+                  "resident": _lib.JJ_ENGINE_RESIDENT}[os.environ.get("JJ_ENGINE", "auto")]
+    bounds = shard_bounds(W, len(devices))
+    stats = {}
+    jobs = [(dev, bounds[k], bounds[k + 1]) for k, dev in enumerate(devices) if bounds[k + 1] > bounds[k]]
+    if len(jobs) == 1:
+        dev, w0, w1 = jobs[0]
+        _run_shard(problem, tab, specs, dev, w0, w1, th_mask, I_mask, th_host, I_host, engine, stats)
+    else:
+        errors = []
+
+        def work(dev, w0, w1):
+            try:
+                _run_shard(problem, tab, specs, dev, w0, w1, th_mask, I_mask, th_host, I_host, engine, stats)
+            except Exception as e:      # surfaced after join
+                errors.append(e)
+        threads = [threading.Thread(target=work, args=j) for j in jobs]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+    last_run_stats.clear()
+    last_run_stats.update(stats)
+    # (plane, Nj, W) -> (Nj, W, plane) views, the reference's layout (quirk Q7)
+    return np.moveaxis(th_host, 0, 2), np.moveaxis(I_host, 0, 2)
+
+
+def shard_bounds(W, n_shards):
+    """Contiguous shards of the problem axis whose starts are multiples of 4 (Philox groups)."""
+    groups = (W + 3) // 4
+    per = [(groups // n_shards + (1 if k < groups % n_shards else 0)) for k in range(n_shards)]
+    b = np.minimum(np.concatenate(([0], np.cumsum(per))) * 4, W)
+    return [int(v) for v in b]

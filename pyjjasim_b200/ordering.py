@@ -1,0 +1,117 @@
+"""
+Geometric nested-dissection ordering of the cycle-space system matrix.
+
+The per-step linear system  A (L + diag(1/(Cv+Rv))) A^T J = b  (reference: time_evolution.py:504-506)
+has one unknown per face of a planar circuit, so the faces' centroids give a natural geometric
+nested dissection: recursively cut the face set at the median of its longer extent, make the faces
+on one side that touch the other side the separator, and recurse into the two halves.
+
+The result is a block elimination tree: leaf blocks (small subdomains) and separator blocks. Blocks
+at the same tree height are mutually independent, which is what the device triangular solves
+exploit: the number of dependent phases is the tree height (~2 log2(sqrt(Nf)/leaf)), not the number
+of rows.  (The reference leaves ordering to SuperLU's COLAMD: 386-14186 dependent row levels.)
+
+Host setup code, runs once per circuit; vectorised over all subdomains of a tree depth.
+"""
+import numpy as np
+import scipy.sparse
+
+__all__ = ["nested_dissection"]
+
+
+def nested_dissection(S, cx, cy, leaf_size=24):
+    """
+    Parameters
+    ----------
+    S : (n, n) scipy sparse symmetric matrix (only its pattern is used)
+    cx, cy : (n,) coordinates of the unknowns
+    leaf_size : stop cutting when a subdomain has at most this many unknowns
+
+    Returns
+    -------
+    perm : (n,) new-to-old permutation (row i of the permuted system is unknown perm[i])
+    block_ptr : (nb + 1,) block b owns permuted rows block_ptr[b]:block_ptr[b+1]
+    block_height : (nb,) 0 for leaves; a separator is one higher than the tallest block below it
+    Blocks are numbered in post-order: every block comes after all blocks of its subtree.
+    """
+    n = S.shape[0]
+    cx = np.asarray(cx, dtype=np.double)
+    cy = np.asarray(cy, dtype=np.double)
+    Sc = scipy.sparse.coo_matrix(S)
+    off = Sc.row != Sc.col
+    ei, ej = Sc.row[off].astype(np.int64), Sc.col[off].astype(np.int64)
+    dom = np.zeros(n, dtype=np.int64)          # subdomain id (path in the cut tree) of each unknown
+    active = np.ones(n, dtype=bool)            # not yet placed in a block
+    blk_depth = np.zeros(n, dtype=np.int64)    # (depth, dom) of the block each unknown ends up in
+    depth, n_dom = 0, 1
+    while True:
+        idx = np.flatnonzero(active)
+        if idx.size == 0:
+            break
+        size = np.bincount(dom[idx], minlength=n_dom)
+        leaf_nodes = idx[size[dom[idx]] <= leaf_size]
+        blk_depth[leaf_nodes] = depth
+        active[leaf_nodes] = False
+        idx = np.flatnonzero(active)
+        if idx.size == 0:
+            break
+        if depth >= 60:
+            raise RuntimeError("nested dissection did not terminate")
+        d = dom[idx]
+        x, y = cx[idx], cy[idx]
+        lo_x = np.full(n_dom, np.inf); hi_x = np.full(n_dom, -np.inf)
+        lo_y = np.full(n_dom, np.inf); hi_y = np.full(n_dom, -np.inf)
+        np.minimum.at(lo_x, d, x); np.maximum.at(hi_x, d, x)
+        np.minimum.at(lo_y, d, y); np.maximum.at(hi_y, d, y)
+        cut_x = (hi_x - lo_x) >= (hi_y - lo_y)          # cut across the longer extent
+        coord = np.where(cut_x[d], x, y)
+        other = np.where(cut_x[d], y, x)
+        order = np.lexsort((other, coord, d))
+        sd = d[order]
+        start = np.searchsorted(sd, np.arange(n_dom))
+        rank = np.empty(idx.size, dtype=np.int64)
+        rank[order] = np.arange(idx.size) - start[sd]
+        half = np.zeros(n, dtype=np.int8)
+        half[idx] = rank >= (size[d] + 1) // 2
+        # separator: unknowns of the lower half coupled to the upper half of the same subdomain
+        both = active[ei] & active[ej]
+        e1, e2 = ei[both], ej[both]
+        cross = (dom[e1] == dom[e2]) & (half[e1] == 0) & (half[e2] == 1)
+        sep = np.unique(e1[cross])
+        blk_depth[sep] = depth
+        active[sep] = False
+        idx = np.flatnonzero(active)
+        dom[idx] = 2 * dom[idx] + half[idx]
+        n_dom *= 2
+        depth += 1
+
+    # A block is (depth, dom); its subtree covers cut-tree paths [dom << s, (dom << s) + 2^s - 1] with
+    # s = maxd - depth. Post-order = by subtree end ascending, deeper first on ties.
+    maxd = int(blk_depth.max()) if n else 0
+    shift = maxd - blk_depth
+    sub_hi = (dom << shift) + (np.int64(1) << shift) - 1
+    keys, inv = np.unique(np.stack((sub_hi, -blk_depth), axis=1), axis=0, return_inverse=True)
+    inv = inv.ravel()
+    nb = keys.shape[0]
+    # inside a block order geometrically along its longer extent (locality for row tiles)
+    lo_x = np.full(nb, np.inf); hi_x = np.full(nb, -np.inf)
+    lo_y = np.full(nb, np.inf); hi_y = np.full(nb, -np.inf)
+    np.minimum.at(lo_x, inv, cx); np.maximum.at(hi_x, inv, cx)
+    np.minimum.at(lo_y, inv, cy); np.maximum.at(hi_y, inv, cy)
+    along_x = (hi_x - lo_x) >= (hi_y - lo_y)
+    c1 = np.where(along_x[inv], cx, cy)
+    c2 = np.where(along_x[inv], cy, cx)
+    perm = np.lexsort((c2, c1, inv))
+    block_ptr = np.concatenate(([0], np.cumsum(np.bincount(inv, minlength=nb))))
+    b_depth = -keys[:, 1]
+    b_hi = keys[:, 0]
+    b_lo = b_hi - ((np.int64(1) << (maxd - b_depth)) - 1)
+    height = np.zeros(nb, dtype=np.int64)
+    stack = []
+    for b in range(nb):                         # post-order: the stack top holds finished subtrees
+        h = 0
+        while stack and b_lo[stack[-1]] >= b_lo[b] and b_hi[stack[-1]] <= b_hi[b]:
+            h = max(h, height[stack.pop()] + 1)
+        height[b] = h
+        stack.append(b)
+    return perm, block_ptr, height

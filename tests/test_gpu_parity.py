@@ -1,0 +1,118 @@
+"""GPU parity: the device path through the public API / C ABI against the golden vectors of the unmodified
+reference and against the CPU oracle, per stored step."""
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+import pyjjasim_b200 as pj
+from oracle import oracle
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+ENGINES = ["streaming", "auto"]
+
+
+def run_device(name, engine, **override):
+    kw, seed = cases.build(name, pj)
+    kw.update(override)
+    if seed is not None:
+        c = kw["circuit"]
+        prob0 = pj.TimeEvolutionProblem(**kw)
+        kw["noise_replay"] = cases.replay_noise(c._Nj(), prob0.get_problem_count(), prob0._Nt(), seed)
+    os.environ["JJ_ENGINE"] = engine
+    try:
+        prob = pj.TimeEvolutionProblem(**kw)
+        return kw, prob, prob.compute()
+    finally:
+        os.environ.pop("JJ_ENGINE", None)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_device_matches_reference_golden(name, engine, golden_dir):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    kw, prob, res = run_device(name, engine)
+    tol = cases.TOL[name]
+    for key in ("theta", "current", "voltage"):
+        got = getattr(res, key)
+        if key in g.files:
+            assert got is not None and got.shape == g[key].shape
+            scale = 1.0 if key == "theta" else 1.0 / kw.get("time_step", 0.05) if key == "voltage" else 1.0
+            err = np.max(np.abs(got - g[key]))
+            assert err <= tol * max(scale, 1.0) * 10, (key, err)
+        else:
+            assert got is None
+    th_err = np.max(np.abs(res.theta - g["theta"]))
+    assert th_err <= tol, th_err
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_vortex_configuration_and_invariants(engine):
+    kw, prob, res = run_device("sq_frustrated", engine)
+    c = kw["circuit"]
+    args, extra = cases.oracle_inputs(kw)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        th, I, V = oracle.time_evolution(*args, prob.get_problem_count(), **extra)
+    n_dev = res.get_vortex_configuration()
+    n_ora = oracle.vortex_configuration(c.get_cycle_matrix(), th)
+    assert np.array_equal(n_dev, n_ora)
+    Is = np.asarray(kw["current_sources"])[:, :, 0]
+    M, A = c.get_cut_matrix(), c.get_cycle_matrix()
+    for k in range(res.theta.shape[2]):
+        assert np.max(np.abs(M @ (res.current[:, :, k] - Is))) < 1e-11
+        assert np.max(np.abs(A @ res.theta[:, :, k] + 2 * np.pi * 0.1)) < 1e-10
+
+
+def test_device_solve_matches_direct_solve():
+    import scipy.sparse.linalg
+    from pyjjasim_b200 import engine
+    from pyjjasim_b200.factor import system_matrix
+    a = pj.SquareArray(30, 30)
+    a.set_inductance(0.1)
+    tab = engine.CircuitTables(a, 0.05)
+    eng = engine.DeviceEngine(0)
+    eng.set_circuit(tab, pj.DefaultCPR())
+    eng.set_problem(7, 0.05)
+    rng = np.random.RandomState(0)
+    b = rng.randn(a._Nf(), 7)
+    J = eng.debug_solve(b)
+    S = system_matrix(a.get_cycle_matrix(), a._L(), tab.Rv, tab.Cv)
+    Jref = scipy.sparse.linalg.spsolve(S.tocsc(), b)
+    eng.close()
+    assert np.max(np.abs(J - Jref)) <= 1e-12 * np.max(np.abs(Jref))
+
+
+def test_chunked_run_equals_single_run(monkeypatch):
+    # time-dependent tables uploaded chunk by chunk give the same result as one chunk
+    from pyjjasim_b200 import engine
+    kw, prob, res = run_device("sq_mixed", "streaming")
+    monkeypatch.setattr(engine, "_TABLE_BYTES", 5 * 8 * 7)      # 7 steps per chunk
+    kw2, prob2, res2 = run_device("sq_mixed", "streaming")
+    assert np.max(np.abs(res.theta - res2.theta)) <= 1e-13
+    assert np.max(np.abs(res.current - res2.current)) <= 1e-13
+
+
+def test_resume_from_final_state():
+    # manual resume contract of the reference: pass the last two thetas as config_at_minus_1/2
+    kw, seed = cases.build("sq_frustrated", pj)
+    kw["store_time_steps"] = None
+    kw["store_voltage"] = False
+    full = pj.TimeEvolutionProblem(**kw).compute().theta
+    kw1 = dict(kw, time_step_count=70)
+    th1 = pj.TimeEvolutionProblem(**kw1).compute().theta
+    kw2 = dict(kw, time_step_count=50, config_at_minus_1=th1[:, :, -1], config_at_minus_2=th1[:, :, -2])
+    th2 = pj.TimeEvolutionProblem(**kw2).compute().theta
+    assert np.max(np.abs(full[:, :, 70:] - th2)) <= 1e-12
+
+
+def test_missing_gpu_library_fails_loudly(monkeypatch):
+    from pyjjasim_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libjjstep.so")
+    kw, _ = cases.build("single_problem", pj)
+    with pytest.raises(RuntimeError):
+        pj.TimeEvolutionProblem(**kw).compute()
