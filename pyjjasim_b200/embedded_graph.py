@@ -112,9 +112,9 @@ class EmbeddedGraph:
         return self._n_components
 
     def is_planar_embedding(self):
-        # Euler: N - E + (all orbits of the successor map) == 2 * components  <=> no crossings
-        f = self._get_faces()
-        return self.node_count() - self.edge_count() + f["orbit_count"] == 2 * self.get_num_components()
+        # Euler's formula counting only positively oriented face cycles, as the reference does
+        # (reference: embedded_graph.py:404-409): crossing edges produce cycles of non-positive area.
+        return self.node_count() + self.face_count() == self.edge_count() + 1
 
     def _assert_single_component(self):
         if self.get_num_components() != 1:

@@ -1,0 +1,236 @@
+"""CPU tests of the host logic: circuit construction, ordering, solve program, input classification, API."""
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse
+import scipy.sparse.linalg
+
+import pyjjasim_b200 as pj
+from pyjjasim_b200 import sources
+from pyjjasim_b200.current_phase_relation import harmonics
+from pyjjasim_b200.engine import CircuitTables, shard_bounds
+from pyjjasim_b200.factor import apply_program_host, build_solve_program, system_matrix
+from pyjjasim_b200.ordering import nested_dissection
+from tests import cases
+from tests.golden.make_golden import matrix_digest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---------------------------------------------------------------- circuits (sizes table)
+@pytest.mark.parametrize("ctor,args,Nn,Nj,Nf", [
+    (pj.SquareArray, (20, 20), 400, 760, 361),
+    (pj.SquareArray, (100, 100), 10000, 19800, 9801),
+    (pj.HoneycombArray, (20, 20), 1600, 2340, 741),
+    (pj.TriangularArray, (5, 4), 40, 95, 56),
+])
+def test_lattice_sizes(ctor, args, Nn, Nj, Nf):
+    a = ctor(*args)
+    assert (a._Nn(), a._Nj(), a._Nf()) == (Nn, Nj, Nf)
+    A, M = a.get_cycle_matrix(), a.get_cut_matrix()
+    assert (A @ M.T).nnz == 0 or np.max(np.abs((A @ M.T).data)) == 0      # cycles are divergence free
+    assert np.all(np.abs(A.data) == 1)
+
+
+def test_cycle_matrices_match_reference_digests(golden_dir):
+    for name in cases.CASES:
+        kw, _ = cases.build(name, pj)
+        g = np.load(os.path.join(golden_dir, name + ".npz"))
+        assert matrix_digest(kw["circuit"].get_cycle_matrix()) == str(g["A_digest"])
+
+
+def test_square_array_conventions():
+    a = pj.SquareArray(4, 3)
+    n1, n2 = a.get_junction_nodes()
+    assert list(n1[:3]) == [0, 1, 2] and list(n2[:3]) == [1, 2, 3]        # horizontal junctions first, row-major
+    base = a.current_base(angle=0)
+    assert np.allclose(base[:9], 1.0) and np.allclose(base[9:], 0.0, atol=1e-12)
+    assert pj.HoneycombArray(3, 3).get_cycle_matrix().getnnz(axis=1).max() == 6
+    assert np.array_equal(np.diff(pj.SQUID().get_cycle_matrix().tocsr().indptr), [4])
+
+
+def test_graph_errors():
+    with pytest.raises(pj.SelfLoopError):
+        pj.EmbeddedGraph([0, 1], [0, 0], [0], [0])
+    with pytest.raises(pj.NonSimpleError):
+        pj.EmbeddedGraph([0, 1], [0, 0], [0, 1], [1, 0])
+    with pytest.raises(pj.NotSingleComponentError):
+        pj.EmbeddedGraph([0, 1, 2, 3], [0, 0, 1, 1], [0, 2], [1, 3], require_single_component=True)
+    with pytest.raises(pj.NotPlanarEmbeddingError):
+        pj.Circuit(pj.EmbeddedGraph([0, 1, 1, 0], [0, 1, 0, 1], [0, 2, 0, 1], [1, 3, 2, 3]))
+    with pytest.raises(ValueError):
+        pj.SquareArray(3, 3).set_resistance(0.0)
+    with pytest.raises(ValueError):
+        pj.SquareArray(3, 3).set_capacitance(-1.0)
+
+
+# ---------------------------------------------------------------- ordering and solve program
+@pytest.mark.parametrize("ctor,args,leaf", [(pj.SquareArray, (23, 17), 8), (pj.HoneycombArray, (9, 7), 6),
+                                            (pj.TriangularArray, (8, 6), 16), (pj.SquareArray, (40, 40), 4)])
+def test_solve_program_matches_direct_solve(ctor, args, leaf):
+    a = ctor(*args)
+    rng = np.random.RandomState(1)
+    a.set_resistance(0.5 + rng.rand(a._Nj()))
+    a.set_inductance(0.1 * rng.rand(a._Nj()))
+    dt = 0.05
+    S = system_matrix(a.get_cycle_matrix(), a._L(), 1 / (dt * a._R()), a._C() / dt ** 2)
+    cx, cy = a.get_face_centroids()
+    perm, bptr, height = nested_dissection(S, cx, cy, leaf_size=leaf)
+    assert sorted(perm) == list(range(a._Nf())) and bptr[-1] == a._Nf()
+    # blocks of equal height must not be coupled (they are processed concurrently)
+    Sp = scipy.sparse.coo_matrix(S.tocsr()[perm][:, perm])
+    blk = np.repeat(np.arange(len(bptr) - 1), np.diff(bptr))
+    cross = (blk[Sp.row] != blk[Sp.col]) & (height[blk[Sp.row]] == height[blk[Sp.col]])
+    assert not np.any(cross)
+    prog = build_solve_program(S, cx, cy, leaf_size=leaf)
+    b = rng.randn(a._Nf(), 3)
+    J = apply_program_host(prog, b)
+    Jref = scipy.sparse.linalg.spsolve(S.tocsc(), b)
+    assert np.max(np.abs(J - Jref)) <= 1e-12 * np.max(np.abs(Jref))
+    for sw in prog.sweeps.values():
+        assert np.all(sw["tile_nrows"] * sw["tile_lpr"] <= 32)
+        assert sw["group_ptr"][-1] == len(sw["tile_row0"])
+    assert prog.stats["levels_fwd"] == 2 * prog.stats["height"] + 1
+
+
+def test_circuit_tables_permutation_consistency():
+    a = pj.HoneycombArray(6, 5)
+    tab = CircuitTables(a, 0.05)
+    A = a.get_cycle_matrix().tocsr()
+    # CSR rows in permuted order reproduce A[perm]
+    rebuilt = scipy.sparse.csr_matrix((tab.face_sign.astype(float), tab.face_junc, tab.face_ptr), shape=A.shape)
+    assert abs(rebuilt - A[tab.perm]).nnz == 0
+    # junction -> faces table is the transpose
+    for j in range(a._Nj()):
+        for k in range(2):
+            f = tab.junc_face[j, k]
+            if f >= 0:
+                assert A[tab.perm[f], j] == tab.junc_sign[j, k]
+    assert np.sum(tab.junc_face >= 0) == A.nnz
+    assert np.sum(np.all(tab.junc_face < 0, axis=1)) == 2        # the honeycomb's two face-less corner junctions
+
+
+# ---------------------------------------------------------------- inputs
+def test_source_classification():
+    N, W, Nt = 12, 5, 9
+    rng = np.random.RandomState(0)
+    assert sources.classify_source(0.0, N, W, Nt).kind == sources.ZERO
+    assert sources.classify_source(1e-9, N, W, Nt).kind == sources.ZERO           # reference quirk Q5 (allclose)
+    s = sources.classify_source(0.3, N, W, Nt)
+    assert s.kind == sources.RANK1 and s.static and np.array_equal(s.value(4), np.full((N, W), 0.3))
+    amp = np.linspace(0, 2, W)
+    base = rng.randn(N)
+    x = base[:, None, None] * amp[None, :, None]
+    s = sources.classify_source(x, N, W, Nt)
+    assert s.kind == sources.RANK1 and s.static and np.allclose(s.value(0), x[:, :, 0], rtol=1e-15)
+    xt = rng.randn(1, W, Nt)
+    s = sources.classify_source(xt, N, W, Nt)
+    assert s.kind == sources.RANK1 and not s.static and np.array_equal(s.amp_chunk(2, 5), xt[0, :, 2:5].T)
+    xd = rng.randn(N, W, 1)
+    s = sources.classify_source(xd, N, W, Nt)
+    assert s.kind == sources.DENSE and s.static and np.array_equal(s.dense_chunk(0, 1)[0], xd[:, :, 0])
+    fn = lambda i: base[:, None] * (amp + np.sin(0.1 * i))
+    s = sources.classify_source(fn, N, W, Nt)
+    assert s.kind == sources.RANK1 and not s.static
+    assert np.allclose(s.base[:, None] * s.amp_chunk(3, 4)[0][None, :], fn(3), rtol=1e-15)
+    s = sources.classify_source(lambda i: rng.randn(N, W), N, W, Nt)
+    assert s.kind == sources.DENSE
+    r1 = pj.RankOneSource(base, lambda i: amp * i)
+    assert r1.problem_count == W and np.array_equal(r1(2), base[:, None] * (2 * amp)[None, :])
+    with pytest.raises(ValueError):
+        sources.classify_source(np.zeros((N, W)), N, W, Nt)                        # quirk Q6: 2-D input is misread
+
+
+def test_cpr_harmonics():
+    a, b = harmonics(pj.DefaultCPR())
+    assert list(a) == [0, 0] and list(b) == [0, 1]
+    cube = pj.CurrentPhaseRelation(lambda Ic, th: Ic * np.sin(th) ** 3, None, None)
+    a, b = harmonics(cube)
+    assert np.allclose(b[[1, 3]], [0.75, -0.25]) and np.allclose(a, 0) and len(b) == 4
+    with pytest.raises(ValueError):
+        harmonics(pj.CurrentPhaseRelation(lambda Ic, th: Ic * th, None, None))      # not periodic
+    with pytest.raises(ValueError):
+        harmonics(pj.CurrentPhaseRelation(lambda Ic, th: Ic ** 2 * np.sin(th), None, None))
+
+
+# ---------------------------------------------------------------- API mirror (reference: time_evolution.py:94-149, 384-408)
+def test_problem_constructor_semantics():
+    a = pj.SquareArray(4, 4)
+    Nj, Nf = a._Nj(), a._Nf()
+    p = pj.TimeEvolutionProblem(a, time_step_count=10, current_sources=np.ones((Nj, 3, 1)), temperature=np.ones((1, 3, 10)))
+    assert p.get_problem_count() == 3 and p._T_is_timedep and not p._Is_is_timedep
+    assert p.current_sources.shape == (Nj, 3, 10) and p.external_flux.shape == (Nf, 3, 10)
+    assert p.config_at_minus_1.shape == (Nj, 3) and np.all(p.config_at_minus_2 == 0)
+    assert pj.TimeEvolutionProblem(a, time_step_count=10, current_sources=lambda i: np.ones((Nj, 7))).get_problem_count() == 7
+    p = pj.TimeEvolutionProblem(a, time_step_count=10, store_time_steps=[2, 5])
+    assert p._Nt_s() == 2 and list(np.flatnonzero(p.store_time_steps)) == [2, 5]
+    mask = np.zeros(10, dtype=bool); mask[7] = True
+    assert pj.TimeEvolutionProblem(a, time_step_count=10, store_time_steps=mask)._Nt_s() == 1
+    with pytest.raises(ValueError, match="No output is stored"):
+        pj.TimeEvolutionProblem(a, store_theta=False, store_voltage=False, store_current=False)
+    with pytest.raises(ValueError, match="No output is stored"):
+        pj.TimeEvolutionProblem(a, time_step_count=10, store_time_steps=np.zeros(10, dtype=bool))
+    with pytest.raises(ValueError):
+        pj.TimeEvolutionProblem(a, time_step_count=10, store_time_steps=[11])
+    with pytest.raises(ValueError):
+        pj.TimeEvolutionProblem(a, stencil_width=6)
+    with pytest.raises(NotImplementedError):
+        pj.TimeEvolutionProblem(a, stencil_width=4)
+    assert np.array_equal(pj.TimeEvolutionProblem(a, time_step=0.1, time_step_count=3).get_time(), [0, 0.1, 0.2])
+
+
+def test_result_container_semantics():
+    a = pj.SquareArray(4, 4)
+    Nj = a._Nj()
+    p = pj.TimeEvolutionProblem(a, time_step_count=6, store_time_steps=[1, 4], store_voltage=False)
+    th = np.random.RandomState(0).randn(Nj, 1, 2)
+    r = pj.TimeEvolutionResult(p, th, th.copy(), None)
+    assert r.voltage is None and r.get_theta().shape == (Nj, 1, 2)
+    assert np.array_equal(r.get_theta([4])[:, :, 0], th[:, :, 1])
+    with pytest.raises(pj.VoltageNotStored):
+        r.get_voltage()
+    with pytest.raises(pj.DataAtTimepointNotStored):
+        r.get_theta([3])
+    with pytest.raises(ValueError):
+        pj.TimeEvolutionResult(p, th[:, :, :1], th, None)
+    n = r.get_vortex_configuration()
+    assert n.shape == (a._Nf(), 1, 2) and n.dtype.kind == "i"
+    assert r.get_phase().shape == (a._Nn(), 1, 2)
+
+
+def test_shard_bounds():
+    assert shard_bounds(256, 8) == [0, 32, 64, 96, 128, 160, 192, 224, 256]
+    assert shard_bounds(10, 4) == [0, 4, 8, 10, 10]
+    b = shard_bounds(4096 + 3, 8)
+    assert b[0] == 0 and b[-1] == 4099 and all(v % 4 == 0 for v in b[:-1]) and sorted(b) == b
+
+
+# ---------------------------------------------------------------- C ABI
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    from pyjjasim_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "jjstep.h")).read()
+    declared = set(re.findall(r"\b(jj_[a-z_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    # struct layouts of the ctypes mirror equal the C compiler's
+    import subprocess, tempfile
+    src = '#include <stdio.h>\n#include "jjstep.h"\nint main(){printf("%zu %zu %zu", sizeof(JJSweep), sizeof(JJCircuit), sizeof(JJStats));return 0;}'
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "s.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o", os.path.join(d, "s")])
+        sizes = [int(v) for v in subprocess.check_output([os.path.join(d, "s")]).split()]
+    assert sizes == [ctypes.sizeof(_lib.JJSweep), ctypes.sizeof(_lib.JJCircuit), ctypes.sizeof(_lib.JJStats)]
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    kw, _ = cases.build("single_problem", pj)
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        pj.TimeEvolutionProblem(**kw).compute()
