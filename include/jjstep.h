@@ -58,7 +58,28 @@ typedef struct {
     int64_t n_cols;  const int32_t *cols;
     int64_t n_vals;  const double  *vals;   /* [tile][step][32 lanes] */
     int32_t stage_rows;
+    const int32_t *tile_stage_off; /* staged tiles: first staging row (resident engine) */
 } JJSweep;
+
+/* Resident-engine plan (see pyjjasim_b200/factor.py: resident_plan). A cluster of C thread blocks owns a
+ * tile of `tile_problems` problems for the whole time loop; block r keeps the right-hand-side rows of
+ * elimination subtree r plus replicas of the separators above the cut in its shared memory. */
+typedef struct {
+    int32_t C, tile_problems;        /* cluster size (1,2,4,8); problems per tile (4 or 8) */
+    int32_t n_rows;                  /* rows of each block's shared-memory vector */
+    int32_t stage_rows, allreduce_rows;
+    int32_t n_ops, n_fwd_ops;
+    const int32_t *ops;              /* [n_ops][4]: (0, level, staged, 0) | (1, row_lo, row_hi, 0) */
+    const JJSweep *prog;             /* [C] tiles of rank r; level_ptr/group_ptr index its levels */
+    const int32_t *junc_ptr;         /* [C+1] rank r owns device junctions junc_ptr[r]:junc_ptr[r+1] */
+    const int32_t *junc_orig;        /* [Nj] original junction index of each device junction */
+    const int32_t *junc_row;         /* [Nj*2] shared-memory rows of its faces on the owner rank, -1 none */
+    const int8_t  *junc_sign;        /* [Nj*2] */
+    const int32_t *face_ptr;         /* [C*(n_rows+1)] CSR over shared-memory rows, into face_junc (global offsets) */
+    const int32_t *face_junc;        /* device junction index */
+    const int8_t  *face_sign;
+    const int32_t *face_fidx;        /* [C*n_rows] permuted face index if this rank adds the flux term, else -1 */
+} JJResidentPlan;
 
 /* Circuit constants, per junction, precomputed on the host in float64 exactly as the reference does
  * (reference: time_evolution.py:470-478): Rv = 1/(dt R), Cv = C/dt^2, c0 = Rv+Cv, c1 = -Rv-2Cv, c2 = Cv. */
@@ -82,6 +103,8 @@ const char *jj_last_error(const JJHandle *h);   /* h may be NULL: error of the l
 /* setup (reference: time_evolution.py:466-519) */
 int jj_set_circuit(JJHandle *h, const JJCircuit *c);
 int jj_set_solver(JJHandle *h, const JJSweep *fwd, const JJSweep *bwd);
+/* optional: enables JJ_ENGINE_RESIDENT. Must follow jj_set_circuit/jj_set_solver. plan == NULL removes it. */
+int jj_set_resident_plan(JJHandle *h, const JJResidentPlan *plan);
 /* W problems, time step dt, Philox seed, index of this shard's first problem in the global batch
  * (keeps noise identical however the batch is sharded over GPUs; must be a multiple of 4) */
 int jj_set_problem(JJHandle *h, int32_t W, double dt, uint64_t seed, int64_t problem_offset, int32_t engine);
@@ -110,6 +133,8 @@ int jj_fetch_current(JJHandle *h, int64_t plane0, int64_t n_planes, double *dst)
 int jj_debug_noise(JJHandle *h, int64_t step, double *dst);
 /* one solve J = S^-1 b through the compiled program, (Nf, W) host arrays in permuted face order */
 int jj_debug_solve(JJHandle *h, const double *b, double *J);
+/* the same through the resident engine's cluster kernel (requires a resident plan) */
+int jj_debug_resident_solve(JJHandle *h, const double *b, double *J);
 
 typedef struct {
     int32_t engine;             /* engine actually used */

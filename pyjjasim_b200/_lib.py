@@ -20,7 +20,8 @@ JJ_ENONFINITE = -5
 EXPORTS = ["jj_create", "jj_destroy", "jj_last_error", "jj_set_circuit", "jj_set_solver", "jj_set_problem",
            "jj_set_state", "jj_get_state", "jj_set_source", "jj_upload_source", "jj_upload_noise",
            "jj_alloc_outputs", "jj_run", "jj_fetch_theta", "jj_fetch_current", "jj_debug_noise",
-           "jj_debug_solve", "jj_stats"]
+           "jj_debug_solve", "jj_stats", "jj_set_resident_plan",
+           "jj_debug_resident_solve"]
 
 _p = C.c_void_p
 _i32p = C.POINTER(C.c_int32)
@@ -34,7 +35,15 @@ class JJSweep(C.Structure):
                 ("tile_row0", _i32p), ("tile_nrows", _i32p), ("tile_lpr", _i32p), ("tile_nsteps", _i32p),
                 ("tile_flags", _i32p), ("tile_col_off", _i64p), ("tile_val_off", _i64p),
                 ("n_cols", C.c_int64), ("cols", _i32p), ("n_vals", C.c_int64), ("vals", _f64p),
-                ("stage_rows", C.c_int32)]
+                ("stage_rows", C.c_int32), ("tile_stage_off", _i32p)]
+
+
+class JJResidentPlan(C.Structure):
+    _fields_ = [("C", C.c_int32), ("tile_problems", C.c_int32), ("n_rows", C.c_int32),
+                ("stage_rows", C.c_int32), ("allreduce_rows", C.c_int32), ("n_ops", C.c_int32),
+                ("n_fwd_ops", C.c_int32), ("ops", _i32p), ("prog", C.POINTER(JJSweep)),
+                ("junc_ptr", _i32p), ("junc_orig", _i32p), ("junc_row", _i32p), ("junc_sign", _i8p),
+                ("face_ptr", _i32p), ("face_junc", _i32p), ("face_sign", _i8p), ("face_fidx", _i32p)]
 
 
 class JJCircuit(C.Structure):
@@ -82,6 +91,8 @@ def load():
     lib.jj_debug_noise.argtypes = [_p, C.c_int64, _f64p]
     lib.jj_debug_solve.argtypes = [_p, _f64p, _f64p]
     lib.jj_stats.argtypes = [_p, C.POINTER(JJStats)]
+    lib.jj_set_resident_plan.argtypes = [_p, C.POINTER(JJResidentPlan)]
+    lib.jj_debug_resident_solve.argtypes = [_p, _f64p, _f64p]
     for name in EXPORTS:
         if name not in ("jj_destroy", "jj_last_error"):
             getattr(lib, name).restype = C.c_int

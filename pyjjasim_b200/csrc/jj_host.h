@@ -73,7 +73,8 @@ struct JJHandle {
     // outputs
     double *th_out = nullptr, *I_out = nullptr; long long n_th_planes = 0, n_I_planes = 0;
     int *flag_d = nullptr;
-    // resident engine (see jj_resident.cu)
+    // resident engine (see jj_resident.cu): plan-level and problem-level state
+    void *resident_plan = nullptr;
     void *resident = nullptr;
     // stats
     long long steps_done = 0, launches = 0, device_bytes = 0;
@@ -89,6 +90,10 @@ int resident_run(JJHandle* h, long long i0, int n, const long long* th_plane, co
 int resident_set_state(JJHandle* h, const double* t1, const double* t2);
 int resident_get_state(JJHandle* h, double* t1, double* t2);
 void resident_free(JJHandle* h);
+int resident_set_plan(JJHandle* h, const JJResidentPlan* plan);
+void resident_drop_plan(JJHandle* h);
+int resident_debug_solve(JJHandle* h, const double* b_d, double* J_d);
+void resident_get_config(JJHandle* h, int* C, int* WT);
 int dev_alloc(JJHandle* h, void** p, size_t bytes);
 void dev_free(JJHandle* h, void* p, size_t bytes);
 }

@@ -1,10 +1,648 @@
-// RESIDENT step engine (placeholder until the cluster kernel lands): reports "not applicable".
+// RESIDENT step engine for sm_100a: one persistent kernel integrates a whole run.
+//
+// A thread-block cluster of C blocks owns a tile of WT problems for all time steps of a jj_run call.
+// The elimination tree of the cycle-space system is cut at depth log2(C): block r keeps the
+// right-hand-side rows of subtree r, plus replicas of the separators above the cut, in its shared
+// memory (rows x WT float64, problem-minor). Per time step, with no global synchronisation at all:
+//
+//   junction pass   theta_n = (A^T J - x)/c0 from J in shared memory; x' = noise - Is + Ic cpr(..) + c1.. + c2..
+//                   (reference: time_evolution.py:533-558, 570-580); theta, x stream through HBM once
+//   face pass       b = A (x'/c0 - theta_s) - 2 pi f assembled into shared memory   (reference: :560-569)
+//   forward sweep   local levels of the compiled solve program (warp per tile, lanes split rows x column
+//                   groups, warp-shuffle reduction), then the replicated separators: partial sums per
+//                   block, all-reduce over distributed shared memory (reduce-scatter + broadcast)
+//   backward sweep  replicated separators redundantly, then local levels      (reference: :506, :562-569)
+//
+// Nothing but theta and x (and snapshots at stored steps) touches HBM: the right-hand side, the
+// intermediate z and the cycle currents J never leave shared memory.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+#include <cstring>
+
 #include "jj_host.h"
-namespace jj {
-int resident_supported(JJHandle*, std::string& why) { why = "not built yet"; return 0; }
-int resident_prepare(JJHandle* h) { h->err = "resident engine not built"; return JJ_EINVAL; }
-int resident_run(JJHandle* h, long long, int, const long long*, const long long*) { h->err = "resident engine not built"; return JJ_EINVAL; }
-int resident_set_state(JJHandle*, const double*, const double*) { return JJ_OK; }
-int resident_get_state(JJHandle* h, double*, double*) { h->err = "resident engine not built"; return JJ_EINVAL; }
-void resident_free(JJHandle*) {}
+
+namespace cg = cooperative_groups;
+using namespace jj;
+
+namespace {
+
+constexpr int NT = 512;           // threads per block
+constexpr int NWARPS = NT / 32;
+constexpr int MAXC = 8;
+
+struct TileHdr {                  // 32 bytes, read as two int4
+    int row0, nrows, lpr, nsteps;
+    int flags, stage_off;
+    unsigned col_off, val_off;
+};
+
+struct RankProg {
+    const TileHdr* tiles;
+    const int* lvl_ptr;           // [n_levels + 1] -> tiles
+    const int* cols;
+    const double* vals;
+};
+
+struct ResArgs {
+    // plan
+    int C, n_rows, stage_rows, ar_rows, n_ops;
+    const int4* ops;
+    RankProg prog[MAXC];
+    const int* junc_ptr; const int* junc_orig; const int2* junc_row; const char2* junc_sign;
+    const int* face_ptr; const int* face_junc; const signed char* face_sign; const int* face_fidx;
+    // circuit
+    int Nj, Nf;
+    const double *Ic, *ic0, *c1, *c2;
+    Cpr cpr;
+    // problem
+    int Wp, n_tiles;
+    double dt;
+    unsigned long long seed; long long group_offset;
+    Source Is, Vs, T, F;
+    const double* noise; long long noise_i0; int noise_K;
+    // state
+    double* rth; double* rx;       // [tile][Nj][WT]
+    double* th1; double* th2;      // canonical [Nj][Wp]: theta_{i0-1}, theta_{i0-2} in; theta_last, theta_{last-1} out
+    // run
+    long long i0; int n;
+    const long long* th_plane; const long long* I_plane;
+    double* snap_th; double* snap_I;   // canonical planes [plane][Nj][Wp]
+    int* flag;
+    // debug solve
+    const double* dbg_b; double* dbg_J;   // canonical [Nf][Wp], permuted faces
+};
+
+struct ResidentState {
+    JJResidentPlan plan{};           // scalars only are meaningful
+    int C = 1, WT = 8, n_rows = 0, stage_rows = 0, ar_rows = 0, n_ops = 0;
+    int4* ops = nullptr;
+    RankProg prog[MAXC]{};
+    std::vector<void*> allocs;
+    std::vector<size_t> alloc_bytes;
+    int *junc_ptr = nullptr, *junc_orig = nullptr; int2* junc_row = nullptr; char2* junc_sign = nullptr;
+    int *face_ptr = nullptr, *face_junc = nullptr; signed char* face_sign = nullptr; int* face_fidx = nullptr;
+    double* ic0 = nullptr;
+    // per problem
+    double *rth = nullptr, *rx = nullptr; size_t state_bytes = 0;
+    long long *plane_d = nullptr; size_t plane_cap = 0;
+    int n_tiles = 0;
+    size_t smem_bytes = 0;
+    int max_clusters = 0;
+    bool prepared = false;
+};
+
+// ------------------------------------------------------------------------------------------------
+template <int WT>
+__device__ __forceinline__ void run_tile(const TileHdr& t, const RankProg& p, double* __restrict__ v,
+                                         double* __restrict__ stage, int lane) {
+    const int m = t.lpr;
+    const int mshift = 31 - __clz(m);
+    const int i = lane >> mshift, s = lane & (m - 1);
+    double acc[WT];
+#pragma unroll
+    for (int q = 0; q < WT; ++q) acc[q] = 0.0;
+    const double* vp = p.vals + t.val_off + lane;
+    const int* cp = p.cols + t.col_off + s;
+#pragma unroll 4
+    for (int st = 0; st < t.nsteps; ++st) {
+        double a = __ldg(vp + (size_t)st * 32);
+        int c = __ldg(cp + st * m);
+        const double2* src = reinterpret_cast<const double2*>(v + (size_t)c * WT);
+#pragma unroll
+        for (int q = 0; q < WT / 2; ++q) {
+            double2 sv = src[q];
+            acc[2 * q] = fma(a, sv.x, acc[2 * q]);
+            acc[2 * q + 1] = fma(a, sv.y, acc[2 * q + 1]);
+        }
+    }
+    for (int off = m >> 1; off > 0; off >>= 1) {
+#pragma unroll
+        for (int q = 0; q < WT; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], off);
+    }
+    __syncwarp();
+    if (s == 0 && i < t.nrows) {
+        double2* self = reinterpret_cast<double2*>(v + (size_t)(t.row0 + i) * WT);
+        if (t.flags & 1) {
+#pragma unroll
+            for (int q = 0; q < WT / 2; ++q) {
+                double2 sv = self[q];
+                acc[2 * q] += sv.x; acc[2 * q + 1] += sv.y;
+            }
+        }
+        double2* dst = (t.flags & 2) ? reinterpret_cast<double2*>(stage + (size_t)(t.stage_off + i) * WT) : self;
+#pragma unroll
+        for (int q = 0; q < WT / 2; ++q) dst[q] = make_double2(acc[2 * q], acc[2 * q + 1]);
+    }
 }
+
+__device__ __forceinline__ TileHdr load_hdr(const TileHdr* p) {
+    const int4* q = reinterpret_cast<const int4*>(p);
+    int4 a = __ldg(q), b = __ldg(q + 1);
+    TileHdr t;
+    t.row0 = a.x; t.nrows = a.y; t.lpr = a.z; t.nsteps = a.w;
+    t.flags = b.x; t.stage_off = b.y; t.col_off = (unsigned)b.z; t.val_off = (unsigned)b.w;
+    return t;
+}
+
+template <int WT>
+__device__ void exec_level(const RankProg& p, int level, int staged, double* v, double* stage) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t0 = __ldg(p.lvl_ptr + level), t1 = __ldg(p.lvl_ptr + level + 1);
+    for (int t = t0 + warp; t < t1; t += NWARPS) {
+        TileHdr h = load_hdr(p.tiles + t);
+        run_tile<WT>(h, p, v, stage, lane);
+    }
+    __syncthreads();
+    if (staged) {
+        for (int t = t0 + warp; t < t1; t += NWARPS) {
+            TileHdr h = load_hdr(p.tiles + t);
+            if (h.flags & 2) {
+                for (int e = lane; e < h.nrows * WT; e += 32)
+                    v[(size_t)h.row0 * WT + e] = stage[(size_t)h.stage_off * WT + e];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// all-reduce of rows [lo, hi) of every block's vector: reduce-scatter into mailboxes, sum in rank order,
+// broadcast the sums back into every replica. Deterministic: the same block adds the partials in the same order.
+template <int WT>
+__device__ void allreduce_rows(cg::cluster_group& cluster, int C, int rank, int lo, int hi, double* v, double* mbox) {
+    const int n = hi - lo;
+    const int ch = (n + C - 1) / C;
+    for (int q = 0; q < C; ++q) {
+        const int r0 = q * ch, r1 = min(n, r0 + ch);
+        if (r1 <= r0) continue;
+        double* dst = cluster.map_shared_rank(mbox, q) + (size_t)rank * ch * WT;
+        const double* src = v + (size_t)(lo + r0) * WT;
+        for (int e = threadIdx.x; e < (r1 - r0) * WT; e += NT) dst[e] = src[e];
+    }
+    cluster.sync();
+    {
+        const int r0 = rank * ch, r1 = min(n, r0 + ch);
+        const int cnt = max(0, r1 - r0) * WT;
+        for (int e = threadIdx.x; e < cnt; e += NT) {
+            double sum = 0.0;
+            for (int r = 0; r < C; ++r) sum += mbox[(size_t)r * ch * WT + e];
+            for (int q = 0; q < C; ++q) cluster.map_shared_rank(v, q)[(size_t)(lo + r0) * WT + e] = sum;
+        }
+    }
+    cluster.sync();
+}
+
+template <int WT, bool CL>
+__device__ void run_ops(const ResArgs& a, cg::cluster_group& cluster, int rank, double* v, double* stage, double* mbox) {
+    const RankProg& p = a.prog[rank];
+    for (int o = 0; o < a.n_ops; ++o) {
+        int4 op = __ldg(a.ops + o);
+        if (op.x == 0) exec_level<WT>(p, op.y, op.z, v, stage);
+        else if (CL) allreduce_rows<WT>(cluster, a.C, rank, op.y, op.z, v, mbox);
+    }
+}
+
+__device__ __forceinline__ void amp4(const Source& s, long long step, int Wp, int w, double out[4]) {
+    const double2* t = reinterpret_cast<const double2*>(s.table + source_row(s, step) * Wp + w);
+    double2 a0 = __ldg(t), a1 = __ldg(t + 1);
+    out[0] = a0.x; out[1] = a0.y; out[2] = a1.x; out[3] = a1.y;
+}
+
+template <int WT, bool DEF>
+__device__ void junction_pass(const ResArgs& a, int rank, int tile, long long n, bool do_post, bool do_pre,
+                              const double* __restrict__ v) {
+    constexpr int G = WT / 4;
+    const int jlo = a.junc_ptr[rank], jhi = a.junc_ptr[rank + 1];
+    const int total = (jhi - jlo) * G;
+    double* snap_th = nullptr; double* snap_I = nullptr;
+    if (do_post) {
+        long long k = n - 1 - a.i0;
+        long long pt = a.th_plane ? a.th_plane[k] : -1, pi = a.I_plane ? a.I_plane[k] : -1;
+        if (pt >= 0) snap_th = a.snap_th + (size_t)pt * a.Nj * a.Wp;
+        if (pi >= 0) snap_I = a.snap_I + (size_t)pi * a.Nj * a.Wp;
+    }
+    for (int idx = threadIdx.x; idx < total; idx += NT) {
+        const int jp = jlo + idx / G;
+        const int q = (idx % G) * 4;
+        const int w = tile * WT + q;
+        if (w >= a.Wp) continue;
+        const int jo = __ldg(a.junc_orig + jp);
+        const size_t sidx = ((size_t)tile * a.Nj + jp) * WT + q;
+        const size_t cidx = (size_t)jo * a.Wp + w;
+        double th1[4], th2[4];
+        if (do_post) {
+            double y[4] = {0, 0, 0, 0};
+            int2 rows = __ldg(a.junc_row + jp);
+            char2 sg = a.junc_sign[jp];
+            if (rows.x >= 0) {
+                const double2* Jp = reinterpret_cast<const double2*>(v + (size_t)rows.x * WT + q);
+                double2 j0 = Jp[0], j1 = Jp[1];
+                double s = (double)sg.x;
+                y[0] += s * j0.x; y[1] += s * j0.y; y[2] += s * j1.x; y[3] += s * j1.y;
+            }
+            if (rows.y >= 0) {
+                const double2* Jp = reinterpret_cast<const double2*>(v + (size_t)rows.y * WT + q);
+                double2 j0 = Jp[0], j1 = Jp[1];
+                double s = (double)sg.y;
+                y[0] += s * j0.x; y[1] += s * j0.y; y[2] += s * j1.x; y[3] += s * j1.y;
+            }
+            const double2* xp = reinterpret_cast<const double2*>(a.rx + sidx);
+            double2 x0 = xp[0], x1 = xp[1];
+            const double2* tp = reinterpret_cast<const double2*>(a.rth + sidx);
+            double2 t0 = tp[0], t1 = tp[1];
+            th2[0] = t0.x; th2[1] = t0.y; th2[2] = t1.x; th2[3] = t1.y;
+            const double ic0 = __ldg(a.ic0 + jo);
+            th1[0] = (y[0] - x0.x) * ic0; th1[1] = (y[1] - x0.y) * ic0;
+            th1[2] = (y[2] - x1.x) * ic0; th1[3] = (y[3] - x1.y) * ic0;
+            if (!(isfinite(th1[0]) && isfinite(th1[1]) && isfinite(th1[2]) && isfinite(th1[3]))) atomicOr(a.flag, 1);
+            if (snap_th) {
+                double2* sp = reinterpret_cast<double2*>(snap_th + cidx);
+                sp[0] = make_double2(th1[0], th1[1]); sp[1] = make_double2(th1[2], th1[3]);
+            }
+            if (snap_I) {
+                double is[4] = {0, 0, 0, 0};
+                if (a.Is.kind == KIND_RANK1) {
+                    double am[4]; amp4(a.Is, n - 1, a.Wp, w, am);
+                    double b = __ldg(a.Is.base + jo);
+                    for (int k = 0; k < 4; ++k) is[k] = b * am[k];
+                }
+                double2* sp = reinterpret_cast<double2*>(snap_I + cidx);
+                sp[0] = make_double2(y[0] + is[0], y[1] + is[1]); sp[1] = make_double2(y[2] + is[2], y[3] + is[3]);
+            }
+            if (do_pre) {
+                double2* op = reinterpret_cast<double2*>(a.rth + sidx);
+                op[0] = make_double2(th1[0], th1[1]); op[1] = make_double2(th1[2], th1[3]);
+            } else {
+                // end of the run: hand theta_last and theta_{last-1} back in the canonical layout
+                double2* o1 = reinterpret_cast<double2*>(a.th1 + cidx);
+                double2* o2 = reinterpret_cast<double2*>(a.th2 + cidx);
+                o1[0] = make_double2(th1[0], th1[1]); o1[1] = make_double2(th1[2], th1[3]);
+                o2[0] = make_double2(th2[0], th2[1]); o2[1] = make_double2(th2[2], th2[3]);
+            }
+        } else {
+            const double2* p1 = reinterpret_cast<const double2*>(a.th1 + cidx);
+            const double2* p2 = reinterpret_cast<const double2*>(a.th2 + cidx);
+            double2 u0 = p1[0], u1 = p1[1], v0 = p2[0], v1 = p2[1];
+            th1[0] = u0.x; th1[1] = u0.y; th1[2] = u1.x; th1[3] = u1.y;
+            th2[0] = v0.x; th2[1] = v0.y; th2[2] = v1.x; th2[3] = v1.y;
+            double2* op = reinterpret_cast<double2*>(a.rth + sidx);
+            op[0] = u0; op[1] = u1;
+        }
+        if (!do_pre) continue;
+        const double Ic = __ldg(a.Ic + jo), c1 = __ldg(a.c1 + jo), c2 = __ldg(a.c2 + jo);
+        double fl[4] = {0, 0, 0, 0};
+        if (a.T.kind != KIND_ZERO) {
+            double z[4], am[4];
+            if (a.noise_K > 0) {
+                const double2* zp = reinterpret_cast<const double2*>(a.noise + ((size_t)(n - a.noise_i0) * a.Nj + jo) * a.Wp + w);
+                double2 z0 = zp[0], z1 = zp[1];
+                z[0] = z0.x; z[1] = z0.y; z[2] = z1.x; z[3] = z1.y;
+            } else {
+                normal4(a.seed, jo, a.group_offset + (w >> 2), n, z);
+            }
+            amp4(a.T, n, a.Wp, w, am);
+            const double b = __ldg(a.T.base + jo);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) fl[k] = (b * am[k]) * z[k];
+        }
+        double is[4] = {0, 0, 0, 0};
+        if (a.Is.kind == KIND_RANK1) {
+            double am[4]; amp4(a.Is, n, a.Wp, w, am);
+            const double b = __ldg(a.Is.base + jo);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) is[k] = b * am[k];
+        }
+        double xn[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double X = Ic * cpr_eval<DEF>(a.cpr, 2.0 * th1[k] - th2[k]) + c1 * th1[k] + c2 * th2[k];
+            xn[k] = (fl[k] - is[k]) + X;
+        }
+        double2* xo = reinterpret_cast<double2*>(a.rx + sidx);
+        xo[0] = make_double2(xn[0], xn[1]); xo[1] = make_double2(xn[2], xn[3]);
+    }
+}
+
+template <int WT>
+__device__ void face_pass(const ResArgs& a, int rank, int tile, long long n, double* __restrict__ v) {
+    constexpr int G = WT / 4;
+    const int* fptr = a.face_ptr + (size_t)rank * (a.n_rows + 1);
+    const int* fidx = a.face_fidx + (size_t)rank * a.n_rows;
+    const int total = a.n_rows * G;
+    for (int idx = threadIdx.x; idx < total; idx += NT) {
+        const int row = idx / G;
+        const int q = (idx % G) * 4;
+        const int w = tile * WT + q;
+        double acc[4] = {0, 0, 0, 0};
+        if (w < a.Wp) {
+            double cum[4] = {0, 0, 0, 0};
+            if (a.Vs.kind == KIND_RANK1) amp4(a.Vs, n, a.Wp, w, cum);
+            const int p0 = __ldg(fptr + row), p1 = __ldg(fptr + row + 1);
+            for (int p = p0; p < p1; ++p) {
+                const int jp = __ldg(a.face_junc + p);
+                const double s = (double)a.face_sign[p];
+                const int jo = __ldg(a.junc_orig + jp);
+                const double ic0 = __ldg(a.ic0 + jo);
+                const double2* xp = reinterpret_cast<const double2*>(a.rx + ((size_t)tile * a.Nj + jp) * WT + q);
+                double2 x0 = __ldcg(xp), x1 = __ldcg(xp + 1);
+                double u[4] = {x0.x * ic0, x0.y * ic0, x1.x * ic0, x1.y * ic0};
+                if (a.Vs.kind == KIND_RANK1) {
+                    const double b = __ldg(a.Vs.base + jo);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) u[k] -= b * cum[k];
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc[k] += s * u[k];
+            }
+            const int g = __ldg(fidx + row);
+            if (g >= 0 && a.F.kind == KIND_RANK1) {
+                double am[4]; amp4(a.F, n, a.Wp, w, am);
+                const double b = __ldg(a.F.base + g);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc[k] -= 6.283185307179586 * (b * am[k]);
+            }
+        }
+        double2* vp = reinterpret_cast<double2*>(v + (size_t)row * WT + q);
+        vp[0] = make_double2(acc[0], acc[1]); vp[1] = make_double2(acc[2], acc[3]);
+    }
+}
+
+template <int WT, bool DEF, bool CL>
+__global__ void __launch_bounds__(NT, 1) k_resident(const ResArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    double* v = smem;
+    double* stage = v + (size_t)a.n_rows * WT;
+    double* mbox = stage + (size_t)a.stage_rows * WT;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = CL ? (int)cluster.block_rank() : 0;
+    const int cluster_id = blockIdx.x / a.C;
+    const int n_clusters = gridDim.x / a.C;
+    for (int tile = cluster_id; tile < a.n_tiles; tile += n_clusters) {
+        if (a.dbg_b) {
+            // debug: one solve of the compiled program on this tile's columns
+            constexpr int G = WT / 4;
+            const int* fidx = a.face_fidx + (size_t)rank * a.n_rows;
+            for (int idx = threadIdx.x; idx < a.n_rows * G; idx += NT) {
+                int row = idx / G, q = (idx % G) * 4, w = tile * WT + q, g = fidx[row];
+                for (int k = 0; k < 4; ++k)
+                    v[(size_t)row * WT + q + k] = (g >= 0 && w < a.Wp) ? a.dbg_b[(size_t)g * a.Wp + w + k] : 0.0;
+            }
+            __syncthreads();
+            run_ops<WT, CL>(a, cluster, rank, v, stage, mbox);
+            for (int idx = threadIdx.x; idx < a.n_rows * G; idx += NT) {
+                int row = idx / G, q = (idx % G) * 4, w = tile * WT + q, g = fidx[row];
+                if (g >= 0 && w < a.Wp)
+                    for (int k = 0; k < 4; ++k) a.dbg_J[(size_t)g * a.Wp + w + k] = v[(size_t)row * WT + q + k];
+            }
+            __syncthreads();
+            continue;
+        }
+        for (long long k = 0; k <= a.n; ++k) {
+            const long long n = a.i0 + k;
+            junction_pass<WT, DEF>(a, rank, tile, n, k > 0, k < a.n, v);
+            if (k == a.n) break;
+            __syncthreads();
+            face_pass<WT>(a, rank, tile, n, v);
+            __syncthreads();
+            run_ops<WT, CL>(a, cluster, rank, v, stage, mbox);
+        }
+        __syncthreads();
+    }
+    if (CL) cluster.sync();      // keep shared memory alive until every peer is done with it
+}
+
+typedef void (*KernelPtr)(const ResArgs);
+
+KernelPtr pick_kernel(int WT, bool def, bool cl) {
+    if (WT == 8) {
+        if (def) return cl ? k_resident<8, true, true> : k_resident<8, true, false>;
+        return cl ? k_resident<8, false, true> : k_resident<8, false, false>;
+    }
+    if (def) return cl ? k_resident<4, true, true> : k_resident<4, true, false>;
+    return cl ? k_resident<4, false, true> : k_resident<4, false, false>;
+}
+
+__global__ void k_recip(int n, const double* c0, double* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = 1.0 / c0[i];
+}
+
+#define RCK(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            h->err = std::string("resident: ") + #call + ": " + cudaGetErrorString(e_);             \
+            return JJ_ECUDA;                                                                        \
+        }                                                                                           \
+    } while (0)
+
+template <typename T>
+int up(JJHandle* h, ResidentState* st, T** dst, const T* src, size_t n) {
+    void* p = nullptr;
+    size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    int rc = dev_alloc(h, &p, bytes);
+    if (rc) return rc;
+    st->allocs.push_back(p); st->alloc_bytes.push_back(bytes);
+    if (n) {
+        cudaError_t e = cudaMemcpyAsync(p, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream);
+        if (e != cudaSuccess) { h->err = std::string("resident upload: ") + cudaGetErrorString(e); return JJ_ECUDA; }
+    }
+    *dst = (T*)p;
+    return JJ_OK;
+}
+
+}  // namespace
+
+namespace jj {
+
+void resident_free_problem(JJHandle* h) {
+    ResidentState* st = (ResidentState*)h->resident_plan;
+    if (!st) return;
+    dev_free(h, st->rth, st->state_bytes); dev_free(h, st->rx, st->state_bytes);
+    dev_free(h, st->plane_d, st->plane_cap);
+    st->rth = st->rx = nullptr; st->plane_d = nullptr; st->plane_cap = 0; st->state_bytes = 0;
+    st->prepared = false;
+}
+
+void resident_free(JJHandle* h) { resident_free_problem(h); h->resident = nullptr; }
+
+void resident_drop_plan(JJHandle* h) {
+    ResidentState* st = (ResidentState*)h->resident_plan;
+    if (!st) return;
+    resident_free_problem(h);
+    for (size_t i = 0; i < st->allocs.size(); ++i) dev_free(h, st->allocs[i], st->alloc_bytes[i]);
+    delete st;
+    h->resident_plan = nullptr;
+    h->resident = nullptr;
+}
+
+int resident_set_plan(JJHandle* h, const JJResidentPlan* pl) {
+    resident_drop_plan(h);
+    if (!pl) return JJ_OK;
+    if (!(pl->C == 1 || pl->C == 2 || pl->C == 4 || pl->C == 8) || !(pl->tile_problems == 4 || pl->tile_problems == 8)) {
+        h->err = "resident plan: cluster size must be 1/2/4/8 and tile_problems 4 or 8";
+        return JJ_EINVAL;
+    }
+    ResidentState* st = new ResidentState();
+    h->resident_plan = st;
+    st->C = pl->C; st->WT = pl->tile_problems; st->n_rows = pl->n_rows; st->stage_rows = pl->stage_rows;
+    st->ar_rows = pl->allreduce_rows; st->n_ops = pl->n_ops;
+    const int Nj = h->cir.Nj;
+    int rc;
+    if ((rc = up(h, st, (int**)&st->ops, pl->ops, (size_t)pl->n_ops * 4))) return rc;
+    for (int r = 0; r < pl->C; ++r) {
+        const JJSweep& s = pl->prog[r];
+        std::vector<TileHdr> hdr(s.n_tiles);
+        for (int t = 0; t < s.n_tiles; ++t) {
+            hdr[t].row0 = s.tile_row0[t]; hdr[t].nrows = s.tile_nrows[t]; hdr[t].lpr = s.tile_lpr[t];
+            hdr[t].nsteps = s.tile_nsteps[t]; hdr[t].flags = s.tile_flags[t];
+            hdr[t].stage_off = s.tile_stage_off ? s.tile_stage_off[t] : 0;
+            if (s.tile_col_off[t] > 0xffffffffLL || s.tile_val_off[t] > 0xffffffffLL) {
+                h->err = "resident plan: program too large"; return JJ_EINVAL;
+            }
+            hdr[t].col_off = (unsigned)s.tile_col_off[t]; hdr[t].val_off = (unsigned)s.tile_val_off[t];
+        }
+        std::vector<int> lvl(s.n_levels + 1);
+        for (int l = 0; l <= s.n_levels; ++l) lvl[l] = s.group_ptr[s.level_ptr[l]];
+        TileHdr* hd; int* lp; int* cp; double* vp;
+        if ((rc = up(h, st, &hd, hdr.data(), hdr.size()))) return rc;
+        if ((rc = up(h, st, &lp, lvl.data(), lvl.size()))) return rc;
+        if ((rc = up(h, st, &cp, s.cols, (size_t)s.n_cols))) return rc;
+        if ((rc = up(h, st, &vp, s.vals, (size_t)s.n_vals))) return rc;
+        st->prog[r].tiles = hd; st->prog[r].lvl_ptr = lp; st->prog[r].cols = cp; st->prog[r].vals = vp;
+    }
+    if ((rc = up(h, st, &st->junc_ptr, pl->junc_ptr, (size_t)pl->C + 1))) return rc;
+    if ((rc = up(h, st, &st->junc_orig, pl->junc_orig, (size_t)Nj))) return rc;
+    if ((rc = up(h, st, (int**)&st->junc_row, pl->junc_row, (size_t)Nj * 2))) return rc;
+    if ((rc = up(h, st, (signed char**)&st->junc_sign, (const signed char*)pl->junc_sign, (size_t)Nj * 2))) return rc;
+    size_t nfp = (size_t)pl->C * (pl->n_rows + 1);
+    if ((rc = up(h, st, &st->face_ptr, pl->face_ptr, nfp))) return rc;
+    int nent = 0;
+    for (size_t i = 0; i < nfp; ++i) nent = std::max(nent, pl->face_ptr[i]);
+    if ((rc = up(h, st, &st->face_junc, pl->face_junc, (size_t)nent))) return rc;
+    if ((rc = up(h, st, &st->face_sign, (const signed char*)pl->face_sign, (size_t)nent))) return rc;
+    if ((rc = up(h, st, &st->face_fidx, pl->face_fidx, (size_t)pl->C * pl->n_rows))) return rc;
+    void* p = nullptr;
+    if ((rc = dev_alloc(h, &p, (size_t)Nj * sizeof(double)))) return rc;
+    st->allocs.push_back(p); st->alloc_bytes.push_back((size_t)Nj * sizeof(double));
+    st->ic0 = (double*)p;
+    k_recip<<<(Nj + 255) / 256, 256, 0, h->stream>>>(Nj, h->cir.c0, st->ic0);
+    h->launches++;
+    RCK(cudaStreamSynchronize(h->stream));
+    st->smem_bytes = ((size_t)st->n_rows + st->stage_rows + st->ar_rows + st->C) * st->WT * sizeof(double);
+    return JJ_OK;
+}
+
+int resident_supported(JJHandle* h, std::string& why) {
+    ResidentState* st = (ResidentState*)h->resident_plan;
+    if (!st) { why = "no resident plan was provided (problem too large for shared memory?)"; return 0; }
+    for (int i = 0; i < 4; ++i)
+        if (h->src[i].dev.kind == KIND_DENSE) { why = "a per-step input is dense (not base x amplitude)"; return 0; }
+    if (h->cir.Nf == 0) { why = "circuit has no faces"; return 0; }
+    return 1;
+}
+
+static int fill_args(JJHandle* h, ResidentState* st, ResArgs& a) {
+    memset(&a, 0, sizeof(a));
+    a.C = st->C; a.n_rows = st->n_rows; a.stage_rows = st->stage_rows; a.ar_rows = st->ar_rows; a.n_ops = st->n_ops;
+    a.ops = st->ops;
+    for (int r = 0; r < st->C; ++r) a.prog[r] = st->prog[r];
+    a.junc_ptr = st->junc_ptr; a.junc_orig = st->junc_orig; a.junc_row = st->junc_row; a.junc_sign = st->junc_sign;
+    a.face_ptr = st->face_ptr; a.face_junc = st->face_junc; a.face_sign = st->face_sign; a.face_fidx = st->face_fidx;
+    a.Nj = h->cir.Nj; a.Nf = h->cir.Nf; a.Ic = h->cir.Ic; a.ic0 = st->ic0; a.c1 = h->cir.c1; a.c2 = h->cir.c2;
+    a.cpr = h->cir.cpr;
+    a.Wp = h->Wp; a.n_tiles = st->n_tiles; a.dt = h->dt; a.seed = h->seed; a.group_offset = h->problem_offset / 4;
+    a.Is = h->src[JJ_SRC_IS].dev; a.Vs = h->src[JJ_SRC_VS].dev; a.T = h->src[JJ_SRC_T].dev; a.F = h->src[JJ_SRC_F].dev;
+    a.noise = h->noise_buf; a.noise_i0 = h->noise_i0; a.noise_K = h->noise_K;
+    a.rth = st->rth; a.rx = st->rx; a.th1 = h->th1; a.th2 = h->th2;
+    a.snap_th = h->th_out; a.snap_I = h->I_out; a.flag = h->flag_d;
+    return JJ_OK;
+}
+
+static int launch(JJHandle* h, ResidentState* st, const ResArgs& a) {
+    KernelPtr k = pick_kernel(st->WT, h->cir.default_cpr, st->C > 1);
+    RCK(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem_bytes));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.blockDim = dim3(NT, 1, 1);
+    cfg.dynamicSmemBytes = st->smem_bytes;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = st->C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (st->max_clusters == 0) {
+        cfg.gridDim = dim3(st->C, 1, 1);
+        int nc = 0;
+        RCK(cudaOccupancyMaxActiveClusters(&nc, (const void*)k, &cfg));
+        if (nc <= 0) { h->err = "resident: kernel does not fit on the device (shared memory / cluster size)"; return JJ_EINVAL; }
+        st->max_clusters = nc;
+    }
+    int ncl = std::min(st->n_tiles, st->max_clusters);
+    cfg.gridDim = dim3(ncl * st->C, 1, 1);
+    RCK(cudaLaunchKernelEx(&cfg, k, a));
+    h->launches++;
+    return JJ_OK;
+}
+
+int resident_prepare(JJHandle* h) {
+    ResidentState* st = (ResidentState*)h->resident_plan;
+    if (!st) { h->err = "resident engine: no plan"; return JJ_ESTATE; }
+    resident_free_problem(h);
+    st->n_tiles = (h->Wp + st->WT - 1) / st->WT;
+    st->state_bytes = (size_t)st->n_tiles * h->cir.Nj * st->WT * sizeof(double);
+    int rc;
+    if ((rc = dev_alloc(h, (void**)&st->rth, st->state_bytes))) return rc;
+    if ((rc = dev_alloc(h, (void**)&st->rx, st->state_bytes))) return rc;
+    RCK(cudaMemsetAsync(st->rth, 0, st->state_bytes, h->stream));
+    RCK(cudaMemsetAsync(st->rx, 0, st->state_bytes, h->stream));
+    st->prepared = true;
+    h->resident = st;
+    return JJ_OK;
+}
+
+int resident_run(JJHandle* h, long long i0, int n, const long long* th_plane, const long long* I_plane) {
+    ResidentState* st = (ResidentState*)h->resident_plan;
+    if (!st || !st->prepared) { h->err = "resident engine not prepared"; return JJ_ESTATE; }
+    size_t need = (size_t)2 * n * sizeof(long long);
+    if (need > st->plane_cap) {
+        RCK(cudaStreamSynchronize(h->stream));
+        dev_free(h, st->plane_d, st->plane_cap);
+        st->plane_d = nullptr; st->plane_cap = 0;
+        int rc = dev_alloc(h, (void**)&st->plane_d, need);
+        if (rc) return rc;
+        st->plane_cap = need;
+    }
+    std::vector<long long> pl((size_t)2 * n, -1);
+    for (int k = 0; k < n; ++k) {
+        if (th_plane) pl[k] = th_plane[k];
+        if (I_plane) pl[n + k] = I_plane[k];
+        if (pl[k] >= h->n_th_planes || pl[n + k] >= h->n_I_planes) { h->err = "run: plane index out of range"; return JJ_EINVAL; }
+    }
+    RCK(cudaMemcpyAsync(st->plane_d, pl.data(), need, cudaMemcpyHostToDevice, h->stream));
+    RCK(cudaStreamSynchronize(h->stream));     // pl goes out of scope
+    ResArgs a;
+    fill_args(h, st, a);
+    a.i0 = i0; a.n = n; a.th_plane = st->plane_d; a.I_plane = st->plane_d + n;
+    return launch(h, st, a);
+}
+
+int resident_debug_solve(JJHandle* h, const double* b_d, double* J_d) {
+    ResidentState* st = (ResidentState*)h->resident_plan;
+    if (!st) { h->err = "resident engine: no plan"; return JJ_ESTATE; }
+    if (!st->prepared) { int rc = resident_prepare(h); if (rc) return rc; }
+    ResArgs a;
+    fill_args(h, st, a);
+    a.dbg_b = b_d; a.dbg_J = J_d;
+    return launch(h, st, a);
+}
+
+void resident_get_config(JJHandle* h, int* C, int* WT) {
+    ResidentState* st = (ResidentState*)h->resident_plan;
+    *C = st ? st->C : 1; *WT = st ? st->WT : 0;
+}
+
+int resident_set_state(JJHandle*, const double*, const double*) { return JJ_OK; }   // reads the canonical arrays
+int resident_get_state(JJHandle* h, double*, double*) { h->err = "internal: canonical state is authoritative"; return JJ_ESTATE; }
+
+}  // namespace jj

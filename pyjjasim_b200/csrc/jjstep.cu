@@ -395,6 +395,7 @@ void jj_destroy(JJHandle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     free_problem(h);
+    resident_drop_plan(h);
     free_sweep(h, h->fwd); free_sweep(h, h->bwd);
     free_circuit(h);
     cudaFree(h->flag_d);
@@ -408,6 +409,7 @@ int jj_set_circuit(JJHandle* h, const JJCircuit* c) {
     REQUIRE(c && c->Nj > 0 && c->Nf >= 0, JJ_EINVAL, "circuit: bad sizes");
     REQUIRE(c->cpr_harmonics >= 1 && c->cpr_harmonics <= 16, JJ_EINVAL, "circuit: cpr_harmonics must be 1..16");
     if (h->have_problem) free_problem(h);
+    resident_drop_plan(h);
     free_circuit(h);
     CircuitDev& d = h->cir;
     d.Nj = c->Nj; d.Nf = c->Nf;
@@ -439,6 +441,7 @@ int jj_set_solver(JJHandle* h, const JJSweep* fwd, const JJSweep* bwd) {
     CK(cudaSetDevice(h->device));
     REQUIRE(fwd && bwd, JJ_EINVAL, "solver: null sweep");
     if (h->have_problem) free_problem(h);
+    resident_drop_plan(h);
     int rc;
     if ((rc = upload_sweep(h, h->fwd, fwd))) return rc;
     if ((rc = upload_sweep(h, h->bwd, bwd))) return rc;
@@ -492,7 +495,6 @@ int jj_set_state(JJHandle* h, const double* t1, const double* t2) {
     if ((rc = h2d_padded(h, h->th1, t1, h->cir.Nj))) return rc;
     if ((rc = h2d_padded(h, h->th2, t2, h->cir.Nj))) return rc;
     CK(cudaStreamSynchronize(h->stream));
-    if (h->resident) { if ((rc = resident_set_state(h, t1, t2))) return rc; }
     h->have_state = true;
     return JJ_OK;
 }
@@ -500,8 +502,7 @@ int jj_set_state(JJHandle* h, const double* t1, const double* t2) {
 int jj_get_state(JJHandle* h, double* t1, double* t2) {
     CK(cudaSetDevice(h->device));
     REQUIRE(h->have_problem, JJ_ESTATE, "get_state: problem not set");
-    if (h->engine == JJ_ENGINE_RESIDENT && h->resident) return resident_get_state(h, t1, t2);
-    int rc;
+    int rc;     // both engines keep theta(-1), theta(-2) in the canonical arrays between runs
     if ((rc = d2h_padded(h, t1, h->th1, h->cir.Nj))) return rc;
     if ((rc = d2h_padded(h, t2, h->th2, h->cir.Nj))) return rc;
     CK(cudaStreamSynchronize(h->stream));
@@ -655,8 +656,8 @@ static int streaming_run(JJHandle* h, long long i0, int n, const long long* th_p
         }
     }
     CK(cudaGetLastError());
-    std::swap(h->th1, h->th2);   // th2 now holds theta_{last-1}... see below
-    // after the final post-only kernel: old th1 buffer = theta_{last-1}, old th2 buffer = theta_last
+    // the final post-only kernel left theta_{last-1} in the th1 buffer and wrote theta_last to the th2 buffer
+    std::swap(h->th1, h->th2);
     return JJ_OK;
 }
 
@@ -675,9 +676,9 @@ int jj_run(JJHandle* h, int64_t i0, int32_t n, const int64_t* th_plane, const in
         if (!resident_supported(h, why)) { h->err = "resident engine not applicable: " + why; return JJ_EINVAL; }
         if (!h->resident) { if ((rc = resident_prepare(h))) return rc; }
     }
-    if (want != h->engine && h->steps_done > 0) {
-        h->err = "run: engine cannot change in the middle of a problem";
-        return JJ_ESTATE;
+    if (want == JJ_ENGINE_RESIDENT && h->thetas) {
+        h->err = "resident engine does not support dense voltage sources";
+        return JJ_EINVAL;
     }
     h->engine = want;
     CK(cudaEventRecord(h->ev0, h->stream));
@@ -748,6 +749,30 @@ int jj_debug_solve(JJHandle* h, const double* b, double* J) {
     return JJ_OK;
 }
 
+int jj_set_resident_plan(JJHandle* h, const JJResidentPlan* plan) {
+    CK(cudaSetDevice(h->device));
+    REQUIRE(h->have_circuit && h->have_solver, JJ_ESTATE, "set_resident_plan: circuit and solver must be set first");
+    if (h->have_problem) free_problem(h);
+    return resident_set_plan(h, plan);
+}
+
+int jj_debug_resident_solve(JJHandle* h, const double* b, double* J) {
+    CK(cudaSetDevice(h->device));
+    REQUIRE(h->have_problem && h->cir.Nf > 0, JJ_ESTATE, "debug_resident_solve: problem not set");
+    double* tmp = nullptr;
+    size_t bytes = (size_t)h->cir.Nf * h->Wp * sizeof(double);
+    int rc = dev_alloc(h, (void**)&tmp, bytes);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(tmp, 0, bytes, h->stream));
+    CK(cudaMemsetAsync(h->v, 0, bytes, h->stream));
+    if ((rc = h2d_padded(h, h->v, b, h->cir.Nf)) == 0 && (rc = resident_debug_solve(h, h->v, tmp)) == 0)
+        rc = d2h_padded(h, J, tmp, h->cir.Nf);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    dev_free(h, tmp, bytes);
+    if (rc == 0 && e != cudaSuccess) { h->err = std::string("debug_resident_solve: ") + cudaGetErrorString(e); rc = JJ_ECUDA; }
+    return rc;
+}
+
 int jj_stats(JJHandle* h, JJStats* out) {
     memset(out, 0, sizeof(*out));
     out->engine = h->engine;
@@ -757,6 +782,7 @@ int jj_stats(JJHandle* h, JJStats* out) {
     out->device_bytes = h->device_bytes;
     out->non_finite = h->non_finite;
     out->cluster_size = 1; out->tile_problems = h->Wp;
+    if (h->engine == JJ_ENGINE_RESIDENT) { int c, w; resident_get_config(h, &c, &w); out->cluster_size = c; out->tile_problems = w; }
     return JJ_OK;
 }
 

@@ -23,7 +23,7 @@ import scipy.sparse
 
 from . import _lib
 from .current_phase_relation import harmonics
-from .factor import build_solve_program, system_matrix
+from .factor import factorize, streaming_program, resident_plan, system_matrix
 from .sources import classify_source, nonnegative_factors, ZERO, RANK1, DENSE
 
 __all__ = ["device_time_evolution_core", "CircuitTables", "DeviceEngine", "last_run_stats"]
@@ -63,10 +63,12 @@ class CircuitTables:
                 cx, cy = circuit.get_face_centroids()
             else:
                 cx, cy = _centroids_from_matrix(circuit, A)
-            self.program = build_solve_program(S, cx, cy, leaf_size=leaf_size)
+            self.factor = factorize(S, cx, cy, leaf_size=leaf_size)
+            self.program = streaming_program(self.factor)
             perm = self.program.perm.astype(np.int64)
         else:
             self.program = None
+            self.factor = None
             perm = np.zeros(0, dtype=np.int64)
         self.perm = perm
         inv = np.empty(Nf, dtype=np.int64)
@@ -90,6 +92,93 @@ class CircuitTables:
         jf[rows, slot] = inv[At.indices]
         js[rows, slot] = At.data
         self.junc_face, self.junc_sign = jf, js
+        self._resident = {}
+
+    # ------------------------------------------------------------------ resident engine plan
+    SMEM_LIMIT = 227 * 1024
+
+    def resident_smem_bytes(self, plan, Wt):
+        return (plan.n_rows + plan.stage_rows + plan.allreduce_rows + plan.C) * Wt * 8
+
+    def choose_resident(self, W):
+        """Pick (cluster size, problems per tile) for the resident engine, or None if the right-hand sides
+        do not fit in a cluster's shared memory. JJ_RESIDENT="C,Wt" overrides."""
+        if self.factor is None:
+            return None
+        env = os.environ.get("JJ_RESIDENT")
+        if env:
+            C, Wt = (int(v) for v in env.split(","))
+            return C, Wt
+        best = None
+        for Wt in (8, 4):
+            if W <= 4 and Wt == 8:
+                continue
+            for limit in (110 * 1024, self.SMEM_LIMIT):
+                for C in (1, 2, 4, 8):
+                    plan = self.resident_plan(C)
+                    if self.resident_smem_bytes(plan, Wt) <= limit:
+                        return C, Wt
+        return best
+
+    def resident_plan(self, C):
+        if C not in self._resident:
+            self._resident[C] = _ResidentTables(self, resident_plan(self.factor, C))
+        return self._resident[C].plan
+
+    def resident_tables(self, C):
+        self.resident_plan(C)
+        return self._resident[C]
+
+
+class _ResidentTables:
+    """Junction / face tables of a resident plan (device junction order, per-rank face lists)."""
+
+    def __init__(self, tab, plan):
+        self.plan = plan
+        C, Nj, Nf = plan.C, tab.Nj, tab.Nf
+        smem = np.stack(plan.smem_index)                      # (C, Nf)
+        jf = tab.junc_face.astype(np.int64)                   # permuted faces, -1 none
+        has = jf >= 0
+        rr = np.where(has, plan.row_rank[np.maximum(jf, 0)], -1)          # rank of each face, -1 replicated / none
+        co = np.where(has, plan.col_owner[np.maximum(jf, 0)], -1)
+        owner = np.where(rr[:, 0] >= 0, rr[:, 0], rr[:, 1])
+        both = (rr[:, 0] >= 0) & (rr[:, 1] >= 0)
+        assert np.all(rr[both, 0] == rr[both, 1]), "faces sharing a junction ended up in different subtrees"
+        shared_only = owner < 0
+        fallback = np.where(co[:, 0] >= 0, co[:, 0], np.where(co[:, 1] >= 0, co[:, 1], np.arange(Nj) % C))
+        owner = np.where(shared_only, fallback, owner).astype(np.int64)
+        order = np.lexsort((np.arange(Nj), owner))            # device junction order
+        self.junc_orig = order.astype(np.int32)
+        jdev = np.empty(Nj, dtype=np.int64)
+        jdev[order] = np.arange(Nj)
+        self.junc_ptr = np.searchsorted(owner[order], np.arange(C + 1)).astype(np.int32)
+        rows = np.where(has, smem[owner[:, None], np.maximum(jf, 0)], -1)
+        self.junc_row = np.ascontiguousarray(rows[order].astype(np.int32))
+        self.junc_sign = np.ascontiguousarray(tab.junc_sign[order].astype(np.int8))
+        # per-rank face lists: entry (g, j) goes to the rank owning j, at that rank's row of face g
+        g_of = np.repeat(np.arange(Nf), np.diff(tab.face_ptr))
+        j_of = tab.face_junc.astype(np.int64)
+        r_of = owner[j_of]
+        row_of = smem[r_of, g_of]
+        assert np.all(row_of >= 0)
+        key = np.lexsort((j_of, row_of, r_of))
+        n_rows = plan.n_rows
+        flat = r_of[key] * n_rows + row_of[key]
+        counts = np.bincount(flat, minlength=C * n_rows)
+        ptr_all = np.concatenate(([0], np.cumsum(counts)))
+        fp = np.zeros((C, n_rows + 1), dtype=np.int32)
+        for r in range(C):
+            fp[r] = ptr_all[r * n_rows: (r + 1) * n_rows + 1]
+        self.face_ptr = fp
+        self.face_junc = jdev[j_of[key]].astype(np.int32)
+        self.face_sign = tab.face_sign[key].astype(np.int8)
+        # which rank adds the flux term of a face / is authoritative for its row
+        fidx = np.full((C, n_rows), -1, dtype=np.int32)
+        for r in range(C):
+            mine = (plan.row_rank == r) | ((plan.row_rank < 0) & (plan.col_owner == r))
+            g = np.flatnonzero(mine)
+            fidx[r, smem[r, g]] = g
+        self.face_fidx = fidx
 
 
 def _centroids_from_matrix(circuit, A):
@@ -163,23 +252,53 @@ class DeviceEngine:
         c.cpr_harmonics = len(a) - 1
         c.cpr_a, c.cpr_b = _lib.f64(a), _lib.f64(b)
         self._ck(self.lib.jj_set_circuit(self.h, C.byref(c)))
-        sweeps = []
-        for name in ("fwd", "bwd"):
-            sw = tab.program.sweeps[name] if tab.program is not None else _empty_sweep()
-            s = _lib.JJSweep()
-            s.n_levels = len(sw["level_ptr"]) - 1
-            s.level_ptr, s.group_ptr = _lib.i32(sw["level_ptr"]), _lib.i32(sw["group_ptr"])
-            s.n_tiles = len(sw["tile_row0"])
-            s.tile_row0, s.tile_nrows = _lib.i32(sw["tile_row0"]), _lib.i32(sw["tile_nrows"])
-            s.tile_lpr, s.tile_nsteps = _lib.i32(sw["tile_lpr"]), _lib.i32(sw["tile_nsteps"])
-            s.tile_flags = _lib.i32(sw["tile_flags"])
-            s.tile_col_off, s.tile_val_off = _lib.i64(sw["tile_col_off"]), _lib.i64(sw["tile_val_off"])
-            s.n_cols, s.cols = sw["cols"].size, _lib.i32(sw["cols"])
-            s.n_vals, s.vals = sw["vals"].size, _lib.f64(sw["vals"])
-            s.stage_rows = sw["stage_rows"]
-            sweeps.append(s)
+        sweeps = [self._sweep_struct(tab.program.sweeps[name] if tab.program is not None else _empty_sweep())
+                  for name in ("fwd", "bwd")]
         self._ck(self.lib.jj_set_solver(self.h, C.byref(sweeps[0]), C.byref(sweeps[1])))
         self.tab = tab
+        self.resident_config = None
+
+    @staticmethod
+    def _sweep_struct(sw):
+        s = _lib.JJSweep()
+        s.n_levels = len(sw["level_ptr"]) - 1
+        s.level_ptr, s.group_ptr = _lib.i32(sw["level_ptr"]), _lib.i32(sw["group_ptr"])
+        s.n_tiles = len(sw["tile_row0"])
+        s.tile_row0, s.tile_nrows = _lib.i32(sw["tile_row0"]), _lib.i32(sw["tile_nrows"])
+        s.tile_lpr, s.tile_nsteps = _lib.i32(sw["tile_lpr"]), _lib.i32(sw["tile_nsteps"])
+        s.tile_flags = _lib.i32(sw["tile_flags"])
+        s.tile_col_off, s.tile_val_off = _lib.i64(sw["tile_col_off"]), _lib.i64(sw["tile_val_off"])
+        s.n_cols, s.cols = sw["cols"].size, _lib.i32(sw["cols"])
+        s.n_vals, s.vals = sw["vals"].size, _lib.f64(sw["vals"])
+        s.stage_rows = sw["stage_rows"]
+        s.tile_stage_off = _lib.i32(sw["tile_stage_off"])
+        return s
+
+    def set_resident(self, Ccl, Wt):
+        """Upload the resident-engine plan for cluster size Ccl and Wt problems per tile."""
+        rt = self.tab.resident_tables(Ccl)
+        plan = rt.plan
+        p = _lib.JJResidentPlan()
+        p.C, p.tile_problems, p.n_rows = Ccl, Wt, plan.n_rows
+        p.stage_rows, p.allreduce_rows = plan.stage_rows, plan.allreduce_rows
+        ops = np.ascontiguousarray(plan.ops, dtype=np.int32)
+        p.n_ops, p.n_fwd_ops, p.ops = len(ops), plan.n_fwd_ops, _lib.i32(ops)
+        progs = (_lib.JJSweep * Ccl)(*[self._sweep_struct(sw) for sw in plan.prog])
+        p.prog = progs
+        fp = np.ascontiguousarray(rt.face_ptr); ff = np.ascontiguousarray(rt.face_fidx)
+        p.junc_ptr, p.junc_orig = _lib.i32(rt.junc_ptr), _lib.i32(rt.junc_orig)
+        p.junc_row, p.junc_sign = _lib.i32(rt.junc_row), _lib.i8(rt.junc_sign)
+        p.face_ptr, p.face_junc, p.face_sign, p.face_fidx = _lib.i32(fp), _lib.i32(rt.face_junc), _lib.i8(rt.face_sign), _lib.i32(ff)
+        self._ck(self.lib.jj_set_resident_plan(self.h, C.byref(p)))
+        self.resident_config = (Ccl, Wt)
+
+    def debug_resident_solve(self, b):
+        bp = _lib.c_f64(np.asarray(b)[self.tab.perm])
+        Jp = np.empty_like(bp)
+        self._ck(self.lib.jj_debug_resident_solve(self.h, _lib.f64(bp), _lib.f64(Jp)))
+        J = np.empty_like(Jp)
+        J[self.tab.perm] = Jp
+        return J
 
     def set_problem(self, W, dt, seed=0, problem_offset=0, engine=_lib.JJ_ENGINE_AUTO):
         self.W = W
@@ -251,7 +370,7 @@ class DeviceEngine:
 def _empty_sweep():
     z32, z64 = np.zeros(1, np.int32), np.zeros(1, np.int64)
     return dict(level_ptr=z32, group_ptr=z32, tile_row0=z32[:0], tile_nrows=z32[:0], tile_lpr=z32[:0],
-                tile_nsteps=z32[:0], tile_flags=z32[:0], tile_col_off=z64[:0], tile_val_off=z64[:0],
+                tile_nsteps=z32[:0], tile_flags=z32[:0], tile_stage_off=z32[:0], tile_col_off=z64[:0], tile_val_off=z64[:0],
                 cols=z32[:0], vals=np.zeros(0), stage_rows=0)
 
 
@@ -305,6 +424,12 @@ def _run_shard(problem, tab, specs, dev, w0, w1, th_mask, I_mask, th_host, I_hos
     eng = DeviceEngine(dev)
     try:
         eng.set_circuit(tab, problem.current_phase_relation)
+        if engine_kind != _lib.JJ_ENGINE_STREAMING:
+            cfg = tab.choose_resident(W)
+            if cfg is not None:
+                eng.set_resident(*cfg)
+            elif engine_kind == _lib.JJ_ENGINE_RESIDENT:
+                raise ValueError("resident engine requested but the circuit does not fit in shared memory")
         seed = problem.noise_seed if getattr(problem, "noise_seed", None) is not None else 0
         eng.set_problem(W, dt, seed=seed, problem_offset=w0, engine=engine_kind)
         eng.set_state(problem.config_at_minus_1[:, w0:w1], problem.config_at_minus_2[:, w0:w1])

@@ -1,6 +1,6 @@
 """
-Host-side factorisation of the cycle-space system and its compilation into a *solve program* for
-the device.
+Host-side factorisation of the cycle-space system and its compilation into *solve programs* for
+the device engines.
 
 Reference behaviour being replaced: ``scipy.sparse.linalg.factorized(A_mat)`` once
 (reference: time_evolution.py:504-506, SuperLU with COLAMD) and two SuperLU triangular sweeps per
@@ -21,6 +21,13 @@ Here (all on the host, once per problem):
      nrows * lanes_per_row == 32) with a column index list; out[row0 + i] = (self ? src[row0 + i] : 0)
      + sum_c V[i, c] * src[cols[c]]. Values are stored in the order a warp consumes them
      ([step][lane], lane = i * lanes_per_row + c % lanes_per_row), so device loads are coalesced.
+
+Two packings of the same tiles exist:
+  * ``streaming_program``  - rows are permuted face indices (streaming engine, any size);
+  * ``resident_plan``      - the elimination tree is cut at depth log2(C); each of the C thread blocks
+    of a cluster owns one subtree (its rows live in that block's shared memory), the separators above
+    the cut are replicated in every block and combined with an all-reduce over distributed shared
+    memory in the forward sweep (resident engine).
 """
 import numpy as np
 import scipy.linalg
@@ -29,10 +36,13 @@ import scipy.sparse.linalg
 
 from .ordering import nested_dissection
 
-__all__ = ["SolveProgram", "build_solve_program", "system_matrix"]
+__all__ = ["Factor", "factorize", "streaming_program", "resident_plan", "system_matrix", "apply_program_host",
+           "build_solve_program"]
 
 TILE_SELF = 1        # add src[row] to the dot product (phase a)
-TILE_STAGED = 2      # result must not be written before the whole level has been read (phase b, multi-tile block)
+TILE_STAGED = 2      # block spans several tiles: results must not overwrite src before the level is complete
+
+OP_LEVEL, OP_ALLREDUCE = 0, 1
 
 
 def system_matrix(A, Lmat, Rv, Cv):
@@ -42,120 +52,36 @@ def system_matrix(A, Lmat, Rv, Cv):
     return scipy.sparse.csc_matrix(A @ mid @ A.T)
 
 
-class SolveProgram:
-    """
-    Device-ready description of  J = S^-1 b  in the permuted face numbering.
-
-    perm : (Nf,) new-to-old face permutation
-    For each sweep ('fwd', 'bwd'):
-      level_ptr : (n_levels + 1,) tiles of level l are level_ptr[l]:level_ptr[l+1]
-      tile_row0, tile_nrows, tile_lpr (lanes per row), tile_nsteps, tile_flags : (n_tiles,) int32
-      tile_col_off, tile_val_off : (n_tiles,) int64 offsets into cols / vals
-      cols : int32 column indices, nsteps * lpr per tile
-      vals : float64, nsteps * 32 per tile
-      stage_rows : rows of staging needed (max over levels of rows in TILE_STAGED tiles)
-    """
+class Factor:
+    """Block Cholesky factor of the permuted system: S[perm][:, perm] = Lc Lc^T."""
 
     def __init__(self):
-        self.perm = None
         self.n = 0
-        self.sweeps = {}
-        self.stats = {}
+        self.perm = None          # new-to-old
+        self.bptr = None          # block b owns permuted rows bptr[b]:bptr[b+1]
+        self.height = None        # leaves 0
+        self.depth = None         # cut-tree depth of the block
+        self.dom = None           # cut-tree path of the block
+        self.dinv = None          # list: inverse of the diagonal block (dense lower triangular)
+        self.Loff = None          # CSR: Lc without the diagonal blocks  (row i: couplings to earlier blocks)
+        self.LoffT = None         # CSR: its transpose                   (row j: couplings to later blocks)
+        self.nnz_L = 0
+
+    @property
+    def nb(self):
+        return len(self.bptr) - 1
+
+    @property
+    def H(self):
+        return int(self.height.max()) if self.nb else 0
 
 
-def _pow2_floor(v):
-    p = 1
-    while p * 2 <= v:
-        p *= 2
-    return p
-
-
-class _Emitter:
-    def __init__(self):
-        self.levels = []          # list of list of tiles
-        self.cur = None
-
-    def begin_level(self):
-        self.cur = []
-        self.levels.append(self.cur)
-
-    def begin_group(self):
-        """Tiles of one group are processed in the order given (streaming engine); groups of a level
-        are independent."""
-        self.cur.append([])
-
-    def tile(self, row0, V, cols, flags):
-        """V: (nrows_real, ncols) dense, rows row0..row0+nrows_real-1."""
-        self.cur[-1].append((row0, V, np.asarray(cols, dtype=np.int32), flags))
-
-    def pack(self, rows_per_tile_hint=None):
-        self.levels = [[g for g in lev if g] for lev in self.levels]
-        n_tiles = sum(len(g) for l in self.levels for g in l)
-        n_groups = sum(len(l) for l in self.levels)
-        level_ptr = np.zeros(len(self.levels) + 1, dtype=np.int32)
-        group_ptr = np.zeros(n_groups + 1, dtype=np.int32)
-        gi = 0
-        row0 = np.zeros(n_tiles, dtype=np.int32); nrows = np.zeros(n_tiles, dtype=np.int32)
-        lpr = np.zeros(n_tiles, dtype=np.int32); nsteps = np.zeros(n_tiles, dtype=np.int32)
-        flags = np.zeros(n_tiles, dtype=np.int32)
-        col_off = np.zeros(n_tiles, dtype=np.int64); val_off = np.zeros(n_tiles, dtype=np.int64)
-        cols_parts, vals_parts = [], []
-        co = vo = 0
-        t = 0
-        stage_rows = 0
-        nnz = 0
-        for li, lev in enumerate(self.levels):
-            staged = 0
-            for grp in lev:
-              gi += 1
-              for (r0, V, cols, fl) in grp:
-                  nr, nc = V.shape
-                  nrp = 1
-                  while nrp < nr:
-                      nrp *= 2
-                  assert nrp <= 32
-                  m = 32 // nrp
-                  st = (nc + m - 1) // m
-                  Vp = np.zeros((nrp, st * m))
-                  Vp[:nr, :nc] = V
-                  cp = np.zeros(st * m, dtype=np.int32)
-                  cp[:nc] = cols
-                  if nc < st * m:
-                      cp[nc:] = cols[-1] if nc else r0      # padded columns: any valid index, value 0
-                  # [step][lane], lane = i*m + s, column = step*m + s
-                  packed = Vp.reshape(nrp, st, m).transpose(1, 0, 2).reshape(st, 32)
-                  row0[t], nrows[t], lpr[t], nsteps[t], flags[t] = r0, nr, m, st, fl
-                  col_off[t], val_off[t] = co, vo
-                  cols_parts.append(cp); vals_parts.append(packed.ravel())
-                  co += cp.size; vo += packed.size
-                  nnz += nr * nc
-                  if fl & TILE_STAGED:
-                      staged += nr
-                  t += 1
-              group_ptr[gi] = t
-            level_ptr[li + 1] = gi
-            stage_rows = max(stage_rows, staged)
-        return dict(level_ptr=level_ptr, group_ptr=group_ptr, tile_row0=row0, tile_nrows=nrows, tile_lpr=lpr, tile_nsteps=nsteps,
-                    tile_flags=flags, tile_col_off=col_off, tile_val_off=val_off,
-                    cols=np.concatenate(cols_parts) if cols_parts else np.zeros(0, np.int32),
-                    vals=np.concatenate(vals_parts) if vals_parts else np.zeros(0),
-                    stage_rows=int(stage_rows), nnz=int(nnz))
-
-
-def _tile_rows_for(total_rows, want_tasks=16):
-    return max(1, min(32, _pow2_floor(max(1, total_rows // want_tasks))))
-
-
-def build_solve_program(S, cx, cy, leaf_size=8, drop_tol=0.0):
-    """
-    S : (Nf, Nf) SPD scipy sparse matrix;  cx, cy : (Nf,) face centroids.
-    Returns a SolveProgram.
-    """
+def factorize(S, cx, cy, leaf_size=8):
     n = S.shape[0]
-    prog = SolveProgram()
-    prog.n = n
-    perm, bptr, height = nested_dissection(S, cx, cy, leaf_size=leaf_size)
-    prog.perm = perm.astype(np.int32)
+    F = Factor()
+    F.n = n
+    perm, bptr, height, depth, dom = nested_dissection(S, cx, cy, leaf_size=leaf_size, return_tree=True)
+    F.perm, F.bptr, F.height, F.depth, F.dom = perm, bptr, height, depth, dom
     Sp = scipy.sparse.csc_matrix(S)[perm][:, perm].tocsc()
     lu = scipy.sparse.linalg.splu(Sp, permc_spec="NATURAL", diag_pivot_thresh=0.0,
                                   options=dict(SymmetricMode=True))
@@ -164,109 +90,365 @@ def build_solve_program(S, cx, cy, leaf_size=8, drop_tol=0.0):
     d = lu.U.diagonal()
     if not np.all(d > 0):
         raise RuntimeError("system matrix is not positive definite")
-    Lc = (lu.L @ scipy.sparse.diags(np.sqrt(d))).tocsr()       # Cholesky factor, S_perm = Lc Lc^T
+    Lc = (lu.L @ scipy.sparse.diags(np.sqrt(d))).tocsr()       # Cholesky factor
     Lc.sort_indices()
-    LcT = Lc.T.tocsr()                                          # rows of LcT = columns of Lc
-    LcT.sort_indices()
-    nb = len(bptr) - 1
-    H = int(height.max()) if nb else 0
-    by_height = [np.flatnonzero(height == h) for h in range(H + 1)]
-    rows_at = [int(sum(bptr[b + 1] - bptr[b] for b in by_height[h])) for h in range(H + 1)]
-
-    fwd, bwd = _Emitter(), _Emitter()
-    dinv = {}
+    F.nnz_L = int(Lc.nnz)
+    nb = F.nb
+    F.dinv = []
     for b in range(nb):
         r0, r1 = bptr[b], bptr[b + 1]
         D = Lc[r0:r1, r0:r1].toarray()
-        dinv[b] = scipy.linalg.solve_triangular(D, np.eye(r1 - r0), lower=True)
-
-    def emit_b_phase(em, h, transpose):
-        em.begin_level()
-        tr = _tile_rows_for(rows_at[h])
-        for b in by_height[h]:
-            r0, r1 = int(bptr[b]), int(bptr[b + 1])
-            k = r1 - r0
-            Di = dinv[b].T if transpose else dinv[b]
-            multi = k > tr
-            em.begin_group()
-            starts = list(range(0, k, tr))
-            if not transpose:
-                starts.reverse()     # in-place safe order: a lower-triangular row block reads rows above it
-            for t0 in starts:
-                t1 = min(k, t0 + tr)
-                if transpose:      # upper triangular: row i uses columns i..k-1
-                    c0, c1 = t0, k
-                else:              # lower triangular: row i uses columns 0..i
-                    c0, c1 = 0, t1
-                em.tile(r0 + t0, Di[t0:t1, c0:c1], np.arange(r0 + c0, r0 + c1), TILE_STAGED if multi else 0)
-
-    def emit_a_phase(em, h, M):
-        """M: CSR whose rows [r0:r1) hold the coupling coefficients (to be negated) outside the block."""
-        em.begin_level()
-        tr = _tile_rows_for(rows_at[h])
-        for b in by_height[h]:
-            r0, r1 = int(bptr[b]), int(bptr[b + 1])
-            k = r1 - r0
-            for t0 in range(0, k, tr):
-                t1 = min(k, t0 + tr)
-                sub = M[r0 + t0:r0 + t1]
-                cols = np.unique(sub.indices)
-                if cols.size == 0:
-                    # still emit an identity tile? no: t_B = b_B unchanged, nothing to do
-                    continue
-                V = -sub[:, cols].toarray()
-                em.begin_group()
-                em.tile(r0 + t0, V, cols, TILE_SELF)
-
-    # forward: heights ascending; a-phase uses Lc[B, <B]
-    Lc_strict = scipy.sparse.tril(Lc, k=-1).tocsr()
-    # remove within-block entries (they belong to D): keep only columns < block start
+        F.dinv.append(scipy.linalg.solve_triangular(D, np.eye(r1 - r0), lower=True))
     blk_of = np.repeat(np.arange(nb), np.diff(bptr))
-    coo = Lc_strict.tocoo()
+    coo = scipy.sparse.tril(Lc, k=-1).tocoo()
     keep = blk_of[coo.row] != blk_of[coo.col]
-    Loff = scipy.sparse.csr_matrix((coo.data[keep], (coo.row[keep], coo.col[keep])), shape=(n, n))
-    LoffT = Loff.T.tocsr()      # row j holds Lc[i, j] for i in later blocks
+    F.Loff = scipy.sparse.csr_matrix((coo.data[keep], (coo.row[keep], coo.col[keep])), shape=(n, n))
+    F.Loff.sort_indices()
+    F.LoffT = F.Loff.T.tocsr()
+    F.LoffT.sort_indices()
+    return F
+
+
+# ----------------------------------------------------------------------------------------------
+# tiles
+# ----------------------------------------------------------------------------------------------
+def _pow2_floor(v):
+    p = 1
+    while p * 2 <= v:
+        p *= 2
+    return p
+
+
+def _tile_rows_for(total_rows, want_tasks=16):
+    return max(1, min(32, _pow2_floor(max(1, total_rows // want_tasks))))
+
+
+def b_tiles(F, b, tr, transpose):
+    """Phase-b tiles of block b (apply D^-1, or D^-T when transpose) in an order that is safe for
+    in-place sequential execution. Returns a list of (row0, V, cols, flags)."""
+    r0, r1 = int(F.bptr[b]), int(F.bptr[b + 1])
+    k = r1 - r0
+    Di = F.dinv[b].T if transpose else F.dinv[b]
+    multi = k > tr
+    starts = list(range(0, k, tr))
+    if not transpose:
+        starts.reverse()          # a lower-triangular row block reads rows above it: do the last rows first
+    out = []
+    for t0 in starts:
+        t1 = min(k, t0 + tr)
+        c0, c1 = (t0, k) if transpose else (0, t1)
+        out.append((r0 + t0, Di[t0:t1, c0:c1], np.arange(r0 + c0, r0 + c1), TILE_STAGED if multi else 0))
+    return out
+
+
+def a_tiles(F, b, tr, M, col_mask=None):
+    """Phase-a tiles of block b: out = src[row] - M[row, cols] src[cols] over columns outside the block.
+    col_mask (bool per column) restricts the columns (resident engine: columns owned by one rank)."""
+    r0, r1 = int(F.bptr[b]), int(F.bptr[b + 1])
+    out = []
+    for t0 in range(r0, r1, tr):
+        t1 = min(r1, t0 + tr)
+        sub = M[t0:t1]
+        cols = np.unique(sub.indices)
+        if col_mask is not None:
+            cols = cols[col_mask[cols]]
+        if cols.size == 0:
+            continue
+        out.append((t0, -sub[:, cols].toarray(), cols, TILE_SELF))
+    return out
+
+
+def pack_levels(levels, row_map=None, col_map=None):
+    """
+    levels: list of levels; a level is a list of groups; a group is a list of tiles (row0, V, cols, flags).
+    row_map / col_map translate permuted row indices into the index space of the consumer.
+    """
+    levels = [[g for g in lev if g] for lev in levels]
+    n_tiles = sum(len(g) for lev in levels for g in lev)
+    n_groups = sum(len(lev) for lev in levels)
+    level_ptr = np.zeros(len(levels) + 1, dtype=np.int32)
+    group_ptr = np.zeros(n_groups + 1, dtype=np.int32)
+    row0 = np.zeros(n_tiles, dtype=np.int32); nrows = np.zeros(n_tiles, dtype=np.int32)
+    lpr = np.zeros(n_tiles, dtype=np.int32); nsteps = np.zeros(n_tiles, dtype=np.int32)
+    flags = np.zeros(n_tiles, dtype=np.int32); stage_off = np.zeros(n_tiles, dtype=np.int32)
+    col_off = np.zeros(n_tiles, dtype=np.int64); val_off = np.zeros(n_tiles, dtype=np.int64)
+    cols_parts, vals_parts = [], []
+    co = vo = t = gi = 0
+    stage_rows = nnz = 0
+    for li, lev in enumerate(levels):
+        staged = 0
+        for grp in lev:
+            gi += 1
+            for (r0, V, cols, fl) in grp:
+                nr, nc = V.shape
+                nrp = 1
+                while nrp < nr:
+                    nrp *= 2
+                assert nrp <= 32
+                m = 32 // nrp
+                st = (nc + m - 1) // m
+                Vp = np.zeros((nrp, st * m))
+                Vp[:nr, :nc] = V
+                cols = np.asarray(cols, dtype=np.int64)
+                if col_map is not None:
+                    cols = col_map[cols]
+                    assert np.all(cols >= 0)
+                cp = np.zeros(st * m, dtype=np.int32)
+                cp[:nc] = cols
+                if nc < st * m:
+                    cp[nc:] = cols[-1]                  # padded columns: any valid index, value 0
+                # [step][lane], lane = i*m + s, column = step*m + s
+                packed = Vp.reshape(nrp, st, m).transpose(1, 0, 2).reshape(st, 32)
+                row0[t] = r0 if row_map is None else row_map[r0]
+                assert row0[t] >= 0
+                nrows[t], lpr[t], nsteps[t], flags[t] = nr, m, st, fl
+                col_off[t], val_off[t] = co, vo
+                cols_parts.append(cp); vals_parts.append(packed.ravel())
+                co += cp.size; vo += packed.size
+                nnz += nr * nc
+                if fl & TILE_STAGED:
+                    stage_off[t] = staged
+                    staged += nr
+                t += 1
+            group_ptr[gi] = t
+        level_ptr[li + 1] = gi
+        stage_rows = max(stage_rows, staged)
+    return dict(level_ptr=level_ptr, group_ptr=group_ptr, tile_row0=row0, tile_nrows=nrows, tile_lpr=lpr,
+                tile_nsteps=nsteps, tile_flags=flags, tile_stage_off=stage_off, tile_col_off=col_off,
+                tile_val_off=val_off,
+                cols=np.concatenate(cols_parts) if cols_parts else np.zeros(0, np.int32),
+                vals=np.concatenate(vals_parts) if vals_parts else np.zeros(0),
+                stage_rows=int(stage_rows), nnz=int(nnz))
+
+
+class SolveProgram:
+    """Streaming packing of the factor: perm (new-to-old faces) and sweeps['fwd'|'bwd'] (see pack_levels)."""
+
+    def __init__(self):
+        self.perm = None
+        self.n = 0
+        self.sweeps = {}
+        self.stats = {}
+        self.factor = None
+
+
+def streaming_program(F):
+    prog = SolveProgram()
+    prog.n, prog.perm, prog.factor = F.n, F.perm.astype(np.int32), F
+    H = F.H
+    by_height = [np.flatnonzero(F.height == h) for h in range(H + 1)]
+    rows_at = [int(sum(F.bptr[b + 1] - F.bptr[b] for b in by_height[h])) for h in range(H + 1)]
+    fwd, bwd = [], []
     for h in range(H + 1):
+        tr = _tile_rows_for(rows_at[h])
         if h > 0:
-            emit_a_phase(fwd, h, Loff)
-        emit_b_phase(fwd, h, transpose=False)
+            fwd.append([[t] for b in by_height[h] for t in a_tiles(F, b, tr, F.Loff)])
+        fwd.append([b_tiles(F, b, tr, False) for b in by_height[h]])
     for h in range(H, -1, -1):
+        tr = _tile_rows_for(rows_at[h])
         if h < H:
-            emit_a_phase(bwd, h, LoffT)
-        emit_b_phase(bwd, h, transpose=True)
-    prog.sweeps["fwd"] = fwd.pack()
-    prog.sweeps["bwd"] = bwd.pack()
-    prog.stats = dict(n=n, blocks=nb, height=H, nnz_L=int(Lc.nnz),
+            bwd.append([[t] for b in by_height[h] for t in a_tiles(F, b, tr, F.LoffT)])
+        bwd.append([b_tiles(F, b, tr, True) for b in by_height[h]])
+    prog.sweeps["fwd"] = pack_levels(fwd)
+    prog.sweeps["bwd"] = pack_levels(bwd)
+    prog.stats = dict(n=F.n, blocks=F.nb, height=H, nnz_L=F.nnz_L,
                       nnz_fwd=prog.sweeps["fwd"]["nnz"], nnz_bwd=prog.sweeps["bwd"]["nnz"],
                       vals_fwd=int(prog.sweeps["fwd"]["vals"].size), vals_bwd=int(prog.sweeps["bwd"]["vals"].size),
-                      levels_fwd=len(fwd.levels), levels_bwd=len(bwd.levels))
+                      levels_fwd=len(fwd), levels_bwd=len(bwd))
     return prog
+
+
+def build_solve_program(S, cx, cy, leaf_size=8):
+    """factorize + streaming_program."""
+    return streaming_program(factorize(S, cx, cy, leaf_size=leaf_size))
 
 
 def apply_program_host(prog, b):
     """
-    Host interpreter of the solve program (float64 numpy) - used by CPU tests to validate the program
-    itself against a direct solve; the device kernels implement exactly these semantics.
+    Host interpreter of the streaming solve program (float64 numpy) - used by CPU tests to validate the
+    program itself against a direct solve; the device kernels implement exactly these semantics.
     b : (Nf, ...) right-hand side in ORIGINAL face numbering. Returns J in original numbering.
     """
     v = np.array(b, dtype=np.double)[prog.perm]
     for name in ("fwd", "bwd"):
-        sw = prog.sweeps[name]
-        for l in range(len(sw["level_ptr"]) - 1):
-            out = []
-            gp = sw["group_ptr"]
-            for t in range(gp[sw["level_ptr"][l]], gp[sw["level_ptr"][l + 1]]):
-                r0, nr, m, st = sw["tile_row0"][t], sw["tile_nrows"][t], sw["tile_lpr"][t], sw["tile_nsteps"][t]
-                nrp = 32 // m
-                cols = sw["cols"][sw["tile_col_off"][t]: sw["tile_col_off"][t] + st * m]
-                packed = sw["vals"][sw["tile_val_off"][t]: sw["tile_val_off"][t] + st * 32]
-                V = packed.reshape(st, nrp, m).transpose(1, 0, 2).reshape(nrp, st * m)[:nr]
-                acc = np.tensordot(V, v[cols], axes=(1, 0))
-                if sw["tile_flags"][t] & TILE_SELF:
-                    acc = acc + v[r0:r0 + nr]
-                out.append((r0, nr, acc))
-            for (r0, nr, acc) in out:
-                v[r0:r0 + nr] = acc
+        _run_packed(prog.sweeps[name], v)
     res = np.empty_like(v)
     res[prog.perm] = v
     return res
+
+
+def _unpack_tile(sw, t):
+    r0, nr, m, st = sw["tile_row0"][t], sw["tile_nrows"][t], sw["tile_lpr"][t], sw["tile_nsteps"][t]
+    nrp = 32 // m
+    cols = sw["cols"][sw["tile_col_off"][t]: sw["tile_col_off"][t] + st * m]
+    packed = sw["vals"][sw["tile_val_off"][t]: sw["tile_val_off"][t] + st * 32]
+    V = packed.reshape(st, nrp, m).transpose(1, 0, 2).reshape(nrp, st * m)[:nr]
+    return r0, nr, cols, V
+
+
+def _run_packed(sw, v, levels=None):
+    gp = sw["group_ptr"]
+    for l in (range(len(sw["level_ptr"]) - 1) if levels is None else levels):
+        out = []
+        for t in range(gp[sw["level_ptr"][l]], gp[sw["level_ptr"][l + 1]]):
+            r0, nr, cols, V = _unpack_tile(sw, t)
+            acc = np.tensordot(V, v[cols], axes=(1, 0))
+            if sw["tile_flags"][t] & TILE_SELF:
+                acc = acc + v[r0:r0 + nr]
+            out.append((r0, nr, acc))
+        for (r0, nr, acc) in out:
+            v[r0:r0 + nr] = acc
+
+
+# ----------------------------------------------------------------------------------------------
+# resident plan
+# ----------------------------------------------------------------------------------------------
+class ResidentPlan:
+    """
+    Per-rank programs for a cluster of C thread blocks (see module docstring).
+
+    C, n_rows            : cluster size, rows of each block's shared-memory vector (local + replicated)
+    n_local_max, n_shared
+    smem_index[r]        : (Nf,) shared-memory row of permuted face g on rank r, or -1
+    owner_rank           : (Nf,) rank whose vector holds the authoritative copy of face g (-1: replicated)
+    prog[r]              : pack_levels(...) result in rank r's index space; one level per OP_LEVEL op
+    ops                  : (n_ops, 4) int32, identical structure on every rank:
+                           (OP_LEVEL, level index, staged?, 0) or (OP_ALLREDUCE, row_lo, row_hi, 0)
+    n_fwd_ops            : ops[:n_fwd_ops] form the forward sweep, the rest the backward sweep
+    """
+
+
+def resident_plan(F, C, want_tasks=16):
+    assert C in (1, 2, 4, 8, 16)
+    d = int(np.log2(C))
+    nb, n = F.nb, F.n
+    shared_blk = F.depth < d
+    blk_rank = np.where(shared_blk, -1, F.dom >> np.maximum(F.depth - d, 0))
+    sizes = np.diff(F.bptr)
+    blk_of = np.repeat(np.arange(nb), sizes)
+    row_rank = blk_rank[blk_of]                                   # -1: replicated
+    n_local = np.array([int(np.sum(row_rank == r)) for r in range(C)])
+    n_local_max = int(n_local.max()) if C else 0
+    # replicated rows: ordered by (height, row) so that one all-reduce covers a contiguous range
+    sh_blocks = np.flatnonzero(shared_blk)
+    sh_blocks = sh_blocks[np.lexsort((sh_blocks, F.height[sh_blocks]))]
+    sh_index = np.full(n, -1, dtype=np.int64)
+    pos = 0
+    sh_range = {}
+    for b in sh_blocks:
+        k = int(sizes[b])
+        sh_index[F.bptr[b]:F.bptr[b + 1]] = n_local_max + pos + np.arange(k)
+        h = int(F.height[b])
+        lo, hi = sh_range.get(h, (n_local_max + pos, n_local_max + pos))
+        sh_range[h] = (lo, n_local_max + pos + k)
+        pos += k
+    n_shared = pos
+    smem_index = []
+    for r in range(C):
+        m = sh_index.copy()
+        rows = np.flatnonzero(row_rank == r)
+        m[rows] = np.arange(rows.size)
+        smem_index.append(m)
+    # columns of replicated blocks are contributed by the lowest rank below the block
+    col_owner = np.where(row_rank >= 0, row_rank,
+                         (F.dom[blk_of] << np.maximum(d - F.depth[blk_of], 0)))
+    col_owner = np.minimum(col_owner, C - 1)
+
+    local_blocks = [np.flatnonzero(blk_rank == r) for r in range(C)]
+    Hloc = max([int(F.height[lb].max()) if lb.size else 0 for lb in local_blocks] + [0])
+    sh_heights = sorted(sh_range)
+
+    def tr_for(blocks):
+        return _tile_rows_for(int(sum(sizes[b] for b in blocks)), want_tasks)
+
+    plan = ResidentPlan()
+    plan.C, plan.n_local_max, plan.n_shared, plan.n_rows = C, n_local_max, n_shared, n_local_max + n_shared
+    plan.smem_index, plan.row_rank, plan.col_owner = smem_index, row_rank, col_owner
+    plan.prog, ops = [], None
+    for r in range(C):
+        levels, rops = [], []
+
+        def level(groups, staged_possible):
+            levels.append(groups)
+            staged = int(any(t[3] & TILE_STAGED for g in groups for t in g))
+            rops.append((OP_LEVEL, len(levels) - 1, staged, 0))
+
+        # ---- forward: local subtree bottom-up
+        for h in range(Hloc + 1):
+            blocks = [b for b in local_blocks[r] if F.height[b] == h]
+            tr = tr_for(blocks)
+            if h > 0:
+                level([[t] for b in blocks for t in a_tiles(F, b, tr, F.Loff)], False)
+            level([b_tiles(F, b, tr, False) for b in blocks], True)
+        # ---- forward: replicated separators bottom-up, partial sums + all-reduce
+        for h in sh_heights:
+            blocks = [b for b in sh_blocks if F.height[b] == h]
+            tr = tr_for(blocks)
+            mask = col_owner == r
+            level([[t] for b in blocks for t in a_tiles(F, b, tr, F.Loff, col_mask=mask)], False)
+            rops.append((OP_ALLREDUCE, sh_range[h][0], sh_range[h][1], 0))
+            level([b_tiles(F, b, tr, False) for b in blocks], True)
+        n_fwd = len(rops)
+        # ---- backward: replicated separators top-down (computed redundantly by every rank)
+        for h in reversed(sh_heights):
+            blocks = [b for b in sh_blocks if F.height[b] == h]
+            tr = tr_for(blocks)
+            level([[t] for b in blocks for t in a_tiles(F, b, tr, F.LoffT)], False)
+            level([b_tiles(F, b, tr, True) for b in blocks], True)
+        # ---- backward: local subtree top-down
+        for h in range(Hloc, -1, -1):
+            blocks = [b for b in local_blocks[r] if F.height[b] == h]
+            tr = tr_for(blocks)
+            level([[t] for b in blocks for t in a_tiles(F, b, tr, F.LoffT)], False)
+            level([b_tiles(F, b, tr, True) for b in blocks], True)
+        plan.prog.append(pack_levels(levels, row_map=smem_index[r], col_map=smem_index[r]))
+        rops = np.array(rops, dtype=np.int32).reshape(-1, 4)
+        if ops is None:
+            ops, plan.n_fwd_ops = rops, n_fwd
+        else:
+            # identical structure on every rank (only the staged hint may differ: take the union)
+            assert np.array_equal(ops[:, [0, 1]], rops[:, [0, 1]])
+            assert np.array_equal(ops[ops[:, 0] == OP_ALLREDUCE], rops[rops[:, 0] == OP_ALLREDUCE])
+            ops[:, 2] = np.where(ops[:, 0] == OP_LEVEL, np.maximum(ops[:, 2], rops[:, 2]), ops[:, 2])
+    plan.ops = ops
+    plan.stage_rows = max(p["stage_rows"] for p in plan.prog)
+    plan.allreduce_rows = max([hi - lo for (lo, hi) in sh_range.values()] + [0])
+    plan.vals = [int(p["vals"].size) for p in plan.prog]
+    return plan
+
+
+def apply_resident_plan_host(F, plan, b_perm):
+    """Host interpreter of a resident plan (CPU test of the plan; mirrors the device kernel's data flow).
+    b_perm: (Nf, ...) right-hand side in PERMUTED numbering. Returns J in permuted numbering."""
+    C = plan.C
+    shape_tail = b_perm.shape[1:]
+    vec = [np.zeros((plan.n_rows,) + shape_tail) for _ in range(C)]
+    # every rank holds its local rows; replicated rows start as PARTIAL right-hand sides: put everything on rank 0
+    for r in range(C):
+        loc = np.flatnonzero(plan.row_rank == r)
+        vec[r][plan.smem_index[r][loc]] = b_perm[loc]
+    sh = np.flatnonzero(plan.row_rank < 0)
+    if sh.size:
+        # split the replicated right-hand side unevenly over the ranks to exercise the reduction
+        w = np.linspace(1.0, 2.0, C)
+        w = w / w.sum()
+        for r in range(C):
+            vec[r][plan.smem_index[r][sh]] = w[r] * b_perm[sh]
+    for op in plan.ops:
+        if op[0] == OP_LEVEL:
+            for r in range(C):
+                _run_packed(plan.prog[r], vec[r], levels=[op[1]])
+        else:
+            lo, hi = op[1], op[2]
+            tot = sum(vec[r][lo:hi] for r in range(C))
+            for r in range(C):
+                vec[r][lo:hi] = tot
+    out = np.zeros_like(b_perm)
+    for r in range(C):
+        loc = np.flatnonzero(plan.row_rank == r)
+        out[loc] = vec[r][plan.smem_index[r][loc]]
+    if sh.size:
+        out[sh] = vec[0][plan.smem_index[0][sh]]
+        for r in range(1, C):
+            assert np.allclose(vec[r][plan.smem_index[r][sh]], out[sh], rtol=1e-12, atol=1e-13)
+    return out

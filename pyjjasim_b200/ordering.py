@@ -19,7 +19,7 @@ import scipy.sparse
 __all__ = ["nested_dissection"]
 
 
-def nested_dissection(S, cx, cy, leaf_size=24):
+def nested_dissection(S, cx, cy, leaf_size=24, return_tree=False):
     """
     Parameters
     ----------
@@ -33,6 +33,9 @@ def nested_dissection(S, cx, cy, leaf_size=24):
     block_ptr : (nb + 1,) block b owns permuted rows block_ptr[b]:block_ptr[b+1]
     block_height : (nb,) 0 for leaves; a separator is one higher than the tallest block below it
     Blocks are numbered in post-order: every block comes after all blocks of its subtree.
+    With return_tree=True also returns block_depth and block_dom: block b is the separator (or leaf) of
+    the subdomain reached from the root by the cuts encoded in the binary digits of block_dom[b]
+    (most significant digit = first cut); its subtree holds exactly the blocks (depth + t, dom * 2^t + r).
     """
     n = S.shape[0]
     cx = np.asarray(cx, dtype=np.double)
@@ -114,4 +117,7 @@ def nested_dissection(S, cx, cy, leaf_size=24):
             h = max(h, height[stack.pop()] + 1)
         height[b] = h
         stack.append(b)
+    if return_tree:
+        first = perm[block_ptr[:-1]] if nb else np.zeros(0, dtype=np.int64)
+        return perm, block_ptr, height, b_depth.astype(np.int64), dom[first]
     return perm, block_ptr, height

@@ -116,3 +116,80 @@ def test_missing_gpu_library_fails_loudly(monkeypatch):
     kw, _ = cases.build("single_problem", pj)
     with pytest.raises(RuntimeError):
         pj.TimeEvolutionProblem(**kw).compute()
+
+
+# ------------------------------------------------------------------------------------------------
+# resident engine (cluster kernel): every cluster size / tile width against the golden vectors
+# ------------------------------------------------------------------------------------------------
+RESIDENT_CONFIGS = ["1,8", "1,4", "2,8", "4,8", "4,4", "8,8", "8,4"]
+
+
+@pytest.mark.parametrize("cfg", RESIDENT_CONFIGS)
+def test_resident_solve_matches_direct_solve(cfg, monkeypatch):
+    import scipy.sparse.linalg
+    from pyjjasim_b200 import engine
+    from pyjjasim_b200.factor import system_matrix
+    Ccl, Wt = (int(v) for v in cfg.split(","))
+    a = pj.SquareArray(40, 37)
+    rng = np.random.RandomState(2)
+    a.set_resistance(0.5 + rng.rand(a._Nj()))
+    a.set_inductance(0.1)
+    tab = engine.CircuitTables(a, 0.05)
+    eng = engine.DeviceEngine(0)
+    eng.set_circuit(tab, pj.DefaultCPR())
+    eng.set_resident(Ccl, Wt)
+    W = 13
+    eng.set_problem(W, 0.05)
+    b = rng.randn(a._Nf(), W)
+    J = eng.debug_resident_solve(b)
+    S = system_matrix(a.get_cycle_matrix(), a._L(), tab.Rv, tab.Cv)
+    Jref = scipy.sparse.linalg.spsolve(S.tocsc(), b)
+    eng.close()
+    assert np.max(np.abs(J - Jref)) <= 1e-12 * np.max(np.abs(Jref))
+
+
+@pytest.mark.parametrize("cfg", RESIDENT_CONFIGS)
+@pytest.mark.parametrize("name", ["sq_mixed", "sq_frustrated", "honeycomb", "noise_recycled", "custom_cpr", "sq_iv"])
+def test_resident_engine_matches_reference_golden(name, cfg, golden_dir, monkeypatch):
+    monkeypatch.setenv("JJ_RESIDENT", cfg)
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    kw, prob, res = run_device(name, "resident")
+    from pyjjasim_b200 import engine
+    st = engine.last_run_stats[0]
+    assert st["engine"] == 2 and (st["cluster_size"], st["tile_problems"]) == tuple(int(v) for v in cfg.split(","))
+    tol = cases.TOL[name]
+    assert np.max(np.abs(res.theta - g["theta"])) <= tol
+    if "current" in g.files:
+        assert np.max(np.abs(res.current - g["current"])) <= 10 * tol
+    if "voltage" in g.files:
+        assert np.max(np.abs(res.voltage - g["voltage"])) <= 10 * tol / kw.get("time_step", 0.05)
+
+
+def test_resident_and_streaming_agree_on_device_noise(monkeypatch):
+    # same Philox stream in both engines: identical draws -> trajectories agree to round-off over a short horizon
+    kw, _ = cases.build("noise_small", pj)
+    kw["noise_seed"] = 99
+    out = {}
+    for eng_name in ("streaming", "resident"):
+        monkeypatch.setenv("JJ_ENGINE", eng_name)
+        out[eng_name] = pj.TimeEvolutionProblem(**kw).compute().theta
+    assert np.max(np.abs(out["streaming"] - out["resident"])) <= 1e-9
+    assert np.std(out["resident"][:, -1, -1]) > 1e-3      # noise actually acted
+
+
+def test_device_noise_statistics_and_shard_invariance():
+    from pyjjasim_b200 import engine
+    a = pj.SquareArray(12, 12)
+    tab = engine.CircuitTables(a, 0.05)
+    eng = engine.DeviceEngine(0)
+    eng.set_circuit(tab, pj.DefaultCPR())
+    eng.set_problem(64, 0.05, seed=5)
+    z = np.stack([eng.debug_noise(s) for s in range(40)])
+    eng.set_problem(32, 0.05, seed=5, problem_offset=32)
+    z2 = eng.debug_noise(7)
+    eng.close()
+    assert np.array_equal(z[7][:, 32:], z2)               # keyed by the global problem index
+    n = z.size
+    assert abs(z.mean()) < 5 / np.sqrt(n) and abs(z.var() - 1) < 5 * np.sqrt(2 / n)
+    assert abs(np.mean(z ** 4) - 3) < 0.1 and np.max(np.abs(z)) < 7
+    assert abs(np.corrcoef(z[:-1].ravel(), z[1:].ravel())[0, 1]) < 5 / np.sqrt(n)
