@@ -1,0 +1,75 @@
+"""
+Multi-GPU use of the time-evolution path: shard the problem axis W, one process per GPU.
+
+Problems never interact (every operation of the stepping loop is column-wise in W,
+reference: time_evolution.py:523-580), so the batch is cut into contiguous shards, each rank integrates its
+shard on its own GPU with its own replica of the factor, and there is NO collective on the step path. The
+only communication is one gather of the stored planes at the end (NCCL all_gather on GPU boxes, gloo in CPU
+tests). Shard starts are multiples of 4 so the counter-based noise, keyed by the global problem index, is
+identical however the batch is sharded.
+
+Single-process alternative: ``TimeEvolutionProblem(..., devices=[0, 1, ...])`` drives several GPUs from host
+threads (engine.device_time_evolution_core).
+"""
+import numpy as np
+
+from .engine import shard_bounds
+
+__all__ = ["shard_for_rank", "gather_problem_axis", "compute_sharded"]
+
+
+def shard_for_rank(W, rank, world_size):
+    """[w0, w1) of this rank."""
+    b = shard_bounds(W, world_size)
+    return b[rank], b[rank + 1]
+
+
+def gather_problem_axis(local, W, group=None):
+    """
+    All-gather arrays sharded along axis 1 (the problem axis): ``local`` is (N, w1 - w0, K) on each rank;
+    returns the full (N, W, K) array on every rank. Uses torch.distributed (any backend).
+    """
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    b = shard_bounds(W, world)
+    widths = [b[r + 1] - b[r] for r in range(world)]
+    wmax = max(widths)
+    N, _, K = local.shape
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    buf = torch.zeros((wmax, N, K), dtype=torch.float64, device=dev)
+    buf[: local.shape[1]] = torch.from_numpy(np.ascontiguousarray(np.moveaxis(local, 1, 0))).to(dev)
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf, group=group)
+    out = np.empty((N, W, K))
+    for r in range(world):
+        if widths[r]:
+            out[:, b[r]:b[r + 1], :] = np.moveaxis(parts[r][: widths[r]].cpu().numpy(), 0, 1)
+    return out
+
+
+def compute_sharded(problem, device=None, group=None, core=None):
+    """
+    SPMD time evolution: every rank calls this with the same TimeEvolutionProblem; each integrates its
+    shard of the problem axis on ``device`` (default: LOCAL_RANK) and all ranks return the complete
+    TimeEvolutionResult. ``core`` replaces the device core (tests inject the CPU oracle here).
+    """
+    import os
+    import torch.distributed as dist
+    from .time_evolution import time_evolution as _time_evolution
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    W = problem.get_problem_count()
+    w0, w1 = shard_for_rank(W, rank, world)
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+
+    def sharded_core(prob, th_mask, I_mask):
+        if core is not None:
+            th, I = core(prob, th_mask, I_mask, w0, w1)
+        else:
+            from .engine import device_time_evolution_core
+            th, I = device_time_evolution_core(prob, th_mask, I_mask, shard=(w0, w1), device=device)
+        return gather_problem_axis(th, W, group), gather_problem_axis(I, W, group)
+
+    return _time_evolution(problem, core=sharded_core)

@@ -517,10 +517,12 @@ def _dense_for_device(name, table, tab):
     return table
 
 
-def device_time_evolution_core(problem, th_store_mask, I_store_mask, engine=None):
+def device_time_evolution_core(problem, th_store_mask, I_store_mask, engine=None, shard=None, device=None):
     """
     Device replacement of time_evolution_core (reference: time_evolution.py:461-582), stencil width 3.
     Returns th_out, I_out of shape (Nj, W, n_stored + 2).
+    shard=(w0, w1), device=d: integrate only problems [w0, w1) on GPU d and return (Nj, w1 - w0, .) arrays
+    (used by distributed.compute_sharded, one process per GPU).
     """
     if getattr(problem, "stencil_width", 3) != 3:
         raise NotImplementedError("only stencil_width=3 is supported")
@@ -546,7 +548,11 @@ def device_time_evolution_core(problem, th_store_mask, I_store_mask, engine=None
     bounds = shard_bounds(W, len(devices))
     stats = {}
     jobs = [(dev, bounds[k], bounds[k + 1]) for k, dev in enumerate(devices) if bounds[k + 1] > bounds[k]]
-    if len(jobs) == 1:
+    if shard is not None:
+        jobs = [(devices[0] if device is None else device, shard[0], shard[1])] if shard[1] > shard[0] else []
+    if len(jobs) == 0:
+        pass
+    elif len(jobs) == 1:
         dev, w0, w1 = jobs[0]
         _run_shard(problem, tab, specs, dev, w0, w1, th_mask, I_mask, th_host, I_host, engine, stats)
     else:
@@ -566,6 +572,8 @@ def device_time_evolution_core(problem, th_store_mask, I_store_mask, engine=None
             raise errors[0]
     last_run_stats.clear()
     last_run_stats.update(stats)
+    if shard is not None:
+        th_host, I_host = th_host[:, :, shard[0]:shard[1]], I_host[:, :, shard[0]:shard[1]]
     # (plane, Nj, W) -> (Nj, W, plane) views, the reference's layout (quirk Q7)
     return np.moveaxis(th_host, 0, 2), np.moveaxis(I_host, 0, 2)
 

@@ -20,6 +20,9 @@ import numpy as np
 __all__ = ["RankOneSource", "SourceSpec", "classify_source"]
 
 ZERO, RANK1, DENSE = 0, 1, 2
+# an input counts as base[e] * amp[w] when that product reproduces it to a few units in the last place
+# (the user's own array was rounded the same number of times)
+_RANK1_RTOL = 2e-15
 
 
 class RankOneSource:
@@ -85,7 +88,7 @@ class SourceSpec:
         return np.broadcast_to(np.asarray(self._dense_fn(i), dtype=np.double), (self.N, self.W))
 
 
-def _rank_one_factor(a2, rtol=4e-16):
+def _rank_one_factor(a2, rtol=_RANK1_RTOL):
     """Try a2 (N, W) == base (N,) x amp (W,). Returns (base, amp) or None."""
     N, W = a2.shape
     flat = np.argmax(np.abs(a2))
@@ -121,7 +124,7 @@ def classify_source(x, N, W, Nt, zero_if_allclose=True):
             def amp_fn(i, _x=x, _base=base, _j0=j0):
                 v = np.broadcast_to(np.asarray(_x(i), dtype=np.double), (N, W))
                 amp = v[_j0, :] / _base[_j0]
-                if not np.allclose(_base[:, None] * amp[None, :], v, rtol=4e-16, atol=0.0):
+                if not np.allclose(_base[:, None] * amp[None, :], v, rtol=_RANK1_RTOL, atol=0.0):
                     raise _NotRankOne()
                 return amp
             # probe a few steps: a callable whose structure changes over time is handled densely
@@ -168,7 +171,7 @@ def classify_source(x, N, W, Nt, zero_if_allclose=True):
         base = rf[0]
         j0 = int(np.argmax(np.abs(base)))
         tab = full[j0, :, :] / base[j0]
-        if np.allclose(base[:, None, None] * tab[None, :, :], full, rtol=4e-16, atol=0.0):
+        if np.allclose(base[:, None, None] * tab[None, :, :], full, rtol=_RANK1_RTOL, atol=0.0):
             return SourceSpec(RANK1, N, W, Nt, base=base, static=False, amp_fn=lambda i, t=tab: t[:, i])
     return SourceSpec(DENSE, N, W, Nt, static=False, dense_fn=lambda i, f=full: f[:, :, i])
 

@@ -271,12 +271,14 @@ def _apply_derivative(x, index, stencil, dt):
     return (stencil[0] * x[:, :, index] + stencil[1] * x[:, :, index - 1]) / dt
 
 
-def time_evolution(problem: TimeEvolutionProblem):
+def time_evolution(problem: TimeEvolutionProblem, core=None):
     """
     Decide which time points must be kept (voltage needs the preceding step as well), run the device
     core, finite-difference the voltage, trim helper steps. (reference: time_evolution.py:422-458)
+    ``core`` (default: the GPU engine) has the signature of the reference's time_evolution_core.
     """
-    from .engine import device_time_evolution_core
+    if core is None:
+        from .engine import device_time_evolution_core as core
     Nt = problem._Nt()
     store = problem.store_time_steps
     zeros = np.zeros(Nt, dtype=bool)
@@ -295,7 +297,7 @@ def time_evolution(problem: TimeEvolutionProblem):
         if has_L:
             V_I_store_mask[Vt_ids] = True
 
-    th_out, I_out = device_time_evolution_core(problem, V_th_store_mask, V_I_store_mask)
+    th_out, I_out = core(problem, V_th_store_mask, V_I_store_mask)
 
     V_out = None
     if problem.store_voltage:
