@@ -103,6 +103,10 @@ def run_ours(args, rank, world, local_rank, dist):
     eng.set_circuit(tab, pj.DefaultCPR())
     kind = {"auto": _lib.JJ_ENGINE_AUTO, "streaming": _lib.JJ_ENGINE_STREAMING,
             "resident": _lib.JJ_ENGINE_RESIDENT}[os.environ.get("JJ_ENGINE", "auto")]
+    if kind != _lib.JJ_ENGINE_STREAMING:
+        cfg = tab.choose_resident(W)
+        if cfg is not None:
+            eng.set_resident(*cfg)
     eng.set_problem(W, DT, seed=SEED, problem_offset=w0, engine=kind)
     eng.set_source(_lib.JJ_SRC_F, _lib.JJ_KIND_RANK1, True, np.ones(tab.Nf))
     eng.upload_source(_lib.JJ_SRC_F, 0, np.full((1, W), FRUST))
@@ -167,6 +171,8 @@ def run_ours(args, rank, world, local_rank, dist):
     # end to end through the public API with host buffers
     e2e = None
     try:
+        if os.environ.get("JJ_BENCH_SKIP_E2E"):
+            raise RuntimeError("skipped (JJ_BENCH_SKIP_E2E)")
         os.environ["JJ_DEVICES"] = str(local_rank)
         th0 = np.zeros((tab.Nj, W))
         reps, e2e_t = max(1, min(3, args.steps)), []
@@ -280,7 +286,7 @@ def main():
     out = run_ours(args, rank, world, local_rank, dist)
     if rank == 0:
         try:
-            out["cpu_baseline"] = cpu_reference(1, 0)
+            out["cpu_baseline"] = {"skipped": True} if os.environ.get("JJ_BENCH_SKIP_E2E") else cpu_reference(1, 0)
         except Exception as e:
             out["cpu_baseline"] = {"error": repr(e)}
         print(json.dumps(out))

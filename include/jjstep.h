@@ -61,6 +61,19 @@ typedef struct {
     const int32_t *tile_stage_off; /* staged tiles: first staging row (resident engine) */
 } JJSweep;
 
+/* Resident engine: the tiles of one cluster rank, packed as one contiguous stream per (level, warp)
+ * (pyjjasim_b200/factor.py: pack_warp_streams). */
+typedef struct {
+    int32_t n_levels, n_warps;   /* n_warps == 16 */
+    int32_t n_tiles;
+    const int32_t *wt_ptr;       /* [n_levels*n_warps + 1] tiles of (level, warp) */
+    const int32_t *ws_ptr;       /* [n_levels*n_warps + 1] first stream step of (level, warp) */
+    const int32_t *thdr;         /* [n_tiles][2]: row0 | (nrows-1)<<16 | log2(lanes per row)<<21 | flags<<24 ;
+                                    nsteps | stage_off<<16 */
+    int64_t n_steps;
+    const uint8_t *stream;       /* [n_steps][320]: 32 float64 values then 32 uint16 shared-memory rows */
+} JJRankStream;
+
 /* Resident-engine plan (see pyjjasim_b200/factor.py: resident_plan). A cluster of C thread blocks owns a
  * tile of `tile_problems` problems for the whole time loop; block r keeps the right-hand-side rows of
  * elimination subtree r plus replicas of the separators above the cut in its shared memory. */
@@ -70,7 +83,7 @@ typedef struct {
     int32_t stage_rows, allreduce_rows;
     int32_t n_ops, n_fwd_ops;
     const int32_t *ops;              /* [n_ops][4]: (0, level, staged, 0) | (1, row_lo, row_hi, 0) */
-    const JJSweep *prog;             /* [C] tiles of rank r; level_ptr/group_ptr index its levels */
+    const JJRankStream *prog;        /* [C] tiles of rank r; a level op names a level of this program */
     const int32_t *junc_ptr;         /* [C+1] rank r owns device junctions junc_ptr[r]:junc_ptr[r+1] */
     const int32_t *junc_orig;        /* [Nj] original junction index of each device junction */
     const int32_t *junc_row;         /* [Nj*2] shared-memory rows of its faces on the owner rank, -1 none */

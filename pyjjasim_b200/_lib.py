@@ -38,10 +38,16 @@ class JJSweep(C.Structure):
                 ("stage_rows", C.c_int32), ("tile_stage_off", _i32p)]
 
 
+class JJRankStream(C.Structure):
+    _fields_ = [("n_levels", C.c_int32), ("n_warps", C.c_int32), ("n_tiles", C.c_int32),
+                ("wt_ptr", _i32p), ("ws_ptr", _i32p), ("thdr", _i32p), ("n_steps", C.c_int64),
+                ("stream", C.POINTER(C.c_uint8))]
+
+
 class JJResidentPlan(C.Structure):
     _fields_ = [("C", C.c_int32), ("tile_problems", C.c_int32), ("n_rows", C.c_int32),
                 ("stage_rows", C.c_int32), ("allreduce_rows", C.c_int32), ("n_ops", C.c_int32),
-                ("n_fwd_ops", C.c_int32), ("ops", _i32p), ("prog", C.POINTER(JJSweep)),
+                ("n_fwd_ops", C.c_int32), ("ops", _i32p), ("prog", C.POINTER(JJRankStream)),
                 ("junc_ptr", _i32p), ("junc_orig", _i32p), ("junc_row", _i32p), ("junc_sign", _i8p),
                 ("face_ptr", _i32p), ("face_junc", _i32p), ("face_sign", _i8p), ("face_fidx", _i32p)]
 

@@ -31,17 +31,11 @@ constexpr int NT = 512;           // threads per block
 constexpr int NWARPS = NT / 32;
 constexpr int MAXC = 8;
 
-struct TileHdr {                  // 32 bytes, read as two int4
-    int row0, nrows, lpr, nsteps;
-    int flags, stage_off;
-    unsigned col_off, val_off;
-};
-
 struct RankProg {
-    const TileHdr* tiles;
-    const int* lvl_ptr;           // [n_levels + 1] -> tiles
-    const int* cols;
-    const double* vals;
+    const int* wt_ptr;            // [n_levels * NWARPS + 1] -> tiles
+    const int* ws_ptr;            // [n_levels * NWARPS + 1] -> stream steps
+    const int2* thdr;             // packed tile headers
+    const unsigned char* stream;  // [n_steps][320]
 };
 
 struct ResArgs {
@@ -74,7 +68,6 @@ struct ResArgs {
 };
 
 struct ResidentState {
-    JJResidentPlan plan{};           // scalars only are meaningful
     int C = 1, WT = 8, n_rows = 0, stage_rows = 0, ar_rows = 0, n_ops = 0;
     int4* ops = nullptr;
     RankProg prog[MAXC]{};
@@ -93,73 +86,134 @@ struct ResidentState {
 };
 
 // ------------------------------------------------------------------------------------------------
+// Shared-memory vector: row r holds WT float64 (problem-minor) as WT/2 16-byte chunks. Rows are 64 B
+// (WT=8) or 32 B (WT=4) apart, so rows r and r+2 (r+4) would start in the same bank; lanes of a
+// quarter-warp typically read the same chunk of different rows. The chunk index is therefore XOR-ed with
+// a few row bits, which spreads eight consecutive rows over all eight 16-byte bank groups.
+// ------------------------------------------------------------------------------------------------
 template <int WT>
-__device__ __forceinline__ void run_tile(const TileHdr& t, const RankProg& p, double* __restrict__ v,
-                                         double* __restrict__ stage, int lane) {
-    const int m = t.lpr;
-    const int mshift = 31 - __clz(m);
-    const int i = lane >> mshift, s = lane & (m - 1);
-    double acc[WT];
-#pragma unroll
-    for (int q = 0; q < WT; ++q) acc[q] = 0.0;
-    const double* vp = p.vals + t.val_off + lane;
-    const int* cp = p.cols + t.col_off + s;
-#pragma unroll 4
-    for (int st = 0; st < t.nsteps; ++st) {
-        double a = __ldg(vp + (size_t)st * 32);
-        int c = __ldg(cp + st * m);
-        const double2* src = reinterpret_cast<const double2*>(v + (size_t)c * WT);
-#pragma unroll
-        for (int q = 0; q < WT / 2; ++q) {
-            double2 sv = src[q];
-            acc[2 * q] = fma(a, sv.x, acc[2 * q]);
-            acc[2 * q + 1] = fma(a, sv.y, acc[2 * q + 1]);
-        }
-    }
-    for (int off = m >> 1; off > 0; off >>= 1) {
-#pragma unroll
-        for (int q = 0; q < WT; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], off);
-    }
-    __syncwarp();
-    if (s == 0 && i < t.nrows) {
-        double2* self = reinterpret_cast<double2*>(v + (size_t)(t.row0 + i) * WT);
-        if (t.flags & 1) {
-#pragma unroll
-            for (int q = 0; q < WT / 2; ++q) {
-                double2 sv = self[q];
-                acc[2 * q] += sv.x; acc[2 * q + 1] += sv.y;
-            }
-        }
-        double2* dst = (t.flags & 2) ? reinterpret_cast<double2*>(stage + (size_t)(t.stage_off + i) * WT) : self;
-#pragma unroll
-        for (int q = 0; q < WT / 2; ++q) dst[q] = make_double2(acc[2 * q], acc[2 * q + 1]);
-    }
+__device__ __forceinline__ int swz(int row) {
+    return WT == 8 ? ((row >> 1) & 3) : ((row >> 2) & 1);
+}
+template <int WT>
+__device__ __forceinline__ double2* chunk_ptr(double* v, int row, int chunk) {
+    return reinterpret_cast<double2*>(v + (size_t)row * WT) + (chunk ^ swz<WT>(row));
+}
+template <int WT>
+__device__ __forceinline__ const double2* chunk_ptr(const double* v, int row, int chunk) {
+    return reinterpret_cast<const double2*>(v + (size_t)row * WT) + (chunk ^ swz<WT>(row));
 }
 
-__device__ __forceinline__ TileHdr load_hdr(const TileHdr* p) {
-    const int4* q = reinterpret_cast<const int4*>(p);
-    int4 a = __ldg(q), b = __ldg(q + 1);
-    TileHdr t;
-    t.row0 = a.x; t.nrows = a.y; t.lpr = a.z; t.nsteps = a.w;
-    t.flags = b.x; t.stage_off = b.y; t.col_off = (unsigned)b.z; t.val_off = (unsigned)b.w;
-    return t;
-}
+constexpr int STEP_BYTES = 320;
+constexpr int RING = 4;           // stream steps kept in flight per warp
 
-template <int WT>
-__device__ void exec_level(const RankProg& p, int level, int staged, double* v, double* stage) {
+// Per-warp read position in the factor stream: tile range, step range and a register ring of RING
+// prefetched steps (values + rows). The ring for the NEXT level is loaded before the barrier that ends the
+// current one, so the L2 latency of the stream overlaps the barrier and the FMAs of earlier steps.
+struct Cursor {
+    int t0, t1, s, s_end;
+    double ra[RING]; int rc[RING];
+};
+
+__device__ __forceinline__ void cursor_open(Cursor& cu, const RankProg& p, int level) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t0 = __ldg(p.lvl_ptr + level), t1 = __ldg(p.lvl_ptr + level + 1);
-    for (int t = t0 + warp; t < t1; t += NWARPS) {
-        TileHdr h = load_hdr(p.tiles + t);
-        run_tile<WT>(h, p, v, stage, lane);
+    const int idx = level * NWARPS + warp;
+    cu.t0 = __ldg(p.wt_ptr + idx); cu.t1 = __ldg(p.wt_ptr + idx + 1);
+    cu.s = __ldg(p.ws_ptr + idx); cu.s_end = __ldg(p.ws_ptr + idx + 1);
+#pragma unroll
+    for (int k = 0; k < RING; ++k) {
+        cu.ra[k] = 0.0; cu.rc[k] = 0;
+        if (cu.s + k < cu.s_end) {
+            const unsigned char* rec = p.stream + (size_t)(cu.s + k) * STEP_BYTES;
+            cu.ra[k] = __ldg(reinterpret_cast<const double*>(rec) + lane);
+            cu.rc[k] = __ldg(reinterpret_cast<const unsigned short*>(rec + 256) + lane);
+        }
     }
+}
+
+// One level of the solve program: every warp streams through its own tiles.
+template <int WT>
+__device__ void exec_level(const RankProg& p, Cursor& cu, int staged, int next_level,
+                           double* __restrict__ v, double* __restrict__ stage) {
+    const int lane = threadIdx.x & 31;
+    const int t0 = cu.t0, t1 = cu.t1;
+    int s = cu.s;
+    const int s_end = cu.s_end;
+    const unsigned char* base = p.stream;
+    double ra[RING]; int rc[RING];
+#pragma unroll
+    for (int k = 0; k < RING; ++k) { ra[k] = cu.ra[k]; rc[k] = cu.rc[k]; }
+    for (int tb = t0; tb < t1; tb += 32) {
+        int2 myh = make_int2(0, 0);
+        if (tb + lane < t1) myh = __ldg(p.thdr + tb + lane);
+        const int nb = min(32, t1 - tb);
+        for (int k = 0; k < nb; ++k) {
+            const int h0 = __shfl_sync(0xffffffffu, myh.x, k), h1 = __shfl_sync(0xffffffffu, myh.y, k);
+            const int row0 = h0 & 0xffff, nrows = ((h0 >> 16) & 31) + 1, mshift = (h0 >> 21) & 7, flags = (h0 >> 24) & 3;
+            const int nsteps = h1 & 0xffff, stage_off = (h1 >> 16) & 0xffff;
+            const int m = 1 << mshift;
+            const int i = lane >> mshift, sub = lane & (m - 1);
+            double acc[WT];
+#pragma unroll
+            for (int q = 0; q < WT; ++q) acc[q] = 0.0;
+            for (int j = 0; j < nsteps; ++j) {
+                const double a = ra[0];
+                const int c = rc[0];
+#pragma unroll
+                for (int r = 0; r < RING - 1; ++r) { ra[r] = ra[r + 1]; rc[r] = rc[r + 1]; }
+                if (s + RING < s_end) {
+                    const unsigned char* rec = base + (size_t)(s + RING) * STEP_BYTES;
+                    ra[RING - 1] = __ldg(reinterpret_cast<const double*>(rec) + lane);
+                    rc[RING - 1] = __ldg(reinterpret_cast<const unsigned short*>(rec + 256) + lane);
+                }
+                ++s;
+                const double2* src = reinterpret_cast<const double2*>(v + (size_t)c * WT);
+                const int f = swz<WT>(c);
+#pragma unroll
+                for (int q = 0; q < WT / 2; ++q) {
+                    const double2 sv = src[q ^ f];
+                    acc[2 * q] = fma(a, sv.x, acc[2 * q]);
+                    acc[2 * q + 1] = fma(a, sv.y, acc[2 * q + 1]);
+                }
+            }
+            for (int off = m >> 1; off > 0; off >>= 1) {
+#pragma unroll
+                for (int q = 0; q < WT; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], off);
+            }
+            __syncwarp();
+            if (sub == 0 && i < nrows) {
+                const int row = row0 + i;
+                const int f = swz<WT>(row);
+                double2* self = reinterpret_cast<double2*>(v + (size_t)row * WT);
+                if (flags & 1) {
+#pragma unroll
+                    for (int q = 0; q < WT / 2; ++q) {
+                        const double2 sv = self[q ^ f];
+                        acc[2 * q] += sv.x; acc[2 * q + 1] += sv.y;
+                    }
+                }
+                // staged results are stored in the physical layout of the destination row
+                double2* dst = (flags & 2) ? reinterpret_cast<double2*>(stage + (size_t)(stage_off + i) * WT) : self;
+#pragma unroll
+                for (int q = 0; q < WT / 2; ++q) dst[q ^ f] = make_double2(acc[2 * q], acc[2 * q + 1]);
+            }
+            __syncwarp();
+        }
+    }
+    if (next_level >= 0) cursor_open(cu, p, next_level);
     __syncthreads();
     if (staged) {
-        for (int t = t0 + warp; t < t1; t += NWARPS) {
-            TileHdr h = load_hdr(p.tiles + t);
-            if (h.flags & 2) {
-                for (int e = lane; e < h.nrows * WT; e += 32)
-                    v[(size_t)h.row0 * WT + e] = stage[(size_t)h.stage_off * WT + e];
+        for (int tb = t0; tb < t1; tb += 32) {
+            int2 myh = make_int2(0, 0);
+            if (tb + lane < t1) myh = __ldg(p.thdr + tb + lane);
+            const int nb = min(32, t1 - tb);
+            for (int k = 0; k < nb; ++k) {
+                const int h0 = __shfl_sync(0xffffffffu, myh.x, k), h1 = __shfl_sync(0xffffffffu, myh.y, k);
+                if ((h0 >> 24) & 2) {
+                    const int row0 = h0 & 0xffff, nrows = ((h0 >> 16) & 31) + 1, stage_off = (h1 >> 16) & 0xffff;
+                    for (int e = lane; e < nrows * WT; e += 32)
+                        v[(size_t)row0 * WT + e] = stage[(size_t)stage_off * WT + e];
+                }
             }
         }
         __syncthreads();
@@ -168,10 +222,12 @@ __device__ void exec_level(const RankProg& p, int level, int staged, double* v, 
 
 // all-reduce of rows [lo, hi) of every block's vector: reduce-scatter into mailboxes, sum in rank order,
 // broadcast the sums back into every replica. Deterministic: the same block adds the partials in the same order.
+// Rows are copied in their physical (swizzled) layout; row indices are identical on all ranks.
 template <int WT>
 __device__ void allreduce_rows(cg::cluster_group& cluster, int C, int rank, int lo, int hi, double* v, double* mbox) {
     const int n = hi - lo;
-    const int ch = (n + C - 1) / C;
+    int ch = (n + C - 1) / C;
+    ch = (ch + 7) & ~7;           // chunk starts keep the row swizzle phase (multiple of 8 rows)
     for (int q = 0; q < C; ++q) {
         const int r0 = q * ch, r1 = min(n, r0 + ch);
         if (r1 <= r0) continue;
@@ -195,10 +251,22 @@ __device__ void allreduce_rows(cg::cluster_group& cluster, int C, int rank, int 
 template <int WT, bool CL>
 __device__ void run_ops(const ResArgs& a, cg::cluster_group& cluster, int rank, double* v, double* stage, double* mbox) {
     const RankProg& p = a.prog[rank];
+    Cursor cu;
+    bool open = false;
     for (int o = 0; o < a.n_ops; ++o) {
-        int4 op = __ldg(a.ops + o);
-        if (op.x == 0) exec_level<WT>(p, op.y, op.z, v, stage);
-        else if (CL) allreduce_rows<WT>(cluster, a.C, rank, op.y, op.z, v, mbox);
+        const int4 op = __ldg(a.ops + o);
+        if (op.x == 0) {
+            if (!open) cursor_open(cu, p, op.y);
+            int next = -1;                       // the next level op, looking past an all-reduce
+            for (int o2 = o + 1; o2 < a.n_ops && o2 <= o + 2; ++o2) {
+                const int4 nx = __ldg(a.ops + o2);
+                if (nx.x == 0) { next = nx.y; break; }
+            }
+            exec_level<WT>(p, cu, op.z, next, v, stage);
+            open = next >= 0;
+        } else if (CL) {
+            allreduce_rows<WT>(cluster, a.C, rank, op.y, op.z, v, mbox);
+        }
     }
 }
 
@@ -235,14 +303,12 @@ __device__ void junction_pass(const ResArgs& a, int rank, int tile, long long n,
             int2 rows = __ldg(a.junc_row + jp);
             char2 sg = a.junc_sign[jp];
             if (rows.x >= 0) {
-                const double2* Jp = reinterpret_cast<const double2*>(v + (size_t)rows.x * WT + q);
-                double2 j0 = Jp[0], j1 = Jp[1];
+                double2 j0 = *chunk_ptr<WT>(v, rows.x, q >> 1), j1 = *chunk_ptr<WT>(v, rows.x, (q >> 1) + 1);
                 double s = (double)sg.x;
                 y[0] += s * j0.x; y[1] += s * j0.y; y[2] += s * j1.x; y[3] += s * j1.y;
             }
             if (rows.y >= 0) {
-                const double2* Jp = reinterpret_cast<const double2*>(v + (size_t)rows.y * WT + q);
-                double2 j0 = Jp[0], j1 = Jp[1];
+                double2 j0 = *chunk_ptr<WT>(v, rows.y, q >> 1), j1 = *chunk_ptr<WT>(v, rows.y, (q >> 1) + 1);
                 double s = (double)sg.y;
                 y[0] += s * j0.x; y[1] += s * j0.y; y[2] += s * j1.x; y[3] += s * j1.y;
             }
@@ -362,8 +428,8 @@ __device__ void face_pass(const ResArgs& a, int rank, int tile, long long n, dou
                 for (int k = 0; k < 4; ++k) acc[k] -= 6.283185307179586 * (b * am[k]);
             }
         }
-        double2* vp = reinterpret_cast<double2*>(v + (size_t)row * WT + q);
-        vp[0] = make_double2(acc[0], acc[1]); vp[1] = make_double2(acc[2], acc[3]);
+        *chunk_ptr<WT>(v, row, q >> 1) = make_double2(acc[0], acc[1]);
+        *chunk_ptr<WT>(v, row, (q >> 1) + 1) = make_double2(acc[2], acc[3]);
     }
 }
 
@@ -384,15 +450,20 @@ __global__ void __launch_bounds__(NT, 1) k_resident(const ResArgs a) {
             const int* fidx = a.face_fidx + (size_t)rank * a.n_rows;
             for (int idx = threadIdx.x; idx < a.n_rows * G; idx += NT) {
                 int row = idx / G, q = (idx % G) * 4, w = tile * WT + q, g = fidx[row];
-                for (int k = 0; k < 4; ++k)
-                    v[(size_t)row * WT + q + k] = (g >= 0 && w < a.Wp) ? a.dbg_b[(size_t)g * a.Wp + w + k] : 0.0;
+                double t[4];
+                for (int k = 0; k < 4; ++k) t[k] = (g >= 0 && w < a.Wp) ? a.dbg_b[(size_t)g * a.Wp + w + k] : 0.0;
+                *chunk_ptr<WT>(v, row, q >> 1) = make_double2(t[0], t[1]);
+                *chunk_ptr<WT>(v, row, (q >> 1) + 1) = make_double2(t[2], t[3]);
             }
             __syncthreads();
             run_ops<WT, CL>(a, cluster, rank, v, stage, mbox);
             for (int idx = threadIdx.x; idx < a.n_rows * G; idx += NT) {
                 int row = idx / G, q = (idx % G) * 4, w = tile * WT + q, g = fidx[row];
-                if (g >= 0 && w < a.Wp)
-                    for (int k = 0; k < 4; ++k) a.dbg_J[(size_t)g * a.Wp + w + k] = v[(size_t)row * WT + q + k];
+                if (g >= 0 && w < a.Wp) {
+                    double2 t0 = *chunk_ptr<WT>(v, row, q >> 1), t1 = *chunk_ptr<WT>(v, row, (q >> 1) + 1);
+                    double* o = a.dbg_J + (size_t)g * a.Wp + w;
+                    o[0] = t0.x; o[1] = t0.y; o[2] = t1.x; o[3] = t1.y;
+                }
             }
             __syncthreads();
             continue;
@@ -491,25 +562,15 @@ int resident_set_plan(JJHandle* h, const JJResidentPlan* pl) {
     int rc;
     if ((rc = up(h, st, (int**)&st->ops, pl->ops, (size_t)pl->n_ops * 4))) return rc;
     for (int r = 0; r < pl->C; ++r) {
-        const JJSweep& s = pl->prog[r];
-        std::vector<TileHdr> hdr(s.n_tiles);
-        for (int t = 0; t < s.n_tiles; ++t) {
-            hdr[t].row0 = s.tile_row0[t]; hdr[t].nrows = s.tile_nrows[t]; hdr[t].lpr = s.tile_lpr[t];
-            hdr[t].nsteps = s.tile_nsteps[t]; hdr[t].flags = s.tile_flags[t];
-            hdr[t].stage_off = s.tile_stage_off ? s.tile_stage_off[t] : 0;
-            if (s.tile_col_off[t] > 0xffffffffLL || s.tile_val_off[t] > 0xffffffffLL) {
-                h->err = "resident plan: program too large"; return JJ_EINVAL;
-            }
-            hdr[t].col_off = (unsigned)s.tile_col_off[t]; hdr[t].val_off = (unsigned)s.tile_val_off[t];
-        }
-        std::vector<int> lvl(s.n_levels + 1);
-        for (int l = 0; l <= s.n_levels; ++l) lvl[l] = s.group_ptr[s.level_ptr[l]];
-        TileHdr* hd; int* lp; int* cp; double* vp;
-        if ((rc = up(h, st, &hd, hdr.data(), hdr.size()))) return rc;
-        if ((rc = up(h, st, &lp, lvl.data(), lvl.size()))) return rc;
-        if ((rc = up(h, st, &cp, s.cols, (size_t)s.n_cols))) return rc;
-        if ((rc = up(h, st, &vp, s.vals, (size_t)s.n_vals))) return rc;
-        st->prog[r].tiles = hd; st->prog[r].lvl_ptr = lp; st->prog[r].cols = cp; st->prog[r].vals = vp;
+        const JJRankStream& ps = pl->prog[r];
+        if (ps.n_warps != NWARPS) { h->err = "resident plan: program packed for a different warp count"; return JJ_EINVAL; }
+        int *wt, *ws; int* th; unsigned char* sb;
+        size_t np = (size_t)ps.n_levels * ps.n_warps + 1;
+        if ((rc = up(h, st, &wt, ps.wt_ptr, np))) return rc;
+        if ((rc = up(h, st, &ws, ps.ws_ptr, np))) return rc;
+        if ((rc = up(h, st, &th, ps.thdr, (size_t)ps.n_tiles * 2))) return rc;
+        if ((rc = up(h, st, &sb, ps.stream, (size_t)ps.n_steps * STEP_BYTES))) return rc;
+        st->prog[r].wt_ptr = wt; st->prog[r].ws_ptr = ws; st->prog[r].thdr = (const int2*)th; st->prog[r].stream = sb;
     }
     if ((rc = up(h, st, &st->junc_ptr, pl->junc_ptr, (size_t)pl->C + 1))) return rc;
     if ((rc = up(h, st, &st->junc_orig, pl->junc_orig, (size_t)Nj))) return rc;
@@ -529,7 +590,7 @@ int resident_set_plan(JJHandle* h, const JJResidentPlan* pl) {
     k_recip<<<(Nj + 255) / 256, 256, 0, h->stream>>>(Nj, h->cir.c0, st->ic0);
     h->launches++;
     RCK(cudaStreamSynchronize(h->stream));
-    st->smem_bytes = ((size_t)st->n_rows + st->stage_rows + st->ar_rows + st->C) * st->WT * sizeof(double);
+    st->smem_bytes = ((size_t)st->n_rows + st->stage_rows + st->ar_rows + 8 * st->C) * st->WT * sizeof(double);
     return JJ_OK;
 }
 

@@ -98,7 +98,7 @@ class CircuitTables:
     SMEM_LIMIT = 227 * 1024
 
     def resident_smem_bytes(self, plan, Wt):
-        return (plan.n_rows + plan.stage_rows + plan.allreduce_rows + plan.C) * Wt * 8
+        return (plan.n_rows + plan.stage_rows + plan.allreduce_rows + 8 * plan.C) * Wt * 8
 
     def choose_resident(self, W):
         """Pick (cluster size, problems per tile) for the resident engine, or None if the right-hand sides
@@ -283,7 +283,16 @@ class DeviceEngine:
         p.stage_rows, p.allreduce_rows = plan.stage_rows, plan.allreduce_rows
         ops = np.ascontiguousarray(plan.ops, dtype=np.int32)
         p.n_ops, p.n_fwd_ops, p.ops = len(ops), plan.n_fwd_ops, _lib.i32(ops)
-        progs = (_lib.JJSweep * Ccl)(*[self._sweep_struct(sw) for sw in plan.prog])
+        def rank_stream(ps):
+            r = _lib.JJRankStream()
+            r.n_levels, r.n_warps, r.n_tiles = ps["n_levels"], ps["n_warps"], len(ps["thdr"])
+            r.wt_ptr, r.ws_ptr = _lib.i32(ps["wt_ptr"]), _lib.i32(ps["ws_ptr"])
+            ps["_thdr_c"] = np.ascontiguousarray(ps["thdr"], dtype=np.int32)
+            r.thdr = _lib.i32(ps["_thdr_c"])
+            r.n_steps = ps["n_steps"]
+            r.stream = ps["stream"].ctypes.data_as(C.POINTER(C.c_uint8))
+            return r
+        progs = (_lib.JJRankStream * Ccl)(*[rank_stream(ps) for ps in plan.prog])
         p.prog = progs
         fp = np.ascontiguousarray(rt.face_ptr); ff = np.ascontiguousarray(rt.face_fidx)
         p.junc_ptr, p.junc_orig = _lib.i32(rt.junc_ptr), _lib.i32(rt.junc_orig)

@@ -221,6 +221,111 @@ def pack_levels(levels, row_map=None, col_map=None):
                 stage_rows=int(stage_rows), nnz=int(nnz))
 
 
+RES_WARPS = 16          # warps per thread block of the resident kernel
+STEP_BYTES = 320        # one stream step: 32 float64 values + 32 uint16 shared-memory rows
+
+
+def pack_warp_streams(levels, row_map, col_map, n_warps=RES_WARPS):
+    """
+    Resident-engine packing. Every (level, warp) pair gets a contiguous *stream*: the tiles assigned to
+    that warp (longest-first balancing), their values and column rows interleaved step by step
+    ([32 float64][32 uint16] = 320 bytes per step), so a warp prefetches straight through tile boundaries.
+    A tile header is two int32: row0 | (nrows-1) << 16 | log2(lanes per row) << 21 | flags << 24, and
+    nsteps | stage_off << 16.
+    """
+    n_levels = len(levels)
+    wt_ptr = np.zeros(n_levels * n_warps + 1, dtype=np.int32)
+    ws_ptr = np.zeros(n_levels * n_warps + 1, dtype=np.int32)
+    hdr, chunks = [], []
+    n_steps = 0
+    stage_rows = 0
+    for li, lev in enumerate(levels):
+        tiles = [t for g in lev for t in g]
+        # longest processing time first onto the least loaded warp
+        cost = []
+        for (r0, V, cols, fl) in tiles:
+            nr, nc = V.shape
+            nrp = 1
+            while nrp < nr:
+                nrp *= 2
+            m = 32 // nrp
+            cost.append((nc + m - 1) // m + 3)
+        order = np.argsort(-np.asarray(cost), kind="stable") if tiles else []
+        load = np.zeros(n_warps)
+        assign = [[] for _ in range(n_warps)]
+        for ti in order:
+            w = int(np.argmin(load))
+            assign[w].append(ti)
+            load[w] += cost[ti]
+        staged = 0
+        stage_off = {}
+        for ti, (r0, V, cols, fl) in enumerate(tiles):
+            if fl & TILE_STAGED:
+                stage_off[ti] = staged
+                staged += V.shape[0]
+        stage_rows = max(stage_rows, staged)
+        for w in range(n_warps):
+            for ti in assign[w]:
+                r0, V, cols, fl = tiles[ti]
+                nr, nc = V.shape
+                nrp = 1
+                while nrp < nr:
+                    nrp *= 2
+                m = 32 // nrp
+                st = (nc + m - 1) // m
+                Vp = np.zeros((nrp, st * m))
+                Vp[:nr, :nc] = V
+                cm = col_map[np.asarray(cols, dtype=np.int64)]
+                assert np.all(cm >= 0) and np.all(cm < 65536)
+                cp = np.zeros(st * m, dtype=np.int64)
+                cp[:nc] = cm
+                cp[nc:] = cm[-1]
+                vals = Vp.reshape(nrp, st, m).transpose(1, 0, 2).reshape(st, 32)
+                lane_cols = np.broadcast_to(cp.reshape(st, 1, m), (st, nrp, m)).reshape(st, 32).astype(np.uint16)
+                rec = np.zeros((st, STEP_BYTES), dtype=np.uint8)
+                rec[:, :256] = np.ascontiguousarray(vals).view(np.uint8).reshape(st, 256)
+                rec[:, 256:] = np.ascontiguousarray(lane_cols).view(np.uint8).reshape(st, 64)
+                chunks.append(rec)
+                row = int(row_map[r0])
+                assert 0 <= row < 65536 and st < 65536
+                mshift = int(np.log2(m))
+                hdr.append((row | ((nr - 1) << 16) | (mshift << 21) | (fl << 24), st | (stage_off.get(ti, 0) << 16)))
+                n_steps += st
+            wt_ptr[li * n_warps + w + 1] = len(hdr)
+            ws_ptr[li * n_warps + w + 1] = n_steps
+    stream = np.concatenate(chunks).ravel() if chunks else np.zeros(0, dtype=np.uint8)
+    return dict(n_levels=n_levels, n_warps=n_warps, wt_ptr=wt_ptr, ws_ptr=ws_ptr,
+                thdr=np.asarray(hdr, dtype=np.int32).reshape(-1, 2), stream=stream, n_steps=n_steps,
+                stage_rows=int(stage_rows), vals=n_steps * 32)
+
+
+def _run_stream_level(ps, v, level):
+    """Host interpreter of one level of a warp-stream program (mirrors the device kernel)."""
+    nw = ps["n_warps"]
+    out = []
+    rec = ps["stream"].reshape(-1, STEP_BYTES)
+    for w in range(nw):
+        idx = level * nw + w
+        s = ps["ws_ptr"][idx]
+        for t in range(ps["wt_ptr"][idx], ps["wt_ptr"][idx + 1]):
+            h0, h1 = int(ps["thdr"][t, 0]), int(ps["thdr"][t, 1])
+            row0, nr, mshift, fl = h0 & 0xffff, ((h0 >> 16) & 31) + 1, (h0 >> 21) & 7, (h0 >> 24) & 3
+            st = h1 & 0xffff
+            m = 1 << mshift
+            vals = rec[s:s + st, :256].copy().view(np.float64).reshape(st, 32)
+            cols = rec[s:s + st, 256:].copy().view(np.uint16).reshape(st, 32).astype(np.int64)
+            s += st
+            prod = vals[(...,) + (None,) * (v.ndim - 1)] * v[cols]          # (st, 32, ...)
+            lane_sum = prod.sum(axis=0)                                      # (32, ...)
+            acc = lane_sum.reshape((32 // m, m) + v.shape[1:]).sum(axis=1)[:nr]
+            if fl & TILE_SELF:
+                acc = acc + v[row0:row0 + nr]
+            out.append((row0, nr, acc))
+        assert s == ps["ws_ptr"][idx + 1]
+    for (row0, nr, acc) in out:
+        v[row0:row0 + nr] = acc
+
+
 class SolveProgram:
     """Streaming packing of the factor: perm (new-to-old faces) and sweeps['fwd'|'bwd'] (see pack_levels)."""
 
@@ -401,7 +506,7 @@ def resident_plan(F, C, want_tasks=16):
             tr = tr_for(blocks)
             level([[t] for b in blocks for t in a_tiles(F, b, tr, F.LoffT)], False)
             level([b_tiles(F, b, tr, True) for b in blocks], True)
-        plan.prog.append(pack_levels(levels, row_map=smem_index[r], col_map=smem_index[r]))
+        plan.prog.append(pack_warp_streams(levels, row_map=smem_index[r], col_map=smem_index[r]))
         rops = np.array(rops, dtype=np.int32).reshape(-1, 4)
         if ops is None:
             ops, plan.n_fwd_ops = rops, n_fwd
@@ -413,7 +518,7 @@ def resident_plan(F, C, want_tasks=16):
     plan.ops = ops
     plan.stage_rows = max(p["stage_rows"] for p in plan.prog)
     plan.allreduce_rows = max([hi - lo for (lo, hi) in sh_range.values()] + [0])
-    plan.vals = [int(p["vals"].size) for p in plan.prog]
+    plan.vals = [int(p["vals"]) for p in plan.prog]
     return plan
 
 
@@ -437,7 +542,7 @@ def apply_resident_plan_host(F, plan, b_perm):
     for op in plan.ops:
         if op[0] == OP_LEVEL:
             for r in range(C):
-                _run_packed(plan.prog[r], vec[r], levels=[op[1]])
+                _run_stream_level(plan.prog[r], vec[r], int(op[1]))
         else:
             lo, hi = op[1], op[2]
             tot = sum(vec[r][lo:hi] for r in range(C))

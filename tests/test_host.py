@@ -219,12 +219,13 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     # struct layouts of the ctypes mirror equal the C compiler's
     import subprocess, tempfile
-    src = '#include <stdio.h>\n#include "jjstep.h"\nint main(){printf("%zu %zu %zu", sizeof(JJSweep), sizeof(JJCircuit), sizeof(JJStats));return 0;}'
+    src = '#include <stdio.h>\n#include "jjstep.h"\nint main(){printf("%zu %zu %zu %zu %zu", sizeof(JJSweep), sizeof(JJCircuit), sizeof(JJStats), sizeof(JJRankStream), sizeof(JJResidentPlan));return 0;}'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "s.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o", os.path.join(d, "s")])
         sizes = [int(v) for v in subprocess.check_output([os.path.join(d, "s")]).split()]
-    assert sizes == [ctypes.sizeof(_lib.JJSweep), ctypes.sizeof(_lib.JJCircuit), ctypes.sizeof(_lib.JJStats)]
+    assert sizes == [ctypes.sizeof(_lib.JJSweep), ctypes.sizeof(_lib.JJCircuit), ctypes.sizeof(_lib.JJStats),
+                     ctypes.sizeof(_lib.JJRankStream), ctypes.sizeof(_lib.JJResidentPlan)]
 
 
 def test_no_gpu_means_loud_failure():
