@@ -82,7 +82,8 @@ typedef struct {
     int32_t n_rows;                  /* rows of each block's shared-memory vector */
     int32_t stage_rows, allreduce_rows;
     int32_t n_ops, n_fwd_ops;
-    const int32_t *ops;              /* [n_ops][4]: (0, level, staged, 0) | (1, row_lo, row_hi, 0) */
+    const int32_t *ops;              /* [C][n_ops][4]: (0, level, staged rows, 0) | (1, row_lo, row_hi, 0); same
+                                        op kinds on every rank */
     const JJRankStream *prog;        /* [C] tiles of rank r; a level op names a level of this program */
     const int32_t *junc_ptr;         /* [C+1] rank r owns device junctions junc_ptr[r]:junc_ptr[r+1] */
     const int32_t *junc_orig;        /* [Nj] original junction index of each device junction */

@@ -149,13 +149,14 @@ __device__ void exec_level(const RankProg& p, Cursor& cu, int staged, int next_l
         const int nb = min(32, t1 - tb);
         for (int k = 0; k < nb; ++k) {
             const int h0 = __shfl_sync(0xffffffffu, myh.x, k), h1 = __shfl_sync(0xffffffffu, myh.y, k);
-            const int row0 = h0 & 0xffff, nrows = ((h0 >> 16) & 31) + 1, mshift = (h0 >> 21) & 7, flags = (h0 >> 24) & 3;
+            const int nrows = (h0 & 31) + 1, mshift = (h0 >> 5) & 7, flags = (h0 >> 8) & 3;
             const int nsteps = h1 & 0xffff, stage_off = (h1 >> 16) & 0xffff;
             const int m = 1 << mshift;
             const int i = lane >> mshift, sub = lane & (m - 1);
             double acc[WT];
 #pragma unroll
             for (int q = 0; q < WT; ++q) acc[q] = 0.0;
+            int out_row = 0xffff;
             for (int j = 0; j < nsteps; ++j) {
                 const double a = ra[0];
                 const int c = rc[0];
@@ -167,6 +168,7 @@ __device__ void exec_level(const RankProg& p, Cursor& cu, int staged, int next_l
                     rc[RING - 1] = __ldg(reinterpret_cast<const unsigned short*>(rec + 256) + lane);
                 }
                 ++s;
+                if (j == 0) { out_row = c; continue; }      // first step of a tile: the output row of every lane
                 const double2* src = reinterpret_cast<const double2*>(v + (size_t)c * WT);
                 const int f = swz<WT>(c);
 #pragma unroll
@@ -181,10 +183,9 @@ __device__ void exec_level(const RankProg& p, Cursor& cu, int staged, int next_l
                 for (int q = 0; q < WT; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], off);
             }
             __syncwarp();
-            if (sub == 0 && i < nrows) {
-                const int row = row0 + i;
-                const int f = swz<WT>(row);
-                double2* self = reinterpret_cast<double2*>(v + (size_t)row * WT);
+            if (sub == 0 && i < nrows && out_row != 0xffff) {
+                const int f = swz<WT>(out_row);
+                double2* self = reinterpret_cast<double2*>(v + (size_t)out_row * WT);
                 if (flags & 1) {
 #pragma unroll
                     for (int q = 0; q < WT / 2; ++q) {
@@ -192,29 +193,29 @@ __device__ void exec_level(const RankProg& p, Cursor& cu, int staged, int next_l
                         acc[2 * q] += sv.x; acc[2 * q + 1] += sv.y;
                     }
                 }
-                // staged results are stored in the physical layout of the destination row
-                double2* dst = (flags & 2) ? reinterpret_cast<double2*>(stage + (size_t)(stage_off + i) * WT) : self;
+                if (flags & 2) {
+                    // staged: keep the destination row with the data (physical layout of the destination row)
+                    double2* dst = reinterpret_cast<double2*>(stage + (size_t)(stage_off + i) * (WT + 2));
 #pragma unroll
-                for (int q = 0; q < WT / 2; ++q) dst[q ^ f] = make_double2(acc[2 * q], acc[2 * q + 1]);
+                    for (int q = 0; q < WT / 2; ++q) dst[q ^ f] = make_double2(acc[2 * q], acc[2 * q + 1]);
+                    reinterpret_cast<int*>(dst + WT / 2)[0] = out_row;
+                } else {
+#pragma unroll
+                    for (int q = 0; q < WT / 2; ++q) self[q ^ f] = make_double2(acc[2 * q], acc[2 * q + 1]);
+                }
             }
             __syncwarp();
         }
     }
     if (next_level >= 0) cursor_open(cu, p, next_level);
     __syncthreads();
-    if (staged) {
-        for (int tb = t0; tb < t1; tb += 32) {
-            int2 myh = make_int2(0, 0);
-            if (tb + lane < t1) myh = __ldg(p.thdr + tb + lane);
-            const int nb = min(32, t1 - tb);
-            for (int k = 0; k < nb; ++k) {
-                const int h0 = __shfl_sync(0xffffffffu, myh.x, k), h1 = __shfl_sync(0xffffffffu, myh.y, k);
-                if ((h0 >> 24) & 2) {
-                    const int row0 = h0 & 0xffff, nrows = ((h0 >> 16) & 31) + 1, stage_off = (h1 >> 16) & 0xffff;
-                    for (int e = lane; e < nrows * WT; e += 32)
-                        v[(size_t)row0 * WT + e] = stage[(size_t)stage_off * WT + e];
-                }
-            }
+    if (staged > 0) {
+        // copy the staged rows (each carries its destination row) back into the vector
+        for (int e = threadIdx.x; e < staged * (WT / 2); e += NT) {
+            const int r = e / (WT / 2), q = e % (WT / 2);
+            const double2* srow = reinterpret_cast<const double2*>(stage + (size_t)r * (WT + 2));
+            const int dst_row = reinterpret_cast<const int*>(srow + WT / 2)[0];
+            reinterpret_cast<double2*>(v + (size_t)dst_row * WT)[q] = srow[q];
         }
         __syncthreads();
     }
@@ -254,12 +255,12 @@ __device__ void run_ops(const ResArgs& a, cg::cluster_group& cluster, int rank, 
     Cursor cu;
     bool open = false;
     for (int o = 0; o < a.n_ops; ++o) {
-        const int4 op = __ldg(a.ops + o);
+        const int4 op = __ldg(a.ops + (size_t)rank * a.n_ops + o);
         if (op.x == 0) {
             if (!open) cursor_open(cu, p, op.y);
             int next = -1;                       // the next level op, looking past an all-reduce
             for (int o2 = o + 1; o2 < a.n_ops && o2 <= o + 2; ++o2) {
-                const int4 nx = __ldg(a.ops + o2);
+                const int4 nx = __ldg(a.ops + (size_t)rank * a.n_ops + o2);
                 if (nx.x == 0) { next = nx.y; break; }
             }
             exec_level<WT>(p, cu, op.z, next, v, stage);
@@ -438,7 +439,7 @@ __global__ void __launch_bounds__(NT, 1) k_resident(const ResArgs a) {
     extern __shared__ __align__(16) double smem[];
     double* v = smem;
     double* stage = v + (size_t)a.n_rows * WT;
-    double* mbox = stage + (size_t)a.stage_rows * WT;
+    double* mbox = stage + (size_t)a.stage_rows * (WT + 2);
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = CL ? (int)cluster.block_rank() : 0;
     const int cluster_id = blockIdx.x / a.C;
@@ -560,7 +561,7 @@ int resident_set_plan(JJHandle* h, const JJResidentPlan* pl) {
     st->ar_rows = pl->allreduce_rows; st->n_ops = pl->n_ops;
     const int Nj = h->cir.Nj;
     int rc;
-    if ((rc = up(h, st, (int**)&st->ops, pl->ops, (size_t)pl->n_ops * 4))) return rc;
+    if ((rc = up(h, st, (int**)&st->ops, pl->ops, (size_t)pl->C * pl->n_ops * 4))) return rc;
     for (int r = 0; r < pl->C; ++r) {
         const JJRankStream& ps = pl->prog[r];
         if (ps.n_warps != NWARPS) { h->err = "resident plan: program packed for a different warp count"; return JJ_EINVAL; }
@@ -590,7 +591,7 @@ int resident_set_plan(JJHandle* h, const JJResidentPlan* pl) {
     k_recip<<<(Nj + 255) / 256, 256, 0, h->stream>>>(Nj, h->cir.c0, st->ic0);
     h->launches++;
     RCK(cudaStreamSynchronize(h->stream));
-    st->smem_bytes = ((size_t)st->n_rows + st->stage_rows + st->ar_rows + 8 * st->C) * st->WT * sizeof(double);
+    st->smem_bytes = (((size_t)st->n_rows + st->ar_rows + 8 * st->C) * st->WT + (size_t)st->stage_rows * (st->WT + 2)) * sizeof(double);
     return JJ_OK;
 }
 

@@ -98,7 +98,7 @@ class CircuitTables:
     SMEM_LIMIT = 227 * 1024
 
     def resident_smem_bytes(self, plan, Wt):
-        return (plan.n_rows + plan.stage_rows + plan.allreduce_rows + 8 * plan.C) * Wt * 8
+        return ((plan.n_rows + plan.allreduce_rows + 8 * plan.C) * Wt + plan.stage_rows * (Wt + 2)) * 8
 
     def choose_resident(self, W):
         """Pick (cluster size, problems per tile) for the resident engine, or None if the right-hand sides
@@ -282,7 +282,7 @@ class DeviceEngine:
         p.C, p.tile_problems, p.n_rows = Ccl, Wt, plan.n_rows
         p.stage_rows, p.allreduce_rows = plan.stage_rows, plan.allreduce_rows
         ops = np.ascontiguousarray(plan.ops, dtype=np.int32)
-        p.n_ops, p.n_fwd_ops, p.ops = len(ops), plan.n_fwd_ops, _lib.i32(ops)
+        p.n_ops, p.n_fwd_ops, p.ops = ops.shape[1], plan.n_fwd_ops, _lib.i32(ops)
         def rank_stream(ps):
             r = _lib.JJRankStream()
             r.n_levels, r.n_warps, r.n_tiles = ps["n_levels"], ps["n_warps"], len(ps["thdr"])

@@ -223,80 +223,168 @@ def pack_levels(levels, row_map=None, col_map=None):
 
 RES_WARPS = 16          # warps per thread block of the resident kernel
 STEP_BYTES = 320        # one stream step: 32 float64 values + 32 uint16 shared-memory rows
+NO_ROW = 0xFFFF
 
 
-def pack_warp_streams(levels, row_map, col_map, n_warps=RES_WARPS):
+def a_rows(F, blocks, M, col_mask=None):
+    """Phase-a row tasks of the given blocks: (permuted row, cols, vals) with out = src[row] + sum vals*src[cols]."""
+    out = []
+    for b in blocks:
+        for g in range(int(F.bptr[b]), int(F.bptr[b + 1])):
+            lo, hi = M.indptr[g], M.indptr[g + 1]
+            cols, vals = M.indices[lo:hi], -M.data[lo:hi]
+            if col_mask is not None:
+                keep = col_mask[cols]
+                cols, vals = cols[keep], vals[keep]
+            if cols.size:
+                out.append((g, cols.astype(np.int64), vals))
+    return out
+
+
+def b_blocks(F, blocks, transpose):
+    """Phase-b block tasks: (first permuted row, dense triangular matrix to apply to the block's own rows)."""
+    return [(int(F.bptr[b]), F.dinv[b].T if transpose else F.dinv[b]) for b in blocks]
+
+
+def _lpt(costs, n_warps):
+    """Longest-processing-time assignment; returns (lists of item indices per warp, makespan)."""
+    load = np.zeros(n_warps)
+    assign = [[] for _ in range(n_warps)]
+    for i in np.argsort(-np.asarray(costs), kind="stable") if len(costs) else []:
+        w = int(np.argmin(load))
+        assign[w].append(int(i))
+        load[w] += costs[i]
+    return assign, float(load.max()) if len(costs) else 0.0
+
+
+def _tile_cost(steps, m):
+    return steps + 3 + 2 * int(np.log2(m))
+
+
+def _tiles_a(rows, m):
+    """Group phase-a rows (sorted by length) into tiles of 32/m rows."""
+    P = 32 // m
+    order = sorted(range(len(rows)), key=lambda i: -rows[i][1].size)
+    tiles = []
+    for k in range(0, len(order), P):
+        grp = [rows[i] for i in order[k:k + P]]
+        tiles.append(dict(m=m, flags=TILE_SELF, rows=[(g, c, v) for (g, c, v) in grp]))
+    return tiles
+
+
+def _tiles_b(blocks, m, transpose):
+    """Phase-b tiles: whole small blocks are packed together (updated in place by one warp), blocks with
+    more rows than a tile holds are cut into row groups that write through the staging buffer."""
+    P = 32 // m
+    tiles = []
+    small = sorted([b for b in blocks if b[1].shape[0] <= P], key=lambda b: -b[1].shape[0])
+    bins = []
+    for (r0, D) in small:
+        k = D.shape[0]
+        for bn in bins:
+            if bn["free"] >= k:
+                break
+        else:
+            bn = dict(free=P, rows=[])
+            bins.append(bn)
+        bn["free"] -= k
+        for i in range(k):
+            c0, c1 = (i, k) if transpose else (0, i + 1)
+            bn["rows"].append((r0 + i, np.arange(r0 + c0, r0 + c1), D[i, c0:c1]))
+    for bn in bins:
+        tiles.append(dict(m=m, flags=0, rows=bn["rows"]))
+    for (r0, D) in blocks:
+        k = D.shape[0]
+        if k <= P:
+            continue
+        for t0 in range(0, k, P):
+            rows = []
+            for i in range(t0, min(k, t0 + P)):
+                c0, c1 = (i, k) if transpose else (0, i + 1)
+                rows.append((r0 + i, np.arange(r0 + c0, r0 + c1), D[i, c0:c1]))
+            tiles.append(dict(m=m, flags=TILE_STAGED, rows=rows))
+    return tiles
+
+
+def _tile_steps(t):
+    m = t["m"]
+    return 1 + max((r[1].size + m - 1) // m for r in t["rows"])
+
+
+def plan_level(kind, items, transpose, n_warps):
+    """Choose the lanes-per-row m that minimises the slowest warp's time and return (tiles, assignment)."""
+    best = None
+    for m in (1, 2, 4, 8, 16, 32):
+        tiles = _tiles_a(items, m) if kind == "a" else _tiles_b(items, m, transpose)
+        costs = [_tile_cost(_tile_steps(t), m) for t in tiles]
+        assign, span = _lpt(costs, n_warps)
+        if best is None or span < best[0]:
+            best = (span, tiles, assign)
+    return best[1], best[2]
+
+
+def pack_ell_streams(level_specs, row_map, col_map, n_warps=RES_WARPS):
     """
-    Resident-engine packing. Every (level, warp) pair gets a contiguous *stream*: the tiles assigned to
-    that warp (longest-first balancing), their values and column rows interleaved step by step
-    ([32 float64][32 uint16] = 320 bytes per step), so a warp prefetches straight through tile boundaries.
-    A tile header is two int32: row0 | (nrows-1) << 16 | log2(lanes per row) << 21 | flags << 24, and
-    nsteps | stage_off << 16.
+    Resident-engine packing. level_specs: list of (kind 'a'|'b', items, transpose) per level, items from
+    a_rows / b_blocks. Every (level, warp) pair gets a contiguous *stream* of 320-byte steps
+    ([32 float64 values][32 uint16 shared-memory rows], one per lane) through which the warp prefetches
+    straight across tile boundaries. A tile is 32/m output rows x m lanes per row; its first step carries the
+    output row of every lane (0xFFFF: none), the following steps one (value, source row) pair per lane.
+    Header: two int32 = (nrows-1) | log2(m) << 5 | flags << 8 , nsteps | stage_off << 16.
     """
-    n_levels = len(levels)
+    n_levels = len(level_specs)
     wt_ptr = np.zeros(n_levels * n_warps + 1, dtype=np.int32)
     ws_ptr = np.zeros(n_levels * n_warps + 1, dtype=np.int32)
     hdr, chunks = [], []
-    n_steps = 0
-    stage_rows = 0
-    for li, lev in enumerate(levels):
-        tiles = [t for g in lev for t in g]
-        # longest processing time first onto the least loaded warp
-        cost = []
-        for (r0, V, cols, fl) in tiles:
-            nr, nc = V.shape
-            nrp = 1
-            while nrp < nr:
-                nrp *= 2
-            m = 32 // nrp
-            cost.append((nc + m - 1) // m + 3)
-        order = np.argsort(-np.asarray(cost), kind="stable") if tiles else []
-        load = np.zeros(n_warps)
-        assign = [[] for _ in range(n_warps)]
-        for ti in order:
-            w = int(np.argmin(load))
-            assign[w].append(ti)
-            load[w] += cost[ti]
+    n_steps = stage_rows = n_vals = 0
+    staged_levels = []
+    for li, (kind, items, transpose) in enumerate(level_specs):
+        tiles, assign = plan_level(kind, items, transpose, n_warps) if items else ([], [[] for _ in range(n_warps)])
         staged = 0
-        stage_off = {}
-        for ti, (r0, V, cols, fl) in enumerate(tiles):
-            if fl & TILE_STAGED:
-                stage_off[ti] = staged
-                staged += V.shape[0]
+        for t in tiles:
+            if t["flags"] & TILE_STAGED:
+                t["stage_off"] = staged
+                staged += len(t["rows"])
         stage_rows = max(stage_rows, staged)
+        staged_levels.append(int(staged))
         for w in range(n_warps):
             for ti in assign[w]:
-                r0, V, cols, fl = tiles[ti]
-                nr, nc = V.shape
-                nrp = 1
-                while nrp < nr:
-                    nrp *= 2
-                m = 32 // nrp
-                st = (nc + m - 1) // m
-                Vp = np.zeros((nrp, st * m))
-                Vp[:nr, :nc] = V
-                cm = col_map[np.asarray(cols, dtype=np.int64)]
-                assert np.all(cm >= 0) and np.all(cm < 65536)
-                cp = np.zeros(st * m, dtype=np.int64)
-                cp[:nc] = cm
-                cp[nc:] = cm[-1]
-                vals = Vp.reshape(nrp, st, m).transpose(1, 0, 2).reshape(st, 32)
-                lane_cols = np.broadcast_to(cp.reshape(st, 1, m), (st, nrp, m)).reshape(st, 32).astype(np.uint16)
+                t = tiles[ti]
+                m = t["m"]
+                P = 32 // m
+                st = _tile_steps(t)
+                vals = np.zeros((st, 32))
+                cols = np.zeros((st, 32), dtype=np.uint16)
+                cols[0, :] = NO_ROW
+                for i, (g, c, v) in enumerate(t["rows"]):
+                    lanes = slice(i * m, (i + 1) * m)
+                    out_row = int(row_map[g])
+                    assert 0 <= out_row < NO_ROW
+                    cols[0, lanes] = out_row
+                    cm = col_map[np.asarray(c, dtype=np.int64)]
+                    assert np.all(cm >= 0) and np.all(cm < NO_ROW)
+                    n = cm.size
+                    ns = (n + m - 1) // m
+                    pc = np.zeros(ns * m, dtype=np.int64); pv = np.zeros(ns * m)
+                    pc[:n] = cm; pv[:n] = v
+                    pc[n:] = cm[-1]
+                    cols[1:1 + ns, lanes] = pc.reshape(ns, m)
+                    vals[1:1 + ns, lanes] = pv.reshape(ns, m)
+                    n_vals += n
                 rec = np.zeros((st, STEP_BYTES), dtype=np.uint8)
-                rec[:, :256] = np.ascontiguousarray(vals).view(np.uint8).reshape(st, 256)
-                rec[:, 256:] = np.ascontiguousarray(lane_cols).view(np.uint8).reshape(st, 64)
+                rec[:, :256] = vals.view(np.uint8).reshape(st, 256)
+                rec[:, 256:] = cols.view(np.uint8).reshape(st, 64)
                 chunks.append(rec)
-                row = int(row_map[r0])
-                assert 0 <= row < 65536 and st < 65536
-                mshift = int(np.log2(m))
-                hdr.append((row | ((nr - 1) << 16) | (mshift << 21) | (fl << 24), st | (stage_off.get(ti, 0) << 16)))
+                assert st < 65536
+                hdr.append(((len(t["rows"]) - 1) | (int(np.log2(m)) << 5) | (t["flags"] << 8),
+                            st | (t.get("stage_off", 0) << 16)))
                 n_steps += st
             wt_ptr[li * n_warps + w + 1] = len(hdr)
             ws_ptr[li * n_warps + w + 1] = n_steps
     stream = np.concatenate(chunks).ravel() if chunks else np.zeros(0, dtype=np.uint8)
     return dict(n_levels=n_levels, n_warps=n_warps, wt_ptr=wt_ptr, ws_ptr=ws_ptr,
                 thdr=np.asarray(hdr, dtype=np.int32).reshape(-1, 2), stream=stream, n_steps=n_steps,
-                stage_rows=int(stage_rows), vals=n_steps * 32)
+                stage_rows=int(stage_rows), vals=int(n_vals), staged_rows=staged_levels)
 
 
 def _run_stream_level(ps, v, level):
@@ -309,21 +397,22 @@ def _run_stream_level(ps, v, level):
         s = ps["ws_ptr"][idx]
         for t in range(ps["wt_ptr"][idx], ps["wt_ptr"][idx + 1]):
             h0, h1 = int(ps["thdr"][t, 0]), int(ps["thdr"][t, 1])
-            row0, nr, mshift, fl = h0 & 0xffff, ((h0 >> 16) & 31) + 1, (h0 >> 21) & 7, (h0 >> 24) & 3
+            nr, mshift, fl = (h0 & 31) + 1, (h0 >> 5) & 7, (h0 >> 8) & 3
             st = h1 & 0xffff
             m = 1 << mshift
             vals = rec[s:s + st, :256].copy().view(np.float64).reshape(st, 32)
             cols = rec[s:s + st, 256:].copy().view(np.uint16).reshape(st, 32).astype(np.int64)
             s += st
-            prod = vals[(...,) + (None,) * (v.ndim - 1)] * v[cols]          # (st, 32, ...)
-            lane_sum = prod.sum(axis=0)                                      # (32, ...)
+            rows = cols[0, ::m][:nr]
+            prod = vals[1:][(...,) + (None,) * (v.ndim - 1)] * v[cols[1:]]    # (st-1, 32, ...)
+            lane_sum = prod.sum(axis=0)
             acc = lane_sum.reshape((32 // m, m) + v.shape[1:]).sum(axis=1)[:nr]
             if fl & TILE_SELF:
-                acc = acc + v[row0:row0 + nr]
-            out.append((row0, nr, acc))
+                acc = acc + v[rows]
+            out.append((rows, acc))
         assert s == ps["ws_ptr"][idx + 1]
-    for (row0, nr, acc) in out:
-        v[row0:row0 + nr] = acc
+    for (rows, acc) in out:
+        v[rows] = acc
 
 
 class SolveProgram:
@@ -471,51 +560,49 @@ def resident_plan(F, C, want_tasks=16):
     plan.smem_index, plan.row_rank, plan.col_owner = smem_index, row_rank, col_owner
     plan.prog, ops = [], None
     for r in range(C):
-        levels, rops = [], []
+        specs, rops = [], []
 
-        def level(groups, staged_possible):
-            levels.append(groups)
-            staged = int(any(t[3] & TILE_STAGED for g in groups for t in g))
-            rops.append((OP_LEVEL, len(levels) - 1, staged, 0))
+        def level(kind, items, transpose=False):
+            specs.append((kind, items, transpose))
+            rops.append([OP_LEVEL, len(specs) - 1, 0, 0])
 
         # ---- forward: local subtree bottom-up
         for h in range(Hloc + 1):
             blocks = [b for b in local_blocks[r] if F.height[b] == h]
-            tr = tr_for(blocks)
             if h > 0:
-                level([[t] for b in blocks for t in a_tiles(F, b, tr, F.Loff)], False)
-            level([b_tiles(F, b, tr, False) for b in blocks], True)
+                level("a", a_rows(F, blocks, F.Loff))
+            level("b", b_blocks(F, blocks, False), False)
         # ---- forward: replicated separators bottom-up, partial sums + all-reduce
         for h in sh_heights:
             blocks = [b for b in sh_blocks if F.height[b] == h]
-            tr = tr_for(blocks)
-            mask = col_owner == r
-            level([[t] for b in blocks for t in a_tiles(F, b, tr, F.Loff, col_mask=mask)], False)
-            rops.append((OP_ALLREDUCE, sh_range[h][0], sh_range[h][1], 0))
-            level([b_tiles(F, b, tr, False) for b in blocks], True)
+            level("a", a_rows(F, blocks, F.Loff, col_mask=(col_owner == r)))
+            rops.append([OP_ALLREDUCE, sh_range[h][0], sh_range[h][1], 0])
+            level("b", b_blocks(F, blocks, False), False)
         n_fwd = len(rops)
         # ---- backward: replicated separators top-down (computed redundantly by every rank)
         for h in reversed(sh_heights):
             blocks = [b for b in sh_blocks if F.height[b] == h]
-            tr = tr_for(blocks)
-            level([[t] for b in blocks for t in a_tiles(F, b, tr, F.LoffT)], False)
-            level([b_tiles(F, b, tr, True) for b in blocks], True)
+            level("a", a_rows(F, blocks, F.LoffT))
+            level("b", b_blocks(F, blocks, True), True)
         # ---- backward: local subtree top-down
         for h in range(Hloc, -1, -1):
             blocks = [b for b in local_blocks[r] if F.height[b] == h]
-            tr = tr_for(blocks)
-            level([[t] for b in blocks for t in a_tiles(F, b, tr, F.LoffT)], False)
-            level([b_tiles(F, b, tr, True) for b in blocks], True)
-        plan.prog.append(pack_warp_streams(levels, row_map=smem_index[r], col_map=smem_index[r]))
+            level("a", a_rows(F, blocks, F.LoffT))
+            level("b", b_blocks(F, blocks, True), True)
+        ps = pack_ell_streams(specs, row_map=smem_index[r], col_map=smem_index[r])
+        plan.prog.append(ps)
+        for op in rops:
+            if op[0] == OP_LEVEL:
+                op[2] = ps["staged_rows"][op[1]]        # number of staged rows of the level (0: none)
         rops = np.array(rops, dtype=np.int32).reshape(-1, 4)
         if ops is None:
             ops, plan.n_fwd_ops = rops, n_fwd
         else:
-            # identical structure on every rank (only the staged hint may differ: take the union)
+            # identical structure on every rank; the staged-row count of a level is per rank
             assert np.array_equal(ops[:, [0, 1]], rops[:, [0, 1]])
             assert np.array_equal(ops[ops[:, 0] == OP_ALLREDUCE], rops[rops[:, 0] == OP_ALLREDUCE])
-            ops[:, 2] = np.where(ops[:, 0] == OP_LEVEL, np.maximum(ops[:, 2], rops[:, 2]), ops[:, 2])
-    plan.ops = ops
+        plan.rank_ops = getattr(plan, "rank_ops", []) + [rops]
+    plan.ops = np.stack(plan.rank_ops)            # (C, n_ops, 4)
     plan.stage_rows = max(p["stage_rows"] for p in plan.prog)
     plan.allreduce_rows = max([hi - lo for (lo, hi) in sh_range.values()] + [0])
     plan.vals = [int(p["vals"]) for p in plan.prog]
@@ -539,7 +626,7 @@ def apply_resident_plan_host(F, plan, b_perm):
         w = w / w.sum()
         for r in range(C):
             vec[r][plan.smem_index[r][sh]] = w[r] * b_perm[sh]
-    for op in plan.ops:
+    for op in plan.ops[0]:
         if op[0] == OP_LEVEL:
             for r in range(C):
                 _run_stream_level(plan.prog[r], vec[r], int(op[1]))
