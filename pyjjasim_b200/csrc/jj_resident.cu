@@ -18,6 +18,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "jj_host.h"
@@ -36,6 +37,13 @@ struct RankProg {
     const int* ws_ptr;            // [n_levels * NWARPS + 1] -> stream steps
     const int2* thdr;             // packed tile headers
     const unsigned char* stream;  // [n_steps][320]
+    int n_levels, n_tiles;
+};
+
+// The level cursors and tile headers of this rank's program are copied into shared memory once per
+// kernel (they are the same for every tile of problems and every time step).
+struct ProgSmem {
+    const int* wt_ptr; const int* ws_ptr; const int2* thdr;
 };
 
 struct ResArgs {
@@ -47,7 +55,8 @@ struct ResArgs {
     const int* face_ptr; const int* face_junc; const signed char* face_sign; const int* face_fidx;
     // circuit
     int Nj, Nf;
-    const double *Ic, *ic0, *c1, *c2;
+    const double *P0;              // [Nj'][4] = Ic, 1/c0, c1, c2 in device junction order
+    const double *P1;              // [Nj'][4] = Is base, noise base, Vs base, 0
     Cpr cpr;
     // problem
     int Wp, n_tiles;
@@ -65,6 +74,7 @@ struct ResArgs {
     int* flag;
     // debug solve
     const double* dbg_b; double* dbg_J;   // canonical [Nf][Wp], permuted faces
+    int dbg_skip;                         // timing experiments only (JJ_RES_DEBUG): 1 skip sweeps, 2 skip junction pass, 4 skip face pass
 };
 
 struct ResidentState {
@@ -75,12 +85,12 @@ struct ResidentState {
     std::vector<size_t> alloc_bytes;
     int *junc_ptr = nullptr, *junc_orig = nullptr; int2* junc_row = nullptr; char2* junc_sign = nullptr;
     int *face_ptr = nullptr, *face_junc = nullptr; signed char* face_sign = nullptr; int* face_fidx = nullptr;
-    double* ic0 = nullptr;
+    double *P0 = nullptr, *P1 = nullptr;
     // per problem
     double *rth = nullptr, *rx = nullptr; size_t state_bytes = 0;
     long long *plane_d = nullptr; size_t plane_cap = 0;
     int n_tiles = 0;
-    size_t smem_bytes = 0;
+    size_t smem_bytes = 0, aux_ints = 0;
     int max_clusters = 0;
     bool prepared = false;
 };
@@ -115,11 +125,11 @@ struct Cursor {
     double ra[RING]; int rc[RING];
 };
 
-__device__ __forceinline__ void cursor_open(Cursor& cu, const RankProg& p, int level) {
+__device__ __forceinline__ void cursor_open(Cursor& cu, const RankProg& p, const ProgSmem& ps, int level) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int idx = level * NWARPS + warp;
-    cu.t0 = __ldg(p.wt_ptr + idx); cu.t1 = __ldg(p.wt_ptr + idx + 1);
-    cu.s = __ldg(p.ws_ptr + idx); cu.s_end = __ldg(p.ws_ptr + idx + 1);
+    cu.t0 = ps.wt_ptr[idx]; cu.t1 = ps.wt_ptr[idx + 1];
+    cu.s = ps.ws_ptr[idx]; cu.s_end = ps.ws_ptr[idx + 1];
 #pragma unroll
     for (int k = 0; k < RING; ++k) {
         cu.ra[k] = 0.0; cu.rc[k] = 0;
@@ -133,7 +143,7 @@ __device__ __forceinline__ void cursor_open(Cursor& cu, const RankProg& p, int l
 
 // One level of the solve program: every warp streams through its own tiles.
 template <int WT>
-__device__ void exec_level(const RankProg& p, Cursor& cu, int staged, int next_level,
+__device__ void exec_level(const RankProg& p, const ProgSmem& ps, Cursor& cu, int staged, int next_level,
                            double* __restrict__ v, double* __restrict__ stage) {
     const int lane = threadIdx.x & 31;
     const int t0 = cu.t0, t1 = cu.t1;
@@ -143,12 +153,10 @@ __device__ void exec_level(const RankProg& p, Cursor& cu, int staged, int next_l
     double ra[RING]; int rc[RING];
 #pragma unroll
     for (int k = 0; k < RING; ++k) { ra[k] = cu.ra[k]; rc[k] = cu.rc[k]; }
-    for (int tb = t0; tb < t1; tb += 32) {
-        int2 myh = make_int2(0, 0);
-        if (tb + lane < t1) myh = __ldg(p.thdr + tb + lane);
-        const int nb = min(32, t1 - tb);
-        for (int k = 0; k < nb; ++k) {
-            const int h0 = __shfl_sync(0xffffffffu, myh.x, k), h1 = __shfl_sync(0xffffffffu, myh.y, k);
+    {
+        for (int t = t0; t < t1; ++t) {
+            const int2 hd = ps.thdr[t];
+            const int h0 = hd.x, h1 = hd.y;
             const int nrows = (h0 & 31) + 1, mshift = (h0 >> 5) & 7, flags = (h0 >> 8) & 3;
             const int nsteps = h1 & 0xffff, stage_off = (h1 >> 16) & 0xffff;
             const int m = 1 << mshift;
@@ -207,7 +215,7 @@ __device__ void exec_level(const RankProg& p, Cursor& cu, int staged, int next_l
             __syncwarp();
         }
     }
-    if (next_level >= 0) cursor_open(cu, p, next_level);
+    if (next_level >= 0) cursor_open(cu, p, ps, next_level);
     __syncthreads();
     if (staged > 0) {
         // copy the staged rows (each carries its destination row) back into the vector
@@ -250,20 +258,21 @@ __device__ void allreduce_rows(cg::cluster_group& cluster, int C, int rank, int 
 }
 
 template <int WT, bool CL>
-__device__ void run_ops(const ResArgs& a, cg::cluster_group& cluster, int rank, double* v, double* stage, double* mbox) {
+__device__ void run_ops(const ResArgs& a, const ProgSmem& ps, cg::cluster_group& cluster, int rank, double* v,
+                        double* stage, double* mbox) {
     const RankProg& p = a.prog[rank];
     Cursor cu;
     bool open = false;
     for (int o = 0; o < a.n_ops; ++o) {
         const int4 op = __ldg(a.ops + (size_t)rank * a.n_ops + o);
         if (op.x == 0) {
-            if (!open) cursor_open(cu, p, op.y);
+            if (!open) cursor_open(cu, p, ps, op.y);
             int next = -1;                       // the next level op, looking past an all-reduce
             for (int o2 = o + 1; o2 < a.n_ops && o2 <= o + 2; ++o2) {
                 const int4 nx = __ldg(a.ops + (size_t)rank * a.n_ops + o2);
                 if (nx.x == 0) { next = nx.y; break; }
             }
-            exec_level<WT>(p, cu, op.z, next, v, stage);
+            exec_level<WT>(p, ps, cu, op.z, next, v, stage);
             open = next >= 0;
         } else if (CL) {
             allreduce_rows<WT>(cluster, a.C, rank, op.y, op.z, v, mbox);
@@ -297,6 +306,13 @@ __device__ void junction_pass(const ResArgs& a, int rank, int tile, long long n,
         if (w >= a.Wp) continue;
         const int jo = __ldg(a.junc_orig + jp);
         const size_t sidx = ((size_t)tile * a.Nj + jp) * WT + q;
+        const double2 pIc = __ldg(reinterpret_cast<const double2*>(a.P0) + 2 * jp);       // Ic, 1/c0
+        const double2 pc = __ldg(reinterpret_cast<const double2*>(a.P0) + 2 * jp + 1);    // c1, c2
+        const double2 pb = __ldg(reinterpret_cast<const double2*>(a.P1) + 2 * jp);        // Is base, noise base
+        if (idx + 2 * NT < total) {      // pull the state two iterations ahead into L2
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.rx + sidx + 8 * NT));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.rth + sidx + 8 * NT));
+        }
         const size_t cidx = (size_t)jo * a.Wp + w;
         double th1[4], th2[4];
         if (do_post) {
@@ -318,10 +334,10 @@ __device__ void junction_pass(const ResArgs& a, int rank, int tile, long long n,
             const double2* tp = reinterpret_cast<const double2*>(a.rth + sidx);
             double2 t0 = tp[0], t1 = tp[1];
             th2[0] = t0.x; th2[1] = t0.y; th2[2] = t1.x; th2[3] = t1.y;
-            const double ic0 = __ldg(a.ic0 + jo);
+            const double ic0 = pIc.y;
             th1[0] = (y[0] - x0.x) * ic0; th1[1] = (y[1] - x0.y) * ic0;
             th1[2] = (y[2] - x1.x) * ic0; th1[3] = (y[3] - x1.y) * ic0;
-            if (!(isfinite(th1[0]) && isfinite(th1[1]) && isfinite(th1[2]) && isfinite(th1[3]))) atomicOr(a.flag, 1);
+            if (!(isfinite(th1[0]) && isfinite(th1[1]) && isfinite(th1[2]) && isfinite(th1[3])) && !a.dbg_skip) atomicOr(a.flag, 1);
             if (snap_th) {
                 double2* sp = reinterpret_cast<double2*>(snap_th + cidx);
                 sp[0] = make_double2(th1[0], th1[1]); sp[1] = make_double2(th1[2], th1[3]);
@@ -330,8 +346,7 @@ __device__ void junction_pass(const ResArgs& a, int rank, int tile, long long n,
                 double is[4] = {0, 0, 0, 0};
                 if (a.Is.kind == KIND_RANK1) {
                     double am[4]; amp4(a.Is, n - 1, a.Wp, w, am);
-                    double b = __ldg(a.Is.base + jo);
-                    for (int k = 0; k < 4; ++k) is[k] = b * am[k];
+                    for (int k = 0; k < 4; ++k) is[k] = pb.x * am[k];
                 }
                 double2* sp = reinterpret_cast<double2*>(snap_I + cidx);
                 sp[0] = make_double2(y[0] + is[0], y[1] + is[1]); sp[1] = make_double2(y[2] + is[2], y[3] + is[3]);
@@ -356,9 +371,9 @@ __device__ void junction_pass(const ResArgs& a, int rank, int tile, long long n,
             op[0] = u0; op[1] = u1;
         }
         if (!do_pre) continue;
-        const double Ic = __ldg(a.Ic + jo), c1 = __ldg(a.c1 + jo), c2 = __ldg(a.c2 + jo);
+        const double Ic = pIc.x, c1 = pc.x, c2 = pc.y;
         double fl[4] = {0, 0, 0, 0};
-        if (a.T.kind != KIND_ZERO) {
+        if (a.T.kind != KIND_ZERO && !(a.dbg_skip & 8)) {
             double z[4], am[4];
             if (a.noise_K > 0) {
                 const double2* zp = reinterpret_cast<const double2*>(a.noise + ((size_t)(n - a.noise_i0) * a.Nj + jo) * a.Wp + w);
@@ -368,21 +383,20 @@ __device__ void junction_pass(const ResArgs& a, int rank, int tile, long long n,
                 normal4(a.seed, jo, a.group_offset + (w >> 2), n, z);
             }
             amp4(a.T, n, a.Wp, w, am);
-            const double b = __ldg(a.T.base + jo);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) fl[k] = (b * am[k]) * z[k];
+            for (int k = 0; k < 4; ++k) fl[k] = (pb.y * am[k]) * z[k];
         }
         double is[4] = {0, 0, 0, 0};
         if (a.Is.kind == KIND_RANK1) {
             double am[4]; amp4(a.Is, n, a.Wp, w, am);
-            const double b = __ldg(a.Is.base + jo);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) is[k] = b * am[k];
+            for (int k = 0; k < 4; ++k) is[k] = pb.x * am[k];
         }
         double xn[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            double X = Ic * cpr_eval<DEF>(a.cpr, 2.0 * th1[k] - th2[k]) + c1 * th1[k] + c2 * th2[k];
+            const double arg = 2.0 * th1[k] - th2[k];
+            double X = Ic * ((a.dbg_skip & 16) ? arg : cpr_eval<DEF>(a.cpr, arg)) + c1 * th1[k] + c2 * th2[k];
             xn[k] = (fl[k] - is[k]) + X;
         }
         double2* xo = reinterpret_cast<double2*>(a.rx + sidx);
@@ -408,13 +422,12 @@ __device__ void face_pass(const ResArgs& a, int rank, int tile, long long n, dou
             for (int p = p0; p < p1; ++p) {
                 const int jp = __ldg(a.face_junc + p);
                 const double s = (double)a.face_sign[p];
-                const int jo = __ldg(a.junc_orig + jp);
-                const double ic0 = __ldg(a.ic0 + jo);
+                const double ic0 = __ldg(a.P0 + 4 * (size_t)jp + 1);
                 const double2* xp = reinterpret_cast<const double2*>(a.rx + ((size_t)tile * a.Nj + jp) * WT + q);
                 double2 x0 = __ldcg(xp), x1 = __ldcg(xp + 1);
                 double u[4] = {x0.x * ic0, x0.y * ic0, x1.x * ic0, x1.y * ic0};
                 if (a.Vs.kind == KIND_RANK1) {
-                    const double b = __ldg(a.Vs.base + jo);
+                    const double b = __ldg(a.P1 + 4 * (size_t)jp + 2);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) u[k] -= b * cum[k];
                 }
@@ -435,13 +448,24 @@ __device__ void face_pass(const ResArgs& a, int rank, int tile, long long n, dou
 }
 
 template <int WT, bool DEF, bool CL>
-__global__ void __launch_bounds__(NT, 1) k_resident(const ResArgs a) {
+__global__ void __launch_bounds__(NT, (WT == 4 ? 2 : 1)) k_resident(const ResArgs a) {
     extern __shared__ __align__(16) double smem[];
     double* v = smem;
     double* stage = v + (size_t)a.n_rows * WT;
     double* mbox = stage + (size_t)a.stage_rows * (WT + 2);
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = CL ? (int)cluster.block_rank() : 0;
+    ProgSmem ps;
+    {
+        int* aux = reinterpret_cast<int*>(mbox + (size_t)(a.ar_rows + 8 * a.C) * WT);
+        const RankProg& p = a.prog[rank];
+        const int np = p.n_levels * NWARPS + 1;
+        int* wt = aux; int* ws = aux + np; int2* th = reinterpret_cast<int2*>(aux + 2 * np);
+        for (int e = threadIdx.x; e < np; e += NT) { wt[e] = p.wt_ptr[e]; ws[e] = p.ws_ptr[e]; }
+        for (int e = threadIdx.x; e < p.n_tiles; e += NT) th[e] = p.thdr[e];
+        ps.wt_ptr = wt; ps.ws_ptr = ws; ps.thdr = th;
+        __syncthreads();
+    }
     const int cluster_id = blockIdx.x / a.C;
     const int n_clusters = gridDim.x / a.C;
     for (int tile = cluster_id; tile < a.n_tiles; tile += n_clusters) {
@@ -457,7 +481,7 @@ __global__ void __launch_bounds__(NT, 1) k_resident(const ResArgs a) {
                 *chunk_ptr<WT>(v, row, (q >> 1) + 1) = make_double2(t[2], t[3]);
             }
             __syncthreads();
-            run_ops<WT, CL>(a, cluster, rank, v, stage, mbox);
+            run_ops<WT, CL>(a, ps, cluster, rank, v, stage, mbox);
             for (int idx = threadIdx.x; idx < a.n_rows * G; idx += NT) {
                 int row = idx / G, q = (idx % G) * 4, w = tile * WT + q, g = fidx[row];
                 if (g >= 0 && w < a.Wp) {
@@ -471,12 +495,12 @@ __global__ void __launch_bounds__(NT, 1) k_resident(const ResArgs a) {
         }
         for (long long k = 0; k <= a.n; ++k) {
             const long long n = a.i0 + k;
-            junction_pass<WT, DEF>(a, rank, tile, n, k > 0, k < a.n, v);
+            if (!(a.dbg_skip & 2) || k == 0 || k == a.n) junction_pass<WT, DEF>(a, rank, tile, n, k > 0, k < a.n, v);
             if (k == a.n) break;
             __syncthreads();
-            face_pass<WT>(a, rank, tile, n, v);
+            if (!(a.dbg_skip & 4)) face_pass<WT>(a, rank, tile, n, v);
             __syncthreads();
-            run_ops<WT, CL>(a, cluster, rank, v, stage, mbox);
+            if (!(a.dbg_skip & 1)) run_ops<WT, CL>(a, ps, cluster, rank, v, stage, mbox);
         }
         __syncthreads();
     }
@@ -494,9 +518,16 @@ KernelPtr pick_kernel(int WT, bool def, bool cl) {
     return cl ? k_resident<4, false, true> : k_resident<4, false, false>;
 }
 
-__global__ void k_recip(int n, const double* c0, double* out) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = 1.0 / c0[i];
+// per-junction constants in device junction order (one coalesced 32-byte record instead of gathers by original index)
+__global__ void k_gather_params(int n, const int* orig, const double* Ic, const double* c0, const double* c1,
+                                const double* c2, const double* isb, const double* tb, const double* vsb,
+                                double* P0, double* P1) {
+    int jp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (jp >= n) return;
+    int jo = orig[jp];
+    P0[4 * jp + 0] = Ic[jo]; P0[4 * jp + 1] = 1.0 / c0[jo]; P0[4 * jp + 2] = c1[jo]; P0[4 * jp + 3] = c2[jo];
+    P1[4 * jp + 0] = isb ? isb[jo] : 0.0; P1[4 * jp + 1] = tb ? tb[jo] : 0.0; P1[4 * jp + 2] = vsb ? vsb[jo] : 0.0;
+    P1[4 * jp + 3] = 0.0;
 }
 
 #define RCK(call)                                                                                   \
@@ -572,6 +603,8 @@ int resident_set_plan(JJHandle* h, const JJResidentPlan* pl) {
         if ((rc = up(h, st, &th, ps.thdr, (size_t)ps.n_tiles * 2))) return rc;
         if ((rc = up(h, st, &sb, ps.stream, (size_t)ps.n_steps * STEP_BYTES))) return rc;
         st->prog[r].wt_ptr = wt; st->prog[r].ws_ptr = ws; st->prog[r].thdr = (const int2*)th; st->prog[r].stream = sb;
+        st->prog[r].n_levels = ps.n_levels; st->prog[r].n_tiles = ps.n_tiles;
+        st->aux_ints = std::max<size_t>(st->aux_ints, 2 * np + 2 + 2 * (size_t)ps.n_tiles);
     }
     if ((rc = up(h, st, &st->junc_ptr, pl->junc_ptr, (size_t)pl->C + 1))) return rc;
     if ((rc = up(h, st, &st->junc_orig, pl->junc_orig, (size_t)Nj))) return rc;
@@ -584,14 +617,15 @@ int resident_set_plan(JJHandle* h, const JJResidentPlan* pl) {
     if ((rc = up(h, st, &st->face_junc, pl->face_junc, (size_t)nent))) return rc;
     if ((rc = up(h, st, &st->face_sign, (const signed char*)pl->face_sign, (size_t)nent))) return rc;
     if ((rc = up(h, st, &st->face_fidx, pl->face_fidx, (size_t)pl->C * pl->n_rows))) return rc;
-    void* p = nullptr;
-    if ((rc = dev_alloc(h, &p, (size_t)Nj * sizeof(double)))) return rc;
-    st->allocs.push_back(p); st->alloc_bytes.push_back((size_t)Nj * sizeof(double));
-    st->ic0 = (double*)p;
-    k_recip<<<(Nj + 255) / 256, 256, 0, h->stream>>>(Nj, h->cir.c0, st->ic0);
-    h->launches++;
+    for (double** pp : {&st->P0, &st->P1}) {
+        void* p = nullptr;
+        if ((rc = dev_alloc(h, &p, (size_t)Nj * 4 * sizeof(double)))) return rc;
+        st->allocs.push_back(p); st->alloc_bytes.push_back((size_t)Nj * 4 * sizeof(double));
+        *pp = (double*)p;
+    }
     RCK(cudaStreamSynchronize(h->stream));
-    st->smem_bytes = (((size_t)st->n_rows + st->ar_rows + 8 * st->C) * st->WT + (size_t)st->stage_rows * (st->WT + 2)) * sizeof(double);
+    st->smem_bytes = (((size_t)st->n_rows + st->ar_rows + 8 * st->C) * st->WT + (size_t)st->stage_rows * (st->WT + 2)) * sizeof(double)
+                     + st->aux_ints * sizeof(int);
     return JJ_OK;
 }
 
@@ -611,18 +645,28 @@ static int fill_args(JJHandle* h, ResidentState* st, ResArgs& a) {
     for (int r = 0; r < st->C; ++r) a.prog[r] = st->prog[r];
     a.junc_ptr = st->junc_ptr; a.junc_orig = st->junc_orig; a.junc_row = st->junc_row; a.junc_sign = st->junc_sign;
     a.face_ptr = st->face_ptr; a.face_junc = st->face_junc; a.face_sign = st->face_sign; a.face_fidx = st->face_fidx;
-    a.Nj = h->cir.Nj; a.Nf = h->cir.Nf; a.Ic = h->cir.Ic; a.ic0 = st->ic0; a.c1 = h->cir.c1; a.c2 = h->cir.c2;
+    a.Nj = h->cir.Nj; a.Nf = h->cir.Nf; a.P0 = st->P0; a.P1 = st->P1;
     a.cpr = h->cir.cpr;
     a.Wp = h->Wp; a.n_tiles = st->n_tiles; a.dt = h->dt; a.seed = h->seed; a.group_offset = h->problem_offset / 4;
     a.Is = h->src[JJ_SRC_IS].dev; a.Vs = h->src[JJ_SRC_VS].dev; a.T = h->src[JJ_SRC_T].dev; a.F = h->src[JJ_SRC_F].dev;
     a.noise = h->noise_buf; a.noise_i0 = h->noise_i0; a.noise_K = h->noise_K;
     a.rth = st->rth; a.rx = st->rx; a.th1 = h->th1; a.th2 = h->th2;
     a.snap_th = h->th_out; a.snap_I = h->I_out; a.flag = h->flag_d;
+    const char* dbg = getenv("JJ_RES_DEBUG");
+    a.dbg_skip = dbg ? atoi(dbg) : 0;
     return JJ_OK;
 }
 
 static int launch(JJHandle* h, ResidentState* st, const ResArgs& a) {
     KernelPtr k = pick_kernel(st->WT, h->cir.default_cpr, st->C > 1);
+    {
+        const Source &is = h->src[JJ_SRC_IS].dev, &t = h->src[JJ_SRC_T].dev, &vs = h->src[JJ_SRC_VS].dev;
+        k_gather_params<<<(h->cir.Nj + 255) / 256, 256, 0, h->stream>>>(
+            h->cir.Nj, st->junc_orig, h->cir.Ic, h->cir.c0, h->cir.c1, h->cir.c2,
+            is.kind == KIND_RANK1 ? is.base : nullptr, t.kind == KIND_RANK1 ? t.base : nullptr,
+            vs.kind == KIND_RANK1 ? vs.base : nullptr, st->P0, st->P1);
+        h->launches++;
+    }
     RCK(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem_bytes));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

@@ -98,7 +98,8 @@ class CircuitTables:
     SMEM_LIMIT = 227 * 1024
 
     def resident_smem_bytes(self, plan, Wt):
-        return ((plan.n_rows + plan.allreduce_rows + 8 * plan.C) * Wt + plan.stage_rows * (Wt + 2)) * 8
+        aux = max(2 * (ps["n_levels"] * ps["n_warps"] + 1) + 2 + 2 * len(ps["thdr"]) for ps in plan.prog)
+        return ((plan.n_rows + plan.allreduce_rows + 8 * plan.C) * Wt + plan.stage_rows * (Wt + 2)) * 8 + 4 * aux
 
     def choose_resident(self, W):
         """Pick (cluster size, problems per tile) for the resident engine, or None if the right-hand sides
