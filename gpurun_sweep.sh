@@ -1,5 +1,6 @@
 mkdir -p gpurun_out
-for cfg in 4,4 8,4 4,8; do
+python -m pytest tests -m gpu -x -q -k "resident" 2>&1 | tail -4
+for cfg in 4,8 8,8; do
 for dbg in 0 2; do
   JJ_RES_DEBUG=$dbg JJ_RESIDENT=$cfg JJ_BENCH_INNER=500 JJ_BENCH_SKIP_E2E=1 python bench.py --steps 2 --warmup 1 > gpurun_out/dbg_$dbg.json 2> gpurun_out/dbg_$dbg.err
   python - <<PY

@@ -68,17 +68,17 @@ typedef struct {
     int32_t n_tiles;
     const int32_t *wt_ptr;       /* [n_levels*n_warps + 1] tiles of (level, warp) */
     const int32_t *ws_ptr;       /* [n_levels*n_warps + 1] first stream step of (level, warp) */
-    const int32_t *thdr;         /* [n_tiles][2]: row0 | (nrows-1)<<16 | log2(lanes per row)<<21 | flags<<24 ;
-                                    nsteps | stage_off<<16 */
+    const int32_t *thdr;         /* [n_tiles][2]: row0 | (nrows-1)<<16 | flags<<19 ; nsteps | stage_off<<16 */
     int64_t n_steps;
-    const uint8_t *stream;       /* [n_steps][320]: 32 float64 values then 32 uint16 shared-memory rows */
+    const uint8_t *stream;       /* [n_steps][320]: 32 float64 (A fragment of an 8x4 block) then 32 uint16
+                                    (shared-memory element codes of the B fragment) */
 } JJRankStream;
 
 /* Resident-engine plan (see pyjjasim_b200/factor.py: resident_plan). A cluster of C thread blocks owns a
  * tile of `tile_problems` problems for the whole time loop; block r keeps the right-hand-side rows of
  * elimination subtree r plus replicas of the separators above the cut in its shared memory. */
 typedef struct {
-    int32_t C, tile_problems;        /* cluster size (1,2,4,8); problems per tile (4 or 8) */
+    int32_t C, tile_problems;        /* cluster size (1,2,4,8); problems per tile (8 = N of the FP64 MMA) */
     int32_t n_rows;                  /* rows of each block's shared-memory vector */
     int32_t stage_rows, allreduce_rows;
     int32_t n_ops, n_fwd_ops;

@@ -141,10 +141,18 @@ __device__ __forceinline__ void cursor_open(Cursor& cu, const RankProg& p, const
     }
 }
 
-// One level of the solve program: every warp streams through its own tiles.
+// C(8 rows x 8 problems) += A(8 x 4) . B(4 x 8) on the FP64 tensor core: lane = row*4 + kk holds A[row][kk],
+// lane = n*4 + kk holds B[kk][n], lane = row*4 + c holds C[row][2c], C[row][2c+1].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// One level of the solve program: every warp streams through its own tiles (8 output rows each).
 template <int WT>
 __device__ void exec_level(const RankProg& p, const ProgSmem& ps, Cursor& cu, int staged, int next_level,
                            double* __restrict__ v, double* __restrict__ stage) {
+    static_assert(WT == 8, "the tensor-core sweep is written for 8 problems per tile");
     const int lane = threadIdx.x & 31;
     const int t0 = cu.t0, t1 = cu.t1;
     int s = cu.s;
@@ -153,67 +161,40 @@ __device__ void exec_level(const RankProg& p, const ProgSmem& ps, Cursor& cu, in
     double ra[RING]; int rc[RING];
 #pragma unroll
     for (int k = 0; k < RING; ++k) { ra[k] = cu.ra[k]; rc[k] = cu.rc[k]; }
-    {
-        for (int t = t0; t < t1; ++t) {
-            const int2 hd = ps.thdr[t];
-            const int h0 = hd.x, h1 = hd.y;
-            const int nrows = (h0 & 31) + 1, mshift = (h0 >> 5) & 7, flags = (h0 >> 8) & 3;
-            const int nsteps = h1 & 0xffff, stage_off = (h1 >> 16) & 0xffff;
-            const int m = 1 << mshift;
-            const int i = lane >> mshift, sub = lane & (m - 1);
-            double acc[WT];
+    const int r = lane >> 2, kk = lane & 3;
+    for (int t = t0; t < t1; ++t) {
+        const int2 hd = ps.thdr[t];
+        const int row0 = hd.x & 0xffff, nrows = ((hd.x >> 16) & 7) + 1, flags = (hd.x >> 19) & 3;
+        const int nsteps = hd.y & 0xffff, stage_off = (hd.y >> 16) & 0xffff;
+        const int row = row0 + r;
+        double2* self = chunk_ptr<WT>(v, row, kk);
+        double c0 = 0.0, c1 = 0.0;
+        if ((flags & 1) && r < nrows) { const double2 sv = *self; c0 = sv.x; c1 = sv.y; }
+        for (int j = 0; j < nsteps; ++j) {
+            const double a = ra[0];
+            const int code = rc[0];
 #pragma unroll
-            for (int q = 0; q < WT; ++q) acc[q] = 0.0;
-            int out_row = 0xffff;
-            for (int j = 0; j < nsteps; ++j) {
-                const double a = ra[0];
-                const int c = rc[0];
-#pragma unroll
-                for (int r = 0; r < RING - 1; ++r) { ra[r] = ra[r + 1]; rc[r] = rc[r + 1]; }
-                if (s + RING < s_end) {
-                    const unsigned char* rec = base + (size_t)(s + RING) * STEP_BYTES;
-                    ra[RING - 1] = __ldg(reinterpret_cast<const double*>(rec) + lane);
-                    rc[RING - 1] = __ldg(reinterpret_cast<const unsigned short*>(rec + 256) + lane);
-                }
-                ++s;
-                if (j == 0) { out_row = c; continue; }      // first step of a tile: the output row of every lane
-                const double2* src = reinterpret_cast<const double2*>(v + (size_t)c * WT);
-                const int f = swz<WT>(c);
-#pragma unroll
-                for (int q = 0; q < WT / 2; ++q) {
-                    const double2 sv = src[q ^ f];
-                    acc[2 * q] = fma(a, sv.x, acc[2 * q]);
-                    acc[2 * q + 1] = fma(a, sv.y, acc[2 * q + 1]);
-                }
+            for (int q = 0; q < RING - 1; ++q) { ra[q] = ra[q + 1]; rc[q] = rc[q + 1]; }
+            if (s + RING < s_end) {
+                const unsigned char* rec = base + (size_t)(s + RING) * STEP_BYTES;
+                ra[RING - 1] = __ldg(reinterpret_cast<const double*>(rec) + lane);
+                rc[RING - 1] = __ldg(reinterpret_cast<const unsigned short*>(rec + 256) + lane);
             }
-            for (int off = m >> 1; off > 0; off >>= 1) {
-#pragma unroll
-                for (int q = 0; q < WT; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], off);
-            }
-            __syncwarp();
-            if (sub == 0 && i < nrows && out_row != 0xffff) {
-                const int f = swz<WT>(out_row);
-                double2* self = reinterpret_cast<double2*>(v + (size_t)out_row * WT);
-                if (flags & 1) {
-#pragma unroll
-                    for (int q = 0; q < WT / 2; ++q) {
-                        const double2 sv = self[q ^ f];
-                        acc[2 * q] += sv.x; acc[2 * q + 1] += sv.y;
-                    }
-                }
-                if (flags & 2) {
-                    // staged: keep the destination row with the data (physical layout of the destination row)
-                    double2* dst = reinterpret_cast<double2*>(stage + (size_t)(stage_off + i) * (WT + 2));
-#pragma unroll
-                    for (int q = 0; q < WT / 2; ++q) dst[q ^ f] = make_double2(acc[2 * q], acc[2 * q + 1]);
-                    reinterpret_cast<int*>(dst + WT / 2)[0] = out_row;
-                } else {
-#pragma unroll
-                    for (int q = 0; q < WT / 2; ++q) self[q ^ f] = make_double2(acc[2 * q], acc[2 * q + 1]);
-                }
-            }
-            __syncwarp();
+            ++s;
+            dmma884(c0, c1, a, v[code]);
         }
+        __syncwarp();            // every lane has read its operands before rows of this block are overwritten
+        if (r < nrows) {
+            if (flags & 2) {
+                // staged: the row keeps the physical layout of its destination and carries the destination index
+                double2* srow = reinterpret_cast<double2*>(stage + (size_t)(stage_off + r) * (WT + 2));
+                srow[kk ^ swz<WT>(row)] = make_double2(c0, c1);
+                if (kk == 0) reinterpret_cast<int*>(srow + WT / 2)[0] = row;
+            } else {
+                *self = make_double2(c0, c1);
+            }
+        }
+        __syncwarp();
     }
     if (next_level >= 0) cursor_open(cu, p, ps, next_level);
     __syncthreads();
@@ -448,7 +429,7 @@ __device__ void face_pass(const ResArgs& a, int rank, int tile, long long n, dou
 }
 
 template <int WT, bool DEF, bool CL>
-__global__ void __launch_bounds__(NT, (WT == 4 ? 2 : 1)) k_resident(const ResArgs a) {
+__global__ void __launch_bounds__(NT, 1) k_resident(const ResArgs a) {
     extern __shared__ __align__(16) double smem[];
     double* v = smem;
     double* stage = v + (size_t)a.n_rows * WT;
@@ -510,12 +491,9 @@ __global__ void __launch_bounds__(NT, (WT == 4 ? 2 : 1)) k_resident(const ResArg
 typedef void (*KernelPtr)(const ResArgs);
 
 KernelPtr pick_kernel(int WT, bool def, bool cl) {
-    if (WT == 8) {
-        if (def) return cl ? k_resident<8, true, true> : k_resident<8, true, false>;
-        return cl ? k_resident<8, false, true> : k_resident<8, false, false>;
-    }
-    if (def) return cl ? k_resident<4, true, true> : k_resident<4, true, false>;
-    return cl ? k_resident<4, false, true> : k_resident<4, false, false>;
+    (void)WT;      // 8 problems per tile: the N of the FP64 MMA
+    if (def) return cl ? k_resident<8, true, true> : k_resident<8, true, false>;
+    return cl ? k_resident<8, false, true> : k_resident<8, false, false>;
 }
 
 // per-junction constants in device junction order (one coalesced 32-byte record instead of gathers by original index)
@@ -582,8 +560,8 @@ void resident_drop_plan(JJHandle* h) {
 int resident_set_plan(JJHandle* h, const JJResidentPlan* pl) {
     resident_drop_plan(h);
     if (!pl) return JJ_OK;
-    if (!(pl->C == 1 || pl->C == 2 || pl->C == 4 || pl->C == 8) || !(pl->tile_problems == 4 || pl->tile_problems == 8)) {
-        h->err = "resident plan: cluster size must be 1/2/4/8 and tile_problems 4 or 8";
+    if (!(pl->C == 1 || pl->C == 2 || pl->C == 4 || pl->C == 8) || pl->tile_problems != 8) {
+        h->err = "resident plan: cluster size must be 1/2/4/8 and tile_problems 8";
         return JJ_EINVAL;
     }
     ResidentState* st = new ResidentState();

@@ -110,16 +110,15 @@ class CircuitTables:
         if env:
             C, Wt = (int(v) for v in env.split(","))
             return C, Wt
-        best = None
-        for Wt in (8, 4):
-            if W <= 4 and Wt == 8:
-                continue
-            for limit in (110 * 1024, self.SMEM_LIMIT):
-                for C in (1, 2, 4, 8):
+        for limit in (110 * 1024, self.SMEM_LIMIT):
+            for C in (1, 2, 4, 8):
+                try:
                     plan = self.resident_plan(C)
-                    if self.resident_smem_bytes(plan, Wt) <= limit:
-                        return C, Wt
-        return best
+                except ValueError:
+                    continue
+                if self.resident_smem_bytes(plan, 8) <= limit:
+                    return C, 8
+        return None
 
     def resident_plan(self, C):
         if C not in self._resident:

@@ -222,22 +222,17 @@ def pack_levels(levels, row_map=None, col_map=None):
 
 
 RES_WARPS = 16          # warps per thread block of the resident kernel
-STEP_BYTES = 320        # one stream step: 32 float64 values + 32 uint16 shared-memory rows
-NO_ROW = 0xFFFF
+RES_WT = 8              # problems per tile of the resident engine (= N of the m8n8k4 FP64 MMA)
+STEP_BYTES = 320        # one stream step: 32 float64 values + 32 uint16 shared-memory element codes
+CHAIN_ROWS = 32         # diagonal blocks up to this many rows are updated in place by a single warp
 
 
 def a_rows(F, blocks, M, col_mask=None):
-    """Phase-a row tasks of the given blocks: (permuted row, cols, vals) with out = src[row] + sum vals*src[cols]."""
+    """Phase-a tasks of the given blocks: per block (first permuted row, CSR rows of M restricted to col_mask)."""
     out = []
     for b in blocks:
-        for g in range(int(F.bptr[b]), int(F.bptr[b + 1])):
-            lo, hi = M.indptr[g], M.indptr[g + 1]
-            cols, vals = M.indices[lo:hi], -M.data[lo:hi]
-            if col_mask is not None:
-                keep = col_mask[cols]
-                cols, vals = cols[keep], vals[keep]
-            if cols.size:
-                out.append((g, cols.astype(np.int64), vals))
+        r0, r1 = int(F.bptr[b]), int(F.bptr[b + 1])
+        out.append((r0, r1, M, col_mask))
     return out
 
 
@@ -247,172 +242,162 @@ def b_blocks(F, blocks, transpose):
 
 
 def _lpt(costs, n_warps):
-    """Longest-processing-time assignment; returns (lists of item indices per warp, makespan)."""
+    """Longest-processing-time assignment; returns lists of item indices per warp."""
     load = np.zeros(n_warps)
     assign = [[] for _ in range(n_warps)]
-    for i in np.argsort(-np.asarray(costs), kind="stable") if len(costs) else []:
+    for i in (np.argsort(-np.asarray(costs), kind="stable") if len(costs) else []):
         w = int(np.argmin(load))
         assign[w].append(int(i))
         load[w] += costs[i]
-    return assign, float(load.max()) if len(costs) else 0.0
+    return assign
 
 
-def _tile_cost(steps, m):
-    return steps + 3 + 2 * int(np.log2(m))
+def _mma_tiles_a(items):
+    """8-row tiles of phase a: out = src[row] - M[row, cols] src[cols]; one unit per tile."""
+    units = []
+    for (r0, r1, M, col_mask) in items:
+        for t0 in range(r0, r1, 8):
+            t1 = min(r1, t0 + 8)
+            sub = M[t0:t1]
+            cols = np.unique(sub.indices)
+            if col_mask is not None:
+                cols = cols[col_mask[cols]]
+            if cols.size == 0:
+                continue
+            units.append([dict(row0=t0, V=-sub[:, cols].toarray(), cols=cols.astype(np.int64), flags=TILE_SELF)])
+    return units
 
 
-def _tiles_a(rows, m):
-    """Group phase-a rows (sorted by length) into tiles of 32/m rows."""
-    P = 32 // m
-    order = sorted(range(len(rows)), key=lambda i: -rows[i][1].size)
-    tiles = []
-    for k in range(0, len(order), P):
-        grp = [rows[i] for i in order[k:k + P]]
-        tiles.append(dict(m=m, flags=TILE_SELF, rows=[(g, c, v) for (g, c, v) in grp]))
-    return tiles
-
-
-def _tiles_b(blocks, m, transpose):
-    """Phase-b tiles: whole small blocks are packed together (updated in place by one warp), blocks with
-    more rows than a tile holds are cut into row groups that write through the staging buffer."""
-    P = 32 // m
-    tiles = []
-    small = sorted([b for b in blocks if b[1].shape[0] <= P], key=lambda b: -b[1].shape[0])
-    bins = []
-    for (r0, D) in small:
-        k = D.shape[0]
-        for bn in bins:
-            if bn["free"] >= k:
-                break
-        else:
-            bn = dict(free=P, rows=[])
-            bins.append(bn)
-        bn["free"] -= k
-        for i in range(k):
-            c0, c1 = (i, k) if transpose else (0, i + 1)
-            bn["rows"].append((r0 + i, np.arange(r0 + c0, r0 + c1), D[i, c0:c1]))
-    for bn in bins:
-        tiles.append(dict(m=m, flags=0, rows=bn["rows"]))
+def _mma_tiles_b(blocks, transpose):
+    """8-row tiles of phase b. A block of at most CHAIN_ROWS rows is one unit: its tiles are processed by one
+    warp in an order that makes the in-place update safe; larger blocks write through the staging buffer."""
+    units = []
     for (r0, D) in blocks:
         k = D.shape[0]
-        if k <= P:
-            continue
-        for t0 in range(0, k, P):
-            rows = []
-            for i in range(t0, min(k, t0 + P)):
-                c0, c1 = (i, k) if transpose else (0, i + 1)
-                rows.append((r0 + i, np.arange(r0 + c0, r0 + c1), D[i, c0:c1]))
-            tiles.append(dict(m=m, flags=TILE_STAGED, rows=rows))
-    return tiles
+        starts = list(range(0, k, 8))
+        if not transpose:
+            starts.reverse()          # lower triangular: a row group reads the rows above it -> last group first
+        tiles = []
+        for t0 in starts:
+            t1 = min(k, t0 + 8)
+            c0, c1 = (t0, k) if transpose else (0, t1)
+            tiles.append(dict(row0=r0 + t0, V=D[t0:t1, c0:c1], cols=np.arange(r0 + c0, r0 + c1, dtype=np.int64), flags=0))
+        if k <= CHAIN_ROWS:
+            units.append(tiles)
+        else:
+            for t in tiles:
+                t["flags"] = TILE_STAGED
+                units.append([t])
+    return units
 
 
-def _tile_steps(t):
-    m = t["m"]
-    return 1 + max((r[1].size + m - 1) // m for r in t["rows"])
+def smem_code(col):
+    """Element offset (in float64) of problem n = 0..7 of shared-memory row `col` in the swizzled layout:
+    16-byte chunk c of row r lives at chunk position c ^ ((r >> 1) & 3)."""
+    col = np.asarray(col, dtype=np.int64)[..., None]
+    n = np.arange(8)
+    return col * 8 + (((n >> 1) ^ ((col >> 1) & 3)) << 1) + (n & 1)
 
 
-def plan_level(kind, items, transpose, n_warps):
-    """Choose the lanes-per-row m that minimises the slowest warp's time and return (tiles, assignment)."""
-    best = None
-    for m in (1, 2, 4, 8, 16, 32):
-        tiles = _tiles_a(items, m) if kind == "a" else _tiles_b(items, m, transpose)
-        costs = [_tile_cost(_tile_steps(t), m) for t in tiles]
-        assign, span = _lpt(costs, n_warps)
-        if best is None or span < best[0]:
-            best = (span, tiles, assign)
-    return best[1], best[2]
-
-
-def pack_ell_streams(level_specs, row_map, col_map, n_warps=RES_WARPS):
+def pack_mma_streams(level_specs, row_map, col_map, n_warps=RES_WARPS):
     """
-    Resident-engine packing. level_specs: list of (kind 'a'|'b', items, transpose) per level, items from
-    a_rows / b_blocks. Every (level, warp) pair gets a contiguous *stream* of 320-byte steps
-    ([32 float64 values][32 uint16 shared-memory rows], one per lane) through which the warp prefetches
-    straight across tile boundaries. A tile is 32/m output rows x m lanes per row; its first step carries the
-    output row of every lane (0xFFFF: none), the following steps one (value, source row) pair per lane.
-    Header: two int32 = (nrows-1) | log2(m) << 5 | flags << 8 , nsteps | stage_off << 16.
+    Resident-engine packing for the FP64 tensor-core sweep. level_specs: list of (kind 'a'|'b', items,
+    transpose) per level. A tile is 8 output rows x K columns (K a multiple of 4) of a dense matrix V; the
+    device computes C(8 rows x 8 problems) += V(8x4) . S(4x8) per stream step with mma.m8n8k4, S gathered from
+    the shared-memory vector. Every (level, warp) pair owns a contiguous stream of 320-byte steps:
+      32 float64: lane = row*4 + kk holds V[row, 4*step + kk]          (the A fragment)
+      32 uint16 : lane = n*4 + kk holds the element code of src[col(4*step + kk)], problem n   (the B fragment)
+    Header (two int32): row0 | (nrows-1) << 16 | flags << 19 ;  nsteps | stage_off << 16.
     """
     n_levels = len(level_specs)
     wt_ptr = np.zeros(n_levels * n_warps + 1, dtype=np.int32)
     ws_ptr = np.zeros(n_levels * n_warps + 1, dtype=np.int32)
     hdr, chunks = [], []
     n_steps = stage_rows = n_vals = 0
-    staged_levels = []
+    staged_rows = []
+    lane = np.arange(32)
     for li, (kind, items, transpose) in enumerate(level_specs):
-        tiles, assign = plan_level(kind, items, transpose, n_warps) if items else ([], [[] for _ in range(n_warps)])
+        units = (_mma_tiles_a(items) if kind == "a" else _mma_tiles_b(items, transpose)) if items else []
+        costs = [sum((t["V"].shape[1] + 3) // 4 + 5 for t in u) for u in units]
+        assign = _lpt(costs, n_warps)
         staged = 0
-        for t in tiles:
-            if t["flags"] & TILE_STAGED:
-                t["stage_off"] = staged
-                staged += len(t["rows"])
+        for u in units:
+            for t in u:
+                if t["flags"] & TILE_STAGED:
+                    t["stage_off"] = staged
+                    staged += t["V"].shape[0]
         stage_rows = max(stage_rows, staged)
-        staged_levels.append(int(staged))
+        staged_rows.append(int(staged))
         for w in range(n_warps):
-            for ti in assign[w]:
-                t = tiles[ti]
-                m = t["m"]
-                P = 32 // m
-                st = _tile_steps(t)
-                vals = np.zeros((st, 32))
-                cols = np.zeros((st, 32), dtype=np.uint16)
-                cols[0, :] = NO_ROW
-                for i, (g, c, v) in enumerate(t["rows"]):
-                    lanes = slice(i * m, (i + 1) * m)
-                    out_row = int(row_map[g])
-                    assert 0 <= out_row < NO_ROW
-                    cols[0, lanes] = out_row
-                    cm = col_map[np.asarray(c, dtype=np.int64)]
-                    assert np.all(cm >= 0) and np.all(cm < NO_ROW)
-                    n = cm.size
-                    ns = (n + m - 1) // m
-                    pc = np.zeros(ns * m, dtype=np.int64); pv = np.zeros(ns * m)
-                    pc[:n] = cm; pv[:n] = v
-                    pc[n:] = cm[-1]
-                    cols[1:1 + ns, lanes] = pc.reshape(ns, m)
-                    vals[1:1 + ns, lanes] = pv.reshape(ns, m)
-                    n_vals += n
-                rec = np.zeros((st, STEP_BYTES), dtype=np.uint8)
-                rec[:, :256] = vals.view(np.uint8).reshape(st, 256)
-                rec[:, 256:] = cols.view(np.uint8).reshape(st, 64)
-                chunks.append(rec)
-                assert st < 65536
-                hdr.append(((len(t["rows"]) - 1) | (int(np.log2(m)) << 5) | (t["flags"] << 8),
-                            st | (t.get("stage_off", 0) << 16)))
-                n_steps += st
+            for ui in assign[w]:
+                for t in units[ui]:
+                    V = t["V"]
+                    nr, nc = V.shape
+                    st = (nc + 3) // 4
+                    Vp = np.zeros((8, st * 4))
+                    Vp[:nr, :nc] = V
+                    cm = col_map[t["cols"]]
+                    assert np.all(cm >= 0) and np.all(cm < 8192)
+                    cp = np.full(st * 4, cm[-1], dtype=np.int64)
+                    cp[:nc] = cm
+                    vals = Vp.reshape(8, st, 4).transpose(1, 0, 2).reshape(st, 32)       # lane = row*4 + kk
+                    codes = smem_code(cp.reshape(st, 4))                                  # (st, 4, 8): [kk][n]
+                    codes = codes.transpose(0, 2, 1).reshape(st, 32).astype(np.uint16)    # lane = n*4 + kk
+                    rec = np.zeros((st, STEP_BYTES), dtype=np.uint8)
+                    rec[:, :256] = np.ascontiguousarray(vals).view(np.uint8).reshape(st, 256)
+                    rec[:, 256:] = np.ascontiguousarray(codes).view(np.uint8).reshape(st, 64)
+                    chunks.append(rec)
+                    row = int(row_map[t["row0"]])
+                    assert 0 <= row < 65536 and st < 65536
+                    hdr.append((row | ((nr - 1) << 16) | (t["flags"] << 19), st | (t.get("stage_off", 0) << 16)))
+                    n_steps += st
+                    n_vals += nr * nc
             wt_ptr[li * n_warps + w + 1] = len(hdr)
             ws_ptr[li * n_warps + w + 1] = n_steps
     stream = np.concatenate(chunks).ravel() if chunks else np.zeros(0, dtype=np.uint8)
     return dict(n_levels=n_levels, n_warps=n_warps, wt_ptr=wt_ptr, ws_ptr=ws_ptr,
                 thdr=np.asarray(hdr, dtype=np.int32).reshape(-1, 2), stream=stream, n_steps=n_steps,
-                stage_rows=int(stage_rows), vals=int(n_vals), staged_rows=staged_levels)
+                stage_rows=int(stage_rows), vals=int(n_vals), staged_rows=staged_rows)
 
 
 def _run_stream_level(ps, v, level):
-    """Host interpreter of one level of a warp-stream program (mirrors the device kernel)."""
+    """Host interpreter of one level of an MMA stream program (mirrors the device kernel, including the
+    sequential in-place semantics of the tiles of one warp). v: (rows, 8) float64."""
+    assert v.ndim == 2 and v.shape[1] == 8
     nw = ps["n_warps"]
-    out = []
     rec = ps["stream"].reshape(-1, STEP_BYTES)
+    flat = v.reshape(-1)
+    # swizzled view of v: the codes address the physical layout, so build it once per tile
+    def physical(vv):
+        rows = np.arange(vv.shape[0])
+        ph = np.empty_like(vv).reshape(vv.shape[0], 4, 2)
+        lg = vv.reshape(vv.shape[0], 4, 2)
+        for c in range(4):
+            ph[rows, c ^ ((rows >> 1) & 3)] = lg[rows, c]
+        return ph.reshape(-1)
+    staged = []
     for w in range(nw):
         idx = level * nw + w
         s = ps["ws_ptr"][idx]
         for t in range(ps["wt_ptr"][idx], ps["wt_ptr"][idx + 1]):
             h0, h1 = int(ps["thdr"][t, 0]), int(ps["thdr"][t, 1])
-            nr, mshift, fl = (h0 & 31) + 1, (h0 >> 5) & 7, (h0 >> 8) & 3
+            row0, nr, fl = h0 & 0xffff, ((h0 >> 16) & 7) + 1, (h0 >> 19) & 3
             st = h1 & 0xffff
-            m = 1 << mshift
-            vals = rec[s:s + st, :256].copy().view(np.float64).reshape(st, 32)
-            cols = rec[s:s + st, 256:].copy().view(np.uint16).reshape(st, 32).astype(np.int64)
+            vals = rec[s:s + st, :256].copy().view(np.float64).reshape(st, 8, 4)          # [step][row][kk]
+            codes = rec[s:s + st, 256:].copy().view(np.uint16).reshape(st, 8, 4).astype(np.int64)   # [step][n][kk]
             s += st
-            rows = cols[0, ::m][:nr]
-            prod = vals[1:][(...,) + (None,) * (v.ndim - 1)] * v[cols[1:]]    # (st-1, 32, ...)
-            lane_sum = prod.sum(axis=0)
-            acc = lane_sum.reshape((32 // m, m) + v.shape[1:]).sum(axis=1)[:nr]
+            ph = physical(v)
+            S = ph[codes]                                                                  # [step][n][kk]
+            acc = np.einsum("srk,snk->rn", vals, S)[:nr]
             if fl & TILE_SELF:
-                acc = acc + v[rows]
-            out.append((rows, acc))
+                acc = acc + v[row0:row0 + nr]
+            if fl & TILE_STAGED:
+                staged.append((row0, nr, acc))
+            else:
+                v[row0:row0 + nr] = acc            # in place, in the warp's program order
         assert s == ps["ws_ptr"][idx + 1]
-    for (rows, acc) in out:
-        v[rows] = acc
+    for (row0, nr, acc) in staged:
+        v[row0:row0 + nr] = acc
 
 
 class SolveProgram:
@@ -555,6 +540,8 @@ def resident_plan(F, C, want_tasks=16):
     def tr_for(blocks):
         return _tile_rows_for(int(sum(sizes[b] for b in blocks)), want_tasks)
 
+    if n_local_max + n_shared > 8192:
+        raise ValueError("resident plan: %d rows per block exceed the 16-bit element codes" % (n_local_max + n_shared))
     plan = ResidentPlan()
     plan.C, plan.n_local_max, plan.n_shared, plan.n_rows = C, n_local_max, n_shared, n_local_max + n_shared
     plan.smem_index, plan.row_rank, plan.col_owner = smem_index, row_rank, col_owner
@@ -589,7 +576,7 @@ def resident_plan(F, C, want_tasks=16):
             blocks = [b for b in local_blocks[r] if F.height[b] == h]
             level("a", a_rows(F, blocks, F.LoffT))
             level("b", b_blocks(F, blocks, True), True)
-        ps = pack_ell_streams(specs, row_map=smem_index[r], col_map=smem_index[r])
+        ps = pack_mma_streams(specs, row_map=smem_index[r], col_map=smem_index[r])
         plan.prog.append(ps)
         for op in rops:
             if op[0] == OP_LEVEL:

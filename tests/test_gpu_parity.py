@@ -121,7 +121,7 @@ def test_missing_gpu_library_fails_loudly(monkeypatch):
 # ------------------------------------------------------------------------------------------------
 # resident engine (cluster kernel): every cluster size / tile width against the golden vectors
 # ------------------------------------------------------------------------------------------------
-RESIDENT_CONFIGS = ["1,8", "1,4", "2,8", "4,8", "4,4", "8,8", "8,4"]
+RESIDENT_CONFIGS = ["1,8", "2,8", "4,8", "8,8"]
 
 
 @pytest.mark.parametrize("cfg", RESIDENT_CONFIGS)
