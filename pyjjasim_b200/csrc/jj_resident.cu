@@ -18,6 +18,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -43,7 +44,7 @@ struct RankProg {
 // The level cursors and tile headers of this rank's program are copied into shared memory once per
 // kernel (they are the same for every tile of problems and every time step).
 struct ProgSmem {
-    const int* wt_ptr; const int* ws_ptr; const int2* thdr;
+    const int* wt_ptr; const int* ws_ptr; const int2* thdr; const int4* ops;
 };
 
 struct ResArgs {
@@ -74,6 +75,7 @@ struct ResArgs {
     int* flag;
     // debug solve
     const double* dbg_b; double* dbg_J;   // canonical [Nf][Wp], permuted faces
+    long long* dbg_prof;                  // per-block cycle counters [block][2 + n_ops] (JJ_RES_PROF), or null
     int dbg_skip;                         // timing experiments only (JJ_RES_DEBUG): 1 skip sweeps, 2 skip junction pass, 4 skip face pass
 };
 
@@ -115,14 +117,17 @@ __device__ __forceinline__ const double2* chunk_ptr(const double* v, int row, in
 }
 
 constexpr int STEP_BYTES = 320;
-constexpr int RING = 4;           // stream steps kept in flight per warp
+#ifndef JJ_RING
+#define JJ_RING 8
+#endif
+constexpr int RING = JJ_RING;     // stream steps kept in flight per warp
 
 // Per-warp read position in the factor stream: tile range, step range and a register ring of RING
 // prefetched steps (values + rows). The ring for the NEXT level is loaded before the barrier that ends the
 // current one, so the L2 latency of the stream overlaps the barrier and the FMAs of earlier steps.
 struct Cursor {
     int t0, t1, s, s_end;
-    double ra[RING]; int rc[RING];
+    double ra[RING]; unsigned rc[RING];
 };
 
 __device__ __forceinline__ void cursor_open(Cursor& cu, const RankProg& p, const ProgSmem& ps, int level) {
@@ -130,11 +135,14 @@ __device__ __forceinline__ void cursor_open(Cursor& cu, const RankProg& p, const
     const int idx = level * NWARPS + warp;
     cu.t0 = ps.wt_ptr[idx]; cu.t1 = ps.wt_ptr[idx + 1];
     cu.s = ps.ws_ptr[idx]; cu.s_end = ps.ws_ptr[idx + 1];
+    // ring slot of stream step s is s % RING, so a slot is refilled in place and never moved while in flight
+    const int first = cu.s - (cu.s & (RING - 1));
 #pragma unroll
     for (int k = 0; k < RING; ++k) {
         cu.ra[k] = 0.0; cu.rc[k] = 0;
-        if (cu.s + k < cu.s_end) {
-            const unsigned char* rec = p.stream + (size_t)(cu.s + k) * STEP_BYTES;
+        const int sk = first + k + ((first + k < cu.s) ? RING : 0);
+        {   // unconditional: the stream buffer is padded by 2*RING steps, so reading past this warp's range is safe
+            const unsigned char* rec = p.stream + (size_t)sk * STEP_BYTES;
             cu.ra[k] = __ldg(reinterpret_cast<const double*>(rec) + lane);
             cu.rc[k] = __ldg(reinterpret_cast<const unsigned short*>(rec + 256) + lane);
         }
@@ -156,9 +164,8 @@ __device__ void exec_level(const RankProg& p, const ProgSmem& ps, Cursor& cu, in
     const int lane = threadIdx.x & 31;
     const int t0 = cu.t0, t1 = cu.t1;
     int s = cu.s;
-    const int s_end = cu.s_end;
     const unsigned char* base = p.stream;
-    double ra[RING]; int rc[RING];
+    double ra[RING]; unsigned rc[RING];
 #pragma unroll
     for (int k = 0; k < RING; ++k) { ra[k] = cu.ra[k]; rc[k] = cu.rc[k]; }
     const int r = lane >> 2, kk = lane & 3;
@@ -170,19 +177,27 @@ __device__ void exec_level(const RankProg& p, const ProgSmem& ps, Cursor& cu, in
         double2* self = chunk_ptr<WT>(v, row, kk);
         double c0 = 0.0, c1 = 0.0;
         if ((flags & 1) && r < nrows) { const double2 sv = *self; c0 = sv.x; c1 = sv.y; }
-        for (int j = 0; j < nsteps; ++j) {
-            const double a = ra[0];
-            const int code = rc[0];
-#pragma unroll
-            for (int q = 0; q < RING - 1; ++q) { ra[q] = ra[q + 1]; rc[q] = rc[q + 1]; }
-            if (s + RING < s_end) {
-                const unsigned char* rec = base + (size_t)(s + RING) * STEP_BYTES;
-                ra[RING - 1] = __ldg(reinterpret_cast<const double*>(rec) + lane);
-                rc[RING - 1] = __ldg(reinterpret_cast<const unsigned short*>(rec + 256) + lane);
-            }
-            ++s;
-            dmma884(c0, c1, a, v[code]);
+        // Ring slot K always holds a stream step congruent to K (mod RING): the MMA consumes it and the refill
+        // for step s + RING is issued right behind it into the SAME registers. Loads are volatile inline PTX so
+        // the compiler neither renames the slot (a copy-back would wait for the load every step) nor predicates
+        // it through a temporary; the stream buffer is padded, so the refill is unconditional.
+#define JJ_STEP(K)                                                                                     \
+    if ((K) >= p_ && j < nsteps) {                                                                     \
+        const double b_ = v[rc[K]];                                                                    \
+        dmma884(c0, c1, ra[K], b_);                                                                    \
+        const unsigned char* rec = base + (size_t)(s + RING) * STEP_BYTES;                             \
+        asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(ra[K]) : "l"(reinterpret_cast<const double*>(rec) + lane)); \
+        asm volatile("ld.global.nc.u16 %0, [%1];" : "=r"(rc[K]) : "l"(reinterpret_cast<const unsigned short*>(rec + 256) + lane)); \
+        ++s; ++j;                                                                                      \
+    }
+        for (int j = 0; j < nsteps;) {
+            const int p_ = s & (RING - 1);
+            JJ_STEP(0) JJ_STEP(1) JJ_STEP(2) JJ_STEP(3)
+#if JJ_RING == 8
+            JJ_STEP(4) JJ_STEP(5) JJ_STEP(6) JJ_STEP(7)
+#endif
         }
+#undef JJ_STEP
         __syncwarp();            // every lane has read its operands before rows of this block are overwritten
         if (r < nrows) {
             if (flags & 2) {
@@ -244,13 +259,19 @@ __device__ void run_ops(const ResArgs& a, const ProgSmem& ps, cg::cluster_group&
     const RankProg& p = a.prog[rank];
     Cursor cu;
     bool open = false;
+    long long tprev = a.dbg_prof ? clock64() : 0;
     for (int o = 0; o < a.n_ops; ++o) {
-        const int4 op = __ldg(a.ops + (size_t)rank * a.n_ops + o);
+        if (a.dbg_prof && o > 0 && threadIdx.x == 0) {
+            const long long tn = clock64();
+            a.dbg_prof[(size_t)blockIdx.x * (2 + a.n_ops) + 2 + (o - 1)] += tn - tprev;
+            tprev = tn;
+        }
+        const int4 op = ps.ops[o];
         if (op.x == 0) {
             if (!open) cursor_open(cu, p, ps, op.y);
             int next = -1;                       // the next level op, looking past an all-reduce
             for (int o2 = o + 1; o2 < a.n_ops && o2 <= o + 2; ++o2) {
-                const int4 nx = __ldg(a.ops + (size_t)rank * a.n_ops + o2);
+                const int4 nx = ps.ops[o2];
                 if (nx.x == 0) { next = nx.y; break; }
             }
             exec_level<WT>(p, ps, cu, op.z, next, v, stage);
@@ -259,6 +280,8 @@ __device__ void run_ops(const ResArgs& a, const ProgSmem& ps, cg::cluster_group&
             allreduce_rows<WT>(cluster, a.C, rank, op.y, op.z, v, mbox);
         }
     }
+    if (a.dbg_prof && threadIdx.x == 0)
+        a.dbg_prof[(size_t)blockIdx.x * (2 + a.n_ops) + 2 + (a.n_ops - 1)] += clock64() - tprev;
 }
 
 __device__ __forceinline__ void amp4(const Source& s, long long step, int Wp, int w, double out[4]) {
@@ -444,7 +467,9 @@ __global__ void __launch_bounds__(NT, 1) k_resident(const ResArgs a) {
         int* wt = aux; int* ws = aux + np; int2* th = reinterpret_cast<int2*>(aux + 2 * np);
         for (int e = threadIdx.x; e < np; e += NT) { wt[e] = p.wt_ptr[e]; ws[e] = p.ws_ptr[e]; }
         for (int e = threadIdx.x; e < p.n_tiles; e += NT) th[e] = p.thdr[e];
-        ps.wt_ptr = wt; ps.ws_ptr = ws; ps.thdr = th;
+        int4* ops_s = reinterpret_cast<int4*>(th + p.n_tiles + (p.n_tiles & 1));
+        for (int e = threadIdx.x; e < a.n_ops; e += NT) ops_s[e] = a.ops[(size_t)rank * a.n_ops + e];
+        ps.wt_ptr = wt; ps.ws_ptr = ws; ps.thdr = th; ps.ops = ops_s;
         __syncthreads();
     }
     const int cluster_id = blockIdx.x / a.C;
@@ -476,11 +501,14 @@ __global__ void __launch_bounds__(NT, 1) k_resident(const ResArgs a) {
         }
         for (long long k = 0; k <= a.n; ++k) {
             const long long n = a.i0 + k;
+            long long tq = a.dbg_prof ? clock64() : 0;
             if (!(a.dbg_skip & 2) || k == 0 || k == a.n) junction_pass<WT, DEF>(a, rank, tile, n, k > 0, k < a.n, v);
             if (k == a.n) break;
             __syncthreads();
+            if (a.dbg_prof && threadIdx.x == 0) { const long long tn = clock64(); a.dbg_prof[(size_t)blockIdx.x * (2 + a.n_ops)] += tn - tq; tq = tn; }
             if (!(a.dbg_skip & 4)) face_pass<WT>(a, rank, tile, n, v);
             __syncthreads();
+            if (a.dbg_prof && threadIdx.x == 0) a.dbg_prof[(size_t)blockIdx.x * (2 + a.n_ops) + 1] += clock64() - tq;
             if (!(a.dbg_skip & 1)) run_ops<WT, CL>(a, ps, cluster, rank, v, stage, mbox);
         }
         __syncthreads();
@@ -579,10 +607,18 @@ int resident_set_plan(JJHandle* h, const JJResidentPlan* pl) {
         if ((rc = up(h, st, &wt, ps.wt_ptr, np))) return rc;
         if ((rc = up(h, st, &ws, ps.ws_ptr, np))) return rc;
         if ((rc = up(h, st, &th, ps.thdr, (size_t)ps.n_tiles * 2))) return rc;
-        if ((rc = up(h, st, &sb, ps.stream, (size_t)ps.n_steps * STEP_BYTES))) return rc;
+        {   // stream + 2*RING zero steps of padding (the kernel prefetches RING steps ahead unconditionally)
+            size_t nbytes = (size_t)ps.n_steps * STEP_BYTES, pad = (size_t)2 * RING * STEP_BYTES;
+            void* pbuf = nullptr;
+            if ((rc = dev_alloc(h, &pbuf, nbytes + pad))) return rc;
+            st->allocs.push_back(pbuf); st->alloc_bytes.push_back(nbytes + pad);
+            RCK(cudaMemsetAsync(pbuf, 0, nbytes + pad, h->stream));
+            if (nbytes) RCK(cudaMemcpyAsync(pbuf, ps.stream, nbytes, cudaMemcpyHostToDevice, h->stream));
+            sb = (unsigned char*)pbuf;
+        }
         st->prog[r].wt_ptr = wt; st->prog[r].ws_ptr = ws; st->prog[r].thdr = (const int2*)th; st->prog[r].stream = sb;
         st->prog[r].n_levels = ps.n_levels; st->prog[r].n_tiles = ps.n_tiles;
-        st->aux_ints = std::max<size_t>(st->aux_ints, 2 * np + 2 + 2 * (size_t)ps.n_tiles);
+        st->aux_ints = std::max<size_t>(st->aux_ints, 2 * np + 2 + 2 * (size_t)ps.n_tiles + 4 + 4 * (size_t)pl->n_ops);
     }
     if ((rc = up(h, st, &st->junc_ptr, pl->junc_ptr, (size_t)pl->C + 1))) return rc;
     if ((rc = up(h, st, &st->junc_orig, pl->junc_orig, (size_t)Nj))) return rc;
@@ -708,7 +744,34 @@ int resident_run(JJHandle* h, long long i0, int n, const long long* th_plane, co
     ResArgs a;
     fill_args(h, st, a);
     a.i0 = i0; a.n = n; a.th_plane = st->plane_d; a.I_plane = st->plane_d + n;
-    return launch(h, st, a);
+    if (!getenv("JJ_RES_PROF")) return launch(h, st, a);
+    // debugging aid: per-phase cycle counts of every block, printed as averages per time step
+    int ncl = std::min(st->n_tiles, st->max_clusters ? st->max_clusters : st->n_tiles);
+    size_t nb = (size_t)std::max(ncl, st->n_tiles) * st->C, slots = 2 + st->n_ops;
+    long long* prof = nullptr;
+    RCK(cudaMalloc((void**)&prof, nb * slots * sizeof(long long)));
+    RCK(cudaMemset(prof, 0, nb * slots * sizeof(long long)));
+    a.dbg_prof = prof;
+    int rc = launch(h, st, a);
+    if (rc) return rc;
+    RCK(cudaStreamSynchronize(h->stream));
+    std::vector<long long> hp(nb * slots);
+    RCK(cudaMemcpy(hp.data(), prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(prof);
+    std::vector<int> ops((size_t)st->C * st->n_ops * 4);
+    RCK(cudaMemcpy(ops.data(), st->ops, ops.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "JJ_RES_PROF: cycles per time step, averaged over blocks (n=%d steps, C=%d)\n", n, st->C);
+    double tot = 0;
+    for (size_t sl = 0; sl < slots; ++sl) {
+        double sum = 0, mx = 0; int cnt = 0;
+        for (size_t b = 0; b < nb; ++b) { double v = (double)hp[b * slots + sl] / n; if (v > 0) { sum += v; ++cnt; } mx = std::max(mx, v); }
+        double avg = cnt ? sum / cnt : 0; tot += avg;
+        if (sl == 0) fprintf(stderr, "  junction pass   avg %9.0f max %9.0f\n", avg, mx);
+        else if (sl == 1) fprintf(stderr, "  face pass       avg %9.0f max %9.0f\n", avg, mx);
+        else fprintf(stderr, "  op %2zu kind %d arg %4d avg %9.0f max %9.0f\n", sl - 2, ops[(sl - 2) * 4], ops[(sl - 2) * 4 + 1], avg, mx);
+    }
+    fprintf(stderr, "  total avg cycles per time step %.0f\n", tot);
+    return JJ_OK;
 }
 
 int resident_debug_solve(JJHandle* h, const double* b_d, double* J_d) {
