@@ -54,6 +54,7 @@ struct ResArgs {
     RankProg prog[MAXC];
     const int* junc_ptr; const int* junc_orig; const int2* junc_row; const char2* junc_sign;
     const int* face_ptr; const int* face_junc; const signed char* face_sign; const int* face_fidx;
+    int face_K; const int* face_ell_j; const double* face_ell_c;   // [C][n_rows][K] device junction / sign/c0
     // circuit
     int Nj, Nf;
     const double *P0;              // [Nj'][4] = Ic, 1/c0, c1, c2 in device junction order
@@ -88,6 +89,7 @@ struct ResidentState {
     int *junc_ptr = nullptr, *junc_orig = nullptr; int2* junc_row = nullptr; char2* junc_sign = nullptr;
     int *face_ptr = nullptr, *face_junc = nullptr; signed char* face_sign = nullptr; int* face_fidx = nullptr;
     double *P0 = nullptr, *P1 = nullptr;
+    int face_K = 0; int* face_ell_j = nullptr; double* face_ell_c = nullptr;
     // per problem
     double *rth = nullptr, *rx = nullptr; size_t state_bytes = 0;
     long long *plane_d = nullptr; size_t plane_cap = 0;
@@ -284,134 +286,202 @@ __device__ void run_ops(const ResArgs& a, const ProgSmem& ps, cg::cluster_group&
         a.dbg_prof[(size_t)blockIdx.x * (2 + a.n_ops) + 2 + (a.n_ops - 1)] += clock64() - tprev;
 }
 
-__device__ __forceinline__ void amp4(const Source& s, long long step, int Wp, int w, double out[4]) {
-    const double2* t = reinterpret_cast<const double2*>(s.table + source_row(s, step) * Wp + w);
-    double2 a0 = __ldg(t), a1 = __ldg(t + 1);
-    out[0] = a0.x; out[1] = a0.y; out[2] = a1.x; out[3] = a1.y;
+// Per-step amplitudes of the rank-one inputs for the 8 problems of this tile, cached in shared memory
+// (double-buffered by step parity so that Is of the previous step is still there for current snapshots).
+struct AmpCache {
+    double T[2][8], Is[2][8], Vs[2][8], F[2][8];
+};
+
+__device__ __forceinline__ void amp_fill(const ResArgs& a, AmpCache* ac, int tile, long long n) {
+    const int e = threadIdx.x & 7, which = threadIdx.x >> 3;
+    if (threadIdx.x >= 32) return;
+    const int w = tile * 8 + e;
+    const Source& s = which == 0 ? a.T : which == 1 ? a.Is : which == 2 ? a.Vs : a.F;
+    double val = 0.0;
+    if (s.kind == KIND_RANK1 && w < a.Wp) val = __ldg(s.table + source_row(s, n) * a.Wp + w);
+    double* dst = which == 0 ? ac->T[n & 1] : which == 1 ? ac->Is[n & 1] : which == 2 ? ac->Vs[n & 1] : ac->F[n & 1];
+    dst[e] = val;
+}
+
+// State and constants of one junction item (one junction x 4 problems), loaded one iteration ahead.
+struct JIn {
+    double2 x0, x1, t0, t1, pIc, pc, pb;
+    int2 rows;
+    int sg, jo;
+};
+
+template <int WT>
+__device__ __forceinline__ void jin_load(const ResArgs& a, int jlo, int tile, int idx, JIn& in) {
+    constexpr int G = WT / 4;
+    const int jp = jlo + idx / G;
+    const size_t sidx = ((size_t)tile * a.Nj + jlo) * WT + (size_t)idx * 4;
+    const double2* xp = reinterpret_cast<const double2*>(a.rx + sidx);
+    const double2* tp = reinterpret_cast<const double2*>(a.rth + sidx);
+    in.x0 = xp[0]; in.x1 = xp[1]; in.t0 = tp[0]; in.t1 = tp[1];
+    in.pIc = __ldg(reinterpret_cast<const double2*>(a.P0) + 2 * jp);
+    in.pc = __ldg(reinterpret_cast<const double2*>(a.P0) + 2 * jp + 1);
+    in.pb = __ldg(reinterpret_cast<const double2*>(a.P1) + 2 * jp);
+    in.rows = __ldg(a.junc_row + jp);
+    const char2 sg = a.junc_sign[jp];
+    in.sg = (int)sg.x * 4 + (int)sg.y;       // signs are -1, 0, +1
+    in.jo = __ldg(a.junc_orig + jp);
+}
+
+// theta_n = (A^T J - x)/c0, snapshots, x' for the next step  (reference: time_evolution.py:533-558, 570-580)
+template <int WT, bool DEF>
+__device__ __forceinline__ void junction_item(const ResArgs& a, const AmpCache* ac, int tile, long long n, int idx,
+                                              int jlo, bool do_pre, const JIn& in, const double* __restrict__ v,
+                                              double* snap_th, double* snap_I) {
+    constexpr int G = WT / 4;
+    const int q = (idx % G) * 4;
+    const int w = tile * WT + q;
+    if (w >= a.Wp) return;
+    const size_t sidx = ((size_t)tile * a.Nj + jlo) * WT + (size_t)idx * 4;
+    double y[4] = {0, 0, 0, 0};
+    if (in.rows.x >= 0) {
+        const double2 j0 = *chunk_ptr<WT>(v, in.rows.x, q >> 1), j1 = *chunk_ptr<WT>(v, in.rows.x, (q >> 1) + 1);
+        const double s = (double)((in.sg + 5) / 4 - 1);
+        y[0] = s * j0.x; y[1] = s * j0.y; y[2] = s * j1.x; y[3] = s * j1.y;
+    }
+    if (in.rows.y >= 0) {
+        const double2 j0 = *chunk_ptr<WT>(v, in.rows.y, q >> 1), j1 = *chunk_ptr<WT>(v, in.rows.y, (q >> 1) + 1);
+        const double s = (double)((in.sg + 5) % 4 - 1);
+        y[0] = fma(s, j0.x, y[0]); y[1] = fma(s, j0.y, y[1]); y[2] = fma(s, j1.x, y[2]); y[3] = fma(s, j1.y, y[3]);
+    }
+    const double ic0 = in.pIc.y;
+    double th1[4] = {(y[0] - in.x0.x) * ic0, (y[1] - in.x0.y) * ic0, (y[2] - in.x1.x) * ic0, (y[3] - in.x1.y) * ic0};
+    const double th2[4] = {in.t0.x, in.t0.y, in.t1.x, in.t1.y};
+    // one finiteness test for the four phases (a NaN or Inf in any of them poisons the sum)
+    if (!(fabs((th1[0] + th1[1]) + (th1[2] + th1[3])) < 1.0e300) && !a.dbg_skip) atomicOr(a.flag, 1);
+    if (snap_th || snap_I || !do_pre) {
+        const size_t cidx = (size_t)in.jo * a.Wp + w;
+        if (snap_th) {
+            double2* sp = reinterpret_cast<double2*>(snap_th + cidx);
+            sp[0] = make_double2(th1[0], th1[1]); sp[1] = make_double2(th1[2], th1[3]);
+        }
+        if (snap_I) {
+            const double* am = ac->Is[(n - 1) & 1] + q;
+            double2* sp = reinterpret_cast<double2*>(snap_I + cidx);
+            sp[0] = make_double2(y[0] + in.pb.x * am[0], y[1] + in.pb.x * am[1]);
+            sp[1] = make_double2(y[2] + in.pb.x * am[2], y[3] + in.pb.x * am[3]);
+        }
+        if (!do_pre) {
+            // end of the run: hand theta_last and theta_{last-1} back in the canonical layout
+            double2* o1 = reinterpret_cast<double2*>(a.th1 + cidx);
+            double2* o2 = reinterpret_cast<double2*>(a.th2 + cidx);
+            o1[0] = make_double2(th1[0], th1[1]); o1[1] = make_double2(th1[2], th1[3]);
+            o2[0] = in.t0; o2[1] = in.t1;
+            return;
+        }
+    }
+    double2* op = reinterpret_cast<double2*>(a.rth + sidx);
+    op[0] = make_double2(th1[0], th1[1]); op[1] = make_double2(th1[2], th1[3]);
+    const double Ic = in.pIc.x, c1 = in.pc.x, c2 = in.pc.y;
+    double fl[4] = {0, 0, 0, 0};
+    if (a.T.kind != KIND_ZERO && !(a.dbg_skip & 8)) {
+        double z[4];
+        if (a.noise_K > 0) {
+            const double2* zp = reinterpret_cast<const double2*>(a.noise + ((size_t)(n - a.noise_i0) * a.Nj + in.jo) * a.Wp + w);
+            const double2 z0 = zp[0], z1 = zp[1];
+            z[0] = z0.x; z[1] = z0.y; z[2] = z1.x; z[3] = z1.y;
+        } else {
+            normal4(a.seed, in.jo, a.group_offset + (w >> 2), n, z);
+        }
+        const double* am = ac->T[n & 1] + q;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) fl[k] = (in.pb.y * am[k]) * z[k];
+    }
+    const double* ia = ac->Is[n & 1] + q;
+    double xn[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double arg = 2.0 * th1[k] - th2[k];
+        const double X = Ic * ((a.dbg_skip & 16) ? arg : cpr_eval<DEF>(a.cpr, arg)) + c1 * th1[k] + c2 * th2[k];
+        xn[k] = (fl[k] - in.pb.x * ia[k]) + X;
+    }
+    double2* xo = reinterpret_cast<double2*>(a.rx + sidx);
+    xo[0] = make_double2(xn[0], xn[1]); xo[1] = make_double2(xn[2], xn[3]);
 }
 
 template <int WT, bool DEF>
-__device__ void junction_pass(const ResArgs& a, int rank, int tile, long long n, bool do_post, bool do_pre,
-                              const double* __restrict__ v) {
+__device__ void junction_pass(const ResArgs& a, const AmpCache* ac, int rank, int tile, long long n, bool do_post,
+                              bool do_pre, const double* __restrict__ v) {
     constexpr int G = WT / 4;
     const int jlo = a.junc_ptr[rank], jhi = a.junc_ptr[rank + 1];
     const int total = (jhi - jlo) * G;
+    if (!do_post) {
+        // first boundary of a run: theta(n-1), theta(n-2) come from the canonical arrays; no solve result yet
+        for (int idx = threadIdx.x; idx < total; idx += NT) {
+            const int jp = jlo + idx / G, q = (idx % G) * 4, w = tile * WT + q;
+            if (w >= a.Wp) continue;
+            const int jo = __ldg(a.junc_orig + jp);
+            const size_t sidx = ((size_t)tile * a.Nj + jlo) * WT + (size_t)idx * 4;
+            const size_t cidx = (size_t)jo * a.Wp + w;
+            const double2* p1 = reinterpret_cast<const double2*>(a.th1 + cidx);
+            const double2* p2 = reinterpret_cast<const double2*>(a.th2 + cidx);
+            const double2 u0 = p1[0], u1 = p1[1], v0 = p2[0], v1 = p2[1];
+            double2* op = reinterpret_cast<double2*>(a.rth + sidx);
+            op[0] = u0; op[1] = u1;
+            const double th1[4] = {u0.x, u0.y, u1.x, u1.y}, th2[4] = {v0.x, v0.y, v1.x, v1.y};
+            const double2 pIc = __ldg(reinterpret_cast<const double2*>(a.P0) + 2 * jp);
+            const double2 pc = __ldg(reinterpret_cast<const double2*>(a.P0) + 2 * jp + 1);
+            const double2 pb = __ldg(reinterpret_cast<const double2*>(a.P1) + 2 * jp);
+            double fl[4] = {0, 0, 0, 0};
+            if (a.T.kind != KIND_ZERO) {
+                double z[4];
+                if (a.noise_K > 0) {
+                    const double2* zp = reinterpret_cast<const double2*>(a.noise + ((size_t)(n - a.noise_i0) * a.Nj + jo) * a.Wp + w);
+                    const double2 z0 = zp[0], z1 = zp[1];
+                    z[0] = z0.x; z[1] = z0.y; z[2] = z1.x; z[3] = z1.y;
+                } else {
+                    normal4(a.seed, jo, a.group_offset + (w >> 2), n, z);
+                }
+                const double* am = ac->T[n & 1] + q;
+                for (int k = 0; k < 4; ++k) fl[k] = (pb.y * am[k]) * z[k];
+            }
+            const double* ia = ac->Is[n & 1] + q;
+            double xn[4];
+            for (int k = 0; k < 4; ++k) {
+                const double X = pIc.x * cpr_eval<DEF>(a.cpr, 2.0 * th1[k] - th2[k]) + pc.x * th1[k] + pc.y * th2[k];
+                xn[k] = (fl[k] - pb.x * ia[k]) + X;
+            }
+            double2* xo = reinterpret_cast<double2*>(a.rx + sidx);
+            xo[0] = make_double2(xn[0], xn[1]); xo[1] = make_double2(xn[2], xn[3]);
+        }
+        return;
+    }
     double* snap_th = nullptr; double* snap_I = nullptr;
-    if (do_post) {
-        long long k = n - 1 - a.i0;
-        long long pt = a.th_plane ? a.th_plane[k] : -1, pi = a.I_plane ? a.I_plane[k] : -1;
+    {
+        const long long k = n - 1 - a.i0;
+        const long long pt = a.th_plane ? a.th_plane[k] : -1, pi = a.I_plane ? a.I_plane[k] : -1;
         if (pt >= 0) snap_th = a.snap_th + (size_t)pt * a.Nj * a.Wp;
         if (pi >= 0) snap_I = a.snap_I + (size_t)pi * a.Nj * a.Wp;
     }
-    for (int idx = threadIdx.x; idx < total; idx += NT) {
-        const int jp = jlo + idx / G;
-        const int q = (idx % G) * 4;
-        const int w = tile * WT + q;
-        if (w >= a.Wp) continue;
-        const int jo = __ldg(a.junc_orig + jp);
-        const size_t sidx = ((size_t)tile * a.Nj + jp) * WT + q;
-        const double2 pIc = __ldg(reinterpret_cast<const double2*>(a.P0) + 2 * jp);       // Ic, 1/c0
-        const double2 pc = __ldg(reinterpret_cast<const double2*>(a.P0) + 2 * jp + 1);    // c1, c2
-        const double2 pb = __ldg(reinterpret_cast<const double2*>(a.P1) + 2 * jp);        // Is base, noise base
-        if (idx + 2 * NT < total) {      // pull the state two iterations ahead into L2
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.rx + sidx + 8 * NT));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.rth + sidx + 8 * NT));
+    // software pipeline: the loads of the next item are in flight while the current one is computed
+    JIn cur, nxt;
+    int idx = threadIdx.x;
+    if (idx < total) jin_load<WT>(a, jlo, tile, idx, cur);
+    for (; idx < total; idx += NT) {
+        const bool more = idx + NT < total;
+        if (more) jin_load<WT>(a, jlo, tile, idx + NT, nxt);
+        if (idx + 3 * NT < total) {      // and the state three iterations ahead is pulled into L2
+            const size_t pf = ((size_t)tile * a.Nj + jlo) * WT + (size_t)(idx + 3 * NT) * 4;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.rx + pf));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.rth + pf));
         }
-        const size_t cidx = (size_t)jo * a.Wp + w;
-        double th1[4], th2[4];
-        if (do_post) {
-            double y[4] = {0, 0, 0, 0};
-            int2 rows = __ldg(a.junc_row + jp);
-            char2 sg = a.junc_sign[jp];
-            if (rows.x >= 0) {
-                double2 j0 = *chunk_ptr<WT>(v, rows.x, q >> 1), j1 = *chunk_ptr<WT>(v, rows.x, (q >> 1) + 1);
-                double s = (double)sg.x;
-                y[0] += s * j0.x; y[1] += s * j0.y; y[2] += s * j1.x; y[3] += s * j1.y;
-            }
-            if (rows.y >= 0) {
-                double2 j0 = *chunk_ptr<WT>(v, rows.y, q >> 1), j1 = *chunk_ptr<WT>(v, rows.y, (q >> 1) + 1);
-                double s = (double)sg.y;
-                y[0] += s * j0.x; y[1] += s * j0.y; y[2] += s * j1.x; y[3] += s * j1.y;
-            }
-            const double2* xp = reinterpret_cast<const double2*>(a.rx + sidx);
-            double2 x0 = xp[0], x1 = xp[1];
-            const double2* tp = reinterpret_cast<const double2*>(a.rth + sidx);
-            double2 t0 = tp[0], t1 = tp[1];
-            th2[0] = t0.x; th2[1] = t0.y; th2[2] = t1.x; th2[3] = t1.y;
-            const double ic0 = pIc.y;
-            th1[0] = (y[0] - x0.x) * ic0; th1[1] = (y[1] - x0.y) * ic0;
-            th1[2] = (y[2] - x1.x) * ic0; th1[3] = (y[3] - x1.y) * ic0;
-            if (!(isfinite(th1[0]) && isfinite(th1[1]) && isfinite(th1[2]) && isfinite(th1[3])) && !a.dbg_skip) atomicOr(a.flag, 1);
-            if (snap_th) {
-                double2* sp = reinterpret_cast<double2*>(snap_th + cidx);
-                sp[0] = make_double2(th1[0], th1[1]); sp[1] = make_double2(th1[2], th1[3]);
-            }
-            if (snap_I) {
-                double is[4] = {0, 0, 0, 0};
-                if (a.Is.kind == KIND_RANK1) {
-                    double am[4]; amp4(a.Is, n - 1, a.Wp, w, am);
-                    for (int k = 0; k < 4; ++k) is[k] = pb.x * am[k];
-                }
-                double2* sp = reinterpret_cast<double2*>(snap_I + cidx);
-                sp[0] = make_double2(y[0] + is[0], y[1] + is[1]); sp[1] = make_double2(y[2] + is[2], y[3] + is[3]);
-            }
-            if (do_pre) {
-                double2* op = reinterpret_cast<double2*>(a.rth + sidx);
-                op[0] = make_double2(th1[0], th1[1]); op[1] = make_double2(th1[2], th1[3]);
-            } else {
-                // end of the run: hand theta_last and theta_{last-1} back in the canonical layout
-                double2* o1 = reinterpret_cast<double2*>(a.th1 + cidx);
-                double2* o2 = reinterpret_cast<double2*>(a.th2 + cidx);
-                o1[0] = make_double2(th1[0], th1[1]); o1[1] = make_double2(th1[2], th1[3]);
-                o2[0] = make_double2(th2[0], th2[1]); o2[1] = make_double2(th2[2], th2[3]);
-            }
-        } else {
-            const double2* p1 = reinterpret_cast<const double2*>(a.th1 + cidx);
-            const double2* p2 = reinterpret_cast<const double2*>(a.th2 + cidx);
-            double2 u0 = p1[0], u1 = p1[1], v0 = p2[0], v1 = p2[1];
-            th1[0] = u0.x; th1[1] = u0.y; th1[2] = u1.x; th1[3] = u1.y;
-            th2[0] = v0.x; th2[1] = v0.y; th2[2] = v1.x; th2[3] = v1.y;
-            double2* op = reinterpret_cast<double2*>(a.rth + sidx);
-            op[0] = u0; op[1] = u1;
-        }
-        if (!do_pre) continue;
-        const double Ic = pIc.x, c1 = pc.x, c2 = pc.y;
-        double fl[4] = {0, 0, 0, 0};
-        if (a.T.kind != KIND_ZERO && !(a.dbg_skip & 8)) {
-            double z[4], am[4];
-            if (a.noise_K > 0) {
-                const double2* zp = reinterpret_cast<const double2*>(a.noise + ((size_t)(n - a.noise_i0) * a.Nj + jo) * a.Wp + w);
-                double2 z0 = zp[0], z1 = zp[1];
-                z[0] = z0.x; z[1] = z0.y; z[2] = z1.x; z[3] = z1.y;
-            } else {
-                normal4(a.seed, jo, a.group_offset + (w >> 2), n, z);
-            }
-            amp4(a.T, n, a.Wp, w, am);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) fl[k] = (pb.y * am[k]) * z[k];
-        }
-        double is[4] = {0, 0, 0, 0};
-        if (a.Is.kind == KIND_RANK1) {
-            double am[4]; amp4(a.Is, n, a.Wp, w, am);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) is[k] = pb.x * am[k];
-        }
-        double xn[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const double arg = 2.0 * th1[k] - th2[k];
-            double X = Ic * ((a.dbg_skip & 16) ? arg : cpr_eval<DEF>(a.cpr, arg)) + c1 * th1[k] + c2 * th2[k];
-            xn[k] = (fl[k] - is[k]) + X;
-        }
-        double2* xo = reinterpret_cast<double2*>(a.rx + sidx);
-        xo[0] = make_double2(xn[0], xn[1]); xo[1] = make_double2(xn[2], xn[3]);
+        junction_item<WT, DEF>(a, ac, tile, n, idx, jlo, do_pre, cur, v, snap_th, snap_I);
+        if (more) cur = nxt;
     }
 }
 
+// b = A (x'/c0 - theta_s) - 2 pi f into shared memory (reference: time_evolution.py:560-569). Every row has a
+// fixed-width list of (device junction, +-1/c0) pairs so all loads of a thread are independent.
 template <int WT>
-__device__ void face_pass(const ResArgs& a, int rank, int tile, long long n, double* __restrict__ v) {
+__device__ void face_pass(const ResArgs& a, const AmpCache* ac, int rank, int tile, long long n, double* __restrict__ v) {
     constexpr int G = WT / 4;
-    const int* fptr = a.face_ptr + (size_t)rank * (a.n_rows + 1);
+    const int K = a.face_K;
+    const int* fj = a.face_ell_j + (size_t)rank * a.n_rows * K;
+    const double* fc = a.face_ell_c + (size_t)rank * a.n_rows * K;
     const int* fidx = a.face_fidx + (size_t)rank * a.n_rows;
     const int total = a.n_rows * G;
     for (int idx = threadIdx.x; idx < total; idx += NT) {
@@ -420,27 +490,44 @@ __device__ void face_pass(const ResArgs& a, int rank, int tile, long long n, dou
         const int w = tile * WT + q;
         double acc[4] = {0, 0, 0, 0};
         if (w < a.Wp) {
-            double cum[4] = {0, 0, 0, 0};
-            if (a.Vs.kind == KIND_RANK1) amp4(a.Vs, n, a.Wp, w, cum);
-            const int p0 = __ldg(fptr + row), p1 = __ldg(fptr + row + 1);
-            for (int p = p0; p < p1; ++p) {
-                const int jp = __ldg(a.face_junc + p);
-                const double s = (double)a.face_sign[p];
-                const double ic0 = __ldg(a.P0 + 4 * (size_t)jp + 1);
-                const double2* xp = reinterpret_cast<const double2*>(a.rx + ((size_t)tile * a.Nj + jp) * WT + q);
-                double2 x0 = __ldcg(xp), x1 = __ldcg(xp + 1);
-                double u[4] = {x0.x * ic0, x0.y * ic0, x1.x * ic0, x1.y * ic0};
-                if (a.Vs.kind == KIND_RANK1) {
-                    const double b = __ldg(a.P1 + 4 * (size_t)jp + 2);
+            const size_t tbase = (size_t)tile * a.Nj * WT + q;
+            for (int k0 = 0; k0 < K; k0 += 4) {
+                int jp[4]; double cf[4]; double2 xa[4], xb[4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) u[k] -= b * cum[k];
+                for (int k = 0; k < 4; ++k) {
+                    jp[k] = (k0 + k < K) ? __ldg(fj + (size_t)row * K + k0 + k) : -1;
+                    cf[k] = (k0 + k < K) ? __ldg(fc + (size_t)row * K + k0 + k) : 0.0;
                 }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) acc[k] += s * u[k];
+                for (int k = 0; k < 4; ++k) {
+                    if (jp[k] >= 0) {
+                        const double2* xp = reinterpret_cast<const double2*>(a.rx + tbase + (size_t)jp[k] * WT);
+                        xa[k] = __ldcg(xp); xb[k] = __ldcg(xp + 1);
+                    } else {
+                        xa[k] = make_double2(0, 0); xb[k] = make_double2(0, 0);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    acc[0] = fma(cf[k], xa[k].x, acc[0]); acc[1] = fma(cf[k], xa[k].y, acc[1]);
+                    acc[2] = fma(cf[k], xb[k].x, acc[2]); acc[3] = fma(cf[k], xb[k].y, acc[3]);
+                }
+                if (a.Vs.kind == KIND_RANK1) {
+                    const double* cum = ac->Vs[n & 1] + q;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (jp[k] >= 0) {
+                            // coefficient = sign / c0: recover sign * Vs base from the per-junction records
+                            const double ic0 = __ldg(a.P0 + 4 * (size_t)jp[k] + 1), vb = __ldg(a.P1 + 4 * (size_t)jp[k] + 2);
+                            const double sv = (cf[k] / ic0) * vb;
+                            for (int e = 0; e < 4; ++e) acc[e] -= sv * cum[e];
+                        }
+                    }
+                }
             }
             const int g = __ldg(fidx + row);
             if (g >= 0 && a.F.kind == KIND_RANK1) {
-                double am[4]; amp4(a.F, n, a.Wp, w, am);
+                const double* am = ac->F[n & 1] + q;
                 const double b = __ldg(a.F.base + g);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) acc[k] -= 6.283185307179586 * (b * am[k]);
@@ -460,6 +547,7 @@ __global__ void __launch_bounds__(NT, 1) k_resident(const ResArgs a) {
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = CL ? (int)cluster.block_rank() : 0;
     ProgSmem ps;
+    AmpCache* ac;
     {
         int* aux = reinterpret_cast<int*>(mbox + (size_t)(a.ar_rows + 8 * a.C) * WT);
         const RankProg& p = a.prog[rank];
@@ -467,9 +555,10 @@ __global__ void __launch_bounds__(NT, 1) k_resident(const ResArgs a) {
         int* wt = aux; int* ws = aux + np; int2* th = reinterpret_cast<int2*>(aux + 2 * np);
         for (int e = threadIdx.x; e < np; e += NT) { wt[e] = p.wt_ptr[e]; ws[e] = p.ws_ptr[e]; }
         for (int e = threadIdx.x; e < p.n_tiles; e += NT) th[e] = p.thdr[e];
-        int4* ops_s = reinterpret_cast<int4*>(th + p.n_tiles + (p.n_tiles & 1));
+        int4* ops_s = reinterpret_cast<int4*>((reinterpret_cast<uintptr_t>(th + p.n_tiles) + 15) & ~(uintptr_t)15);
         for (int e = threadIdx.x; e < a.n_ops; e += NT) ops_s[e] = a.ops[(size_t)rank * a.n_ops + e];
         ps.wt_ptr = wt; ps.ws_ptr = ws; ps.thdr = th; ps.ops = ops_s;
+        ac = reinterpret_cast<AmpCache*>(ops_s + a.n_ops);
         __syncthreads();
     }
     const int cluster_id = blockIdx.x / a.C;
@@ -499,14 +588,17 @@ __global__ void __launch_bounds__(NT, 1) k_resident(const ResArgs a) {
             __syncthreads();
             continue;
         }
+        amp_fill(a, ac, tile, a.i0);
+        __syncthreads();
         for (long long k = 0; k <= a.n; ++k) {
             const long long n = a.i0 + k;
             long long tq = a.dbg_prof ? clock64() : 0;
-            if (!(a.dbg_skip & 2) || k == 0 || k == a.n) junction_pass<WT, DEF>(a, rank, tile, n, k > 0, k < a.n, v);
+            if (!(a.dbg_skip & 2) || k == 0 || k == a.n) junction_pass<WT, DEF>(a, ac, rank, tile, n, k > 0, k < a.n, v);
             if (k == a.n) break;
             __syncthreads();
             if (a.dbg_prof && threadIdx.x == 0) { const long long tn = clock64(); a.dbg_prof[(size_t)blockIdx.x * (2 + a.n_ops)] += tn - tq; tq = tn; }
-            if (!(a.dbg_skip & 4)) face_pass<WT>(a, rank, tile, n, v);
+            if (!(a.dbg_skip & 4)) face_pass<WT>(a, ac, rank, tile, n, v);
+            if (k + 1 < a.n) amp_fill(a, ac, tile, n + 1);     // other parity: read after the barriers of the sweeps
             __syncthreads();
             if (a.dbg_prof && threadIdx.x == 0) a.dbg_prof[(size_t)blockIdx.x * (2 + a.n_ops) + 1] += clock64() - tq;
             if (!(a.dbg_skip & 1)) run_ops<WT, CL>(a, ps, cluster, rank, v, stage, mbox);
@@ -618,7 +710,7 @@ int resident_set_plan(JJHandle* h, const JJResidentPlan* pl) {
         }
         st->prog[r].wt_ptr = wt; st->prog[r].ws_ptr = ws; st->prog[r].thdr = (const int2*)th; st->prog[r].stream = sb;
         st->prog[r].n_levels = ps.n_levels; st->prog[r].n_tiles = ps.n_tiles;
-        st->aux_ints = std::max<size_t>(st->aux_ints, 2 * np + 2 + 2 * (size_t)ps.n_tiles + 4 + 4 * (size_t)pl->n_ops);
+        st->aux_ints = std::max<size_t>(st->aux_ints, 2 * np + 2 + 2 * (size_t)ps.n_tiles + 4 + 4 * (size_t)pl->n_ops + sizeof(AmpCache) / sizeof(int) + 16);
     }
     if ((rc = up(h, st, &st->junc_ptr, pl->junc_ptr, (size_t)pl->C + 1))) return rc;
     if ((rc = up(h, st, &st->junc_orig, pl->junc_orig, (size_t)Nj))) return rc;
@@ -631,6 +723,31 @@ int resident_set_plan(JJHandle* h, const JJResidentPlan* pl) {
     if ((rc = up(h, st, &st->face_junc, pl->face_junc, (size_t)nent))) return rc;
     if ((rc = up(h, st, &st->face_sign, (const signed char*)pl->face_sign, (size_t)nent))) return rc;
     if ((rc = up(h, st, &st->face_fidx, pl->face_fidx, (size_t)pl->C * pl->n_rows))) return rc;
+    {   // fixed-width (ELL) form of the per-rank face lists with the coefficient sign / c0 folded in
+        int K = 1;
+        for (int r = 0; r < pl->C; ++r)
+            for (int row = 0; row < pl->n_rows; ++row) {
+                const int* fp = pl->face_ptr + (size_t)r * (pl->n_rows + 1) + row;
+                K = std::max(K, fp[1] - fp[0]);
+            }
+        K = (K + 3) / 4 * 4;
+        std::vector<int> ej((size_t)pl->C * pl->n_rows * K, -1);
+        std::vector<double> ec((size_t)pl->C * pl->n_rows * K, 0.0);
+        std::vector<double> c0h(Nj);
+        RCK(cudaMemcpy(c0h.data(), h->cir.c0, (size_t)Nj * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int r = 0; r < pl->C; ++r)
+            for (int row = 0; row < pl->n_rows; ++row) {
+                const int* fp = pl->face_ptr + (size_t)r * (pl->n_rows + 1) + row;
+                for (int p = fp[0]; p < fp[1]; ++p) {
+                    size_t o = ((size_t)r * pl->n_rows + row) * K + (p - fp[0]);
+                    ej[o] = pl->face_junc[p];
+                    ec[o] = (double)pl->face_sign[p] * (1.0 / c0h[pl->junc_orig[pl->face_junc[p]]]);
+                }
+            }
+        st->face_K = K;
+        if ((rc = up(h, st, &st->face_ell_j, ej.data(), ej.size()))) return rc;
+        if ((rc = up(h, st, &st->face_ell_c, ec.data(), ec.size()))) return rc;
+    }
     for (double** pp : {&st->P0, &st->P1}) {
         void* p = nullptr;
         if ((rc = dev_alloc(h, &p, (size_t)Nj * 4 * sizeof(double)))) return rc;
@@ -659,6 +776,7 @@ static int fill_args(JJHandle* h, ResidentState* st, ResArgs& a) {
     for (int r = 0; r < st->C; ++r) a.prog[r] = st->prog[r];
     a.junc_ptr = st->junc_ptr; a.junc_orig = st->junc_orig; a.junc_row = st->junc_row; a.junc_sign = st->junc_sign;
     a.face_ptr = st->face_ptr; a.face_junc = st->face_junc; a.face_sign = st->face_sign; a.face_fidx = st->face_fidx;
+    a.face_K = st->face_K; a.face_ell_j = st->face_ell_j; a.face_ell_c = st->face_ell_c;
     a.Nj = h->cir.Nj; a.Nf = h->cir.Nf; a.P0 = st->P0; a.P1 = st->P1;
     a.cpr = h->cir.cpr;
     a.Wp = h->Wp; a.n_tiles = st->n_tiles; a.dt = h->dt; a.seed = h->seed; a.group_offset = h->problem_offset / 4;

@@ -98,7 +98,7 @@ class CircuitTables:
     SMEM_LIMIT = 227 * 1024
 
     def resident_smem_bytes(self, plan, Wt):
-        aux = max(2 * (ps["n_levels"] * ps["n_warps"] + 1) + 6 + 2 * len(ps["thdr"]) for ps in plan.prog) + 4 * plan.ops.shape[1]
+        aux = max(2 * (ps["n_levels"] * ps["n_warps"] + 1) + 6 + 2 * len(ps["thdr"]) for ps in plan.prog) + 4 * plan.ops.shape[1] + 140
         return ((plan.n_rows + plan.allreduce_rows + 8 * plan.C) * Wt + plan.stage_rows * (Wt + 2)) * 8 + 4 * aux
 
     def choose_resident(self, W):

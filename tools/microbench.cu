@@ -53,6 +53,23 @@ __global__ void k_ldg_chase(long long* out, const int* next, int n) {
     long long t1 = clock64();
     if (threadIdx.x == 0) { out[0] = (t1 - t0); out[1] = p; }
 }
+__global__ void k_prefetch(long long* out, const int* next, const int* chain, int mode) {
+    // mode 0: cold chase; 1: prefetch.global.L1 of the chain first; 2: prefetch.global.L2; 3: plain loads first (warm)
+    int acc = 0;
+    for (int i = 0; i < 64; ++i) {
+        const int* p = next + chain[i];
+        if (mode == 1) asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+        if (mode == 2) asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+        if (mode == 3) acc += __ldg(p);
+    }
+    long long t0 = clock64();
+    while (clock64() - t0 < 20000) {}
+    int p = chain[0] + (acc & 0);
+    long long t1 = clock64();
+    for (int i = 0; i < 64; ++i) p = __ldg(next + p);
+    long long t2 = clock64();
+    if (threadIdx.x == 0) { out[0] = t2 - t1; out[1] = p; }
+}
 __global__ void k_sync(long long* out, int n) {
     long long t0 = clock64();
     for (int i = 0; i < n; ++i) __syncthreads();
@@ -79,6 +96,15 @@ int main() {
         if (rep) printf("LDS + dependent DMMA chain: %.1f cycles per step\n", (double)h[0] / n);
         k_ldg_chase<<<1, 32>>>(d, next, n); cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
         if (rep) printf("dependent __ldg chase (L2): %.1f cycles per load\n", (double)h[0] / n);
+        for (int mode = 0; mode < 4; ++mode) {
+            int hc[64]; int p = 777 + 100000 * (mode + 4 * rep);
+            for (int i = 0; i < 64; ++i) { hc[i] = p; p = hn[p]; }
+            int* dc; cudaMalloc(&dc, 256); cudaMemcpy(dc, hc, 256, cudaMemcpyHostToDevice);
+            k_prefetch<<<1, 1>>>(d, next, dc, mode); cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+            const char* nm[4] = {"nothing (cold)", "prefetch.global.L1", "prefetch.global.L2", "plain loads (warm L1/L2)"};
+            if (rep) printf("dependent load latency after %s: %.1f cycles\n", nm[mode], h[0] / 64.0);
+            cudaFree(dc);
+        }
         k_sync<<<1, 512>>>(d, n); cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
         if (rep) printf("__syncthreads, 512 threads: %.1f cycles\n", (double)h[0] / n);
     }
