@@ -102,8 +102,13 @@ def run_ours(args, rank, world, local_rank, dist):
     eng = engine.DeviceEngine(local_rank)
     eng.set_circuit(tab, pj.DefaultCPR())
     kind = {"auto": _lib.JJ_ENGINE_AUTO, "streaming": _lib.JJ_ENGINE_STREAMING,
-            "resident": _lib.JJ_ENGINE_RESIDENT}[os.environ.get("JJ_ENGINE", "auto")]
-    if kind != _lib.JJ_ENGINE_STREAMING:
+            "resident": _lib.JJ_ENGINE_RESIDENT, "subdomain": _lib.JJ_ENGINE_SUBDOMAIN}[os.environ.get("JJ_ENGINE", "auto")]
+    cfg = None
+    if kind in (_lib.JJ_ENGINE_AUTO, _lib.JJ_ENGINE_SUBDOMAIN):
+        cfg = tab.choose_subdomain(W)
+        if cfg is not None:
+            eng.set_subdomain(*cfg)
+    if kind == _lib.JJ_ENGINE_RESIDENT or (kind == _lib.JJ_ENGINE_AUTO and cfg is None):
         cfg = tab.choose_resident(W)
         if cfg is not None:
             eng.set_resident(*cfg)
@@ -203,8 +208,8 @@ def run_ours(args, rank, world, local_rank, dist):
            "config": {"workload": f"cfg2: SquareArray({NX},{NX}) f=0.1 thermal noise, {W} temperatures per GPU, dt=0.5",
                       "Nj": tab.Nj, "Nf": tab.Nf, "problems_per_gpu": W, "time_steps_per_step": INNER,
                       "l2": "256 MiB buffer written between timed steps (L2 flush)", "noise": "device Philox4x32-10, seed 1234",
-                      "engine": {1: "streaming", 2: "resident"}.get(st["engine"], str(st["engine"])),
-                      "cluster_size": st["cluster_size"], "tile_problems": st["tile_problems"]},
+                      "engine": {1: "streaming", 2: "resident", 3: "subdomain"}.get(st["engine"], str(st["engine"])),
+                      "subdomains_or_cluster": st["cluster_size"], "problems_per_block": st["tile_problems"]},
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": traffic, "peak_source": peak_src,

@@ -38,8 +38,11 @@ enum { JJ_KIND_ZERO = 0, JJ_KIND_RANK1 = 1, JJ_KIND_DENSE = 2 };
 /* step engines */
 enum { JJ_ENGINE_AUTO = 0,      /* pick RESIDENT when the problem fits, else STREAMING */
        JJ_ENGINE_STREAMING = 1, /* problem-minor (Nj, W) arrays in HBM, one kernel per phase */
-       JJ_ENGINE_RESIDENT = 2   /* persistent kernel: a thread-block cluster owns a tile of problems for the
-                                   whole time loop, right-hand sides live in shared memory */ };
+       JJ_ENGINE_RESIDENT = 2,  /* persistent kernel: a thread-block cluster owns a tile of problems for the
+                                   whole time loop, right-hand sides live in shared memory */
+       JJ_ENGINE_SUBDOMAIN = 3  /* persistent cooperative kernel: a thread block owns a (subdomain of the
+                                   elimination tree, chunk of problems) pair; the separators above the cut are
+                                   solved for all problems at once by a dense FP64 tensor-core product */ };
 
 /* One sweep (forward or backward) of the compiled solve program, see pyjjasim_b200/factor.py.
  * Replaces the two SuperLU triangular sweeps per step (reference: time_evolution.py:506, :560-569). */
@@ -95,6 +98,42 @@ typedef struct {
     const int32_t *face_fidx;        /* [C*n_rows] permuted face index if this rank adds the flux term, else -1 */
 } JJResidentPlan;
 
+/* Subdomain engine: sweep program of one subdomain, packed like JJRankStream; levels [0, n_bwd) are the
+ * backward sweep, [n_bwd, n_levels) the forward sweep (pyjjasim_b200/subdomain.py). */
+typedef struct {
+    int32_t n_levels, n_bwd, n_warps, n_tiles;
+    const int32_t *wt_ptr;       /* [n_levels*n_warps + 1] */
+    const int32_t *ws_ptr;       /* [n_levels*n_warps + 1] */
+    const int32_t *thdr;         /* [n_tiles][2]: row0 | (nrows-1)<<16 | flags<<19 | g0<<21 | (ng-1)<<25 ; nsteps | stage_off<<16 */
+    const int32_t *lstaged;      /* [n_levels] staged rows of the level */
+    int64_t n_steps;
+    const uint8_t *stream;       /* [n_steps][320] as in JJRankStream; element codes address rows of 8*NG float64 */
+} JJSubProgram;
+
+/* Subdomain-engine plan (pyjjasim_b200/subdomain.py: subdomain_plan). Replaces the two SuperLU sweeps per step
+ * (reference: time_evolution.py:506, :560-569): P uncoupled subdomains + n_top separator rows whose Schur
+ * complement inverse is applied as a dense product. */
+typedef struct {
+    int32_t P, NG;                   /* subdomains; problems per chunk = 8*NG (NG = 1, 2, 4, 8) */
+    int32_t n_rows, n_loc_max, stage_rows;
+    int32_t n_top, n_top_pad, n_slots;
+    const int32_t *n_loc, *n_halo;   /* [P] local rows / halo rows (coupled top rows) of each subdomain */
+    const int32_t *hptr;             /* [P+1] first contribution slot of each subdomain */
+    const int32_t *halo_top;         /* [n_slots] top row of each slot */
+    const int32_t *tptr, *tslot;     /* [n_top+1], [n_slots]: slots that sum into each top row */
+    const int32_t *top_face;         /* [n_top] permuted face index of each top row */
+    const double  *Sinv_packed;      /* [n_top_pad/8][n_top_pad/4][8][4] MMA A fragments of S_top^-1 */
+    const JJSubProgram *prog;        /* [P] */
+    const int32_t *junc_ptr;         /* [P+1] subdomain s owns device junctions junc_ptr[s]:junc_ptr[s+1] */
+    const int32_t *junc_orig;        /* [Nj] */
+    const int32_t *junc_row;         /* [Nj*2] shared-memory rows of its faces on the owner, -1 none */
+    const int8_t  *junc_sign;        /* [Nj*2] */
+    int32_t face_K;                  /* fixed width of the face lists (multiple of 4) */
+    const int32_t *face_ell_j;       /* [P][n_rows][face_K] device junction, -1 pad */
+    const double  *face_ell_c;       /* [P][n_rows][face_K] sign / c0 */
+    const int32_t *face_fidx;        /* [P][n_rows] permuted face index of local rows, -1 for halo rows */
+} JJSubdomainPlan;
+
 /* Circuit constants, per junction, precomputed on the host in float64 exactly as the reference does
  * (reference: time_evolution.py:470-478): Rv = 1/(dt R), Cv = C/dt^2, c0 = Rv+Cv, c1 = -Rv-2Cv, c2 = Cv. */
 typedef struct {
@@ -119,6 +158,8 @@ int jj_set_circuit(JJHandle *h, const JJCircuit *c);
 int jj_set_solver(JJHandle *h, const JJSweep *fwd, const JJSweep *bwd);
 /* optional: enables JJ_ENGINE_RESIDENT. Must follow jj_set_circuit/jj_set_solver. plan == NULL removes it. */
 int jj_set_resident_plan(JJHandle *h, const JJResidentPlan *plan);
+/* optional: enables JJ_ENGINE_SUBDOMAIN. Must follow jj_set_circuit/jj_set_solver. plan == NULL removes it. */
+int jj_set_subdomain_plan(JJHandle *h, const JJSubdomainPlan *plan);
 /* W problems, time step dt, Philox seed, index of this shard's first problem in the global batch
  * (keeps noise identical however the batch is sharded over GPUs; must be a multiple of 4) */
 int jj_set_problem(JJHandle *h, int32_t W, double dt, uint64_t seed, int64_t problem_offset, int32_t engine);
@@ -149,6 +190,9 @@ int jj_debug_noise(JJHandle *h, int64_t step, double *dst);
 int jj_debug_solve(JJHandle *h, const double *b, double *J);
 /* the same through the resident engine's cluster kernel (requires a resident plan) */
 int jj_debug_resident_solve(JJHandle *h, const double *b, double *J);
+
+/* the same through the subdomain engine's cooperative kernel (requires a subdomain plan) */
+int jj_debug_subdomain_solve(JJHandle *h, const double *b, double *J);
 
 typedef struct {
     int32_t engine;             /* engine actually used */

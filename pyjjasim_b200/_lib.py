@@ -14,14 +14,14 @@ LIB_PATH = os.path.join(_HERE, "libjjstep.so")
 
 JJ_SRC_IS, JJ_SRC_F, JJ_SRC_VS, JJ_SRC_T = 0, 1, 2, 3
 JJ_KIND_ZERO, JJ_KIND_RANK1, JJ_KIND_DENSE = 0, 1, 2
-JJ_ENGINE_AUTO, JJ_ENGINE_STREAMING, JJ_ENGINE_RESIDENT = 0, 1, 2
+JJ_ENGINE_AUTO, JJ_ENGINE_STREAMING, JJ_ENGINE_RESIDENT, JJ_ENGINE_SUBDOMAIN = 0, 1, 2, 3
 JJ_ENONFINITE = -5
 
 EXPORTS = ["jj_create", "jj_destroy", "jj_last_error", "jj_set_circuit", "jj_set_solver", "jj_set_problem",
            "jj_set_state", "jj_get_state", "jj_set_source", "jj_upload_source", "jj_upload_noise",
            "jj_alloc_outputs", "jj_run", "jj_fetch_theta", "jj_fetch_current", "jj_debug_noise",
            "jj_debug_solve", "jj_stats", "jj_set_resident_plan",
-           "jj_debug_resident_solve"]
+           "jj_debug_resident_solve", "jj_set_subdomain_plan", "jj_debug_subdomain_solve"]
 
 _p = C.c_void_p
 _i32p = C.POINTER(C.c_int32)
@@ -50,6 +50,21 @@ class JJResidentPlan(C.Structure):
                 ("n_fwd_ops", C.c_int32), ("ops", _i32p), ("prog", C.POINTER(JJRankStream)),
                 ("junc_ptr", _i32p), ("junc_orig", _i32p), ("junc_row", _i32p), ("junc_sign", _i8p),
                 ("face_ptr", _i32p), ("face_junc", _i32p), ("face_sign", _i8p), ("face_fidx", _i32p)]
+
+
+class JJSubProgram(C.Structure):
+    _fields_ = [("n_levels", C.c_int32), ("n_bwd", C.c_int32), ("n_warps", C.c_int32), ("n_tiles", C.c_int32),
+                ("wt_ptr", _i32p), ("ws_ptr", _i32p), ("thdr", _i32p), ("lstaged", _i32p), ("n_steps", C.c_int64),
+                ("stream", C.POINTER(C.c_uint8))]
+
+
+class JJSubdomainPlan(C.Structure):
+    _fields_ = [("P", C.c_int32), ("NG", C.c_int32), ("n_rows", C.c_int32), ("n_loc_max", C.c_int32),
+                ("stage_rows", C.c_int32), ("n_top", C.c_int32), ("n_top_pad", C.c_int32), ("n_slots", C.c_int32),
+                ("n_loc", _i32p), ("n_halo", _i32p), ("hptr", _i32p), ("halo_top", _i32p), ("tptr", _i32p),
+                ("tslot", _i32p), ("top_face", _i32p), ("Sinv_packed", _f64p), ("prog", C.POINTER(JJSubProgram)),
+                ("junc_ptr", _i32p), ("junc_orig", _i32p), ("junc_row", _i32p), ("junc_sign", _i8p),
+                ("face_K", C.c_int32), ("face_ell_j", _i32p), ("face_ell_c", _f64p), ("face_fidx", _i32p)]
 
 
 class JJCircuit(C.Structure):
@@ -99,6 +114,8 @@ def load():
     lib.jj_stats.argtypes = [_p, C.POINTER(JJStats)]
     lib.jj_set_resident_plan.argtypes = [_p, C.POINTER(JJResidentPlan)]
     lib.jj_debug_resident_solve.argtypes = [_p, _f64p, _f64p]
+    lib.jj_set_subdomain_plan.argtypes = [_p, C.POINTER(JJSubdomainPlan)]
+    lib.jj_debug_subdomain_solve.argtypes = [_p, _f64p, _f64p]
     for name in EXPORTS:
         if name not in ("jj_destroy", "jj_last_error"):
             getattr(lib, name).restype = C.c_int

@@ -76,6 +76,8 @@ struct JJHandle {
     // resident engine (see jj_resident.cu): plan-level and problem-level state
     void *resident_plan = nullptr;
     void *resident = nullptr;
+    // subdomain engine (see jj_subdomain.cu)
+    void *subdomain_plan = nullptr;
     // stats
     long long steps_done = 0, launches = 0, device_bytes = 0;
     double last_ms = 0.0;
@@ -94,6 +96,16 @@ int resident_set_plan(JJHandle* h, const JJResidentPlan* plan);
 void resident_drop_plan(JJHandle* h);
 int resident_debug_solve(JJHandle* h, const double* b_d, double* J_d);
 void resident_get_config(JJHandle* h, int* C, int* WT);
+// implemented in jj_subdomain.cu
+int subdomain_supported(JJHandle* h, std::string& why_not);
+int subdomain_prepare(JJHandle* h);
+bool subdomain_prepared(JJHandle* h);
+int subdomain_run(JJHandle* h, long long i0, int n, const long long* th_plane, const long long* I_plane);
+void subdomain_free_problem(JJHandle* h);
+int subdomain_set_plan(JJHandle* h, const JJSubdomainPlan* plan);
+void subdomain_drop_plan(JJHandle* h);
+int subdomain_debug_solve(JJHandle* h, const double* b_d, double* J_d);
+void subdomain_get_config(JJHandle* h, int* P, int* PC);
 int dev_alloc(JJHandle* h, void** p, size_t bytes);
 void dev_free(JJHandle* h, void* p, size_t bytes);
 }

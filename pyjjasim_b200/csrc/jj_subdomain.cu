@@ -1,0 +1,1015 @@
+// SUBDOMAIN step engine for sm_100a: one persistent cooperative kernel integrates a whole jj_run call.
+//
+// Host plan: pyjjasim_b200/subdomain.py. The elimination tree of the cycle-space system is cut into P
+// mutually uncoupled subdomains plus the separators above the cut (the TOP rows). A thread block owns a
+// (subdomain, chunk of PC = 8*NG problems) item; everything local to it runs out of shared memory:
+//
+//   backward sweep  J_loc = D^-T (z_loc - L[top, loc]^T J_top) level by level   (reference: time_evolution.py:562-569)
+//   junction pass   theta_n = (A^T J - x)/c0; x' = noise - Is + Ic cpr(2 theta_n - theta_{n-1}) + c1.. + c2..  (:533-558, :570-580)
+//   face pass       b = A (x'/c0 - theta_s) - 2 pi f for local faces, partial sums for top faces           (:560-569)
+//   forward sweep   z_loc = D^-1 (b_loc - L z), then the subdomain's contribution to the top right-hand side
+//
+// followed, once per time step and for all problems at once, by
+//
+//   top assembly    r_top = sum of the subdomain contributions - 2 pi f_top
+//   top product     J_top = S_top^-1 r_top, a dense FP64 tensor-core product spread over all SMs
+//
+// with a grid barrier between the three stages. The local sweeps stream the factor from L2 as
+// mma.m8n8k4 fragments (one A fragment feeds NG MMAs, one per group of 8 problems); theta and x stream
+// through HBM once per step; b, z, J of the local rows never leave shared memory when every block has a
+// single item.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "jj_host.h"
+
+using namespace jj;
+
+namespace {
+
+constexpr int NT = 512;
+constexpr int NWARPS = NT / 32;
+constexpr int RING = 8;
+constexpr int STEP_BYTES = 320;
+constexpr double TWO_PI = 6.283185307179586;
+
+struct SubProgDev {
+    const int* wt_ptr; const int* ws_ptr; const int2* thdr; const int* lstaged;
+    const unsigned char* stream;
+    int n_levels, n_bwd, n_tiles, pad_;
+};
+
+struct SubArgs {
+    // plan
+    int P, n_rows, n_loc_max, stage_rows, n_top, n_top_pad, n_slots;
+    int max_np, max_levels, max_tiles;
+    const SubProgDev* prog;
+    const int *n_loc, *n_halo, *hptr, *halo_top, *tptr, *tslot, *top_face;
+    const double* SinvP;
+    const int* junc_ptr; const int* junc_orig; const int2* junc_row; const char2* junc_sign;
+    int face_K; const int* face_ell_j; const double* face_ell_c; const int* face_fidx;
+    // circuit
+    int Nj, Nf;
+    const double *P0, *P1;          // [Nj'][4] = Ic, 1/c0, c1, c2 | Is base, noise base, Vs base, 0 (device junction order)
+    Cpr cpr;
+    // problem
+    int Wp, n_chunks;
+    double dt;
+    unsigned long long seed; long long group_offset;
+    Source Is, Vs, T, F;
+    const double* noise; long long noise_i0; int noise_K;
+    // state
+    double *rth, *rx;               // [chunk][Nj'][PC]
+    double *th1, *th2;              // canonical [Nj][Wp]
+    double *zloc, *ctop, *rtop, *jtop;
+    unsigned* bar;
+    // run
+    long long i0; int n;
+    const long long* th_plane; const long long* I_plane;
+    double *snap_th, *snap_I;
+    int* flag;
+    const double* dbg_b; double* dbg_J;   // debug solve: canonical [Nf][Wp], permuted faces
+    long long* prof;                       // optional per-block cycle counters [block][8]
+};
+
+struct SubState {
+    int P = 1, NG = 4, PC = 32, n_rows = 0, n_loc_max = 0, stage_rows = 0, n_top = 0, n_top_pad = 0, n_slots = 0;
+    int max_np = 0, max_levels = 0, max_tiles = 0, face_K = 0;
+    SubProgDev* prog = nullptr;
+    int *n_loc = nullptr, *n_halo = nullptr, *hptr = nullptr, *halo_top = nullptr, *tptr = nullptr, *tslot = nullptr, *top_face = nullptr;
+    double* SinvP = nullptr;
+    int *junc_ptr = nullptr, *junc_orig = nullptr; int2* junc_row = nullptr; char2* junc_sign = nullptr;
+    int* face_ell_j = nullptr; double* face_ell_c = nullptr; int* face_fidx = nullptr;
+    double *P0 = nullptr, *P1 = nullptr;
+    std::vector<void*> allocs; std::vector<size_t> alloc_bytes;
+    // per problem
+    double *rth = nullptr, *rx = nullptr, *zloc = nullptr, *ctop = nullptr, *rtop = nullptr, *jtop = nullptr;
+    size_t state_bytes = 0, z_bytes = 0, c_bytes = 0, t_bytes = 0;
+    unsigned* bar = nullptr;
+    long long* plane_d = nullptr; size_t plane_cap = 0;
+    int n_chunks = 0, grid = 0;
+    size_t smem_bytes = 0;
+    bool prepared = false;
+};
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory vector: row r holds PC float64; the 8-problem group g of row r sits at group position
+// g ^ (r & (NG-1)), so the four rows gathered by one MMA B fragment fall into different bank groups.
+// ------------------------------------------------------------------------------------------------
+template <int NG>
+__device__ __forceinline__ int vgrp(int row, int g) { return (g ^ (row & (NG - 1))) << 3; }
+template <int NG>
+__device__ __forceinline__ int velem(int row, int q) { return row * (8 * NG) + vgrp<NG>(row, q >> 3) + (q & 7); }
+
+struct Cursor {
+    int t0, t1, s;
+    double ra[RING]; unsigned rc[RING];
+};
+
+struct ProgSmem {
+    const int* wt; const int* ws; const int* lstaged; const int2* thdr;
+    const unsigned char* stream;
+    int n_levels, n_bwd;
+};
+
+__device__ __forceinline__ void cursor_open(Cursor& cu, const ProgSmem& ps, int level) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int idx = level * NWARPS + warp;
+    cu.t0 = ps.wt[idx]; cu.t1 = ps.wt[idx + 1];
+    cu.s = ps.ws[idx];
+    // ring slot of stream step s is s % RING; the stream buffer is padded by 2*RING steps
+    const int first = cu.s - (cu.s & (RING - 1));
+#pragma unroll
+    for (int k = 0; k < RING; ++k) {
+        const int sk = first + k + ((first + k < cu.s) ? RING : 0);
+        const unsigned char* rec = ps.stream + (size_t)sk * STEP_BYTES;
+        cu.ra[k] = __ldg(reinterpret_cast<const double*>(rec) + lane);
+        cu.rc[k] = __ldg(reinterpret_cast<const unsigned short*>(rec + 256) + lane);
+    }
+}
+
+// C(8 rows x 8 problems) += A(8 x 4) . B(4 x 8) on the FP64 tensor core: lane = row*4 + kk holds A[row][kk],
+// lane = n*4 + kk holds B[kk][n], lane = row*4 + c holds C[row][2c], C[row][2c+1].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// One level of a subdomain's sweep program: every warp walks its own stream of 8-row tiles.
+template <int NG>
+__device__ void exec_level(const ProgSmem& ps, Cursor& cu, int level, int next_level, double* __restrict__ v,
+                           double* __restrict__ stage) {
+    constexpr int PC = 8 * NG;
+    const int lane = threadIdx.x & 31;
+    int s = cu.s;
+    const unsigned char* base = ps.stream;
+    double ra[RING]; unsigned rc[RING];
+#pragma unroll
+    for (int k = 0; k < RING; ++k) { ra[k] = cu.ra[k]; rc[k] = cu.rc[k]; }
+    const int r = lane >> 2, kk = lane & 3;
+    for (int t = cu.t0; t < cu.t1; ++t) {
+        const int2 hd = ps.thdr[t];
+        const int row0 = hd.x & 0xffff, nrows = ((hd.x >> 16) & 7) + 1, flags = (hd.x >> 19) & 3;
+        const int g0 = (hd.x >> 21) & 15, ng = ((hd.x >> 25) & 15) + 1;
+        const int nsteps = hd.y & 0xffff, stage_off = (hd.y >> 16) & 0x7fff;
+        const int row = row0 + r;
+        const int rowoff = row * PC + 2 * kk;
+        double acc[NG][2];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) { acc[g][0] = 0.0; acc[g][1] = 0.0; }
+        if ((flags & 1) && r < nrows) {
+#pragma unroll
+            for (int g = 0; g < NG; ++g)
+                if (g < ng) {
+                    const double2 sv = *reinterpret_cast<const double2*>(v + rowoff + vgrp<NG>(row, g0 + g));
+                    acc[g][0] = sv.x; acc[g][1] = sv.y;
+                }
+        }
+        const unsigned gx = (unsigned)g0 << 3;
+        // ring slot K always holds a stream step congruent to K (mod RING); it is refilled in place right after use
+#define JJ_STEP(K)                                                                                     \
+    if ((K) >= p_ && j < nsteps) {                                                                     \
+        const unsigned code = rc[K] ^ gx;                                                              \
+        _Pragma("unroll") for (int g = 0; g < NG; ++g)                                                 \
+            if (g < ng) dmma884(acc[g][0], acc[g][1], ra[K], v[code ^ (unsigned)(g << 3)]);            \
+        const unsigned char* rec = base + (size_t)(s + RING) * STEP_BYTES;                             \
+        asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(ra[K]) : "l"(reinterpret_cast<const double*>(rec) + lane)); \
+        asm volatile("ld.global.nc.u16 %0, [%1];" : "=r"(rc[K]) : "l"(reinterpret_cast<const unsigned short*>(rec + 256) + lane)); \
+        ++s; ++j;                                                                                      \
+    }
+        for (int j = 0; j < nsteps;) {
+            const int p_ = s & (RING - 1);
+            JJ_STEP(0) JJ_STEP(1) JJ_STEP(2) JJ_STEP(3) JJ_STEP(4) JJ_STEP(5) JJ_STEP(6) JJ_STEP(7)
+        }
+#undef JJ_STEP
+        __syncwarp();            // every lane has read its operands before rows of this block are overwritten
+        if (r < nrows) {
+            if (flags & 2) {
+                // staged: the row keeps the physical layout of its destination and carries the destination index
+                double* srow = stage + (size_t)(stage_off + r) * (PC + 2);
+#pragma unroll
+                for (int g = 0; g < NG; ++g)
+                    if (g < ng) *reinterpret_cast<double2*>(srow + vgrp<NG>(row, g0 + g) + 2 * kk) = make_double2(acc[g][0], acc[g][1]);
+                if (kk == 0) reinterpret_cast<int*>(srow + PC)[0] = row;
+            } else {
+#pragma unroll
+                for (int g = 0; g < NG; ++g)
+                    if (g < ng) *reinterpret_cast<double2*>(v + rowoff + vgrp<NG>(row, g0 + g)) = make_double2(acc[g][0], acc[g][1]);
+            }
+        }
+        __syncwarp();
+    }
+    if (next_level >= 0) cursor_open(cu, ps, next_level);
+    __syncthreads();
+    const int staged = ps.lstaged[level];
+    if (staged > 0) {
+        for (int e = threadIdx.x; e < staged * (PC / 2); e += NT) {
+            const int rr = e / (PC / 2), q = e % (PC / 2);
+            const double* srow = stage + (size_t)rr * (PC + 2);
+            const int dst_row = reinterpret_cast<const int*>(srow + PC)[0];
+            reinterpret_cast<double2*>(v + (size_t)dst_row * PC)[q] = reinterpret_cast<const double2*>(srow)[q];
+        }
+        __syncthreads();
+    }
+}
+
+template <int NG>
+__device__ void run_levels(const ProgSmem& ps, int l0, int l1, double* v, double* stage) {
+    if (l0 >= l1) return;
+    Cursor cu;
+    cursor_open(cu, ps, l0);
+    for (int l = l0; l < l1; ++l) exec_level<NG>(ps, cu, l, l + 1 < l1 ? l + 1 : -1, v, stage);
+}
+
+// Per-step amplitudes of the rank-one inputs for the problems of a chunk (both step parities are filled
+// per item: the current snapshot of step n-1 needs Is of step n-1).
+template <int PC>
+struct AmpCache {
+    double T[2][PC], Is[2][PC], Vs[2][PC], F[2][PC];
+};
+
+template <int PC>
+__device__ __forceinline__ void amp_fill(const SubArgs& a, AmpCache<PC>* ac, int c, long long n) {
+    for (int t = threadIdx.x; t < 4 * PC; t += NT) {
+        const int e = t % PC, which = t / PC;
+        const int w = c * PC + e;
+        const Source& s = which == 0 ? a.T : which == 1 ? a.Is : which == 2 ? a.Vs : a.F;
+        double val = 0.0;
+        if (s.kind == KIND_RANK1 && w < a.Wp && n >= a.i0 && n < a.i0 + a.n) val = __ldg(s.table + source_row(s, n) * a.Wp + w);
+        double* dst = which == 0 ? ac->T[n & 1] : which == 1 ? ac->Is[n & 1] : which == 2 ? ac->Vs[n & 1] : ac->F[n & 1];
+        dst[e] = val;
+    }
+}
+
+// State and constants of one junction item (one junction x 4 problems), loaded one iteration ahead.
+struct JIn {
+    double2 x0, x1, t0, t1, pIc, pc, pb;
+    int2 rows;
+    int sg, jo;
+};
+
+template <int PC>
+__device__ __forceinline__ void jin_load(const SubArgs& a, int jlo, int c, int idx, JIn& in) {
+    constexpr int G = PC / 4;
+    const int jp = jlo + idx / G;
+    const size_t sidx = ((size_t)c * a.Nj + jlo) * PC + (size_t)idx * 4;
+    const double2* xp = reinterpret_cast<const double2*>(a.rx + sidx);
+    const double2* tp = reinterpret_cast<const double2*>(a.rth + sidx);
+    in.x0 = xp[0]; in.x1 = xp[1]; in.t0 = tp[0]; in.t1 = tp[1];
+    in.pIc = __ldg(reinterpret_cast<const double2*>(a.P0) + 2 * jp);
+    in.pc = __ldg(reinterpret_cast<const double2*>(a.P0) + 2 * jp + 1);
+    in.pb = __ldg(reinterpret_cast<const double2*>(a.P1) + 2 * jp);
+    in.rows = __ldg(a.junc_row + jp);
+    const char2 sg = a.junc_sign[jp];
+    in.sg = (int)sg.x * 4 + (int)sg.y;       // signs are -1, 0, +1
+    in.jo = __ldg(a.junc_orig + jp);
+}
+
+template <bool DEF>
+__device__ __forceinline__ void next_x(const SubArgs& a, double Ic, double c1, double c2, double isb, double nb,
+                                       const double* ampT, const double* ampIs, int jo, int w, long long n,
+                                       const double th1[4], const double th2[4], double xn[4]) {
+    double fl[4] = {0, 0, 0, 0};
+    if (a.T.kind != KIND_ZERO) {
+        double z[4];
+        if (a.noise_K > 0) {
+            const double2* zp = reinterpret_cast<const double2*>(a.noise + ((size_t)(n - a.noise_i0) * a.Nj + jo) * a.Wp + w);
+            const double2 z0 = zp[0], z1 = zp[1];
+            z[0] = z0.x; z[1] = z0.y; z[2] = z1.x; z[3] = z1.y;
+        } else {
+            normal4(a.seed, jo, a.group_offset + (w >> 2), n, z);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) fl[k] = (nb * ampT[k]) * z[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double X = Ic * cpr_eval<DEF>(a.cpr, 2.0 * th1[k] - th2[k]) + c1 * th1[k] + c2 * th2[k];
+        xn[k] = (fl[k] - isb * ampIs[k]) + X;
+    }
+}
+
+// theta_n = (A^T J - x)/c0, snapshots, x' for the next step  (reference: time_evolution.py:533-558, 570-580)
+template <int NG, bool DEF>
+__device__ __forceinline__ void junction_item(const SubArgs& a, const AmpCache<8 * NG>* ac, int c, long long n, int idx,
+                                              int jlo, bool do_pre, const JIn& in, const double* __restrict__ v,
+                                              double* snap_th, double* snap_I) {
+    constexpr int PC = 8 * NG, G = PC / 4;
+    const int q = (idx % G) * 4;
+    const int w = c * PC + q;
+    if (w >= a.Wp) return;
+    const size_t sidx = ((size_t)c * a.Nj + jlo) * PC + (size_t)idx * 4;
+    double y[4] = {0, 0, 0, 0};
+    if (in.rows.x >= 0) {
+        const double2* jp = reinterpret_cast<const double2*>(v + velem<NG>(in.rows.x, q));
+        const double2 j0 = jp[0], j1 = jp[1];
+        const double s = (double)((in.sg + 5) / 4 - 1);
+        y[0] = s * j0.x; y[1] = s * j0.y; y[2] = s * j1.x; y[3] = s * j1.y;
+    }
+    if (in.rows.y >= 0) {
+        const double2* jp = reinterpret_cast<const double2*>(v + velem<NG>(in.rows.y, q));
+        const double2 j0 = jp[0], j1 = jp[1];
+        const double s = (double)((in.sg + 5) % 4 - 1);
+        y[0] = fma(s, j0.x, y[0]); y[1] = fma(s, j0.y, y[1]); y[2] = fma(s, j1.x, y[2]); y[3] = fma(s, j1.y, y[3]);
+    }
+    const double ic0 = in.pIc.y;
+    const double th1[4] = {(y[0] - in.x0.x) * ic0, (y[1] - in.x0.y) * ic0, (y[2] - in.x1.x) * ic0, (y[3] - in.x1.y) * ic0};
+    const double th2[4] = {in.t0.x, in.t0.y, in.t1.x, in.t1.y};
+    // one finiteness test for the four phases (a NaN or Inf in any of them poisons the sum)
+    if (!(fabs((th1[0] + th1[1]) + (th1[2] + th1[3])) < 1.0e300)) atomicOr(a.flag, 1);
+    if (snap_th || snap_I || !do_pre) {
+        const size_t cidx = (size_t)in.jo * a.Wp + w;
+        if (snap_th) {
+            double2* sp = reinterpret_cast<double2*>(snap_th + cidx);
+            sp[0] = make_double2(th1[0], th1[1]); sp[1] = make_double2(th1[2], th1[3]);
+        }
+        if (snap_I) {
+            const double* am = ac->Is[(n - 1) & 1] + q;
+            double2* sp = reinterpret_cast<double2*>(snap_I + cidx);
+            sp[0] = make_double2(y[0] + in.pb.x * am[0], y[1] + in.pb.x * am[1]);
+            sp[1] = make_double2(y[2] + in.pb.x * am[2], y[3] + in.pb.x * am[3]);
+        }
+        if (!do_pre) {
+            // end of the run: hand theta_last and theta_{last-1} back in the canonical layout
+            double2* o1 = reinterpret_cast<double2*>(a.th1 + cidx);
+            double2* o2 = reinterpret_cast<double2*>(a.th2 + cidx);
+            o1[0] = make_double2(th1[0], th1[1]); o1[1] = make_double2(th1[2], th1[3]);
+            o2[0] = in.t0; o2[1] = in.t1;
+            return;
+        }
+    }
+    double2* op = reinterpret_cast<double2*>(a.rth + sidx);
+    op[0] = make_double2(th1[0], th1[1]); op[1] = make_double2(th1[2], th1[3]);
+    double xn[4];
+    next_x<DEF>(a, in.pIc.x, in.pc.x, in.pc.y, in.pb.x, in.pb.y, ac->T[n & 1] + q, ac->Is[n & 1] + q, in.jo, w, n, th1, th2, xn);
+    double2* xo = reinterpret_cast<double2*>(a.rx + sidx);
+    xo[0] = make_double2(xn[0], xn[1]); xo[1] = make_double2(xn[2], xn[3]);
+}
+
+template <int NG, bool DEF>
+__device__ void junction_pass(const SubArgs& a, const AmpCache<8 * NG>* ac, int s, int c, long long n, bool do_post,
+                              bool do_pre, const double* __restrict__ v) {
+    constexpr int PC = 8 * NG, G = PC / 4;
+    const int jlo = a.junc_ptr[s], jhi = a.junc_ptr[s + 1];
+    const int total = (jhi - jlo) * G;
+    if (!do_post) {
+        // first boundary of a run: theta(n-1), theta(n-2) come from the canonical arrays; no solve result yet
+        for (int idx = threadIdx.x; idx < total; idx += NT) {
+            const int jp = jlo + idx / G, q = (idx % G) * 4, w = c * PC + q;
+            if (w >= a.Wp) continue;
+            const int jo = __ldg(a.junc_orig + jp);
+            const size_t sidx = ((size_t)c * a.Nj + jlo) * PC + (size_t)idx * 4;
+            const size_t cidx = (size_t)jo * a.Wp + w;
+            const double2* p1 = reinterpret_cast<const double2*>(a.th1 + cidx);
+            const double2* p2 = reinterpret_cast<const double2*>(a.th2 + cidx);
+            const double2 u0 = p1[0], u1 = p1[1], v0 = p2[0], v1 = p2[1];
+            double2* op = reinterpret_cast<double2*>(a.rth + sidx);
+            op[0] = u0; op[1] = u1;
+            const double th1[4] = {u0.x, u0.y, u1.x, u1.y}, th2[4] = {v0.x, v0.y, v1.x, v1.y};
+            const double2 pIc = __ldg(reinterpret_cast<const double2*>(a.P0) + 2 * jp);
+            const double2 pc = __ldg(reinterpret_cast<const double2*>(a.P0) + 2 * jp + 1);
+            const double2 pb = __ldg(reinterpret_cast<const double2*>(a.P1) + 2 * jp);
+            double xn[4];
+            next_x<DEF>(a, pIc.x, pc.x, pc.y, pb.x, pb.y, ac->T[n & 1] + q, ac->Is[n & 1] + q, jo, w, n, th1, th2, xn);
+            double2* xo = reinterpret_cast<double2*>(a.rx + sidx);
+            xo[0] = make_double2(xn[0], xn[1]); xo[1] = make_double2(xn[2], xn[3]);
+        }
+        return;
+    }
+    double* snap_th = nullptr; double* snap_I = nullptr;
+    {
+        const long long k = n - 1 - a.i0;
+        const long long pt = a.th_plane ? a.th_plane[k] : -1, pi = a.I_plane ? a.I_plane[k] : -1;
+        if (pt >= 0) snap_th = a.snap_th + (size_t)pt * a.Nj * a.Wp;
+        if (pi >= 0) snap_I = a.snap_I + (size_t)pi * a.Nj * a.Wp;
+    }
+    // software pipeline: the loads of the next item are in flight while the current one is computed
+    JIn cur, nxt;
+    int idx = threadIdx.x;
+    if (idx < total) jin_load<PC>(a, jlo, c, idx, cur);
+    for (; idx < total; idx += NT) {
+        const bool more = idx + NT < total;
+        if (more) jin_load<PC>(a, jlo, c, idx + NT, nxt);
+        if (idx + 3 * NT < total) {      // and the state three iterations ahead is pulled into L2
+            const size_t pf = ((size_t)c * a.Nj + jlo) * PC + (size_t)(idx + 3 * NT) * 4;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.rx + pf));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.rth + pf));
+        }
+        junction_item<NG, DEF>(a, ac, c, n, idx, jlo, do_pre, cur, v, snap_th, snap_I);
+        if (more) cur = nxt;
+    }
+}
+
+// b = A (x'/c0 - theta_s) - 2 pi f into shared memory (reference: time_evolution.py:560-569). Every row has a
+// fixed-width list of (device junction, +-1/c0) pairs; halo rows hold the partial sum over the junctions this
+// subdomain owns (their flux term is added by the top assembly).
+template <int NG>
+__device__ void face_pass(const SubArgs& a, const AmpCache<8 * NG>* ac, int s, int c, long long n, int rows_used,
+                          double* __restrict__ v) {
+    constexpr int PC = 8 * NG, G = PC / 4;
+    const int K = a.face_K;
+    const int* fj = a.face_ell_j + (size_t)s * a.n_rows * K;
+    const double* fc = a.face_ell_c + (size_t)s * a.n_rows * K;
+    const int* fidx = a.face_fidx + (size_t)s * a.n_rows;
+    const int total = rows_used * G;
+    for (int idx = threadIdx.x; idx < total; idx += NT) {
+        const int row = idx / G;
+        const int q = (idx % G) * 4;
+        const int w = c * PC + q;
+        double acc[4] = {0, 0, 0, 0};
+        if (w < a.Wp) {
+            const size_t tbase = (size_t)c * a.Nj * PC + q;
+            for (int k0 = 0; k0 < K; k0 += 4) {
+                int jp[4]; double cf[4]; double2 xa[4], xb[4];
+                {
+                    const int4 j4 = __ldg(reinterpret_cast<const int4*>(fj + (size_t)row * K + k0));
+                    jp[0] = j4.x; jp[1] = j4.y; jp[2] = j4.z; jp[3] = j4.w;
+                    const double2 ca = __ldg(reinterpret_cast<const double2*>(fc + (size_t)row * K + k0));
+                    const double2 cb = __ldg(reinterpret_cast<const double2*>(fc + (size_t)row * K + k0) + 1);
+                    cf[0] = ca.x; cf[1] = ca.y; cf[2] = cb.x; cf[3] = cb.y;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (jp[k] >= 0) {
+                        const double2* xp = reinterpret_cast<const double2*>(a.rx + tbase + (size_t)jp[k] * PC);
+                        xa[k] = __ldcg(xp); xb[k] = __ldcg(xp + 1);
+                    } else {
+                        xa[k] = make_double2(0, 0); xb[k] = make_double2(0, 0);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    acc[0] = fma(cf[k], xa[k].x, acc[0]); acc[1] = fma(cf[k], xa[k].y, acc[1]);
+                    acc[2] = fma(cf[k], xb[k].x, acc[2]); acc[3] = fma(cf[k], xb[k].y, acc[3]);
+                }
+                if (a.Vs.kind == KIND_RANK1) {
+                    const double* cum = ac->Vs[n & 1] + q;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (jp[k] >= 0) {
+                            // coefficient = sign / c0: recover sign * Vs base from the per-junction records
+                            const double ic0 = __ldg(a.P0 + 4 * (size_t)jp[k] + 1), vb = __ldg(a.P1 + 4 * (size_t)jp[k] + 2);
+                            const double sv = (cf[k] / ic0) * vb;
+                            for (int e = 0; e < 4; ++e) acc[e] -= sv * cum[e];
+                        }
+                    }
+                }
+            }
+            const int g = __ldg(fidx + row);
+            if (g >= 0 && a.F.kind == KIND_RANK1) {
+                const double* am = ac->F[n & 1] + q;
+                const double b = __ldg(a.F.base + g);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc[k] -= TWO_PI * (b * am[k]);
+            }
+        }
+        double2* dst = reinterpret_cast<double2*>(v + velem<NG>(row, q));
+        dst[0] = make_double2(acc[0], acc[1]);
+        dst[1] = make_double2(acc[2], acc[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// grid barrier: monotonic arrival counter (zeroed by the host before the launch); the kernel is launched
+// cooperatively, so all blocks are resident.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        unsigned seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+        } while (seen < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// r_top = sum of the subdomain contributions - 2 pi f_top (+ debug right-hand side), logical [chunk][row][PC]
+template <int NG>
+__device__ void top_assemble(const SubArgs& a, long long n) {
+    constexpr int PC = 8 * NG, G = PC / 4;
+    const long long total = (long long)a.n_chunks * a.n_top * G;
+    for (long long idx = (long long)blockIdx.x * NT + threadIdx.x; idx < total; idx += (long long)gridDim.x * NT) {
+        const int q = (int)(idx % G) * 4;
+        const long long t = idx / G;
+        const int k = (int)(t % a.n_top), c = (int)(t / a.n_top);
+        const int w = c * PC + q;
+        double acc[4] = {0, 0, 0, 0};
+        for (int sl = a.tptr[k]; sl < a.tptr[k + 1]; ++sl) {
+            const double2* p = reinterpret_cast<const double2*>(a.ctop + ((size_t)c * a.n_slots + a.tslot[sl]) * PC + q);
+            const double2 u0 = __ldcg(p), u1 = __ldcg(p + 1);
+            acc[0] += u0.x; acc[1] += u0.y; acc[2] += u1.x; acc[3] += u1.y;
+        }
+        if (w < a.Wp) {
+            const int g = a.top_face[k];
+            if (a.dbg_b) {
+                for (int e = 0; e < 4; ++e) acc[e] += a.dbg_b[(size_t)g * a.Wp + w + e];
+            } else if (a.F.kind == KIND_RANK1) {
+                const double b = __ldg(a.F.base + g);
+                const double* am = a.F.table + source_row(a.F, n) * a.Wp + w;
+                for (int e = 0; e < 4; ++e) acc[e] -= TWO_PI * (b * __ldg(am + e));
+            }
+        }
+        double2* dst = reinterpret_cast<double2*>(a.rtop + ((size_t)c * a.n_top_pad + k) * PC + q);
+        dst[0] = make_double2(acc[0], acc[1]);
+        dst[1] = make_double2(acc[2], acc[3]);
+    }
+}
+
+// J_top = S_top^-1 r_top: item = (32 rows, one chunk); warp = (8-row tile, problem group)
+template <int NG>
+__device__ void top_product(const SubArgs& a) {
+    constexpr int PC = 8 * NG;
+    const int MT = a.n_top_pad / 32, KS = a.n_top_pad / 4;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rt = warp & 3;
+    for (int item = blockIdx.x; item < MT * a.n_chunks; item += gridDim.x) {
+        const int mt = item % MT, c = item / MT;
+        const double* A = a.SinvP + ((size_t)(mt * 4 + rt) * KS) * 32 + lane;
+        for (int g = warp >> 2; g < NG; g += 4) {
+            const double* B = a.rtop + ((size_t)c * a.n_top_pad + (lane & 3)) * PC + 8 * g + (lane >> 2);
+            double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
+            double ac[8], bc[8], an[8], bn[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { ac[j] = __ldg(A + (size_t)j * 32); bc[j] = __ldcg(B + (size_t)j * 4 * PC); }
+            for (int ks0 = 0; ks0 < KS; ks0 += 8) {
+                const bool more = ks0 + 8 < KS;
+                if (more) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        an[j] = __ldg(A + (size_t)(ks0 + 8 + j) * 32);
+                        bn[j] = __ldcg(B + (size_t)(ks0 + 8 + j) * 4 * PC);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {
+                    dmma884(c00, c01, ac[j], bc[j]);
+                    dmma884(c10, c11, ac[j + 1], bc[j + 1]);
+                }
+                if (more) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { ac[j] = an[j]; bc[j] = bn[j]; }
+                }
+            }
+            const int row = 32 * mt + 8 * rt + (lane >> 2);
+            double2* dst = reinterpret_cast<double2*>(a.jtop + ((size_t)c * a.n_top_pad + row) * PC + 8 * g + 2 * (lane & 3));
+            *dst = make_double2(c00 + c10, c01 + c11);
+        }
+    }
+}
+
+template <int NG>
+__device__ __forceinline__ void load_prog(const SubArgs& a, int s, ProgSmem& ps, int* aux) {
+    const SubProgDev p = a.prog[s];
+    int* wt = aux; int* ws = aux + a.max_np; int* ls = ws + a.max_np;
+    int2* th = reinterpret_cast<int2*>(ls + a.max_levels + (a.max_levels & 1));
+    const int np = p.n_levels * NWARPS + 1;
+    for (int e = threadIdx.x; e < np; e += NT) { wt[e] = p.wt_ptr[e]; ws[e] = p.ws_ptr[e]; }
+    for (int e = threadIdx.x; e < p.n_levels; e += NT) ls[e] = p.lstaged[e];
+    for (int e = threadIdx.x; e < p.n_tiles; e += NT) th[e] = p.thdr[e];
+    ps.wt = wt; ps.ws = ws; ps.lstaged = ls; ps.thdr = th; ps.stream = p.stream;
+    ps.n_levels = p.n_levels; ps.n_bwd = p.n_bwd;
+}
+
+// copy between the shared-memory vector (swizzled rows) and logical [row][PC] global arrays
+template <int NG>
+__device__ __forceinline__ void rows_to_global(const double* v, int row0, int nrows, double* dst) {
+    constexpr int PC = 8 * NG;
+    for (int e = threadIdx.x; e < nrows * (PC / 2); e += NT) {
+        const int r = e / (PC / 2), q = (e % (PC / 2)) * 2;
+        reinterpret_cast<double2*>(dst + (size_t)r * PC)[q >> 1] = *reinterpret_cast<const double2*>(v + velem<NG>(row0 + r, q));
+    }
+}
+
+template <int NG, bool DEF>
+__global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
+    constexpr int PC = 8 * NG;
+    extern __shared__ __align__(16) double smem[];
+    double* v = smem;
+    double* stage = v + (size_t)a.n_rows * PC;
+    AmpCache<PC>* ac = reinterpret_cast<AmpCache<PC>*>(stage + (size_t)a.stage_rows * (PC + 2));
+    int* aux = reinterpret_cast<int*>(ac + 1);
+    ProgSmem ps;
+    const int n_items = a.P * a.n_chunks;
+    const bool keep_z = n_items <= (int)gridDim.x;     // every block has at most one item: z stays in shared memory
+    unsigned bar_target = 0;
+    int cur_s = -1;
+
+    if (a.dbg_b) {
+        // ---- debug: one solve J = S^-1 b through the plan
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int s = item % a.P, c = item / a.P;
+            __syncthreads();
+            load_prog<NG>(a, s, ps, aux);
+            const int nl = a.n_loc[s], nh = a.n_halo[s];
+            const int* fidx = a.face_fidx + (size_t)s * a.n_rows;
+            for (int e = threadIdx.x; e < (nl + nh) * PC; e += NT) {
+                const int row = e / PC, q = e % PC, w = c * PC + q;
+                double val = 0.0;
+                if (row < nl && w < a.Wp) val = a.dbg_b[(size_t)fidx[row] * a.Wp + w];
+                v[velem<NG>(row, q)] = val;
+            }
+            __syncthreads();
+            run_levels<NG>(ps, ps.n_bwd, ps.n_levels, v, stage);
+            rows_to_global<NG>(v, nl, nh, a.ctop + ((size_t)c * a.n_slots + a.hptr[s]) * PC);
+            rows_to_global<NG>(v, 0, nl, a.zloc + ((size_t)item * a.n_loc_max) * PC);
+        }
+        grid_barrier(a.bar, bar_target);
+        top_assemble<NG>(a, 0);
+        grid_barrier(a.bar, bar_target);
+        top_product<NG>(a);
+        grid_barrier(a.bar, bar_target);
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int s = item % a.P, c = item / a.P;
+            __syncthreads();
+            load_prog<NG>(a, s, ps, aux);
+            const int nl = a.n_loc[s], nh = a.n_halo[s];
+            const int* fidx = a.face_fidx + (size_t)s * a.n_rows;
+            const int* ht = a.halo_top + a.hptr[s];
+            for (int e = threadIdx.x; e < (nl + nh) * PC; e += NT) {
+                const int row = e / PC, q = e % PC;
+                double val;
+                if (row < nl) val = __ldcg(a.zloc + ((size_t)item * a.n_loc_max + row) * PC + q);
+                else val = __ldcg(a.jtop + ((size_t)c * a.n_top_pad + ht[row - nl]) * PC + q);
+                v[velem<NG>(row, q)] = val;
+            }
+            __syncthreads();
+            run_levels<NG>(ps, 0, ps.n_bwd, v, stage);
+            for (int e = threadIdx.x; e < nl * PC; e += NT) {
+                const int row = e / PC, q = e % PC, w = c * PC + q;
+                if (w < a.Wp) a.dbg_J[(size_t)fidx[row] * a.Wp + w] = v[velem<NG>(row, q)];
+            }
+        }
+        for (long long e = (long long)blockIdx.x * NT + threadIdx.x; e < (long long)a.n_top * a.n_chunks * PC; e += (long long)gridDim.x * NT) {
+            const int q = (int)(e % PC); const long long t = e / PC;
+            const int k = (int)(t % a.n_top), c = (int)(t / a.n_top), w = c * PC + q;
+            if (w < a.Wp) a.dbg_J[(size_t)a.top_face[k] * a.Wp + w] = __ldcg(a.jtop + ((size_t)c * a.n_top_pad + k) * PC + q);
+        }
+        return;
+    }
+
+    for (long long k = 0; k <= a.n; ++k) {
+        const long long n = a.i0 + k;
+        long long tq = a.prof ? clock64() : 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int s = item % a.P, c = item / a.P;
+            if (s != cur_s) { __syncthreads(); load_prog<NG>(a, s, ps, aux); cur_s = s; }
+            const int nl = a.n_loc[s], nh = a.n_halo[s];
+            amp_fill<PC>(a, ac, c, n - 1);
+            amp_fill<PC>(a, ac, c, n);
+            if (k > 0) {
+                // J_top of the halo rows and z of the local rows, then the backward sweep
+                const int* ht = a.halo_top + a.hptr[s];
+                for (int e = threadIdx.x; e < nh * (PC / 2); e += NT) {
+                    const int r = e / (PC / 2), q = (e % (PC / 2)) * 2;
+                    const double2 val = __ldcg(reinterpret_cast<const double2*>(a.jtop + ((size_t)c * a.n_top_pad + ht[r]) * PC + q));
+                    *reinterpret_cast<double2*>(v + velem<NG>(nl + r, q)) = val;
+                }
+                if (!keep_z) {
+                    const double2* src = reinterpret_cast<const double2*>(a.zloc + ((size_t)item * a.n_loc_max) * PC);
+                    double2* dst = reinterpret_cast<double2*>(v);
+                    for (int e = threadIdx.x; e < nl * (PC / 2); e += NT) dst[e] = src[e];
+                }
+                __syncthreads();
+                run_levels<NG>(ps, 0, ps.n_bwd, v, stage);
+            } else {
+                __syncthreads();
+            }
+            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * 8 + 0] += tn - tq; tq = tn; }
+            junction_pass<NG, DEF>(a, ac, s, c, n, k > 0, k < a.n, v);
+            if (k == a.n) { __syncthreads(); continue; }
+            __syncthreads();
+            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * 8 + 1] += tn - tq; tq = tn; }
+            face_pass<NG>(a, ac, s, c, n, nl + nh, v);
+            __syncthreads();
+            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * 8 + 2] += tn - tq; tq = tn; }
+            run_levels<NG>(ps, ps.n_bwd, ps.n_levels, v, stage);
+            rows_to_global<NG>(v, nl, nh, a.ctop + ((size_t)c * a.n_slots + a.hptr[s]) * PC);
+            if (!keep_z) {
+                const double2* src = reinterpret_cast<const double2*>(v);
+                double2* dst = reinterpret_cast<double2*>(a.zloc + ((size_t)item * a.n_loc_max) * PC);
+                for (int e = threadIdx.x; e < nl * (PC / 2); e += NT) dst[e] = src[e];
+            }
+            __syncthreads();     // the vector is reused by the next item / the next step
+            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * 8 + 3] += tn - tq; tq = tn; }
+        }
+        if (k == a.n) break;
+        if (a.n_top > 0) {
+            grid_barrier(a.bar, bar_target);
+            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * 8 + 4] += tn - tq; tq = tn; }
+            top_assemble<NG>(a, n);
+            grid_barrier(a.bar, bar_target);
+            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * 8 + 5] += tn - tq; tq = tn; }
+            top_product<NG>(a);
+            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * 8 + 6] += tn - tq; tq = tn; }
+            grid_barrier(a.bar, bar_target);
+            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * 8 + 7] += tn - tq; tq = tn; }
+        }
+    }
+}
+
+typedef void (*KernelPtr)(const SubArgs);
+
+KernelPtr pick_kernel(int NG, bool def) {
+    switch (NG) {
+        case 1: return def ? k_subdomain<1, true> : k_subdomain<1, false>;
+        case 2: return def ? k_subdomain<2, true> : k_subdomain<2, false>;
+        case 4: return def ? k_subdomain<4, true> : k_subdomain<4, false>;
+        default: return def ? k_subdomain<8, true> : k_subdomain<8, false>;
+    }
+}
+
+// per-junction constants in device junction order (one coalesced 32-byte record instead of gathers by original index)
+__global__ void k_sub_gather_params(int n, const int* orig, const double* Ic, const double* c0, const double* c1,
+                                    const double* c2, const double* isb, const double* tb, const double* vsb,
+                                    double* P0, double* P1) {
+    int jp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (jp >= n) return;
+    int jo = orig[jp];
+    P0[4 * jp + 0] = Ic[jo]; P0[4 * jp + 1] = 1.0 / c0[jo]; P0[4 * jp + 2] = c1[jo]; P0[4 * jp + 3] = c2[jo];
+    P1[4 * jp + 0] = isb ? isb[jo] : 0.0; P1[4 * jp + 1] = tb ? tb[jo] : 0.0; P1[4 * jp + 2] = vsb ? vsb[jo] : 0.0;
+    P1[4 * jp + 3] = 0.0;
+}
+
+#define SCK(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            h->err = std::string("subdomain: ") + #call + ": " + cudaGetErrorString(e_);            \
+            return JJ_ECUDA;                                                                        \
+        }                                                                                           \
+    } while (0)
+
+template <typename T>
+int up(JJHandle* h, SubState* st, T** dst, const T* src, size_t n, size_t pad_bytes = 0) {
+    void* p = nullptr;
+    size_t bytes = std::max<size_t>(n, 1) * sizeof(T) + pad_bytes;
+    int rc = dev_alloc(h, &p, bytes);
+    if (rc) return rc;
+    st->allocs.push_back(p); st->alloc_bytes.push_back(bytes);
+    cudaError_t e = cudaMemsetAsync(p, 0, bytes, h->stream);
+    if (e == cudaSuccess && n) e = cudaMemcpyAsync(p, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream);
+    if (e != cudaSuccess) { h->err = std::string("subdomain upload: ") + cudaGetErrorString(e); return JJ_ECUDA; }
+    *dst = (T*)p;
+    return JJ_OK;
+}
+
+size_t smem_for(const SubState* st) {
+    const int PC = st->PC;
+    size_t amp = (size_t)4 * 2 * PC * sizeof(double);
+    size_t aux = ((size_t)2 * st->max_np + st->max_levels + 2 + 2 * (size_t)st->max_tiles + 8) * sizeof(int);
+    return ((size_t)st->n_rows * PC + (size_t)st->stage_rows * (PC + 2)) * sizeof(double) + amp + aux;
+}
+
+}  // namespace
+
+namespace jj {
+
+void subdomain_free_problem(JJHandle* h) {
+    SubState* st = (SubState*)h->subdomain_plan;
+    if (!st) return;
+    dev_free(h, st->rth, st->state_bytes); dev_free(h, st->rx, st->state_bytes);
+    dev_free(h, st->zloc, st->z_bytes); dev_free(h, st->ctop, st->c_bytes);
+    dev_free(h, st->rtop, st->t_bytes); dev_free(h, st->jtop, st->t_bytes);
+    dev_free(h, st->bar, 256);
+    dev_free(h, st->plane_d, st->plane_cap);
+    st->rth = st->rx = st->zloc = st->ctop = st->rtop = st->jtop = nullptr; st->bar = nullptr;
+    st->plane_d = nullptr; st->plane_cap = 0; st->state_bytes = st->z_bytes = st->c_bytes = st->t_bytes = 0;
+    st->prepared = false;
+}
+
+void subdomain_drop_plan(JJHandle* h) {
+    SubState* st = (SubState*)h->subdomain_plan;
+    if (!st) return;
+    subdomain_free_problem(h);
+    for (size_t i = 0; i < st->allocs.size(); ++i) dev_free(h, st->allocs[i], st->alloc_bytes[i]);
+    delete st;
+    h->subdomain_plan = nullptr;
+}
+
+int subdomain_set_plan(JJHandle* h, const JJSubdomainPlan* pl) {
+    subdomain_drop_plan(h);
+    if (!pl) return JJ_OK;
+    if (!(pl->NG == 1 || pl->NG == 2 || pl->NG == 4 || pl->NG == 8) || pl->P < 1 || pl->n_top_pad % 32 != 0) {
+        h->err = "subdomain plan: NG must be 1/2/4/8, P >= 1, n_top_pad a multiple of 32";
+        return JJ_EINVAL;
+    }
+    SubState* st = new SubState();
+    h->subdomain_plan = st;
+    st->P = pl->P; st->NG = pl->NG; st->PC = 8 * pl->NG;
+    st->n_rows = pl->n_rows; st->n_loc_max = pl->n_loc_max; st->stage_rows = pl->stage_rows;
+    st->n_top = pl->n_top; st->n_top_pad = pl->n_top_pad; st->n_slots = pl->n_slots; st->face_K = pl->face_K;
+    if ((size_t)st->n_rows * st->PC > 65536) { h->err = "subdomain plan: shared-memory vector exceeds the 16-bit element codes"; return JJ_EINVAL; }
+    const int Nj = h->cir.Nj, P = pl->P;
+    int rc;
+    std::vector<SubProgDev> progs(P);
+    for (int s = 0; s < P; ++s) {
+        const JJSubProgram& ps = pl->prog[s];
+        if (ps.n_warps != NWARPS) { h->err = "subdomain plan: program packed for a different warp count"; return JJ_EINVAL; }
+        const size_t np = (size_t)ps.n_levels * NWARPS + 1;
+        int *wt, *ws, *th, *ls; unsigned char* sb;
+        if ((rc = up(h, st, &wt, ps.wt_ptr, np))) return rc;
+        if ((rc = up(h, st, &ws, ps.ws_ptr, np))) return rc;
+        if ((rc = up(h, st, &th, ps.thdr, (size_t)ps.n_tiles * 2))) return rc;
+        if ((rc = up(h, st, &ls, ps.lstaged, (size_t)ps.n_levels))) return rc;
+        // stream + 2*RING zero steps of padding (the kernel prefetches RING steps ahead unconditionally)
+        if ((rc = up(h, st, &sb, ps.stream, (size_t)ps.n_steps * STEP_BYTES, (size_t)2 * RING * STEP_BYTES))) return rc;
+        progs[s].wt_ptr = wt; progs[s].ws_ptr = ws; progs[s].thdr = (const int2*)th; progs[s].lstaged = ls; progs[s].stream = sb;
+        progs[s].n_levels = ps.n_levels; progs[s].n_bwd = ps.n_bwd; progs[s].n_tiles = ps.n_tiles; progs[s].pad_ = 0;
+        st->max_np = std::max(st->max_np, (int)np);
+        st->max_levels = std::max(st->max_levels, ps.n_levels);
+        st->max_tiles = std::max(st->max_tiles, ps.n_tiles);
+    }
+    if ((rc = up(h, st, &st->prog, progs.data(), (size_t)P))) return rc;
+    if ((rc = up(h, st, &st->n_loc, pl->n_loc, (size_t)P))) return rc;
+    if ((rc = up(h, st, &st->n_halo, pl->n_halo, (size_t)P))) return rc;
+    if ((rc = up(h, st, &st->hptr, pl->hptr, (size_t)P + 1))) return rc;
+    if ((rc = up(h, st, &st->halo_top, pl->halo_top, (size_t)pl->n_slots))) return rc;
+    if ((rc = up(h, st, &st->tptr, pl->tptr, (size_t)pl->n_top + 1))) return rc;
+    if ((rc = up(h, st, &st->tslot, pl->tslot, (size_t)pl->n_slots))) return rc;
+    if ((rc = up(h, st, &st->top_face, pl->top_face, (size_t)pl->n_top))) return rc;
+    if ((rc = up(h, st, &st->SinvP, pl->Sinv_packed, (size_t)pl->n_top_pad * pl->n_top_pad))) return rc;
+    if ((rc = up(h, st, &st->junc_ptr, pl->junc_ptr, (size_t)P + 1))) return rc;
+    if ((rc = up(h, st, &st->junc_orig, pl->junc_orig, (size_t)Nj))) return rc;
+    if ((rc = up(h, st, (int**)&st->junc_row, pl->junc_row, (size_t)Nj * 2))) return rc;
+    if ((rc = up(h, st, (signed char**)&st->junc_sign, (const signed char*)pl->junc_sign, (size_t)Nj * 2))) return rc;
+    const size_t nell = (size_t)P * pl->n_rows * pl->face_K;
+    if ((rc = up(h, st, &st->face_ell_j, pl->face_ell_j, nell))) return rc;
+    if ((rc = up(h, st, &st->face_ell_c, pl->face_ell_c, nell))) return rc;
+    if ((rc = up(h, st, &st->face_fidx, pl->face_fidx, (size_t)P * pl->n_rows))) return rc;
+    for (double** pp : {&st->P0, &st->P1}) {
+        void* p = nullptr;
+        if ((rc = dev_alloc(h, &p, (size_t)Nj * 4 * sizeof(double)))) return rc;
+        st->allocs.push_back(p); st->alloc_bytes.push_back((size_t)Nj * 4 * sizeof(double));
+        *pp = (double*)p;
+    }
+    SCK(cudaStreamSynchronize(h->stream));
+    st->smem_bytes = smem_for(st);
+    if (st->smem_bytes > 227 * 1024) { h->err = "subdomain plan: shared memory per block exceeds 227 KB"; return JJ_EINVAL; }
+    return JJ_OK;
+}
+
+int subdomain_supported(JJHandle* h, std::string& why) {
+    SubState* st = (SubState*)h->subdomain_plan;
+    if (!st) { why = "no subdomain plan was provided"; return 0; }
+    for (int i = 0; i < 4; ++i)
+        if (h->src[i].dev.kind == KIND_DENSE) { why = "a per-step input is dense (not base x amplitude)"; return 0; }
+    if (h->cir.Nf == 0) { why = "circuit has no faces"; return 0; }
+    return 1;
+}
+
+static void fill_args(JJHandle* h, SubState* st, SubArgs& a) {
+    memset(&a, 0, sizeof(a));
+    a.P = st->P; a.n_rows = st->n_rows; a.n_loc_max = st->n_loc_max; a.stage_rows = st->stage_rows;
+    a.n_top = st->n_top; a.n_top_pad = st->n_top_pad; a.n_slots = st->n_slots;
+    a.max_np = st->max_np; a.max_levels = st->max_levels; a.max_tiles = st->max_tiles;
+    a.prog = st->prog; a.n_loc = st->n_loc; a.n_halo = st->n_halo; a.hptr = st->hptr; a.halo_top = st->halo_top;
+    a.tptr = st->tptr; a.tslot = st->tslot; a.top_face = st->top_face; a.SinvP = st->SinvP;
+    a.junc_ptr = st->junc_ptr; a.junc_orig = st->junc_orig; a.junc_row = st->junc_row; a.junc_sign = st->junc_sign;
+    a.face_K = st->face_K; a.face_ell_j = st->face_ell_j; a.face_ell_c = st->face_ell_c; a.face_fidx = st->face_fidx;
+    a.Nj = h->cir.Nj; a.Nf = h->cir.Nf; a.P0 = st->P0; a.P1 = st->P1; a.cpr = h->cir.cpr;
+    a.Wp = h->Wp; a.n_chunks = st->n_chunks; a.dt = h->dt; a.seed = h->seed; a.group_offset = h->problem_offset / 4;
+    a.Is = h->src[JJ_SRC_IS].dev; a.Vs = h->src[JJ_SRC_VS].dev; a.T = h->src[JJ_SRC_T].dev; a.F = h->src[JJ_SRC_F].dev;
+    a.noise = h->noise_buf; a.noise_i0 = h->noise_i0; a.noise_K = h->noise_K;
+    a.rth = st->rth; a.rx = st->rx; a.th1 = h->th1; a.th2 = h->th2;
+    a.zloc = st->zloc; a.ctop = st->ctop; a.rtop = st->rtop; a.jtop = st->jtop; a.bar = st->bar;
+    a.snap_th = h->th_out; a.snap_I = h->I_out; a.flag = h->flag_d;
+}
+
+static int launch(JJHandle* h, SubState* st, SubArgs& a) {
+    KernelPtr k = pick_kernel(st->NG, h->cir.default_cpr);
+    {
+        const Source &is = h->src[JJ_SRC_IS].dev, &t = h->src[JJ_SRC_T].dev, &vs = h->src[JJ_SRC_VS].dev;
+        k_sub_gather_params<<<(h->cir.Nj + 255) / 256, 256, 0, h->stream>>>(
+            h->cir.Nj, st->junc_orig, h->cir.Ic, h->cir.c0, h->cir.c1, h->cir.c2,
+            is.kind == KIND_RANK1 ? is.base : nullptr, t.kind == KIND_RANK1 ? t.base : nullptr,
+            vs.kind == KIND_RANK1 ? vs.base : nullptr, st->P0, st->P1);
+        h->launches++;
+    }
+    SCK(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem_bytes));
+    if (st->grid == 0) {
+        int per_sm = 0, sms = 0;
+        SCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, NT, st->smem_bytes));
+        SCK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+        if (per_sm <= 0) { h->err = "subdomain: kernel does not fit on the device"; return JJ_EINVAL; }
+        st->grid = sms * std::min(per_sm, 1);
+    }
+    const int MT = st->n_top_pad / 32;
+    int want = std::max(st->P * st->n_chunks, MT * st->n_chunks);
+    const char* env = getenv("JJ_SUB_GRID");
+    int grid = std::min(st->grid, std::max(1, want));
+    if (env && atoi(env) > 0) grid = std::min(st->grid, atoi(env));
+    SCK(cudaMemsetAsync(st->bar, 0, 256, h->stream));
+    void* params[] = {(void*)&a};
+    SCK(cudaLaunchCooperativeKernel((const void*)k, dim3(grid), dim3(NT), params, st->smem_bytes, h->stream));
+    h->launches++;
+    return JJ_OK;
+}
+
+int subdomain_prepare(JJHandle* h) {
+    SubState* st = (SubState*)h->subdomain_plan;
+    if (!st) { h->err = "subdomain engine: no plan"; return JJ_ESTATE; }
+    subdomain_free_problem(h);
+    const int PC = st->PC;
+    st->n_chunks = (h->Wp + PC - 1) / PC;
+    st->state_bytes = (size_t)st->n_chunks * h->cir.Nj * PC * sizeof(double);
+    st->z_bytes = (size_t)st->n_chunks * st->P * std::max(st->n_loc_max, 1) * PC * sizeof(double);
+    st->c_bytes = (size_t)st->n_chunks * std::max(st->n_slots, 1) * PC * sizeof(double);
+    st->t_bytes = (size_t)st->n_chunks * std::max(st->n_top_pad, 32) * PC * sizeof(double);
+    int rc;
+    if ((rc = dev_alloc(h, (void**)&st->rth, st->state_bytes))) return rc;
+    if ((rc = dev_alloc(h, (void**)&st->rx, st->state_bytes))) return rc;
+    if ((rc = dev_alloc(h, (void**)&st->zloc, st->z_bytes))) return rc;
+    if ((rc = dev_alloc(h, (void**)&st->ctop, st->c_bytes))) return rc;
+    if ((rc = dev_alloc(h, (void**)&st->rtop, st->t_bytes))) return rc;
+    if ((rc = dev_alloc(h, (void**)&st->jtop, st->t_bytes))) return rc;
+    if ((rc = dev_alloc(h, (void**)&st->bar, 256))) return rc;
+    SCK(cudaMemsetAsync(st->rth, 0, st->state_bytes, h->stream));
+    SCK(cudaMemsetAsync(st->rx, 0, st->state_bytes, h->stream));
+    SCK(cudaMemsetAsync(st->zloc, 0, st->z_bytes, h->stream));
+    SCK(cudaMemsetAsync(st->ctop, 0, st->c_bytes, h->stream));
+    SCK(cudaMemsetAsync(st->rtop, 0, st->t_bytes, h->stream));
+    SCK(cudaMemsetAsync(st->jtop, 0, st->t_bytes, h->stream));
+    st->prepared = true;
+    return JJ_OK;
+}
+
+bool subdomain_prepared(JJHandle* h) {
+    SubState* st = (SubState*)h->subdomain_plan;
+    return st && st->prepared;
+}
+
+int subdomain_run(JJHandle* h, long long i0, int n, const long long* th_plane, const long long* I_plane) {
+    SubState* st = (SubState*)h->subdomain_plan;
+    if (!st || !st->prepared) { h->err = "subdomain engine not prepared"; return JJ_ESTATE; }
+    size_t need = (size_t)2 * n * sizeof(long long);
+    if (need > st->plane_cap) {
+        SCK(cudaStreamSynchronize(h->stream));
+        dev_free(h, st->plane_d, st->plane_cap);
+        st->plane_d = nullptr; st->plane_cap = 0;
+        int rc = dev_alloc(h, (void**)&st->plane_d, need);
+        if (rc) return rc;
+        st->plane_cap = need;
+    }
+    std::vector<long long> pl((size_t)2 * n, -1);
+    for (int k = 0; k < n; ++k) {
+        if (th_plane) pl[k] = th_plane[k];
+        if (I_plane) pl[n + k] = I_plane[k];
+        if (pl[k] >= h->n_th_planes || pl[n + k] >= h->n_I_planes) { h->err = "run: plane index out of range"; return JJ_EINVAL; }
+    }
+    SCK(cudaMemcpyAsync(st->plane_d, pl.data(), need, cudaMemcpyHostToDevice, h->stream));
+    SCK(cudaStreamSynchronize(h->stream));     // pl goes out of scope
+    SubArgs a;
+    fill_args(h, st, a);
+    a.i0 = i0; a.n = n; a.th_plane = st->plane_d; a.I_plane = st->plane_d + n;
+    if (!getenv("JJ_SUB_PROF")) return launch(h, st, a);
+    // debugging aid: per-phase cycle counts of every block, printed as averages per time step
+    const size_t nb = 1024;
+    long long* prof = nullptr;
+    SCK(cudaMalloc((void**)&prof, nb * 8 * sizeof(long long)));
+    SCK(cudaMemset(prof, 0, nb * 8 * sizeof(long long)));
+    a.prof = prof;
+    int rc = launch(h, st, a);
+    if (rc) { cudaFree(prof); return rc; }
+    SCK(cudaStreamSynchronize(h->stream));
+    std::vector<long long> hp(nb * 8);
+    SCK(cudaMemcpy(hp.data(), prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(prof);
+    static const char* names[8] = {"bwd sweep", "junction pass", "face pass", "fwd sweep + store", "barrier 1 (wait)", "top assemble + barrier 2",
+                                   "top product", "barrier 3 (wait)"};
+    fprintf(stderr, "JJ_SUB_PROF: cycles per time step (n=%d steps, P=%d, PC=%d, chunks=%d)\n", n, st->P, st->PC, st->n_chunks);
+    double tot = 0;
+    for (int sl = 0; sl < 8; ++sl) {
+        double sum = 0, mx = 0; int cnt = 0;
+        for (size_t b = 0; b < nb; ++b) { double v = (double)hp[b * 8 + sl] / n; if (v > 0) { sum += v; ++cnt; } mx = std::max(mx, v); }
+        double avg = cnt ? sum / cnt : 0; tot += avg;
+        fprintf(stderr, "  %-26s avg %9.0f max %9.0f (blocks %d)\n", names[sl], avg, mx, cnt);
+    }
+    fprintf(stderr, "  total avg cycles per time step %.0f\n", tot);
+    return JJ_OK;
+}
+
+int subdomain_debug_solve(JJHandle* h, const double* b_d, double* J_d) {
+    SubState* st = (SubState*)h->subdomain_plan;
+    if (!st) { h->err = "subdomain engine: no plan"; return JJ_ESTATE; }
+    if (!st->prepared) { int rc = subdomain_prepare(h); if (rc) return rc; }
+    SubArgs a;
+    fill_args(h, st, a);
+    a.dbg_b = b_d; a.dbg_J = J_d;
+    return launch(h, st, a);
+}
+
+void subdomain_get_config(JJHandle* h, int* P, int* PC) {
+    SubState* st = (SubState*)h->subdomain_plan;
+    *P = st ? st->P : 1; *PC = st ? st->PC : 0;
+}
+
+}  // namespace jj

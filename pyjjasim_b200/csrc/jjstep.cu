@@ -379,6 +379,7 @@ static void free_problem(JJHandle* h) {
     dev_free(h, h->th_out, (size_t)h->n_th_planes * nj); dev_free(h, h->I_out, (size_t)h->n_I_planes * nj);
     h->th_out = h->I_out = nullptr; h->n_th_planes = h->n_I_planes = 0;
     resident_free(h);
+    subdomain_free_problem(h);
     h->have_problem = h->have_state = false;
 }
 
@@ -396,6 +397,7 @@ void jj_destroy(JJHandle* h) {
     cudaStreamSynchronize(h->stream);
     free_problem(h);
     resident_drop_plan(h);
+    subdomain_drop_plan(h);
     free_sweep(h, h->fwd); free_sweep(h, h->bwd);
     free_circuit(h);
     cudaFree(h->flag_d);
@@ -410,6 +412,7 @@ int jj_set_circuit(JJHandle* h, const JJCircuit* c) {
     REQUIRE(c->cpr_harmonics >= 1 && c->cpr_harmonics <= 16, JJ_EINVAL, "circuit: cpr_harmonics must be 1..16");
     if (h->have_problem) free_problem(h);
     resident_drop_plan(h);
+    subdomain_drop_plan(h);
     free_circuit(h);
     CircuitDev& d = h->cir;
     d.Nj = c->Nj; d.Nf = c->Nf;
@@ -442,6 +445,7 @@ int jj_set_solver(JJHandle* h, const JJSweep* fwd, const JJSweep* bwd) {
     REQUIRE(fwd && bwd, JJ_EINVAL, "solver: null sweep");
     if (h->have_problem) free_problem(h);
     resident_drop_plan(h);
+    subdomain_drop_plan(h);
     int rc;
     if ((rc = upload_sweep(h, h->fwd, fwd))) return rc;
     if ((rc = upload_sweep(h, h->bwd, bwd))) return rc;
@@ -454,7 +458,7 @@ int jj_set_problem(JJHandle* h, int32_t W, double dt, uint64_t seed, int64_t pro
     REQUIRE(h->have_circuit && h->have_solver, JJ_ESTATE, "set_problem: circuit and solver must be set first");
     REQUIRE(W > 0 && dt > 0, JJ_EINVAL, "set_problem: W and dt must be positive");
     REQUIRE(problem_offset % 4 == 0, JJ_EINVAL, "set_problem: problem_offset must be a multiple of 4");
-    REQUIRE(engine >= 0 && engine <= 2, JJ_EINVAL, "set_problem: unknown engine");
+    REQUIRE(engine >= 0 && engine <= 3, JJ_EINVAL, "set_problem: unknown engine");
     free_problem(h);
     h->W = W; h->Wp = (W + 3) / 4 * 4; h->dt = dt; h->seed = seed; h->problem_offset = problem_offset;
     h->engine_req = engine;
@@ -671,18 +675,25 @@ int jj_run(JJHandle* h, int64_t i0, int32_t n, const int64_t* th_plane, const in
     // engine choice
     int want = h->engine_req;
     std::string why;
-    if (want == JJ_ENGINE_AUTO) want = resident_supported(h, why) ? JJ_ENGINE_RESIDENT : JJ_ENGINE_STREAMING;
+    if (want == JJ_ENGINE_AUTO)
+        want = (!h->thetas && subdomain_supported(h, why)) ? JJ_ENGINE_SUBDOMAIN
+               : (!h->thetas && resident_supported(h, why)) ? JJ_ENGINE_RESIDENT : JJ_ENGINE_STREAMING;
     if (want == JJ_ENGINE_RESIDENT) {
         if (!resident_supported(h, why)) { h->err = "resident engine not applicable: " + why; return JJ_EINVAL; }
         if (!h->resident) { if ((rc = resident_prepare(h))) return rc; }
     }
-    if (want == JJ_ENGINE_RESIDENT && h->thetas) {
-        h->err = "resident engine does not support dense voltage sources";
+    if (want == JJ_ENGINE_SUBDOMAIN) {
+        if (!subdomain_supported(h, why)) { h->err = "subdomain engine not applicable: " + why; return JJ_EINVAL; }
+        if (!subdomain_prepared(h)) { if ((rc = subdomain_prepare(h))) return rc; }
+    }
+    if ((want == JJ_ENGINE_RESIDENT || want == JJ_ENGINE_SUBDOMAIN) && h->thetas) {
+        h->err = "the shared-memory engines do not support dense voltage sources";
         return JJ_EINVAL;
     }
     h->engine = want;
     CK(cudaEventRecord(h->ev0, h->stream));
     if (want == JJ_ENGINE_RESIDENT) rc = resident_run(h, i0, n, (const long long*)th_plane, (const long long*)I_plane);
+    else if (want == JJ_ENGINE_SUBDOMAIN) rc = subdomain_run(h, i0, n, (const long long*)th_plane, (const long long*)I_plane);
     else rc = streaming_run(h, i0, n, (const long long*)th_plane, (const long long*)I_plane);
     if (rc) return rc;
     CK(cudaEventRecord(h->ev1, h->stream));
@@ -756,6 +767,30 @@ int jj_set_resident_plan(JJHandle* h, const JJResidentPlan* plan) {
     return resident_set_plan(h, plan);
 }
 
+int jj_set_subdomain_plan(JJHandle* h, const JJSubdomainPlan* plan) {
+    CK(cudaSetDevice(h->device));
+    REQUIRE(h->have_circuit && h->have_solver, JJ_ESTATE, "set_subdomain_plan: circuit and solver must be set first");
+    if (h->have_problem) free_problem(h);
+    return subdomain_set_plan(h, plan);
+}
+
+int jj_debug_subdomain_solve(JJHandle* h, const double* b, double* J) {
+    CK(cudaSetDevice(h->device));
+    REQUIRE(h->have_problem && h->cir.Nf > 0, JJ_ESTATE, "debug_subdomain_solve: problem not set");
+    double* tmp = nullptr;
+    size_t bytes = (size_t)h->cir.Nf * h->Wp * sizeof(double);
+    int rc = dev_alloc(h, (void**)&tmp, bytes);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(tmp, 0, bytes, h->stream));
+    CK(cudaMemsetAsync(h->v, 0, bytes, h->stream));
+    if ((rc = h2d_padded(h, h->v, b, h->cir.Nf)) == 0 && (rc = subdomain_debug_solve(h, h->v, tmp)) == 0)
+        rc = d2h_padded(h, J, tmp, h->cir.Nf);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    dev_free(h, tmp, bytes);
+    if (rc == 0 && e != cudaSuccess) { h->err = std::string("debug_subdomain_solve: ") + cudaGetErrorString(e); rc = JJ_ECUDA; }
+    return rc;
+}
+
 int jj_debug_resident_solve(JJHandle* h, const double* b, double* J) {
     CK(cudaSetDevice(h->device));
     REQUIRE(h->have_problem && h->cir.Nf > 0, JJ_ESTATE, "debug_resident_solve: problem not set");
@@ -783,6 +818,7 @@ int jj_stats(JJHandle* h, JJStats* out) {
     out->non_finite = h->non_finite;
     out->cluster_size = 1; out->tile_problems = h->Wp;
     if (h->engine == JJ_ENGINE_RESIDENT) { int c, w; resident_get_config(h, &c, &w); out->cluster_size = c; out->tile_problems = w; }
+    if (h->engine == JJ_ENGINE_SUBDOMAIN) { int c, w; subdomain_get_config(h, &c, &w); out->cluster_size = c; out->tile_problems = w; }
     return JJ_OK;
 }
 

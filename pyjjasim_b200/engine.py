@@ -24,6 +24,7 @@ import scipy.sparse
 from . import _lib
 from .current_phase_relation import harmonics
 from .factor import factorize, streaming_program, resident_plan, system_matrix
+from .subdomain import subdomain_plan, face_tables
 from .sources import classify_source, nonnegative_factors, ZERO, RANK1, DENSE
 
 __all__ = ["device_time_evolution_core", "CircuitTables", "DeviceEngine", "last_run_stats"]
@@ -93,6 +94,51 @@ class CircuitTables:
         js[rows, slot] = At.data
         self.junc_face, self.junc_sign = jf, js
         self._resident = {}
+        self._subdomain = {}
+
+    # ------------------------------------------------------------------ subdomain engine plan
+    def subdomain_smem_bytes(self, plan):
+        PC = plan.PC
+        aux = 2 * max(ps["n_levels"] * ps["n_warps"] + 1 for ps in plan.prog) + max(ps["n_levels"] for ps in plan.prog) \
+            + 2 * max(len(ps["thdr"]) for ps in plan.prog) + 10
+        return (plan.n_rows * PC + plan.stage_rows * (PC + 2)) * 8 + 64 * PC + 4 * aux
+
+    def subdomain_plan(self, d, NG):
+        key = (d, NG)
+        if key not in self._subdomain:
+            plan = subdomain_plan(self.factor, self.junc_face, d, NG)
+            face_tables(plan, self.face_ptr, self.face_junc, self.face_sign, self.junc_sign, self.c0)
+            self._subdomain[key] = plan
+        return self._subdomain[key]
+
+    def choose_subdomain(self, W, n_sm=148):
+        """Pick (cut depth d, problem groups NG) for the subdomain engine, or None. JJ_SUBDOMAIN="d,NG" overrides.
+        Preference: fill the SMs with (subdomain, chunk) items, keep chunks wide (factor reuse) and the top small."""
+        if self.factor is None:
+            return None
+        env = os.environ.get("JJ_SUBDOMAIN")
+        if env:
+            d, NG = (int(v) for v in env.split(","))
+            return d, NG
+        Wp = (W + 3) // 4 * 4
+        max_d = int(self.factor.depth.max()) if self.factor.nb else 0
+        NG = 4 if Wp > 16 else 2 if Wp > 8 else 1
+        chunks = (Wp + 8 * NG - 1) // (8 * NG)
+        # as many subdomains as there are SMs to fill, but none smaller than ~64 faces (below that the top product
+        # and the barriers cost more than the local sweeps save)
+        d_hi = 0
+        while d_hi < min(max_d - 1, 6) and (2 << d_hi) * chunks <= n_sm and self.Nf >= 64 * (2 << d_hi):
+            d_hi += 1
+        for d in list(range(d_hi, 7)):
+            if d > max(max_d - 1, 0):
+                break
+            try:
+                plan = self.subdomain_plan(d, NG)
+            except ValueError:
+                continue
+            if self.subdomain_smem_bytes(plan) <= self.SMEM_LIMIT:
+                return d, NG
+        return None
 
     # ------------------------------------------------------------------ resident engine plan
     SMEM_LIMIT = 227 * 1024
@@ -301,6 +347,59 @@ class DeviceEngine:
         self._ck(self.lib.jj_set_resident_plan(self.h, C.byref(p)))
         self.resident_config = (Ccl, Wt)
 
+    def set_subdomain(self, d, NG):
+        """Upload the subdomain-engine plan for cut depth d and NG groups of 8 problems per chunk."""
+        plan = self.tab.subdomain_plan(d, NG)
+        p = _lib.JJSubdomainPlan()
+        p.P, p.NG, p.n_rows, p.n_loc_max, p.stage_rows = plan.P, plan.NG, plan.n_rows, plan.n_loc_max, plan.stage_rows
+        p.n_top, p.n_top_pad, p.n_slots = plan.n_top, plan.n_top_pad, plan.n_slots
+        keep = []
+
+        def a32(x):
+            x = np.ascontiguousarray(x, dtype=np.int32)
+            if x.size == 0:
+                x = np.zeros(1, dtype=np.int32)
+            keep.append(x)
+            return _lib.i32(x)
+
+        def a64f(x):
+            x = np.ascontiguousarray(x, dtype=np.double)
+            if x.size == 0:
+                x = np.zeros(1)
+            keep.append(x)
+            return _lib.f64(x)
+        p.n_loc, p.n_halo, p.hptr, p.halo_top = a32(plan.n_loc), a32(plan.n_halo), a32(plan.hptr), a32(plan.halo_top)
+        p.tptr, p.tslot, p.top_face = a32(plan.tptr), a32(plan.tslot), a32(plan.top_rows)
+        p.Sinv_packed = a64f(plan.Sinv_packed)
+
+        def sub_prog(ps, n_bwd):
+            r = _lib.JJSubProgram()
+            r.n_levels, r.n_bwd, r.n_warps, r.n_tiles = ps["n_levels"], int(n_bwd), ps["n_warps"], len(ps["thdr"])
+            r.wt_ptr, r.ws_ptr, r.thdr, r.lstaged = a32(ps["wt_ptr"]), a32(ps["ws_ptr"]), a32(ps["thdr"]), a32(ps["lstaged"])
+            r.n_steps = ps["n_steps"]
+            st = ps["stream"] if ps["stream"].size else np.zeros(1, dtype=np.uint8)
+            keep.append(st)
+            r.stream = st.ctypes.data_as(C.POINTER(C.c_uint8))
+            return r
+        progs = (_lib.JJSubProgram * plan.P)(*[sub_prog(ps, nb) for ps, nb in zip(plan.prog, plan.n_bwd)])
+        p.prog = progs
+        p.junc_ptr, p.junc_orig, p.junc_row = a32(plan.junc_ptr), a32(plan.junc_orig), a32(plan.junc_row)
+        js = np.ascontiguousarray(plan.junc_sign, dtype=np.int8)
+        keep.append(js)
+        p.junc_sign = _lib.i8(js)
+        p.face_K = plan.face_K
+        p.face_ell_j, p.face_ell_c, p.face_fidx = a32(plan.face_ell_j), a64f(plan.face_ell_c), a32(plan.face_fidx)
+        self._ck(self.lib.jj_set_subdomain_plan(self.h, C.byref(p)))
+        self.subdomain_config = (d, NG)
+
+    def debug_subdomain_solve(self, b):
+        bp = _lib.c_f64(np.asarray(b)[self.tab.perm])
+        Jp = np.empty_like(bp)
+        self._ck(self.lib.jj_debug_subdomain_solve(self.h, _lib.f64(bp), _lib.f64(Jp)))
+        J = np.empty_like(Jp)
+        J[self.tab.perm] = Jp
+        return J
+
     def debug_resident_solve(self, b):
         bp = _lib.c_f64(np.asarray(b)[self.tab.perm])
         Jp = np.empty_like(bp)
@@ -433,7 +532,13 @@ def _run_shard(problem, tab, specs, dev, w0, w1, th_mask, I_mask, th_host, I_hos
     eng = DeviceEngine(dev)
     try:
         eng.set_circuit(tab, problem.current_phase_relation)
-        if engine_kind != _lib.JJ_ENGINE_STREAMING:
+        if engine_kind in (_lib.JJ_ENGINE_AUTO, _lib.JJ_ENGINE_SUBDOMAIN):
+            cfg = tab.choose_subdomain(W)
+            if cfg is not None:
+                eng.set_subdomain(*cfg)
+            elif engine_kind == _lib.JJ_ENGINE_SUBDOMAIN:
+                raise ValueError("subdomain engine requested but no plan fits in shared memory")
+        if engine_kind == _lib.JJ_ENGINE_RESIDENT or (engine_kind == _lib.JJ_ENGINE_AUTO and cfg is None):
             cfg = tab.choose_resident(W)
             if cfg is not None:
                 eng.set_resident(*cfg)
@@ -553,7 +658,8 @@ def device_time_evolution_core(problem, th_store_mask, I_store_mask, engine=None
         devices = [int(d) for d in env.split(",")] if env else [0]
     if engine is None:
         engine = {"auto": _lib.JJ_ENGINE_AUTO, "streaming": _lib.JJ_ENGINE_STREAMING,
-                  "resident": _lib.JJ_ENGINE_RESIDENT}[os.environ.get("JJ_ENGINE", "auto")]
+                  "resident": _lib.JJ_ENGINE_RESIDENT,
+                  "subdomain": _lib.JJ_ENGINE_SUBDOMAIN}[os.environ.get("JJ_ENGINE", "auto")]
     bounds = shard_bounds(W, len(devices))
     stats = {}
     jobs = [(dev, bounds[k], bounds[k + 1]) for k, dev in enumerate(devices) if bounds[k + 1] > bounds[k]]

@@ -66,6 +66,7 @@ class Factor:
         self.Loff = None          # CSR: Lc without the diagonal blocks  (row i: couplings to earlier blocks)
         self.LoffT = None         # CSR: its transpose                   (row j: couplings to later blocks)
         self.nnz_L = 0
+        self.Lc = None            # CSR: the full Cholesky factor (subdomain engine: Schur complement of the top separators)
 
     @property
     def nb(self):
@@ -93,6 +94,7 @@ def factorize(S, cx, cy, leaf_size=8):
     Lc = (lu.L @ scipy.sparse.diags(np.sqrt(d))).tocsr()       # Cholesky factor
     Lc.sort_indices()
     F.nnz_L = int(Lc.nnz)
+    F.Lc = Lc
     nb = F.nb
     F.dinv = []
     for b in range(nb):

@@ -193,3 +193,74 @@ def test_device_noise_statistics_and_shard_invariance():
     assert abs(z.mean()) < 5 / np.sqrt(n) and abs(z.var() - 1) < 5 * np.sqrt(2 / n)
     assert abs(np.mean(z ** 4) - 3) < 0.1 and np.max(np.abs(z)) < 7
     assert abs(np.corrcoef(z[:-1].ravel(), z[1:].ravel())[0, 1]) < 5 / np.sqrt(n)
+
+
+# ------------------------------------------------------------------------------------------------
+# subdomain engine (cooperative kernel): cut depths / chunk widths against a direct solve and the golden vectors
+# ------------------------------------------------------------------------------------------------
+SUBDOMAIN_CONFIGS = ["0,1", "1,2", "2,4", "3,4", "2,8", "4,1"]
+
+
+@pytest.mark.parametrize("W", [13, 70])
+@pytest.mark.parametrize("cfg", SUBDOMAIN_CONFIGS)
+def test_subdomain_solve_matches_direct_solve(cfg, W):
+    import scipy.sparse.linalg
+    from pyjjasim_b200 import engine
+    from pyjjasim_b200.factor import system_matrix
+    d, NG = (int(v) for v in cfg.split(","))
+    a = pj.SquareArray(40, 37)
+    rng = np.random.RandomState(2)
+    a.set_resistance(0.5 + rng.rand(a._Nj()))
+    a.set_inductance(0.1)
+    tab = engine.CircuitTables(a, 0.05)
+    eng = engine.DeviceEngine(0)
+    eng.set_circuit(tab, pj.DefaultCPR())
+    eng.set_subdomain(d, NG)
+    eng.set_problem(W, 0.05)
+    b = rng.randn(a._Nf(), W)
+    J = eng.debug_subdomain_solve(b)
+    S = system_matrix(a.get_cycle_matrix(), a._L(), tab.Rv, tab.Cv)
+    Jref = scipy.sparse.linalg.spsolve(S.tocsc(), b)
+    eng.close()
+    assert np.max(np.abs(J - Jref)) <= 1e-12 * np.max(np.abs(Jref))
+
+
+@pytest.mark.parametrize("cfg", ["0,1", "1,2", "2,4", "3,1"])
+@pytest.mark.parametrize("name", ["sq_mixed", "sq_frustrated", "honeycomb", "noise_recycled", "custom_cpr", "sq_iv"])
+def test_subdomain_engine_matches_reference_golden(name, cfg, golden_dir, monkeypatch):
+    monkeypatch.setenv("JJ_SUBDOMAIN", cfg)
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    kw, prob, res = run_device(name, "subdomain")
+    from pyjjasim_b200 import engine
+    st = engine.last_run_stats[0]
+    d, NG = (int(v) for v in cfg.split(","))
+    assert st["engine"] == 3 and (st["cluster_size"], st["tile_problems"]) == (1 << d, 8 * NG)
+    tol = cases.TOL[name]
+    assert np.max(np.abs(res.theta - g["theta"])) <= tol
+    if "current" in g.files:
+        assert np.max(np.abs(res.current - g["current"])) <= 10 * tol
+    if "voltage" in g.files:
+        assert np.max(np.abs(res.voltage - g["voltage"])) <= 10 * tol / kw.get("time_step", 0.05)
+
+
+def test_subdomain_multiple_items_per_block(monkeypatch):
+    # more (subdomain, chunk) items than thread blocks: z goes through global memory; same trajectories
+    monkeypatch.setenv("JJ_SUBDOMAIN", "2,1")
+    kw, _ = cases.build("noise_small", pj)
+    kw["noise_seed"] = 7
+    out = {}
+    for grid in ("0", "3"):
+        monkeypatch.setenv("JJ_SUB_GRID", grid)
+        monkeypatch.setenv("JJ_ENGINE", "subdomain")
+        out[grid] = pj.TimeEvolutionProblem(**kw).compute().theta
+    assert np.array_equal(out["0"], out["3"])
+
+
+def test_subdomain_and_streaming_agree_on_device_noise(monkeypatch):
+    kw, _ = cases.build("noise_small", pj)
+    kw["noise_seed"] = 99
+    out = {}
+    for eng_name in ("streaming", "subdomain"):
+        monkeypatch.setenv("JJ_ENGINE", eng_name)
+        out[eng_name] = pj.TimeEvolutionProblem(**kw).compute().theta
+    assert np.max(np.abs(out["streaming"] - out["subdomain"])) <= 1e-9

@@ -95,6 +95,30 @@ def test_solve_program_matches_direct_solve(ctor, args, leaf):
     assert prog.stats["levels_fwd"] == 2 * prog.stats["height"] + 1
 
 
+@pytest.mark.parametrize("ctor,args,d,NG", [(pj.SquareArray, (23, 17), 2, 4), (pj.HoneycombArray, (9, 7), 1, 2),
+                                            (pj.SquareArray, (40, 37), 3, 4), (pj.SquareArray, (12, 10), 0, 1),
+                                            (pj.TriangularArray, (8, 6), 2, 8)])
+def test_subdomain_plan_matches_direct_solve(ctor, args, d, NG):
+    # the subdomain engine's plan (local sweeps + dense top inverse), interpreted on the host
+    from pyjjasim_b200.subdomain import apply_subdomain_plan_host
+    a = ctor(*args)
+    rng = np.random.RandomState(1)
+    a.set_resistance(0.5 + rng.rand(a._Nj()))
+    a.set_inductance(0.1 * rng.rand(a._Nj()))
+    tab = CircuitTables(a, 0.05)
+    plan = tab.subdomain_plan(d, NG)
+    assert plan.P == 1 << d and plan.n_top + int(plan.n_loc.sum()) == a._Nf()
+    # every junction is owned once, every face entry appears in exactly one list
+    assert plan.junc_ptr[-1] == a._Nj() and np.sum(plan.face_ell_j >= 0) == a.get_cycle_matrix().nnz
+    S = system_matrix(a.get_cycle_matrix(), a._L(), tab.Rv, tab.Cv)
+    b = rng.randn(a._Nf(), plan.PC)
+    Jp = apply_subdomain_plan_host(plan, b[tab.perm])
+    J = np.empty_like(Jp)
+    J[tab.perm] = Jp
+    Jref = scipy.sparse.linalg.spsolve(S.tocsc(), b)
+    assert np.max(np.abs(J - Jref)) <= 1e-12 * np.max(np.abs(Jref))
+
+
 def test_circuit_tables_permutation_consistency():
     a = pj.HoneycombArray(6, 5)
     tab = CircuitTables(a, 0.05)
@@ -219,13 +243,14 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     # struct layouts of the ctypes mirror equal the C compiler's
     import subprocess, tempfile
-    src = '#include <stdio.h>\n#include "jjstep.h"\nint main(){printf("%zu %zu %zu %zu %zu", sizeof(JJSweep), sizeof(JJCircuit), sizeof(JJStats), sizeof(JJRankStream), sizeof(JJResidentPlan));return 0;}'
+    src = '#include <stdio.h>\n#include "jjstep.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu", sizeof(JJSweep), sizeof(JJCircuit), sizeof(JJStats), sizeof(JJRankStream), sizeof(JJResidentPlan), sizeof(JJSubProgram), sizeof(JJSubdomainPlan));return 0;}'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "s.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o", os.path.join(d, "s")])
         sizes = [int(v) for v in subprocess.check_output([os.path.join(d, "s")]).split()]
     assert sizes == [ctypes.sizeof(_lib.JJSweep), ctypes.sizeof(_lib.JJCircuit), ctypes.sizeof(_lib.JJStats),
-                     ctypes.sizeof(_lib.JJRankStream), ctypes.sizeof(_lib.JJResidentPlan)]
+                     ctypes.sizeof(_lib.JJRankStream), ctypes.sizeof(_lib.JJResidentPlan),
+                     ctypes.sizeof(_lib.JJSubProgram), ctypes.sizeof(_lib.JJSubdomainPlan)]
 
 
 def test_no_gpu_means_loud_failure():
