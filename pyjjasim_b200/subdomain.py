@@ -29,6 +29,7 @@ groups of row r are stored at group position g ^ (r & (NG-1)) (bank-conflict-fre
 import numpy as np
 import scipy.linalg
 import scipy.sparse
+import scipy.sparse.csgraph
 
 from .factor import TILE_SELF, TILE_STAGED, CHAIN_ROWS, STEP_BYTES, RES_WARPS, _lpt
 
@@ -85,16 +86,25 @@ def _pack_levels(levels, NG, n_warps):
                     t["stage_off"] = staged
                     staged += t["V"].shape[0]
         lstaged.append(staged)
-        split = 1
-        while split * 2 <= NG and len(units) * split * 2 <= n_warps:
-            split *= 2
-        ng = NG // split
-        tasks = [(ui, g0) for ui in range(len(units)) for g0 in range(0, NG, ng)]
-        costs = [sum(t["rec"].shape[0] * ng + 6 for t in units[ui]) for (ui, g0) in tasks]
+        # a unit is split over problem groups while it is longer than a warp's fair share of the level (or while
+        # there are fewer tasks than warps): the copies re-read the unit's stream but run concurrently
+        ucost = [sum(t["rec"].shape[0] for t in u) for u in units]
+        split = [1] * len(units)
+        while True:
+            share = sum(c * NG + 6 * sp for c, sp in zip(ucost, split)) / float(n_warps)
+            worst = max(range(len(units)), key=lambda i: ucost[i] * (NG // split[i])) if units else None
+            if worst is None or split[worst] >= NG:
+                break
+            if ucost[worst] * (NG // split[worst]) > 1.25 * share + 4 or sum(split) * 2 <= n_warps:
+                split[worst] *= 2
+            else:
+                break
+        tasks = [(ui, g0, NG // split[ui]) for ui in range(len(units)) for g0 in range(0, NG, NG // split[ui])]
+        costs = [ucost[ui] * ng + 6 * len(units[ui]) for (ui, g0, ng) in tasks]
         assign = _lpt(costs, n_warps)
         for w in range(n_warps):
             for ti in assign[w]:
-                ui, g0 = tasks[ti]
+                ui, g0, ng = tasks[ti]
                 for t in units[ui]:
                     nr, nc = t["V"].shape
                     st = t["rec"].shape[0]
@@ -114,12 +124,152 @@ def _pack_levels(levels, NG, n_warps):
                 vals=int(n_vals))
 
 
-def subdomain_plan(F, junc_face, d, NG, n_warps=RES_WARPS):
+def _tiles_sparse(M, row0, col_index, flags=TILE_SELF):
+    """8-row tiles of out[row0 + i] (+)= -M[i, :] src: M is CSR, col_index maps its columns to vector rows."""
+    units = []
+    M = scipy.sparse.csr_matrix(M)
+    for t0 in range(0, M.shape[0], 8):
+        sub = M[t0:t0 + 8]
+        cols = np.unique(sub.indices[sub.data != 0]) if sub.nnz else np.zeros(0, dtype=np.int64)
+        if cols.size == 0:
+            continue
+        units.append([dict(row0=int(row0 + t0), V=-sub[:, cols].toarray(), cols=col_index[cols], flags=flags)])
+    return units
+
+
+def _subdomain_levels(F, loc, hrows, blk_of, stage_cap, groups=None):
+    """
+    Sweep program of one subdomain as a list of levels (each a list of units of 8-row tiles).
+
+    The local tree levels are collected into a few GROUPS of consecutive heights. Inside a group the
+    triangular solve is replaced by the explicit inverse of the group's diagonal part (a block-diagonal matrix:
+    one dense triangular block per subtree that lies inside the group), so a sweep needs two wide levels per
+    group instead of two per tree level:
+        forward    t_R = b_R - L[R, lower groups] z            (sparse rows, in place)
+                   z_R = inv(L[R, R]) t_R                      (dense triangular blocks)
+        backward   t_R = z_R - L[higher groups + halo, R]^T J  (sparse rows, in place)
+                   J_R = inv(L[R, R])^T t_R
+    A block of at most CHAIN_ROWS rows is applied in place by one warp (its row tiles in dependency order);
+    larger blocks go through the staging rows, in passes of at most stage_cap rows ordered so that no pass
+    reads a row an earlier pass has replaced.
+
+    The local rows are renumbered: by group, then by block of the group's inverse, so every dense block is a
+    contiguous row range. Returns (levels, n_bwd, order, group_bounds); order[i] = index into loc of local row i.
+    """
+    n = loc.size
+    if n == 0:
+        return [], 0, np.zeros(0, dtype=np.int64), []
+    hrow = F.height[blk_of[loc]].astype(np.int64)
+    H = int(hrow.max())
+    L0 = scipy.sparse.csr_matrix(F.Lc[loc][:, loc])
+    if groups is None:
+        groups = _auto_groups(L0, hrow, stage_cap)
+    cuts = sorted(set(int(g) for g in groups if 0 <= int(g) < H))
+    gid = np.searchsorted(np.asarray(cuts, dtype=np.int64), hrow, side="left") if cuts else np.zeros(n, dtype=np.int64)
+    n_groups = len(cuts) + 1
+    # blocks of each group's inverse = connected components of L restricted to the group
+    comp = np.zeros(n, dtype=np.int64)
+    for g in range(n_groups):
+        R = np.flatnonzero(gid == g)
+        if R.size == 0:
+            continue
+        sub = L0[R][:, R]
+        _, lab = scipy.sparse.csgraph.connected_components(sub + sub.T, directed=False)
+        first = np.full(lab.max() + 1, n, dtype=np.int64)
+        np.minimum.at(first, lab, R)
+        comp[R] = first[lab]
+    order = np.lexsort((np.arange(n), comp, gid))
+    Lp = L0[order][:, order].tocsr()
+    assert scipy.sparse.triu(Lp, k=1).nnz == 0
+    gid_p, comp_p = gid[order], comp[order]
+    Lh = scipy.sparse.csr_matrix(F.Loff[hrows][:, loc[order]]) if hrows.size else scipy.sparse.csr_matrix((0, n))
+    ident = np.arange(n + hrows.size, dtype=np.int64)
+    gstart = np.searchsorted(gid_p, np.arange(n_groups + 1))
+    fwd, bwd = [], []
+    for g in range(n_groups):
+        a, b = int(gstart[g]), int(gstart[g + 1])
+        if a == b:
+            continue
+        Linv = scipy.linalg.solve_triangular(Lp[a:b, a:b].toarray(), np.eye(b - a), lower=True)
+        cstart = np.flatnonzero(np.concatenate(([True], comp_p[a + 1:b] != comp_p[a:b - 1], [True])))
+        chains_f, chains_b, staged_f, staged_b = [], [], [], []
+        for ci in range(cstart.size - 1):
+            c0, c1 = int(cstart[ci]), int(cstart[ci + 1])            # relative to a
+            starts = list(range(c0, c1, 8))
+            tf, tb = [], []
+            for t0 in starts:
+                t1 = min(c1, t0 + 8)
+                Vf = Linv[t0:t1, c0:t1]
+                cf = np.flatnonzero(np.any(Vf != 0, axis=0))
+                tf.append(dict(row0=a + t0, V=Vf[:, cf], cols=ident[a + c0 + cf], flags=0))
+                Vb = Linv[t0:c1, t0:t1].T
+                cb = np.flatnonzero(np.any(Vb != 0, axis=0))
+                tb.append(dict(row0=a + t0, V=Vb[:, cb], cols=ident[a + t0 + cb], flags=0))
+            if c1 - c0 <= CHAIN_ROWS:
+                chains_f.append(tf[::-1])       # lower triangular: a row group reads the rows above it -> last group first
+                chains_b.append(tb)
+            else:
+                staged_f.extend(tf)
+                staged_b.extend(tb)
+
+        def passes(tiles, descending):
+            tiles = sorted(tiles, key=lambda t: -t["row0"] if descending else t["row0"])
+            out, cur, rows = [], [], 0
+            for t in tiles:
+                t["flags"] = TILE_STAGED
+                nr = t["V"].shape[0]
+                if cur and rows + nr > stage_cap:
+                    out.append(cur)
+                    cur, rows = [], 0
+                cur.append([t])
+                rows += nr
+            if cur:
+                out.append(cur)
+            return out
+        pf, pb = passes(staged_f, True), passes(staged_b, False)
+        inv_f = [chains_f + (pf[0] if pf else [])] + pf[1:]
+        inv_b = [chains_b + (pb[0] if pb else [])] + pb[1:]
+        fwd.append((_tiles_sparse(Lp[a:b, :a], a, ident) if a > 0 else [], inv_f))
+        above = scipy.sparse.hstack([Lp[b:, a:b].T, Lh[:, a:b].T]).tocsr() if (b < n or hrows.size) else None
+        bwd.append((_tiles_sparse(above, a, ident[b:]) if above is not None else [], inv_b))
+    levels = []
+    for (ta, inv) in reversed(bwd):
+        levels.append(ta)
+        levels.extend(inv)
+    levels = [u for u in levels if u]
+    n_bwd = len(levels)
+    for (ta, inv) in fwd:
+        levels.append(ta)
+        levels.extend(inv)
+    if hrows.size:
+        levels.append(_tiles_sparse(Lh, n, ident))
+    levels = levels[:n_bwd] + [u for u in levels[n_bwd:] if u]
+    return levels, n_bwd, order, cuts
+
+
+def _auto_groups(L0, hrow, stage_cap):
+    """Group boundaries: the lowest group takes as many tree levels as keep its subtrees within CHAIN_ROWS rows
+    (applied in place by single warps); everything above forms one group (staged, usually a single pass)."""
+    H = int(hrow.max())
+    best = -1
+    for hb in range(H):
+        R = np.flatnonzero(hrow <= hb)
+        sub = L0[R][:, R]
+        _, lab = scipy.sparse.csgraph.connected_components(sub + sub.T, directed=False)
+        if np.bincount(lab).max() <= CHAIN_ROWS:
+            best = hb
+        else:
+            break
+    return [best] if best >= 0 else []
+
+
+def subdomain_plan(F, junc_face, d, NG, n_warps=RES_WARPS, groups=None):
     """
     F         : factor.Factor of the permuted cycle-space system
     junc_face : (Nj, 2) permuted faces of every junction, -1 none (CircuitTables.junc_face)
     d         : cut depth, P = 2^d subdomains
     NG        : problem groups of 8 per chunk (PC = 8 * NG problems share one pass over the factor)
+    groups    : tree heights after which a new level group starts (see _subdomain_levels); None = automatic
     """
     assert NG in (1, 2, 4, 8)
     n, nb = F.n, F.nb
@@ -196,74 +346,19 @@ def subdomain_plan(F, junc_face, d, NG, n_warps=RES_WARPS):
     plan.row_sub = row_sub
 
     # ---- per-subdomain sweep programs: backward levels first (they open a time step), then forward
-    Loff, LoffT = F.Loff, F.LoffT
     plan.prog, plan.n_bwd = [], []
+    plan.group_bounds = []
+    smem_limit = 227 * 1024 - 20 * 1024                 # room for headers, cursors and the amplitude cache
+    stage_cap = (smem_limit // 8 - plan.n_rows * PC) // (PC + 2)
+    if stage_cap < 8:
+        raise ValueError("subdomain plan: the right-hand sides leave no room for the staging rows")
+    stage_cap = min(stage_cap, 4096)
     for s in range(P):
-        vr = vrow[s]
-        lb = np.flatnonzero(blk_sub == s)
-        Hloc = int(F.height[lb].max()) if lb.size else -1
-
-        def tiles_a(blocks, M):
-            units = []
-            for b in blocks:
-                r0, r1 = int(F.bptr[b]), int(F.bptr[b + 1])
-                for t0 in range(r0, r1, 8):
-                    t1 = min(r1, t0 + 8)
-                    sub = M[t0:t1]
-                    cols = np.unique(sub.indices)
-                    if cols.size == 0:
-                        continue
-                    assert np.all(vr[cols] >= 0)
-                    units.append([dict(row0=int(vr[t0]), V=-sub[:, cols].toarray(), cols=vr[cols], flags=TILE_SELF)])
-            return units
-
-        def tiles_b(blocks, transpose):
-            units = []
-            for b in blocks:
-                r0 = int(F.bptr[b])
-                D = F.dinv[b].T if transpose else F.dinv[b]
-                k = D.shape[0]
-                starts = list(range(0, k, 8))
-                if not transpose:
-                    starts.reverse()      # lower triangular: a row group reads the rows above it -> last group first
-                tiles = []
-                for t0 in starts:
-                    t1 = min(k, t0 + 8)
-                    c0, c1 = (t0, k) if transpose else (0, t1)
-                    tiles.append(dict(row0=int(vr[r0 + t0]), V=D[t0:t1, c0:c1], cols=vr[r0 + c0: r0 + c1], flags=0))
-                if k <= CHAIN_ROWS:
-                    units.append(tiles)
-                else:
-                    for t in tiles:
-                        t["flags"] = TILE_STAGED
-                        units.append([t])
-            return units
-
-        levels = []
-        for h in range(Hloc, -1, -1):
-            blocks = lb[F.height[lb] == h]
-            levels.append(tiles_a(blocks, LoffT))
-            levels.append(tiles_b(blocks, True))
-        levels = [u for u in levels if u]
-        n_bwd = len(levels)
-        for h in range(Hloc + 1):
-            blocks = lb[F.height[lb] == h]
-            if h > 0:
-                levels.append(tiles_a(blocks, Loff))
-            levels.append(tiles_b(blocks, False))
-        hrows = top_rows[halo[s]]
-        units = []
-        for t0 in range(0, hrows.size, 8):
-            sub = Loff[hrows[t0:t0 + 8]]
-            cols = np.unique(sub.indices)
-            cols = cols[row_sub[cols] == s]
-            if cols.size == 0:
-                continue
-            units.append([dict(row0=int(loc[s].size + t0), V=-sub[:, cols].toarray(), cols=vr[cols], flags=TILE_SELF)])
-        levels.append(units)
-        levels = levels[:n_bwd] + [u for u in levels[n_bwd:] if u]
+        levels, n_bwd, order, gb = _subdomain_levels(F, loc[s], top_rows[halo[s]], blk_of, stage_cap, groups)
+        vrow[s, loc[s][order]] = np.arange(loc[s].size)
         plan.prog.append(_pack_levels(levels, NG, n_warps))
         plan.n_bwd.append(n_bwd)
+        plan.group_bounds.append(gb)
     plan.n_bwd = np.asarray(plan.n_bwd, dtype=np.int32)
     plan.stage_rows = max(p["stage_rows"] for p in plan.prog)
 
