@@ -139,6 +139,48 @@ __device__ __forceinline__ void fast_sincos(double x, double* sn, double* cs, bo
     }
 }
 
+// Four sines at once, branch-free on the common path: the Horner steps of the four arguments interleave
+// (independent FP64 chains hide the ~9-cycle DFMA latency) and the coefficients come from the constant bank
+// as direct instruction operands instead of 64-bit immediates rebuilt per use.
+static __constant__ double c_sin_poly[10] = {
+    -1.9572941063391261e-20, 8.2206352466243295e-18, -2.8114572543455206e-15, 7.6471637318198164e-13,
+    -1.6059043836821613e-10, 2.5052108385441720e-08, -2.7557319223985893e-06, 1.9841269841269841e-04,
+    -8.3333333333333332e-03, 1.6666666666666666e-01};
+static __constant__ double c_sin_red[3] = {0.31830988618379067154, 3.141592653589793116, 1.2246467991473532072e-16};
+
+__device__ __forceinline__ void fast_sin4(const double x[4], double out[4]) {
+    const bool ok = (fabs(x[0]) < 1.0e8) & (fabs(x[1]) < 1.0e8) & (fabs(x[2]) < 1.0e8) & (fabs(x[3]) < 1.0e8);
+    if (!ok) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) out[i] = sin(x[i]);
+        return;
+    }
+    double k[4], r[4], r2[4], p[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        k[i] = rint(x[i] * c_sin_red[0]);
+        r[i] = fma(-k[i], c_sin_red[1], x[i]);
+        r[i] = fma(-k[i], c_sin_red[2], r[i]);
+        r2[i] = r[i] * r[i];
+        p[i] = c_sin_poly[0];
+    }
+#pragma unroll
+    for (int m = 1; m < 10; ++m) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) p[i] = fma(p[i], r2[i], c_sin_poly[m]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double sv = fma(-r[i] * r2[i], p[i], r[i]);
+        // sign (-1)^k: flip the sign bit when k is odd (k is integral and |k| < 2^31 here)
+        const int ki = __double2int_rn(k[i]);
+        out[i] = __hiloint2double(__double2hiint(sv) ^ (ki << 31), __double2loint(sv));
+    }
+}
+
+template <bool DEFAULT>
+__device__ __forceinline__ void cpr_eval4(const Cpr& c, const double th[4], double out[4]);
+
 template <bool DEFAULT>
 __device__ __forceinline__ double cpr_eval(const Cpr& c, double th) {
     double s, co;
@@ -153,6 +195,13 @@ __device__ __forceinline__ double cpr_eval(const Cpr& c, double th) {
         acc += c.a[m] * cm + c.b[m] * sm;
     }
     return acc;
+}
+
+template <bool DEFAULT>
+__device__ __forceinline__ void cpr_eval4(const Cpr& c, const double th[4], double out[4]) {
+    if (DEFAULT) { fast_sin4(th, out); return; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out[i] = cpr_eval<false>(c, th[i]);
 }
 
 }  // namespace jj

@@ -55,6 +55,7 @@ struct SubArgs {
     // circuit
     int Nj, Nf;
     const double *P0, *P1;          // [Nj'][4] = Ic, 1/c0, c1, c2 | Is base, noise base, Vs base, 0 (device junction order)
+    const double* jrec;             // [Nj'][8] junction records, see junction_item
     Cpr cpr;
     // problem
     int Wp, n_chunks;
@@ -84,7 +85,7 @@ struct SubState {
     double* SinvP = nullptr;
     int *junc_ptr = nullptr, *junc_orig = nullptr; int2* junc_row = nullptr; char2* junc_sign = nullptr;
     int* face_ell_j = nullptr; double* face_ell_c = nullptr; int* face_fidx = nullptr;
-    double *P0 = nullptr, *P1 = nullptr;
+    double *P0 = nullptr, *P1 = nullptr, *jrec = nullptr;
     std::vector<void*> allocs; std::vector<size_t> alloc_bytes;
     // per problem
     double *rth = nullptr, *rx = nullptr, *zloc = nullptr, *ctop = nullptr, *rtop = nullptr, *jtop = nullptr;
@@ -97,16 +98,20 @@ struct SubState {
 };
 
 // ------------------------------------------------------------------------------------------------
-// shared-memory vector: row r holds PC float64; the 8-problem group g of row r sits at group position
-// g ^ (r & (NG-1)), so the four rows gathered by one MMA B fragment fall into different bank groups.
+// shared-memory vector: row r holds PC float64 as PC/4 chunks of 32 bytes; chunk c of row r sits at chunk
+// position c ^ (r & 3) (c ^ (r & 1) when a row has only two chunks). One MMA B fragment gathers, per half
+// warp, the same logical chunk of four rows: consecutive rows land in four different bank octets.
 // ------------------------------------------------------------------------------------------------
 template <int NG>
-__device__ __forceinline__ int vgrp(int row, int g) { return (g ^ (row & (NG - 1))) << 3; }
-template <int NG>
-__device__ __forceinline__ int velem(int row, int q) { return row * (8 * NG) + vgrp<NG>(row, q >> 3) + (q & 7); }
+__device__ __forceinline__ int velem(int row, int q) {
+    constexpr int CM = NG >= 2 ? 3 : 1;
+    return row * (8 * NG) + (((q >> 2) ^ (row & CM)) << 2) + (q & 3);
+}
 
 struct Cursor {
     int t0, t1, s;
+    const unsigned char* pA;      // + lane*8: A fragment of the first step of the current ring block
+    const unsigned char* pC;      // + 256 + lane*2: its element codes
     double ra[RING]; unsigned rc[RING];
 };
 
@@ -122,13 +127,15 @@ __device__ __forceinline__ void cursor_open(Cursor& cu, const ProgSmem& ps, int 
     cu.t0 = ps.wt[idx]; cu.t1 = ps.wt[idx + 1];
     cu.s = ps.ws[idx];
     // ring slot of stream step s is s % RING; the stream buffer is padded by 2*RING steps
-    const int first = cu.s - (cu.s & (RING - 1));
+    const int p = cu.s & (RING - 1);
+    const unsigned char* blk = ps.stream + (size_t)(cu.s - p) * STEP_BYTES;
+    cu.pA = blk + lane * 8;
+    cu.pC = blk + 256 + lane * 2;
 #pragma unroll
     for (int k = 0; k < RING; ++k) {
-        const int sk = first + k + ((first + k < cu.s) ? RING : 0);
-        const unsigned char* rec = ps.stream + (size_t)sk * STEP_BYTES;
-        cu.ra[k] = __ldg(reinterpret_cast<const double*>(rec) + lane);
-        cu.rc[k] = __ldg(reinterpret_cast<const unsigned short*>(rec + 256) + lane);
+        const int off = (k + (k < p ? RING : 0)) * STEP_BYTES;
+        cu.ra[k] = __ldg(reinterpret_cast<const double*>(cu.pA + off));
+        cu.rc[k] = __ldg(reinterpret_cast<const unsigned short*>(cu.pC + off));
     }
 }
 
@@ -139,14 +146,22 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double b;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(b) : "r"(addr));
+    return b;
+}
+
 // One level of a subdomain's sweep program: every warp walks its own stream of 8-row tiles.
 template <int NG>
 __device__ void exec_level(const ProgSmem& ps, Cursor& cu, int level, int next_level, double* __restrict__ v,
                            double* __restrict__ stage) {
     constexpr int PC = 8 * NG;
     const int lane = threadIdx.x & 31;
+    const unsigned vb = (unsigned)__cvta_generic_to_shared(v);      // 256-byte aligned: group g of an element is addr ^ (g << 6)
     int s = cu.s;
-    const unsigned char* base = ps.stream;
+    const unsigned char* pA = cu.pA;
+    const unsigned char* pC = cu.pC;
     double ra[RING]; unsigned rc[RING];
 #pragma unroll
     for (int k = 0; k < RING; ++k) { ra[k] = cu.ra[k]; rc[k] = cu.rc[k]; }
@@ -157,7 +172,7 @@ __device__ void exec_level(const ProgSmem& ps, Cursor& cu, int level, int next_l
         const int g0 = (hd.x >> 21) & 15, ng = ((hd.x >> 25) & 15) + 1;
         const int nsteps = hd.y & 0xffff, stage_off = (hd.y >> 16) & 0x7fff;
         const int row = row0 + r;
-        const int rowoff = row * PC + 2 * kk;
+        const int celem = velem<NG>(row, 2 * kk);          // this lane's two C values of group 0; group g: ^ (g << 3)
         double acc[NG][2];
 #pragma unroll
         for (int g = 0; g < NG; ++g) { acc[g][0] = 0.0; acc[g][1] = 0.0; }
@@ -165,40 +180,43 @@ __device__ void exec_level(const ProgSmem& ps, Cursor& cu, int level, int next_l
 #pragma unroll
             for (int g = 0; g < NG; ++g)
                 if (g < ng) {
-                    const double2 sv = *reinterpret_cast<const double2*>(v + rowoff + vgrp<NG>(row, g0 + g));
+                    const double2 sv = *reinterpret_cast<const double2*>(v + (celem ^ ((g0 + g) << 3)));
                     acc[g][0] = sv.x; acc[g][1] = sv.y;
                 }
         }
         const unsigned gx = (unsigned)g0 << 3;
         // ring slot K always holds a stream step congruent to K (mod RING); it is refilled in place right after use
+        // with immediate offsets from the block pointers
 #define JJ_STEP(K)                                                                                     \
     if ((K) >= p_ && j < nsteps) {                                                                     \
-        const unsigned code = rc[K] ^ gx;                                                              \
+        const unsigned a0 = vb + ((rc[K] ^ gx) << 3);                                                  \
         _Pragma("unroll") for (int g = 0; g < NG; ++g)                                                 \
-            if (g < ng) dmma884(acc[g][0], acc[g][1], ra[K], v[code ^ (unsigned)(g << 3)]);            \
-        const unsigned char* rec = base + (size_t)(s + RING) * STEP_BYTES;                             \
-        asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(ra[K]) : "l"(reinterpret_cast<const double*>(rec) + lane)); \
-        asm volatile("ld.global.nc.u16 %0, [%1];" : "=r"(rc[K]) : "l"(reinterpret_cast<const unsigned short*>(rec + 256) + lane)); \
-        ++s; ++j;                                                                                      \
+            if (g < ng) dmma884(acc[g][0], acc[g][1], ra[K], lds_f64(a0 ^ (unsigned)(g << 6)));        \
+        asm volatile("ld.global.nc.f64 %0, [%1+%2];" : "=d"(ra[K]) : "l"(pA), "n"((RING + (K)) * STEP_BYTES)); \
+        asm volatile("ld.global.nc.u16 %0, [%1+%2];" : "=r"(rc[K]) : "l"(pC), "n"((RING + (K)) * STEP_BYTES)); \
+        ++j;                                                                                           \
     }
         for (int j = 0; j < nsteps;) {
             const int p_ = s & (RING - 1);
+            const int j0 = j;
             JJ_STEP(0) JJ_STEP(1) JJ_STEP(2) JJ_STEP(3) JJ_STEP(4) JJ_STEP(5) JJ_STEP(6) JJ_STEP(7)
+            s += j - j0;
+            if ((s & (RING - 1)) == 0) { pA += RING * STEP_BYTES; pC += RING * STEP_BYTES; }
         }
 #undef JJ_STEP
         __syncwarp();            // every lane has read its operands before rows of this block are overwritten
         if (r < nrows) {
             if (flags & 2) {
                 // staged: the row keeps the physical layout of its destination and carries the destination index
-                double* srow = stage + (size_t)(stage_off + r) * (PC + 2);
+                double* srow = stage + (size_t)(stage_off + r) * (PC + 2) - (size_t)row * PC;
 #pragma unroll
                 for (int g = 0; g < NG; ++g)
-                    if (g < ng) *reinterpret_cast<double2*>(srow + vgrp<NG>(row, g0 + g) + 2 * kk) = make_double2(acc[g][0], acc[g][1]);
-                if (kk == 0) reinterpret_cast<int*>(srow + PC)[0] = row;
+                    if (g < ng) *reinterpret_cast<double2*>(srow + (celem ^ ((g0 + g) << 3))) = make_double2(acc[g][0], acc[g][1]);
+                if (kk == 0) reinterpret_cast<int*>(stage + (size_t)(stage_off + r) * (PC + 2) + PC)[0] = row;
             } else {
 #pragma unroll
                 for (int g = 0; g < NG; ++g)
-                    if (g < ng) *reinterpret_cast<double2*>(v + rowoff + vgrp<NG>(row, g0 + g)) = make_double2(acc[g][0], acc[g][1]);
+                    if (g < ng) *reinterpret_cast<double2*>(v + (celem ^ ((g0 + g) << 3))) = make_double2(acc[g][0], acc[g][1]);
             }
         }
         __syncwarp();
@@ -245,30 +263,8 @@ __device__ __forceinline__ void amp_fill(const SubArgs& a, AmpCache<PC>* ac, int
     }
 }
 
-// State and constants of one junction item (one junction x 4 problems), loaded one iteration ahead.
-struct JIn {
-    double2 x0, x1, t0, t1, pIc, pc, pb;
-    int2 rows;
-    int sg, jo;
-};
-
-template <int PC>
-__device__ __forceinline__ void jin_load(const SubArgs& a, int jlo, int c, int idx, JIn& in) {
-    constexpr int G = PC / 4;
-    const int jp = jlo + idx / G;
-    const size_t sidx = ((size_t)c * a.Nj + jlo) * PC + (size_t)idx * 4;
-    const double2* xp = reinterpret_cast<const double2*>(a.rx + sidx);
-    const double2* tp = reinterpret_cast<const double2*>(a.rth + sidx);
-    in.x0 = xp[0]; in.x1 = xp[1]; in.t0 = tp[0]; in.t1 = tp[1];
-    in.pIc = __ldg(reinterpret_cast<const double2*>(a.P0) + 2 * jp);
-    in.pc = __ldg(reinterpret_cast<const double2*>(a.P0) + 2 * jp + 1);
-    in.pb = __ldg(reinterpret_cast<const double2*>(a.P1) + 2 * jp);
-    in.rows = __ldg(a.junc_row + jp);
-    const char2 sg = a.junc_sign[jp];
-    in.sg = (int)sg.x * 4 + (int)sg.y;       // signs are -1, 0, +1
-    in.jo = __ldg(a.junc_orig + jp);
-}
-
+// x' = (noise - Is) + Ic cpr(2 theta_n - theta_{n-1}) + c1 theta_n + c2 theta_{n-1} for four problems
+// (reference: time_evolution.py:533-558)
 template <bool DEF>
 __device__ __forceinline__ void next_x(const SubArgs& a, double Ic, double c1, double c2, double isb, double nb,
                                        const double* ampT, const double* ampIs, int jo, int w, long long n,
@@ -286,43 +282,48 @@ __device__ __forceinline__ void next_x(const SubArgs& a, double Ic, double c1, d
 #pragma unroll
         for (int k = 0; k < 4; ++k) fl[k] = (nb * ampT[k]) * z[k];
     }
+    double arg[4], g[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) arg[k] = 2.0 * th1[k] - th2[k];
+    cpr_eval4<DEF>(a.cpr, arg, g);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const double X = Ic * cpr_eval<DEF>(a.cpr, 2.0 * th1[k] - th2[k]) + c1 * th1[k] + c2 * th2[k];
+        const double X = Ic * g[k] + c1 * th1[k] + c2 * th2[k];
         xn[k] = (fl[k] - isb * ampIs[k]) + X;
     }
 }
 
-// theta_n = (A^T J - x)/c0, snapshots, x' for the next step  (reference: time_evolution.py:533-558, 570-580)
+// theta_n = (A^T J - x)/c0, snapshots, x' for the next step  (reference: time_evolution.py:533-558, 570-580).
+// One thread = one junction x four problems. The 64-byte junction record holds Ic, 1/c0, c1, c2, the Is and
+// noise bases, the two shared-memory rows of its faces (row 0 with sign 0 when absent) and the original index.
 template <int NG, bool DEF>
 __device__ __forceinline__ void junction_item(const SubArgs& a, const AmpCache<8 * NG>* ac, int c, long long n, int idx,
-                                              int jlo, bool do_pre, const JIn& in, const double* __restrict__ v,
+                                              int jlo, bool do_pre, const double* __restrict__ v,
                                               double* snap_th, double* snap_I) {
     constexpr int PC = 8 * NG, G = PC / 4;
     const int q = (idx % G) * 4;
     const int w = c * PC + q;
     if (w >= a.Wp) return;
+    const int jp = jlo + idx / G;
     const size_t sidx = ((size_t)c * a.Nj + jlo) * PC + (size_t)idx * 4;
-    double y[4] = {0, 0, 0, 0};
-    if (in.rows.x >= 0) {
-        const double2* jp = reinterpret_cast<const double2*>(v + velem<NG>(in.rows.x, q));
-        const double2 j0 = jp[0], j1 = jp[1];
-        const double s = (double)((in.sg + 5) / 4 - 1);
-        y[0] = s * j0.x; y[1] = s * j0.y; y[2] = s * j1.x; y[3] = s * j1.y;
-    }
-    if (in.rows.y >= 0) {
-        const double2* jp = reinterpret_cast<const double2*>(v + velem<NG>(in.rows.y, q));
-        const double2 j0 = jp[0], j1 = jp[1];
-        const double s = (double)((in.sg + 5) % 4 - 1);
-        y[0] = fma(s, j0.x, y[0]); y[1] = fma(s, j0.y, y[1]); y[2] = fma(s, j1.x, y[2]); y[3] = fma(s, j1.y, y[3]);
-    }
-    const double ic0 = in.pIc.y;
-    const double th1[4] = {(y[0] - in.x0.x) * ic0, (y[1] - in.x0.y) * ic0, (y[2] - in.x1.x) * ic0, (y[3] - in.x1.y) * ic0};
-    const double th2[4] = {in.t0.x, in.t0.y, in.t1.x, in.t1.y};
+    const double2* xp = reinterpret_cast<const double2*>(a.rx + sidx);
+    const double2* tp = reinterpret_cast<const double2*>(a.rth + sidx);
+    const double2 x0 = xp[0], x1 = xp[1], t0 = tp[0], t1 = tp[1];
+    const double2* rec = reinterpret_cast<const double2*>(a.jrec + 8 * (size_t)jp);
+    const double2 rIc = __ldg(rec), rc = __ldg(rec + 1), rb = __ldg(rec + 2);
+    const int4 ri = __ldg(reinterpret_cast<const int4*>(rec + 3));      // row0, row1, original junction, signs
+    const double s0 = (double)((ri.w & 3) - 1), s1 = (double)(((ri.w >> 2) & 3) - 1);
+    const double2* ja = reinterpret_cast<const double2*>(v + velem<NG>(ri.x, q));
+    const double2* jb = reinterpret_cast<const double2*>(v + velem<NG>(ri.y, q));
+    const double2 a0 = ja[0], a1 = ja[1], b0 = jb[0], b1 = jb[1];
+    const double y[4] = {fma(s1, b0.x, s0 * a0.x), fma(s1, b0.y, s0 * a0.y), fma(s1, b1.x, s0 * a1.x), fma(s1, b1.y, s0 * a1.y)};
+    const double ic0 = rIc.y;
+    const double th1[4] = {(y[0] - x0.x) * ic0, (y[1] - x0.y) * ic0, (y[2] - x1.x) * ic0, (y[3] - x1.y) * ic0};
+    const double th2[4] = {t0.x, t0.y, t1.x, t1.y};
     // one finiteness test for the four phases (a NaN or Inf in any of them poisons the sum)
     if (!(fabs((th1[0] + th1[1]) + (th1[2] + th1[3])) < 1.0e300)) atomicOr(a.flag, 1);
     if (snap_th || snap_I || !do_pre) {
-        const size_t cidx = (size_t)in.jo * a.Wp + w;
+        const size_t cidx = (size_t)ri.z * a.Wp + w;
         if (snap_th) {
             double2* sp = reinterpret_cast<double2*>(snap_th + cidx);
             sp[0] = make_double2(th1[0], th1[1]); sp[1] = make_double2(th1[2], th1[3]);
@@ -330,22 +331,22 @@ __device__ __forceinline__ void junction_item(const SubArgs& a, const AmpCache<8
         if (snap_I) {
             const double* am = ac->Is[(n - 1) & 1] + q;
             double2* sp = reinterpret_cast<double2*>(snap_I + cidx);
-            sp[0] = make_double2(y[0] + in.pb.x * am[0], y[1] + in.pb.x * am[1]);
-            sp[1] = make_double2(y[2] + in.pb.x * am[2], y[3] + in.pb.x * am[3]);
+            sp[0] = make_double2(y[0] + rb.x * am[0], y[1] + rb.x * am[1]);
+            sp[1] = make_double2(y[2] + rb.x * am[2], y[3] + rb.x * am[3]);
         }
         if (!do_pre) {
             // end of the run: hand theta_last and theta_{last-1} back in the canonical layout
             double2* o1 = reinterpret_cast<double2*>(a.th1 + cidx);
             double2* o2 = reinterpret_cast<double2*>(a.th2 + cidx);
             o1[0] = make_double2(th1[0], th1[1]); o1[1] = make_double2(th1[2], th1[3]);
-            o2[0] = in.t0; o2[1] = in.t1;
+            o2[0] = t0; o2[1] = t1;
             return;
         }
     }
     double2* op = reinterpret_cast<double2*>(a.rth + sidx);
     op[0] = make_double2(th1[0], th1[1]); op[1] = make_double2(th1[2], th1[3]);
     double xn[4];
-    next_x<DEF>(a, in.pIc.x, in.pc.x, in.pc.y, in.pb.x, in.pb.y, ac->T[n & 1] + q, ac->Is[n & 1] + q, in.jo, w, n, th1, th2, xn);
+    next_x<DEF>(a, rIc.x, rc.x, rc.y, rb.x, rb.y, ac->T[n & 1] + q, ac->Is[n & 1] + q, ri.z, w, n, th1, th2, xn);
     double2* xo = reinterpret_cast<double2*>(a.rx + sidx);
     xo[0] = make_double2(xn[0], xn[1]); xo[1] = make_double2(xn[2], xn[3]);
 }
@@ -361,7 +362,9 @@ __device__ void junction_pass(const SubArgs& a, const AmpCache<8 * NG>* ac, int 
         for (int idx = threadIdx.x; idx < total; idx += NT) {
             const int jp = jlo + idx / G, q = (idx % G) * 4, w = c * PC + q;
             if (w >= a.Wp) continue;
-            const int jo = __ldg(a.junc_orig + jp);
+            const double2* rec = reinterpret_cast<const double2*>(a.jrec + 8 * (size_t)jp);
+            const double2 rIc = __ldg(rec), rc = __ldg(rec + 1), rb = __ldg(rec + 2);
+            const int jo = __ldg(reinterpret_cast<const int4*>(rec + 3)).z;
             const size_t sidx = ((size_t)c * a.Nj + jlo) * PC + (size_t)idx * 4;
             const size_t cidx = (size_t)jo * a.Wp + w;
             const double2* p1 = reinterpret_cast<const double2*>(a.th1 + cidx);
@@ -370,11 +373,8 @@ __device__ void junction_pass(const SubArgs& a, const AmpCache<8 * NG>* ac, int 
             double2* op = reinterpret_cast<double2*>(a.rth + sidx);
             op[0] = u0; op[1] = u1;
             const double th1[4] = {u0.x, u0.y, u1.x, u1.y}, th2[4] = {v0.x, v0.y, v1.x, v1.y};
-            const double2 pIc = __ldg(reinterpret_cast<const double2*>(a.P0) + 2 * jp);
-            const double2 pc = __ldg(reinterpret_cast<const double2*>(a.P0) + 2 * jp + 1);
-            const double2 pb = __ldg(reinterpret_cast<const double2*>(a.P1) + 2 * jp);
             double xn[4];
-            next_x<DEF>(a, pIc.x, pc.x, pc.y, pb.x, pb.y, ac->T[n & 1] + q, ac->Is[n & 1] + q, jo, w, n, th1, th2, xn);
+            next_x<DEF>(a, rIc.x, rc.x, rc.y, rb.x, rb.y, ac->T[n & 1] + q, ac->Is[n & 1] + q, jo, w, n, th1, th2, xn);
             double2* xo = reinterpret_cast<double2*>(a.rx + sidx);
             xo[0] = make_double2(xn[0], xn[1]); xo[1] = make_double2(xn[2], xn[3]);
         }
@@ -387,20 +387,13 @@ __device__ void junction_pass(const SubArgs& a, const AmpCache<8 * NG>* ac, int 
         if (pt >= 0) snap_th = a.snap_th + (size_t)pt * a.Nj * a.Wp;
         if (pi >= 0) snap_I = a.snap_I + (size_t)pi * a.Nj * a.Wp;
     }
-    // software pipeline: the loads of the next item are in flight while the current one is computed
-    JIn cur, nxt;
-    int idx = threadIdx.x;
-    if (idx < total) jin_load<PC>(a, jlo, c, idx, cur);
-    for (; idx < total; idx += NT) {
-        const bool more = idx + NT < total;
-        if (more) jin_load<PC>(a, jlo, c, idx + NT, nxt);
-        if (idx + 3 * NT < total) {      // and the state three iterations ahead is pulled into L2
-            const size_t pf = ((size_t)c * a.Nj + jlo) * PC + (size_t)(idx + 3 * NT) * 4;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.rx + pf));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.rth + pf));
+    const size_t sbase = ((size_t)c * a.Nj + jlo) * PC;
+    for (int idx = threadIdx.x; idx < total; idx += NT) {
+        if (idx + 2 * NT < total) {      // the state two iterations ahead is pulled into L2
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.rx + sbase + (size_t)(idx + 2 * NT) * 4));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.rth + sbase + (size_t)(idx + 2 * NT) * 4));
         }
-        junction_item<NG, DEF>(a, ac, c, n, idx, jlo, do_pre, cur, v, snap_th, snap_I);
-        if (more) cur = nxt;
+        junction_item<NG, DEF>(a, ac, c, n, idx, jlo, do_pre, v, snap_th, snap_I);
     }
 }
 
@@ -592,7 +585,7 @@ __device__ __forceinline__ void rows_to_global(const double* v, int row0, int nr
 template <int NG, bool DEF>
 __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
     constexpr int PC = 8 * NG;
-    extern __shared__ __align__(16) double smem[];
+    extern __shared__ __align__(1024) double smem[];
     double* v = smem;
     double* stage = v + (size_t)a.n_rows * PC;
     AmpCache<PC>* ac = reinterpret_cast<AmpCache<PC>*>(stage + (size_t)a.stage_rows * (PC + 2));
@@ -727,16 +720,24 @@ KernelPtr pick_kernel(int NG, bool def) {
     }
 }
 
-// per-junction constants in device junction order (one coalesced 32-byte record instead of gathers by original index)
+// per-junction constants in device junction order (coalesced records instead of gathers by original index)
 __global__ void k_sub_gather_params(int n, const int* orig, const double* Ic, const double* c0, const double* c1,
                                     const double* c2, const double* isb, const double* tb, const double* vsb,
-                                    double* P0, double* P1) {
+                                    const int2* rows, const char2* sign, double* P0, double* P1, double* jrec) {
     int jp = blockIdx.x * blockDim.x + threadIdx.x;
     if (jp >= n) return;
     int jo = orig[jp];
     P0[4 * jp + 0] = Ic[jo]; P0[4 * jp + 1] = 1.0 / c0[jo]; P0[4 * jp + 2] = c1[jo]; P0[4 * jp + 3] = c2[jo];
     P1[4 * jp + 0] = isb ? isb[jo] : 0.0; P1[4 * jp + 1] = tb ? tb[jo] : 0.0; P1[4 * jp + 2] = vsb ? vsb[jo] : 0.0;
     P1[4 * jp + 3] = 0.0;
+    double* r = jrec + 8 * (size_t)jp;
+    r[0] = Ic[jo]; r[1] = 1.0 / c0[jo]; r[2] = c1[jo]; r[3] = c2[jo];
+    r[4] = isb ? isb[jo] : 0.0; r[5] = tb ? tb[jo] : 0.0;
+    const int2 rw = rows[jp];
+    const char2 sg = sign[jp];
+    const int s0 = rw.x >= 0 ? (int)sg.x : 0, s1 = rw.y >= 0 ? (int)sg.y : 0;
+    int4 ri = make_int4(rw.x >= 0 ? rw.x : 0, rw.y >= 0 ? rw.y : 0, jo, (s0 + 1) | ((s1 + 1) << 2));
+    *reinterpret_cast<int4*>(r + 6) = ri;
 }
 
 #define SCK(call)                                                                                   \
@@ -845,10 +846,11 @@ int subdomain_set_plan(JJHandle* h, const JJSubdomainPlan* pl) {
     if ((rc = up(h, st, &st->face_ell_j, pl->face_ell_j, nell))) return rc;
     if ((rc = up(h, st, &st->face_ell_c, pl->face_ell_c, nell))) return rc;
     if ((rc = up(h, st, &st->face_fidx, pl->face_fidx, (size_t)P * pl->n_rows))) return rc;
-    for (double** pp : {&st->P0, &st->P1}) {
+    for (double** pp : {&st->P0, &st->P1, &st->jrec}) {
         void* p = nullptr;
-        if ((rc = dev_alloc(h, &p, (size_t)Nj * 4 * sizeof(double)))) return rc;
-        st->allocs.push_back(p); st->alloc_bytes.push_back((size_t)Nj * 4 * sizeof(double));
+        const size_t bytes = (size_t)Nj * (pp == &st->jrec ? 8 : 4) * sizeof(double);
+        if ((rc = dev_alloc(h, &p, bytes))) return rc;
+        st->allocs.push_back(p); st->alloc_bytes.push_back(bytes);
         *pp = (double*)p;
     }
     SCK(cudaStreamSynchronize(h->stream));
@@ -875,7 +877,7 @@ static void fill_args(JJHandle* h, SubState* st, SubArgs& a) {
     a.tptr = st->tptr; a.tslot = st->tslot; a.top_face = st->top_face; a.SinvP = st->SinvP;
     a.junc_ptr = st->junc_ptr; a.junc_orig = st->junc_orig; a.junc_row = st->junc_row; a.junc_sign = st->junc_sign;
     a.face_K = st->face_K; a.face_ell_j = st->face_ell_j; a.face_ell_c = st->face_ell_c; a.face_fidx = st->face_fidx;
-    a.Nj = h->cir.Nj; a.Nf = h->cir.Nf; a.P0 = st->P0; a.P1 = st->P1; a.cpr = h->cir.cpr;
+    a.Nj = h->cir.Nj; a.Nf = h->cir.Nf; a.P0 = st->P0; a.P1 = st->P1; a.jrec = st->jrec; a.cpr = h->cir.cpr;
     a.Wp = h->Wp; a.n_chunks = st->n_chunks; a.dt = h->dt; a.seed = h->seed; a.group_offset = h->problem_offset / 4;
     a.Is = h->src[JJ_SRC_IS].dev; a.Vs = h->src[JJ_SRC_VS].dev; a.T = h->src[JJ_SRC_T].dev; a.F = h->src[JJ_SRC_F].dev;
     a.noise = h->noise_buf; a.noise_i0 = h->noise_i0; a.noise_K = h->noise_K;
@@ -891,7 +893,7 @@ static int launch(JJHandle* h, SubState* st, SubArgs& a) {
         k_sub_gather_params<<<(h->cir.Nj + 255) / 256, 256, 0, h->stream>>>(
             h->cir.Nj, st->junc_orig, h->cir.Ic, h->cir.c0, h->cir.c1, h->cir.c2,
             is.kind == KIND_RANK1 ? is.base : nullptr, t.kind == KIND_RANK1 ? t.base : nullptr,
-            vs.kind == KIND_RANK1 ? vs.base : nullptr, st->P0, st->P1);
+            vs.kind == KIND_RANK1 ? vs.base : nullptr, st->junc_row, st->junc_sign, st->P0, st->P1, st->jrec);
         h->launches++;
     }
     SCK(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem_bytes));

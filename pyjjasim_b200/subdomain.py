@@ -23,8 +23,8 @@ Data exchanged through global memory (L2 resident): per (chunk, subdomain) the c
 subdomain to the top right-hand side (`halo` rows = top rows coupled to the subdomain), and J_top.
 
 A subdomain's shared-memory vector has rows [0, n_loc) = its local faces (ascending permuted index) and
-rows [n_loc, n_loc + n_halo) = its halo rows (ascending top index); a row holds PC float64, the 8-problem
-groups of row r are stored at group position g ^ (r & (NG-1)) (bank-conflict-free tensor-core gathers).
+rows [n_loc, n_loc + n_halo) = its halo rows (ascending top index); a row holds PC float64 as 32-byte chunks
+of 4 problems, chunk c of row r is stored at chunk position c ^ (r & 3) (bank-conflict-free tensor-core gathers).
 """
 import numpy as np
 import scipy.linalg
@@ -37,11 +37,13 @@ __all__ = ["SubdomainPlan", "subdomain_plan", "apply_subdomain_plan_host", "elem
 
 
 def elem_code(row, NG):
-    """Element offset (float64 units) of problem n = 0..7 of group 0 of shared-memory row `row`;
+    """Element offset (float64 units) of problem n = 0..7 of group 0 of shared-memory row `row`: a row is PC/4
+    chunks of 4 float64 and chunk c sits at position c ^ (row & 3) (c ^ (row & 1) when PC = 8);
     group g lives at ``code ^ (g << 3)``."""
     row = np.asarray(row, dtype=np.int64)[..., None]
     n = np.arange(8)
-    return row * (8 * NG) + ((row & (NG - 1)) << 3) + n
+    cm = 3 if NG >= 2 else 1
+    return row * (8 * NG) + (((n >> 2) ^ (row & cm)) << 2) + (n & 3)
 
 
 class SubdomainPlan:
