@@ -152,25 +152,59 @@ __device__ __forceinline__ double lds_f64(unsigned addr) {
     return b;
 }
 
-// One level of a subdomain's sweep program: every warp walks its own stream of 8-row tiles.
+// The stream steps of one tile for NGT of the NG problem groups. Ring slot K always holds a stream step
+// congruent to K (mod RING); it is refilled in place right after use, with immediate offsets from the block
+// pointers. All B fragments of a step are fetched before its MMAs issue.
+template <int NG, int NGT>
+__device__ __forceinline__ void tile_steps(int nsteps, int& s, const unsigned char*& pA, const unsigned char*& pC,
+                                           double (&ra)[RING], unsigned (&rc)[RING], unsigned vb, unsigned gx,
+                                           double (&acc)[NG][2]) {
+#define JJ_SLOT(K)                                                                                     \
+    case K: {                                                                                          \
+        if (j >= nsteps) break;                                                                        \
+        const unsigned a0 = vb + ((rc[K] ^ gx) << 3);                                                  \
+        double b_[NGT];                                                                                \
+        _Pragma("unroll") for (int g = 0; g < NGT; ++g) b_[g] = lds_f64(a0 ^ (unsigned)(g << 6));      \
+        _Pragma("unroll") for (int g = 0; g < NGT; ++g) dmma884(acc[g][0], acc[g][1], ra[K], b_[g]);   \
+        asm volatile("ld.global.nc.f64 %0, [%1+%2];" : "=d"(ra[K]) : "l"(pA), "n"((RING + (K)) * STEP_BYTES)); \
+        asm volatile("ld.global.nc.u16 %0, [%1+%2];" : "=r"(rc[K]) : "l"(pC), "n"((RING + (K)) * STEP_BYTES)); \
+        ++j;                                                                                           \
+    }
+    for (int j = 0; j < nsteps;) {
+        const int j0 = j;
+        switch (s & (RING - 1)) {
+            JJ_SLOT(0) JJ_SLOT(1) JJ_SLOT(2) JJ_SLOT(3) JJ_SLOT(4) JJ_SLOT(5) JJ_SLOT(6) JJ_SLOT(7)
+        }
+        s += j - j0;
+        if ((s & (RING - 1)) == 0) { pA += RING * STEP_BYTES; pC += RING * STEP_BYTES; }
+    }
+#undef JJ_SLOT
+}
+
+__device__ __forceinline__ int bcast0(int x) { return __shfl_sync(0xffffffffu, x, 0); }
+
+// One level of a subdomain's sweep program: every warp walks its own stream of 8-row tiles. Everything that
+// steers control flow is broadcast from lane 0, so the compiler knows the warp is converged at every MMA.
 template <int NG>
 __device__ void exec_level(const ProgSmem& ps, Cursor& cu, int level, int next_level, double* __restrict__ v,
                            double* __restrict__ stage) {
     constexpr int PC = 8 * NG;
     const int lane = threadIdx.x & 31;
-    const unsigned vb = (unsigned)__cvta_generic_to_shared(v);      // 256-byte aligned: group g of an element is addr ^ (g << 6)
-    int s = cu.s;
+    const unsigned vb = (unsigned)__cvta_generic_to_shared(v);      // 1 KB aligned: group g of an element is addr ^ (g << 6)
+    int s = bcast0(cu.s);
+    const int t0 = bcast0(cu.t0), t1 = bcast0(cu.t1);
     const unsigned char* pA = cu.pA;
     const unsigned char* pC = cu.pC;
     double ra[RING]; unsigned rc[RING];
 #pragma unroll
     for (int k = 0; k < RING; ++k) { ra[k] = cu.ra[k]; rc[k] = cu.rc[k]; }
     const int r = lane >> 2, kk = lane & 3;
-    for (int t = cu.t0; t < cu.t1; ++t) {
-        const int2 hd = ps.thdr[t];
-        const int row0 = hd.x & 0xffff, nrows = ((hd.x >> 16) & 7) + 1, flags = (hd.x >> 19) & 3;
-        const int g0 = (hd.x >> 21) & 15, ng = ((hd.x >> 25) & 15) + 1;
-        const int nsteps = hd.y & 0xffff, stage_off = (hd.y >> 16) & 0x7fff;
+    for (int t = t0; t < t1; ++t) {
+        const int2 hd0 = ps.thdr[t];
+        const int hx = bcast0(hd0.x), hy = bcast0(hd0.y);
+        const int row0 = hx & 0xffff, nrows = ((hx >> 16) & 7) + 1, flags = (hx >> 19) & 3;
+        const int g0 = (hx >> 21) & 15, ng = ((hx >> 25) & 15) + 1;
+        const int nsteps = hy & 0xffff, stage_off = (hy >> 16) & 0x7fff;
         const int row = row0 + r;
         const int celem = velem<NG>(row, 2 * kk);          // this lane's two C values of group 0; group g: ^ (g << 3)
         double acc[NG][2];
@@ -185,25 +219,10 @@ __device__ void exec_level(const ProgSmem& ps, Cursor& cu, int level, int next_l
                 }
         }
         const unsigned gx = (unsigned)g0 << 3;
-        // ring slot K always holds a stream step congruent to K (mod RING); it is refilled in place right after use
-        // with immediate offsets from the block pointers
-#define JJ_STEP(K)                                                                                     \
-    if ((K) >= p_ && j < nsteps) {                                                                     \
-        const unsigned a0 = vb + ((rc[K] ^ gx) << 3);                                                  \
-        _Pragma("unroll") for (int g = 0; g < NG; ++g)                                                 \
-            if (g < ng) dmma884(acc[g][0], acc[g][1], ra[K], lds_f64(a0 ^ (unsigned)(g << 6)));        \
-        asm volatile("ld.global.nc.f64 %0, [%1+%2];" : "=d"(ra[K]) : "l"(pA), "n"((RING + (K)) * STEP_BYTES)); \
-        asm volatile("ld.global.nc.u16 %0, [%1+%2];" : "=r"(rc[K]) : "l"(pC), "n"((RING + (K)) * STEP_BYTES)); \
-        ++j;                                                                                           \
-    }
-        for (int j = 0; j < nsteps;) {
-            const int p_ = s & (RING - 1);
-            const int j0 = j;
-            JJ_STEP(0) JJ_STEP(1) JJ_STEP(2) JJ_STEP(3) JJ_STEP(4) JJ_STEP(5) JJ_STEP(6) JJ_STEP(7)
-            s += j - j0;
-            if ((s & (RING - 1)) == 0) { pA += RING * STEP_BYTES; pC += RING * STEP_BYTES; }
-        }
-#undef JJ_STEP
+        if (ng == NG) tile_steps<NG, NG>(nsteps, s, pA, pC, ra, rc, vb, gx, acc);
+        else if (NG >= 4 && ng == NG / 2) tile_steps<NG, (NG >= 4 ? NG / 2 : 1)>(nsteps, s, pA, pC, ra, rc, vb, gx, acc);
+        else if (NG >= 8 && ng == NG / 4) tile_steps<NG, (NG >= 8 ? NG / 4 : 1)>(nsteps, s, pA, pC, ra, rc, vb, gx, acc);
+        else tile_steps<NG, 1>(nsteps, s, pA, pC, ra, rc, vb, gx, acc);
         __syncwarp();            // every lane has read its operands before rows of this block are overwritten
         if (r < nrows) {
             if (flags & 2) {
