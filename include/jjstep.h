@@ -102,8 +102,9 @@ typedef struct {
  * backward sweep, [n_bwd, n_levels) the forward sweep (pyjjasim_b200/subdomain.py). */
 typedef struct {
     int32_t n_levels, n_bwd, n_warps, n_tiles;
-    const int32_t *wt_ptr;       /* [n_levels*n_warps + 1] */
-    const int32_t *ws_ptr;       /* [n_levels*n_warps + 1] */
+    const int32_t *wt_ptr;       /* [n_levels*n_warps][2] first / past-the-last tile of (level, warp) */
+    const int32_t *ws_ptr;       /* [n_levels*n_warps] first stream step of (level, warp); tiles and steps are laid
+                                    out warp-major inside a sweep, so a warp's stream continues across levels */
     const int32_t *thdr;         /* [n_tiles][2]: row0 | (nrows-1)<<16 | flags<<19 | g0<<21 | (ng-1)<<25 ; nsteps | stage_off<<16 */
     const int32_t *lstaged;      /* [n_levels] staged rows of the level */
     int64_t n_steps;

@@ -36,6 +36,7 @@ constexpr int NWARPS = NT / 32;
 constexpr int RING = 8;
 constexpr int STEP_BYTES = 320;
 constexpr double TWO_PI = 6.283185307179586;
+constexpr int PROF_SLOTS = 8 + 48;     // phase counters + per-level counters of the sweeps (JJ_SUB_PROF)
 
 struct SubProgDev {
     const int* wt_ptr; const int* ws_ptr; const int2* thdr; const int* lstaged;
@@ -124,7 +125,7 @@ struct ProgSmem {
 __device__ __forceinline__ void cursor_open(Cursor& cu, const ProgSmem& ps, int level) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int idx = level * NWARPS + warp;
-    cu.t0 = ps.wt[idx]; cu.t1 = ps.wt[idx + 1];
+    cu.t0 = ps.wt[2 * idx]; cu.t1 = ps.wt[2 * idx + 1];
     cu.s = ps.ws[idx];
     // ring slot of stream step s is s % RING; the stream buffer is padded by 2*RING steps
     const int p = cu.s & (RING - 1);
@@ -154,18 +155,26 @@ __device__ __forceinline__ double lds_f64(unsigned addr) {
 
 // The stream steps of one tile for NGT of the NG problem groups. Ring slot K always holds a stream step
 // congruent to K (mod RING); it is refilled in place right after use, with immediate offsets from the block
-// pointers. All B fragments of a step are fetched before its MMAs issue.
+// pointers. All B fragments of a step are fetched before its MMAs issue. When a tile covers only one or two
+// groups, even and odd steps accumulate separately (two independent MMA chains per group instead of one).
 template <int NG, int NGT>
 __device__ __forceinline__ void tile_steps(int nsteps, int& s, const unsigned char*& pA, const unsigned char*& pC,
                                            double (&ra)[RING], unsigned (&rc)[RING], unsigned vb, unsigned gx,
                                            double (&acc)[NG][2]) {
+    constexpr bool DUAL = NGT <= 2;
+    double alt[NGT][2];
+#pragma unroll
+    for (int g = 0; g < NGT; ++g) { alt[g][0] = 0.0; alt[g][1] = 0.0; }
 #define JJ_SLOT(K)                                                                                     \
     case K: {                                                                                          \
         if (j >= nsteps) break;                                                                        \
         const unsigned a0 = vb + ((rc[K] ^ gx) << 3);                                                  \
         double b_[NGT];                                                                                \
         _Pragma("unroll") for (int g = 0; g < NGT; ++g) b_[g] = lds_f64(a0 ^ (unsigned)(g << 6));      \
-        _Pragma("unroll") for (int g = 0; g < NGT; ++g) dmma884(acc[g][0], acc[g][1], ra[K], b_[g]);   \
+        _Pragma("unroll") for (int g = 0; g < NGT; ++g) {                                              \
+            if (DUAL && ((K) & 1)) dmma884(alt[g][0], alt[g][1], ra[K], b_[g]);                        \
+            else dmma884(acc[g][0], acc[g][1], ra[K], b_[g]);                                          \
+        }                                                                                              \
         asm volatile("ld.global.nc.f64 %0, [%1+%2];" : "=d"(ra[K]) : "l"(pA), "n"((RING + (K)) * STEP_BYTES)); \
         asm volatile("ld.global.nc.u16 %0, [%1+%2];" : "=r"(rc[K]) : "l"(pC), "n"((RING + (K)) * STEP_BYTES)); \
         ++j;                                                                                           \
@@ -179,6 +188,10 @@ __device__ __forceinline__ void tile_steps(int nsteps, int& s, const unsigned ch
         if ((s & (RING - 1)) == 0) { pA += RING * STEP_BYTES; pC += RING * STEP_BYTES; }
     }
 #undef JJ_SLOT
+    if (DUAL) {
+#pragma unroll
+        for (int g = 0; g < NGT; ++g) { acc[g][0] += alt[g][0]; acc[g][1] += alt[g][1]; }
+    }
 }
 
 __device__ __forceinline__ int bcast0(int x) { return __shfl_sync(0xffffffffu, x, 0); }
@@ -199,9 +212,10 @@ __device__ void exec_level(const ProgSmem& ps, Cursor& cu, int level, int next_l
 #pragma unroll
     for (int k = 0; k < RING; ++k) { ra[k] = cu.ra[k]; rc[k] = cu.rc[k]; }
     const int r = lane >> 2, kk = lane & 3;
+    int2 hdn = t0 < t1 ? ps.thdr[t0] : make_int2(0, 0);
     for (int t = t0; t < t1; ++t) {
-        const int2 hd0 = ps.thdr[t];
-        const int hx = bcast0(hd0.x), hy = bcast0(hd0.y);
+        const int hx = bcast0(hdn.x), hy = bcast0(hdn.y);
+        if (t + 1 < t1) hdn = ps.thdr[t + 1];        // header of the next tile: its latency hides behind this tile
         const int row0 = hx & 0xffff, nrows = ((hx >> 16) & 7) + 1, flags = (hx >> 19) & 3;
         const int g0 = (hx >> 21) & 15, ng = ((hx >> 25) & 15) + 1;
         const int nsteps = hy & 0xffff, stage_off = (hy >> 16) & 0x7fff;
@@ -240,7 +254,18 @@ __device__ void exec_level(const ProgSmem& ps, Cursor& cu, int level, int next_l
         }
         __syncwarp();
     }
-    if (next_level >= 0) cursor_open(cu, ps, next_level);
+    if (next_level >= 0) {
+        // the streams are laid out warp-major inside a sweep: normally the next level simply continues this
+        // warp's stream and the ring stays as it is
+        const int idx = next_level * NWARPS + (threadIdx.x >> 5);
+        if (bcast0(ps.ws[idx]) == s) {
+            cu.t0 = ps.wt[2 * idx]; cu.t1 = ps.wt[2 * idx + 1]; cu.s = s; cu.pA = pA; cu.pC = pC;
+#pragma unroll
+            for (int k = 0; k < RING; ++k) { cu.ra[k] = ra[k]; cu.rc[k] = rc[k]; }
+        } else {
+            cursor_open(cu, ps, next_level);
+        }
+    }
     __syncthreads();
     const int staged = ps.lstaged[level];
     if (staged > 0) {
@@ -255,11 +280,15 @@ __device__ void exec_level(const ProgSmem& ps, Cursor& cu, int level, int next_l
 }
 
 template <int NG>
-__device__ void run_levels(const ProgSmem& ps, int l0, int l1, double* v, double* stage) {
+__device__ void run_levels(const ProgSmem& ps, int l0, int l1, double* v, double* stage, long long* prof) {
     if (l0 >= l1) return;
     Cursor cu;
     cursor_open(cu, ps, l0);
-    for (int l = l0; l < l1; ++l) exec_level<NG>(ps, cu, l, l + 1 < l1 ? l + 1 : -1, v, stage);
+    long long tq = prof ? clock64() : 0;
+    for (int l = l0; l < l1; ++l) {
+        exec_level<NG>(ps, cu, l, l + 1 < l1 ? l + 1 : -1, v, stage);
+        if (prof && threadIdx.x == 0 && l < 48) { const long long tn = clock64(); prof[(size_t)blockIdx.x * PROF_SLOTS + 8 + l] += tn - tq; tq = tn; }
+    }
 }
 
 // Per-step amplitudes of the rank-one inputs for the problems of a chunk (both step parities are filled
@@ -536,55 +565,55 @@ __device__ void top_assemble(const SubArgs& a, long long n) {
     }
 }
 
-// J_top = S_top^-1 r_top: item = (32 rows, one chunk); warp = (8-row tile, problem group)
+// J_top = S_top^-1 r_top. Task = (chunk, 8-row tile, problem group), one per warp and round; consecutive tasks
+// differ in the group first, so the warps of a block share A row tiles and B fragments through L1.
 template <int NG>
 __device__ void top_product(const SubArgs& a) {
     constexpr int PC = 8 * NG;
-    const int MT = a.n_top_pad / 32, KS = a.n_top_pad / 4;
+    const int RT = (a.n_top + 7) / 8, KS = a.n_top_pad / 4;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int rt = warp & 3;
-    for (int item = blockIdx.x; item < MT * a.n_chunks; item += gridDim.x) {
-        const int mt = item % MT, c = item / MT;
-        const double* A = a.SinvP + ((size_t)(mt * 4 + rt) * KS) * 32 + lane;
-        for (int g = warp >> 2; g < NG; g += 4) {
-            const double* B = a.rtop + ((size_t)c * a.n_top_pad + (lane & 3)) * PC + 8 * g + (lane >> 2);
-            double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
-            double ac[8], bc[8], an[8], bn[8];
+    const int n_tasks = a.n_chunks * RT * NG;
+    for (int task = blockIdx.x * NWARPS + warp; task < n_tasks; task += gridDim.x * NWARPS) {
+        const int g = task % NG, rt = (task / NG) % RT, c = task / (NG * RT);
+        const double* A = a.SinvP + ((size_t)rt * KS) * 32 + lane;
+        const double* B = a.rtop + ((size_t)c * a.n_top_pad + (lane & 3)) * PC + 8 * g + (lane >> 2);
+        double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
+        double ac[8], bc[8], an[8], bn[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { ac[j] = __ldg(A + (size_t)j * 32); bc[j] = __ldcg(B + (size_t)j * 4 * PC); }
-            for (int ks0 = 0; ks0 < KS; ks0 += 8) {
-                const bool more = ks0 + 8 < KS;
-                if (more) {
+        for (int j = 0; j < 8; ++j) { ac[j] = __ldg(A + (size_t)j * 32); bc[j] = __ldcg(B + (size_t)j * 4 * PC); }
+        for (int ks0 = 0; ks0 < KS; ks0 += 8) {
+            const bool more = ks0 + 8 < KS;
+            if (more) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        an[j] = __ldg(A + (size_t)(ks0 + 8 + j) * 32);
-                        bn[j] = __ldcg(B + (size_t)(ks0 + 8 + j) * 4 * PC);
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 8; j += 2) {
-                    dmma884(c00, c01, ac[j], bc[j]);
-                    dmma884(c10, c11, ac[j + 1], bc[j + 1]);
-                }
-                if (more) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) { ac[j] = an[j]; bc[j] = bn[j]; }
+                for (int j = 0; j < 8; ++j) {
+                    an[j] = __ldg(A + (size_t)(ks0 + 8 + j) * 32);
+                    bn[j] = __ldcg(B + (size_t)(ks0 + 8 + j) * 4 * PC);
                 }
             }
-            const int row = 32 * mt + 8 * rt + (lane >> 2);
-            double2* dst = reinterpret_cast<double2*>(a.jtop + ((size_t)c * a.n_top_pad + row) * PC + 8 * g + 2 * (lane & 3));
-            *dst = make_double2(c00 + c10, c01 + c11);
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+                dmma884(c00, c01, ac[j], bc[j]);
+                dmma884(c10, c11, ac[j + 1], bc[j + 1]);
+            }
+            if (more) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { ac[j] = an[j]; bc[j] = bn[j]; }
+            }
         }
+        const int row = 8 * rt + (lane >> 2);
+        double2* dst = reinterpret_cast<double2*>(a.jtop + ((size_t)c * a.n_top_pad + row) * PC + 8 * g + 2 * (lane & 3));
+        *dst = make_double2(c00 + c10, c01 + c11);
     }
 }
 
 template <int NG>
 __device__ __forceinline__ void load_prog(const SubArgs& a, int s, ProgSmem& ps, int* aux) {
     const SubProgDev p = a.prog[s];
-    int* wt = aux; int* ws = aux + a.max_np; int* ls = ws + a.max_np;
+    int* wt = aux; int* ws = aux + 2 * a.max_np; int* ls = ws + a.max_np;
     int2* th = reinterpret_cast<int2*>(ls + a.max_levels + (a.max_levels & 1));
-    const int np = p.n_levels * NWARPS + 1;
-    for (int e = threadIdx.x; e < np; e += NT) { wt[e] = p.wt_ptr[e]; ws[e] = p.ws_ptr[e]; }
+    const int np = p.n_levels * NWARPS;
+    for (int e = threadIdx.x; e < 2 * np; e += NT) wt[e] = p.wt_ptr[e];
+    for (int e = threadIdx.x; e < np; e += NT) ws[e] = p.ws_ptr[e];
     for (int e = threadIdx.x; e < p.n_levels; e += NT) ls[e] = p.lstaged[e];
     for (int e = threadIdx.x; e < p.n_tiles; e += NT) th[e] = p.thdr[e];
     ps.wt = wt; ps.ws = ws; ps.lstaged = ls; ps.thdr = th; ps.stream = p.stream;
@@ -630,7 +659,7 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
                 v[velem<NG>(row, q)] = val;
             }
             __syncthreads();
-            run_levels<NG>(ps, ps.n_bwd, ps.n_levels, v, stage);
+            run_levels<NG>(ps, ps.n_bwd, ps.n_levels, v, stage, a.prof);
             rows_to_global<NG>(v, nl, nh, a.ctop + ((size_t)c * a.n_slots + a.hptr[s]) * PC);
             rows_to_global<NG>(v, 0, nl, a.zloc + ((size_t)item * a.n_loc_max) * PC);
         }
@@ -654,7 +683,7 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
                 v[velem<NG>(row, q)] = val;
             }
             __syncthreads();
-            run_levels<NG>(ps, 0, ps.n_bwd, v, stage);
+            run_levels<NG>(ps, 0, ps.n_bwd, v, stage, a.prof);
             for (int e = threadIdx.x; e < nl * PC; e += NT) {
                 const int row = e / PC, q = e % PC, w = c * PC + q;
                 if (w < a.Wp) a.dbg_J[(size_t)fidx[row] * a.Wp + w] = v[velem<NG>(row, q)];
@@ -691,19 +720,19 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
                     for (int e = threadIdx.x; e < nl * (PC / 2); e += NT) dst[e] = src[e];
                 }
                 __syncthreads();
-                run_levels<NG>(ps, 0, ps.n_bwd, v, stage);
+                run_levels<NG>(ps, 0, ps.n_bwd, v, stage, a.prof);
             } else {
                 __syncthreads();
             }
-            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * 8 + 0] += tn - tq; tq = tn; }
+            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 0] += tn - tq; tq = tn; }
             junction_pass<NG, DEF>(a, ac, s, c, n, k > 0, k < a.n, v);
             if (k == a.n) { __syncthreads(); continue; }
             __syncthreads();
-            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * 8 + 1] += tn - tq; tq = tn; }
+            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 1] += tn - tq; tq = tn; }
             face_pass<NG>(a, ac, s, c, n, nl + nh, v);
             __syncthreads();
-            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * 8 + 2] += tn - tq; tq = tn; }
-            run_levels<NG>(ps, ps.n_bwd, ps.n_levels, v, stage);
+            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 2] += tn - tq; tq = tn; }
+            run_levels<NG>(ps, ps.n_bwd, ps.n_levels, v, stage, a.prof);
             rows_to_global<NG>(v, nl, nh, a.ctop + ((size_t)c * a.n_slots + a.hptr[s]) * PC);
             if (!keep_z) {
                 const double2* src = reinterpret_cast<const double2*>(v);
@@ -711,19 +740,19 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
                 for (int e = threadIdx.x; e < nl * (PC / 2); e += NT) dst[e] = src[e];
             }
             __syncthreads();     // the vector is reused by the next item / the next step
-            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * 8 + 3] += tn - tq; tq = tn; }
+            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 3] += tn - tq; tq = tn; }
         }
         if (k == a.n) break;
         if (a.n_top > 0) {
             grid_barrier(a.bar, bar_target);
-            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * 8 + 4] += tn - tq; tq = tn; }
+            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 4] += tn - tq; tq = tn; }
             top_assemble<NG>(a, n);
             grid_barrier(a.bar, bar_target);
-            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * 8 + 5] += tn - tq; tq = tn; }
+            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 5] += tn - tq; tq = tn; }
             top_product<NG>(a);
-            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * 8 + 6] += tn - tq; tq = tn; }
+            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 6] += tn - tq; tq = tn; }
             grid_barrier(a.bar, bar_target);
-            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * 8 + 7] += tn - tq; tq = tn; }
+            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 7] += tn - tq; tq = tn; }
         }
     }
 }
@@ -785,7 +814,7 @@ int up(JJHandle* h, SubState* st, T** dst, const T* src, size_t n, size_t pad_by
 size_t smem_for(const SubState* st) {
     const int PC = st->PC;
     size_t amp = (size_t)4 * 2 * PC * sizeof(double);
-    size_t aux = ((size_t)2 * st->max_np + st->max_levels + 2 + 2 * (size_t)st->max_tiles + 8) * sizeof(int);
+    size_t aux = ((size_t)3 * st->max_np + st->max_levels + 2 + 2 * (size_t)st->max_tiles + 8) * sizeof(int);
     return ((size_t)st->n_rows * PC + (size_t)st->stage_rows * (PC + 2)) * sizeof(double) + amp + aux;
 }
 
@@ -834,9 +863,9 @@ int subdomain_set_plan(JJHandle* h, const JJSubdomainPlan* pl) {
     for (int s = 0; s < P; ++s) {
         const JJSubProgram& ps = pl->prog[s];
         if (ps.n_warps != NWARPS) { h->err = "subdomain plan: program packed for a different warp count"; return JJ_EINVAL; }
-        const size_t np = (size_t)ps.n_levels * NWARPS + 1;
+        const size_t np = (size_t)ps.n_levels * NWARPS;
         int *wt, *ws, *th, *ls; unsigned char* sb;
-        if ((rc = up(h, st, &wt, ps.wt_ptr, np))) return rc;
+        if ((rc = up(h, st, &wt, ps.wt_ptr, 2 * np))) return rc;
         if ((rc = up(h, st, &ws, ps.ws_ptr, np))) return rc;
         if ((rc = up(h, st, &th, ps.thdr, (size_t)ps.n_tiles * 2))) return rc;
         if ((rc = up(h, st, &ls, ps.lstaged, (size_t)ps.n_levels))) return rc;
@@ -923,8 +952,8 @@ static int launch(JJHandle* h, SubState* st, SubArgs& a) {
         if (per_sm <= 0) { h->err = "subdomain: kernel does not fit on the device"; return JJ_EINVAL; }
         st->grid = sms * std::min(per_sm, 1);
     }
-    const int MT = st->n_top_pad / 32;
-    int want = std::max(st->P * st->n_chunks, MT * st->n_chunks);
+    const int top_tasks = st->n_chunks * ((st->n_top + 7) / 8) * st->NG;
+    int want = std::max(st->P * st->n_chunks, (top_tasks + NWARPS - 1) / NWARPS);
     const char* env = getenv("JJ_SUB_GRID");
     int grid = std::min(st->grid, std::max(1, want));
     if (env && atoi(env) > 0) grid = std::min(st->grid, atoi(env));
@@ -995,24 +1024,25 @@ int subdomain_run(JJHandle* h, long long i0, int n, const long long* th_plane, c
     // debugging aid: per-phase cycle counts of every block, printed as averages per time step
     const size_t nb = 1024;
     long long* prof = nullptr;
-    SCK(cudaMalloc((void**)&prof, nb * 8 * sizeof(long long)));
-    SCK(cudaMemset(prof, 0, nb * 8 * sizeof(long long)));
+    SCK(cudaMalloc((void**)&prof, nb * PROF_SLOTS * sizeof(long long)));
+    SCK(cudaMemset(prof, 0, nb * PROF_SLOTS * sizeof(long long)));
     a.prof = prof;
     int rc = launch(h, st, a);
     if (rc) { cudaFree(prof); return rc; }
     SCK(cudaStreamSynchronize(h->stream));
-    std::vector<long long> hp(nb * 8);
+    std::vector<long long> hp(nb * PROF_SLOTS);
     SCK(cudaMemcpy(hp.data(), prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     cudaFree(prof);
     static const char* names[8] = {"bwd sweep", "junction pass", "face pass", "fwd sweep + store", "barrier 1 (wait)", "top assemble + barrier 2",
                                    "top product", "barrier 3 (wait)"};
     fprintf(stderr, "JJ_SUB_PROF: cycles per time step (n=%d steps, P=%d, PC=%d, chunks=%d)\n", n, st->P, st->PC, st->n_chunks);
     double tot = 0;
-    for (int sl = 0; sl < 8; ++sl) {
+    for (int sl = 0; sl < PROF_SLOTS; ++sl) {
         double sum = 0, mx = 0; int cnt = 0;
-        for (size_t b = 0; b < nb; ++b) { double v = (double)hp[b * 8 + sl] / n; if (v > 0) { sum += v; ++cnt; } mx = std::max(mx, v); }
-        double avg = cnt ? sum / cnt : 0; tot += avg;
-        fprintf(stderr, "  %-26s avg %9.0f max %9.0f (blocks %d)\n", names[sl], avg, mx, cnt);
+        for (size_t b = 0; b < nb; ++b) { double v = (double)hp[b * PROF_SLOTS + sl] / n; if (v > 0) { sum += v; ++cnt; } mx = std::max(mx, v); }
+        double avg = cnt ? sum / cnt : 0;
+        if (sl < 8) { tot += avg; fprintf(stderr, "  %-26s avg %9.0f max %9.0f (blocks %d)\n", names[sl], avg, mx, cnt); }
+        else if (cnt) fprintf(stderr, "    sweep level %2d           avg %9.0f max %9.0f\n", sl - 8, avg, mx);
     }
     fprintf(stderr, "  total avg cycles per time step %.0f\n", tot);
     return JJ_OK;

@@ -99,7 +99,7 @@ class CircuitTables:
     # ------------------------------------------------------------------ subdomain engine plan
     def subdomain_smem_bytes(self, plan):
         PC = plan.PC
-        aux = 2 * max(ps["n_levels"] * ps["n_warps"] + 1 for ps in plan.prog) + max(ps["n_levels"] for ps in plan.prog) \
+        aux = 3 * max(ps["n_levels"] * ps["n_warps"] + 1 for ps in plan.prog) + max(ps["n_levels"] for ps in plan.prog) \
             + 2 * max(len(ps["thdr"]) for ps in plan.prog) + 10
         return (plan.n_rows * PC + plan.stage_rows * (PC + 2)) * 8 + 64 * PC + 4 * aux
 

@@ -68,16 +68,19 @@ def _tile_record(V, cols, NG):
     return rec
 
 
-def _pack_levels(levels, NG, n_warps):
+def _pack_levels(levels, NG, n_warps, n_bwd=0):
     """levels: list of unit lists; a unit is a list of tiles dict(row0, V, cols, flags) executed in order by
-    one warp. Returns the per-(level, warp) streams. Levels with fewer units than warps are split over
-    problem groups (a warp then handles ng < NG groups of a unit), which keeps all warps busy in the
-    upper, narrow levels of the subtree at the price of re-reading those (small) streams."""
+    one warp. Returns the per-(level, warp) tile ranges and streams. Units longer than a warp's fair share of a
+    level (and units of levels with fewer units than warps) are split over problem groups: a warp then handles
+    ng < NG groups of the unit; the copies re-read the unit's (small) stream but run concurrently.
+    Tiles and stream steps are emitted warp-major inside each sweep (levels [0, n_bwd) and [n_bwd, ...)), so the
+    stream of a warp is contiguous across the levels of a sweep and its prefetch ring never drains."""
     n_levels = len(levels)
-    wt_ptr = np.zeros(n_levels * n_warps + 1, dtype=np.int32)
-    ws_ptr = np.zeros(n_levels * n_warps + 1, dtype=np.int32)
+    wt_ptr = np.zeros((n_levels * n_warps, 2), dtype=np.int32)
+    ws_ptr = np.zeros(n_levels * n_warps, dtype=np.int32)
     hdr, chunks, lstaged = [], [], []
     n_steps = n_vals = 0
+    assigned = []                      # per level: per warp list of (unit index, g0, ng)
     for li, units in enumerate(levels):
         staged = 0
         for u in units:
@@ -88,8 +91,6 @@ def _pack_levels(levels, NG, n_warps):
                     t["stage_off"] = staged
                     staged += t["V"].shape[0]
         lstaged.append(staged)
-        # a unit is split over problem groups while it is longer than a warp's fair share of the level (or while
-        # there are fewer tasks than warps): the copies re-read the unit's stream but run concurrently
         ucost = [sum(t["rec"].shape[0] for t in u) for u in units]
         split = [1] * len(units)
         while True:
@@ -104,21 +105,24 @@ def _pack_levels(levels, NG, n_warps):
         tasks = [(ui, g0, NG // split[ui]) for ui in range(len(units)) for g0 in range(0, NG, NG // split[ui])]
         costs = [ucost[ui] * ng + 6 * len(units[ui]) for (ui, g0, ng) in tasks]
         assign = _lpt(costs, n_warps)
+        assigned.append([[tasks[ti] for ti in assign[w]] for w in range(n_warps)])
+    for (l0, l1) in ((0, n_bwd), (n_bwd, n_levels)):
         for w in range(n_warps):
-            for ti in assign[w]:
-                ui, g0, ng = tasks[ti]
-                for t in units[ui]:
-                    nr, nc = t["V"].shape
-                    st = t["rec"].shape[0]
-                    assert 0 <= t["row0"] < 65536 and st < 65536 and t["stage_off"] < 32768
-                    hdr.append((t["row0"] | ((nr - 1) << 16) | (t["flags"] << 19) | (g0 << 21) | ((ng - 1) << 25),
-                                st | (t["stage_off"] << 16)))
-                    chunks.append(t["rec"])
-                    n_steps += st
-                    if g0 == 0:
-                        n_vals += nr * nc
-            wt_ptr[li * n_warps + w + 1] = len(hdr)
-            ws_ptr[li * n_warps + w + 1] = n_steps
+            for li in range(l0, l1):
+                wt_ptr[li * n_warps + w, 0] = len(hdr)
+                ws_ptr[li * n_warps + w] = n_steps
+                for (ui, g0, ng) in assigned[li][w]:
+                    for t in levels[li][ui]:
+                        nr, nc = t["V"].shape
+                        st = t["rec"].shape[0]
+                        assert 0 <= t["row0"] < 65536 and st < 65536 and t["stage_off"] < 32768
+                        hdr.append((t["row0"] | ((nr - 1) << 16) | (t["flags"] << 19) | (g0 << 21) | ((ng - 1) << 25),
+                                    st | (t["stage_off"] << 16)))
+                        chunks.append(t["rec"])
+                        n_steps += st
+                        if g0 == 0:
+                            n_vals += nr * nc
+                wt_ptr[li * n_warps + w, 1] = len(hdr)
     stream = np.concatenate(chunks).ravel() if chunks else np.zeros(0, dtype=np.uint8)
     return dict(n_levels=n_levels, n_warps=n_warps, wt_ptr=wt_ptr, ws_ptr=ws_ptr,
                 thdr=np.asarray(hdr, dtype=np.int32).reshape(-1, 2), stream=stream, n_steps=int(n_steps),
@@ -358,7 +362,7 @@ def subdomain_plan(F, junc_face, d, NG, n_warps=RES_WARPS, groups=None):
     for s in range(P):
         levels, n_bwd, order, gb = _subdomain_levels(F, loc[s], top_rows[halo[s]], blk_of, stage_cap, groups)
         vrow[s, loc[s][order]] = np.arange(loc[s].size)
-        plan.prog.append(_pack_levels(levels, NG, n_warps))
+        plan.prog.append(_pack_levels(levels, NG, n_warps, n_bwd))
         plan.n_bwd.append(n_bwd)
         plan.group_bounds.append(gb)
     plan.n_bwd = np.asarray(plan.n_bwd, dtype=np.int32)
@@ -440,7 +444,7 @@ def _run_level_host(ps, v, level, NG):
     for w in range(nw):
         idx = level * nw + w
         s = ps["ws_ptr"][idx]
-        for t in range(ps["wt_ptr"][idx], ps["wt_ptr"][idx + 1]):
+        for t in range(ps["wt_ptr"][idx, 0], ps["wt_ptr"][idx, 1]):
             h0, h1 = int(ps["thdr"][t, 0]), int(ps["thdr"][t, 1])
             row0, nr, fl = h0 & 0xffff, ((h0 >> 16) & 7) + 1, (h0 >> 19) & 3
             g0, ng = (h0 >> 21) & 15, ((h0 >> 25) & 15) + 1
@@ -458,7 +462,6 @@ def _run_level_host(ps, v, level, NG):
                 staged.append((row0, nr, pcols, acc))
             else:
                 v[row0:row0 + nr, pcols] = acc
-        assert s == ps["ws_ptr"][idx + 1]
     for (row0, nr, pcols, acc) in staged:
         v[row0:row0 + nr, pcols] = acc
 
