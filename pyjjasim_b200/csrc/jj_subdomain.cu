@@ -452,65 +452,85 @@ template <int NG>
 __device__ void face_pass(const SubArgs& a, const AmpCache<8 * NG>* ac, int s, int c, long long n, int rows_used,
                           double* __restrict__ v) {
     constexpr int PC = 8 * NG, G = PC / 4;
+    constexpr int U = 2;                  // rows per thread and iteration: 16 independent 16-byte loads in flight
     const int K = a.face_K;
     const int* fj = a.face_ell_j + (size_t)s * a.n_rows * K;
     const double* fc = a.face_ell_c + (size_t)s * a.n_rows * K;
     const int* fidx = a.face_fidx + (size_t)s * a.n_rows;
     const int total = rows_used * G;
-    for (int idx = threadIdx.x; idx < total; idx += NT) {
-        const int row = idx / G;
-        const int q = (idx % G) * 4;
-        const int w = c * PC + q;
-        double acc[4] = {0, 0, 0, 0};
-        if (w < a.Wp) {
-            const size_t tbase = (size_t)c * a.Nj * PC + q;
-            for (int k0 = 0; k0 < K; k0 += 4) {
-                int jp[4]; double cf[4]; double2 xa[4], xb[4];
-                {
-                    const int4 j4 = __ldg(reinterpret_cast<const int4*>(fj + (size_t)row * K + k0));
-                    jp[0] = j4.x; jp[1] = j4.y; jp[2] = j4.z; jp[3] = j4.w;
-                    const double2 ca = __ldg(reinterpret_cast<const double2*>(fc + (size_t)row * K + k0));
-                    const double2 cb = __ldg(reinterpret_cast<const double2*>(fc + (size_t)row * K + k0) + 1);
-                    cf[0] = ca.x; cf[1] = ca.y; cf[2] = cb.x; cf[3] = cb.y;
-                }
+    const bool has_vs = a.Vs.kind == KIND_RANK1, has_f = a.F.kind == KIND_RANK1;
+    for (int idx0 = threadIdx.x; idx0 < total; idx0 += U * NT) {
+        double acc[U][4];
+        int row[U], q[U];
+        bool live[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int idx = idx0 + u * NT;
+            live[u] = idx < total;
+            row[u] = live[u] ? idx / G : 0;
+            q[u] = (idx % G) * 4;
+            acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.0;
+            live[u] = live[u] && (c * PC + q[u] < a.Wp);
+        }
+        for (int k0 = 0; k0 < K; k0 += 4) {
+            int jp[U][4]; double cf[U][4]; double2 xa[U][4], xb[U][4];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int4 j4 = __ldg(reinterpret_cast<const int4*>(fj + (size_t)row[u] * K + k0));
+                jp[u][0] = j4.x; jp[u][1] = j4.y; jp[u][2] = j4.z; jp[u][3] = j4.w;
+                const double2 ca = __ldg(reinterpret_cast<const double2*>(fc + (size_t)row[u] * K + k0));
+                const double2 cb = __ldg(reinterpret_cast<const double2*>(fc + (size_t)row[u] * K + k0) + 1);
+                cf[u][0] = ca.x; cf[u][1] = ca.y; cf[u][2] = cb.x; cf[u][3] = cb.y;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const size_t tbase = (size_t)c * a.Nj * PC + q[u];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    if (jp[k] >= 0) {
-                        const double2* xp = reinterpret_cast<const double2*>(a.rx + tbase + (size_t)jp[k] * PC);
-                        xa[k] = __ldcg(xp); xb[k] = __ldcg(xp + 1);
-                    } else {
-                        xa[k] = make_double2(0, 0); xb[k] = make_double2(0, 0);
-                    }
+                    // absent entries (-1) read junction 0 with coefficient 0; x' was written by this block (plain loads)
+                    const double2* xp = reinterpret_cast<const double2*>(a.rx + tbase + (size_t)max(jp[u][k], 0) * PC);
+                    xa[u][k] = xp[0]; xb[u][k] = xp[1];
                 }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    acc[0] = fma(cf[k], xa[k].x, acc[0]); acc[1] = fma(cf[k], xa[k].y, acc[1]);
-                    acc[2] = fma(cf[k], xb[k].x, acc[2]); acc[3] = fma(cf[k], xb[k].y, acc[3]);
+                    acc[u][0] = fma(cf[u][k], xa[u][k].x, acc[u][0]); acc[u][1] = fma(cf[u][k], xa[u][k].y, acc[u][1]);
+                    acc[u][2] = fma(cf[u][k], xb[u][k].x, acc[u][2]); acc[u][3] = fma(cf[u][k], xb[u][k].y, acc[u][3]);
                 }
-                if (a.Vs.kind == KIND_RANK1) {
-                    const double* cum = ac->Vs[n & 1] + q;
+                if (has_vs) {
+                    const double* cum = ac->Vs[n & 1] + q[u];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        if (jp[k] >= 0) {
+                        if (jp[u][k] >= 0) {
                             // coefficient = sign / c0: recover sign * Vs base from the per-junction records
-                            const double ic0 = __ldg(a.P0 + 4 * (size_t)jp[k] + 1), vb = __ldg(a.P1 + 4 * (size_t)jp[k] + 2);
-                            const double sv = (cf[k] / ic0) * vb;
-                            for (int e = 0; e < 4; ++e) acc[e] -= sv * cum[e];
+                            const double ic0 = __ldg(a.P0 + 4 * (size_t)jp[u][k] + 1), vb = __ldg(a.P1 + 4 * (size_t)jp[u][k] + 2);
+                            const double sv = (cf[u][k] / ic0) * vb;
+                            for (int e = 0; e < 4; ++e) acc[u][e] -= sv * cum[e];
                         }
                     }
                 }
             }
-            const int g = __ldg(fidx + row);
-            if (g >= 0 && a.F.kind == KIND_RANK1) {
-                const double* am = ac->F[n & 1] + q;
-                const double b = __ldg(a.F.base + g);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) acc[k] -= TWO_PI * (b * am[k]);
-            }
         }
-        double2* dst = reinterpret_cast<double2*>(v + velem<NG>(row, q));
-        dst[0] = make_double2(acc[0], acc[1]);
-        dst[1] = make_double2(acc[2], acc[3]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (idx0 + u * NT >= total) continue;
+            if (live[u]) {
+                const int g = __ldg(fidx + row[u]);
+                if (g >= 0 && has_f) {
+                    const double* am = ac->F[n & 1] + q[u];
+                    const double b = __ldg(a.F.base + g);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc[u][k] -= TWO_PI * (b * am[k]);
+                }
+            } else {
+                acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.0;
+            }
+            double2* dst = reinterpret_cast<double2*>(v + velem<NG>(row[u], q[u]));
+            dst[0] = make_double2(acc[u][0], acc[u][1]);
+            dst[1] = make_double2(acc[u][2], acc[u][3]);
+        }
     }
 }
 
@@ -580,14 +600,14 @@ __device__ void top_product(const SubArgs& a) {
         double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
         double ac[8], bc[8], an[8], bn[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { ac[j] = __ldg(A + (size_t)j * 32); bc[j] = __ldcg(B + (size_t)j * 4 * PC); }
+        for (int j = 0; j < 8; ++j) { ac[j] = __ldg(A + (size_t)j * 32); bc[j] = B[(size_t)j * 4 * PC]; }
         for (int ks0 = 0; ks0 < KS; ks0 += 8) {
             const bool more = ks0 + 8 < KS;
             if (more) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     an[j] = __ldg(A + (size_t)(ks0 + 8 + j) * 32);
-                    bn[j] = __ldcg(B + (size_t)(ks0 + 8 + j) * 4 * PC);
+                    bn[j] = B[(size_t)(ks0 + 8 + j) * 4 * PC];
                 }
             }
 #pragma unroll
