@@ -98,7 +98,10 @@ def run_ours(args, rank, world, local_rank, dist):
     torch.cuda.set_device(local_rank)
     a, T, w0 = workload(rank, world)
     W = T.size
-    tab = engine.CircuitTables(a, DT)
+    n_parts = None
+    if os.environ.get("JJ_ENGINE", "auto") in ("auto", "subdomain") and not os.environ.get("JJ_SUBDOMAIN"):
+        n_parts = engine.subdomain_layout(a._Nf(), W, engine._sm_count(local_rank))[2]
+    tab = engine.CircuitTables(a, DT, n_parts=n_parts)
     eng = engine.DeviceEngine(local_rank)
     eng.set_circuit(tab, pj.DefaultCPR())
     kind = {"auto": _lib.JJ_ENGINE_AUTO, "streaming": _lib.JJ_ENGINE_STREAMING,

@@ -149,6 +149,8 @@ typedef struct {
     const double *cpr_a, *cpr_b; /* [M+1]; DefaultCPR is M=1, a={0,0}, b={0,1} (reference: static_problem.py:77-85) */
 } JJCircuit;
 
+/* multiprocessor count of a CUDA device (the host sizes the subdomain plan to it); <= 0 on failure */
+int  jj_sm_count(int device);
 /* create / destroy an engine bound to one CUDA device */
 int  jj_create(int device, JJHandle **out);
 void jj_destroy(JJHandle *h);

@@ -585,10 +585,11 @@ __device__ void top_assemble(const SubArgs& a, long long n) {
     }
 }
 
-// J_top = S_top^-1 r_top. Task = (chunk, 8-row tile, problem group), one per warp and round; consecutive tasks
-// differ in the group first, so the warps of a block share A row tiles and B fragments through L1.
+// J_top = S_top^-1 r_top, direct version (no shared-memory staging; used when the staging rows are too few).
+// Task = (chunk, 8-row tile, problem group), one per warp and round; consecutive tasks differ in the group
+// first, so the warps of a block share A row tiles and B fragments through L1.
 template <int NG>
-__device__ void top_product(const SubArgs& a) {
+__device__ void top_product_direct(const SubArgs& a) {
     constexpr int PC = 8 * NG;
     const int RT = (a.n_top + 7) / 8, KS = a.n_top_pad / 4;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -598,32 +599,91 @@ __device__ void top_product(const SubArgs& a) {
         const double* A = a.SinvP + ((size_t)rt * KS) * 32 + lane;
         const double* B = a.rtop + ((size_t)c * a.n_top_pad + (lane & 3)) * PC + 8 * g + (lane >> 2);
         double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
-        double ac[8], bc[8], an[8], bn[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { ac[j] = __ldg(A + (size_t)j * 32); bc[j] = B[(size_t)j * 4 * PC]; }
         for (int ks0 = 0; ks0 < KS; ks0 += 8) {
-            const bool more = ks0 + 8 < KS;
-            if (more) {
+            double ac[8], bc[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    an[j] = __ldg(A + (size_t)(ks0 + 8 + j) * 32);
-                    bn[j] = B[(size_t)(ks0 + 8 + j) * 4 * PC];
-                }
-            }
+            for (int j = 0; j < 8; ++j) { ac[j] = __ldg(A + (size_t)(ks0 + j) * 32); bc[j] = B[(size_t)(ks0 + j) * 4 * PC]; }
 #pragma unroll
             for (int j = 0; j < 8; j += 2) {
                 dmma884(c00, c01, ac[j], bc[j]);
                 dmma884(c10, c11, ac[j + 1], bc[j + 1]);
-            }
-            if (more) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { ac[j] = an[j]; bc[j] = bn[j]; }
             }
         }
         const int row = 8 * rt + (lane >> 2);
         double2* dst = reinterpret_cast<double2*>(a.jtop + ((size_t)c * a.n_top_pad + row) * PC + 8 * g + 2 * (lane & 3));
         *dst = make_double2(c00 + c10, c01 + c11);
     }
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc));
+}
+
+// J_top = S_top^-1 r_top as a block-level product: a block computes 32 rows x (4 groups of 8 problems) of one
+// chunk; per K block the four A row tiles and the four B fragments are staged once in shared memory by cp.async
+// (a TOP_STAGES-deep ring in the staging rows, which are idle between the sweeps) and read by all 16 warps:
+// warp = (row tile, group). 128 bytes of L2 traffic per MMA instead of 512.
+constexpr int TOP_STAGES = 4;
+template <int NG>
+__device__ void top_product(const SubArgs& a, double* buf, int KB) {
+    constexpr int PC = 8 * NG;
+    constexpr int GP = (NG + 3) / 4;              // passes over the groups of a chunk, 4 at a time
+    const int Q = a.n_top_pad / 32, KS = a.n_top_pad / 4;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rt = warp & 3, gl = warp >> 2;
+    const int stage_doubles = KB * 8 * 32;        // KB x (4 A + 4 B) fragments of 32 doubles
+    const int n_tasks = a.n_chunks * Q * GP;
+    const int nkb = KS / KB;                      // KS is a multiple of 8, KB of 1, 2 or 4
+    // this thread's 16-byte piece of a stage (stage = KB x 8 fragments x 16 pieces <= NT pieces)
+    const bool loader = (int)threadIdx.x < stage_doubles / 2;
+    const int l_frag = threadIdx.x / 16, l_piece = threadIdx.x % 16;
+    const int l_which = l_frag / KB, l_kl = l_frag % KB;                 // which: 0..3 A row tiles, 4..7 B groups
+    for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+        const int gp = task % GP, q = (task / GP) % Q, c = task / (GP * Q);
+        const int g = 4 * gp + gl;
+        const bool active = g < NG;
+        const double* src0;
+        size_t src_step;                          // per K block
+        if (l_which < 4) {
+            src0 = a.SinvP + ((size_t)(4 * q + l_which) * KS + l_kl) * 32 + l_piece * 2;
+            src_step = (size_t)KB * 32;
+        } else {
+            const int gg = min(4 * gp + (l_which - 4), NG - 1);
+            src0 = a.rtop + ((size_t)c * a.n_top_pad + 4 * l_kl + (l_piece >> 2)) * PC + 8 * gg + (l_piece & 3) * 2;
+            src_step = (size_t)KB * 4 * PC;
+        }
+        double* dst0 = buf + (size_t)threadIdx.x * 2;
+        auto issue = [&](int kb) {
+            if (loader && kb < nkb) cp_async16(dst0 + (size_t)(kb % TOP_STAGES) * stage_doubles, src0 + (size_t)kb * src_step);
+            asm volatile("cp.async.commit_group;");
+        };
+        __syncthreads();                          // the ring is free (previous task / phase done)
+#pragma unroll
+        for (int k = 0; k < TOP_STAGES - 1; ++k) issue(k);
+        double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(TOP_STAGES - 2));
+            __syncthreads();                      // stage kb has landed for everyone; stage kb-1 is no longer read
+            issue(kb + TOP_STAGES - 1);
+            if (active) {
+                const double* st = buf + (size_t)(kb % TOP_STAGES) * stage_doubles;
+                for (int kl = 0; kl < KB; ++kl) {
+                    const double av = st[(size_t)(rt * KB + kl) * 32 + lane];
+                    // B fragment staged as [kk][n]: lane = n*4 + kk reads element kk*8 + n
+                    const double bv = st[(size_t)((4 + gl) * KB + kl) * 32 + (lane & 3) * 8 + (lane >> 2)];
+                    if (kl & 1) dmma884(c10, c11, av, bv); else dmma884(c00, c01, av, bv);
+                }
+            }
+        }
+        asm volatile("cp.async.wait_group 0;");
+        if (active) {
+            const int row = 32 * q + 8 * rt + (lane >> 2);
+            double2* dst = reinterpret_cast<double2*>(a.jtop + ((size_t)c * a.n_top_pad + row) * PC + 8 * g + 2 * (lane & 3));
+            *dst = make_double2(c00 + c10, c01 + c11);
+        }
+    }
+    __syncthreads();
 }
 
 template <int NG>
@@ -663,6 +723,10 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
     const bool keep_z = n_items <= (int)gridDim.x;     // every block has at most one item: z stays in shared memory
     unsigned bar_target = 0;
     int cur_s = -1;
+    // K block of the staged top product: TOP_STAGES stages of KB x 2 KB must fit in the staging rows
+    const int stage_bytes = a.stage_rows * (PC + 2) * 8;
+    const int top_kb = stage_bytes >= TOP_STAGES * 4 * 2048 ? 4 : stage_bytes >= TOP_STAGES * 2 * 2048 ? 2
+                       : stage_bytes >= TOP_STAGES * 2048 ? 1 : 0;
 
     if (a.dbg_b) {
         // ---- debug: one solve J = S^-1 b through the plan
@@ -686,7 +750,7 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
         grid_barrier(a.bar, bar_target);
         top_assemble<NG>(a, 0);
         grid_barrier(a.bar, bar_target);
-        top_product<NG>(a);
+        if (top_kb > 0) top_product<NG>(a, stage, top_kb); else top_product_direct<NG>(a);
         grid_barrier(a.bar, bar_target);
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int s = item % a.P, c = item / a.P;
@@ -769,7 +833,7 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
             top_assemble<NG>(a, n);
             grid_barrier(a.bar, bar_target);
             if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 5] += tn - tq; tq = tn; }
-            top_product<NG>(a);
+            if (top_kb > 0) top_product<NG>(a, stage, top_kb); else top_product_direct<NG>(a);
             if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 6] += tn - tq; tq = tn; }
             grid_barrier(a.bar, bar_target);
             if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 7] += tn - tq; tq = tn; }
@@ -972,8 +1036,8 @@ static int launch(JJHandle* h, SubState* st, SubArgs& a) {
         if (per_sm <= 0) { h->err = "subdomain: kernel does not fit on the device"; return JJ_EINVAL; }
         st->grid = sms * std::min(per_sm, 1);
     }
-    const int top_tasks = st->n_chunks * ((st->n_top + 7) / 8) * st->NG;
-    int want = std::max(st->P * st->n_chunks, (top_tasks + NWARPS - 1) / NWARPS);
+    const int top_tasks = st->n_chunks * (st->n_top_pad / 32) * ((st->NG + 3) / 4);
+    int want = std::max(st->P * st->n_chunks, top_tasks);
     const char* env = getenv("JJ_SUB_GRID");
     int grid = std::min(st->grid, std::max(1, want));
     if (env && atoi(env) > 0) grid = std::min(st->grid, atoi(env));

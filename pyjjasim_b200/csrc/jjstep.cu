@@ -337,6 +337,12 @@ static int run_sweep(JJHandle* h, const SweepDev& s, double* v) {
 
 extern "C" {
 
+int jj_sm_count(int device) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
+    return sms;
+}
+
 int jj_create(int device, JJHandle** out) {
     *out = nullptr;
     int n = 0;

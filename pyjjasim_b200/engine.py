@@ -41,7 +41,7 @@ class CircuitTables:
     every junction, and the compiled solve program of A (L + 1/(Cv+Rv)) A^T (reference: :504-506).
     """
 
-    def __init__(self, circuit, dt, leaf_size=None):
+    def __init__(self, circuit, dt, leaf_size=None, n_parts=None):
         A = scipy.sparse.csr_matrix(circuit.get_cycle_matrix())
         A.sum_duplicates()
         A.eliminate_zeros()
@@ -64,7 +64,7 @@ class CircuitTables:
                 cx, cy = circuit.get_face_centroids()
             else:
                 cx, cy = _centroids_from_matrix(circuit, A)
-            self.factor = factorize(S, cx, cy, leaf_size=leaf_size)
+            self.factor = factorize(S, cx, cy, leaf_size=leaf_size, n_parts=n_parts)
             self.program = streaming_program(self.factor)
             perm = self.program.perm.astype(np.int64)
         else:
@@ -95,6 +95,7 @@ class CircuitTables:
         self.junc_face, self.junc_sign = jf, js
         self._resident = {}
         self._subdomain = {}
+        self.n_parts = n_parts
 
     # ------------------------------------------------------------------ subdomain engine plan
     def subdomain_smem_bytes(self, plan):
@@ -112,26 +113,25 @@ class CircuitTables:
         return self._subdomain[key]
 
     def choose_subdomain(self, W, n_sm=148):
-        """Pick (cut depth d, problem groups NG) for the subdomain engine, or None. JJ_SUBDOMAIN="d,NG" overrides.
-        Preference: fill the SMs with (subdomain, chunk) items, keep chunks wide (factor reuse) and the top small."""
+        """Pick (cut, problem groups NG) for the subdomain engine, or None. cut = None uses the n_parts subtrees
+        this ordering was made with (see subdomain_layout); otherwise cut is a tree depth (2^cut subdomains).
+        JJ_SUBDOMAIN="cut,NG" overrides ("p,NG" selects the parts)."""
         if self.factor is None:
             return None
         env = os.environ.get("JJ_SUBDOMAIN")
         if env:
-            d, NG = (int(v) for v in env.split(","))
-            return d, NG
-        Wp = (W + 3) // 4 * 4
-        max_d = int(self.factor.depth.max()) if self.factor.nb else 0
-        NG = 4 if Wp > 16 else 2 if Wp > 8 else 1
-        chunks = (Wp + 8 * NG - 1) // (8 * NG)
-        # as many subdomains as there are SMs to fill, but none smaller than ~64 faces (below that the top product
-        # and the barriers cost more than the local sweeps save)
-        d_hi = 0
-        while d_hi < min(max_d - 1, 6) and (2 << d_hi) * chunks <= n_sm and self.Nf >= 64 * (2 << d_hi):
-            d_hi += 1
-        for d in list(range(d_hi, 7)):
-            if d > max(max_d - 1, 0):
-                break
+            d, NG = env.split(",")
+            return (None if d.strip().startswith("p") else int(d)), int(NG)
+        NG, chunks, _ = subdomain_layout(self.Nf, W, n_sm)
+        if self.n_parts is not None and self.factor.blk_part is not None:
+            cands = [None]
+        else:
+            max_d = int(self.factor.depth.max()) if self.factor.nb else 0
+            d_hi = 0
+            while d_hi < min(max_d - 1, 6) and (2 << d_hi) * chunks <= n_sm and self.Nf >= 64 * (2 << d_hi):
+                d_hi += 1
+            cands = [d for d in range(d_hi, 7) if d <= max(max_d - 1, 0)]
+        for d in cands:
             try:
                 plan = self.subdomain_plan(d, NG)
             except ValueError:
@@ -227,6 +227,17 @@ class _ResidentTables:
         self.face_fidx = fidx
 
 
+def subdomain_layout(Nf, W, n_sm=148):
+    """(NG, chunks, n_parts) of the subdomain engine for W problems on a circuit with Nf faces: chunks of 8*NG
+    problems, and as many subdomains as fill the SMs with (subdomain, chunk) thread blocks - but none smaller
+    than ~64 faces (below that the top product and the barriers cost more than the local sweeps save)."""
+    Wp = (W + 3) // 4 * 4
+    NG = 4 if Wp > 16 else 2 if Wp > 8 else 1
+    chunks = (Wp + 8 * NG - 1) // (8 * NG)
+    n_parts = max(1, min(n_sm // chunks, Nf // 64))
+    return NG, chunks, n_parts
+
+
 def _centroids_from_matrix(circuit, A):
     x, y = circuit.get_node_coordinates()
     n1, n2 = circuit.get_junction_nodes()
@@ -239,16 +250,16 @@ def _centroids_from_matrix(circuit, A):
 _tables_cache = {}
 
 
-def _tables_for(circuit, dt):
+def _tables_for(circuit, dt, n_parts=None):
     """Cache per circuit object, invalidated when component values change."""
     L = circuit._L()
     key = (id(circuit), float(dt), hash(np.asarray(circuit._R()).tobytes()), hash(np.asarray(circuit._C()).tobytes()),
            hash(np.asarray(circuit._Ic()).tobytes()), hash(L.data.tobytes()) ^ hash(L.indices.tobytes()),
-           os.environ.get("JJ_LEAF_SIZE", "8"))
+           os.environ.get("JJ_LEAF_SIZE", "8"), n_parts)
     hit = _tables_cache.get(id(circuit))
     if hit is not None and hit[0] == key:
         return hit[1]
-    tab = CircuitTables(circuit, dt)
+    tab = CircuitTables(circuit, dt, n_parts=n_parts)
     _tables_cache[id(circuit)] = (key, tab)
     return tab
 
@@ -348,7 +359,8 @@ class DeviceEngine:
         self.resident_config = (Ccl, Wt)
 
     def set_subdomain(self, d, NG):
-        """Upload the subdomain-engine plan for cut depth d and NG groups of 8 problems per chunk."""
+        """Upload the subdomain-engine plan for cut depth d (None: the n_parts subtrees of the ordering) and NG
+        groups of 8 problems per chunk."""
         plan = self.tab.subdomain_plan(d, NG)
         p = _lib.JJSubdomainPlan()
         p.P, p.NG, p.n_rows, p.n_loc_max, p.stage_rows = plan.P, plan.NG, plan.n_rows, plan.n_loc_max, plan.stage_rows
@@ -641,8 +653,19 @@ def device_time_evolution_core(problem, th_store_mask, I_store_mask, engine=None
     if getattr(problem, "stencil_width", 3) != 3:
         raise NotImplementedError("only stencil_width=3 is supported")
     circuit = problem.get_circuit()
-    tab = _tables_for(circuit, problem._dt())
-    Nj, W = tab.Nj, problem.get_problem_count()
+    W = problem.get_problem_count()
+    devices = getattr(problem, "devices", None)
+    if devices is None:
+        env = os.environ.get("JJ_DEVICES")
+        devices = [int(d) for d in env.split(",")] if env else [0]
+    # the dissection tree is made with one subtree per (SM, problem chunk) pair of the subdomain engine
+    W_dev = (shard[1] - shard[0]) if shard is not None else -(-W // max(1, len(devices)))
+    n_parts = None
+    if os.environ.get("JJ_ENGINE", "auto") in ("auto", "subdomain") and not os.environ.get("JJ_SUBDOMAIN") \
+            and engine in (None, _lib.JJ_ENGINE_AUTO, _lib.JJ_ENGINE_SUBDOMAIN):
+        n_parts = subdomain_layout(circuit._Nf(), max(1, W_dev), _sm_count(devices[0] if device is None else device))[2]
+    tab = _tables_for(circuit, problem._dt(), n_parts)
+    Nj = tab.Nj
     th_mask = np.asarray(th_store_mask, dtype=bool)
     I_mask = np.asarray(I_store_mask, dtype=bool)
     specs = _classify_all(problem, tab)
@@ -652,10 +675,6 @@ def device_time_evolution_core(problem, th_store_mask, I_store_mask, engine=None
     th_host[0] = problem.config_at_minus_2
     I_host[1] = problem._cp(problem.config_at_minus_1)
     I_host[0] = problem._cp(problem.config_at_minus_2)
-    devices = getattr(problem, "devices", None)
-    if devices is None:
-        env = os.environ.get("JJ_DEVICES")
-        devices = [int(d) for d in env.split(",")] if env else [0]
     if engine is None:
         engine = {"auto": _lib.JJ_ENGINE_AUTO, "streaming": _lib.JJ_ENGINE_STREAMING,
                   "resident": _lib.JJ_ENGINE_RESIDENT,
@@ -691,6 +710,19 @@ def device_time_evolution_core(problem, th_store_mask, I_store_mask, engine=None
         th_host, I_host = th_host[:, :, shard[0]:shard[1]], I_host[:, :, shard[0]:shard[1]]
     # (plane, Nj, W) -> (Nj, W, plane) views, the reference's layout (quirk Q7)
     return np.moveaxis(th_host, 0, 2), np.moveaxis(I_host, 0, 2)
+
+
+_sm_cache = {}
+
+
+def _sm_count(device):
+    """Multiprocessor count of a device (through the C ABI; 148 = B200 if the library cannot tell yet)."""
+    if device not in _sm_cache:
+        try:
+            _sm_cache[device] = int(_lib.load().jj_sm_count(int(device)))
+        except Exception:
+            _sm_cache[device] = 0
+    return _sm_cache[device] if _sm_cache[device] > 0 else 148
 
 
 def shard_bounds(W, n_shards):

@@ -66,6 +66,7 @@ class Factor:
         self.Loff = None          # CSR: Lc without the diagonal blocks  (row i: couplings to earlier blocks)
         self.LoffT = None         # CSR: its transpose                   (row j: couplings to later blocks)
         self.nnz_L = 0
+        self.blk_part = None      # part (subtree) of each block when the ordering was made with n_parts
         self.Lc = None            # CSR: the full Cholesky factor (subdomain engine: Schur complement of the top separators)
 
     @property
@@ -77,11 +78,18 @@ class Factor:
         return int(self.height.max()) if self.nb else 0
 
 
-def factorize(S, cx, cy, leaf_size=8):
+def factorize(S, cx, cy, leaf_size=8, n_parts=None):
+    """n_parts: make the dissection tree with that many equal subtrees (ordering.nested_dissection); the part of
+    every block is kept in F.blk_part (-1: separators above the parts)."""
     n = S.shape[0]
     F = Factor()
     F.n = n
-    perm, bptr, height, depth, dom = nested_dissection(S, cx, cy, leaf_size=leaf_size, return_tree=True)
+    if n_parts is None:
+        perm, bptr, height, depth, dom = nested_dissection(S, cx, cy, leaf_size=leaf_size, return_tree=True)
+        F.blk_part = None
+    else:
+        perm, bptr, height, depth, dom, F.blk_part = nested_dissection(S, cx, cy, leaf_size=leaf_size, return_tree=True,
+                                                                      n_parts=n_parts)
     F.perm, F.bptr, F.height, F.depth, F.dom = perm, bptr, height, depth, dom
     Sp = scipy.sparse.csc_matrix(S)[perm][:, perm].tocsc()
     lu = scipy.sparse.linalg.splu(Sp, permc_spec="NATURAL", diag_pivot_thresh=0.0,

@@ -19,7 +19,7 @@ import scipy.sparse
 __all__ = ["nested_dissection"]
 
 
-def nested_dissection(S, cx, cy, leaf_size=24, return_tree=False):
+def nested_dissection(S, cx, cy, leaf_size=24, return_tree=False, n_parts=None):
     """
     Parameters
     ----------
@@ -36,6 +36,11 @@ def nested_dissection(S, cx, cy, leaf_size=24, return_tree=False):
     With return_tree=True also returns block_depth and block_dom: block b is the separator (or leaf) of
     the subdomain reached from the root by the cuts encoded in the binary digits of block_dom[b]
     (most significant digit = first cut); its subtree holds exactly the blocks (depth + t, dom * 2^t + r).
+
+    n_parts : if given, the first cuts are made UNEVEN so that the tree has n_parts subtrees of about equal size
+    (a domain that still has to yield p parts is cut p//2 : p - p//2); with return_tree=True a sixth array
+    block_part is returned: the index of the part a block belongs to, or -1 for the separators above the parts.
+    (The subdomain engine wants one part per (SM, problem chunk) pair, which is rarely a power of two.)
     """
     n = S.shape[0]
     cx = np.asarray(cx, dtype=np.double)
@@ -47,11 +52,23 @@ def nested_dissection(S, cx, cy, leaf_size=24, return_tree=False):
     active = np.ones(n, dtype=bool)            # not yet placed in a block
     blk_depth = np.zeros(n, dtype=np.int64)    # (depth, dom) of the block each unknown ends up in
     depth, n_dom = 0, 1
+    parts = np.array([max(1, int(n_parts or 1))], dtype=np.int64)      # parts still to be made out of each domain
+    part_of = np.full(n, -1, dtype=np.int64)
+    n_made = 0
+    if parts[0] == 1:
+        part_of[:] = 0
+        n_made = 1
     while True:
         idx = np.flatnonzero(active)
         if idx.size == 0:
             break
         size = np.bincount(dom[idx], minlength=n_dom)
+        # a domain too small to be cut further becomes a single part
+        small = (size <= leaf_size) & (parts > 1)
+        for dm in np.flatnonzero(small):
+            part_of[idx[dom[idx] == dm]] = n_made
+            n_made += 1
+            parts[dm] = 1
         leaf_nodes = idx[size[dom[idx]] <= leaf_size]
         blk_depth[leaf_nodes] = depth
         active[leaf_nodes] = False
@@ -75,7 +92,9 @@ def nested_dissection(S, cx, cy, leaf_size=24, return_tree=False):
         rank = np.empty(idx.size, dtype=np.int64)
         rank[order] = np.arange(idx.size) - start[sd]
         half = np.zeros(n, dtype=np.int8)
-        half[idx] = rank >= (size[d] + 1) // 2
+        p_lo = parts // 2
+        lo_count = np.where(parts > 1, np.rint(size * (p_lo / np.maximum(parts, 1))).astype(np.int64), (size + 1) // 2)
+        half[idx] = rank >= lo_count[d]
         # separator: unknowns of the lower half coupled to the upper half of the same subdomain
         both = active[ei] & active[ej]
         e1, e2 = ei[both], ej[both]
@@ -85,6 +104,21 @@ def nested_dissection(S, cx, cy, leaf_size=24, return_tree=False):
         active[sep] = False
         idx = np.flatnonzero(active)
         dom[idx] = 2 * dom[idx] + half[idx]
+        new_parts = np.ones(2 * n_dom, dtype=np.int64)
+        new_parts[0::2] = np.where(parts > 1, p_lo, 1)
+        new_parts[1::2] = np.where(parts > 1, parts - p_lo, 1)
+        fresh = np.zeros(2 * n_dom, dtype=bool)          # domains that just became a part of their own
+        fresh[0::2] = (parts > 1) & (new_parts[0::2] == 1)
+        fresh[1::2] = (parts > 1) & (new_parts[1::2] == 1)
+        if fresh.any() and idx.size:
+            ids = np.full(2 * n_dom, -1, dtype=np.int64)
+            present = np.unique(dom[idx])
+            present = present[fresh[present]]
+            ids[present] = n_made + np.arange(present.size)
+            n_made += present.size
+            sel = fresh[dom[idx]]
+            part_of[idx[sel]] = ids[dom[idx[sel]]]
+        parts = new_parts
         n_dom *= 2
         depth += 1
 
@@ -119,5 +153,7 @@ def nested_dissection(S, cx, cy, leaf_size=24, return_tree=False):
         stack.append(b)
     if return_tree:
         first = perm[block_ptr[:-1]] if nb else np.zeros(0, dtype=np.int64)
+        if n_parts is not None:
+            return perm, block_ptr, height, b_depth.astype(np.int64), dom[first], part_of[first]
         return perm, block_ptr, height, b_depth.astype(np.int64), dom[first]
     return perm, block_ptr, height

@@ -273,18 +273,24 @@ def subdomain_plan(F, junc_face, d, NG, n_warps=RES_WARPS, groups=None):
     """
     F         : factor.Factor of the permuted cycle-space system
     junc_face : (Nj, 2) permuted faces of every junction, -1 none (CircuitTables.junc_face)
-    d         : cut depth, P = 2^d subdomains
+    d         : cut depth, P = 2^d subdomains; None: the subtrees of an ordering made with n_parts (F.blk_part)
     NG        : problem groups of 8 per chunk (PC = 8 * NG problems share one pass over the factor)
     groups    : tree heights after which a new level group starts (see _subdomain_levels); None = automatic
     """
     assert NG in (1, 2, 4, 8)
     n, nb = F.n, F.nb
-    P = 1 << d
     PC = 8 * NG
     sizes = np.diff(F.bptr)
     blk_of = np.repeat(np.arange(nb), sizes)
-    top_blk = F.depth < d
-    blk_sub = np.where(top_blk, -1, F.dom >> np.maximum(F.depth - d, 0)).astype(np.int64)
+    if d is None:
+        # the ordering was made with n_parts equal subtrees: they are the subdomains
+        assert F.blk_part is not None
+        blk_sub = np.asarray(F.blk_part, dtype=np.int64)
+        P = int(blk_sub.max()) + 1
+    else:
+        P = 1 << d
+        top_blk = F.depth < d
+        blk_sub = np.where(top_blk, -1, F.dom >> np.maximum(F.depth - d, 0)).astype(np.int64)
     row_sub = blk_sub[blk_of]
     top_rows = np.flatnonzero(row_sub < 0)
     n_top = int(top_rows.size)
@@ -367,6 +373,13 @@ def subdomain_plan(F, junc_face, d, NG, n_warps=RES_WARPS, groups=None):
         plan.group_bounds.append(gb)
     plan.n_bwd = np.asarray(plan.n_bwd, dtype=np.int32)
     plan.stage_rows = max(p["stage_rows"] for p in plan.prog)
+    if n_top:
+        # the staged top product keeps a ring of 4 stages x 8 KB (or 4 KB, 2 KB) in the staging rows
+        for ring in (32768, 16384, 8192):
+            need = -(-ring // ((PC + 2) * 8))
+            if need <= stage_cap:
+                plan.stage_rows = max(plan.stage_rows, need)
+                break
 
     # ---- top: explicit inverse of the Schur complement, packed as FP64 MMA A fragments
     nTp = plan.n_top_pad

@@ -119,6 +119,33 @@ def test_subdomain_plan_matches_direct_solve(ctor, args, d, NG):
     assert np.max(np.abs(J - Jref)) <= 1e-12 * np.max(np.abs(Jref))
 
 
+@pytest.mark.parametrize("ctor,args,n_parts,NG", [(pj.SquareArray, (23, 17), 3, 2), (pj.HoneycombArray, (9, 7), 5, 1),
+                                                  (pj.SquareArray, (40, 37), 6, 4), (pj.SquareArray, (20, 20), 1, 4)])
+def test_subdomain_plan_with_uneven_dissection(ctor, args, n_parts, NG):
+    # orderings made with n_parts subtrees (one per SM and problem chunk, rarely a power of two)
+    from pyjjasim_b200.subdomain import apply_subdomain_plan_host
+    a = ctor(*args)
+    rng = np.random.RandomState(4)
+    a.set_resistance(0.5 + rng.rand(a._Nj()))
+    tab = CircuitTables(a, 0.05, n_parts=n_parts)
+    part = np.asarray(tab.factor.blk_part)
+    sizes = np.diff(tab.factor.bptr)
+    rows = np.array([sizes[part == k].sum() for k in range(part.max() + 1)])
+    assert part.max() + 1 == n_parts and (a._Nf() < 500 or rows.min() >= 0.6 * rows.max())
+    plan = tab.subdomain_plan(None, NG)
+    assert plan.P == n_parts
+    S = system_matrix(a.get_cycle_matrix(), a._L(), tab.Rv, tab.Cv)
+    b = rng.randn(a._Nf(), plan.PC)
+    Jp = apply_subdomain_plan_host(plan, b[tab.perm])
+    J = np.empty_like(Jp)
+    J[tab.perm] = Jp
+    Jref = scipy.sparse.linalg.spsolve(S.tocsc(), b)
+    assert np.max(np.abs(J - Jref)) <= 1e-12 * np.max(np.abs(Jref))
+    # the streaming program of the same ordering is still a valid solve
+    J2 = apply_program_host(tab.program, b)
+    assert np.max(np.abs(J2 - Jref)) <= 1e-12 * np.max(np.abs(Jref))
+
+
 def test_circuit_tables_permutation_consistency():
     a = pj.HoneycombArray(6, 5)
     tab = CircuitTables(a, 0.05)
