@@ -109,6 +109,28 @@ __device__ __forceinline__ int velem(int row, int q) {
     return row * (8 * NG) + (((q >> 2) ^ (row & CM)) << 2) + (q & 3);
 }
 
+// L2 residency hints: the factor streams, the packed Schur inverse and the junction records are re-read every
+// time step (evict_last), while the state streams through once per step (evict_first) and would otherwise
+// push them out of the 126 MB L2 between two uses.
+__device__ __forceinline__ unsigned long long policy_evict_last() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long policy_evict_first() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ double2 ldg_hint_d2(const double* p, unsigned long long pol) {
+    double2 v;
+    asm volatile("ld.global.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void stg_hint_d2(double* p, double2 v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
+
 struct Cursor {
     int t0, t1, s;
     const unsigned char* pA;      // + lane*8: A fragment of the first step of the current ring block
@@ -125,6 +147,7 @@ struct ProgSmem {
 __device__ __forceinline__ void cursor_open(Cursor& cu, const ProgSmem& ps, int level) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int idx = level * NWARPS + warp;
+    const unsigned long long pol = policy_evict_last();
     cu.t0 = ps.wt[2 * idx]; cu.t1 = ps.wt[2 * idx + 1];
     cu.s = ps.ws[idx];
     // ring slot of stream step s is s % RING; the stream buffer is padded by 2*RING steps
@@ -135,8 +158,8 @@ __device__ __forceinline__ void cursor_open(Cursor& cu, const ProgSmem& ps, int 
 #pragma unroll
     for (int k = 0; k < RING; ++k) {
         const int off = (k + (k < p ? RING : 0)) * STEP_BYTES;
-        cu.ra[k] = __ldg(reinterpret_cast<const double*>(cu.pA + off));
-        cu.rc[k] = __ldg(reinterpret_cast<const unsigned short*>(cu.pC + off));
+        asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(cu.ra[k]) : "l"(cu.pA + off), "l"(pol));
+        asm volatile("ld.global.nc.L2::cache_hint.u16 %0, [%1], %2;" : "=r"(cu.rc[k]) : "l"(cu.pC + off), "l"(pol));
     }
 }
 
@@ -162,6 +185,7 @@ __device__ __forceinline__ void tile_steps(int nsteps, int& s, const unsigned ch
                                            double (&ra)[RING], unsigned (&rc)[RING], unsigned vb, unsigned gx,
                                            double (&acc)[NG][2]) {
     constexpr bool DUAL = NGT <= 2;
+    const unsigned long long pol = policy_evict_last();
     double alt[NGT][2];
 #pragma unroll
     for (int g = 0; g < NGT; ++g) { alt[g][0] = 0.0; alt[g][1] = 0.0; }
@@ -175,8 +199,8 @@ __device__ __forceinline__ void tile_steps(int nsteps, int& s, const unsigned ch
             if (DUAL && ((K) & 1)) dmma884(alt[g][0], alt[g][1], ra[K], b_[g]);                        \
             else dmma884(acc[g][0], acc[g][1], ra[K], b_[g]);                                          \
         }                                                                                              \
-        asm volatile("ld.global.nc.f64 %0, [%1+%2];" : "=d"(ra[K]) : "l"(pA), "n"((RING + (K)) * STEP_BYTES)); \
-        asm volatile("ld.global.nc.u16 %0, [%1+%2];" : "=r"(rc[K]) : "l"(pC), "n"((RING + (K)) * STEP_BYTES)); \
+        asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1+%2], %3;" : "=d"(ra[K]) : "l"(pA), "n"((RING + (K)) * STEP_BYTES), "l"(pol)); \
+        asm volatile("ld.global.nc.L2::cache_hint.u16 %0, [%1+%2], %3;" : "=r"(rc[K]) : "l"(pC), "n"((RING + (K)) * STEP_BYTES), "l"(pol)); \
         ++j;                                                                                           \
     }
     for (int j = 0; j < nsteps;) {
@@ -354,9 +378,9 @@ __device__ __forceinline__ void junction_item(const SubArgs& a, const AmpCache<8
     if (w >= a.Wp) return;
     const int jp = jlo + idx / G;
     const size_t sidx = ((size_t)c * a.Nj + jlo) * PC + (size_t)idx * 4;
-    const double2* xp = reinterpret_cast<const double2*>(a.rx + sidx);
-    const double2* tp = reinterpret_cast<const double2*>(a.rth + sidx);
-    const double2 x0 = xp[0], x1 = xp[1], t0 = tp[0], t1 = tp[1];
+    const unsigned long long pol_first = policy_evict_first();
+    const double2 x0 = ldg_hint_d2(a.rx + sidx, pol_first), x1 = ldg_hint_d2(a.rx + sidx + 2, pol_first);
+    const double2 t0 = ldg_hint_d2(a.rth + sidx, pol_first), t1 = ldg_hint_d2(a.rth + sidx + 2, pol_first);
     const double2* rec = reinterpret_cast<const double2*>(a.jrec + 8 * (size_t)jp);
     const double2 rIc = __ldg(rec), rc = __ldg(rec + 1), rb = __ldg(rec + 2);
     const int4 ri = __ldg(reinterpret_cast<const int4*>(rec + 3));      // row0, row1, original junction, signs
@@ -391,8 +415,8 @@ __device__ __forceinline__ void junction_item(const SubArgs& a, const AmpCache<8
             return;
         }
     }
-    double2* op = reinterpret_cast<double2*>(a.rth + sidx);
-    op[0] = make_double2(th1[0], th1[1]); op[1] = make_double2(th1[2], th1[3]);
+    stg_hint_d2(a.rth + sidx, make_double2(th1[0], th1[1]), pol_first);
+    stg_hint_d2(a.rth + sidx + 2, make_double2(th1[2], th1[3]), pol_first);
     double xn[4];
     next_x<DEF>(a, rIc.x, rc.x, rc.y, rb.x, rb.y, ac->T[n & 1] + q, ac->Is[n & 1] + q, ri.z, w, n, th1, th2, xn);
     double2* xo = reinterpret_cast<double2*>(a.rx + sidx);
@@ -625,14 +649,14 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 // (a TOP_STAGES-deep ring in the staging rows, which are idle between the sweeps) and read by all 16 warps:
 // warp = (row tile, group). 128 bytes of L2 traffic per MMA instead of 512.
 constexpr int TOP_STAGES = 4;
-template <int NG>
-__device__ void top_product(const SubArgs& a, double* buf, int KB) {
+template <int NG, int KB>
+__device__ void top_product(const SubArgs& a, double* buf) {
     constexpr int PC = 8 * NG;
     constexpr int GP = (NG + 3) / 4;              // passes over the groups of a chunk, 4 at a time
     const int Q = a.n_top_pad / 32, KS = a.n_top_pad / 4;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rt = warp & 3, gl = warp >> 2;
-    const int stage_doubles = KB * 8 * 32;        // KB x (4 A + 4 B) fragments of 32 doubles
+    constexpr int stage_doubles = KB * 8 * 32;    // KB x (4 A + 4 B) fragments of 32 doubles
     const int n_tasks = a.n_chunks * Q * GP;
     const int nkb = KS / KB;                      // KS is a multiple of 8, KB of 1, 2 or 4
     // this thread's 16-byte piece of a stage (stage = KB x 8 fragments x 16 pieces <= NT pieces)
@@ -668,11 +692,15 @@ __device__ void top_product(const SubArgs& a, double* buf, int KB) {
             issue(kb + TOP_STAGES - 1);
             if (active) {
                 const double* st = buf + (size_t)(kb % TOP_STAGES) * stage_doubles;
+                const double* pa = st + (size_t)rt * KB * 32 + lane;
+                // B fragment staged as [kk][n]: lane = n*4 + kk reads element kk*8 + n
+                const double* pb = st + (size_t)(4 + gl) * KB * 32 + (lane & 3) * 8 + (lane >> 2);
+                double av[KB], bv[KB];
+#pragma unroll
+                for (int kl = 0; kl < KB; ++kl) { av[kl] = pa[kl * 32]; bv[kl] = pb[kl * 32]; }
+#pragma unroll
                 for (int kl = 0; kl < KB; ++kl) {
-                    const double av = st[(size_t)(rt * KB + kl) * 32 + lane];
-                    // B fragment staged as [kk][n]: lane = n*4 + kk reads element kk*8 + n
-                    const double bv = st[(size_t)((4 + gl) * KB + kl) * 32 + (lane & 3) * 8 + (lane >> 2)];
-                    if (kl & 1) dmma884(c10, c11, av, bv); else dmma884(c00, c01, av, bv);
+                    if (kl & 1) dmma884(c10, c11, av[kl], bv[kl]); else dmma884(c00, c01, av[kl], bv[kl]);
                 }
             }
         }
@@ -750,7 +778,8 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
         grid_barrier(a.bar, bar_target);
         top_assemble<NG>(a, 0);
         grid_barrier(a.bar, bar_target);
-        if (top_kb > 0) top_product<NG>(a, stage, top_kb); else top_product_direct<NG>(a);
+        if (top_kb == 4) top_product<NG, 4>(a, stage); else if (top_kb == 2) top_product<NG, 2>(a, stage);
+            else if (top_kb == 1) top_product<NG, 1>(a, stage); else top_product_direct<NG>(a);
         grid_barrier(a.bar, bar_target);
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int s = item % a.P, c = item / a.P;
@@ -833,7 +862,8 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
             top_assemble<NG>(a, n);
             grid_barrier(a.bar, bar_target);
             if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 5] += tn - tq; tq = tn; }
-            if (top_kb > 0) top_product<NG>(a, stage, top_kb); else top_product_direct<NG>(a);
+            if (top_kb == 4) top_product<NG, 4>(a, stage); else if (top_kb == 2) top_product<NG, 2>(a, stage);
+            else if (top_kb == 1) top_product<NG, 1>(a, stage); else top_product_direct<NG>(a);
             if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 6] += tn - tq; tq = tn; }
             grid_barrier(a.bar, bar_target);
             if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 7] += tn - tq; tq = tn; }
