@@ -644,71 +644,95 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc));
 }
 
-// J_top = S_top^-1 r_top as a block-level product: a block computes 32 rows x (4 groups of 8 problems) of one
-// chunk; per K block the four A row tiles and the four B fragments are staged once in shared memory by cp.async
-// (a TOP_STAGES-deep ring in the staging rows, which are idle between the sweeps) and read by all 16 warps:
-// warp = (row tile, group). 128 bytes of L2 traffic per MMA instead of 512.
-constexpr int TOP_STAGES = 4;
+// J_top = S_top^-1 r_top as a block-level product: a block computes RB 8-row tiles x (up to 4 groups of 8
+// problems) of one chunk. Per K block the RB A row tiles and the B fragments of the groups are staged once in
+// shared memory by cp.async (a ring in the staging rows, which are idle between the sweeps); warp w < RB owns row
+// tile w and feeds one A fragment to the MMAs of all groups. RB is chosen so that one round of blocks covers the
+// whole product (no tail), and the L2 traffic drops from 512 to 64 + 256/RB bytes per MMA.
 template <int NG, int KB>
-__device__ void top_product(const SubArgs& a, double* buf) {
+__device__ void top_product(const SubArgs& a, double* buf, int RB, int S) {
     constexpr int PC = 8 * NG;
-    constexpr int GP = (NG + 3) / 4;              // passes over the groups of a chunk, 4 at a time
-    const int Q = a.n_top_pad / 32, KS = a.n_top_pad / 4;
+    constexpr int GW = NG < 4 ? NG : 4;            // groups per pass
+    constexpr int GP = (NG + 3) / 4;               // passes over the groups of a chunk
+    const int RT = (a.n_top + 7) / 8, RTP = a.n_top_pad / 8, KS = a.n_top_pad / 4;
+    const int NB = (RT + RB - 1) / RB;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int rt = warp & 3, gl = warp >> 2;
-    constexpr int stage_doubles = KB * 8 * 32;    // KB x (4 A + 4 B) fragments of 32 doubles
-    const int n_tasks = a.n_chunks * Q * GP;
-    const int nkb = KS / KB;                      // KS is a multiple of 8, KB of 1, 2 or 4
-    // this thread's 16-byte piece of a stage (stage = KB x 8 fragments x 16 pieces <= NT pieces)
-    const bool loader = (int)threadIdx.x < stage_doubles / 2;
-    const int l_frag = threadIdx.x / 16, l_piece = threadIdx.x % 16;
-    const int l_which = l_frag / KB, l_kl = l_frag % KB;                 // which: 0..3 A row tiles, 4..7 B groups
+    const int stage_doubles = (RB + GW) * KB * 32;
+    const int pieces = stage_doubles / 2;          // 16-byte pieces per stage, at most 2 per thread
+    const int n_tasks = a.n_chunks * NB * GP;
+    const int nkb = KS / KB;                       // KS is a multiple of 8
     for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
-        const int gp = task % GP, q = (task / GP) % Q, c = task / (GP * Q);
-        const int g = 4 * gp + gl;
-        const bool active = g < NG;
-        const double* src0;
-        size_t src_step;                          // per K block
-        if (l_which < 4) {
-            src0 = a.SinvP + ((size_t)(4 * q + l_which) * KS + l_kl) * 32 + l_piece * 2;
-            src_step = (size_t)KB * 32;
-        } else {
-            const int gg = min(4 * gp + (l_which - 4), NG - 1);
-            src0 = a.rtop + ((size_t)c * a.n_top_pad + 4 * l_kl + (l_piece >> 2)) * PC + 8 * gg + (l_piece & 3) * 2;
-            src_step = (size_t)KB * 4 * PC;
+        const int gp = task % GP, nb = (task / GP) % NB, c = task / (GP * NB);
+        const int rt = nb * RB + warp;
+        const bool active = warp < RB && rt < RT;
+        // this thread's pieces of a stage: fragment f = piece / 16; f < RB*KB: A row tile f / KB, else B group
+        const double* src0[2]; size_t step[2]; bool have[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int i = threadIdx.x + j * NT;
+            have[j] = i < pieces;
+            const int frag = i / 16, piece = i % 16, which = frag / KB, kl = frag % KB;
+            if (which < RB) {
+                src0[j] = a.SinvP + ((size_t)min(nb * RB + which, RTP - 1) * KS + kl) * 32 + piece * 2;
+                step[j] = (size_t)KB * 32;
+            } else {
+                const int gg = min(4 * gp + (which - RB), NG - 1);
+                src0[j] = a.rtop + ((size_t)c * a.n_top_pad + 4 * kl + (piece >> 2)) * PC + 8 * gg + (piece & 3) * 2;
+                step[j] = (size_t)KB * 4 * PC;
+            }
         }
-        double* dst0 = buf + (size_t)threadIdx.x * 2;
+        // blocks walk K in rotated order so that the blocks sharing an operand do not ask L2 for the same lines
+        // at the same moment (the sum order differs per block but is fixed, so results stay deterministic)
+        const int rot = (int)(((unsigned)nb * 7u + (unsigned)c * 13u + (unsigned)gp * 5u) % (unsigned)nkb);
         auto issue = [&](int kb) {
-            if (loader && kb < nkb) cp_async16(dst0 + (size_t)(kb % TOP_STAGES) * stage_doubles, src0 + (size_t)kb * src_step);
+            if (kb < nkb) {
+                int ke = kb + rot; if (ke >= nkb) ke -= nkb;
+                double* dst = buf + (size_t)(kb % S) * stage_doubles + (size_t)threadIdx.x * 2;
+                if (have[0]) cp_async16(dst, src0[0] + (size_t)ke * step[0]);
+                if (have[1]) cp_async16(dst + 2 * NT, src0[1] + (size_t)ke * step[1]);
+            }
             asm volatile("cp.async.commit_group;");
         };
-        __syncthreads();                          // the ring is free (previous task / phase done)
+        __syncthreads();                           // the ring is free (previous task / phase done)
+        for (int k = 0; k < S - 1; ++k) issue(k);
+        double acc[GW][2];
 #pragma unroll
-        for (int k = 0; k < TOP_STAGES - 1; ++k) issue(k);
-        double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
+        for (int g = 0; g < GW; ++g) { acc[g][0] = 0.0; acc[g][1] = 0.0; }
         for (int kb = 0; kb < nkb; ++kb) {
-            asm volatile("cp.async.wait_group %0;" ::"n"(TOP_STAGES - 2));
-            __syncthreads();                      // stage kb has landed for everyone; stage kb-1 is no longer read
-            issue(kb + TOP_STAGES - 1);
+            if (S == 4) asm volatile("cp.async.wait_group 2;");
+            else if (S == 3) asm volatile("cp.async.wait_group 1;");
+            else asm volatile("cp.async.wait_group 0;");
+            __syncthreads();                       // stage kb has landed for everyone; stage kb-1 is no longer read
+            issue(kb + S - 1);
             if (active) {
-                const double* st = buf + (size_t)(kb % TOP_STAGES) * stage_doubles;
-                const double* pa = st + (size_t)rt * KB * 32 + lane;
+                const double* st = buf + (size_t)(kb % S) * stage_doubles;
+                const double* pa = st + (size_t)warp * KB * 32 + lane;
                 // B fragment staged as [kk][n]: lane = n*4 + kk reads element kk*8 + n
-                const double* pb = st + (size_t)(4 + gl) * KB * 32 + (lane & 3) * 8 + (lane >> 2);
-                double av[KB], bv[KB];
+                const double* pb = st + (size_t)RB * KB * 32 + (lane & 3) * 8 + (lane >> 2);
+                double av[KB];
 #pragma unroll
-                for (int kl = 0; kl < KB; ++kl) { av[kl] = pa[kl * 32]; bv[kl] = pb[kl * 32]; }
+                for (int kl = 0; kl < KB; ++kl) av[kl] = pa[kl * 32];
 #pragma unroll
                 for (int kl = 0; kl < KB; ++kl) {
-                    if (kl & 1) dmma884(c10, c11, av[kl], bv[kl]); else dmma884(c00, c01, av[kl], bv[kl]);
+                    double bv[GW];
+#pragma unroll
+                    for (int g = 0; g < GW; ++g) bv[g] = pb[(g * KB + kl) * 32];
+#pragma unroll
+                    for (int g = 0; g < GW; ++g) dmma884(acc[g][0], acc[g][1], av[kl], bv[g]);
                 }
             }
         }
         asm volatile("cp.async.wait_group 0;");
         if (active) {
-            const int row = 32 * q + 8 * rt + (lane >> 2);
-            double2* dst = reinterpret_cast<double2*>(a.jtop + ((size_t)c * a.n_top_pad + row) * PC + 8 * g + 2 * (lane & 3));
-            *dst = make_double2(c00 + c10, c01 + c11);
+            const int row = 8 * rt + (lane >> 2);
+#pragma unroll
+            for (int g = 0; g < GW; ++g) {
+                const int gg = 4 * gp + g;
+                if (gg < NG) {
+                    double2* dst = reinterpret_cast<double2*>(a.jtop + ((size_t)c * a.n_top_pad + row) * PC + 8 * gg + 2 * (lane & 3));
+                    *dst = make_double2(acc[g][0], acc[g][1]);
+                }
+            }
         }
     }
     __syncthreads();
@@ -751,11 +775,20 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
     const bool keep_z = n_items <= (int)gridDim.x;     // every block has at most one item: z stays in shared memory
     unsigned bar_target = 0;
     int cur_s = -1;
-    // K block of the staged top product: TOP_STAGES stages of KB x 2 KB must fit in the staging rows
-    const int stage_bytes = a.stage_rows * (PC + 2) * 8;
-    const int top_kb = stage_bytes >= TOP_STAGES * 4 * 2048 ? 4 : stage_bytes >= TOP_STAGES * 2 * 2048 ? 2
-                       : stage_bytes >= TOP_STAGES * 2048 ? 1 : 0;
-
+    // staged top product: RB row tiles per block so that one round of blocks covers it, K block KB and ring depth S
+    // so that the ring fits in the staging rows (at most two 16-byte pieces per thread and stage)
+    int top_rb = 0, top_kb = 0, top_s = 0;
+    if (a.n_top > 0) {
+        const int stage_bytes = a.stage_rows * (PC + 2) * 8;
+        const int GWr = NG < 4 ? NG : 4, GPr = (NG + 3) / 4;
+        const int per_chunk = max(1, (int)gridDim.x / (a.n_chunks * GPr));
+        top_rb = min(NWARPS, ((a.n_top + 7) / 8 + per_chunk - 1) / per_chunk);
+        for (int need = 3; need >= 2 && top_kb == 0; --need)
+            for (int kb = 4; kb >= 1 && top_kb == 0; kb >>= 1) {
+                const int sb = (top_rb + GWr) * kb * 256;
+                if (sb / 16 <= 2 * NT && need * sb <= stage_bytes) { top_kb = kb; top_s = min(4, stage_bytes / sb); }
+            }
+    }
     if (a.dbg_b) {
         // ---- debug: one solve J = S^-1 b through the plan
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -778,8 +811,8 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
         grid_barrier(a.bar, bar_target);
         top_assemble<NG>(a, 0);
         grid_barrier(a.bar, bar_target);
-        if (top_kb == 4) top_product<NG, 4>(a, stage); else if (top_kb == 2) top_product<NG, 2>(a, stage);
-            else if (top_kb == 1) top_product<NG, 1>(a, stage); else top_product_direct<NG>(a);
+        if (top_kb == 4) top_product<NG, 4>(a, stage, top_rb, top_s); else if (top_kb == 2) top_product<NG, 2>(a, stage, top_rb, top_s);
+            else if (top_kb == 1) top_product<NG, 1>(a, stage, top_rb, top_s); else top_product_direct<NG>(a);
         grid_barrier(a.bar, bar_target);
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int s = item % a.P, c = item / a.P;
@@ -862,8 +895,8 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
             top_assemble<NG>(a, n);
             grid_barrier(a.bar, bar_target);
             if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 5] += tn - tq; tq = tn; }
-            if (top_kb == 4) top_product<NG, 4>(a, stage); else if (top_kb == 2) top_product<NG, 2>(a, stage);
-            else if (top_kb == 1) top_product<NG, 1>(a, stage); else top_product_direct<NG>(a);
+            if (top_kb == 4) top_product<NG, 4>(a, stage, top_rb, top_s); else if (top_kb == 2) top_product<NG, 2>(a, stage, top_rb, top_s);
+            else if (top_kb == 1) top_product<NG, 1>(a, stage, top_rb, top_s); else top_product_direct<NG>(a);
             if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 6] += tn - tq; tq = tn; }
             grid_barrier(a.bar, bar_target);
             if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 7] += tn - tq; tq = tn; }
@@ -1066,12 +1099,28 @@ static int launch(JJHandle* h, SubState* st, SubArgs& a) {
         if (per_sm <= 0) { h->err = "subdomain: kernel does not fit on the device"; return JJ_EINVAL; }
         st->grid = sms * std::min(per_sm, 1);
     }
-    const int top_tasks = st->n_chunks * (st->n_top_pad / 32) * ((st->NG + 3) / 4);
+    // the staged top product sizes its row blocks to the grid: give it up to 18 blocks per chunk and group pass
+    const int top_tasks = st->n_chunks * ((st->NG + 3) / 4) * std::min(18, (st->n_top + 7) / 8);
     int want = std::max(st->P * st->n_chunks, top_tasks);
     const char* env = getenv("JJ_SUB_GRID");
     int grid = std::min(st->grid, std::max(1, want));
     if (env && atoi(env) > 0) grid = std::min(st->grid, atoi(env));
     SCK(cudaMemsetAsync(st->bar, 0, 256, h->stream));
+    if (st->n_top > 0 && !getenv("JJ_SUB_NO_L2_WINDOW")) {
+        // keep the packed Schur inverse resident in L2: it is re-read by every block once per time step while
+        // the state (hundreds of MB per step) streams through the same cache
+        static bool limit_set = false;
+        if (!limit_set) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)32 << 20); limit_set = true; }
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof(attr));
+        attr.accessPolicyWindow.base_ptr = (void*)st->SinvP;
+        attr.accessPolicyWindow.num_bytes = (size_t)st->n_top_pad * st->n_top_pad * sizeof(double);
+        attr.accessPolicyWindow.hitRatio = 1.0f;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+        cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+        cudaGetLastError();
+    }
     void* params[] = {(void*)&a};
     SCK(cudaLaunchCooperativeKernel((const void*)k, dim3(grid), dim3(NT), params, st->smem_bytes, h->stream));
     h->launches++;
