@@ -465,15 +465,27 @@ int jj_set_problem(JJHandle* h, int32_t W, double dt, uint64_t seed, int64_t pro
     REQUIRE(W > 0 && dt > 0, JJ_EINVAL, "set_problem: W and dt must be positive");
     REQUIRE(problem_offset % 4 == 0, JJ_EINVAL, "set_problem: problem_offset must be a multiple of 4");
     REQUIRE(engine >= 0 && engine <= 3, JJ_EINVAL, "set_problem: unknown engine");
-    free_problem(h);
+    // same problem count as before (annealing loops, repeated compute() calls on a cached engine): keep the state
+    // arrays of all engines and only reset them; cudaMalloc/cudaFree of ~10 large arrays costs tens of milliseconds
+    const bool same = h->have_problem && h->W == W && h->th1 && h->th2 && h->x && !h->thetas;
+    size_t nj = (size_t)h->cir.Nj * ((W + 3) / 4 * 4) * sizeof(double), nf = (size_t)h->cir.Nf * ((W + 3) / 4 * 4) * sizeof(double);
+    int rc;
+    if (same) {
+        for (int i = 0; i < 4; ++i) free_source(h, h->src[i]);
+        dev_free(h, h->noise_buf, h->noise_cap); h->noise_buf = nullptr; h->noise_cap = 0; h->noise_K = 0;
+        dev_free(h, h->th_out, (size_t)h->n_th_planes * nj); dev_free(h, h->I_out, (size_t)h->n_I_planes * nj);
+        h->th_out = h->I_out = nullptr; h->n_th_planes = h->n_I_planes = 0;
+    } else {
+        free_problem(h);
+    }
     h->W = W; h->Wp = (W + 3) / 4 * 4; h->dt = dt; h->seed = seed; h->problem_offset = problem_offset;
     h->engine_req = engine;
-    size_t nj = (size_t)h->cir.Nj * h->Wp * sizeof(double), nf = (size_t)h->cir.Nf * h->Wp * sizeof(double);
-    int rc;
-    if ((rc = dev_alloc(h, (void**)&h->th1, nj))) return rc;
-    if ((rc = dev_alloc(h, (void**)&h->th2, nj))) return rc;
-    if ((rc = dev_alloc(h, (void**)&h->x, nj))) return rc;
-    if ((rc = dev_alloc(h, (void**)&h->v, nf))) return rc;
+    if (!same) {
+        if ((rc = dev_alloc(h, (void**)&h->th1, nj))) return rc;
+        if ((rc = dev_alloc(h, (void**)&h->th2, nj))) return rc;
+        if ((rc = dev_alloc(h, (void**)&h->x, nj))) return rc;
+        if ((rc = dev_alloc(h, (void**)&h->v, nf))) return rc;
+    }
     CK(cudaMemsetAsync(h->th1, 0, nj, h->stream));
     CK(cudaMemsetAsync(h->th2, 0, nj, h->stream));
     CK(cudaMemsetAsync(h->x, 0, nj, h->stream));

@@ -144,7 +144,7 @@ def classify_source(x, N, W, Nt, zero_if_allclose=True):
     timedep = arr.ndim > 0 and arr.shape[-1] > 1     # reference: _is_timedep
     if not timedep:
         s0 = full[:, :, 0]
-        if zero_if_allclose and np.allclose(s0, 0):
+        if zero_if_allclose and np.allclose(a3[:, :, 0], 0):      # same values as s0, without the broadcast copies
             return SourceSpec(ZERO, N, W, Nt)
         # exploit broadcast structure first (exact), then a numerical rank-one test
         if a3.shape[0] == 1:
