@@ -76,6 +76,7 @@ struct SubArgs {
     int* flag;
     const double* dbg_b; double* dbg_J;   // debug solve: canonical [Nf][Wp], permuted faces
     long long* prof;                       // optional per-block cycle counters [block][8]
+    int dbg;                               // timing experiments only (JJ_SUB_DEBUG): 1 no MMA in the top product, 2 no loads
 };
 
 struct SubState {
@@ -738,6 +739,111 @@ __device__ void top_product(const SubArgs& a, double* buf, int RB, int S) {
     __syncthreads();
 }
 
+// The same product with the K range of every stage split over the warps: warp = (row tile, K slot), KQ K slots per
+// row tile, one k-step per warp and stage, so RB*KQ (up to 16) warps issue MMAs and all four FP64 tensor pipes of
+// the SM are busy even when a block has only a few row tiles. The KQ partial sums of a row tile meet in shared
+// memory at the end and are added in a fixed order.
+template <int NG>
+__device__ void top_product_ksplit(const SubArgs& a, double* buf, int RB, int KQ, int S) {
+    constexpr int PC = 8 * NG;
+    constexpr int GW = NG < 4 ? NG : 4;
+    constexpr int GP = (NG + 3) / 4;
+    const int KB = KQ;
+    const int RT = (a.n_top + 7) / 8, RTP = a.n_top_pad / 8, KS = a.n_top_pad / 4;
+    const int NB = (RT + RB - 1) / RB;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rtl = warp / KQ, kq = warp % KQ;
+    const int stage_doubles = (RB + GW) * KB * 32;
+    const int pieces = stage_doubles / 2;
+    const int n_tasks = a.n_chunks * NB * GP;
+    const int nkb = KS / KB;
+    for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+        const int gp = task % GP, nb = (task / GP) % NB, c = task / (GP * NB);
+        const int rt = nb * RB + rtl;
+        const bool active = rtl < RB && rt < RT;
+        const double* src0[2]; size_t step[2]; bool have[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int i = threadIdx.x + j * NT;
+            have[j] = i < pieces;
+            const int frag = i / 16, piece = i % 16, which = frag / KB, kl = frag % KB;
+            if (which < RB) {
+                src0[j] = a.SinvP + ((size_t)min(nb * RB + which, RTP - 1) * KS + kl) * 32 + piece * 2;
+                step[j] = (size_t)KB * 32;
+            } else {
+                const int gg = min(4 * gp + (which - RB), NG - 1);
+                src0[j] = a.rtop + ((size_t)c * a.n_top_pad + 4 * kl + (piece >> 2)) * PC + 8 * gg + (piece & 3) * 2;
+                step[j] = (size_t)KB * 4 * PC;
+            }
+        }
+        // running source pointers and ring slots: the per-iteration bookkeeping is a handful of instructions
+        const double* sp0 = src0[0]; const double* sp1 = src0[1];
+        int issued = 0, islot = 0;
+        auto issue = [&]() {
+            if (issued < nkb) {
+                double* dst = buf + (size_t)islot * stage_doubles + (size_t)threadIdx.x * 2;
+                if (have[0]) cp_async16(dst, sp0);
+                if (have[1]) cp_async16(dst + 2 * NT, sp1);
+                sp0 += step[0]; sp1 += step[1];
+                ++issued;
+                if (++islot == S) islot = 0;
+            }
+            asm volatile("cp.async.commit_group;");
+        };
+        __syncthreads();                           // the ring is free (previous task / phase done)
+        for (int k = 0; k < S - 1; ++k) issue();
+        double acc[GW][2];
+#pragma unroll
+        for (int g = 0; g < GW; ++g) { acc[g][0] = 0.0; acc[g][1] = 0.0; }
+        const int a_off = (rtl * KB + kq) * 32 + lane;
+        const int b_off = (RB * KB + kq) * 32 + (lane & 3) * 8 + (lane >> 2);    // B staged as [kk][n]; group g: + g*KB*32
+        const double* st = buf;
+        int cslot = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+            if (S == 4) asm volatile("cp.async.wait_group 2;");
+            else if (S == 3) asm volatile("cp.async.wait_group 1;");
+            else asm volatile("cp.async.wait_group 0;");
+            __syncthreads();
+            issue();
+            if (active) {
+                const double av = st[a_off];
+                double bv[GW];
+#pragma unroll
+                for (int g = 0; g < GW; ++g) bv[g] = st[b_off + g * KB * 32];
+#pragma unroll
+                for (int g = 0; g < GW; ++g) dmma884(acc[g][0], acc[g][1], av, bv[g]);
+            }
+            st += stage_doubles;
+            if (++cslot == S) { cslot = 0; st = buf; }
+        }
+        asm volatile("cp.async.wait_group 0;");
+        __syncthreads();                           // everyone is done with the ring: reuse it for the partial sums
+        if (active) {
+#pragma unroll
+            for (int g = 0; g < GW; ++g)
+                *reinterpret_cast<double2*>(buf + ((size_t)(warp * GW + g) * 32 + lane) * 2) = make_double2(acc[g][0], acc[g][1]);
+        }
+        __syncthreads();
+        if (active && kq == 0) {
+            const int row = 8 * rt + (lane >> 2);
+#pragma unroll
+            for (int g = 0; g < GW; ++g) {
+                const int gg = 4 * gp + g;
+                if (gg < NG) {
+                    double2 sum = make_double2(0.0, 0.0);
+                    for (int k2 = 0; k2 < KQ; ++k2) {
+                        const double2 part = *reinterpret_cast<const double2*>(buf + ((size_t)((warp + k2) * GW + g) * 32 + lane) * 2);
+                        sum.x += part.x; sum.y += part.y;
+                    }
+                    double2* dst = reinterpret_cast<double2*>(a.jtop + ((size_t)c * a.n_top_pad + row) * PC + 8 * gg + 2 * (lane & 3));
+                    *dst = sum;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
 template <int NG>
 __device__ __forceinline__ void load_prog(const SubArgs& a, int s, ProgSmem& ps, int* aux) {
     const SubProgDev p = a.prog[s];
@@ -777,7 +883,7 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
     int cur_s = -1;
     // staged top product: RB row tiles per block so that one round of blocks covers it, K block KB and ring depth S
     // so that the ring fits in the staging rows (at most two 16-byte pieces per thread and stage)
-    int top_rb = 0, top_kb = 0, top_s = 0;
+    int top_rb = 0, top_kb = 0, top_s = 0, top_kq = 0;
     if (a.n_top > 0) {
         const int stage_bytes = a.stage_rows * (PC + 2) * 8;
         const int GWr = NG < 4 ? NG : 4, GPr = (NG + 3) / 4;
@@ -788,6 +894,15 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
                 const int sb = (top_rb + GWr) * kb * 256;
                 if (sb / 16 <= 2 * NT && need * sb <= stage_bytes) { top_kb = kb; top_s = min(4, stage_bytes / sb); }
             }
+        // few row tiles per block: split K over the idle warps (KQ must divide the number of k-steps)
+        int kq = NWARPS / top_rb;
+        while (kq > 1 && (a.n_top_pad / 4) % kq != 0) --kq;
+        if (kq >= 2 && top_kb > 0) {
+            const int sb = (top_rb + GWr) * kq * 256;
+            if (sb / 16 <= 2 * NT && 3 * sb <= stage_bytes && NWARPS * GWr * 64 * 8 <= stage_bytes) {
+                top_kq = kq; top_s = min(4, stage_bytes / sb);
+            }
+        }
     }
     if (a.dbg_b) {
         // ---- debug: one solve J = S^-1 b through the plan
@@ -811,7 +926,8 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
         grid_barrier(a.bar, bar_target);
         top_assemble<NG>(a, 0);
         grid_barrier(a.bar, bar_target);
-        if (top_kb == 4) top_product<NG, 4>(a, stage, top_rb, top_s); else if (top_kb == 2) top_product<NG, 2>(a, stage, top_rb, top_s);
+        if (top_kq >= 2) top_product_ksplit<NG>(a, stage, top_rb, top_kq, top_s);
+            else if (top_kb == 4) top_product<NG, 4>(a, stage, top_rb, top_s); else if (top_kb == 2) top_product<NG, 2>(a, stage, top_rb, top_s);
             else if (top_kb == 1) top_product<NG, 1>(a, stage, top_rb, top_s); else top_product_direct<NG>(a);
         grid_barrier(a.bar, bar_target);
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -895,7 +1011,8 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
             top_assemble<NG>(a, n);
             grid_barrier(a.bar, bar_target);
             if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 5] += tn - tq; tq = tn; }
-            if (top_kb == 4) top_product<NG, 4>(a, stage, top_rb, top_s); else if (top_kb == 2) top_product<NG, 2>(a, stage, top_rb, top_s);
+            if (top_kq >= 2) top_product_ksplit<NG>(a, stage, top_rb, top_kq, top_s);
+            else if (top_kb == 4) top_product<NG, 4>(a, stage, top_rb, top_s); else if (top_kb == 2) top_product<NG, 2>(a, stage, top_rb, top_s);
             else if (top_kb == 1) top_product<NG, 1>(a, stage, top_rb, top_s); else top_product_direct<NG>(a);
             if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 6] += tn - tq; tq = tn; }
             grid_barrier(a.bar, bar_target);
@@ -1079,6 +1196,7 @@ static void fill_args(JJHandle* h, SubState* st, SubArgs& a) {
     a.rth = st->rth; a.rx = st->rx; a.th1 = h->th1; a.th2 = h->th2;
     a.zloc = st->zloc; a.ctop = st->ctop; a.rtop = st->rtop; a.jtop = st->jtop; a.bar = st->bar;
     a.snap_th = h->th_out; a.snap_I = h->I_out; a.flag = h->flag_d;
+    { const char* d = getenv("JJ_SUB_DEBUG"); a.dbg = d ? atoi(d) : 0; }
 }
 
 static int launch(JJHandle* h, SubState* st, SubArgs& a) {
