@@ -761,19 +761,24 @@ __device__ void top_product_ksplit(const SubArgs& a, double* buf, int RB, int KQ
         const int gp = task % GP, nb = (task / GP) % NB, c = task / (GP * NB);
         const int rt = nb * RB + rtl;
         const bool active = rtl < RB && rt < RT;
-        const double* src0[2]; size_t step[2]; bool have[2];
+        // B fragments are staged as [kk][n ^ 4*(kk>>1)]: a half warp (n = 0..3 or 4..7, kk = 0..3) then reads 16
+        // doubles that fall into 16 different 8-byte banks
+        const double* src0[2]; size_t step[2]; bool have[2]; int dofs[2];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int i = threadIdx.x + j * NT;
             have[j] = i < pieces;
             const int frag = i / 16, piece = i % 16, which = frag / KB, kl = frag % KB;
+            dofs[j] = i * 2;
             if (which < RB) {
                 src0[j] = a.SinvP + ((size_t)min(nb * RB + which, RTP - 1) * KS + kl) * 32 + piece * 2;
                 step[j] = (size_t)KB * 32;
             } else {
                 const int gg = min(4 * gp + (which - RB), NG - 1);
-                src0[j] = a.rtop + ((size_t)c * a.n_top_pad + 4 * kl + (piece >> 2)) * PC + 8 * gg + (piece & 3) * 2;
+                const int kk = piece >> 2, n2 = (piece & 3) * 2;
+                src0[j] = a.rtop + ((size_t)c * a.n_top_pad + 4 * kl + kk) * PC + 8 * gg + n2;
                 step[j] = (size_t)KB * 4 * PC;
+                dofs[j] = frag * 32 + kk * 8 + (n2 ^ ((kk >> 1) << 2));
             }
         }
         // running source pointers and ring slots: the per-iteration bookkeeping is a handful of instructions
@@ -781,9 +786,9 @@ __device__ void top_product_ksplit(const SubArgs& a, double* buf, int RB, int KQ
         int issued = 0, islot = 0;
         auto issue = [&]() {
             if (issued < nkb) {
-                double* dst = buf + (size_t)islot * stage_doubles + (size_t)threadIdx.x * 2;
-                if (have[0]) cp_async16(dst, sp0);
-                if (have[1]) cp_async16(dst + 2 * NT, sp1);
+                double* dst = buf + (size_t)islot * stage_doubles;
+                if (have[0]) cp_async16(dst + dofs[0], sp0);
+                if (have[1]) cp_async16(dst + dofs[1], sp1);
                 sp0 += step[0]; sp1 += step[1];
                 ++issued;
                 if (++islot == S) islot = 0;
@@ -796,7 +801,7 @@ __device__ void top_product_ksplit(const SubArgs& a, double* buf, int RB, int KQ
 #pragma unroll
         for (int g = 0; g < GW; ++g) { acc[g][0] = 0.0; acc[g][1] = 0.0; }
         const int a_off = (rtl * KB + kq) * 32 + lane;
-        const int b_off = (RB * KB + kq) * 32 + (lane & 3) * 8 + (lane >> 2);    // B staged as [kk][n]; group g: + g*KB*32
+        const int b_off = (RB * KB + kq) * 32 + (lane & 3) * 8 + ((lane >> 2) ^ (((lane & 3) >> 1) << 2));   // group g: + g*KB*32
         const double* st = buf;
         int cslot = 0;
         for (int kb = 0; kb < nkb; ++kb) {
