@@ -172,6 +172,8 @@ def run_ours(args, rank, world, local_rank, dist):
     if os.path.isfile(tp):
         try:
             traffic = json.load(open(tp)).get(str(st["engine"]))
+            if isinstance(traffic, dict):      # measured DRAM bytes per time step (ncu) x time steps per launch
+                traffic = traffic["bytes_per_time_step"] * INNER
         except Exception:
             traffic = None
     eng.close()
