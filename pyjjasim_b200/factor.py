@@ -78,7 +78,7 @@ class Factor:
         return int(self.height.max()) if self.nb else 0
 
 
-def factorize(S, cx, cy, leaf_size=8, n_parts=None):
+def factorize(S, cx, cy, leaf_size=8, n_parts=None, part_weights=None):
     """n_parts: make the dissection tree with that many equal subtrees (ordering.nested_dissection); the part of
     every block is kept in F.blk_part (-1: separators above the parts)."""
     n = S.shape[0]
@@ -89,7 +89,7 @@ def factorize(S, cx, cy, leaf_size=8, n_parts=None):
         F.blk_part = None
     else:
         perm, bptr, height, depth, dom, F.blk_part = nested_dissection(S, cx, cy, leaf_size=leaf_size, return_tree=True,
-                                                                      n_parts=n_parts)
+                                                                      n_parts=n_parts, part_weights=part_weights)
     F.perm, F.bptr, F.height, F.depth, F.dom = perm, bptr, height, depth, dom
     Sp = scipy.sparse.csc_matrix(S)[perm][:, perm].tocsc()
     lu = scipy.sparse.linalg.splu(Sp, permc_spec="NATURAL", diag_pivot_thresh=0.0,

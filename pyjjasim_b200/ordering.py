@@ -19,7 +19,7 @@ import scipy.sparse
 __all__ = ["nested_dissection"]
 
 
-def nested_dissection(S, cx, cy, leaf_size=24, return_tree=False, n_parts=None):
+def nested_dissection(S, cx, cy, leaf_size=24, return_tree=False, n_parts=None, part_weights=None):
     """
     Parameters
     ----------
@@ -41,6 +41,8 @@ def nested_dissection(S, cx, cy, leaf_size=24, return_tree=False, n_parts=None):
     (a domain that still has to yield p parts is cut p//2 : p - p//2); with return_tree=True a sixth array
     block_part is returned: the index of the part a block belongs to, or -1 for the separators above the parts.
     (The subdomain engine wants one part per (SM, problem chunk) pair, which is rarely a power of two.)
+    part_weights : optional (n_parts,) relative sizes of the parts, in tree order (part k is the k-th leaf of the
+    cut tree from left to right); used to balance the WORK of the parts rather than their row counts.
     """
     n = S.shape[0]
     cx = np.asarray(cx, dtype=np.double)
@@ -53,11 +55,13 @@ def nested_dissection(S, cx, cy, leaf_size=24, return_tree=False, n_parts=None):
     blk_depth = np.zeros(n, dtype=np.int64)    # (depth, dom) of the block each unknown ends up in
     depth, n_dom = 0, 1
     parts = np.array([max(1, int(n_parts or 1))], dtype=np.int64)      # parts still to be made out of each domain
+    pos0 = np.zeros(1, dtype=np.int64)                                # tree-order position of a domain's first part
+    wcum = np.concatenate(([0.0], np.cumsum(np.ones(int(parts[0])) if part_weights is None
+                                              else np.asarray(part_weights, dtype=np.double))))
+    assert wcum.size == parts[0] + 1
     part_of = np.full(n, -1, dtype=np.int64)
-    n_made = 0
     if parts[0] == 1:
         part_of[:] = 0
-        n_made = 1
     while True:
         idx = np.flatnonzero(active)
         if idx.size == 0:
@@ -66,8 +70,7 @@ def nested_dissection(S, cx, cy, leaf_size=24, return_tree=False, n_parts=None):
         # a domain too small to be cut further becomes a single part
         small = (size <= leaf_size) & (parts > 1)
         for dm in np.flatnonzero(small):
-            part_of[idx[dom[idx] == dm]] = n_made
-            n_made += 1
+            part_of[idx[dom[idx] == dm]] = pos0[dm]
             parts[dm] = 1
         leaf_nodes = idx[size[dom[idx]] <= leaf_size]
         blk_depth[leaf_nodes] = depth
@@ -93,7 +96,8 @@ def nested_dissection(S, cx, cy, leaf_size=24, return_tree=False, n_parts=None):
         rank[order] = np.arange(idx.size) - start[sd]
         half = np.zeros(n, dtype=np.int8)
         p_lo = parts // 2
-        lo_count = np.where(parts > 1, np.rint(size * (p_lo / np.maximum(parts, 1))).astype(np.int64), (size + 1) // 2)
+        frac = (wcum[pos0 + p_lo] - wcum[pos0]) / np.maximum(wcum[pos0 + parts] - wcum[pos0], 1e-300)
+        lo_count = np.where(parts > 1, np.rint(size * frac).astype(np.int64), (size + 1) // 2)
         half[idx] = rank >= lo_count[d]
         # separator: unknowns of the lower half coupled to the upper half of the same subdomain
         both = active[ei] & active[ej]
@@ -107,18 +111,17 @@ def nested_dissection(S, cx, cy, leaf_size=24, return_tree=False, n_parts=None):
         new_parts = np.ones(2 * n_dom, dtype=np.int64)
         new_parts[0::2] = np.where(parts > 1, p_lo, 1)
         new_parts[1::2] = np.where(parts > 1, parts - p_lo, 1)
+        new_pos0 = np.zeros(2 * n_dom, dtype=np.int64)
+        new_pos0[0::2] = pos0
+        new_pos0[1::2] = np.where(parts > 1, pos0 + p_lo, pos0)
         fresh = np.zeros(2 * n_dom, dtype=bool)          # domains that just became a part of their own
         fresh[0::2] = (parts > 1) & (new_parts[0::2] == 1)
         fresh[1::2] = (parts > 1) & (new_parts[1::2] == 1)
         if fresh.any() and idx.size:
-            ids = np.full(2 * n_dom, -1, dtype=np.int64)
-            present = np.unique(dom[idx])
-            present = present[fresh[present]]
-            ids[present] = n_made + np.arange(present.size)
-            n_made += present.size
             sel = fresh[dom[idx]]
-            part_of[idx[sel]] = ids[dom[idx[sel]]]
+            part_of[idx[sel]] = new_pos0[dom[idx[sel]]]
         parts = new_parts
+        pos0 = new_pos0
         n_dom *= 2
         depth += 1
 
@@ -154,6 +157,13 @@ def nested_dissection(S, cx, cy, leaf_size=24, return_tree=False, n_parts=None):
     if return_tree:
         first = perm[block_ptr[:-1]] if nb else np.zeros(0, dtype=np.int64)
         if n_parts is not None:
-            return perm, block_ptr, height, b_depth.astype(np.int64), dom[first], part_of[first]
+            # parts are numbered by tree position; positions that stayed empty (tiny domains) are squeezed out
+            bp = part_of[first]
+            used = np.unique(bp[bp >= 0])
+            if used.size and used.size != used[-1] + 1:
+                remap = np.full(int(used[-1]) + 1, -1, dtype=np.int64)
+                remap[used] = np.arange(used.size)
+                bp = np.where(bp >= 0, remap[np.maximum(bp, 0)], -1)
+            return perm, block_ptr, height, b_depth.astype(np.int64), dom[first], bp
         return perm, block_ptr, height, b_depth.astype(np.int64), dom[first]
     return perm, block_ptr, height
