@@ -33,7 +33,7 @@ namespace {
 
 constexpr int NT = 512;
 constexpr int NWARPS = NT / 32;
-constexpr int RING = 8;
+constexpr int RING = 4;            // stream steps per ring block; every tile is padded to a multiple of it
 constexpr int STEP_BYTES = 320;
 constexpr double TWO_PI = 6.283185307179586;
 constexpr int PROF_SLOTS = 8 + 48;     // phase counters + per-level counters of the sweeps (JJ_SUB_PROF)
@@ -151,14 +151,14 @@ __device__ __forceinline__ void cursor_open(Cursor& cu, const ProgSmem& ps, int 
     const unsigned long long pol = policy_evict_last();
     cu.t0 = ps.wt[2 * idx]; cu.t1 = ps.wt[2 * idx + 1];
     cu.s = ps.ws[idx];
-    // ring slot of stream step s is s % RING; the stream buffer is padded by 2*RING steps
-    const int p = cu.s & (RING - 1);
-    const unsigned char* blk = ps.stream + (size_t)(cu.s - p) * STEP_BYTES;
+    // every tile is a whole number of ring blocks, so a warp's stream position is always block aligned; the
+    // stream buffer is padded by 2*RING steps
+    const unsigned char* blk = ps.stream + (size_t)cu.s * STEP_BYTES;
     cu.pA = blk + lane * 8;
     cu.pC = blk + 256 + lane * 2;
 #pragma unroll
     for (int k = 0; k < RING; ++k) {
-        const int off = (k + (k < p ? RING : 0)) * STEP_BYTES;
+        const int off = k * STEP_BYTES;
         asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(cu.ra[k]) : "l"(cu.pA + off), "l"(pol));
         asm volatile("ld.global.nc.L2::cache_hint.u16 %0, [%1], %2;" : "=r"(cu.rc[k]) : "l"(cu.pC + off), "l"(pol));
     }
@@ -177,46 +177,30 @@ __device__ __forceinline__ double lds_f64(unsigned addr) {
     return b;
 }
 
-// The stream steps of one tile for NGT of the NG problem groups. Ring slot K always holds a stream step
-// congruent to K (mod RING); it is refilled in place right after use, with immediate offsets from the block
-// pointers. All B fragments of a step are fetched before its MMAs issue. When a tile covers only one or two
-// groups, even and odd steps accumulate separately (two independent MMA chains per group instead of one).
+// The stream steps of one tile for NGT of the NG problem groups. A tile is a whole number of ring blocks of RING
+// steps (padded with zero steps by the host), so the loop has no per-step control flow: ring slot K holds step K of
+// the current block and is refilled in place, right after use, with step K of the next block (immediate offsets
+// from the block pointers). All B fragments of a step are fetched before its MMAs issue.
 template <int NG, int NGT>
 __device__ __forceinline__ void tile_steps(int nsteps, int& s, const unsigned char*& pA, const unsigned char*& pC,
                                            double (&ra)[RING], unsigned (&rc)[RING], unsigned vb, unsigned gx,
                                            double (&acc)[NG][2]) {
-    constexpr bool DUAL = NGT <= 2;
     const unsigned long long pol = policy_evict_last();
-    double alt[NGT][2];
+    for (int j = 0; j < nsteps; j += RING) {
 #pragma unroll
-    for (int g = 0; g < NGT; ++g) { alt[g][0] = 0.0; alt[g][1] = 0.0; }
-#define JJ_SLOT(K)                                                                                     \
-    case K: {                                                                                          \
-        if (j >= nsteps) break;                                                                        \
-        const unsigned a0 = vb + ((rc[K] ^ gx) << 3);                                                  \
-        double b_[NGT];                                                                                \
-        _Pragma("unroll") for (int g = 0; g < NGT; ++g) b_[g] = lds_f64(a0 ^ (unsigned)(g << 6));      \
-        _Pragma("unroll") for (int g = 0; g < NGT; ++g) {                                              \
-            if (DUAL && ((K) & 1)) dmma884(alt[g][0], alt[g][1], ra[K], b_[g]);                        \
-            else dmma884(acc[g][0], acc[g][1], ra[K], b_[g]);                                          \
-        }                                                                                              \
-        asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1+%2], %3;" : "=d"(ra[K]) : "l"(pA), "n"((RING + (K)) * STEP_BYTES), "l"(pol)); \
-        asm volatile("ld.global.nc.L2::cache_hint.u16 %0, [%1+%2], %3;" : "=r"(rc[K]) : "l"(pC), "n"((RING + (K)) * STEP_BYTES), "l"(pol)); \
-        ++j;                                                                                           \
-    }
-    for (int j = 0; j < nsteps;) {
-        const int j0 = j;
-        switch (s & (RING - 1)) {
-            JJ_SLOT(0) JJ_SLOT(1) JJ_SLOT(2) JJ_SLOT(3) JJ_SLOT(4) JJ_SLOT(5) JJ_SLOT(6) JJ_SLOT(7)
+        for (int K = 0; K < RING; ++K) {
+            const unsigned a0 = vb + ((rc[K] ^ gx) << 3);
+            double b_[NGT];
+#pragma unroll
+            for (int g = 0; g < NGT; ++g) b_[g] = lds_f64(a0 ^ (unsigned)(g << 6));
+#pragma unroll
+            for (int g = 0; g < NGT; ++g) dmma884(acc[g][0], acc[g][1], ra[K], b_[g]);
+            asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(ra[K]) : "l"(pA + (RING + K) * STEP_BYTES), "l"(pol));
+            asm volatile("ld.global.nc.L2::cache_hint.u16 %0, [%1], %2;" : "=r"(rc[K]) : "l"(pC + (RING + K) * STEP_BYTES), "l"(pol));
         }
-        s += j - j0;
-        if ((s & (RING - 1)) == 0) { pA += RING * STEP_BYTES; pC += RING * STEP_BYTES; }
+        pA += RING * STEP_BYTES; pC += RING * STEP_BYTES;
     }
-#undef JJ_SLOT
-    if (DUAL) {
-#pragma unroll
-        for (int g = 0; g < NGT; ++g) { acc[g][0] += alt[g][0]; acc[g][1] += alt[g][1]; }
-    }
+    s += nsteps;
 }
 
 __device__ __forceinline__ int bcast0(int x) { return __shfl_sync(0xffffffffu, x, 0); }

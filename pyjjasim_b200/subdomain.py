@@ -35,6 +35,8 @@ from .factor import TILE_SELF, TILE_STAGED, CHAIN_ROWS, STEP_BYTES, RES_WARPS, _
 
 __all__ = ["SubdomainPlan", "subdomain_plan", "apply_subdomain_plan_host", "elem_code"]
 
+RING_STEPS = 4          # the device walks a tile's stream in ring blocks of this many steps (csrc/jj_subdomain.cu: RING)
+
 
 def elem_code(row, NG):
     """Element offset (float64 units) of problem n = 0..7 of group 0 of shared-memory row `row`: a row is PC/4
@@ -53,7 +55,7 @@ class SubdomainPlan:
 def _tile_record(V, cols, NG):
     """320-byte stream steps of one tile: A fragment (lane = row*4 + kk) and element codes (lane = n*4 + kk)."""
     nr, nc = V.shape
-    st = (nc + 3) // 4
+    st = ((nc + 3) // 4 + RING_STEPS - 1) // RING_STEPS * RING_STEPS      # whole ring blocks (zero steps at the end)
     Vp = np.zeros((8, st * 4))
     Vp[:nr, :nc] = V
     cp = np.full(st * 4, cols[-1], dtype=np.int64)
