@@ -177,15 +177,28 @@ __device__ __forceinline__ double lds_f64(unsigned addr) {
     return b;
 }
 
-// The stream steps of one tile for NGT of the NG problem groups. A tile is a whole number of ring blocks of RING
-// steps (padded with zero steps by the host), so the loop has no per-step control flow: ring slot K holds step K of
-// the current block and is refilled in place, right after use, with step K of the next block (immediate offsets
-// from the block pointers). All B fragments of a step are fetched before its MMAs issue.
+// One tile for NGT of the NG problem groups: load the running sums (TILE_SELF) or start from zero, walk the
+// tile's stream, write the 8-row result (in place or into the staging rows). A tile is a whole number of ring
+// blocks of RING steps (padded with zero steps by the host), so the step loop has no per-step control flow: ring
+// slot K holds step K of the current block and is refilled in place, right after use, with step K of the next
+// block. All B fragments of a step are fetched before its MMAs issue. NGT is a template parameter so that none
+// of the per-group work is predicated.
 template <int NG, int NGT>
-__device__ __forceinline__ void tile_steps(int nsteps, int& s, const unsigned char*& pA, const unsigned char*& pC,
-                                           double (&ra)[RING], unsigned (&rc)[RING], unsigned vb, unsigned gx,
-                                           double (&acc)[NG][2]) {
-    const unsigned long long pol = policy_evict_last();
+__device__ __forceinline__ void tile_run(int nsteps, int flags, bool in_rows, int celem0, int row, int stage_off,
+                                         int kk, const unsigned char*& pA, const unsigned char*& pC,
+                                         double (&ra)[RING], unsigned (&rc)[RING], unsigned vb, unsigned gx,
+                                         unsigned long long pol, double* __restrict__ v, double* __restrict__ stage) {
+    constexpr int PC = 8 * NG;
+    double acc[NGT][2];
+#pragma unroll
+    for (int g = 0; g < NGT; ++g) { acc[g][0] = 0.0; acc[g][1] = 0.0; }
+    if ((flags & 1) && in_rows) {
+#pragma unroll
+        for (int g = 0; g < NGT; ++g) {
+            const double2 sv = *reinterpret_cast<const double2*>(v + (celem0 ^ (g << 3)));
+            acc[g][0] = sv.x; acc[g][1] = sv.y;
+        }
+    }
     for (int j = 0; j < nsteps; j += RING) {
 #pragma unroll
         for (int K = 0; K < RING; ++K) {
@@ -200,7 +213,20 @@ __device__ __forceinline__ void tile_steps(int nsteps, int& s, const unsigned ch
         }
         pA += RING * STEP_BYTES; pC += RING * STEP_BYTES;
     }
-    s += nsteps;
+    __syncwarp();                // every lane has read its operands before rows of this block are overwritten
+    if (in_rows) {
+        if (flags & 2) {
+            // staged: the row keeps the physical layout of its destination and carries the destination index
+            double* srow = stage + (size_t)stage_off * (PC + 2) - (size_t)row * PC;
+#pragma unroll
+            for (int g = 0; g < NGT; ++g) *reinterpret_cast<double2*>(srow + (celem0 ^ (g << 3))) = make_double2(acc[g][0], acc[g][1]);
+            if (kk == 0) reinterpret_cast<int*>(stage + (size_t)stage_off * (PC + 2) + PC)[0] = row;
+        } else {
+#pragma unroll
+            for (int g = 0; g < NGT; ++g) *reinterpret_cast<double2*>(v + (celem0 ^ (g << 3))) = make_double2(acc[g][0], acc[g][1]);
+        }
+    }
+    __syncwarp();
 }
 
 __device__ __forceinline__ int bcast0(int x) { return __shfl_sync(0xffffffffu, x, 0); }
@@ -213,6 +239,7 @@ __device__ void exec_level(const ProgSmem& ps, Cursor& cu, int level, int next_l
     constexpr int PC = 8 * NG;
     const int lane = threadIdx.x & 31;
     const unsigned vb = (unsigned)__cvta_generic_to_shared(v);      // 1 KB aligned: group g of an element is addr ^ (g << 6)
+    const unsigned long long pol = policy_evict_last();
     int s = bcast0(cu.s);
     const int t0 = bcast0(cu.t0), t1 = bcast0(cu.t1);
     const unsigned char* pA = cu.pA;
@@ -229,39 +256,17 @@ __device__ void exec_level(const ProgSmem& ps, Cursor& cu, int level, int next_l
         const int g0 = (hx >> 21) & 15, ng = ((hx >> 25) & 15) + 1;
         const int nsteps = hy & 0xffff, stage_off = (hy >> 16) & 0x7fff;
         const int row = row0 + r;
-        const int celem = velem<NG>(row, 2 * kk);          // this lane's two C values of group 0; group g: ^ (g << 3)
-        double acc[NG][2];
-#pragma unroll
-        for (int g = 0; g < NG; ++g) { acc[g][0] = 0.0; acc[g][1] = 0.0; }
-        if ((flags & 1) && r < nrows) {
-#pragma unroll
-            for (int g = 0; g < NG; ++g)
-                if (g < ng) {
-                    const double2 sv = *reinterpret_cast<const double2*>(v + (celem ^ ((g0 + g) << 3)));
-                    acc[g][0] = sv.x; acc[g][1] = sv.y;
-                }
-        }
+        // this lane's two C values of the tile's first group g0; group g0 + g: ^ (g << 3)
+        const int celem0 = velem<NG>(row, 2 * kk) ^ (g0 << 3);
         const unsigned gx = (unsigned)g0 << 3;
-        if (ng == NG) tile_steps<NG, NG>(nsteps, s, pA, pC, ra, rc, vb, gx, acc);
-        else if (NG >= 4 && ng == NG / 2) tile_steps<NG, (NG >= 4 ? NG / 2 : 1)>(nsteps, s, pA, pC, ra, rc, vb, gx, acc);
-        else if (NG >= 8 && ng == NG / 4) tile_steps<NG, (NG >= 8 ? NG / 4 : 1)>(nsteps, s, pA, pC, ra, rc, vb, gx, acc);
-        else tile_steps<NG, 1>(nsteps, s, pA, pC, ra, rc, vb, gx, acc);
-        __syncwarp();            // every lane has read its operands before rows of this block are overwritten
-        if (r < nrows) {
-            if (flags & 2) {
-                // staged: the row keeps the physical layout of its destination and carries the destination index
-                double* srow = stage + (size_t)(stage_off + r) * (PC + 2) - (size_t)row * PC;
-#pragma unroll
-                for (int g = 0; g < NG; ++g)
-                    if (g < ng) *reinterpret_cast<double2*>(srow + (celem ^ ((g0 + g) << 3))) = make_double2(acc[g][0], acc[g][1]);
-                if (kk == 0) reinterpret_cast<int*>(stage + (size_t)(stage_off + r) * (PC + 2) + PC)[0] = row;
-            } else {
-#pragma unroll
-                for (int g = 0; g < NG; ++g)
-                    if (g < ng) *reinterpret_cast<double2*>(v + (celem ^ ((g0 + g) << 3))) = make_double2(acc[g][0], acc[g][1]);
-            }
-        }
-        __syncwarp();
+        const bool in_rows = r < nrows;
+        if (ng == NG) tile_run<NG, NG>(nsteps, flags, in_rows, celem0, row, stage_off + r, kk, pA, pC, ra, rc, vb, gx, pol, v, stage);
+        else if (NG >= 4 && ng == NG / 2)
+            tile_run<NG, (NG >= 4 ? NG / 2 : 1)>(nsteps, flags, in_rows, celem0, row, stage_off + r, kk, pA, pC, ra, rc, vb, gx, pol, v, stage);
+        else if (NG >= 8 && ng == NG / 4)
+            tile_run<NG, (NG >= 8 ? NG / 4 : 1)>(nsteps, flags, in_rows, celem0, row, stage_off + r, kk, pA, pC, ra, rc, vb, gx, pol, v, stage);
+        else tile_run<NG, 1>(nsteps, flags, in_rows, celem0, row, stage_off + r, kk, pA, pC, ra, rc, vb, gx, pol, v, stage);
+        s += nsteps;
     }
     if (next_level >= 0) {
         // the streams are laid out warp-major inside a sweep: normally the next level simply continues this
