@@ -197,6 +197,19 @@ int jj_debug_resident_solve(JJHandle *h, const double *b, double *J);
 /* the same through the subdomain engine's cooperative kernel (requires a subdomain plan) */
 int jj_debug_subdomain_solve(JJHandle *h, const double *b, double *J);
 
+/* ---- the annealing caller of the path (reference: time_evolution.py:1070-1191, AnnealingProblem.compute) ----
+ * The reference re-enters compute() every `interval_steps` steps with theta(-2) := theta(-1), pulls every theta
+ * plane to the host, derives the vortex configurations there and adapts the temperatures. These three entry points
+ * keep the state and the stored planes on the device between intervals. */
+/* zero-velocity restart: theta(-2) := theta(-1) on the device (reference: time_evolution.py:1169-1171) */
+int jj_restart_at_rest(JJHandle *h);
+/* n = -A round(theta / 2 pi) of stored theta plane `plane` (-1: the current state theta(-1)); dst is (Nf, W) int32,
+ * faces in the PERMUTED order (reference: time_evolution.py:734-755, get_vortex_configuration) */
+int jj_vortex_configuration(JJHandle *h, int64_t plane, int32_t *dst);
+/* dst[w] = sum over faces and over consecutive planes p0 <= p < p0+n-1 of |n(p+1) - n(p)|: the numerator of the
+ * reference's vortex mobility (reference: time_evolution.py:1128-1133, get_vortex_mobility); exact integers */
+int jj_vortex_mobility(JJHandle *h, int64_t plane0, int64_t n_planes, int64_t *dst /* [W] */);
+
 typedef struct {
     int32_t engine;             /* engine actually used */
     int32_t cluster_size, tile_problems;

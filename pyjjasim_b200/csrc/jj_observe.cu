@@ -1,0 +1,154 @@
+// libjjstep.so - observables computed on the device from the stored theta planes, and the zero-velocity
+// restart, for the annealing caller of the stepping loop (reference: time_evolution.py:1142-1191):
+//   vortex configuration  n = -A round(theta / 2 pi)                        (reference: time_evolution.py:734-755)
+//   vortex mobility sums  sum_f sum_t |n_f(t+1) - n_f(t)| per problem        (reference: time_evolution.py:1128-1133)
+//   restart at rest       theta(-2) := theta(-1)                            (reference: time_evolution.py:1169-1171)
+// Everything here is integer arithmetic on rounded phases: results are exact, not approximate.
+#include <cmath>
+#include <cstring>
+
+#include "jj_host.h"
+
+using namespace jj;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+            return JJ_ECUDA;                                                                       \
+        }                                                                                          \
+    } while (0)
+
+#define REQUIRE(cond, code, msg)                                                                   \
+    do {                                                                                           \
+        if (!(cond)) { h->err = (msg); return (code); }                                            \
+    } while (0)
+
+namespace {
+
+constexpr int LANES = 32;     // problems per block (one 256-byte row segment per junction and warp)
+constexpr int ROWS = 8;       // faces in flight per block
+
+struct FaceView {
+    int Nj, Nf, Wp;
+    const int* face_ptr; const int* face_junc; const signed char* face_sign;
+};
+
+// vorticity of face f for problem w in one theta plane; the division is a true division and the rounding is
+// to nearest-even, like np.round(theta / (2.0 * np.pi))
+__device__ __forceinline__ int vorticity(const FaceView& c, const double* __restrict__ plane, int p0, int p1, int w) {
+    double acc = 0.0;
+    for (int p = p0; p < p1; ++p) {
+        const double th = plane[(size_t)c.face_junc[p] * c.Wp + w];
+        acc -= (double)c.face_sign[p] * rint(th / 6.283185307179586);
+    }
+    return (int)acc;
+}
+
+__global__ void __launch_bounds__(LANES * ROWS) k_vortex_configuration(const FaceView c, const double* __restrict__ plane,
+                                                                        int* __restrict__ out) {
+    const int w = blockIdx.x * LANES + threadIdx.x;
+    const int f = blockIdx.y * ROWS + threadIdx.y;
+    if (w >= c.Wp || f >= c.Nf) return;
+    out[(size_t)f * c.Wp + w] = vorticity(c, plane, c.face_ptr[f], c.face_ptr[f + 1], w);
+}
+
+// out[w] += sum over this block's faces and over consecutive planes of |n(t+1) - n(t)|
+__global__ void __launch_bounds__(LANES * ROWS) k_vortex_mobility(const FaceView c, const double* __restrict__ planes,
+                                                                   long long n_planes, unsigned long long* __restrict__ out) {
+    __shared__ unsigned long long part[ROWS][LANES];
+    const int w = blockIdx.x * LANES + threadIdx.x;
+    const size_t plane = (size_t)c.Nj * c.Wp;
+    unsigned long long acc = 0;
+    if (w < c.Wp) {
+        for (int f = blockIdx.y * ROWS + threadIdx.y; f < c.Nf; f += gridDim.y * ROWS) {
+            const int p0 = c.face_ptr[f], p1 = c.face_ptr[f + 1];
+            int prev = vorticity(c, planes, p0, p1, w);
+            for (long long t = 1; t < n_planes; ++t) {
+                const int cur = vorticity(c, planes + (size_t)t * plane, p0, p1, w);
+                acc += (unsigned long long)abs(cur - prev);
+                prev = cur;
+            }
+        }
+    }
+    part[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && w < c.Wp) {
+        unsigned long long s = 0;
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) s += part[r][threadIdx.x];
+        if (s) atomicAdd(out + w, s);       // integer sum: independent of the order of arrival
+    }
+}
+
+FaceView view(const JJHandle* h) {
+    FaceView c;
+    c.Nj = h->cir.Nj; c.Nf = h->cir.Nf; c.Wp = h->Wp;
+    c.face_ptr = h->cir.face_ptr; c.face_junc = h->cir.face_junc; c.face_sign = h->cir.face_sign;
+    return c;
+}
+
+}  // namespace
+
+extern "C" {
+
+int jj_restart_at_rest(JJHandle* h) {
+    CK(cudaSetDevice(h->device));
+    REQUIRE(h->have_problem && h->have_state, JJ_ESTATE, "restart_at_rest: problem/state not set");
+    REQUIRE(!h->thetas, JJ_EINVAL, "restart_at_rest: not available with dense voltage sources");
+    const size_t bytes = (size_t)h->cir.Nj * h->Wp * sizeof(double);
+    CK(cudaMemcpyAsync(h->th2, h->th1, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    return JJ_OK;
+}
+
+int jj_vortex_configuration(JJHandle* h, int64_t plane, int32_t* dst) {
+    CK(cudaSetDevice(h->device));
+    REQUIRE(h->have_problem, JJ_ESTATE, "vortex_configuration: problem not set");
+    REQUIRE(plane >= -1 && plane < h->n_th_planes, JJ_EINVAL, "vortex_configuration: theta plane out of range");
+    if (h->cir.Nf == 0) return JJ_OK;
+    const FaceView c = view(h);
+    const double* src = plane < 0 ? h->th1 : h->th_out + (size_t)plane * c.Nj * c.Wp;   // -1: the current state
+    int* buf = nullptr;
+    const size_t bytes = (size_t)c.Nf * c.Wp * sizeof(int);
+    int rc = dev_alloc(h, (void**)&buf, bytes);
+    if (rc) return rc;
+    dim3 grid((c.Wp + LANES - 1) / LANES, (c.Nf + ROWS - 1) / ROWS), block(LANES, ROWS);
+    k_vortex_configuration<<<grid, block, 0, h->stream>>>(c, src, buf);
+    h->launches++;
+    cudaError_t e = cudaMemcpy2DAsync(dst, (size_t)h->W * sizeof(int), buf, (size_t)c.Wp * sizeof(int),
+                                      (size_t)h->W * sizeof(int), c.Nf, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    dev_free(h, buf, bytes);
+    if (e != cudaSuccess) { h->err = std::string("vortex_configuration: ") + cudaGetErrorString(e); return JJ_ECUDA; }
+    return JJ_OK;
+}
+
+int jj_vortex_mobility(JJHandle* h, int64_t plane0, int64_t n_planes, int64_t* dst) {
+    CK(cudaSetDevice(h->device));
+    REQUIRE(h->have_problem, JJ_ESTATE, "vortex_mobility: problem not set");
+    REQUIRE(plane0 >= 0 && n_planes >= 0 && plane0 + n_planes <= h->n_th_planes, JJ_EINVAL,
+            "vortex_mobility: theta plane range out of bounds");
+    if (h->cir.Nf == 0 || n_planes < 2) { memset(dst, 0, (size_t)h->W * sizeof(int64_t)); return JJ_OK; }
+    const FaceView c = view(h);
+    unsigned long long* buf = nullptr;
+    const size_t bytes = (size_t)c.Wp * sizeof(unsigned long long);
+    int rc = dev_alloc(h, (void**)&buf, bytes);
+    if (rc) return rc;
+    cudaError_t e = cudaMemsetAsync(buf, 0, bytes, h->stream);
+    // enough blocks to fill the machine: problem strips x face slices
+    const int strips = (c.Wp + LANES - 1) / LANES;
+    int slices = (c.Nf + ROWS - 1) / ROWS;
+    const int want = (148 * 8 + strips - 1) / strips;
+    if (slices > want) slices = want;
+    dim3 grid(strips, slices), block(LANES, ROWS);
+    k_vortex_mobility<<<grid, block, 0, h->stream>>>(c, h->th_out + (size_t)plane0 * c.Nj * c.Wp, n_planes, buf);
+    h->launches++;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dst, buf, (size_t)h->W * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    dev_free(h, buf, bytes);
+    if (e != cudaSuccess) { h->err = std::string("vortex_mobility: ") + cudaGetErrorString(e); return JJ_ECUDA; }
+    return JJ_OK;
+}
+
+}  // extern "C"

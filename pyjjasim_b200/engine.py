@@ -279,6 +279,7 @@ def _centroids_from_matrix(circuit, A):
 
 
 _tables_cache = {}
+_engine_lock = threading.Lock()
 
 
 def _tables_for(circuit, dt, n_parts=None):
@@ -287,11 +288,16 @@ def _tables_for(circuit, dt, n_parts=None):
     key = (id(circuit), float(dt), hash(np.asarray(circuit._R()).tobytes()), hash(np.asarray(circuit._C()).tobytes()),
            hash(np.asarray(circuit._Ic()).tobytes()), hash(L.data.tobytes()) ^ hash(L.indices.tobytes()),
            os.environ.get("JJ_LEAF_SIZE", ""), n_parts)
-    hit = _tables_cache.get(id(circuit))
-    if hit is not None and hit[0] == key:
-        return hit[1]
+    with _engine_lock:
+        hit = _tables_cache.get(key)
+        if hit is not None:
+            return hit
     tab = CircuitTables(circuit, dt, n_parts=n_parts)
-    _tables_cache[id(circuit)] = (key, tab)
+    with _engine_lock:
+        # a few entries: an annealing schedule alternates between dt and dt / 2 on the same circuit
+        while len(_tables_cache) >= 4:
+            _tables_cache.pop(next(iter(_tables_cache)))
+        _tables_cache[key] = tab
     return tab
 
 
@@ -512,6 +518,27 @@ class DeviceEngine:
         J[self.tab.perm] = Jp
         return J
 
+    # --- annealing support (reference: time_evolution.py:1142-1191) ------------------------------
+    def restart_at_rest(self):
+        """theta(-2) := theta(-1) on the device (reference: time_evolution.py:1169-1171)."""
+        self._ck(self.lib.jj_restart_at_rest(self.h))
+
+    def vortex_configuration(self, plane=-1):
+        """n = -A round(theta / 2 pi) of a stored theta plane (-1: the current state), (Nf, W) int array in the
+        ORIGINAL face numbering (reference: time_evolution.py:734-755)."""
+        out = np.zeros((self.tab.Nf, self.W), dtype=np.int32)
+        self._ck(self.lib.jj_vortex_configuration(self.h, int(plane), _lib.i32(out)))
+        n = np.empty_like(out)
+        n[self.tab.perm] = out
+        return n.astype(int)
+
+    def vortex_mobility_sums(self, plane0, n_planes):
+        """(W,) integer sums over faces and consecutive stored planes of |n(t+1) - n(t)|
+        (numerator of the reference's get_vortex_mobility, time_evolution.py:1128-1133)."""
+        out = np.zeros(self.W, dtype=np.int64)
+        self._ck(self.lib.jj_vortex_mobility(self.h, int(plane0), int(n_planes), _lib.i64(out)))
+        return out
+
     def stats(self):
         s = _lib.JJStats()
         self._ck(self.lib.jj_stats(self.h, C.byref(s)))
@@ -545,6 +572,19 @@ def _classify_all(problem, tab):
     if raw is None:       # a reference-style problem object: use its stored inputs
         raw = dict(f=problem.external_flux, Is=problem.current_sources, Vs=problem.voltage_sources,
                    T=problem.temperature)
+    else:
+        # an input attribute replaced after construction (the reference's annealing loop assigns prob.temperature
+        # between compute() calls, time_evolution.py:1166): the reference reads the new attribute, with the
+        # time-dependence flag frozen at construction - a "constant" input is sliced at step 0 once (:509-519)
+        raw = dict(raw)
+        kept = getattr(problem, "_kept_sources", {})
+        for name, attr, flag in (("f", "external_flux", "_f_is_timedep"), ("Is", "current_sources", "_Is_is_timedep"),
+                                 ("Vs", "voltage_sources", "_Vs_is_timedep"), ("T", "temperature", "_T_is_timedep")):
+            cur = getattr(problem, attr)
+            if name in kept and cur is not kept[name]:
+                if not getattr(problem, flag):
+                    cur = np.asarray(cur(0))[..., None] if callable(cur) else np.asarray(cur)[:, :, 0:1]
+                raw[name] = cur
     specs = dict(Is=classify_source(raw["Is"], Nj, W, Nt), f=classify_source(raw["f"], Nf, W, Nt),
                  Vs=classify_source(raw["Vs"], Nj, W, Nt),
                  T=nonnegative_factors(classify_source(raw["T"], Nj, W, Nt)))
@@ -568,7 +608,6 @@ _WHICH = dict(Is=_lib.JJ_SRC_IS, f=_lib.JJ_SRC_F, Vs=_lib.JJ_SRC_VS, T=_lib.JJ_S
 
 
 _engine_cache = {}           # (device) -> (key, DeviceEngine): circuit, solver and plan stay uploaded between compute() calls
-_engine_lock = threading.Lock()
 
 
 def _engine_for(tab, cpr, dev, W, engine_kind):
@@ -613,6 +652,30 @@ def _release_engine(dev, key, eng, ok):
         old[1].close()
 
 
+def _setup_sources(eng, specs, sh, tab):
+    """Declare the device form of each input and upload the parts that do not change with time."""
+    for name, s in specs.items():
+        which = _WHICH[name]
+        if s.kind == ZERO:
+            eng.set_source(which, _lib.JJ_KIND_ZERO, True)
+            continue
+        if s.kind == RANK1:
+            base = s.base
+            if name == "T":
+                base = np.sqrt(2.0 * s.base * tab.Rv)
+            elif name == "f":
+                base = s.base[tab.perm]
+            static = s.static and name != "Vs"
+            eng.set_source(which, _lib.JJ_KIND_RANK1, static, base)
+            if static:
+                amp = sh.amp(name, 0, 1)
+                eng.upload_source(which, 0, np.sqrt(amp) if name == "T" else amp)
+        else:
+            eng.set_source(which, _lib.JJ_KIND_DENSE, s.static)
+            if s.static:
+                eng.upload_source(which, 0, _dense_for_device(name, sh.dense(name, 0, 1), tab))
+
+
 def _run_shard(problem, tab, specs, dev, w0, w1, th_mask, I_mask, th_host, I_host, engine_kind, stats_out):
     """Integrate problems [w0, w1) on one device and write stored planes into th_host / I_host
     (plane-major (n_planes + 2, Nj, W) arrays, planes 0 and 1 are the initial conditions)."""
@@ -628,26 +691,7 @@ def _run_shard(problem, tab, specs, dev, w0, w1, th_mask, I_mask, th_host, I_hos
         replay = getattr(problem, "noise_replay", None)
         # static parts
         vs_cum = np.zeros(W)          # running sum of Vs amplitude * dt (rank-one voltage sources)
-        for name, s in specs.items():
-            which = _WHICH[name]
-            if s.kind == ZERO:
-                eng.set_source(which, _lib.JJ_KIND_ZERO, True)
-                continue
-            if s.kind == RANK1:
-                base = s.base
-                if name == "T":
-                    base = np.sqrt(2.0 * s.base * tab.Rv)
-                elif name == "f":
-                    base = s.base[tab.perm]
-                static = s.static and name != "Vs"
-                eng.set_source(which, _lib.JJ_KIND_RANK1, static, base)
-                if static:
-                    amp = sh.amp(name, 0, 1)
-                    eng.upload_source(which, 0, np.sqrt(amp) if name == "T" else amp)
-            else:
-                eng.set_source(which, _lib.JJ_KIND_DENSE, s.static)
-                if s.static:
-                    eng.upload_source(which, 0, _dense_for_device(name, sh.dense(name, 0, 1), tab))
+        _setup_sources(eng, specs, sh, tab)
         K = _chunk_length(specs, tab, W, Nt, replay is not None)
         th_idx = np.cumsum(th_mask) - 1      # plane index (without the +2 offset) of each stored step
         I_idx = np.cumsum(I_mask) - 1
@@ -782,6 +826,143 @@ def device_time_evolution_core(problem, th_store_mask, I_store_mask, engine=None
         th_host, I_host = th_host[:, :, shard[0]:shard[1]], I_host[:, :, shard[0]:shard[1]]
     # (plane, Nj, W) -> (Nj, W, plane) views, the reference's layout (quirk Q7)
     return np.moveaxis(th_host, 0, 2), np.moveaxis(I_host, 0, 2)
+
+
+def _engine_kind(engine):
+    if engine is None:
+        engine = {"auto": _lib.JJ_ENGINE_AUTO, "streaming": _lib.JJ_ENGINE_STREAMING,
+                  "resident": _lib.JJ_ENGINE_RESIDENT,
+                  "subdomain": _lib.JJ_ENGINE_SUBDOMAIN}[os.environ.get("JJ_ENGINE", "auto")]
+    return engine
+
+
+def _n_parts_for(circuit, W_dev, device, engine):
+    if os.environ.get("JJ_ENGINE", "auto") in ("auto", "subdomain") and not os.environ.get("JJ_SUBDOMAIN") \
+            and engine in (None, _lib.JJ_ENGINE_AUTO, _lib.JJ_ENGINE_SUBDOMAIN):
+        return subdomain_layout(circuit._Nf(), max(1, W_dev), _sm_count(device))[2]
+    return None
+
+
+def _anneal_shard(problem, tab, tab2, specs, dev, w0, w1, ann, adjust, out, engine_kind, stats_out):
+    """Anneal problems [w0, w1) on one device (reference: time_evolution.py:1142-1191). The state, the factor and
+    the stored theta planes stay on the device for the whole schedule; per interval the host receives one integer
+    per problem (the vortex-mobility sum) and sends one temperature per problem."""
+    W = w1 - w0
+    dt, n_int, steps = ann["dt"], ann["interval_count"], ann["interval_steps"]
+    seed, replay = ann["seed"], ann["noise_replay"]
+    cpr = problem.current_phase_relation
+    sh = _ShardInputs(specs, w0, w1)
+    planes = np.arange(steps, dtype=np.int64)
+    total_ms = 0.0
+    launches = 0
+    key, eng = _engine_for(tab, cpr, dev, W, engine_kind)
+    ok = False
+    try:
+        eng.set_problem(W, dt, seed=seed, problem_offset=w0, engine=engine_kind)     # theta(-1) = theta(-2) = 0
+        _setup_sources(eng, specs, sh, tab)
+        eng.set_source(_lib.JJ_SRC_T, _lib.JJ_KIND_RANK1, True, np.sqrt(2.0 * tab.Rv))
+        eng.alloc_outputs(steps, 0)
+        for i in range(n_int):
+            T = out["T"][w0:w1]
+            # the reference stops drawing noise once every temperature is numerically zero (time_evolution.py:512)
+            amp = np.zeros(W) if np.allclose(T, 0) else np.sqrt(T)
+            eng.upload_source(_lib.JJ_SRC_T, 0, amp[None, :])
+            if replay is not None:
+                Z = replay(i) if callable(replay) else replay[i]
+                eng.upload_noise(i * steps, np.asarray(Z)[:, :, w0:w1])
+            if i > 0:
+                eng.restart_at_rest()
+            eng.run(i * steps, steps, planes, None)
+            total_ms += eng.stats()["step_ms"]
+            sums = eng.vortex_mobility_sums(0, steps)
+            out["T"][w0:w1] = adjust(sums, i, T)
+            out["profiles"][i, w0:w1] = out["T"][w0:w1]
+        th, _ = eng.get_state()
+        launches += eng.stats()["kernel_launches"]
+        ok = True
+    finally:
+        _release_engine(dev, key, eng, ok)
+    # closing runs at T = 0 with half the time step (reference: time_evolution.py:1176-1183)
+    key, eng = _engine_for(tab2, cpr, dev, W, engine_kind)
+    ok = False
+    try:
+        eng.set_problem(W, dt / 2, seed=seed, problem_offset=w0, engine=engine_kind)
+        eng.set_state(th, th)
+        _setup_sources(eng, specs, sh, tab2)
+        eng.set_source(_lib.JJ_SRC_T, _lib.JJ_KIND_ZERO, True)
+        eng.alloc_outputs(0, 0)
+        for r in range(ann["final_runs"]):
+            if r > 0:
+                eng.restart_at_rest()
+            eng.run(r * steps, steps, None, None)
+            total_ms += eng.stats()["step_ms"]
+        th, _ = eng.get_state()
+        out["theta"][:, w0:w1] = th
+        out["n"][:, w0:w1] = eng.vortex_configuration(-1)
+        st = eng.stats()
+        st["total_ms"] = total_ms
+        st["problems"] = W
+        st["kernel_launches"] += launches
+        stats_out[dev] = st
+        ok = True
+    finally:
+        _release_engine(dev, key, eng, ok)
+
+
+def device_annealing(problem, T0, adjust, interval_count, final_runs=5, engine=None):
+    """
+    Device-resident annealing schedule around the stepping loop (reference: time_evolution.py:1142-1191).
+
+    problem : the TimeEvolutionProblem the reference's loop would re-run (circuit, dt, interval_steps steps, flux,
+              current sources; its temperature is ignored). T0 : (W,) start temperatures.
+    adjust(sums, i, T) -> new T : the temperature rule, given the exact integer mobility sums of interval i.
+    Returns dict(profiles (interval_count, W), theta (Nj, W), n (Nf, W), stats).
+    """
+    if getattr(problem, "stencil_width", 3) != 3:
+        raise NotImplementedError("only stencil_width=3 is supported")
+    circuit = problem.get_circuit()
+    W = problem.get_problem_count()
+    devices = getattr(problem, "devices", None)
+    if devices is None:
+        env = os.environ.get("JJ_DEVICES")
+        devices = [int(d) for d in env.split(",")] if env else [0]
+    engine = _engine_kind(engine)
+    n_parts = _n_parts_for(circuit, -(-W // max(1, len(devices))), devices[0], engine)
+    dt = problem._dt()
+    tab = _tables_for(circuit, dt, n_parts)
+    tab2 = _tables_for(circuit, dt / 2, n_parts)
+    specs = _classify_all(problem, tab)
+    specs.pop("T")
+    if specs["Vs"].kind == DENSE:
+        raise NotImplementedError("annealing with dense voltage sources is not supported")
+    out = dict(T=np.array(T0, dtype=np.double).reshape(W).copy(), profiles=np.zeros((interval_count, W)),
+               theta=np.zeros((tab.Nj, W)), n=np.zeros((tab.Nf, W), dtype=int))
+    ann = dict(dt=dt, interval_count=int(interval_count), interval_steps=problem._Nt(), final_runs=int(final_runs),
+               seed=problem.noise_seed if getattr(problem, "noise_seed", None) is not None else 0,
+               noise_replay=getattr(problem, "noise_replay", None))
+    bounds = shard_bounds(W, len(devices))
+    jobs = [(dev, bounds[k], bounds[k + 1]) for k, dev in enumerate(devices) if bounds[k + 1] > bounds[k]]
+    stats, errors = {}, []
+
+    def work(dev, w0, w1):
+        try:
+            _anneal_shard(problem, tab, tab2, specs, dev, w0, w1, ann, adjust, out, engine, stats)
+        except Exception as e:      # surfaced after join
+            errors.append(e)
+    if len(jobs) == 1:
+        _anneal_shard(problem, tab, tab2, specs, *jobs[0], ann, adjust, out, engine, stats)
+    else:
+        threads = [threading.Thread(target=work, args=j) for j in jobs]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+    last_run_stats.clear()
+    last_run_stats.update(stats)
+    out["stats"] = stats
+    return out
 
 
 _sm_cache = {}

@@ -181,3 +181,50 @@ def oracle_inputs(kw):
     if cpr is not None:
         extra["cpr"] = cpr.eval
     return args, extra
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Annealing cases (reference: time_evolution.py:1070-1191, AnnealingProblem): constructor arguments + numpy seed.
+def _anneal_small(pkg):
+    # Nj <= 500: fresh draws every step; the mobility target is crossed in both directions within the run
+    a = pkg.SquareArray(7, 7)
+    return dict(circuit=a, time_step=0.5, interval_steps=10, external_flux=0.2, current_sources=0, problem_count=6,
+                interval_count=14, vortex_mobility=0.02, start_T=0.4, T_factor=1.25), 21
+
+
+def _anneal_recycled(pkg):
+    # Nj > 500: recycled draws (quirk Q2), per-face flux array, non-zero bias current, per-iteration mobility targets
+    a = pkg.SquareArray(17, 17)
+    rng = np.random.RandomState(4)
+    f = 0.1 + 0.02 * rng.rand(a._Nf())
+    return dict(circuit=a, time_step=0.5, interval_steps=6, external_flux=f, current_sources=0.1, problem_count=5,
+                interval_count=9, vortex_mobility=np.linspace(0.03, 0.0, 9), start_T=0.3, T_factor=1.1), 22
+
+
+ANNEAL_CASES = {"anneal_small": _anneal_small, "anneal_recycled": _anneal_recycled}
+
+
+def anneal_noise(Nj, W, interval_steps, interval_count, seed):
+    """The reference's draws during AnnealingProblem.compute as (interval_count, interval_steps, Nj, W): the global
+    generator runs on across the compute() calls while the recycling pattern restarts with every call
+    (reference: time_evolution.py:533-537, :1164-1174). The closing T = 0 runs draw nothing."""
+    rs = np.random.RandomState(seed)
+    out = np.empty((interval_count, interval_steps, Nj, W))
+    for k in range(interval_count):
+        rand = None
+        for i in range(interval_steps):
+            if Nj > 500:
+                rand = rs.randn(Nj, W) if i % 3 == 0 else rand[rs.permutation(Nj), :]
+            else:
+                rand = rs.randn(Nj, W)
+            out[k, i] = rand
+    return out
+
+
+def anneal_oracle_inputs(kw):
+    c = kw["circuit"]
+    args = (c.get_cycle_matrix(), c._Ic(), c._R(), c._C(), c._L())
+    extra = {k: kw[k] for k in ("time_step", "interval_steps", "external_flux", "current_sources", "problem_count",
+                                "interval_count", "start_T", "T_factor") if k in kw}
+    extra["vortex_mobility_target"] = kw.get("vortex_mobility", 0.001)
+    return args, extra

@@ -264,3 +264,95 @@ def test_subdomain_and_streaming_agree_on_device_noise(monkeypatch):
         monkeypatch.setenv("JJ_ENGINE", eng_name)
         out[eng_name] = pj.TimeEvolutionProblem(**kw).compute().theta
     assert np.max(np.abs(out["streaming"] - out["subdomain"])) <= 1e-9
+
+
+# ---------------------------------------------------------------- annealing caller (reference: time_evolution.py:1070-1191)
+def _anneal(name, engine, **extra_kw):
+    kw, seed = cases.ANNEAL_CASES[name](pj)
+    Z = cases.anneal_noise(kw["circuit"]._Nj(), kw["problem_count"], kw["interval_steps"], kw["interval_count"], seed)
+    os.environ["JJ_ENGINE"] = engine
+    try:
+        ap = pj.AnnealingProblem(noise_replay=Z, **kw, **extra_kw)
+        return kw, Z, ap, ap.anneal()
+    finally:
+        os.environ.pop("JJ_ENGINE", None)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", list(cases.ANNEAL_CASES))
+def test_annealing_matches_reference_golden(name, engine, golden_dir):
+    # the reference's own draws injected: the temperature schedule (decided by exact integer vortex-mobility sums)
+    # and the final vortex configuration equal the unmodified reference's; phases agree with the oracle
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    kw, Z, ap, (theta, n, profiles) = _anneal(name, engine)
+    assert np.array_equal(profiles, g["temperature_profiles"])
+    assert np.array_equal(n, g["n"])
+    args, extra = cases.anneal_oracle_inputs(kw)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        prof_o, th_o, n_o = oracle.annealing(*args, noise=lambda k, s: Z[k, s], **extra)
+    assert np.max(np.abs(theta - th_o)) <= 1e-7          # ~150 noisy steps; tolerance stated in SURVEY.md section 8c
+    assert np.array_equal(ap.T[0, :, 0], profiles[-1])
+    status, configs, prof2 = pj.AnnealingProblem(noise_replay=Z, **kw).compute()
+    assert np.array_equal(prof2, profiles) and np.all(status == 2) and len(configs) == kw["problem_count"]
+    assert np.array_equal(configs[1].get_vortex_configuration(), n[:, 1])
+
+
+def test_annealing_equals_reference_style_loop():
+    # the loop exactly as the reference writes it (re-entering compute(), assigning prob.temperature and the
+    # initial conditions, vortex configurations on the host) gives the same schedule as the device-resident path
+    kw, Z, ap, (theta, n, profiles) = _anneal("anneal_small", "auto")
+    ref_style = pj.AnnealingProblem(**kw)
+    f = np.atleast_1d(kw["external_flux"])[:, None, None]
+    th = np.zeros((kw["circuit"].junction_count(), kw["problem_count"]))
+    prob = pj.TimeEvolutionProblem(kw["circuit"], time_step_count=kw["interval_steps"], time_step=kw["time_step"],
+                                   external_flux=f, current_sources=kw["current_sources"], temperature=ref_style.T,
+                                   store_current=False, store_voltage=False, stencil_width=3)
+    prof = np.zeros_like(profiles)
+    for i in range(kw["interval_count"]):
+        prob.temperature = ref_style.T * np.ones((1, 1, kw["interval_steps"]))
+        prob.config_at_minus_1 = th
+        prob.config_at_minus_2 = th.copy()
+        prob.noise_replay = Z[i]
+        out = prob.compute()
+        ref_style._temperature_adjustment(ref_style.get_vortex_mobility(out.get_vortex_configuration()), i)
+        th = out.get_theta()[..., -1]
+        prof[i, :] = ref_style.T[0, :, 0]
+    assert np.array_equal(prof, profiles)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_device_vortex_observables_are_exact(engine):
+    # n = -A round(theta / 2 pi) and the mobility sums computed on the device from stored theta planes equal the
+    # reference's formulas applied on the host to the very same planes (integers: exact)
+    from pyjjasim_b200 import engine as eng_mod
+    kw, _ = cases.build("sq_frustrated", pj)
+    c, W, Nt = kw["circuit"], 6, 60
+    kw.update(store_time_steps=None, store_current=False, store_voltage=False, time_step_count=Nt,
+              current_sources=c.current_base(angle=0)[:, None, None] * np.linspace(0.9, 2.4, W)[None, :, None])
+    prob = pj.TimeEvolutionProblem(**kw)
+    os.environ["JJ_ENGINE"] = engine
+    try:
+        tab = eng_mod._tables_for(c, 0.05)
+        key, e = eng_mod._engine_for(tab, pj.DefaultCPR(), 0, W, eng_mod._engine_kind(None))
+        e.set_problem(W, 0.05, engine=eng_mod._engine_kind(None))
+        e.alloc_outputs(Nt, 0)
+        specs = eng_mod._classify_all(prob, tab)
+        eng_mod._setup_sources(e, specs, eng_mod._ShardInputs(specs, 0, W), tab)
+        e.run(0, Nt, np.arange(Nt), None)
+        theta = np.moveaxis(e.fetch_theta(0, Nt), 0, 2)
+        n_host = oracle.vortex_configuration(c.get_cycle_matrix(), theta)
+        assert np.abs(np.diff(n_host, axis=2)).sum() > 0        # vortices do move in this run
+        for k in (0, Nt // 2, Nt - 1):
+            assert np.array_equal(e.vortex_configuration(k), n_host[:, :, k])
+        assert np.array_equal(e.vortex_configuration(-1), n_host[:, :, -1])
+        assert np.array_equal(e.vortex_mobility_sums(0, Nt), np.abs(np.diff(n_host, axis=2)).sum(axis=(0, 2)))
+        assert np.array_equal(e.vortex_mobility_sums(3, 10), np.abs(np.diff(n_host[:, :, 3:13], axis=2)).sum(axis=(0, 2)))
+        assert np.array_equal(e.vortex_mobility_sums(5, 1), np.zeros(W, dtype=int))
+        a1, a2 = e.get_state()
+        e.restart_at_rest()
+        b1, b2 = e.get_state()
+        assert np.array_equal(b1, a1) and np.array_equal(b2, a1) and not np.array_equal(a2, a1)
+        eng_mod._release_engine(0, key, e, True)
+    finally:
+        os.environ.pop("JJ_ENGINE", None)

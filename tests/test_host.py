@@ -287,3 +287,44 @@ def test_no_gpu_means_loud_failure():
     kw, _ = cases.build("single_problem", pj)
     with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
         pj.TimeEvolutionProblem(**kw).compute()
+
+
+# ---------------------------------------------------------------- annealing caller, host side
+def test_annealing_problem_mirrors_reference_host_logic():
+    from tests import cases
+    from oracle import oracle
+    kw, _ = cases.ANNEAL_CASES["anneal_small"](pj)
+    ap = pj.AnnealingProblem(**kw)
+    assert ap.T.shape == (1, kw["problem_count"], 1) and np.all(ap.T == kw["start_T"])
+    rng = np.random.RandomState(0)
+    Nf = kw["circuit"].face_count()
+    n = rng.randint(-1, 2, size=(Nf, kw["problem_count"], kw["interval_steps"]))
+    mob = ap.get_vortex_mobility(n)
+    assert np.array_equal(mob, oracle.vortex_mobility(n, Nf, kw["time_step"], kw["interval_count"]))
+    T0 = ap.T.copy()
+    ap._temperature_adjustment(mob, 3)
+    upper = kw["vortex_mobility"] * ((kw["interval_count"] - 3) / kw["interval_count"]) ** 1.5
+    want = np.where(mob > upper, 1 / kw["T_factor"], kw["T_factor"])
+    assert np.array_equal(ap.T[0, :, 0], T0[0, :, 0] * want)
+    prob = ap._problem()
+    assert prob.get_problem_count() == kw["problem_count"] and prob._Nt() == kw["interval_steps"]
+    assert not prob.store_current and not prob.store_voltage and not prob._T_is_timedep
+
+
+def test_inputs_replaced_after_construction_are_honoured():
+    # the reference's annealing loop assigns prob.temperature between compute() calls (time_evolution.py:1166); the
+    # time-dependence flag stays as constructed, so the new array is read at step 0 only (:509-519)
+    from pyjjasim_b200 import engine
+    from pyjjasim_b200.sources import RANK1, ZERO
+    a = pj.SquareArray(4, 4)
+    W = 3
+    prob = pj.TimeEvolutionProblem(a, time_step_count=5, temperature=0.5 * np.ones((1, W, 1)),
+                                   store_current=False, store_voltage=False)
+    tab = type("T", (), dict(Nj=a._Nj(), Nf=a._Nf()))()
+    s = engine._classify_all(prob, tab)
+    assert s["T"].kind == RANK1 and np.allclose(s["T"].amp_chunk(0, 1), 0.5)
+    prob.temperature = np.array([0.1, 0.2, 0.3])[None, :, None] * np.ones((1, 1, 5))
+    s = engine._classify_all(prob, tab)
+    assert s["T"].kind == RANK1 and s["T"].static and np.allclose(s["T"].amp_chunk(0, 1), [[0.1, 0.2, 0.3]])
+    prob.temperature = np.zeros((1, 1, 5))
+    assert engine._classify_all(prob, tab)["T"].kind == ZERO

@@ -89,3 +89,25 @@ def test_invariants_kcl_and_flux_quantisation():
         assert np.max(np.abs(M @ (I[:, :, k] - Is))) < 1e-12
         r = A @ (th[:, :, k] + c._L() @ (I[:, :, k] - Is)) + 2 * np.pi * 0.1
         assert np.max(np.abs(r)) < 1e-11
+
+
+# ---------------------------------------------------------------- annealing caller (reference: time_evolution.py:1070-1191)
+@pytest.mark.parametrize("name", list(cases.ANNEAL_CASES))
+def test_annealing_oracle_matches_reference_golden(name, golden_dir):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    kw, seed = cases.ANNEAL_CASES[name](pj)
+    args, extra = cases.anneal_oracle_inputs(kw)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        prof, th, n = oracle.annealing(*args, rng=np.random.RandomState(seed), **extra)
+    assert np.array_equal(prof, g["temperature_profiles"])
+    assert np.array_equal(n, g["n"])
+    # the temperature moved in both directions, so both branches of the adjustment rule were taken
+    d = np.diff(np.vstack((np.full((1, prof.shape[1]), kw["start_T"]), prof)), axis=0)
+    assert (d > 0).any() and (d < 0).any()
+    # the replayed draw sequence (what the GPU parity test injects) reproduces the seeded run
+    Z = cases.anneal_noise(kw["circuit"]._Nj(), kw["problem_count"], kw["interval_steps"], kw["interval_count"], seed)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        prof2, th2, n2 = oracle.annealing(*args, noise=lambda k, s: Z[k, s], **extra)
+    assert np.array_equal(prof2, prof) and np.array_equal(th2, th) and np.array_equal(n2, n)
