@@ -1,3 +1,3 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q -k "anneal or observables" 2>&1 | tail -25
+timeout 900 python tools/anneal_bench.py > gpurun_out/anneal_bench.json 2> gpurun_out/anneal_bench.err; tail -c 2000 gpurun_out/anneal_bench.json; tail -5 gpurun_out/anneal_bench.err

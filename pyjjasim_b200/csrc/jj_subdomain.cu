@@ -361,7 +361,9 @@ __device__ __forceinline__ void next_x(const SubArgs& a, double Ic, double c1, d
 template <int NG, bool DEF>
 __device__ __forceinline__ void junction_item(const SubArgs& a, const AmpCache<8 * NG>* ac, int c, long long n, int idx,
                                               int jlo, bool do_pre, const double* __restrict__ v,
-                                              double* snap_th, double* snap_I) {
+                                              double* snap_th, double* snap_I, const double2 x0, const double2 x1,
+                                              const double2 t0, const double2 t1, const double2 rIc, const double2 rc,
+                                              const double2 rb, const int4 ri) {
     constexpr int PC = 8 * NG, G = PC / 4;
     const int q = (idx % G) * 4;
     const int w = c * PC + q;
@@ -369,11 +371,7 @@ __device__ __forceinline__ void junction_item(const SubArgs& a, const AmpCache<8
     const int jp = jlo + idx / G;
     const size_t sidx = ((size_t)c * a.Nj + jlo) * PC + (size_t)idx * 4;
     const unsigned long long pol_first = policy_evict_first();
-    const double2 x0 = ldg_hint_d2(a.rx + sidx, pol_first), x1 = ldg_hint_d2(a.rx + sidx + 2, pol_first);
-    const double2 t0 = ldg_hint_d2(a.rth + sidx, pol_first), t1 = ldg_hint_d2(a.rth + sidx + 2, pol_first);
-    const double2* rec = reinterpret_cast<const double2*>(a.jrec + 8 * (size_t)jp);
-    const double2 rIc = __ldg(rec), rc = __ldg(rec + 1), rb = __ldg(rec + 2);
-    const int4 ri = __ldg(reinterpret_cast<const int4*>(rec + 3));      // row0, row1, original junction, signs
+    // ri = row0, row1, original junction, signs
     const double s0 = (double)((ri.w & 3) - 1), s1 = (double)(((ri.w >> 2) & 3) - 1);
     const double2* ja = reinterpret_cast<const double2*>(v + velem<NG>(ri.x, q));
     const double2* jb = reinterpret_cast<const double2*>(v + velem<NG>(ri.y, q));
@@ -450,12 +448,36 @@ __device__ void junction_pass(const SubArgs& a, const AmpCache<8 * NG>* ac, int 
         if (pi >= 0) snap_I = a.snap_I + (size_t)pi * a.Nj * a.Wp;
     }
     const size_t sbase = ((size_t)c * a.Nj + jlo) * PC;
+    // software pipeline: the state of the next item is in flight (registers) while this one is computed, and the
+    // state three iterations ahead is pulled into L2
+    const unsigned long long pol_first = policy_evict_first();
+    double2 x0, x1, t0, t1, rIc, rc, rb;
+    int4 ri = make_int4(0, 0, 0, 0);
+    x0 = x1 = t0 = t1 = rIc = rc = rb = make_double2(0.0, 0.0);
+    if ((int)threadIdx.x < total) {
+        const size_t si = sbase + (size_t)threadIdx.x * 4;
+        x0 = ldg_hint_d2(a.rx + si, pol_first); x1 = ldg_hint_d2(a.rx + si + 2, pol_first);
+        t0 = ldg_hint_d2(a.rth + si, pol_first); t1 = ldg_hint_d2(a.rth + si + 2, pol_first);
+        const double2* rec = reinterpret_cast<const double2*>(a.jrec + 8 * (size_t)(jlo + threadIdx.x / G));
+        rIc = __ldg(rec); rc = __ldg(rec + 1); rb = __ldg(rec + 2); ri = __ldg(reinterpret_cast<const int4*>(rec + 3));
+    }
     for (int idx = threadIdx.x; idx < total; idx += NT) {
-        if (idx + 2 * NT < total) {      // the state two iterations ahead is pulled into L2
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.rx + sbase + (size_t)(idx + 2 * NT) * 4));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.rth + sbase + (size_t)(idx + 2 * NT) * 4));
+        if (idx + 3 * NT < total) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.rx + sbase + (size_t)(idx + 3 * NT) * 4));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.rth + sbase + (size_t)(idx + 3 * NT) * 4));
         }
-        junction_item<NG, DEF>(a, ac, c, n, idx, jlo, do_pre, v, snap_th, snap_I);
+        double2 nx0, nx1, nt0, nt1, nIc, nc, nb;
+        int4 ni = make_int4(0, 0, 0, 0);
+        nx0 = nx1 = nt0 = nt1 = nIc = nc = nb = make_double2(0.0, 0.0);
+        if (idx + NT < total) {
+            const size_t si = sbase + (size_t)(idx + NT) * 4;
+            nx0 = ldg_hint_d2(a.rx + si, pol_first); nx1 = ldg_hint_d2(a.rx + si + 2, pol_first);
+            nt0 = ldg_hint_d2(a.rth + si, pol_first); nt1 = ldg_hint_d2(a.rth + si + 2, pol_first);
+            const double2* rec = reinterpret_cast<const double2*>(a.jrec + 8 * (size_t)(jlo + (idx + NT) / G));
+            nIc = __ldg(rec); nc = __ldg(rec + 1); nb = __ldg(rec + 2); ni = __ldg(reinterpret_cast<const int4*>(rec + 3));
+        }
+        junction_item<NG, DEF>(a, ac, c, n, idx, jlo, do_pre, v, snap_th, snap_I, x0, x1, t0, t1, rIc, rc, rb, ri);
+        x0 = nx0; x1 = nx1; t0 = nt0; t1 = nt1; rIc = nIc; rc = nc; rb = nb; ri = ni;
     }
 }
 
