@@ -194,7 +194,12 @@ def run_ours(args, rank, world, local_rank, dist):
                                            temperature=T[None, :, None], store_time_steps=[INNER // 3, INNER - 1],
                                            store_current=False, store_voltage=False, config_at_minus_1=th0,
                                            noise_seed=SEED)
-            res = prob.compute()
+            if os.environ.get("JJ_BENCH_E2E_PROFILE") and r == reps:       # where the host time of the last repeat goes
+                import cProfile, pstats
+                pr = cProfile.Profile(); pr.enable(); res = prob.compute(); pr.disable()
+                pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(14)
+            else:
+                res = prob.compute()
             e2e_t.append(time.perf_counter() - t1)
             th0 = np.ascontiguousarray(res.theta[:, :, -1])
         e2e_s = float(np.mean(e2e_t[1:]))                 # first call pays the one-off factorisation

@@ -72,6 +72,7 @@ struct JJHandle {
     double *noise_buf = nullptr; size_t noise_cap = 0; long long noise_i0 = 0; int noise_K = 0;
     // outputs
     double *th_out = nullptr, *I_out = nullptr; long long n_th_planes = 0, n_I_planes = 0;
+    long long th_cap_planes = 0, I_cap_planes = 0;   // allocated planes (kept across jj_set_problem calls of equal W)
     int *flag_d = nullptr;
     // resident engine (see jj_resident.cu): plan-level and problem-level state
     void *resident_plan = nullptr;

@@ -32,6 +32,7 @@ using namespace jj;
 namespace {
 
 constexpr int NT = 512;
+constexpr size_t BAR_BYTES = 8192;      // grid barrier counter + one counter per problem chunk, 128 bytes apart
 constexpr int NWARPS = NT / 32;
 constexpr int RING = 4;            // stream steps per ring block; every tile is padded to a multiple of it
 constexpr int STEP_BYTES = 320;
@@ -574,10 +575,10 @@ __device__ void face_pass(const SubArgs& a, const AmpCache<8 * NG>* ac, int s, i
 // grid barrier: monotonic arrival counter (zeroed by the host before the launch); the kernel is launched
 // cooperatively, so all blocks are resident.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
+__device__ __forceinline__ void group_barrier(unsigned* ctr, unsigned& target, unsigned members) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        target += gridDim.x;
+        target += members;
         __threadfence();
         atomicAdd(ctr, 1u);
         unsigned seen;
@@ -588,16 +589,18 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
     }
     __syncthreads();
 }
+__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) { group_barrier(ctr, target, gridDim.x); }
 
 // r_top = sum of the subdomain contributions - 2 pi f_top (+ debug right-hand side), logical [chunk][row][PC]
 template <int NG>
-__device__ void top_assemble(const SubArgs& a, long long n) {
+__device__ void top_assemble(const SubArgs& a, long long n, int c0, int nc, int worker, int n_workers) {
+    // chunks [c0, c0 + nc) are assembled by n_workers thread blocks; this block is number `worker` of them
     constexpr int PC = 8 * NG, G = PC / 4;
-    const long long total = (long long)a.n_chunks * a.n_top * G;
-    for (long long idx = (long long)blockIdx.x * NT + threadIdx.x; idx < total; idx += (long long)gridDim.x * NT) {
+    const long long total = (long long)nc * a.n_top * G;
+    for (long long idx = (long long)worker * NT + threadIdx.x; idx < total; idx += (long long)n_workers * NT) {
         const int q = (int)(idx % G) * 4;
         const long long t = idx / G;
-        const int k = (int)(t % a.n_top), c = (int)(t / a.n_top);
+        const int k = (int)(t % a.n_top), c = c0 + (int)(t / a.n_top);
         const int w = c * PC + q;
         double acc[4] = {0, 0, 0, 0};
         for (int sl = a.tptr[k]; sl < a.tptr[k + 1]; ++sl) {
@@ -754,22 +757,24 @@ __device__ void top_product(const SubArgs& a, double* buf, int RB, int S) {
 // row tile, one k-step per warp and stage, so RB*KQ (up to 16) warps issue MMAs and all four FP64 tensor pipes of
 // the SM are busy even when a block has only a few row tiles. The KQ partial sums of a row tile meet in shared
 // memory at the end and are added in a fixed order.
-template <int NG>
-__device__ void top_product_ksplit(const SubArgs& a, double* buf, int RB, int KQ, int S) {
+template <int NG, int KM>
+__device__ void top_product_ksplit(const SubArgs& a, double* buf, int RB, int KQ, int S, int c0, int nc, int worker,
+                                   int n_workers) {
+    // KM k-steps per warp and stage: a stage holds KB = KQ * KM k-steps, so one block barrier covers KM * GW MMAs per warp
     constexpr int PC = 8 * NG;
     constexpr int GW = NG < 4 ? NG : 4;
     constexpr int GP = (NG + 3) / 4;
-    const int KB = KQ;
+    const int KB = KQ * KM;
     const int RT = (a.n_top + 7) / 8, RTP = a.n_top_pad / 8, KS = a.n_top_pad / 4;
     const int NB = (RT + RB - 1) / RB;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rtl = warp / KQ, kq = warp % KQ;
     const int stage_doubles = (RB + GW) * KB * 32;
     const int pieces = stage_doubles / 2;
-    const int n_tasks = a.n_chunks * NB * GP;
+    const int n_tasks = nc * NB * GP;
     const int nkb = KS / KB;
-    for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
-        const int gp = task % GP, nb = (task / GP) % NB, c = task / (GP * NB);
+    for (int task = worker; task < n_tasks; task += n_workers) {
+        const int gp = task % GP, nb = (task / GP) % NB, c = c0 + task / (GP * NB);
         const int rt = nb * RB + rtl;
         const bool active = rtl < RB && rt < RT;
         // B fragments are staged as [kk][n ^ 4*(kk>>1)]: a half warp (n = 0..3 or 4..7, kk = 0..3) then reads 16
@@ -798,14 +803,17 @@ __device__ void top_product_ksplit(const SubArgs& a, double* buf, int RB, int KQ
         auto issue = [&]() {
             if (issued < nkb) {
                 double* dst = buf + (size_t)islot * stage_doubles;
-                if (have[0]) cp_async16(dst + dofs[0], sp0);
-                if (have[1]) cp_async16(dst + dofs[1], sp1);
+                if (!(a.dbg & 32)) {      // timing experiment: JJ_SUB_DEBUG=32 skips the staging loads
+                    if (have[0]) cp_async16(dst + dofs[0], sp0);
+                    if (have[1]) cp_async16(dst + dofs[1], sp1);
+                }
                 sp0 += step[0]; sp1 += step[1];
                 ++issued;
                 if (++islot == S) islot = 0;
             }
             asm volatile("cp.async.commit_group;");
         };
+        long long tp0 = a.prof ? clock64() : 0;
         __syncthreads();                           // the ring is free (previous task / phase done)
         for (int k = 0; k < S - 1; ++k) issue();
         double acc[GW][2];
@@ -820,19 +828,33 @@ __device__ void top_product_ksplit(const SubArgs& a, double* buf, int RB, int KQ
             else if (S == 3) asm volatile("cp.async.wait_group 1;");
             else asm volatile("cp.async.wait_group 0;");
             __syncthreads();
+            if (a.prof && kb == 0 && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 8 + 40] += tn - tp0; tp0 = tn; }
             issue();
             if (active) {
-                const double av = st[a_off];
-                double bv[GW];
+                double av[KM], bv[KM][GW];
 #pragma unroll
-                for (int g = 0; g < GW; ++g) bv[g] = st[b_off + g * KB * 32];
+                for (int m = 0; m < KM; ++m) {
+                    av[m] = st[a_off + m * KQ * 32];
 #pragma unroll
-                for (int g = 0; g < GW; ++g) dmma884(acc[g][0], acc[g][1], av, bv[g]);
+                    for (int g = 0; g < GW; ++g) bv[m][g] = st[b_off + m * KQ * 32 + g * KB * 32];
+                }
+                if (a.dbg & 16) {         // timing experiment: JJ_SUB_DEBUG=16 replaces the MMAs by one add each
+#pragma unroll
+                    for (int m = 0; m < KM; ++m)
+#pragma unroll
+                        for (int g = 0; g < GW; ++g) acc[g][0] += av[m] + bv[m][g];
+                } else {
+#pragma unroll
+                    for (int m = 0; m < KM; ++m)
+#pragma unroll
+                        for (int g = 0; g < GW; ++g) dmma884(acc[g][0], acc[g][1], av[m], bv[m][g]);
+                }
             }
             st += stage_doubles;
             if (++cslot == S) { cslot = 0; st = buf; }
         }
         asm volatile("cp.async.wait_group 0;");
+        if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 8 + 41] += tn - tp0; tp0 = tn; }
         __syncthreads();                           // everyone is done with the ring: reuse it for the partial sums
         if (active) {
 #pragma unroll
@@ -852,6 +874,121 @@ __device__ void top_product_ksplit(const SubArgs& a, double* buf, int RB, int KQ
                         sum.x += part.x; sum.y += part.y;
                     }
                     double2* dst = reinterpret_cast<double2*>(a.jtop + ((size_t)c * a.n_top_pad + row) * PC + 8 * gg + 2 * (lane & 3));
+                    if (a.dbg & 48) sum = make_double2(0.0, 0.0);      // timing experiments: keep the dynamics finite
+                    *dst = sum;
+                }
+            }
+        }
+        if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 8 + 42] += tn - tp0; }
+    }
+    __syncthreads();
+}
+
+// J_top = S_top^-1 r_top with the A fragments (the packed inverse) read straight from L2 into registers: a fragment is
+// used by exactly one warp, so staging it in shared memory only costs shared-memory bandwidth (the product was bound
+// by it: 52 KB of shared-memory traffic per 30 MMAs). Only the B fragments (r_top, shared by all row tiles of the
+// block) go through the cp.async ring; a stage holds KB = KQ * KM k-steps; warp = (row tile, K slot) as in
+// top_product_ksplit, A fragments of the next stage are in flight while this stage is multiplied.
+template <int NG, int KM>
+__device__ void top_product_areg(const SubArgs& a, double* buf, int RB, int KQ, int S, int c0, int nc, int worker,
+                                 int n_workers) {
+    constexpr int PC = 8 * NG;
+    constexpr int GW = NG < 4 ? NG : 4;
+    constexpr int GP = (NG + 3) / 4;
+    const int KB = KQ * KM;
+    const int RT = (a.n_top + 7) / 8, RTP = a.n_top_pad / 8, KS = a.n_top_pad / 4;
+    const int NB = (RT + RB - 1) / RB;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rtl = warp / KQ, kq = warp % KQ;
+    const int stage_doubles = GW * KB * 32;
+    const int pieces = stage_doubles / 2;            // <= NT: one 16-byte piece per thread and stage
+    const int n_tasks = nc * NB * GP;
+    const int nkb = KS / KB;
+    const unsigned long long pol = policy_evict_last();
+    for (int task = worker; task < n_tasks; task += n_workers) {
+        const int gp = task % GP, nb = (task / GP) % NB, c = c0 + task / (GP * NB);
+        const int rt = nb * RB + rtl;
+        const bool active = rtl < RB && rt < RT;
+        // B fragments are staged as [kk][n ^ 4*(kk>>1)] (see top_product_ksplit)
+        const int i = threadIdx.x;
+        const bool have = i < pieces;
+        const int frag = i / 16, piece = i % 16, gsel = frag / KB, kl = frag % KB;
+        const int gg = min(4 * gp + gsel, NG - 1), kk = piece >> 2, n2 = (piece & 3) * 2;
+        const double* sp = a.rtop + ((size_t)c * a.n_top_pad + 4 * kl + kk) * PC + 8 * gg + n2;
+        const size_t sstep = (size_t)KB * 4 * PC;
+        const int dofs = frag * 32 + kk * 8 + (n2 ^ ((kk >> 1) << 2));
+        int issued = 0, islot = 0;
+        auto issue = [&]() {
+            if (issued < nkb) {
+                if (have) cp_async16(buf + (size_t)islot * stage_doubles + dofs, sp);
+                sp += sstep;
+                ++issued;
+                if (++islot == S) islot = 0;
+            }
+            asm volatile("cp.async.commit_group;");
+        };
+        const double* ap = a.SinvP + ((size_t)min(rt, RTP - 1) * KS + kq) * 32 + lane;
+        double an[KM];
+#pragma unroll
+        for (int m = 0; m < KM; ++m) {
+            asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(an[m]) : "l"(ap + (size_t)m * KQ * 32), "l"(pol));
+        }
+        __syncthreads();                           // the ring is free (previous task / phase done)
+        for (int k = 0; k < S - 1; ++k) issue();
+        double acc[GW][2];
+#pragma unroll
+        for (int g = 0; g < GW; ++g) { acc[g][0] = 0.0; acc[g][1] = 0.0; }
+        const int b_off = kq * 32 + (lane & 3) * 8 + ((lane >> 2) ^ (((lane & 3) >> 1) << 2));   // group g: + g*KB*32
+        const double* st = buf;
+        int cslot = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+            if (S >= 4) asm volatile("cp.async.wait_group 2;");
+            else if (S == 3) asm volatile("cp.async.wait_group 1;");
+            else asm volatile("cp.async.wait_group 0;");
+            __syncthreads();
+            issue();
+            double av[KM];
+#pragma unroll
+            for (int m = 0; m < KM; ++m) av[m] = an[m];
+            ap += (size_t)KB * 32;
+            if (kb + 1 < nkb) {
+#pragma unroll
+                for (int m = 0; m < KM; ++m)
+                    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(an[m]) : "l"(ap + (size_t)m * KQ * 32), "l"(pol));
+            }
+            if (active) {
+#pragma unroll
+                for (int m = 0; m < KM; ++m) {
+                    double bv[GW];
+#pragma unroll
+                    for (int g = 0; g < GW; ++g) bv[g] = st[b_off + m * KQ * 32 + g * KB * 32];
+#pragma unroll
+                    for (int g = 0; g < GW; ++g) dmma884(acc[g][0], acc[g][1], av[m], bv[g]);
+                }
+            }
+            st += stage_doubles;
+            if (++cslot == S) { cslot = 0; st = buf; }
+        }
+        asm volatile("cp.async.wait_group 0;");
+        __syncthreads();                           // everyone is done with the ring: reuse it for the partial sums
+        if (active) {
+#pragma unroll
+            for (int g = 0; g < GW; ++g)
+                *reinterpret_cast<double2*>(buf + ((size_t)(warp * GW + g) * 32 + lane) * 2) = make_double2(acc[g][0], acc[g][1]);
+        }
+        __syncthreads();
+        if (active && kq == 0) {
+            const int row = 8 * rt + (lane >> 2);
+#pragma unroll
+            for (int g = 0; g < GW; ++g) {
+                const int gg2 = 4 * gp + g;
+                if (gg2 < NG) {
+                    double2 sum = make_double2(0.0, 0.0);
+                    for (int k2 = 0; k2 < KQ; ++k2) {
+                        const double2 part = *reinterpret_cast<const double2*>(buf + ((size_t)((warp + k2) * GW + g) * 32 + lane) * 2);
+                        sum.x += part.x; sum.y += part.y;
+                    }
+                    double2* dst = reinterpret_cast<double2*>(a.jtop + ((size_t)c * a.n_top_pad + row) * PC + 8 * gg2 + 2 * (lane & 3));
                     *dst = sum;
                 }
             }
@@ -920,6 +1057,39 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
             }
         }
     }
+    // chunk-local top phase: exactly one item per block, K-split product available, and the row blocks of a chunk
+    // fit its P blocks in one round
+    bool chunk_local = false;
+    if (a.n_top > 0 && n_items == (int)gridDim.x && top_kq >= 2 && a.n_chunks <= 60 && !(a.dbg & 4)) {
+        const int GPr = (NG + 3) / 4;
+        const int rb = min(NWARPS, ((a.n_top + 7) / 8 * GPr + a.P - 1) / a.P);
+        int kq = NWARPS / rb;
+        while (kq > 1 && (a.n_top_pad / 4) % kq != 0) --kq;
+        const int stage_bytes = a.stage_rows * (PC + 2) * 8, GWr = NG < 4 ? NG : 4;
+        const int sb = (rb + GWr) * kq * 256;
+        if (kq >= 2 && sb / 16 <= 2 * NT && 3 * sb <= stage_bytes && NWARPS * GWr * 64 * 8 <= stage_bytes) {
+            chunk_local = true; top_rb = rb; top_kq = kq; top_s = min(4, stage_bytes / sb);
+        }
+    }
+    // two k-steps per warp and stage when the ring still holds three such stages
+    int top_km = 1;
+    if (top_kq >= 2 && !(a.dbg & 8)) {
+        const int stage_bytes = a.stage_rows * (PC + 2) * 8, GWr = NG < 4 ? NG : 4;
+        const int sb2 = (top_rb + GWr) * top_kq * 2 * 256;
+        if ((a.n_top_pad / 4) % (2 * top_kq) == 0 && sb2 / 16 <= 2 * NT && 3 * sb2 <= stage_bytes) {
+            top_km = 2; top_s = min(4, stage_bytes / sb2);
+        }
+    }
+    // A fragments in registers, B ring of KM k-steps per warp and stage (largest KM whose ring holds >= 3 stages)
+    int top_ar = 0;
+    if (top_kq >= 2 && !(a.dbg & 64)) {
+        const int stage_bytes = a.stage_rows * (PC + 2) * 8, GWr = NG < 4 ? NG : 4;
+        for (int km = 4; km >= 1 && top_ar == 0; km >>= 1) {
+            const int sb = GWr * top_kq * km * 256;
+            if ((a.n_top_pad / 4) % (top_kq * km) == 0 && sb / 16 <= NT && 3 * sb <= stage_bytes &&
+                NWARPS * GWr * 64 * 8 <= stage_bytes) { top_ar = km; top_s = min(4, stage_bytes / sb); }
+        }
+    }
     if (a.dbg_b) {
         // ---- debug: one solve J = S^-1 b through the plan
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -940,9 +1110,13 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
             rows_to_global<NG>(v, 0, nl, a.zloc + ((size_t)item * a.n_loc_max) * PC);
         }
         grid_barrier(a.bar, bar_target);
-        top_assemble<NG>(a, 0);
+        top_assemble<NG>(a, 0, 0, a.n_chunks, blockIdx.x, gridDim.x);
         grid_barrier(a.bar, bar_target);
-        if (top_kq >= 2) top_product_ksplit<NG>(a, stage, top_rb, top_kq, top_s);
+        if (top_ar == 4) top_product_areg<NG, 4>(a, stage, top_rb, top_kq, top_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
+            else if (top_ar == 2) top_product_areg<NG, 2>(a, stage, top_rb, top_kq, top_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
+            else if (top_ar == 1) top_product_areg<NG, 1>(a, stage, top_rb, top_kq, top_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
+            else if (top_kq >= 2 && top_km == 2) top_product_ksplit<NG, 2>(a, stage, top_rb, top_kq, top_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
+            else if (top_kq >= 2) top_product_ksplit<NG, 1>(a, stage, top_rb, top_kq, top_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
             else if (top_kb == 4) top_product<NG, 4>(a, stage, top_rb, top_s); else if (top_kb == 2) top_product<NG, 2>(a, stage, top_rb, top_s);
             else if (top_kb == 1) top_product<NG, 1>(a, stage, top_rb, top_s); else top_product_direct<NG>(a);
         grid_barrier(a.bar, bar_target);
@@ -1021,13 +1195,36 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
             if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 3] += tn - tq; tq = tn; }
         }
         if (k == a.n) break;
-        if (a.n_top > 0) {
+        if (a.n_top > 0 && chunk_local) {
+            // every block owns one (subdomain, chunk) item and the top rows of a chunk are assembled and multiplied
+            // by the P blocks of that chunk: the three barriers of a time step only join those P blocks (one counter
+            // per chunk, each on its own 128-byte line), and the chunks drift apart freely
+            const int c = blockIdx.x / a.P, s = blockIdx.x % a.P;
+            unsigned* ctr = a.bar + 32 * (1 + c);
+            group_barrier(ctr, bar_target, a.P);
+            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 4] += tn - tq; tq = tn; }
+            top_assemble<NG>(a, n, c, 1, s, a.P);
+            group_barrier(ctr, bar_target, a.P);
+            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 5] += tn - tq; tq = tn; }
+            if (top_ar == 4) top_product_areg<NG, 4>(a, stage, top_rb, top_kq, top_s, c, 1, s, a.P);
+            else if (top_ar == 2) top_product_areg<NG, 2>(a, stage, top_rb, top_kq, top_s, c, 1, s, a.P);
+            else if (top_ar == 1) top_product_areg<NG, 1>(a, stage, top_rb, top_kq, top_s, c, 1, s, a.P);
+            else if (top_km == 2) top_product_ksplit<NG, 2>(a, stage, top_rb, top_kq, top_s, c, 1, s, a.P);
+            else top_product_ksplit<NG, 1>(a, stage, top_rb, top_kq, top_s, c, 1, s, a.P);
+            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 6] += tn - tq; tq = tn; }
+            group_barrier(ctr, bar_target, a.P);
+            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 7] += tn - tq; tq = tn; }
+        } else if (a.n_top > 0) {
             grid_barrier(a.bar, bar_target);
             if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 4] += tn - tq; tq = tn; }
-            top_assemble<NG>(a, n);
+            top_assemble<NG>(a, n, 0, a.n_chunks, blockIdx.x, gridDim.x);
             grid_barrier(a.bar, bar_target);
             if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 5] += tn - tq; tq = tn; }
-            if (top_kq >= 2) top_product_ksplit<NG>(a, stage, top_rb, top_kq, top_s);
+            if (top_ar == 4) top_product_areg<NG, 4>(a, stage, top_rb, top_kq, top_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
+            else if (top_ar == 2) top_product_areg<NG, 2>(a, stage, top_rb, top_kq, top_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
+            else if (top_ar == 1) top_product_areg<NG, 1>(a, stage, top_rb, top_kq, top_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
+            else if (top_kq >= 2 && top_km == 2) top_product_ksplit<NG, 2>(a, stage, top_rb, top_kq, top_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
+            else if (top_kq >= 2) top_product_ksplit<NG, 1>(a, stage, top_rb, top_kq, top_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
             else if (top_kb == 4) top_product<NG, 4>(a, stage, top_rb, top_s); else if (top_kb == 2) top_product<NG, 2>(a, stage, top_rb, top_s);
             else if (top_kb == 1) top_product<NG, 1>(a, stage, top_rb, top_s); else top_product_direct<NG>(a);
             if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 6] += tn - tq; tq = tn; }
@@ -1108,7 +1305,7 @@ void subdomain_free_problem(JJHandle* h) {
     dev_free(h, st->rth, st->state_bytes); dev_free(h, st->rx, st->state_bytes);
     dev_free(h, st->zloc, st->z_bytes); dev_free(h, st->ctop, st->c_bytes);
     dev_free(h, st->rtop, st->t_bytes); dev_free(h, st->jtop, st->t_bytes);
-    dev_free(h, st->bar, 256);
+    dev_free(h, st->bar, BAR_BYTES);
     dev_free(h, st->plane_d, st->plane_cap);
     st->rth = st->rx = st->zloc = st->ctop = st->rtop = st->jtop = nullptr; st->bar = nullptr;
     st->plane_d = nullptr; st->plane_cap = 0; st->state_bytes = st->z_bytes = st->c_bytes = st->t_bytes = 0;
@@ -1239,7 +1436,7 @@ static int launch(JJHandle* h, SubState* st, SubArgs& a) {
     const char* env = getenv("JJ_SUB_GRID");
     int grid = std::min(st->grid, std::max(1, want));
     if (env && atoi(env) > 0) grid = std::min(st->grid, atoi(env));
-    SCK(cudaMemsetAsync(st->bar, 0, 256, h->stream));
+    SCK(cudaMemsetAsync(st->bar, 0, BAR_BYTES, h->stream));
     if (st->n_top > 0 && !getenv("JJ_SUB_NO_L2_WINDOW")) {
         // keep the packed Schur inverse resident in L2: it is re-read by every block once per time step while
         // the state (hundreds of MB per step) streams through the same cache
@@ -1278,7 +1475,7 @@ int subdomain_prepare(JJHandle* h) {
     if ((rc = dev_alloc(h, (void**)&st->ctop, st->c_bytes))) return rc;
     if ((rc = dev_alloc(h, (void**)&st->rtop, st->t_bytes))) return rc;
     if ((rc = dev_alloc(h, (void**)&st->jtop, st->t_bytes))) return rc;
-    if ((rc = dev_alloc(h, (void**)&st->bar, 256))) return rc;
+    if ((rc = dev_alloc(h, (void**)&st->bar, BAR_BYTES))) return rc;
     SCK(cudaMemsetAsync(st->rth, 0, st->state_bytes, h->stream));
     SCK(cudaMemsetAsync(st->rx, 0, st->state_bytes, h->stream));
     SCK(cudaMemsetAsync(st->zloc, 0, st->z_bytes, h->stream));
@@ -1342,6 +1539,17 @@ int subdomain_run(JJHandle* h, long long i0, int n, const long long* th_plane, c
         else if (cnt) fprintf(stderr, "    sweep level %2d           avg %9.0f max %9.0f\n", sl - 8, avg, mx);
     }
     fprintf(stderr, "  total avg cycles per time step %.0f\n", tot);
+    // local work (sweeps + junction + face pass) per subdomain, averaged over its chunks: what the dissection balances
+    fprintf(stderr, "  local cycles per subdomain:");
+    for (int s = 0; s < st->P; ++s) {
+        double sum = 0; int cnt = 0;
+        for (size_t b = s; b < nb && b < (size_t)st->P * st->n_chunks; b += st->P) {
+            double v = 0; for (int sl = 0; sl < 4; ++sl) v += (double)hp[b * PROF_SLOTS + sl] / n;
+            if (v > 0) { sum += v; ++cnt; }
+        }
+        fprintf(stderr, " %.0f", cnt ? sum / cnt : 0.0);
+    }
+    fprintf(stderr, "\n");
     return JJ_OK;
 }
 

@@ -382,8 +382,8 @@ static void free_problem(JJHandle* h) {
     h->th1 = h->th2 = h->x = h->thetas = h->v = nullptr;
     for (int i = 0; i < 4; ++i) free_source(h, h->src[i]);
     dev_free(h, h->noise_buf, h->noise_cap); h->noise_buf = nullptr; h->noise_cap = 0; h->noise_K = 0;
-    dev_free(h, h->th_out, (size_t)h->n_th_planes * nj); dev_free(h, h->I_out, (size_t)h->n_I_planes * nj);
-    h->th_out = h->I_out = nullptr; h->n_th_planes = h->n_I_planes = 0;
+    dev_free(h, h->th_out, (size_t)h->th_cap_planes * nj); dev_free(h, h->I_out, (size_t)h->I_cap_planes * nj);
+    h->th_out = h->I_out = nullptr; h->n_th_planes = h->n_I_planes = 0; h->th_cap_planes = h->I_cap_planes = 0;
     resident_free(h);
     subdomain_free_problem(h);
     h->have_problem = h->have_state = false;
@@ -473,8 +473,9 @@ int jj_set_problem(JJHandle* h, int32_t W, double dt, uint64_t seed, int64_t pro
     if (same) {
         for (int i = 0; i < 4; ++i) free_source(h, h->src[i]);
         dev_free(h, h->noise_buf, h->noise_cap); h->noise_buf = nullptr; h->noise_cap = 0; h->noise_K = 0;
-        dev_free(h, h->th_out, (size_t)h->n_th_planes * nj); dev_free(h, h->I_out, (size_t)h->n_I_planes * nj);
-        h->th_out = h->I_out = nullptr; h->n_th_planes = h->n_I_planes = 0;
+        // the output planes stay allocated (jj_alloc_outputs reuses them when they are large enough): cudaFree and
+        // cudaMalloc of ~100 MB cost tens of milliseconds per compute() call
+        h->n_th_planes = h->n_I_planes = 0;
     } else {
         free_problem(h);
     }
@@ -603,13 +604,21 @@ int jj_alloc_outputs(JJHandle* h, int64_t n_th, int64_t n_I) {
     CK(cudaSetDevice(h->device));
     REQUIRE(h->have_problem && n_th >= 0 && n_I >= 0, JJ_ESTATE, "alloc_outputs: problem not set");
     size_t nj = (size_t)h->cir.Nj * h->Wp * sizeof(double);
-    CK(cudaStreamSynchronize(h->stream));
-    dev_free(h, h->th_out, (size_t)h->n_th_planes * nj); dev_free(h, h->I_out, (size_t)h->n_I_planes * nj);
-    h->th_out = h->I_out = nullptr; h->n_th_planes = h->n_I_planes = 0;
     int rc;
-    if ((rc = dev_alloc(h, (void**)&h->th_out, (size_t)n_th * nj))) return rc;
+    if (n_th > h->th_cap_planes || n_I > h->I_cap_planes) CK(cudaStreamSynchronize(h->stream));
+    if (n_th > h->th_cap_planes) {
+        dev_free(h, h->th_out, (size_t)h->th_cap_planes * nj);
+        h->th_out = nullptr; h->th_cap_planes = 0; h->n_th_planes = 0;
+        if ((rc = dev_alloc(h, (void**)&h->th_out, (size_t)n_th * nj))) return rc;
+        h->th_cap_planes = n_th;
+    }
     h->n_th_planes = n_th;
-    if ((rc = dev_alloc(h, (void**)&h->I_out, (size_t)n_I * nj))) return rc;
+    if (n_I > h->I_cap_planes) {
+        dev_free(h, h->I_out, (size_t)h->I_cap_planes * nj);
+        h->I_out = nullptr; h->I_cap_planes = 0; h->n_I_planes = 0;
+        if ((rc = dev_alloc(h, (void**)&h->I_out, (size_t)n_I * nj))) return rc;
+        h->I_cap_planes = n_I;
+    }
     h->n_I_planes = n_I;
     return JJ_OK;
 }

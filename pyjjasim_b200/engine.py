@@ -494,15 +494,27 @@ class DeviceEngine:
         ip = np.ascontiguousarray(I_plane if I_plane is not None else -np.ones(n), dtype=np.int64)
         self._ck(self.lib.jj_run(self.h, int(i0), int(n), _lib.i64(tp), _lib.i64(ip)))
 
-    def fetch_theta(self, p0, n):
-        out = np.empty((n, self.tab.Nj, self.W))
-        self._ck(self.lib.jj_fetch_theta(self.h, int(p0), int(n), _lib.f64(out)))
-        return out
+    def _fetch_target(self, n, out):
+        if out is not None and out.shape == (n, self.tab.Nj, self.W) and out.flags.c_contiguous \
+                and out.dtype == np.double and out.flags.writeable:
+            return out, True
+        return np.empty((n, self.tab.Nj, self.W)), False
 
-    def fetch_current(self, p0, n):
-        out = np.empty((n, self.tab.Nj, self.W))
-        self._ck(self.lib.jj_fetch_current(self.h, int(p0), int(n), _lib.f64(out)))
-        return out
+    def fetch_theta(self, p0, n, out=None):
+        """Stored theta planes [p0, p0 + n) as (n, Nj, W); written straight into ``out`` when that is a contiguous
+        array of this shape (saves one pass over the result on the host)."""
+        buf, direct = self._fetch_target(n, out)
+        self._ck(self.lib.jj_fetch_theta(self.h, int(p0), int(n), _lib.f64(buf)))
+        if out is not None and not direct:
+            out[...] = buf
+        return buf
+
+    def fetch_current(self, p0, n, out=None):
+        buf, direct = self._fetch_target(n, out)
+        self._ck(self.lib.jj_fetch_current(self.h, int(p0), int(n), _lib.f64(buf)))
+        if out is not None and not direct:
+            out[...] = buf
+        return buf
 
     def debug_noise(self, step):
         out = np.empty((self.tab.Nj, self.W))
@@ -731,10 +743,10 @@ def _run_shard(problem, tab, specs, dev, w0, w1, th_mask, I_mask, th_host, I_hos
             total_ms += eng.stats()["step_ms"]
             if n_th:
                 first = th_idx[i0:i1][tm][0]
-                th_host[2 + first: 2 + first + n_th, :, w0:w1] = eng.fetch_theta(0, n_th)
+                eng.fetch_theta(0, n_th, out=th_host[2 + first: 2 + first + n_th, :, w0:w1])
             if n_I:
                 first = I_idx[i0:i1][im][0]
-                I_host[2 + first: 2 + first + n_I, :, w0:w1] = eng.fetch_current(0, n_I)
+                eng.fetch_current(0, n_I, out=I_host[2 + first: 2 + first + n_I, :, w0:w1])
         st = eng.stats()
         st["total_ms"] = total_ms
         st["problems"] = W
@@ -753,10 +765,14 @@ def _dense_for_device(name, table, tab):
     return table
 
 
-def device_time_evolution_core(problem, th_store_mask, I_store_mask, engine=None, shard=None, device=None):
+def device_time_evolution_core(problem, th_store_mask, I_store_mask, engine=None, shard=None, device=None,
+                               initial_planes=True):
     """
     Device replacement of time_evolution_core (reference: time_evolution.py:461-582), stencil width 3.
     Returns th_out, I_out of shape (Nj, W, n_stored + 2).
+    initial_planes=False: the two leading planes (the initial conditions theta(-2), theta(-1) and their
+    supercurrents) are left unwritten; time_evolution() asks for that when it is going to drop them unread
+    (no voltage requested), which saves two passes over (Nj, W) arrays per plane on the host.
     shard=(w0, w1), device=d: integrate only problems [w0, w1) on GPU d and return (Nj, w1 - w0, .) arrays
     (used by distributed.compute_sharded, one process per GPU).
     """
@@ -782,9 +798,12 @@ def device_time_evolution_core(problem, th_store_mask, I_store_mask, engine=None
     # every plane is written below: the two initial conditions here, the stored steps by the shards
     th_host = np.empty((int(th_mask.sum()) + 2, Nj, W))
     I_host = np.empty((int(I_mask.sum()) + 2, Nj, W))
-    th_host[1] = problem.config_at_minus_1
-    th_host[0] = problem.config_at_minus_2
-    if I_mask.any():
+    if initial_planes:
+        th_host[1] = problem.config_at_minus_1
+        th_host[0] = problem.config_at_minus_2
+    if not initial_planes:
+        pass
+    elif I_mask.any():
         # supercurrent of the initial conditions (reference: time_evolution.py:487); only read when currents
         # are stored or differentiated, so the two full-size sin passes are skipped otherwise
         I_host[1] = problem._cp(problem.config_at_minus_1)

@@ -280,8 +280,6 @@ def time_evolution(problem: TimeEvolutionProblem, core=None):
     core, finite-difference the voltage, trim helper steps. (reference: time_evolution.py:422-458)
     ``core`` (default: the GPU engine) has the signature of the reference's time_evolution_core.
     """
-    if core is None:
-        from .engine import device_time_evolution_core as core
     Nt = problem._Nt()
     store = problem.store_time_steps
     zeros = np.zeros(Nt, dtype=bool)
@@ -300,7 +298,13 @@ def time_evolution(problem: TimeEvolutionProblem, core=None):
         if has_L:
             V_I_store_mask[Vt_ids] = True
 
-    th_out, I_out = core(problem, V_th_store_mask, V_I_store_mask)
+    if core is None:
+        # the initial-condition planes are only read by the voltage stencil below
+        from .engine import device_time_evolution_core
+        th_out, I_out = device_time_evolution_core(problem, V_th_store_mask, V_I_store_mask,
+                                                   initial_planes=bool(problem.store_voltage))
+    else:
+        th_out, I_out = core(problem, V_th_store_mask, V_I_store_mask)
 
     V_out = None
     if problem.store_voltage:
