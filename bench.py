@@ -298,6 +298,8 @@ def main():
         import torch
         import torch.distributed as td
         torch.cuda.set_device(local_rank)
+        # NCCL's own banner ("NCCL version ...") goes to stdout by default: keep stdout for the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         td.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist = td
     out = run_ours(args, rank, world, local_rank, dist)

@@ -1,6 +1,6 @@
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-for dbg in 0 64; do
+for dbg in 0; do
 JJ_SUB_DEBUG=$dbg JJ_BENCH_INNER=300 JJ_BENCH_SKIP_E2E=1 timeout 300 python bench.py --steps 3 --warmup 2 > gpurun_out/it.json 2> gpurun_out/it.err
 python -c "
 import json

@@ -133,6 +133,26 @@ __device__ __forceinline__ void stg_hint_d2(double* p, double2 v, unsigned long 
     asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.256): four problems of one junction in one request
+struct double4v { double2 lo, hi; };
+__device__ __forceinline__ double4v ldg256_hint(const double* p, unsigned long long pol) {
+    double4v v;
+    asm volatile("ld.global.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=d"(v.lo.x), "=d"(v.lo.y), "=d"(v.hi.x), "=d"(v.hi.y) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ double4v ldg256(const double* p) {
+    double4v v;
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.lo.x), "=d"(v.lo.y), "=d"(v.hi.x), "=d"(v.hi.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg256_hint(double* p, double2 lo, double2 hi, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "d"(lo.x), "d"(lo.y), "d"(hi.x), "d"(hi.y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void stg256(double* p, double2 lo, double2 hi) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(lo.x), "d"(lo.y), "d"(hi.x), "d"(hi.y) : "memory");
+}
+
 struct Cursor {
     int t0, t1, s;
     const unsigned char* pA;      // + lane*8: A fragment of the first step of the current ring block
@@ -404,12 +424,10 @@ __device__ __forceinline__ void junction_item(const SubArgs& a, const AmpCache<8
             return;
         }
     }
-    stg_hint_d2(a.rth + sidx, make_double2(th1[0], th1[1]), pol_first);
-    stg_hint_d2(a.rth + sidx + 2, make_double2(th1[2], th1[3]), pol_first);
+    stg256_hint(a.rth + sidx, make_double2(th1[0], th1[1]), make_double2(th1[2], th1[3]), pol_first);
     double xn[4];
     next_x<DEF>(a, rIc.x, rc.x, rc.y, rb.x, rb.y, ac->T[n & 1] + q, ac->Is[n & 1] + q, ri.z, w, n, th1, th2, xn);
-    double2* xo = reinterpret_cast<double2*>(a.rx + sidx);
-    xo[0] = make_double2(xn[0], xn[1]); xo[1] = make_double2(xn[2], xn[3]);
+    stg256(a.rx + sidx, make_double2(xn[0], xn[1]), make_double2(xn[2], xn[3]));
 }
 
 template <int NG, bool DEF>
@@ -457,8 +475,8 @@ __device__ void junction_pass(const SubArgs& a, const AmpCache<8 * NG>* ac, int 
     x0 = x1 = t0 = t1 = rIc = rc = rb = make_double2(0.0, 0.0);
     if ((int)threadIdx.x < total) {
         const size_t si = sbase + (size_t)threadIdx.x * 4;
-        x0 = ldg_hint_d2(a.rx + si, pol_first); x1 = ldg_hint_d2(a.rx + si + 2, pol_first);
-        t0 = ldg_hint_d2(a.rth + si, pol_first); t1 = ldg_hint_d2(a.rth + si + 2, pol_first);
+        const double4v xv = ldg256_hint(a.rx + si, pol_first), tv = ldg256_hint(a.rth + si, pol_first);
+        x0 = xv.lo; x1 = xv.hi; t0 = tv.lo; t1 = tv.hi;
         const double2* rec = reinterpret_cast<const double2*>(a.jrec + 8 * (size_t)(jlo + threadIdx.x / G));
         rIc = __ldg(rec); rc = __ldg(rec + 1); rb = __ldg(rec + 2); ri = __ldg(reinterpret_cast<const int4*>(rec + 3));
     }
@@ -472,8 +490,8 @@ __device__ void junction_pass(const SubArgs& a, const AmpCache<8 * NG>* ac, int 
         nx0 = nx1 = nt0 = nt1 = nIc = nc = nb = make_double2(0.0, 0.0);
         if (idx + NT < total) {
             const size_t si = sbase + (size_t)(idx + NT) * 4;
-            nx0 = ldg_hint_d2(a.rx + si, pol_first); nx1 = ldg_hint_d2(a.rx + si + 2, pol_first);
-            nt0 = ldg_hint_d2(a.rth + si, pol_first); nt1 = ldg_hint_d2(a.rth + si + 2, pol_first);
+            const double4v xv = ldg256_hint(a.rx + si, pol_first), tv = ldg256_hint(a.rth + si, pol_first);
+            nx0 = xv.lo; nx1 = xv.hi; nt0 = tv.lo; nt1 = tv.hi;
             const double2* rec = reinterpret_cast<const double2*>(a.jrec + 8 * (size_t)(jlo + (idx + NT) / G));
             nIc = __ldg(rec); nc = __ldg(rec + 1); nb = __ldg(rec + 2); ni = __ldg(reinterpret_cast<const int4*>(rec + 3));
         }
@@ -525,8 +543,8 @@ __device__ void face_pass(const SubArgs& a, const AmpCache<8 * NG>* ac, int s, i
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     // absent entries (-1) read junction 0 with coefficient 0; x' was written by this block (plain loads)
-                    const double2* xp = reinterpret_cast<const double2*>(a.rx + tbase + (size_t)max(jp[u][k], 0) * PC);
-                    xa[u][k] = xp[0]; xb[u][k] = xp[1];
+                    const double4v xv = ldg256(a.rx + tbase + (size_t)max(jp[u][k], 0) * PC);
+                    xa[u][k] = xv.lo; xb[u][k] = xv.hi;
                 }
             }
 #pragma unroll
