@@ -924,7 +924,10 @@ __device__ void top_product_areg(const SubArgs& a, double* buf, int RB, int KQ, 
     const int nkb = KS / KB;
     const unsigned long long pol = policy_evict_last();
     for (int task = worker; task < n_tasks; task += n_workers) {
-        const int gp = task % GP, nb = (task / GP) % NB, c = c0 + task / (GP * NB);
+        // chunk-minor task order: blocks that run at the same time multiply the SAME row block of the inverse by
+        // different problem chunks, so its A fragments are read from HBM once and hit in L2 for the other chunks
+        // (large circuits: the packed inverse is hundreds of MB, far more than the L2)
+        const int c = c0 + task % nc, nb = (task / nc) % NB, gp = task / (nc * NB);
         const int rt = nb * RB + rtl;
         const bool active = rtl < RB && rt < RT;
         // B fragments are staged as [kk][n ^ 4*(kk>>1)] (see top_product_ksplit)
@@ -1099,13 +1102,17 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
         }
     }
     // A fragments in registers, B ring of KM k-steps per warp and stage (largest KM whose ring holds >= 3 stages)
-    int top_ar = 0;
-    if (top_kq >= 2 && !(a.dbg & 64)) {
+    int top_ar = 0, ar_kq = top_kq, ar_s = top_s;
+    if (a.n_top > 0 && top_rb > 0 && !(a.dbg & 64)) {
         const int stage_bytes = a.stage_rows * (PC + 2) * 8, GWr = NG < 4 ? NG : 4;
+        if (ar_kq < 2) {            // many row tiles per block (large tops): one K slot, a warp walks the whole K range
+            ar_kq = max(1, NWARPS / top_rb);
+            while (ar_kq > 1 && (a.n_top_pad / 4) % ar_kq != 0) --ar_kq;
+        }
         for (int km = 4; km >= 1 && top_ar == 0; km >>= 1) {
-            const int sb = GWr * top_kq * km * 256;
-            if ((a.n_top_pad / 4) % (top_kq * km) == 0 && sb / 16 <= NT && 3 * sb <= stage_bytes &&
-                NWARPS * GWr * 64 * 8 <= stage_bytes) { top_ar = km; top_s = min(4, stage_bytes / sb); }
+            const int sb = GWr * ar_kq * km * 256;
+            if ((a.n_top_pad / 4) % (ar_kq * km) == 0 && sb / 16 <= NT && 3 * sb <= stage_bytes &&
+                NWARPS * GWr * 64 * 8 <= stage_bytes) { top_ar = km; ar_s = min(4, stage_bytes / sb); }
         }
     }
     if (a.dbg_b) {
@@ -1130,9 +1137,9 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
         grid_barrier(a.bar, bar_target);
         top_assemble<NG>(a, 0, 0, a.n_chunks, blockIdx.x, gridDim.x);
         grid_barrier(a.bar, bar_target);
-        if (top_ar == 4) top_product_areg<NG, 4>(a, stage, top_rb, top_kq, top_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
-            else if (top_ar == 2) top_product_areg<NG, 2>(a, stage, top_rb, top_kq, top_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
-            else if (top_ar == 1) top_product_areg<NG, 1>(a, stage, top_rb, top_kq, top_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
+        if (top_ar == 4) top_product_areg<NG, 4>(a, stage, top_rb, ar_kq, ar_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
+            else if (top_ar == 2) top_product_areg<NG, 2>(a, stage, top_rb, ar_kq, ar_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
+            else if (top_ar == 1) top_product_areg<NG, 1>(a, stage, top_rb, ar_kq, ar_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
             else if (top_kq >= 2 && top_km == 2) top_product_ksplit<NG, 2>(a, stage, top_rb, top_kq, top_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
             else if (top_kq >= 2) top_product_ksplit<NG, 1>(a, stage, top_rb, top_kq, top_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
             else if (top_kb == 4) top_product<NG, 4>(a, stage, top_rb, top_s); else if (top_kb == 2) top_product<NG, 2>(a, stage, top_rb, top_s);
@@ -1224,9 +1231,9 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
             top_assemble<NG>(a, n, c, 1, s, a.P);
             group_barrier(ctr, bar_target, a.P);
             if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 5] += tn - tq; tq = tn; }
-            if (top_ar == 4) top_product_areg<NG, 4>(a, stage, top_rb, top_kq, top_s, c, 1, s, a.P);
-            else if (top_ar == 2) top_product_areg<NG, 2>(a, stage, top_rb, top_kq, top_s, c, 1, s, a.P);
-            else if (top_ar == 1) top_product_areg<NG, 1>(a, stage, top_rb, top_kq, top_s, c, 1, s, a.P);
+            if (top_ar == 4) top_product_areg<NG, 4>(a, stage, top_rb, ar_kq, ar_s, c, 1, s, a.P);
+            else if (top_ar == 2) top_product_areg<NG, 2>(a, stage, top_rb, ar_kq, ar_s, c, 1, s, a.P);
+            else if (top_ar == 1) top_product_areg<NG, 1>(a, stage, top_rb, ar_kq, ar_s, c, 1, s, a.P);
             else if (top_km == 2) top_product_ksplit<NG, 2>(a, stage, top_rb, top_kq, top_s, c, 1, s, a.P);
             else top_product_ksplit<NG, 1>(a, stage, top_rb, top_kq, top_s, c, 1, s, a.P);
             if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 6] += tn - tq; tq = tn; }
@@ -1238,9 +1245,9 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
             top_assemble<NG>(a, n, 0, a.n_chunks, blockIdx.x, gridDim.x);
             grid_barrier(a.bar, bar_target);
             if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 5] += tn - tq; tq = tn; }
-            if (top_ar == 4) top_product_areg<NG, 4>(a, stage, top_rb, top_kq, top_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
-            else if (top_ar == 2) top_product_areg<NG, 2>(a, stage, top_rb, top_kq, top_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
-            else if (top_ar == 1) top_product_areg<NG, 1>(a, stage, top_rb, top_kq, top_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
+            if (top_ar == 4) top_product_areg<NG, 4>(a, stage, top_rb, ar_kq, ar_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
+            else if (top_ar == 2) top_product_areg<NG, 2>(a, stage, top_rb, ar_kq, ar_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
+            else if (top_ar == 1) top_product_areg<NG, 1>(a, stage, top_rb, ar_kq, ar_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
             else if (top_kq >= 2 && top_km == 2) top_product_ksplit<NG, 2>(a, stage, top_rb, top_kq, top_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
             else if (top_kq >= 2) top_product_ksplit<NG, 1>(a, stage, top_rb, top_kq, top_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
             else if (top_kb == 4) top_product<NG, 4>(a, stage, top_rb, top_s); else if (top_kb == 2) top_product<NG, 2>(a, stage, top_rb, top_s);

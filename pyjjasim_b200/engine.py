@@ -84,11 +84,18 @@ class CircuitTables:
         barrier of each time step."""
         weights = np.ones(n_parts)
         best, best_spread = F, None
+        if A.shape[0] > 30000:
+            rounds = 1              # every round is a full ordering + factorisation: seconds to minutes at this size
         for _ in range(rounds + 1):
             if F.blk_part is None or int(np.max(F.blk_part)) + 1 != n_parts:
                 return best
             self._finish_tables(A, F.perm.astype(np.int64))
-            plan = subdomain_plan(F, self.junc_face, None, 4)
+            try:
+                plan = subdomain_plan(F, self.junc_face, None, 4)
+            except ValueError:
+                # subdomains too large for the shared-memory engine (big circuits): nothing to balance, the
+                # streaming engine will run this circuit
+                return best
             steps = np.array([p["n_steps"] for p in plan.prog], dtype=np.double)
             cost = 41.0 * steps + 52.0 * np.diff(plan.junc_ptr) + 42.0 * (plan.n_loc + plan.n_halo)
             spread = float(cost.max() / cost.mean())
@@ -258,6 +265,10 @@ class _ResidentTables:
         self.face_fidx = fidx
 
 
+_ROWS_FIT = 560               # local rows of a subdomain that still fit in 227 KB at 32 problems with a ~15 % halo
+_ROWS_PER_SUBDOMAIN = 450     # target when a circuit has to be cut finer than one subdomain per (SM, chunk) anyway
+
+
 def subdomain_layout(Nf, W, n_sm=148):
     """(NG, chunks, n_parts) of the subdomain engine for W problems on a circuit with Nf faces: chunks of 8*NG
     problems, and as many subdomains as fill the SMs with (subdomain, chunk) thread blocks - but none smaller
@@ -266,6 +277,19 @@ def subdomain_layout(Nf, W, n_sm=148):
     NG = 4 if Wp > 16 else 2 if Wp > 8 else 1
     chunks = (Wp + 8 * NG - 1) // (8 * NG)
     n_parts = max(1, min(n_sm // chunks, Nf // 64))
+    # larger circuits: the rows of a subdomain (local + halo) must fit in a block's shared memory, so there are more
+    # (subdomain, chunk) items than SMs and every block loops over several items per time step. With n_sm // k
+    # subdomains the items spread evenly when the chunk count is a multiple of k; k = 1 pins one subdomain to each block.
+    need = -(-Nf // _ROWS_PER_SUBDOMAIN)
+    if Nf <= _ROWS_FIT * n_parts:
+        pass                                        # one item per block and the subdomains fit (cfg2: 545 rows each)
+    elif need > n_parts and need <= n_sm:
+        n_parts = n_sm // max(1, n_sm // need)
+    elif need > 4 * n_sm:
+        pass                                        # the dense top cannot follow (n_top grows like sqrt(parts * Nf)): streaming engine
+    elif need > n_sm:
+        half = max(1, n_sm // 2)
+        n_parts = -(-need // half) * half           # the dense top limits how far this goes (subdomain_plan raises)
     return NG, chunks, n_parts
 
 

@@ -341,6 +341,11 @@ def subdomain_plan(F, junc_face, d, NG, n_warps=RES_WARPS, groups=None):
     plan.P, plan.NG, plan.PC, plan.d = P, NG, PC, d
     plan.n_top, plan.top_rows = n_top, top_rows.astype(np.int32)
     plan.n_top_pad = (n_top + 31) // 32 * 32
+    if plan.n_top_pad > 8192:
+        # the separators above the cut are solved by a DENSE inverse: 8192^2 float64 is 0.5 GB and 67 M multiply-adds
+        # per problem and time step; beyond that the circuit needs a multi-level top (not built) and runs on the
+        # streaming engine
+        raise ValueError("subdomain plan: %d top rows are too many for the dense top product" % n_top)
     loc = [np.flatnonzero(row_sub == s) for s in range(P)]
     halo = [np.array(sorted(coupled[s]), dtype=np.int64) for s in range(P)]
     plan.n_loc = np.array([l.size for l in loc], dtype=np.int32)

@@ -356,3 +356,27 @@ def test_device_vortex_observables_are_exact(engine):
         eng_mod._release_engine(0, key, e, True)
     finally:
         os.environ.pop("JJ_ENGINE", None)
+
+
+def test_larger_circuit_runs_on_subdomain_engine_with_several_items_per_block():
+    # a circuit too large for one subdomain per (SM, chunk) pair (the cfg3 / cfg4 regime, scaled down): the layout cuts
+    # it finer, every block loops over several (subdomain, chunk) items per time step, the top product takes the
+    # grid-wide register-A path; per-step parity with the oracle
+    from pyjjasim_b200 import engine
+    a = pj.SquareArray(80, 80)
+    W, Nt = 512, 12
+    NG, chunks, n_parts = engine.subdomain_layout(a._Nf(), W, engine._sm_count(0))
+    assert n_parts * chunks > engine._sm_count(0)
+    Is = pj.RankOneSource(a.current_base(angle=0), np.linspace(0.2, 1.8, W))
+    kw = dict(circuit=a, time_step=0.05, time_step_count=Nt, external_flux=0.1, current_sources=Is,
+              store_time_steps=[3, Nt - 1], store_current=False, store_voltage=False)
+    prob = pj.TimeEvolutionProblem(**kw)
+    res = prob.compute()
+    st = engine.last_run_stats[0]
+    assert st["engine"] == 3 and st["cluster_size"] == n_parts
+    kw["current_sources"] = (a.current_base(angle=0)[:, None] * np.linspace(0.2, 1.8, W)[None, :])[:, :, None]
+    args, extra = cases.oracle_inputs(kw)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        th, _, _ = oracle.time_evolution(*args, W, **extra)
+    assert np.max(np.abs(res.theta - th)) <= 1e-9
