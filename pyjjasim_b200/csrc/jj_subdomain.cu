@@ -353,6 +353,11 @@ __device__ __forceinline__ void next_x(const SubArgs& a, double Ic, double c1, d
                                        const double* ampT, const double* ampIs, int jo, int w, long long n,
                                        const double th1[4], const double th2[4], double xn[4]) {
     double fl[4] = {0, 0, 0, 0};
+    if (a.dbg & 128) {      // timing experiment (JJ_SUB_DEBUG=128): linear CPR, no noise -> the pass is loads + stores + a few FMAs
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xn[k] = (Ic * (2.0 * th1[k] - th2[k]) + c1 * th1[k] + c2 * th2[k]) - isb * ampIs[k];
+        return;
+    }
     if (a.T.kind != KIND_ZERO) {
         double z[4];
         if (a.noise_K > 0) {
@@ -424,10 +429,10 @@ __device__ __forceinline__ void junction_item(const SubArgs& a, const AmpCache<8
             return;
         }
     }
-    stg256_hint(a.rth + sidx, make_double2(th1[0], th1[1]), make_double2(th1[2], th1[3]), pol_first);
+    if (!(a.dbg & 256)) stg256_hint(a.rth + sidx, make_double2(th1[0], th1[1]), make_double2(th1[2], th1[3]), pol_first);
     double xn[4];
     next_x<DEF>(a, rIc.x, rc.x, rc.y, rb.x, rb.y, ac->T[n & 1] + q, ac->Is[n & 1] + q, ri.z, w, n, th1, th2, xn);
-    stg256(a.rx + sidx, make_double2(xn[0], xn[1]), make_double2(xn[2], xn[3]));
+    if (!(a.dbg & 256) || xn[0] == 12345.678) /* the test keeps x' live in the experiment */ stg256(a.rx + sidx, make_double2(xn[0], xn[1]), make_double2(xn[2], xn[3]));
 }
 
 template <int NG, bool DEF>
@@ -488,7 +493,7 @@ __device__ void junction_pass(const SubArgs& a, const AmpCache<8 * NG>* ac, int 
         double2 nx0, nx1, nt0, nt1, nIc, nc, nb;
         int4 ni = make_int4(0, 0, 0, 0);
         nx0 = nx1 = nt0 = nt1 = nIc = nc = nb = make_double2(0.0, 0.0);
-        if (idx + NT < total) {
+        if (idx + NT < total && !(a.dbg & 256)) {      // JJ_SUB_DEBUG=256 (timing experiment): no state traffic
             const size_t si = sbase + (size_t)(idx + NT) * 4;
             const double4v xv = ldg256_hint(a.rx + si, pol_first), tv = ldg256_hint(a.rth + si, pol_first);
             nx0 = xv.lo; nx1 = xv.hi; nt0 = tv.lo; nt1 = tv.hi;

@@ -328,3 +328,24 @@ def test_inputs_replaced_after_construction_are_honoured():
     assert s["T"].kind == RANK1 and s["T"].static and np.allclose(s["T"].amp_chunk(0, 1), [[0.1, 0.2, 0.3]])
     prob.temperature = np.zeros((1, 1, 5))
     assert engine._classify_all(prob, tab)["T"].kind == ZERO
+
+
+def test_subdomain_layout_rules():
+    # (problem groups per chunk, chunks, subdomains) of the subdomain engine on a 148-SM device
+    from pyjjasim_b200.engine import subdomain_layout
+    assert subdomain_layout(9801, 256) == (4, 8, 18)          # cfg2: one (subdomain, chunk) item per block, 144 blocks
+    assert subdomain_layout(361, 32) == (4, 1, 5)             # cfg1: no subdomain smaller than ~64 faces
+    NG, chunks, P = subdomain_layout(65025, 512)              # cfg4 per GPU: cut finer than one item per block
+    assert (NG, chunks, P) == (4, 16, 148) and 65025 / P <= 450
+    NG, chunks, P = subdomain_layout(79401, 512)              # cfg3: more subdomains than SMs, in units of half the SM count
+    assert P == 222 and 79401 / P <= 450
+    assert subdomain_layout(998001, 64)[2] == 74              # cfg5: the dense top cannot follow; classic rule, streaming engine
+    assert subdomain_layout(100, 8) == (1, 1, 1)
+
+
+def test_large_subdomain_plan_falls_back_instead_of_raising():
+    # subdomains too large for shared memory must not make the tables constructor fail (the streaming engine runs them)
+    from pyjjasim_b200 import engine
+    a = pj.SquareArray(70, 70)
+    tab = engine.CircuitTables(a, 0.05, n_parts=2)            # 2 400 rows per subdomain
+    assert tab.choose_subdomain(64) is None
