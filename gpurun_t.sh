@@ -1,1 +1,2 @@
-timeout 900 python -m pytest tests -m gpu -x -q -k "larger_circuit" 2>&1 | tail -5
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3

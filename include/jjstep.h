@@ -36,7 +36,7 @@ enum { JJ_SRC_IS = 0, JJ_SRC_F = 1, JJ_SRC_VS = 2, JJ_SRC_T = 3 };
 /* device forms of an input (see pyjjasim_b200/sources.py) */
 enum { JJ_KIND_ZERO = 0, JJ_KIND_RANK1 = 1, JJ_KIND_DENSE = 2 };
 /* step engines */
-enum { JJ_ENGINE_AUTO = 0,      /* pick RESIDENT when the problem fits, else STREAMING */
+enum { JJ_ENGINE_AUTO = 0,      /* first that applies: SUBDOMAIN (a plan was set and the inputs are rank one), RESIDENT, STREAMING */
        JJ_ENGINE_STREAMING = 1, /* problem-minor (Nj, W) arrays in HBM, one kernel per phase */
        JJ_ENGINE_RESIDENT = 2,  /* persistent kernel: a thread-block cluster owns a tile of problems for the
                                    whole time loop, right-hand sides live in shared memory */

@@ -380,3 +380,66 @@ def test_larger_circuit_runs_on_subdomain_engine_with_several_items_per_block():
         warnings.simplefilter("ignore")
         th, _, _ = oracle.time_evolution(*args, W, **extra)
     assert np.max(np.abs(res.theta - th)) <= 1e-9
+
+
+# ---------------------------------------------------------------- full-size configurations: size-independent properties
+def _flux_and_kcl(a, res, f, Is_last):
+    # flux quantisation A theta + 2 pi f = 0 and Kirchhoff's current law M (I - Is) = 0 hold at every stored step
+    # whatever happened before it: a solve that is wrong anywhere in the circuit breaks them
+    A, M = a.get_cycle_matrix(), a.get_cut_matrix()
+    th, I = res.theta[:, :, -1], res.current[:, :, -1]
+    scale = max(1.0, float(np.max(np.abs(th))))
+    return (float(np.max(np.abs(A @ th + 2 * np.pi * f))) / scale, float(np.max(np.abs(M @ (I - Is_last)))))
+
+
+def test_full_size_cfg2_invariants_and_chunking():
+    # BASELINE config 2 at full size (SquareArray(100,100), 256 temperatures, f = 0.1, dt = 0.5) over a short horizon
+    a = pj.SquareArray(100, 100)
+    W, Nt = 256, 60
+    T = np.geomspace(1e-2, 1.0, W)[None, :, None]
+    kw = dict(circuit=a, time_step=0.5, time_step_count=Nt, external_flux=0.1, temperature=T, noise_seed=1234,
+              store_time_steps=[Nt // 3, Nt - 1], store_voltage=False)
+    res = pj.TimeEvolutionProblem(**kw).compute()
+    from pyjjasim_b200 import engine
+    assert engine.last_run_stats[0]["engine"] == 3
+    flux, kcl = _flux_and_kcl(a, res, 0.1, 0.0)
+    assert flux < 1e-10 and kcl < 1e-9
+    # the hotter problems hold more vortices at the end than the coldest ones (the noise really is per problem)
+    n = res.get_vortex_configuration()[:, :, -1]
+    assert np.abs(n[:, -32:]).sum() > np.abs(n[:, :32]).sum()
+    assert np.all(np.isfinite(res.theta))
+
+
+def test_full_size_cfg4_share_invariants():
+    # BASELINE config 4 (SquareArray(256,256) with capacitance, DC + AC drive) with one GPU's share of 512 problems:
+    # 148 subdomains, 16 items per block, dense top of ~5 800 rows; a few steps, then the invariants
+    a = pj.SquareArray(256, 256)
+    a.set_capacitance(1.0)
+    W, Nt, dt = 512, 6, 0.05
+    base = a.current_base(angle=0)
+    IDC, IA = np.linspace(0, 2, W), np.linspace(0, 3, W)
+    Is = pj.RankOneSource(base, lambda i: IDC + IA * np.sin(0.25 * i * dt), problem_count=W)
+    res = pj.TimeEvolutionProblem(a, time_step=dt, time_step_count=Nt, current_sources=Is, external_flux=0.05,
+                                  temperature=0.01 * np.ones((1, W, 1)), noise_seed=5, store_time_steps=[Nt - 1],
+                                  store_voltage=False).compute()
+    from pyjjasim_b200 import engine
+    st = engine.last_run_stats[0]
+    assert st["engine"] == 3 and st["cluster_size"] == 148
+    flux, kcl = _flux_and_kcl(a, res, 0.05, Is(Nt - 1))
+    assert flux < 1e-10 and kcl < 1e-9
+
+
+def test_annealing_shards_over_devices():
+    # two GPUs: problems never interact and the temperatures are per problem, so the sharded schedule equals the
+    # single-device one exactly
+    import ctypes
+    from pyjjasim_b200 import _lib
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    if lib.jj_create(1, ctypes.byref(h)) != 0:
+        pytest.skip("needs two CUDA devices")
+    lib.jj_destroy(h)
+    kw, Z, ap, (theta, n, profiles) = _anneal("anneal_small", "auto")
+    kw2, Z2, ap2, (theta2, n2, profiles2) = _anneal("anneal_small", "auto", devices=[0, 1])
+    assert np.array_equal(profiles, profiles2) and np.array_equal(n, n2)
+    assert np.max(np.abs(theta - theta2)) <= 1e-9
