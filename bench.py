@@ -297,6 +297,11 @@ def main():
         return
 
     dist = None
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner at communicator
+    # creation) is sent to stderr by pointing fd 1 at fd 2 until the line is ready
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         import torch
         import torch.distributed as td
@@ -311,7 +316,10 @@ def main():
             out["cpu_baseline"] = {"skipped": True} if os.environ.get("JJ_BENCH_SKIP_E2E") else cpu_reference(1, 0)
         except Exception as e:
             out["cpu_baseline"] = {"error": repr(e)}
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(out), flush=True)
+        os.dup2(2, 1)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
