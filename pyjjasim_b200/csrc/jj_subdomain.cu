@@ -1114,7 +1114,7 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
             ar_kq = max(1, NWARPS / top_rb);
             while (ar_kq > 1 && (a.n_top_pad / 4) % ar_kq != 0) --ar_kq;
         }
-        for (int km = 4; km >= 1 && top_ar == 0; km >>= 1) {
+        for (int km = 8; km >= 1 && top_ar == 0; km >>= 1) {
             const int sb = GWr * ar_kq * km * 256;
             if ((a.n_top_pad / 4) % (ar_kq * km) == 0 && sb / 16 <= NT && 3 * sb <= stage_bytes &&
                 NWARPS * GWr * 64 * 8 <= stage_bytes) { top_ar = km; ar_s = min(4, stage_bytes / sb); }
@@ -1142,7 +1142,8 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
         grid_barrier(a.bar, bar_target);
         top_assemble<NG>(a, 0, 0, a.n_chunks, blockIdx.x, gridDim.x);
         grid_barrier(a.bar, bar_target);
-        if (top_ar == 4) top_product_areg<NG, 4>(a, stage, top_rb, ar_kq, ar_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
+        if (top_ar == 8) top_product_areg<NG, 8>(a, stage, top_rb, ar_kq, ar_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
+        else if (top_ar == 4) top_product_areg<NG, 4>(a, stage, top_rb, ar_kq, ar_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
             else if (top_ar == 2) top_product_areg<NG, 2>(a, stage, top_rb, ar_kq, ar_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
             else if (top_ar == 1) top_product_areg<NG, 1>(a, stage, top_rb, ar_kq, ar_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
             else if (top_kq >= 2 && top_km == 2) top_product_ksplit<NG, 2>(a, stage, top_rb, top_kq, top_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
@@ -1236,7 +1237,8 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
             top_assemble<NG>(a, n, c, 1, s, a.P);
             group_barrier(ctr, bar_target, a.P);
             if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 5] += tn - tq; tq = tn; }
-            if (top_ar == 4) top_product_areg<NG, 4>(a, stage, top_rb, ar_kq, ar_s, c, 1, s, a.P);
+            if (top_ar == 8) top_product_areg<NG, 8>(a, stage, top_rb, ar_kq, ar_s, c, 1, s, a.P);
+            else if (top_ar == 4) top_product_areg<NG, 4>(a, stage, top_rb, ar_kq, ar_s, c, 1, s, a.P);
             else if (top_ar == 2) top_product_areg<NG, 2>(a, stage, top_rb, ar_kq, ar_s, c, 1, s, a.P);
             else if (top_ar == 1) top_product_areg<NG, 1>(a, stage, top_rb, ar_kq, ar_s, c, 1, s, a.P);
             else if (top_km == 2) top_product_ksplit<NG, 2>(a, stage, top_rb, top_kq, top_s, c, 1, s, a.P);
@@ -1250,7 +1252,8 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
             top_assemble<NG>(a, n, 0, a.n_chunks, blockIdx.x, gridDim.x);
             grid_barrier(a.bar, bar_target);
             if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 5] += tn - tq; tq = tn; }
-            if (top_ar == 4) top_product_areg<NG, 4>(a, stage, top_rb, ar_kq, ar_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
+            if (top_ar == 8) top_product_areg<NG, 8>(a, stage, top_rb, ar_kq, ar_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
+            else if (top_ar == 4) top_product_areg<NG, 4>(a, stage, top_rb, ar_kq, ar_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
             else if (top_ar == 2) top_product_areg<NG, 2>(a, stage, top_rb, ar_kq, ar_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
             else if (top_ar == 1) top_product_areg<NG, 1>(a, stage, top_rb, ar_kq, ar_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
             else if (top_kq >= 2 && top_km == 2) top_product_ksplit<NG, 2>(a, stage, top_rb, top_kq, top_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
