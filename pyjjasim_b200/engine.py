@@ -17,6 +17,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import threading
+import weakref
 
 import numpy as np
 import scipy.sparse
@@ -314,14 +315,18 @@ def _tables_for(circuit, dt, n_parts=None):
            os.environ.get("JJ_LEAF_SIZE", ""), n_parts)
     with _engine_lock:
         hit = _tables_cache.get(key)
-        if hit is not None:
-            return hit
+        if hit is not None and hit[0]() is circuit:       # id() values are reused after garbage collection
+            return hit[1]
     tab = CircuitTables(circuit, dt, n_parts=n_parts)
+    try:
+        ref = weakref.ref(circuit)
+    except TypeError:
+        ref = (lambda c=circuit: c)
     with _engine_lock:
         # a few entries: an annealing schedule alternates between dt and dt / 2 on the same circuit
         while len(_tables_cache) >= 4:
             _tables_cache.pop(next(iter(_tables_cache)))
-        _tables_cache[key] = tab
+        _tables_cache[key] = (ref, tab)
     return tab
 
 
