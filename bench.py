@@ -101,8 +101,8 @@ def run_ours(args, rank, world, local_rank, dist):
     n_parts = None
     if os.environ.get("JJ_ENGINE", "auto") in ("auto", "subdomain") and not os.environ.get("JJ_SUBDOMAIN"):
         n_parts = engine.subdomain_layout(a._Nf(), W, engine._sm_count(local_rank))[2]
-        if os.environ.get("JJ_BENCH_NPARTS"):        # experiments: same decomposition at another problem count
-            n_parts = int(os.environ["JJ_BENCH_NPARTS"])
+    if os.environ.get("JJ_BENCH_NPARTS"):            # experiments: another decomposition / problem count
+        n_parts = int(os.environ["JJ_BENCH_NPARTS"])
     tab = engine.CircuitTables(a, DT, n_parts=n_parts)
     eng = engine.DeviceEngine(local_rank)
     eng.set_circuit(tab, pj.DefaultCPR())

@@ -602,13 +602,14 @@ __device__ __forceinline__ void group_barrier(unsigned* ctr, unsigned& target, u
     __syncthreads();
     if (threadIdx.x == 0) {
         target += members;
-        __threadfence();
-        atomicAdd(ctr, 1u);
+        // arrive with release semantics (cumulative over the writes of the whole block, which the __syncthreads above
+        // ordered before this thread) without waiting for the atomic's round trip; the acquire load of the poll is
+        // all the consumer side needs (cross-block data is read with ld.cg / cp.async.cg / after this point only)
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
         unsigned seen;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
         } while (seen < target);
-        __threadfence();
     }
     __syncthreads();
 }
@@ -664,7 +665,7 @@ __device__ void top_product_direct(const SubArgs& a) {
         for (int ks0 = 0; ks0 < KS; ks0 += 8) {
             double ac[8], bc[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { ac[j] = __ldg(A + (size_t)(ks0 + j) * 32); bc[j] = B[(size_t)(ks0 + j) * 4 * PC]; }
+            for (int j = 0; j < 8; ++j) { ac[j] = __ldg(A + (size_t)(ks0 + j) * 32); bc[j] = __ldcg(B + (size_t)(ks0 + j) * 4 * PC); }
 #pragma unroll
             for (int j = 0; j < 8; j += 2) {
                 dmma884(c00, c01, ac[j], bc[j]);
