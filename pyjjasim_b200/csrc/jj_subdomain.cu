@@ -51,6 +51,8 @@ struct SubArgs {
     int max_np, max_levels, max_tiles;
     const SubProgDev* prog;
     const int *n_loc, *n_halo, *hptr, *halo_top, *tptr, *tslot, *top_face;
+    const int4* tslot4;             // [n_top] the (at most four) slots of a top row, -1 padded; null when a row has more
+    const double* topF;             // [n_top] flux base of each top row (gathered per launch), null without rank-one flux
     const double* SinvP;
     const int* junc_ptr; const int* junc_orig; const int2* junc_row; const char2* junc_sign;
     int face_K; const int* face_ell_j; const double* face_ell_c; const int* face_fidx;
@@ -86,6 +88,7 @@ struct SubState {
     SubProgDev* prog = nullptr;
     int *n_loc = nullptr, *n_halo = nullptr, *hptr = nullptr, *halo_top = nullptr, *tptr = nullptr, *tslot = nullptr, *top_face = nullptr;
     double* SinvP = nullptr;
+    int4* tslot4 = nullptr; double* topF = nullptr;
     int *junc_ptr = nullptr, *junc_orig = nullptr; int2* junc_row = nullptr; char2* junc_sign = nullptr;
     int* face_ell_j = nullptr; double* face_ell_c = nullptr; int* face_fidx = nullptr;
     double *P0 = nullptr, *P1 = nullptr, *jrec = nullptr;
@@ -627,17 +630,33 @@ __device__ void top_assemble(const SubArgs& a, long long n, int c0, int nc, int 
         const int k = (int)(t % a.n_top), c = c0 + (int)(t / a.n_top);
         const int w = c * PC + q;
         double acc[4] = {0, 0, 0, 0};
-        for (int sl = a.tptr[k]; sl < a.tptr[k + 1]; ++sl) {
-            const double2* p = reinterpret_cast<const double2*>(a.ctop + ((size_t)c * a.n_slots + a.tslot[sl]) * PC + q);
-            const double2 u0 = __ldcg(p), u1 = __ldcg(p + 1);
-            acc[0] += u0.x; acc[1] += u0.y; acc[2] += u1.x; acc[3] += u1.y;
+        if (a.tslot4) {
+            // one 16-byte load names all slots of the row: two dependent memory levels instead of three; the slots
+            // are added in the same (ascending) order as the list walk below
+            const int4 s4 = __ldg(a.tslot4 + k);
+            const int sl[4] = {s4.x, s4.y, s4.z, s4.w};
+            double2 u0[4], u1[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const double2* p = reinterpret_cast<const double2*>(a.ctop + ((size_t)c * a.n_slots + max(sl[e], 0)) * PC + q);
+                u0[e] = __ldcg(p); u1[e] = __ldcg(p + 1);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (sl[e] >= 0) { acc[0] += u0[e].x; acc[1] += u0[e].y; acc[2] += u1[e].x; acc[3] += u1[e].y; }
+        } else {
+            for (int sl = a.tptr[k]; sl < a.tptr[k + 1]; ++sl) {
+                const double2* p = reinterpret_cast<const double2*>(a.ctop + ((size_t)c * a.n_slots + a.tslot[sl]) * PC + q);
+                const double2 u0 = __ldcg(p), u1 = __ldcg(p + 1);
+                acc[0] += u0.x; acc[1] += u0.y; acc[2] += u1.x; acc[3] += u1.y;
+            }
         }
         if (w < a.Wp) {
             const int g = a.top_face[k];
             if (a.dbg_b) {
                 for (int e = 0; e < 4; ++e) acc[e] += a.dbg_b[(size_t)g * a.Wp + w + e];
             } else if (a.F.kind == KIND_RANK1) {
-                const double b = __ldg(a.F.base + g);
+                const double b = a.topF ? __ldg(a.topF + k) : __ldg(a.F.base + g);
                 const double* am = a.F.table + source_row(a.F, n) * a.Wp + w;
                 for (int e = 0; e < 4; ++e) acc[e] -= TWO_PI * (b * __ldg(am + e));
             }
@@ -1268,6 +1287,12 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
     }
 }
 
+// flux base of the top rows, gathered once per launch (the assembly then needs no dependent index load for it)
+__global__ void k_sub_gather_top(int n_top, const int* top_face, const double* fbase, double* topF) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n_top) topF[k] = fbase[top_face[k]];
+}
+
 typedef void (*KernelPtr)(const SubArgs);
 
 KernelPtr pick_kernel(int NG, bool def) {
@@ -1396,6 +1421,25 @@ int subdomain_set_plan(JJHandle* h, const JJSubdomainPlan* pl) {
     if ((rc = up(h, st, &st->tptr, pl->tptr, (size_t)pl->n_top + 1))) return rc;
     if ((rc = up(h, st, &st->tslot, pl->tslot, (size_t)pl->n_slots))) return rc;
     if ((rc = up(h, st, &st->top_face, pl->top_face, (size_t)pl->n_top))) return rc;
+    {
+        // fixed-width slot lists of the top rows (a row of a planar circuit is shared by at most a few subdomains)
+        std::vector<int4> t4((size_t)std::max(pl->n_top, 1), make_int4(-1, -1, -1, -1));
+        bool fits = true;
+        for (int k = 0; k < pl->n_top && fits; ++k) {
+            const int cnt = pl->tptr[k + 1] - pl->tptr[k];
+            if (cnt > 4) { fits = false; break; }
+            int v4[4] = {-1, -1, -1, -1};
+            for (int e = 0; e < cnt; ++e) v4[e] = pl->tslot[pl->tptr[k] + e];
+            t4[k] = make_int4(v4[0], v4[1], v4[2], v4[3]);
+        }
+        st->tslot4 = nullptr;
+        if (fits && pl->n_top > 0) { if ((rc = up(h, st, &st->tslot4, t4.data(), (size_t)pl->n_top))) return rc; }
+        void* p = nullptr;
+        const size_t bytes = (size_t)std::max(pl->n_top, 1) * sizeof(double);
+        if ((rc = dev_alloc(h, &p, bytes))) return rc;
+        st->allocs.push_back(p); st->alloc_bytes.push_back(bytes);
+        st->topF = (double*)p;
+    }
     if ((rc = up(h, st, &st->SinvP, pl->Sinv_packed, (size_t)pl->n_top_pad * pl->n_top_pad))) return rc;
     if ((rc = up(h, st, &st->junc_ptr, pl->junc_ptr, (size_t)P + 1))) return rc;
     if ((rc = up(h, st, &st->junc_orig, pl->junc_orig, (size_t)Nj))) return rc;
@@ -1434,6 +1478,8 @@ static void fill_args(JJHandle* h, SubState* st, SubArgs& a) {
     a.max_np = st->max_np; a.max_levels = st->max_levels; a.max_tiles = st->max_tiles;
     a.prog = st->prog; a.n_loc = st->n_loc; a.n_halo = st->n_halo; a.hptr = st->hptr; a.halo_top = st->halo_top;
     a.tptr = st->tptr; a.tslot = st->tslot; a.top_face = st->top_face; a.SinvP = st->SinvP;
+    a.tslot4 = getenv("JJ_SUB_NO_TSLOT4") ? nullptr : st->tslot4;
+    a.topF = (h->src[JJ_SRC_F].dev.kind == KIND_RANK1 && st->n_top > 0) ? st->topF : nullptr;
     a.junc_ptr = st->junc_ptr; a.junc_orig = st->junc_orig; a.junc_row = st->junc_row; a.junc_sign = st->junc_sign;
     a.face_K = st->face_K; a.face_ell_j = st->face_ell_j; a.face_ell_c = st->face_ell_c; a.face_fidx = st->face_fidx;
     a.Nj = h->cir.Nj; a.Nf = h->cir.Nf; a.P0 = st->P0; a.P1 = st->P1; a.jrec = st->jrec; a.cpr = h->cir.cpr;
@@ -1454,6 +1500,10 @@ static int launch(JJHandle* h, SubState* st, SubArgs& a) {
             h->cir.Nj, st->junc_orig, h->cir.Ic, h->cir.c0, h->cir.c1, h->cir.c2,
             is.kind == KIND_RANK1 ? is.base : nullptr, t.kind == KIND_RANK1 ? t.base : nullptr,
             vs.kind == KIND_RANK1 ? vs.base : nullptr, st->junc_row, st->junc_sign, st->P0, st->P1, st->jrec);
+        h->launches++;
+    }
+    if (a.topF) {
+        k_sub_gather_top<<<(st->n_top + 255) / 256, 256, 0, h->stream>>>(st->n_top, st->top_face, h->src[JJ_SRC_F].dev.base, st->topF);
         h->launches++;
     }
     SCK(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem_bytes));

@@ -443,3 +443,16 @@ def test_annealing_shards_over_devices():
     kw2, Z2, ap2, (theta2, n2, profiles2) = _anneal("anneal_small", "auto", devices=[0, 1])
     assert np.array_equal(profiles, profiles2) and np.array_equal(n, n2)
     assert np.max(np.abs(theta - theta2)) <= 1e-9
+
+
+def test_annealing_single_problem_and_one_step_intervals():
+    # ragged sizes: one problem (padded to a quad on the device), intervals of a single step (no mobility to measure:
+    # the temperature only rises), no closing-run surprises
+    a = pj.SquareArray(6, 5)
+    ap = pj.AnnealingProblem(a, time_step=0.5, interval_steps=1, external_flux=0.15, problem_count=1, interval_count=6,
+                             vortex_mobility=0.01, start_T=0.2, T_factor=1.5, noise_seed=3)
+    theta, n, prof = ap.anneal()
+    assert theta.shape == (a._Nj(), 1) and n.shape == (a._Nf(), 1) and prof.shape == (6, 1)
+    assert np.allclose(prof[:, 0], 0.2 * 1.5 ** np.arange(1, 7))
+    assert np.array_equal(n, oracle.vortex_configuration(a.get_cycle_matrix(), theta))
+    assert np.max(np.abs(a.get_cycle_matrix() @ theta + 2 * np.pi * 0.15)) < 1e-10

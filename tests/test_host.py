@@ -349,3 +349,16 @@ def test_large_subdomain_plan_falls_back_instead_of_raising():
     a = pj.SquareArray(70, 70)
     tab = engine.CircuitTables(a, 0.05, n_parts=2)            # 2 400 rows per subdomain
     assert tab.choose_subdomain(64) is None
+
+
+def test_annealing_problem_input_errors_mirror_reference():
+    # the reference hands current_sources straight to TimeEvolutionProblem, where a (Nj,) array is broadcast against
+    # (Nj, W, Nt) along the TIME axis and fails; scalars and (Nj, 1, 1) arrays work
+    a = pj.SquareArray(5, 5)
+    with pytest.raises(ValueError):
+        pj.AnnealingProblem(a, current_sources=np.ones(a._Nj()), problem_count=3, interval_steps=7)._problem()
+    prob = pj.AnnealingProblem(a, current_sources=0.1 * np.ones((a._Nj(), 1, 1)), problem_count=3, interval_steps=7)._problem()
+    assert prob.get_problem_count() == 3 and prob._Is(0).shape == (a._Nj(), 3)
+    # per-face flux array
+    prob = pj.AnnealingProblem(a, external_flux=np.linspace(0, 0.3, a._Nf()), problem_count=2)._problem()
+    assert prob._f(0).shape == (a._Nf(), 2)
