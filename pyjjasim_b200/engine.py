@@ -273,11 +273,12 @@ _ROWS_PER_SUBDOMAIN = 450     # target when a circuit has to be cut finer than o
 def subdomain_layout(Nf, W, n_sm=148):
     """(NG, chunks, n_parts) of the subdomain engine for W problems on a circuit with Nf faces: chunks of 8*NG
     problems, and as many subdomains as fill the SMs with (subdomain, chunk) thread blocks - but none smaller
-    than ~64 faces (below that the top product and the barriers cost more than the local sweeps save)."""
+    than ~45 faces (below that the top product and the barriers cost more than the local sweeps save; cfg1: 8 x 45
+    faces run 6 % faster than 5 x 72)."""
     Wp = (W + 3) // 4 * 4
     NG = 4 if Wp > 16 else 2 if Wp > 8 else 1
     chunks = (Wp + 8 * NG - 1) // (8 * NG)
-    n_parts = max(1, min(n_sm // chunks, Nf // 64))
+    n_parts = max(1, min(n_sm // chunks, Nf // 45))
     # larger circuits: the rows of a subdomain (local + halo) must fit in a block's shared memory, so there are more
     # (subdomain, chunk) items than SMs and every block loops over several items per time step. With n_sm // k
     # subdomains the items spread evenly when the chunk count is a multiple of k; k = 1 pins one subdomain to each block.

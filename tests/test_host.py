@@ -334,13 +334,13 @@ def test_subdomain_layout_rules():
     # (problem groups per chunk, chunks, subdomains) of the subdomain engine on a 148-SM device
     from pyjjasim_b200.engine import subdomain_layout
     assert subdomain_layout(9801, 256) == (4, 8, 18)          # cfg2: one (subdomain, chunk) item per block, 144 blocks
-    assert subdomain_layout(361, 32) == (4, 1, 5)             # cfg1: no subdomain smaller than ~64 faces
+    assert subdomain_layout(361, 32) == (4, 1, 8)             # cfg1: no subdomain smaller than ~45 faces
     NG, chunks, P = subdomain_layout(65025, 512)              # cfg4 per GPU: cut finer than one item per block
     assert (NG, chunks, P) == (4, 16, 148) and 65025 / P <= 450
     NG, chunks, P = subdomain_layout(79401, 512)              # cfg3: more subdomains than SMs, in units of half the SM count
     assert P == 222 and 79401 / P <= 450
     assert subdomain_layout(998001, 64)[2] == 74              # cfg5: the dense top cannot follow; classic rule, streaming engine
-    assert subdomain_layout(100, 8) == (1, 1, 1)
+    assert subdomain_layout(100, 8) == (1, 1, 2)
 
 
 def test_large_subdomain_plan_falls_back_instead_of_raising():
