@@ -456,3 +456,29 @@ def test_annealing_single_problem_and_one_step_intervals():
     assert np.allclose(prof[:, 0], 0.2 * 1.5 ** np.arange(1, 7))
     assert np.array_equal(n, oracle.vortex_configuration(a.get_cycle_matrix(), theta))
     assert np.max(np.abs(a.get_cycle_matrix() @ theta + 2 * np.pi * 0.15)) < 1e-10
+
+
+def test_full_length_cfg1_iv_curve_against_oracle():
+    # BASELINE config 1 at full length: SquareArray(20,20), 32 bias currents, f = 0, T = 0, dt = 0.05, 10 000 steps
+    # (examples/time_evolution_example_2_IV_curve.py). Non-chaotic: the phases of the running problems reach ~1e3 rad
+    # and still agree with the oracle to 1e-9 relative; the DC voltages (the IV curve) agree to 1e-10
+    a = pj.SquareArray(20, 20)
+    W, Nt, dt = 32, 10000, 0.05
+    Is = a.current_base(angle=0)[:, None, None] * np.linspace(0, 2, W)[None, :, None]
+    kw = dict(circuit=a, time_step=dt, time_step_count=Nt, current_sources=Is,
+              store_time_steps=[Nt // 3, Nt - 1], store_current=False, store_voltage=False)
+    res = pj.TimeEvolutionProblem(**kw).compute()
+    args, extra = cases.oracle_inputs(kw)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        th, _, _ = oracle.time_evolution(*args, W, **extra)
+    scale = max(1.0, float(np.max(np.abs(th))))
+    assert scale > 100.0                                   # the problems above the critical current do run
+    assert np.max(np.abs(res.theta - th)) <= 1e-9 * scale
+    span = (Nt - 1 - Nt // 3) * dt
+    V_dev = (res.theta[:, :, 1] - res.theta[:, :, 0]) / span
+    V_ora = (th[:, :, 1] - th[:, :, 0]) / span
+    assert np.max(np.abs(V_dev - V_ora)) <= 1e-10
+    # the IV curve itself: zero voltage below the array's critical current, ohmic far above it
+    Vmean = (a.current_base(angle=0) @ V_dev) / np.sum(a.current_base(angle=0) ** 2)
+    assert abs(Vmean[4]) < 1e-6 and Vmean[-1] > 1.5
