@@ -482,3 +482,36 @@ def test_full_length_cfg1_iv_curve_against_oracle():
     # the IV curve itself: zero voltage below the array's critical current, ohmic far above it
     Vmean = (a.current_base(angle=0) @ V_dev) / np.sum(a.current_base(angle=0) ** 2)
     assert abs(Vmean[4]) < 1e-6 and Vmean[-1] > 1.5
+
+
+def test_long_noisy_run_statistics_match_oracle():
+    # chaotic regime (f = 0.1, T > 0): trajectories cannot be compared step by step with different generators
+    # (device Philox vs the reference's MT19937), so compare what the north star names: time-averaged vortex counts
+    # and DC voltages over a long run, per temperature, within the ensemble's own sampling noise
+    a = pj.SquareArray(24, 24)
+    W, Nt, dt = 24, 3000, 0.5
+    T = np.repeat(np.array([0.05, 0.2, 0.6]), W // 3)[None, :, None]
+    store = np.arange(Nt // 3, Nt, 20)
+    kw = dict(circuit=a, time_step=dt, time_step_count=Nt, external_flux=0.1, temperature=T,
+              store_time_steps=store, store_current=False, store_voltage=False)
+    res = pj.TimeEvolutionProblem(noise_seed=77, **kw).compute()
+    args, extra = cases.oracle_inputs(kw)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        th, _, _ = oracle.time_evolution(*args, W, rng=np.random.RandomState(5), **extra)
+    A = a.get_cycle_matrix()
+
+    def stats(theta):
+        n = oracle.vortex_configuration(A, theta)                       # (Nf, W, K)
+        dens = np.abs(n).sum(axis=0).mean(axis=1) / A.shape[0]           # vortices + antivortices per face
+        net = n.sum(axis=0).mean(axis=1) / A.shape[0]                    # net vorticity per face (-> f)
+        v = np.abs(theta[:, :, -1] - theta[:, :, 0]).mean(axis=0) / ((store[-1] - store[0]) * dt)
+        return dens.reshape(3, -1), net.reshape(3, -1), v.reshape(3, -1)
+    for got, want, name in zip(stats(res.theta), stats(th), ("density", "net vorticity", "mean |V|")):
+        for t in range(3):
+            g, w_ = got[t], want[t]
+            sigma = np.sqrt(g.var() / g.size + w_.var() / w_.size) + 1e-3 * max(abs(w_.mean()), 1e-3) + 1e-4
+            assert abs(g.mean() - w_.mean()) <= 5 * sigma, (name, t, g.mean(), w_.mean(), sigma)
+    # hotter ensembles hold more vortex-antivortex pairs
+    d = stats(res.theta)[0].mean(axis=1)
+    assert d[2] > d[0]
