@@ -210,6 +210,11 @@ int jj_vortex_configuration(JJHandle *h, int64_t plane, int32_t *dst);
  * reference's vortex mobility (reference: time_evolution.py:1128-1133, get_vortex_mobility); exact integers */
 int jj_vortex_mobility(JJHandle *h, int64_t plane0, int64_t n_planes, int64_t *dst /* [W] */);
 
+/* Page-locked host memory for result planes: jj_fetch_* into such a buffer is a single DMA at PCIe speed instead of
+ * a staged copy into pageable memory. The Python wrapper pools these blocks and hands them out as numpy arrays. */
+int jj_host_alloc(int device, uint64_t bytes, void **out);   /* device: whose context pins the block (portable) */
+int jj_host_free(void *p);
+
 typedef struct {
     int32_t engine;             /* engine actually used */
     int32_t cluster_size, tile_problems;

@@ -22,7 +22,8 @@ EXPORTS = ["jj_create", "jj_destroy", "jj_last_error", "jj_set_circuit", "jj_set
            "jj_alloc_outputs", "jj_run", "jj_fetch_theta", "jj_fetch_current", "jj_debug_noise",
            "jj_debug_solve", "jj_stats", "jj_set_resident_plan",
            "jj_debug_resident_solve", "jj_set_subdomain_plan", "jj_debug_subdomain_solve", "jj_sm_count",
-           "jj_restart_at_rest", "jj_vortex_configuration", "jj_vortex_mobility"]
+           "jj_restart_at_rest", "jj_vortex_configuration", "jj_vortex_mobility",
+           "jj_host_alloc", "jj_host_free"]
 
 _p = C.c_void_p
 _i32p = C.POINTER(C.c_int32)
@@ -121,6 +122,8 @@ def load():
     lib.jj_restart_at_rest.argtypes = [_p]
     lib.jj_vortex_configuration.argtypes = [_p, C.c_int64, _i32p]
     lib.jj_vortex_mobility.argtypes = [_p, C.c_int64, C.c_int64, _i64p]
+    lib.jj_host_alloc.argtypes = [C.c_int, C.c_uint64, C.POINTER(_p)]
+    lib.jj_host_free.argtypes = [_p]
     for name in EXPORTS:
         if name not in ("jj_destroy", "jj_last_error"):
             getattr(lib, name).restype = C.c_int

@@ -151,4 +151,17 @@ int jj_vortex_mobility(JJHandle* h, int64_t plane0, int64_t n_planes, int64_t* d
     return JJ_OK;
 }
 
+int jj_host_alloc(int device, uint64_t bytes, void** out) {
+    if (!out) return JJ_EINVAL;
+    *out = nullptr;
+    if (bytes == 0) return JJ_OK;
+    if (cudaSetDevice(device) != cudaSuccess) return JJ_ECUDA;      // never create a context on another GPU by accident
+    return cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable) == cudaSuccess ? JJ_OK : JJ_ENOMEM;
+}
+
+int jj_host_free(void* p) {
+    if (!p) return JJ_OK;
+    return cudaFreeHost(p) == cudaSuccess ? JJ_OK : JJ_ECUDA;
+}
+
 }  // extern "C"

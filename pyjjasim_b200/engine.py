@@ -35,6 +35,66 @@ _DENSE_BYTES = 256 << 20     # budget for one chunk of dense tables / injected n
 last_run_stats = {}          # filled by device_time_evolution_core (per device), for benchmarks and tests
 
 
+class _PinnedBlock:
+    """A page-locked host block exposed through the array interface; returns to the pool when the last array that
+    views it is gone."""
+
+    def __init__(self, pool, ptr, nbytes):
+        self._pool, self._ptr, self._nbytes = pool, ptr, nbytes
+        self.__array_interface__ = dict(data=(ptr, False), shape=(nbytes // 8,), typestr="<f8", version=3)
+
+    def __del__(self):
+        try:
+            self._pool._release(self._ptr, self._nbytes)
+        except Exception:
+            pass
+
+
+class _PinnedPool:
+    """Result planes in page-locked memory (device -> host at PCIe speed, no page faults on fresh numpy pages). Blocks
+    are reused across compute() calls of the same result size; pinning is slow, so only a few sizes are kept."""
+
+    MAX_BLOCK = 2 << 30
+    MAX_CACHED = 2 << 30
+    MAX_PINNED = 6 << 30          # in use + cached; results beyond that are ordinary numpy arrays
+
+    def __init__(self):
+        self._free, self._cached, self._in_use, self._lock = {}, 0, 0, threading.Lock()
+
+    def empty(self, shape, device=0):
+        nbytes = int(np.prod(shape)) * 8
+        if os.environ.get("JJ_PINNED_RESULTS", "1") == "0" or nbytes == 0 or nbytes > self.MAX_BLOCK:
+            return np.empty(shape)
+        with self._lock:
+            lst = self._free.get(nbytes)
+            ptr = lst.pop() if lst else None
+            if ptr is not None:
+                self._cached -= nbytes
+            elif self._in_use + self._cached + nbytes > self.MAX_PINNED:
+                return np.empty(shape)
+            self._in_use += nbytes
+        if ptr is None:
+            out = C.c_void_p()
+            if _lib.load().jj_host_alloc(int(device), nbytes, C.byref(out)) != 0 or not out.value:
+                with self._lock:
+                    self._in_use -= nbytes
+                return np.empty(shape)
+            ptr = out.value
+        return np.asarray(_PinnedBlock(self, ptr, nbytes)).reshape(shape)
+
+    def _release(self, ptr, nbytes):
+        with self._lock:
+            self._in_use -= nbytes
+            if self._cached + nbytes <= self.MAX_CACHED and len(self._free.get(nbytes, ())) < 2:
+                self._free.setdefault(nbytes, []).append(ptr)
+                self._cached += nbytes
+                return
+        _lib.load().jj_host_free(C.c_void_p(ptr))
+
+
+_pinned = _PinnedPool()
+
+
 class CircuitTables:
     """
     Everything the device needs that depends only on (circuit, dt): coefficient vectors
@@ -826,8 +886,9 @@ def device_time_evolution_core(problem, th_store_mask, I_store_mask, engine=None
     I_mask = np.asarray(I_store_mask, dtype=bool)
     specs = _classify_all(problem, tab)
     # every plane is written below: the two initial conditions here, the stored steps by the shards
-    th_host = np.empty((int(th_mask.sum()) + 2, Nj, W))
-    I_host = np.empty((int(I_mask.sum()) + 2, Nj, W))
+    pin_dev = devices[0] if device is None else device
+    th_host = _pinned.empty((int(th_mask.sum()) + 2, Nj, W), pin_dev) if th_mask.any() else np.empty((2, Nj, W))
+    I_host = _pinned.empty((int(I_mask.sum()) + 2, Nj, W), pin_dev) if I_mask.any() else np.empty((2, Nj, W))
     if initial_planes:
         th_host[1] = problem.config_at_minus_1
         th_host[0] = problem.config_at_minus_2

@@ -515,3 +515,27 @@ def test_long_noisy_run_statistics_match_oracle():
     # hotter ensembles hold more vortex-antivortex pairs
     d = stats(res.theta)[0].mean(axis=1)
     assert d[2] > d[0]
+
+
+def test_result_planes_come_from_the_pinned_pool_and_are_reused():
+    # stored planes are fetched into page-locked blocks that go back to a pool when the result is dropped
+    from pyjjasim_b200 import engine
+    kw, _ = cases.build("sq_frustrated", pj)
+    kw.update(store_voltage=False, store_current=False)       # (voltage trimming copies the planes with np.delete)
+    r1 = pj.TimeEvolutionProblem(**kw).compute()
+    ref = r1.theta.copy()
+    base = r1.theta
+    while getattr(base, "base", None) is not None:
+        base = base.base
+    assert isinstance(base, engine._PinnedBlock)
+    ptr = base._ptr
+    del base, r1
+    import gc
+    gc.collect()
+    r2 = pj.TimeEvolutionProblem(**kw).compute()
+    b2 = r2.theta
+    while getattr(b2, "base", None) is not None:
+        b2 = b2.base
+    assert isinstance(b2, engine._PinnedBlock)
+    assert np.array_equal(r2.theta, ref)
+    assert engine._pinned._in_use > 0 and b2._ptr == ptr

@@ -1,0 +1,7 @@
+mkdir -p gpurun_out
+timeout 900 python bench.py > gpurun_out/bench_r01.json 2> gpurun_out/bench_r01.err; python -c "
+import json
+d=json.load(open('gpurun_out/bench_r01.json')); print('value %.2f G  e2e %.2f G  %.4f s/step'%(d['value']/1e9, d['e2e']['value']/1e9, d['e2e']['seconds_per_step']))"
+JJ_PINNED_RESULTS=0 timeout 900 python bench.py > gpurun_out/bench_np.json 2> gpurun_out/bench_np.err; python -c "
+import json
+d=json.load(open('gpurun_out/bench_np.json')); print('unpinned: value %.2f G  e2e %.2f G  %.4f s/step'%(d['value']/1e9, d['e2e']['value']/1e9, d['e2e']['seconds_per_step']))"
