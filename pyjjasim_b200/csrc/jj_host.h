@@ -74,6 +74,7 @@ struct JJHandle {
     double *th_out = nullptr, *I_out = nullptr; long long n_th_planes = 0, n_I_planes = 0;
     long long th_cap_planes = 0, I_cap_planes = 0;   // allocated planes (kept across jj_set_problem calls of equal W)
     int *flag_d = nullptr;
+    void *scratch = nullptr; size_t scratch_cap = 0;     // grow-only device scratch of the observable kernels (jj_observe.cu)
     // resident engine (see jj_resident.cu): plan-level and problem-level state
     void *resident_plan = nullptr;
     void *resident = nullptr;

@@ -82,6 +82,21 @@ __global__ void __launch_bounds__(LANES * ROWS) k_vortex_mobility(const FaceView
     }
 }
 
+// device scratch kept in the handle: an annealing schedule calls jj_vortex_mobility once per interval, and a
+// cudaMalloc / cudaFree pair per call costs more than the kernel
+int scratch(JJHandle* h, size_t bytes, void** out) {
+    if (bytes > h->scratch_cap) {
+        cudaStreamSynchronize(h->stream);
+        dev_free(h, h->scratch, h->scratch_cap);
+        h->scratch = nullptr; h->scratch_cap = 0;
+        int rc = dev_alloc(h, &h->scratch, bytes);
+        if (rc) return rc;
+        h->scratch_cap = bytes;
+    }
+    *out = h->scratch;
+    return JJ_OK;
+}
+
 FaceView view(const JJHandle* h) {
     FaceView c;
     c.Nj = h->cir.Nj; c.Nf = h->cir.Nf; c.Wp = h->Wp;
@@ -111,7 +126,7 @@ int jj_vortex_configuration(JJHandle* h, int64_t plane, int32_t* dst) {
     const double* src = plane < 0 ? h->th1 : h->th_out + (size_t)plane * c.Nj * c.Wp;   // -1: the current state
     int* buf = nullptr;
     const size_t bytes = (size_t)c.Nf * c.Wp * sizeof(int);
-    int rc = dev_alloc(h, (void**)&buf, bytes);
+    int rc = scratch(h, bytes, (void**)&buf);
     if (rc) return rc;
     dim3 grid((c.Wp + LANES - 1) / LANES, (c.Nf + ROWS - 1) / ROWS), block(LANES, ROWS);
     k_vortex_configuration<<<grid, block, 0, h->stream>>>(c, src, buf);
@@ -119,7 +134,6 @@ int jj_vortex_configuration(JJHandle* h, int64_t plane, int32_t* dst) {
     cudaError_t e = cudaMemcpy2DAsync(dst, (size_t)h->W * sizeof(int), buf, (size_t)c.Wp * sizeof(int),
                                       (size_t)h->W * sizeof(int), c.Nf, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    dev_free(h, buf, bytes);
     if (e != cudaSuccess) { h->err = std::string("vortex_configuration: ") + cudaGetErrorString(e); return JJ_ECUDA; }
     return JJ_OK;
 }
@@ -133,7 +147,7 @@ int jj_vortex_mobility(JJHandle* h, int64_t plane0, int64_t n_planes, int64_t* d
     const FaceView c = view(h);
     unsigned long long* buf = nullptr;
     const size_t bytes = (size_t)c.Wp * sizeof(unsigned long long);
-    int rc = dev_alloc(h, (void**)&buf, bytes);
+    int rc = scratch(h, bytes, (void**)&buf);
     if (rc) return rc;
     cudaError_t e = cudaMemsetAsync(buf, 0, bytes, h->stream);
     // enough blocks to fill the machine: problem strips x face slices
@@ -146,7 +160,6 @@ int jj_vortex_mobility(JJHandle* h, int64_t plane0, int64_t n_planes, int64_t* d
     h->launches++;
     if (e == cudaSuccess) e = cudaMemcpyAsync(dst, buf, (size_t)h->W * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    dev_free(h, buf, bytes);
     if (e != cudaSuccess) { h->err = std::string("vortex_mobility: ") + cudaGetErrorString(e); return JJ_ECUDA; }
     return JJ_OK;
 }

@@ -407,6 +407,7 @@ void jj_destroy(JJHandle* h) {
     free_sweep(h, h->fwd); free_sweep(h, h->bwd);
     free_circuit(h);
     cudaFree(h->flag_d);
+    cudaFree(h->scratch);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
     cudaStreamDestroy(h->stream);
     delete h;

@@ -709,7 +709,8 @@ def _chunk_length(specs, tab, W, Nt, has_replay):
 _WHICH = dict(Is=_lib.JJ_SRC_IS, f=_lib.JJ_SRC_F, Vs=_lib.JJ_SRC_VS, T=_lib.JJ_SRC_T)
 
 
-_engine_cache = {}           # (device) -> (key, DeviceEngine): circuit, solver and plan stay uploaded between compute() calls
+_engine_cache = {}           # device -> [(key, DeviceEngine)]: circuit, solver and plan stay uploaded between compute() calls
+_ENGINES_PER_DEVICE = 2
 
 
 def _engine_for(tab, cpr, dev, W, engine_kind):
@@ -729,11 +730,11 @@ def _engine_for(tab, cpr, dev, W, engine_kind):
             raise ValueError("resident engine requested but the circuit does not fit in shared memory")
     key = (id(tab), tuple(a), tuple(b), sub_cfg, res_cfg)
     with _engine_lock:
-        hit = _engine_cache.pop(dev, None)
-    if hit is not None and hit[0] == key:
-        return key, hit[1]
-    if hit is not None:
-        hit[1].close()
+        entries = _engine_cache.setdefault(dev, [])
+        for i, (k, e) in enumerate(entries):
+            if k == key:
+                del entries[i]
+                return key, e
     eng = DeviceEngine(dev)
     eng.set_circuit(tab, cpr)
     if sub_cfg is not None:
@@ -747,11 +748,13 @@ def _release_engine(dev, key, eng, ok):
     if not ok:
         eng.close()
         return
+    # two engines per device stay uploaded: an annealing schedule alternates between the tables of dt and dt / 2
     with _engine_lock:
-        old = _engine_cache.pop(dev, None)
-        _engine_cache[dev] = (key, eng)
-    if old is not None:
-        old[1].close()
+        entries = _engine_cache.setdefault(dev, [])
+        entries.append((key, eng))
+        old = [entries.pop(0)] if len(entries) > _ENGINES_PER_DEVICE else []
+    for _, e in old:
+        e.close()
 
 
 def _setup_sources(eng, specs, sh, tab):
