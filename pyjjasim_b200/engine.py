@@ -120,8 +120,9 @@ class CircuitTables:
         self.n_parts = n_parts
         if leaf_size is None:
             # the subdomain engine applies explicit inverses of level groups: larger leaves give it fewer, fatter
-            # tiles and better balanced items (measured on cfg2: 24 beats 8 by 4 %)
-            leaf_size = int(os.environ.get("JJ_LEAF_SIZE", "24" if n_parts is not None else "8"))
+            # tiles and better balanced items (measured on cfg2: 24 beats 8 by 4 %, 32 - the largest block a single
+            # warp applies in place - beats 24 by another 2 %; 40 is 25 % slower; cfg1 / cfg3 / cfg4 do not care)
+            leaf_size = int(os.environ.get("JJ_LEAF_SIZE", "32" if n_parts is not None else "8"))
         if Nf > 0:
             S = system_matrix(A, circuit._L(), self.Rv, self.Cv)
             if hasattr(circuit, "get_face_centroids"):
