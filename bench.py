@@ -87,7 +87,7 @@ def workload(rank, world):
 
 def algorithmic_bytes_per_time_step(tab, W):
     """8 W (4 Nj + 2 Nf) + 32 W Nf + 24 nnz(L)."""
-    nnzL = tab.program.stats["nnz_L"]
+    nnzL = tab.factor.nnz_L
     return 8 * W * (4 * tab.Nj + 2 * tab.Nf) + 32 * W * tab.Nf + 24 * nnzL
 
 
@@ -105,18 +105,13 @@ def run_ours(args, rank, world, local_rank, dist):
         n_parts = int(os.environ["JJ_BENCH_NPARTS"])
     tab = engine.CircuitTables(a, DT, n_parts=n_parts)
     eng = engine.DeviceEngine(local_rank)
-    eng.set_circuit(tab, pj.DefaultCPR())
     kind = {"auto": _lib.JJ_ENGINE_AUTO, "streaming": _lib.JJ_ENGINE_STREAMING,
-            "resident": _lib.JJ_ENGINE_RESIDENT, "subdomain": _lib.JJ_ENGINE_SUBDOMAIN}[os.environ.get("JJ_ENGINE", "auto")]
-    cfg = None
-    if kind in (_lib.JJ_ENGINE_AUTO, _lib.JJ_ENGINE_SUBDOMAIN):
-        cfg = tab.choose_subdomain(W)
-        if cfg is not None:
-            eng.set_subdomain(*cfg)
-    if kind == _lib.JJ_ENGINE_RESIDENT or (kind == _lib.JJ_ENGINE_AUTO and cfg is None):
-        cfg = tab.choose_resident(W)
-        if cfg is not None:
-            eng.set_resident(*cfg)
+            "subdomain": _lib.JJ_ENGINE_SUBDOMAIN}[os.environ.get("JJ_ENGINE", "auto")]
+    cfg = tab.choose_subdomain(W) if kind in (_lib.JJ_ENGINE_AUTO, _lib.JJ_ENGINE_SUBDOMAIN) else None
+    eng.set_circuit(tab, pj.DefaultCPR(), with_program=cfg is None)
+    if cfg is not None:
+        eng.set_subdomain(*cfg)
+        kind = _lib.JJ_ENGINE_SUBDOMAIN
     eng.set_problem(W, DT, seed=SEED, problem_offset=w0, engine=kind)
     eng.set_source(_lib.JJ_SRC_F, _lib.JJ_KIND_RANK1, True, np.ones(tab.Nf))
     eng.upload_source(_lib.JJ_SRC_F, 0, np.full((1, W), FRUST))
@@ -225,7 +220,7 @@ def run_ours(args, rank, world, local_rank, dist):
            "config": {"workload": f"cfg2: SquareArray({NX},{NX}) f=0.1 thermal noise, {W} temperatures per GPU, dt=0.5",
                       "Nj": tab.Nj, "Nf": tab.Nf, "problems_per_gpu": W, "time_steps_per_step": INNER,
                       "l2": "256 MiB buffer written between timed steps (L2 flush)", "noise": "device Philox4x32-10, seed 1234",
-                      "engine": {1: "streaming", 2: "resident", 3: "subdomain"}.get(st["engine"], str(st["engine"])),
+                      "engine": {1: "streaming", 3: "subdomain"}.get(st["engine"], str(st["engine"])),
                       "subdomains_or_cluster": st["cluster_size"], "problems_per_block": st["tile_problems"]},
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -36,13 +36,14 @@ enum { JJ_SRC_IS = 0, JJ_SRC_F = 1, JJ_SRC_VS = 2, JJ_SRC_T = 3 };
 /* device forms of an input (see pyjjasim_b200/sources.py) */
 enum { JJ_KIND_ZERO = 0, JJ_KIND_RANK1 = 1, JJ_KIND_DENSE = 2 };
 /* step engines */
-enum { JJ_ENGINE_AUTO = 0,      /* first that applies: SUBDOMAIN (a plan was set and the inputs are rank one), RESIDENT, STREAMING */
-       JJ_ENGINE_STREAMING = 1, /* problem-minor (Nj, W) arrays in HBM, one kernel per phase */
-       JJ_ENGINE_RESIDENT = 2,  /* persistent kernel: a thread-block cluster owns a tile of problems for the
-                                   whole time loop, right-hand sides live in shared memory */
-       JJ_ENGINE_SUBDOMAIN = 3  /* persistent cooperative kernel: a thread block owns a (subdomain of the
-                                   elimination tree, chunk of problems) pair; the separators above the cut are
-                                   solved for all problems at once by a dense FP64 tensor-core product */ };
+enum { JJ_ENGINE_AUTO = 0,      /* SUBDOMAIN when a plan was set and the inputs are rank one, else STREAMING */
+       JJ_ENGINE_STREAMING = 1, /* problem-minor (Nj, W) arrays in HBM, one kernel per phase: any input form
+                                   (dense per-step tables, dense voltage sources); needs a real jj_set_solver program */
+       /* 2 was the cluster-resident engine of round 1 (retired: the subdomain engine covers its shapes) */
+       JJ_ENGINE_SUBDOMAIN = 3  /* persistent cooperative kernel: a thread block owns (subdomain of the elimination
+                                   tree, chunk of problems) items; the separators above the subdomains are swept level
+                                   by level as gathered dense FP64 tensor-core products over all SMs, and the last few
+                                   tree levels by one dense inverse */ };
 
 /* One sweep (forward or backward) of the compiled solve program, see pyjjasim_b200/factor.py.
  * Replaces the two SuperLU triangular sweeps per step (reference: time_evolution.py:506, :560-569). */
@@ -61,45 +62,12 @@ typedef struct {
     int64_t n_cols;  const int32_t *cols;
     int64_t n_vals;  const double  *vals;   /* [tile][step][32 lanes] */
     int32_t stage_rows;
-    const int32_t *tile_stage_off; /* staged tiles: first staging row (resident engine) */
+    const int32_t *tile_stage_off; /* staged tiles: first staging row */
 } JJSweep;
 
-/* Resident engine: the tiles of one cluster rank, packed as one contiguous stream per (level, warp)
- * (pyjjasim_b200/factor.py: pack_warp_streams). */
-typedef struct {
-    int32_t n_levels, n_warps;   /* n_warps == 16 */
-    int32_t n_tiles;
-    const int32_t *wt_ptr;       /* [n_levels*n_warps + 1] tiles of (level, warp) */
-    const int32_t *ws_ptr;       /* [n_levels*n_warps + 1] first stream step of (level, warp) */
-    const int32_t *thdr;         /* [n_tiles][2]: row0 | (nrows-1)<<16 | flags<<19 ; nsteps | stage_off<<16 */
-    int64_t n_steps;
-    const uint8_t *stream;       /* [n_steps][320]: 32 float64 (A fragment of an 8x4 block) then 32 uint16
-                                    (shared-memory element codes of the B fragment) */
-} JJRankStream;
-
-/* Resident-engine plan (see pyjjasim_b200/factor.py: resident_plan). A cluster of C thread blocks owns a
- * tile of `tile_problems` problems for the whole time loop; block r keeps the right-hand-side rows of
- * elimination subtree r plus replicas of the separators above the cut in its shared memory. */
-typedef struct {
-    int32_t C, tile_problems;        /* cluster size (1,2,4,8); problems per tile (8 = N of the FP64 MMA) */
-    int32_t n_rows;                  /* rows of each block's shared-memory vector */
-    int32_t stage_rows, allreduce_rows;
-    int32_t n_ops, n_fwd_ops;
-    const int32_t *ops;              /* [C][n_ops][4]: (0, level, staged rows, 0) | (1, row_lo, row_hi, 0); same
-                                        op kinds on every rank */
-    const JJRankStream *prog;        /* [C] tiles of rank r; a level op names a level of this program */
-    const int32_t *junc_ptr;         /* [C+1] rank r owns device junctions junc_ptr[r]:junc_ptr[r+1] */
-    const int32_t *junc_orig;        /* [Nj] original junction index of each device junction */
-    const int32_t *junc_row;         /* [Nj*2] shared-memory rows of its faces on the owner rank, -1 none */
-    const int8_t  *junc_sign;        /* [Nj*2] */
-    const int32_t *face_ptr;         /* [C*(n_rows+1)] CSR over shared-memory rows, into face_junc (global offsets) */
-    const int32_t *face_junc;        /* device junction index */
-    const int8_t  *face_sign;
-    const int32_t *face_fidx;        /* [C*n_rows] permuted face index if this rank adds the flux term, else -1 */
-} JJResidentPlan;
-
-/* Subdomain engine: sweep program of one subdomain, packed like JJRankStream; levels [0, n_bwd) are the
- * backward sweep, [n_bwd, n_levels) the forward sweep (pyjjasim_b200/subdomain.py). */
+/* Subdomain engine: sweep program of one subdomain: the 8-row tiles of every (level, warp) pair packed as one
+ * contiguous stream; levels [0, n_bwd) are the backward sweep, [n_bwd, n_levels) the forward sweep
+ * (pyjjasim_b200/subdomain.py). */
 typedef struct {
     int32_t n_levels, n_bwd, n_warps, n_tiles;
     const int32_t *wt_ptr;       /* [n_levels*n_warps][2] first / past-the-last tile of (level, warp) */
@@ -108,22 +76,37 @@ typedef struct {
     const int32_t *thdr;         /* [n_tiles][2]: row0 | (nrows-1)<<16 | flags<<19 | g0<<21 | (ng-1)<<25 ; nsteps | stage_off<<16 */
     const int32_t *lstaged;      /* [n_levels] staged rows of the level */
     int64_t n_steps;
-    const uint8_t *stream;       /* [n_steps][320] as in JJRankStream; element codes address rows of 8*NG float64 */
+    const uint8_t *stream;       /* [n_steps][320]: 32 float64 (A fragment of an 8x4 block of the factor) then 32 uint16
+                                    (shared-memory element codes of the B fragment; rows of 8*NG float64) */
 } JJSubProgram;
 
 /* Subdomain-engine plan (pyjjasim_b200/subdomain.py: subdomain_plan). Replaces the two SuperLU sweeps per step
- * (reference: time_evolution.py:506, :560-569): P uncoupled subdomains + n_top separator rows whose Schur
- * complement inverse is applied as a dense product. */
+ * (reference: time_evolution.py:506, :560-569). The elimination tree of the nested dissection is cut in three:
+ *   - P mutually uncoupled SUBDOMAINS (leaves of the cut), swept out of shared memory by one thread block each;
+ *   - the UPPER separators, rows [0, tt0) of the top numbering: swept depth by depth in global memory (three planes
+ *     r, z, J of n_up_pad rows per problem chunk) as gathered dense products, two phases per tree depth
+ *     (t = r - L[B, below] z ; z = inv(L[B,B]) t, and transposed for the backward sweep);
+ *   - the TOP OF THE TOP, rows [tt0, tt0 + n_tt): the last few tree levels, one dense inverse of their Schur complement. */
 typedef struct {
     int32_t P, NG;                   /* subdomains; problems per chunk = 8*NG (NG = 1, 2, 4, 8) */
     int32_t n_rows, n_loc_max, stage_rows;
-    int32_t n_top, n_top_pad, n_slots;
+    int32_t n_top, n_up_pad, n_slots;/* separator rows above the subdomains; row stride of the r / z / J planes */
+    int32_t tt0, n_tt, n_tt_pad;     /* dense top of the top (n_tt_pad: n_tt rounded up to 32; tt0 + n_tt_pad <= n_up_pad) */
     const int32_t *n_loc, *n_halo;   /* [P] local rows / halo rows (coupled top rows) of each subdomain */
     const int32_t *hptr;             /* [P+1] first contribution slot of each subdomain */
     const int32_t *halo_top;         /* [n_slots] top row of each slot */
     const int32_t *tptr, *tslot;     /* [n_top+1], [n_slots]: slots that sum into each top row */
     const int32_t *top_face;         /* [n_top] permuted face index of each top row */
-    const double  *Sinv_packed;      /* [n_top_pad/8][n_top_pad/4][8][4] MMA A fragments of S_top^-1 */
+    const double  *Sinv_packed;      /* [n_tt_pad/8][n_tt_pad/4][8][4] MMA A fragments of the inverse Schur complement */
+    /* upper program: phases [0, n_up_fwd) run after the top assembly, phases [n_up_fwd, n_up_fwd + n_up_bwd) after the
+     * dense product; a grid barrier separates phases. A task computes out[rows] = V . X[cols] for up_RB 8-row tiles. */
+    int32_t up_RB, up_KB;            /* row tiles per task; k-steps (of 4 columns) per pipeline stage: nk % up_KB == 0 */
+    int32_t n_up_fwd, n_up_bwd, n_up_tasks;
+    const int32_t *up_phase_ptr;     /* [n_up_fwd + n_up_bwd + 1] first task of each phase (tasks sorted by cost) */
+    const int32_t *up_task;          /* [n_up_tasks][4]: out code, rows (1..8*up_RB), nk, first column (index into up_cols) */
+    const int64_t *up_task_aoff;     /* [n_up_tasks] offset of the task's A fragments in up_A (float64 units) */
+    int64_t n_up_cols; const int32_t *up_cols;   /* row codes: plane << 28 | row, plane 0 = r, 1 = z, 2 = J */
+    int64_t n_up_vals; const double *up_A;       /* per task [row tile][nk][32]: lane = row*4 + kk holds V[row][4k + kk] */
     const JJSubProgram *prog;        /* [P] */
     const int32_t *junc_ptr;         /* [P+1] subdomain s owns device junctions junc_ptr[s]:junc_ptr[s+1] */
     const int32_t *junc_orig;        /* [Nj] */
@@ -158,9 +141,8 @@ const char *jj_last_error(const JJHandle *h);   /* h may be NULL: error of the l
 
 /* setup (reference: time_evolution.py:466-519) */
 int jj_set_circuit(JJHandle *h, const JJCircuit *c);
+/* the streaming engine's solve program; sweeps with n_levels == 0 are accepted when only the subdomain engine runs */
 int jj_set_solver(JJHandle *h, const JJSweep *fwd, const JJSweep *bwd);
-/* optional: enables JJ_ENGINE_RESIDENT. Must follow jj_set_circuit/jj_set_solver. plan == NULL removes it. */
-int jj_set_resident_plan(JJHandle *h, const JJResidentPlan *plan);
 /* optional: enables JJ_ENGINE_SUBDOMAIN. Must follow jj_set_circuit/jj_set_solver. plan == NULL removes it. */
 int jj_set_subdomain_plan(JJHandle *h, const JJSubdomainPlan *plan);
 /* W problems, time step dt, Philox seed, index of this shard's first problem in the global batch
@@ -191,9 +173,6 @@ int jj_fetch_current(JJHandle *h, int64_t plane0, int64_t n_planes, double *dst)
 int jj_debug_noise(JJHandle *h, int64_t step, double *dst);
 /* one solve J = S^-1 b through the compiled program, (Nf, W) host arrays in permuted face order */
 int jj_debug_solve(JJHandle *h, const double *b, double *J);
-/* the same through the resident engine's cluster kernel (requires a resident plan) */
-int jj_debug_resident_solve(JJHandle *h, const double *b, double *J);
-
 /* the same through the subdomain engine's cooperative kernel (requires a subdomain plan) */
 int jj_debug_subdomain_solve(JJHandle *h, const double *b, double *J);
 

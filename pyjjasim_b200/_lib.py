@@ -14,14 +14,13 @@ LIB_PATH = os.path.join(_HERE, "libjjstep.so")
 
 JJ_SRC_IS, JJ_SRC_F, JJ_SRC_VS, JJ_SRC_T = 0, 1, 2, 3
 JJ_KIND_ZERO, JJ_KIND_RANK1, JJ_KIND_DENSE = 0, 1, 2
-JJ_ENGINE_AUTO, JJ_ENGINE_STREAMING, JJ_ENGINE_RESIDENT, JJ_ENGINE_SUBDOMAIN = 0, 1, 2, 3
+JJ_ENGINE_AUTO, JJ_ENGINE_STREAMING, JJ_ENGINE_SUBDOMAIN = 0, 1, 3
 JJ_ENONFINITE = -5
 
 EXPORTS = ["jj_create", "jj_destroy", "jj_last_error", "jj_set_circuit", "jj_set_solver", "jj_set_problem",
            "jj_set_state", "jj_get_state", "jj_set_source", "jj_upload_source", "jj_upload_noise",
            "jj_alloc_outputs", "jj_run", "jj_fetch_theta", "jj_fetch_current", "jj_debug_noise",
-           "jj_debug_solve", "jj_stats", "jj_set_resident_plan",
-           "jj_debug_resident_solve", "jj_set_subdomain_plan", "jj_debug_subdomain_solve", "jj_sm_count",
+           "jj_debug_solve", "jj_stats", "jj_set_subdomain_plan", "jj_debug_subdomain_solve", "jj_sm_count",
            "jj_restart_at_rest", "jj_vortex_configuration", "jj_vortex_mobility",
            "jj_host_alloc", "jj_host_free"]
 
@@ -40,20 +39,6 @@ class JJSweep(C.Structure):
                 ("stage_rows", C.c_int32), ("tile_stage_off", _i32p)]
 
 
-class JJRankStream(C.Structure):
-    _fields_ = [("n_levels", C.c_int32), ("n_warps", C.c_int32), ("n_tiles", C.c_int32),
-                ("wt_ptr", _i32p), ("ws_ptr", _i32p), ("thdr", _i32p), ("n_steps", C.c_int64),
-                ("stream", C.POINTER(C.c_uint8))]
-
-
-class JJResidentPlan(C.Structure):
-    _fields_ = [("C", C.c_int32), ("tile_problems", C.c_int32), ("n_rows", C.c_int32),
-                ("stage_rows", C.c_int32), ("allreduce_rows", C.c_int32), ("n_ops", C.c_int32),
-                ("n_fwd_ops", C.c_int32), ("ops", _i32p), ("prog", C.POINTER(JJRankStream)),
-                ("junc_ptr", _i32p), ("junc_orig", _i32p), ("junc_row", _i32p), ("junc_sign", _i8p),
-                ("face_ptr", _i32p), ("face_junc", _i32p), ("face_sign", _i8p), ("face_fidx", _i32p)]
-
-
 class JJSubProgram(C.Structure):
     _fields_ = [("n_levels", C.c_int32), ("n_bwd", C.c_int32), ("n_warps", C.c_int32), ("n_tiles", C.c_int32),
                 ("wt_ptr", _i32p), ("ws_ptr", _i32p), ("thdr", _i32p), ("lstaged", _i32p), ("n_steps", C.c_int64),
@@ -62,9 +47,14 @@ class JJSubProgram(C.Structure):
 
 class JJSubdomainPlan(C.Structure):
     _fields_ = [("P", C.c_int32), ("NG", C.c_int32), ("n_rows", C.c_int32), ("n_loc_max", C.c_int32),
-                ("stage_rows", C.c_int32), ("n_top", C.c_int32), ("n_top_pad", C.c_int32), ("n_slots", C.c_int32),
+                ("stage_rows", C.c_int32), ("n_top", C.c_int32), ("n_up_pad", C.c_int32), ("n_slots", C.c_int32),
+                ("tt0", C.c_int32), ("n_tt", C.c_int32), ("n_tt_pad", C.c_int32),
                 ("n_loc", _i32p), ("n_halo", _i32p), ("hptr", _i32p), ("halo_top", _i32p), ("tptr", _i32p),
-                ("tslot", _i32p), ("top_face", _i32p), ("Sinv_packed", _f64p), ("prog", C.POINTER(JJSubProgram)),
+                ("tslot", _i32p), ("top_face", _i32p), ("Sinv_packed", _f64p),
+                ("up_RB", C.c_int32), ("up_KB", C.c_int32), ("n_up_fwd", C.c_int32), ("n_up_bwd", C.c_int32),
+                ("n_up_tasks", C.c_int32), ("up_phase_ptr", _i32p), ("up_task", _i32p), ("up_task_aoff", _i64p),
+                ("n_up_cols", C.c_int64), ("up_cols", _i32p), ("n_up_vals", C.c_int64), ("up_A", _f64p),
+                ("prog", C.POINTER(JJSubProgram)),
                 ("junc_ptr", _i32p), ("junc_orig", _i32p), ("junc_row", _i32p), ("junc_sign", _i8p),
                 ("face_K", C.c_int32), ("face_ell_j", _i32p), ("face_ell_c", _f64p), ("face_fidx", _i32p)]
 
@@ -114,8 +104,6 @@ def load():
     lib.jj_debug_noise.argtypes = [_p, C.c_int64, _f64p]
     lib.jj_debug_solve.argtypes = [_p, _f64p, _f64p]
     lib.jj_stats.argtypes = [_p, C.POINTER(JJStats)]
-    lib.jj_set_resident_plan.argtypes = [_p, C.POINTER(JJResidentPlan)]
-    lib.jj_debug_resident_solve.argtypes = [_p, _f64p, _f64p]
     lib.jj_set_subdomain_plan.argtypes = [_p, C.POINTER(JJSubdomainPlan)]
     lib.jj_debug_subdomain_solve.argtypes = [_p, _f64p, _f64p]
     lib.jj_sm_count.argtypes = [C.c_int]

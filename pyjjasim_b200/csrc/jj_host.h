@@ -75,9 +75,6 @@ struct JJHandle {
     long long th_cap_planes = 0, I_cap_planes = 0;   // allocated planes (kept across jj_set_problem calls of equal W)
     int *flag_d = nullptr;
     void *scratch = nullptr; size_t scratch_cap = 0;     // grow-only device scratch of the observable kernels (jj_observe.cu)
-    // resident engine (see jj_resident.cu): plan-level and problem-level state
-    void *resident_plan = nullptr;
-    void *resident = nullptr;
     // subdomain engine (see jj_subdomain.cu)
     void *subdomain_plan = nullptr;
     // stats
@@ -87,17 +84,6 @@ struct JJHandle {
 };
 
 namespace jj {
-// implemented in jj_resident.cu
-int resident_supported(JJHandle* h, std::string& why_not);
-int resident_prepare(JJHandle* h);
-int resident_run(JJHandle* h, long long i0, int n, const long long* th_plane, const long long* I_plane);
-int resident_set_state(JJHandle* h, const double* t1, const double* t2);
-int resident_get_state(JJHandle* h, double* t1, double* t2);
-void resident_free(JJHandle* h);
-int resident_set_plan(JJHandle* h, const JJResidentPlan* plan);
-void resident_drop_plan(JJHandle* h);
-int resident_debug_solve(JJHandle* h, const double* b_d, double* J_d);
-void resident_get_config(JJHandle* h, int* C, int* WT);
 // implemented in jj_subdomain.cu
 int subdomain_supported(JJHandle* h, std::string& why_not);
 int subdomain_prepare(JJHandle* h);

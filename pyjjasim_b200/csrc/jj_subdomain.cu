@@ -12,9 +12,12 @@
 // followed, once per time step and for all problems at once, by
 //
 //   top assembly    r_top = sum of the subdomain contributions - 2 pi f_top
-//   top product     J_top = S_top^-1 r_top, a dense FP64 tensor-core product spread over all SMs
+//   upper forward   the separators between the subdomains and the top of the tree, two phases per tree depth,
+//                   every phase a set of independent gathered dense FP64 tensor-core products (upper_phase)
+//   top product     J_tt = S_tt^-1 r_tt for the last few tree levels, one dense product spread over all SMs
+//   upper backward  the same separators top-down
 //
-// with a grid barrier between the three stages. The local sweeps stream the factor from L2 as
+// with a grid barrier between stages (circuits whose separators all fit the dense product skip the upper phases). The local sweeps stream the factor from L2 as
 // mma.m8n8k4 fragments (one A fragment feeds NG MMAs, one per group of 8 problems); theta and x stream
 // through HBM once per step; b, z, J of the local rows never leave shared memory when every block has a
 // single item.
@@ -29,15 +32,8 @@
 
 using namespace jj;
 
-namespace {
-
-constexpr int NT = 512;
-constexpr size_t BAR_BYTES = 8192;      // grid barrier counter + one counter per problem chunk, 128 bytes apart
-constexpr int NWARPS = NT / 32;
-constexpr int RING = 4;            // stream steps per ring block; every tile is padded to a multiple of it
-constexpr int STEP_BYTES = 320;
-constexpr double TWO_PI = 6.283185307179586;
-constexpr int PROF_SLOTS = 8 + 48;     // phase counters + per-level counters of the sweeps (JJ_SUB_PROF)
+// kernel arguments: shared by the host unit and the per-chunk-width kernel units (see the end of the device part)
+namespace jj {
 
 struct SubProgDev {
     const int* wt_ptr; const int* ws_ptr; const int2* thdr; const int* lstaged;
@@ -47,8 +43,14 @@ struct SubProgDev {
 
 struct SubArgs {
     // plan
-    int P, n_rows, n_loc_max, stage_rows, n_top, n_top_pad, n_slots;
+    int P, n_rows, n_loc_max, stage_rows, n_top, n_up_pad, n_slots;
+    int tt0, n_tt, n_tt_pad;        // dense top of the top: rows [tt0, tt0 + n_tt) of the top numbering
     int max_np, max_levels, max_tiles;
+    // upper program (see JJSubdomainPlan): phases of tasks out[rows] = V . X[cols] over the r / z / J planes
+    int up_RB, up_KB, n_up_fwd, n_up_bwd;
+    const int* up_phase_ptr; const int4* up_task; const long long* up_task_aoff;
+    const int* up_cols; const double* up_A;
+    double* U;                      // [3 planes][chunk][n_up_pad][PC]; rtop = plane 0, jtop = plane 2
     const SubProgDev* prog;
     const int *n_loc, *n_halo, *hptr, *halo_top, *tptr, *tslot, *top_face;
     const int4* tslot4;             // [n_top] the (at most four) slots of a top row, -1 padded; null when a row has more
@@ -79,11 +81,30 @@ struct SubArgs {
     int* flag;
     const double* dbg_b; double* dbg_J;   // debug solve: canonical [Nf][Wp], permuted faces
     long long* prof;                       // optional per-block cycle counters [block][8]
-    int dbg;                               // timing experiments only (JJ_SUB_DEBUG): 1 no MMA in the top product, 2 no loads
+    int dbg;                               // JJ_SUB_DEBUG (read once per plan): 4 no chunk-local top phase, 64 direct top
+                                           // product; the physics-altering timing experiments (128, 256) exist only in
+                                           // builds with -DJJ_EXPERIMENTS
 };
 
+}  // namespace jj
+
+namespace {
+
+constexpr int NT = 512;
+constexpr size_t BAR_BYTES = 8192;      // grid barrier counter + one counter per problem chunk, 128 bytes apart
+constexpr int NWARPS = NT / 32;
+constexpr int RING = 4;            // stream steps per ring block; every tile is padded to a multiple of it
+constexpr int STEP_BYTES = 320;
+constexpr double TWO_PI = 6.283185307179586;
+constexpr int PROF_SLOTS = 8 + 48;     // phase counters + per-level counters of the sweeps (JJ_SUB_PROF)
+
 struct SubState {
-    int P = 1, NG = 4, PC = 32, n_rows = 0, n_loc_max = 0, stage_rows = 0, n_top = 0, n_top_pad = 0, n_slots = 0;
+    int P = 1, NG = 4, PC = 32, n_rows = 0, n_loc_max = 0, stage_rows = 0, n_top = 0, n_up_pad = 0, n_slots = 0;
+    int tt0 = 0, n_tt = 0, n_tt_pad = 0, up_RB = 4, up_KB = 8, n_up_fwd = 0, n_up_bwd = 0;
+    int* up_phase_ptr = nullptr; int4* up_task = nullptr; long long* up_task_aoff = nullptr;
+    int* up_cols = nullptr; double* up_A = nullptr;
+    double* U = nullptr; size_t u_bytes = 0;
+    int dbg = 0; bool prof = false, no_tslot4 = false, no_l2_window = false, l2_limit_set = false; int grid_env = 0;
     int max_np = 0, max_levels = 0, max_tiles = 0, face_K = 0;
     SubProgDev* prog = nullptr;
     int *n_loc = nullptr, *n_halo = nullptr, *hptr = nullptr, *halo_top = nullptr, *tptr = nullptr, *tslot = nullptr, *top_face = nullptr;
@@ -95,7 +116,7 @@ struct SubState {
     std::vector<void*> allocs; std::vector<size_t> alloc_bytes;
     // per problem
     double *rth = nullptr, *rx = nullptr, *zloc = nullptr, *ctop = nullptr, *rtop = nullptr, *jtop = nullptr;
-    size_t state_bytes = 0, z_bytes = 0, c_bytes = 0, t_bytes = 0;
+    size_t state_bytes = 0, z_bytes = 0, c_bytes = 0;
     unsigned* bar = nullptr;
     long long* plane_d = nullptr; size_t plane_cap = 0;
     int n_chunks = 0, grid = 0;
@@ -127,15 +148,6 @@ __device__ __forceinline__ unsigned long long policy_evict_first() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
-__device__ __forceinline__ double2 ldg_hint_d2(const double* p, unsigned long long pol) {
-    double2 v;
-    asm volatile("ld.global.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ void stg_hint_d2(double* p, double2 v, unsigned long long pol) {
-    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
-}
-
 // 256-bit global accesses (sm_100: LDG/STG.E.256): four problems of one junction in one request
 struct double4v { double2 lo, hi; };
 __device__ __forceinline__ double4v ldg256_hint(const double* p, unsigned long long pol) {
@@ -356,11 +368,13 @@ __device__ __forceinline__ void next_x(const SubArgs& a, double Ic, double c1, d
                                        const double* ampT, const double* ampIs, int jo, int w, long long n,
                                        const double th1[4], const double th2[4], double xn[4]) {
     double fl[4] = {0, 0, 0, 0};
+#ifdef JJ_EXPERIMENTS
     if (a.dbg & 128) {      // timing experiment (JJ_SUB_DEBUG=128): linear CPR, no noise -> the pass is loads + stores + a few FMAs
 #pragma unroll
         for (int k = 0; k < 4; ++k) xn[k] = (Ic * (2.0 * th1[k] - th2[k]) + c1 * th1[k] + c2 * th2[k]) - isb * ampIs[k];
         return;
     }
+#endif
     if (a.T.kind != KIND_ZERO) {
         double z[4];
         if (a.noise_K > 0) {
@@ -397,7 +411,6 @@ __device__ __forceinline__ void junction_item(const SubArgs& a, const AmpCache<8
     const int q = (idx % G) * 4;
     const int w = c * PC + q;
     if (w >= a.Wp) return;
-    const int jp = jlo + idx / G;
     const size_t sidx = ((size_t)c * a.Nj + jlo) * PC + (size_t)idx * 4;
     const unsigned long long pol_first = policy_evict_first();
     // ri = row0, row1, original junction, signs
@@ -432,10 +445,16 @@ __device__ __forceinline__ void junction_item(const SubArgs& a, const AmpCache<8
             return;
         }
     }
-    if (!(a.dbg & 256)) stg256_hint(a.rth + sidx, make_double2(th1[0], th1[1]), make_double2(th1[2], th1[3]), pol_first);
     double xn[4];
+#ifdef JJ_EXPERIMENTS       // timing experiment (JJ_SUB_DEBUG=256): no state traffic; never part of a release build
+    if (!(a.dbg & 256)) stg256_hint(a.rth + sidx, make_double2(th1[0], th1[1]), make_double2(th1[2], th1[3]), pol_first);
     next_x<DEF>(a, rIc.x, rc.x, rc.y, rb.x, rb.y, ac->T[n & 1] + q, ac->Is[n & 1] + q, ri.z, w, n, th1, th2, xn);
-    if (!(a.dbg & 256) || xn[0] == 12345.678) /* the test keeps x' live in the experiment */ stg256(a.rx + sidx, make_double2(xn[0], xn[1]), make_double2(xn[2], xn[3]));
+    if (!(a.dbg & 256) || xn[0] == 12345.678) stg256(a.rx + sidx, make_double2(xn[0], xn[1]), make_double2(xn[2], xn[3]));
+#else
+    stg256_hint(a.rth + sidx, make_double2(th1[0], th1[1]), make_double2(th1[2], th1[3]), pol_first);
+    next_x<DEF>(a, rIc.x, rc.x, rc.y, rb.x, rb.y, ac->T[n & 1] + q, ac->Is[n & 1] + q, ri.z, w, n, th1, th2, xn);
+    stg256(a.rx + sidx, make_double2(xn[0], xn[1]), make_double2(xn[2], xn[3]));
+#endif
 }
 
 template <int NG, bool DEF>
@@ -496,7 +515,11 @@ __device__ void junction_pass(const SubArgs& a, const AmpCache<8 * NG>* ac, int 
         double2 nx0, nx1, nt0, nt1, nIc, nc, nb;
         int4 ni = make_int4(0, 0, 0, 0);
         nx0 = nx1 = nt0 = nt1 = nIc = nc = nb = make_double2(0.0, 0.0);
-        if (idx + NT < total && !(a.dbg & 256)) {      // JJ_SUB_DEBUG=256 (timing experiment): no state traffic
+#ifdef JJ_EXPERIMENTS
+        if (idx + NT < total && !(a.dbg & 256)) {
+#else
+        if (idx + NT < total) {
+#endif
             const size_t si = sbase + (size_t)(idx + NT) * 4;
             const double4v xv = ldg256_hint(a.rx + si, pol_first), tv = ldg256_hint(a.rth + si, pol_first);
             nx0 = xv.lo; nx1 = xv.hi; nt0 = tv.lo; nt1 = tv.hi;
@@ -661,25 +684,25 @@ __device__ void top_assemble(const SubArgs& a, long long n, int c0, int nc, int 
                 for (int e = 0; e < 4; ++e) acc[e] -= TWO_PI * (b * __ldg(am + e));
             }
         }
-        double2* dst = reinterpret_cast<double2*>(a.rtop + ((size_t)c * a.n_top_pad + k) * PC + q);
+        double2* dst = reinterpret_cast<double2*>(a.rtop + ((size_t)c * a.n_up_pad + k) * PC + q);
         dst[0] = make_double2(acc[0], acc[1]);
         dst[1] = make_double2(acc[2], acc[3]);
     }
 }
 
-// J_top = S_top^-1 r_top, direct version (no shared-memory staging; used when the staging rows are too few).
+// J_tt = S_tt^-1 r_tt, direct version (no shared-memory staging; used when the staging rows are too few).
 // Task = (chunk, 8-row tile, problem group), one per warp and round; consecutive tasks differ in the group
 // first, so the warps of a block share A row tiles and B fragments through L1.
 template <int NG>
 __device__ void top_product_direct(const SubArgs& a) {
     constexpr int PC = 8 * NG;
-    const int RT = (a.n_top + 7) / 8, KS = a.n_top_pad / 4;
+    const int RT = (a.n_tt + 7) / 8, KS = a.n_tt_pad / 4;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tasks = a.n_chunks * RT * NG;
     for (int task = blockIdx.x * NWARPS + warp; task < n_tasks; task += gridDim.x * NWARPS) {
         const int g = task % NG, rt = (task / NG) % RT, c = task / (NG * RT);
         const double* A = a.SinvP + ((size_t)rt * KS) * 32 + lane;
-        const double* B = a.rtop + ((size_t)c * a.n_top_pad + (lane & 3)) * PC + 8 * g + (lane >> 2);
+        const double* B = a.rtop + ((size_t)c * a.n_up_pad + a.tt0 + (lane & 3)) * PC + 8 * g + (lane >> 2);
         double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
         for (int ks0 = 0; ks0 < KS; ks0 += 8) {
             double ac[8], bc[8];
@@ -692,7 +715,7 @@ __device__ void top_product_direct(const SubArgs& a) {
             }
         }
         const int row = 8 * rt + (lane >> 2);
-        double2* dst = reinterpret_cast<double2*>(a.jtop + ((size_t)c * a.n_top_pad + row) * PC + 8 * g + 2 * (lane & 3));
+        double2* dst = reinterpret_cast<double2*>(a.jtop + ((size_t)c * a.n_up_pad + a.tt0 + row) * PC + 8 * g + 2 * (lane & 3));
         *dst = make_double2(c00 + c10, c01 + c11);
     }
 }
@@ -702,236 +725,12 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc));
 }
 
-// J_top = S_top^-1 r_top as a block-level product: a block computes RB 8-row tiles x (up to 4 groups of 8
-// problems) of one chunk. Per K block the RB A row tiles and the B fragments of the groups are staged once in
-// shared memory by cp.async (a ring in the staging rows, which are idle between the sweeps); warp w < RB owns row
-// tile w and feeds one A fragment to the MMAs of all groups. RB is chosen so that one round of blocks covers the
-// whole product (no tail), and the L2 traffic drops from 512 to 64 + 256/RB bytes per MMA.
-template <int NG, int KB>
-__device__ void top_product(const SubArgs& a, double* buf, int RB, int S) {
-    constexpr int PC = 8 * NG;
-    constexpr int GW = NG < 4 ? NG : 4;            // groups per pass
-    constexpr int GP = (NG + 3) / 4;               // passes over the groups of a chunk
-    const int RT = (a.n_top + 7) / 8, RTP = a.n_top_pad / 8, KS = a.n_top_pad / 4;
-    const int NB = (RT + RB - 1) / RB;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int stage_doubles = (RB + GW) * KB * 32;
-    const int pieces = stage_doubles / 2;          // 16-byte pieces per stage, at most 2 per thread
-    const int n_tasks = a.n_chunks * NB * GP;
-    const int nkb = KS / KB;                       // KS is a multiple of 8
-    for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
-        const int gp = task % GP, nb = (task / GP) % NB, c = task / (GP * NB);
-        const int rt = nb * RB + warp;
-        const bool active = warp < RB && rt < RT;
-        // this thread's pieces of a stage: fragment f = piece / 16; f < RB*KB: A row tile f / KB, else B group
-        const double* src0[2]; size_t step[2]; bool have[2];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int i = threadIdx.x + j * NT;
-            have[j] = i < pieces;
-            const int frag = i / 16, piece = i % 16, which = frag / KB, kl = frag % KB;
-            if (which < RB) {
-                src0[j] = a.SinvP + ((size_t)min(nb * RB + which, RTP - 1) * KS + kl) * 32 + piece * 2;
-                step[j] = (size_t)KB * 32;
-            } else {
-                const int gg = min(4 * gp + (which - RB), NG - 1);
-                src0[j] = a.rtop + ((size_t)c * a.n_top_pad + 4 * kl + (piece >> 2)) * PC + 8 * gg + (piece & 3) * 2;
-                step[j] = (size_t)KB * 4 * PC;
-            }
-        }
-        // blocks walk K in rotated order so that the blocks sharing an operand do not ask L2 for the same lines
-        // at the same moment (the sum order differs per block but is fixed, so results stay deterministic)
-        const int rot = (int)(((unsigned)nb * 7u + (unsigned)c * 13u + (unsigned)gp * 5u) % (unsigned)nkb);
-        auto issue = [&](int kb) {
-            if (kb < nkb) {
-                int ke = kb + rot; if (ke >= nkb) ke -= nkb;
-                double* dst = buf + (size_t)(kb % S) * stage_doubles + (size_t)threadIdx.x * 2;
-                if (have[0]) cp_async16(dst, src0[0] + (size_t)ke * step[0]);
-                if (have[1]) cp_async16(dst + 2 * NT, src0[1] + (size_t)ke * step[1]);
-            }
-            asm volatile("cp.async.commit_group;");
-        };
-        __syncthreads();                           // the ring is free (previous task / phase done)
-        for (int k = 0; k < S - 1; ++k) issue(k);
-        double acc[GW][2];
-#pragma unroll
-        for (int g = 0; g < GW; ++g) { acc[g][0] = 0.0; acc[g][1] = 0.0; }
-        for (int kb = 0; kb < nkb; ++kb) {
-            if (S == 4) asm volatile("cp.async.wait_group 2;");
-            else if (S == 3) asm volatile("cp.async.wait_group 1;");
-            else asm volatile("cp.async.wait_group 0;");
-            __syncthreads();                       // stage kb has landed for everyone; stage kb-1 is no longer read
-            issue(kb + S - 1);
-            if (active) {
-                const double* st = buf + (size_t)(kb % S) * stage_doubles;
-                const double* pa = st + (size_t)warp * KB * 32 + lane;
-                // B fragment staged as [kk][n]: lane = n*4 + kk reads element kk*8 + n
-                const double* pb = st + (size_t)RB * KB * 32 + (lane & 3) * 8 + (lane >> 2);
-                double av[KB];
-#pragma unroll
-                for (int kl = 0; kl < KB; ++kl) av[kl] = pa[kl * 32];
-#pragma unroll
-                for (int kl = 0; kl < KB; ++kl) {
-                    double bv[GW];
-#pragma unroll
-                    for (int g = 0; g < GW; ++g) bv[g] = pb[(g * KB + kl) * 32];
-#pragma unroll
-                    for (int g = 0; g < GW; ++g) dmma884(acc[g][0], acc[g][1], av[kl], bv[g]);
-                }
-            }
-        }
-        asm volatile("cp.async.wait_group 0;");
-        if (active) {
-            const int row = 8 * rt + (lane >> 2);
-#pragma unroll
-            for (int g = 0; g < GW; ++g) {
-                const int gg = 4 * gp + g;
-                if (gg < NG) {
-                    double2* dst = reinterpret_cast<double2*>(a.jtop + ((size_t)c * a.n_top_pad + row) * PC + 8 * gg + 2 * (lane & 3));
-                    *dst = make_double2(acc[g][0], acc[g][1]);
-                }
-            }
-        }
-    }
-    __syncthreads();
-}
-
-// The same product with the K range of every stage split over the warps: warp = (row tile, K slot), KQ K slots per
-// row tile, one k-step per warp and stage, so RB*KQ (up to 16) warps issue MMAs and all four FP64 tensor pipes of
-// the SM are busy even when a block has only a few row tiles. The KQ partial sums of a row tile meet in shared
-// memory at the end and are added in a fixed order.
-template <int NG, int KM>
-__device__ void top_product_ksplit(const SubArgs& a, double* buf, int RB, int KQ, int S, int c0, int nc, int worker,
-                                   int n_workers) {
-    // KM k-steps per warp and stage: a stage holds KB = KQ * KM k-steps, so one block barrier covers KM * GW MMAs per warp
-    constexpr int PC = 8 * NG;
-    constexpr int GW = NG < 4 ? NG : 4;
-    constexpr int GP = (NG + 3) / 4;
-    const int KB = KQ * KM;
-    const int RT = (a.n_top + 7) / 8, RTP = a.n_top_pad / 8, KS = a.n_top_pad / 4;
-    const int NB = (RT + RB - 1) / RB;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int rtl = warp / KQ, kq = warp % KQ;
-    const int stage_doubles = (RB + GW) * KB * 32;
-    const int pieces = stage_doubles / 2;
-    const int n_tasks = nc * NB * GP;
-    const int nkb = KS / KB;
-    for (int task = worker; task < n_tasks; task += n_workers) {
-        const int gp = task % GP, nb = (task / GP) % NB, c = c0 + task / (GP * NB);
-        const int rt = nb * RB + rtl;
-        const bool active = rtl < RB && rt < RT;
-        // B fragments are staged as [kk][n ^ 4*(kk>>1)]: a half warp (n = 0..3 or 4..7, kk = 0..3) then reads 16
-        // doubles that fall into 16 different 8-byte banks
-        const double* src0[2]; size_t step[2]; bool have[2]; int dofs[2];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int i = threadIdx.x + j * NT;
-            have[j] = i < pieces;
-            const int frag = i / 16, piece = i % 16, which = frag / KB, kl = frag % KB;
-            dofs[j] = i * 2;
-            if (which < RB) {
-                src0[j] = a.SinvP + ((size_t)min(nb * RB + which, RTP - 1) * KS + kl) * 32 + piece * 2;
-                step[j] = (size_t)KB * 32;
-            } else {
-                const int gg = min(4 * gp + (which - RB), NG - 1);
-                const int kk = piece >> 2, n2 = (piece & 3) * 2;
-                src0[j] = a.rtop + ((size_t)c * a.n_top_pad + 4 * kl + kk) * PC + 8 * gg + n2;
-                step[j] = (size_t)KB * 4 * PC;
-                dofs[j] = frag * 32 + kk * 8 + (n2 ^ ((kk >> 1) << 2));
-            }
-        }
-        // running source pointers and ring slots: the per-iteration bookkeeping is a handful of instructions
-        const double* sp0 = src0[0]; const double* sp1 = src0[1];
-        int issued = 0, islot = 0;
-        auto issue = [&]() {
-            if (issued < nkb) {
-                double* dst = buf + (size_t)islot * stage_doubles;
-                if (!(a.dbg & 32)) {      // timing experiment: JJ_SUB_DEBUG=32 skips the staging loads
-                    if (have[0]) cp_async16(dst + dofs[0], sp0);
-                    if (have[1]) cp_async16(dst + dofs[1], sp1);
-                }
-                sp0 += step[0]; sp1 += step[1];
-                ++issued;
-                if (++islot == S) islot = 0;
-            }
-            asm volatile("cp.async.commit_group;");
-        };
-        long long tp0 = a.prof ? clock64() : 0;
-        __syncthreads();                           // the ring is free (previous task / phase done)
-        for (int k = 0; k < S - 1; ++k) issue();
-        double acc[GW][2];
-#pragma unroll
-        for (int g = 0; g < GW; ++g) { acc[g][0] = 0.0; acc[g][1] = 0.0; }
-        const int a_off = (rtl * KB + kq) * 32 + lane;
-        const int b_off = (RB * KB + kq) * 32 + (lane & 3) * 8 + ((lane >> 2) ^ (((lane & 3) >> 1) << 2));   // group g: + g*KB*32
-        const double* st = buf;
-        int cslot = 0;
-        for (int kb = 0; kb < nkb; ++kb) {
-            if (S == 4) asm volatile("cp.async.wait_group 2;");
-            else if (S == 3) asm volatile("cp.async.wait_group 1;");
-            else asm volatile("cp.async.wait_group 0;");
-            __syncthreads();
-            if (a.prof && kb == 0 && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 8 + 40] += tn - tp0; tp0 = tn; }
-            issue();
-            if (active) {
-                double av[KM], bv[KM][GW];
-#pragma unroll
-                for (int m = 0; m < KM; ++m) {
-                    av[m] = st[a_off + m * KQ * 32];
-#pragma unroll
-                    for (int g = 0; g < GW; ++g) bv[m][g] = st[b_off + m * KQ * 32 + g * KB * 32];
-                }
-                if (a.dbg & 16) {         // timing experiment: JJ_SUB_DEBUG=16 replaces the MMAs by one add each
-#pragma unroll
-                    for (int m = 0; m < KM; ++m)
-#pragma unroll
-                        for (int g = 0; g < GW; ++g) acc[g][0] += av[m] + bv[m][g];
-                } else {
-#pragma unroll
-                    for (int m = 0; m < KM; ++m)
-#pragma unroll
-                        for (int g = 0; g < GW; ++g) dmma884(acc[g][0], acc[g][1], av[m], bv[m][g]);
-                }
-            }
-            st += stage_doubles;
-            if (++cslot == S) { cslot = 0; st = buf; }
-        }
-        asm volatile("cp.async.wait_group 0;");
-        if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 8 + 41] += tn - tp0; tp0 = tn; }
-        __syncthreads();                           // everyone is done with the ring: reuse it for the partial sums
-        if (active) {
-#pragma unroll
-            for (int g = 0; g < GW; ++g)
-                *reinterpret_cast<double2*>(buf + ((size_t)(warp * GW + g) * 32 + lane) * 2) = make_double2(acc[g][0], acc[g][1]);
-        }
-        __syncthreads();
-        if (active && kq == 0) {
-            const int row = 8 * rt + (lane >> 2);
-#pragma unroll
-            for (int g = 0; g < GW; ++g) {
-                const int gg = 4 * gp + g;
-                if (gg < NG) {
-                    double2 sum = make_double2(0.0, 0.0);
-                    for (int k2 = 0; k2 < KQ; ++k2) {
-                        const double2 part = *reinterpret_cast<const double2*>(buf + ((size_t)((warp + k2) * GW + g) * 32 + lane) * 2);
-                        sum.x += part.x; sum.y += part.y;
-                    }
-                    double2* dst = reinterpret_cast<double2*>(a.jtop + ((size_t)c * a.n_top_pad + row) * PC + 8 * gg + 2 * (lane & 3));
-                    if (a.dbg & 48) sum = make_double2(0.0, 0.0);      // timing experiments: keep the dynamics finite
-                    *dst = sum;
-                }
-            }
-        }
-        if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 8 + 42] += tn - tp0; }
-    }
-    __syncthreads();
-}
-
-// J_top = S_top^-1 r_top with the A fragments (the packed inverse) read straight from L2 into registers: a fragment is
-// used by exactly one warp, so staging it in shared memory only costs shared-memory bandwidth (the product was bound
-// by it: 52 KB of shared-memory traffic per 30 MMAs). Only the B fragments (r_top, shared by all row tiles of the
-// block) go through the cp.async ring; a stage holds KB = KQ * KM k-steps; warp = (row tile, K slot) as in
-// top_product_ksplit, A fragments of the next stage are in flight while this stage is multiplied.
+// J_tt = S_tt^-1 r_tt (dense top of the top) with the A fragments (the packed inverse) read straight from L2 into
+// registers: a fragment is used by exactly one warp, so staging it in shared memory only costs shared-memory bandwidth.
+// Only the B fragments (r_tt, shared by all row tiles of the block) go through a cp.async ring in the staging rows
+// (idle between the sweeps); a stage holds KB = KQ * KM k-steps; warp = (row tile, K slot): the K range is split over
+// otherwise idle warps, the KQ partial sums of a row tile meet in shared memory and are added in a fixed order. The A
+// fragments of the next stage are in flight while this stage is multiplied.
 template <int NG, int KM>
 __device__ void top_product_areg(const SubArgs& a, double* buf, int RB, int KQ, int S, int c0, int nc, int worker,
                                  int n_workers) {
@@ -939,7 +738,7 @@ __device__ void top_product_areg(const SubArgs& a, double* buf, int RB, int KQ, 
     constexpr int GW = NG < 4 ? NG : 4;
     constexpr int GP = (NG + 3) / 4;
     const int KB = KQ * KM;
-    const int RT = (a.n_top + 7) / 8, RTP = a.n_top_pad / 8, KS = a.n_top_pad / 4;
+    const int RT = (a.n_tt + 7) / 8, RTP = a.n_tt_pad / 8, KS = a.n_tt_pad / 4;
     const int NB = (RT + RB - 1) / RB;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rtl = warp / KQ, kq = warp % KQ;
@@ -955,12 +754,13 @@ __device__ void top_product_areg(const SubArgs& a, double* buf, int RB, int KQ, 
         const int c = c0 + task % nc, nb = (task / nc) % NB, gp = task / (nc * NB);
         const int rt = nb * RB + rtl;
         const bool active = rtl < RB && rt < RT;
-        // B fragments are staged as [kk][n ^ 4*(kk>>1)] (see top_product_ksplit)
+        // B fragments are staged as [kk][n ^ 4*(kk>>1)]: a half warp (n = 0..3 or 4..7, kk = 0..3) then reads 16
+        // doubles that fall into 16 different 8-byte banks
         const int i = threadIdx.x;
         const bool have = i < pieces;
         const int frag = i / 16, piece = i % 16, gsel = frag / KB, kl = frag % KB;
         const int gg = min(4 * gp + gsel, NG - 1), kk = piece >> 2, n2 = (piece & 3) * 2;
-        const double* sp = a.rtop + ((size_t)c * a.n_top_pad + 4 * kl + kk) * PC + 8 * gg + n2;
+        const double* sp = a.rtop + ((size_t)c * a.n_up_pad + a.tt0 + 4 * kl + kk) * PC + 8 * gg + n2;
         const size_t sstep = (size_t)KB * 4 * PC;
         const int dofs = frag * 32 + kk * 8 + (n2 ^ ((kk >> 1) << 2));
         int issued = 0, islot = 0;
@@ -1034,8 +834,129 @@ __device__ void top_product_areg(const SubArgs& a, double* buf, int RB, int KQ, 
                         const double2 part = *reinterpret_cast<const double2*>(buf + ((size_t)((warp + k2) * GW + g) * 32 + lane) * 2);
                         sum.x += part.x; sum.y += part.y;
                     }
-                    double2* dst = reinterpret_cast<double2*>(a.jtop + ((size_t)c * a.n_top_pad + row) * PC + 8 * gg2 + 2 * (lane & 3));
+                    double2* dst = reinterpret_cast<double2*>(a.jtop + ((size_t)c * a.n_up_pad + a.tt0 + row) * PC + 8 * gg2 + 2 * (lane & 3));
                     *dst = sum;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// One phase of the upper program (the separators between the subdomains and the dense top of the top): every task is
+// a gathered dense product  out[rows] = V . X[cols]  over the r / z / J planes of the separator rows, for up_RB 8-row
+// tiles and one problem chunk. It is the dense top product with two differences: the B fragments are gathered row by
+// row through the task's column list (row codes plane << 28 | row, prefetched one stage ahead), and the A fragments
+// are the task's own. Tasks of a phase are independent (a grid barrier ends the phase); they are sorted by
+// decreasing cost on the host and dealt to the blocks round-robin, chunk-minor: the blocks that run at the same time
+// apply the SAME A fragments to different problem chunks, so these come from HBM once and hit in L2 afterwards.
+template <int NG>
+__device__ void upper_phase(const SubArgs& a, double* buf, int phase) {
+    constexpr int PC = 8 * NG;
+    constexpr int GW = NG < 4 ? NG : 4;
+    constexpr int GP = (NG + 3) / 4;
+    constexpr int KM = 2;                              // k-steps per warp and stage (host: subdomain.UP_KM)
+    const int RB = a.up_RB, KB = a.up_KB, KQ = NWARPS / RB;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rtl = warp / KQ, kq = warp % KQ;
+    const int stage_doubles = GW * KB * 32;
+    const int pieces = stage_doubles / 2;              // <= NT: one 16-byte piece per thread and stage
+    const int stage_bytes = a.stage_rows * (PC + 2) * 8;
+    const int S = min(4, stage_bytes / (stage_doubles * 8));
+    const int t_lo = __ldg(a.up_phase_ptr + phase), n_t = __ldg(a.up_phase_ptr + phase + 1) - t_lo;
+    const long long n_pairs = (long long)n_t * a.n_chunks * GP;
+    const size_t plane_elems = (size_t)a.n_chunks * a.n_up_pad * PC;
+    const unsigned long long pol = policy_evict_last();
+    for (long long p = blockIdx.x; p < n_pairs; p += gridDim.x) {
+        const int c = (int)(p % a.n_chunks), t = t_lo + (int)((p / a.n_chunks) % n_t), gp = (int)(p / ((long long)a.n_chunks * n_t));
+        const int4 hd = __ldg(a.up_task + t);          // out code, rows, k-steps, first column
+        const int tiles = (hd.y + 7) >> 3, nk = hd.z;
+        const int nkb = nk / KB;
+        const bool active = rtl < tiles;
+        const int i = threadIdx.x;
+        const bool have = i < pieces;
+        const int frag = i / 16, piece = i % 16, gsel = frag / KB, kl = frag % KB;
+        const int gg = min(4 * gp + gsel, NG - 1), kk = piece >> 2, n2 = (piece & 3) * 2;
+        const int* cp = a.up_cols + hd.w + 4 * kl + kk;
+        const double* ubase = a.U + (size_t)c * a.n_up_pad * PC + 8 * gg + n2;
+        const int dofs = frag * 32 + kk * 8 + (n2 ^ ((kk >> 1) << 2));
+        int cnext = have ? __ldg(cp) : 0;
+        int issued = 0, islot = 0;
+        auto issue = [&]() {
+            if (issued < nkb) {
+                const int code = cnext;
+                cp += 4 * KB;
+                ++issued;
+                if (have && issued < nkb) cnext = __ldg(cp);
+                if (have) cp_async16(buf + (size_t)islot * stage_doubles + dofs,
+                                     ubase + (size_t)(code >> 28) * plane_elems + (size_t)(code & 0xfffffff) * PC);
+                if (++islot == S) islot = 0;
+            }
+            asm volatile("cp.async.commit_group;");
+        };
+        const double* ap = a.up_A + __ldg(a.up_task_aoff + t) + ((size_t)min(rtl, tiles - 1) * nk + kq) * 32 + lane;
+        double an[KM];
+#pragma unroll
+        for (int m = 0; m < KM; ++m) {
+            asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(an[m]) : "l"(ap + (size_t)m * KQ * 32), "l"(pol));
+        }
+        __syncthreads();                           // the ring is free (previous task / phase done)
+        for (int k = 0; k < S - 1; ++k) issue();
+        double acc[GW][2];
+#pragma unroll
+        for (int g = 0; g < GW; ++g) { acc[g][0] = 0.0; acc[g][1] = 0.0; }
+        const int b_off = kq * 32 + (lane & 3) * 8 + ((lane >> 2) ^ (((lane & 3) >> 1) << 2));   // group g: + g*KB*32
+        const double* st = buf;
+        int cslot = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+            if (S >= 4) asm volatile("cp.async.wait_group 2;");
+            else if (S == 3) asm volatile("cp.async.wait_group 1;");
+            else asm volatile("cp.async.wait_group 0;");
+            __syncthreads();
+            issue();
+            double av[KM];
+#pragma unroll
+            for (int m = 0; m < KM; ++m) av[m] = an[m];
+            ap += (size_t)KB * 32;
+            if (kb + 1 < nkb) {
+#pragma unroll
+                for (int m = 0; m < KM; ++m)
+                    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(an[m]) : "l"(ap + (size_t)m * KQ * 32), "l"(pol));
+            }
+            if (active) {
+#pragma unroll
+                for (int m = 0; m < KM; ++m) {
+                    double bv[GW];
+#pragma unroll
+                    for (int g = 0; g < GW; ++g) bv[g] = st[b_off + m * KQ * 32 + g * KB * 32];
+#pragma unroll
+                    for (int g = 0; g < GW; ++g) dmma884(acc[g][0], acc[g][1], av[m], bv[g]);
+                }
+            }
+            st += stage_doubles;
+            if (++cslot == S) { cslot = 0; st = buf; }
+        }
+        asm volatile("cp.async.wait_group 0;");
+        __syncthreads();                           // everyone is done with the ring: reuse it for the partial sums
+        if (active) {
+#pragma unroll
+            for (int g = 0; g < GW; ++g)
+                *reinterpret_cast<double2*>(buf + ((size_t)(warp * GW + g) * 32 + lane) * 2) = make_double2(acc[g][0], acc[g][1]);
+        }
+        __syncthreads();
+        const int row = 8 * rtl + (lane >> 2);
+        if (active && kq == 0 && row < hd.y) {
+            double* obase = a.U + (size_t)(hd.x >> 28) * plane_elems + ((size_t)c * a.n_up_pad + (hd.x & 0xfffffff) + row) * PC;
+#pragma unroll
+            for (int g = 0; g < GW; ++g) {
+                const int gg2 = 4 * gp + g;
+                if (gg2 < NG) {
+                    double2 sum = make_double2(0.0, 0.0);
+                    for (int k2 = 0; k2 < KQ; ++k2) {
+                        const double2 part = *reinterpret_cast<const double2*>(buf + ((size_t)((warp + k2) * GW + g) * 32 + lane) * 2);
+                        sum.x += part.x; sum.y += part.y;
+                    }
+                    *reinterpret_cast<double2*>(obase + 8 * gg2 + 2 * (lane & 3)) = sum;
                 }
             }
         }
@@ -1080,66 +1001,64 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
     const bool keep_z = n_items <= (int)gridDim.x;     // every block has at most one item: z stays in shared memory
     unsigned bar_target = 0;
     int cur_s = -1;
-    // staged top product: RB row tiles per block so that one round of blocks covers it, K block KB and ring depth S
-    // so that the ring fits in the staging rows (at most two 16-byte pieces per thread and stage)
-    int top_rb = 0, top_kb = 0, top_s = 0, top_kq = 0;
-    if (a.n_top > 0) {
+    // dense top product (top_product_areg): RB row tiles per block so that one round of blocks covers it, the K range
+    // of a stage split over KQ = 16 / RB warps (KQ must divide the number of k-steps), KM k-steps per warp and stage,
+    // a ring of S stages in the staging rows. Without upper phases and with exactly one item per block the whole top
+    // phase is CHUNK-LOCAL: the top rows of a problem chunk are assembled and multiplied by the P blocks of that
+    // chunk, and the barriers only join those blocks.
+    const int n_up = a.n_up_fwd + a.n_up_bwd;
+    int top_rb = 0, ar_kq = 1, top_ar = 0, ar_s = 0;
+    bool chunk_local = false;
+    if (a.n_tt > 0) {
         const int stage_bytes = a.stage_rows * (PC + 2) * 8;
         const int GWr = NG < 4 ? NG : 4, GPr = (NG + 3) / 4;
-        const int per_chunk = max(1, (int)gridDim.x / (a.n_chunks * GPr));
-        top_rb = min(NWARPS, ((a.n_top + 7) / 8 + per_chunk - 1) / per_chunk);
-        for (int need = 3; need >= 2 && top_kb == 0; --need)
-            for (int kb = 4; kb >= 1 && top_kb == 0; kb >>= 1) {
-                const int sb = (top_rb + GWr) * kb * 256;
-                if (sb / 16 <= 2 * NT && need * sb <= stage_bytes) { top_kb = kb; top_s = min(4, stage_bytes / sb); }
+        const int RT = (a.n_tt + 7) / 8, KS = a.n_tt_pad / 4;
+        auto pick = [&](int rb, int& kq, int& km, int& ss) {
+            kq = max(1, NWARPS / rb);
+            while (kq > 1 && KS % kq != 0) --kq;
+            km = 0;
+            for (int m = 8; m >= 1 && km == 0; m >>= 1) {
+                const int sb = GWr * kq * m * 256;
+                if (KS % (kq * m) == 0 && sb / 16 <= NT && 3 * sb <= stage_bytes && NWARPS * GWr * 64 * 8 <= stage_bytes) {
+                    km = m; ss = min(4, stage_bytes / sb);
+                }
             }
-        // few row tiles per block: split K over the idle warps (KQ must divide the number of k-steps)
-        int kq = NWARPS / top_rb;
-        while (kq > 1 && (a.n_top_pad / 4) % kq != 0) --kq;
-        if (kq >= 2 && top_kb > 0) {
-            const int sb = (top_rb + GWr) * kq * 256;
-            if (sb / 16 <= 2 * NT && 3 * sb <= stage_bytes && NWARPS * GWr * 64 * 8 <= stage_bytes) {
-                top_kq = kq; top_s = min(4, stage_bytes / sb);
-            }
+        };
+        if (n_up == 0 && n_items == (int)gridDim.x && a.n_chunks <= 60 && !(a.dbg & 4)) {
+            const int rb = min(NWARPS, (RT * GPr + a.P - 1) / a.P);
+            int kq, km, ss = 0;
+            pick(rb, kq, km, ss);
+            if (kq >= 2 && km > 0) { chunk_local = true; top_rb = rb; ar_kq = kq; top_ar = km; ar_s = ss; }
+        }
+        if (!chunk_local) {
+            const int per_chunk = max(1, (int)gridDim.x / (a.n_chunks * GPr));
+            top_rb = min(NWARPS, (RT + per_chunk - 1) / per_chunk);
+            if (!(a.dbg & 64)) pick(top_rb, ar_kq, top_ar, ar_s);
         }
     }
-    // chunk-local top phase: exactly one item per block, K-split product available, and the row blocks of a chunk
-    // fit its P blocks in one round
-    bool chunk_local = false;
-    if (a.n_top > 0 && n_items == (int)gridDim.x && top_kq >= 2 && a.n_chunks <= 60 && !(a.dbg & 4)) {
-        const int GPr = (NG + 3) / 4;
-        const int rb = min(NWARPS, ((a.n_top + 7) / 8 * GPr + a.P - 1) / a.P);
-        int kq = NWARPS / rb;
-        while (kq > 1 && (a.n_top_pad / 4) % kq != 0) --kq;
-        const int stage_bytes = a.stage_rows * (PC + 2) * 8, GWr = NG < 4 ? NG : 4;
-        const int sb = (rb + GWr) * kq * 256;
-        if (kq >= 2 && sb / 16 <= 2 * NT && 3 * sb <= stage_bytes && NWARPS * GWr * 64 * 8 <= stage_bytes) {
-            chunk_local = true; top_rb = rb; top_kq = kq; top_s = min(4, stage_bytes / sb);
+    auto dense_top = [&](int c0, int nc, int worker, int n_workers) {
+        if (top_ar == 8) top_product_areg<NG, 8>(a, stage, top_rb, ar_kq, ar_s, c0, nc, worker, n_workers);
+        else if (top_ar == 4) top_product_areg<NG, 4>(a, stage, top_rb, ar_kq, ar_s, c0, nc, worker, n_workers);
+        else if (top_ar == 2) top_product_areg<NG, 2>(a, stage, top_rb, ar_kq, ar_s, c0, nc, worker, n_workers);
+        else if (top_ar == 1) top_product_areg<NG, 1>(a, stage, top_rb, ar_kq, ar_s, c0, nc, worker, n_workers);
+        else top_product_direct<NG>(a);
+    };
+    // the solve of the separator rows for all chunks, between the forward and the backward local sweeps
+    auto top_phase_grid = [&](long long n, long long& tq) {
+        grid_barrier(a.bar, bar_target);
+        if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 4] += tn - tq; tq = tn; }
+        top_assemble<NG>(a, n, 0, a.n_chunks, blockIdx.x, gridDim.x);
+        grid_barrier(a.bar, bar_target);
+        for (int ph = 0; ph < a.n_up_fwd; ++ph) { upper_phase<NG>(a, stage, ph); grid_barrier(a.bar, bar_target); }
+        if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 5] += tn - tq; tq = tn; }
+        if (a.n_tt > 0) {
+            dense_top(0, a.n_chunks, blockIdx.x, gridDim.x);
+            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 6] += tn - tq; tq = tn; }
+            grid_barrier(a.bar, bar_target);
         }
-    }
-    // two k-steps per warp and stage when the ring still holds three such stages
-    int top_km = 1;
-    if (top_kq >= 2 && !(a.dbg & 8)) {
-        const int stage_bytes = a.stage_rows * (PC + 2) * 8, GWr = NG < 4 ? NG : 4;
-        const int sb2 = (top_rb + GWr) * top_kq * 2 * 256;
-        if ((a.n_top_pad / 4) % (2 * top_kq) == 0 && sb2 / 16 <= 2 * NT && 3 * sb2 <= stage_bytes) {
-            top_km = 2; top_s = min(4, stage_bytes / sb2);
-        }
-    }
-    // A fragments in registers, B ring of KM k-steps per warp and stage (largest KM whose ring holds >= 3 stages)
-    int top_ar = 0, ar_kq = top_kq, ar_s = top_s;
-    if (a.n_top > 0 && top_rb > 0 && !(a.dbg & 64)) {
-        const int stage_bytes = a.stage_rows * (PC + 2) * 8, GWr = NG < 4 ? NG : 4;
-        if (ar_kq < 2) {            // many row tiles per block (large tops): one K slot, a warp walks the whole K range
-            ar_kq = max(1, NWARPS / top_rb);
-            while (ar_kq > 1 && (a.n_top_pad / 4) % ar_kq != 0) --ar_kq;
-        }
-        for (int km = 8; km >= 1 && top_ar == 0; km >>= 1) {
-            const int sb = GWr * ar_kq * km * 256;
-            if ((a.n_top_pad / 4) % (ar_kq * km) == 0 && sb / 16 <= NT && 3 * sb <= stage_bytes &&
-                NWARPS * GWr * 64 * 8 <= stage_bytes) { top_ar = km; ar_s = min(4, stage_bytes / sb); }
-        }
-    }
+        for (int ph = a.n_up_fwd; ph < n_up; ++ph) { upper_phase<NG>(a, stage, ph); grid_barrier(a.bar, bar_target); }
+        if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 7] += tn - tq; tq = tn; }
+    };
     if (a.dbg_b) {
         // ---- debug: one solve J = S^-1 b through the plan
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -1159,18 +1078,7 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
             rows_to_global<NG>(v, nl, nh, a.ctop + ((size_t)c * a.n_slots + a.hptr[s]) * PC);
             rows_to_global<NG>(v, 0, nl, a.zloc + ((size_t)item * a.n_loc_max) * PC);
         }
-        grid_barrier(a.bar, bar_target);
-        top_assemble<NG>(a, 0, 0, a.n_chunks, blockIdx.x, gridDim.x);
-        grid_barrier(a.bar, bar_target);
-        if (top_ar == 8) top_product_areg<NG, 8>(a, stage, top_rb, ar_kq, ar_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
-        else if (top_ar == 4) top_product_areg<NG, 4>(a, stage, top_rb, ar_kq, ar_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
-            else if (top_ar == 2) top_product_areg<NG, 2>(a, stage, top_rb, ar_kq, ar_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
-            else if (top_ar == 1) top_product_areg<NG, 1>(a, stage, top_rb, ar_kq, ar_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
-            else if (top_kq >= 2 && top_km == 2) top_product_ksplit<NG, 2>(a, stage, top_rb, top_kq, top_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
-            else if (top_kq >= 2) top_product_ksplit<NG, 1>(a, stage, top_rb, top_kq, top_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
-            else if (top_kb == 4) top_product<NG, 4>(a, stage, top_rb, top_s); else if (top_kb == 2) top_product<NG, 2>(a, stage, top_rb, top_s);
-            else if (top_kb == 1) top_product<NG, 1>(a, stage, top_rb, top_s); else top_product_direct<NG>(a);
-        grid_barrier(a.bar, bar_target);
+        { long long tq = 0; top_phase_grid(0, tq); }
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int s = item % a.P, c = item / a.P;
             __syncthreads();
@@ -1182,7 +1090,7 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
                 const int row = e / PC, q = e % PC;
                 double val;
                 if (row < nl) val = __ldcg(a.zloc + ((size_t)item * a.n_loc_max + row) * PC + q);
-                else val = __ldcg(a.jtop + ((size_t)c * a.n_top_pad + ht[row - nl]) * PC + q);
+                else val = __ldcg(a.jtop + ((size_t)c * a.n_up_pad + ht[row - nl]) * PC + q);
                 v[velem<NG>(row, q)] = val;
             }
             __syncthreads();
@@ -1195,7 +1103,7 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
         for (long long e = (long long)blockIdx.x * NT + threadIdx.x; e < (long long)a.n_top * a.n_chunks * PC; e += (long long)gridDim.x * NT) {
             const int q = (int)(e % PC); const long long t = e / PC;
             const int k = (int)(t % a.n_top), c = (int)(t / a.n_top), w = c * PC + q;
-            if (w < a.Wp) a.dbg_J[(size_t)a.top_face[k] * a.Wp + w] = __ldcg(a.jtop + ((size_t)c * a.n_top_pad + k) * PC + q);
+            if (w < a.Wp) a.dbg_J[(size_t)a.top_face[k] * a.Wp + w] = __ldcg(a.jtop + ((size_t)c * a.n_up_pad + k) * PC + q);
         }
         return;
     }
@@ -1214,7 +1122,7 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
                 const int* ht = a.halo_top + a.hptr[s];
                 for (int e = threadIdx.x; e < nh * (PC / 2); e += NT) {
                     const int r = e / (PC / 2), q = (e % (PC / 2)) * 2;
-                    const double2 val = __ldcg(reinterpret_cast<const double2*>(a.jtop + ((size_t)c * a.n_top_pad + ht[r]) * PC + q));
+                    const double2 val = __ldcg(reinterpret_cast<const double2*>(a.jtop + ((size_t)c * a.n_up_pad + ht[r]) * PC + q));
                     *reinterpret_cast<double2*>(v + velem<NG>(nl + r, q)) = val;
                 }
                 if (!keep_z) {
@@ -1257,32 +1165,12 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
             top_assemble<NG>(a, n, c, 1, s, a.P);
             group_barrier(ctr, bar_target, a.P);
             if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 5] += tn - tq; tq = tn; }
-            if (top_ar == 8) top_product_areg<NG, 8>(a, stage, top_rb, ar_kq, ar_s, c, 1, s, a.P);
-            else if (top_ar == 4) top_product_areg<NG, 4>(a, stage, top_rb, ar_kq, ar_s, c, 1, s, a.P);
-            else if (top_ar == 2) top_product_areg<NG, 2>(a, stage, top_rb, ar_kq, ar_s, c, 1, s, a.P);
-            else if (top_ar == 1) top_product_areg<NG, 1>(a, stage, top_rb, ar_kq, ar_s, c, 1, s, a.P);
-            else if (top_km == 2) top_product_ksplit<NG, 2>(a, stage, top_rb, top_kq, top_s, c, 1, s, a.P);
-            else top_product_ksplit<NG, 1>(a, stage, top_rb, top_kq, top_s, c, 1, s, a.P);
+            dense_top(c, 1, s, a.P);
             if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 6] += tn - tq; tq = tn; }
             group_barrier(ctr, bar_target, a.P);
             if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 7] += tn - tq; tq = tn; }
         } else if (a.n_top > 0) {
-            grid_barrier(a.bar, bar_target);
-            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 4] += tn - tq; tq = tn; }
-            top_assemble<NG>(a, n, 0, a.n_chunks, blockIdx.x, gridDim.x);
-            grid_barrier(a.bar, bar_target);
-            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 5] += tn - tq; tq = tn; }
-            if (top_ar == 8) top_product_areg<NG, 8>(a, stage, top_rb, ar_kq, ar_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
-            else if (top_ar == 4) top_product_areg<NG, 4>(a, stage, top_rb, ar_kq, ar_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
-            else if (top_ar == 2) top_product_areg<NG, 2>(a, stage, top_rb, ar_kq, ar_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
-            else if (top_ar == 1) top_product_areg<NG, 1>(a, stage, top_rb, ar_kq, ar_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
-            else if (top_kq >= 2 && top_km == 2) top_product_ksplit<NG, 2>(a, stage, top_rb, top_kq, top_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
-            else if (top_kq >= 2) top_product_ksplit<NG, 1>(a, stage, top_rb, top_kq, top_s, 0, a.n_chunks, blockIdx.x, gridDim.x);
-            else if (top_kb == 4) top_product<NG, 4>(a, stage, top_rb, top_s); else if (top_kb == 2) top_product<NG, 2>(a, stage, top_rb, top_s);
-            else if (top_kb == 1) top_product<NG, 1>(a, stage, top_rb, top_s); else top_product_direct<NG>(a);
-            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 6] += tn - tq; tq = tn; }
-            grid_barrier(a.bar, bar_target);
-            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 7] += tn - tq; tq = tn; }
+            top_phase_grid(n, tq);
         }
     }
 }
@@ -1295,12 +1183,35 @@ __global__ void k_sub_gather_top(int n_top, const int* top_face, const double* f
 
 typedef void (*KernelPtr)(const SubArgs);
 
+}  // namespace
+
+// The step kernel is compiled once per chunk width in its own translation unit (build.sh compiles this file with
+// -DJJ_SUB_NG=1|2|4|8 in parallel; without the macro only the host side below is compiled).
+namespace jj {
+KernelPtr subdomain_kernel_ng1(bool def);
+KernelPtr subdomain_kernel_ng2(bool def);
+KernelPtr subdomain_kernel_ng4(bool def);
+KernelPtr subdomain_kernel_ng8(bool def);
+}
+
+#ifdef JJ_SUB_NG
+#define JJ_SUB_CAT2(a, b) a##b
+#define JJ_SUB_CAT(a, b) JJ_SUB_CAT2(a, b)
+namespace jj {
+KernelPtr JJ_SUB_CAT(subdomain_kernel_ng, JJ_SUB_NG)(bool def) {
+    return def ? k_subdomain<JJ_SUB_NG, true> : k_subdomain<JJ_SUB_NG, false>;
+}
+}
+#else
+
+namespace {
+
 KernelPtr pick_kernel(int NG, bool def) {
     switch (NG) {
-        case 1: return def ? k_subdomain<1, true> : k_subdomain<1, false>;
-        case 2: return def ? k_subdomain<2, true> : k_subdomain<2, false>;
-        case 4: return def ? k_subdomain<4, true> : k_subdomain<4, false>;
-        default: return def ? k_subdomain<8, true> : k_subdomain<8, false>;
+        case 1: return subdomain_kernel_ng1(def);
+        case 2: return subdomain_kernel_ng2(def);
+        case 4: return subdomain_kernel_ng4(def);
+        default: return subdomain_kernel_ng8(def);
     }
 }
 
@@ -1363,11 +1274,11 @@ void subdomain_free_problem(JJHandle* h) {
     if (!st) return;
     dev_free(h, st->rth, st->state_bytes); dev_free(h, st->rx, st->state_bytes);
     dev_free(h, st->zloc, st->z_bytes); dev_free(h, st->ctop, st->c_bytes);
-    dev_free(h, st->rtop, st->t_bytes); dev_free(h, st->jtop, st->t_bytes);
+    dev_free(h, st->U, st->u_bytes);
     dev_free(h, st->bar, BAR_BYTES);
     dev_free(h, st->plane_d, st->plane_cap);
-    st->rth = st->rx = st->zloc = st->ctop = st->rtop = st->jtop = nullptr; st->bar = nullptr;
-    st->plane_d = nullptr; st->plane_cap = 0; st->state_bytes = st->z_bytes = st->c_bytes = st->t_bytes = 0;
+    st->rth = st->rx = st->zloc = st->ctop = st->rtop = st->jtop = st->U = nullptr; st->bar = nullptr;
+    st->plane_d = nullptr; st->plane_cap = 0; st->state_bytes = st->z_bytes = st->c_bytes = st->u_bytes = 0;
     st->prepared = false;
 }
 
@@ -1383,15 +1294,33 @@ void subdomain_drop_plan(JJHandle* h) {
 int subdomain_set_plan(JJHandle* h, const JJSubdomainPlan* pl) {
     subdomain_drop_plan(h);
     if (!pl) return JJ_OK;
-    if (!(pl->NG == 1 || pl->NG == 2 || pl->NG == 4 || pl->NG == 8) || pl->P < 1 || pl->n_top_pad % 32 != 0) {
-        h->err = "subdomain plan: NG must be 1/2/4/8, P >= 1, n_top_pad a multiple of 32";
+    if (!(pl->NG == 1 || pl->NG == 2 || pl->NG == 4 || pl->NG == 8) || pl->P < 1 || pl->n_tt_pad % 32 != 0 ||
+        pl->n_up_pad % 32 != 0 || pl->n_up_pad <= pl->n_top || pl->tt0 + pl->n_tt != pl->n_top ||
+        pl->tt0 + pl->n_tt_pad > pl->n_up_pad || pl->n_up_pad >= (1 << 28)) {
+        h->err = "subdomain plan: NG must be 1/2/4/8, P >= 1, n_tt_pad and n_up_pad multiples of 32 with "
+                 "tt0 + n_tt == n_top < n_up_pad and tt0 + n_tt_pad <= n_up_pad";
+        return JJ_EINVAL;
+    }
+    if (pl->n_up_fwd + pl->n_up_bwd > 0 &&
+        !((pl->up_RB == 4 || pl->up_RB == 8 || pl->up_RB == 16) && pl->up_KB == 2 * (NWARPS / pl->up_RB))) {
+        h->err = "subdomain plan: upper program needs up_RB in {4, 8, 16} and up_KB == 2 * (16 / up_RB)";
         return JJ_EINVAL;
     }
     SubState* st = new SubState();
     h->subdomain_plan = st;
     st->P = pl->P; st->NG = pl->NG; st->PC = 8 * pl->NG;
     st->n_rows = pl->n_rows; st->n_loc_max = pl->n_loc_max; st->stage_rows = pl->stage_rows;
-    st->n_top = pl->n_top; st->n_top_pad = pl->n_top_pad; st->n_slots = pl->n_slots; st->face_K = pl->face_K;
+    st->n_top = pl->n_top; st->n_up_pad = pl->n_up_pad; st->n_slots = pl->n_slots; st->face_K = pl->face_K;
+    st->tt0 = pl->tt0; st->n_tt = pl->n_tt; st->n_tt_pad = pl->n_tt_pad;
+    st->up_RB = pl->up_RB; st->up_KB = pl->up_KB; st->n_up_fwd = pl->n_up_fwd; st->n_up_bwd = pl->n_up_bwd;
+    {   // switches read once per plan (never on the launch path)
+        const char* e;
+        st->dbg = (e = getenv("JJ_SUB_DEBUG")) ? atoi(e) : 0;
+        st->prof = getenv("JJ_SUB_PROF") != nullptr;
+        st->no_tslot4 = getenv("JJ_SUB_NO_TSLOT4") != nullptr;
+        st->no_l2_window = getenv("JJ_SUB_NO_L2_WINDOW") != nullptr;
+        st->grid_env = (e = getenv("JJ_SUB_GRID")) ? atoi(e) : 0;
+    }
     if ((size_t)st->n_rows * st->PC > 65536) { h->err = "subdomain plan: shared-memory vector exceeds the 16-bit element codes"; return JJ_EINVAL; }
     const int Nj = h->cir.Nj, P = pl->P;
     int rc;
@@ -1440,7 +1369,28 @@ int subdomain_set_plan(JJHandle* h, const JJSubdomainPlan* pl) {
         st->allocs.push_back(p); st->alloc_bytes.push_back(bytes);
         st->topF = (double*)p;
     }
-    if ((rc = up(h, st, &st->SinvP, pl->Sinv_packed, (size_t)pl->n_top_pad * pl->n_top_pad))) return rc;
+    if ((rc = up(h, st, &st->SinvP, pl->Sinv_packed, (size_t)pl->n_tt_pad * pl->n_tt_pad))) return rc;
+    {
+        const int n_ph = pl->n_up_fwd + pl->n_up_bwd;
+        if (n_ph > 0) {
+            if (pl->up_phase_ptr[n_ph] != pl->n_up_tasks) { h->err = "subdomain plan: up_phase_ptr does not cover the tasks"; return JJ_EINVAL; }
+            for (int t = 0; t < pl->n_up_tasks; ++t) {
+                const int32_t* hd = pl->up_task + 4 * (size_t)t;
+                const int64_t tiles = (hd[1] + 7) / 8;
+                if (hd[1] < 1 || hd[1] > 8 * pl->up_RB || hd[2] < pl->up_KB || hd[2] % pl->up_KB != 0 || hd[3] < 0 ||
+                    (int64_t)hd[3] + 4 * (int64_t)hd[2] > pl->n_up_cols ||
+                    pl->up_task_aoff[t] < 0 || pl->up_task_aoff[t] + tiles * hd[2] * 32 > pl->n_up_vals) {
+                    h->err = "subdomain plan: malformed task in the upper program"; return JJ_EINVAL;
+                }
+            }
+        }
+        if ((rc = up(h, st, &st->up_phase_ptr, pl->up_phase_ptr, (size_t)n_ph + 1))) return rc;
+        if ((rc = up(h, st, (int**)&st->up_task, pl->up_task, (size_t)pl->n_up_tasks * 4))) return rc;
+        if ((rc = up(h, st, (long long**)&st->up_task_aoff, (const long long*)pl->up_task_aoff, (size_t)pl->n_up_tasks))) return rc;
+        if ((rc = up(h, st, &st->up_cols, pl->up_cols, (size_t)pl->n_up_cols))) return rc;
+        // the kernel prefetches the A fragments of one stage past the end of a task: pad by one stage
+        if ((rc = up(h, st, &st->up_A, pl->up_A, (size_t)pl->n_up_vals, (size_t)(pl->up_KB + 2) * 32 * sizeof(double)))) return rc;
+    }
     if ((rc = up(h, st, &st->junc_ptr, pl->junc_ptr, (size_t)P + 1))) return rc;
     if ((rc = up(h, st, &st->junc_orig, pl->junc_orig, (size_t)Nj))) return rc;
     if ((rc = up(h, st, (int**)&st->junc_row, pl->junc_row, (size_t)Nj * 2))) return rc;
@@ -1474,11 +1424,15 @@ int subdomain_supported(JJHandle* h, std::string& why) {
 static void fill_args(JJHandle* h, SubState* st, SubArgs& a) {
     memset(&a, 0, sizeof(a));
     a.P = st->P; a.n_rows = st->n_rows; a.n_loc_max = st->n_loc_max; a.stage_rows = st->stage_rows;
-    a.n_top = st->n_top; a.n_top_pad = st->n_top_pad; a.n_slots = st->n_slots;
+    a.n_top = st->n_top; a.n_up_pad = st->n_up_pad; a.n_slots = st->n_slots;
+    a.tt0 = st->tt0; a.n_tt = st->n_tt; a.n_tt_pad = st->n_tt_pad;
+    a.up_RB = st->up_RB; a.up_KB = st->up_KB; a.n_up_fwd = st->n_up_fwd; a.n_up_bwd = st->n_up_bwd;
+    a.up_phase_ptr = st->up_phase_ptr; a.up_task = st->up_task; a.up_task_aoff = st->up_task_aoff;
+    a.up_cols = st->up_cols; a.up_A = st->up_A; a.U = st->U;
     a.max_np = st->max_np; a.max_levels = st->max_levels; a.max_tiles = st->max_tiles;
     a.prog = st->prog; a.n_loc = st->n_loc; a.n_halo = st->n_halo; a.hptr = st->hptr; a.halo_top = st->halo_top;
     a.tptr = st->tptr; a.tslot = st->tslot; a.top_face = st->top_face; a.SinvP = st->SinvP;
-    a.tslot4 = getenv("JJ_SUB_NO_TSLOT4") ? nullptr : st->tslot4;
+    a.tslot4 = st->no_tslot4 ? nullptr : st->tslot4;
     a.topF = (h->src[JJ_SRC_F].dev.kind == KIND_RANK1 && st->n_top > 0) ? st->topF : nullptr;
     a.junc_ptr = st->junc_ptr; a.junc_orig = st->junc_orig; a.junc_row = st->junc_row; a.junc_sign = st->junc_sign;
     a.face_K = st->face_K; a.face_ell_j = st->face_ell_j; a.face_ell_c = st->face_ell_c; a.face_fidx = st->face_fidx;
@@ -1489,7 +1443,7 @@ static void fill_args(JJHandle* h, SubState* st, SubArgs& a) {
     a.rth = st->rth; a.rx = st->rx; a.th1 = h->th1; a.th2 = h->th2;
     a.zloc = st->zloc; a.ctop = st->ctop; a.rtop = st->rtop; a.jtop = st->jtop; a.bar = st->bar;
     a.snap_th = h->th_out; a.snap_I = h->I_out; a.flag = h->flag_d;
-    { const char* d = getenv("JJ_SUB_DEBUG"); a.dbg = d ? atoi(d) : 0; }
+    a.dbg = st->dbg;
 }
 
 static int launch(JJHandle* h, SubState* st, SubArgs& a) {
@@ -1515,21 +1469,20 @@ static int launch(JJHandle* h, SubState* st, SubArgs& a) {
         st->grid = sms * std::min(per_sm, 1);
     }
     // the staged top product sizes its row blocks to the grid: give it up to 18 blocks per chunk and group pass
-    const int top_tasks = st->n_chunks * ((st->NG + 3) / 4) * std::min(18, (st->n_top + 7) / 8);
+    const int top_tasks = st->n_chunks * ((st->NG + 3) / 4) * std::min(18, (st->n_tt + 7) / 8);
     int want = std::max(st->P * st->n_chunks, top_tasks);
-    const char* env = getenv("JJ_SUB_GRID");
+    if (st->n_up_fwd + st->n_up_bwd > 0) want = st->grid;      // the upper phases spread over every SM
     int grid = std::min(st->grid, std::max(1, want));
-    if (env && atoi(env) > 0) grid = std::min(st->grid, atoi(env));
+    if (st->grid_env > 0) grid = std::min(st->grid, st->grid_env);
     SCK(cudaMemsetAsync(st->bar, 0, BAR_BYTES, h->stream));
-    if (st->n_top > 0 && !getenv("JJ_SUB_NO_L2_WINDOW")) {
+    if (st->n_tt > 0 && !st->no_l2_window) {
         // keep the packed Schur inverse resident in L2: it is re-read by every block once per time step while
-        // the state (hundreds of MB per step) streams through the same cache
-        static bool limit_set = false;
-        if (!limit_set) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)32 << 20); limit_set = true; }
+        // the state (hundreds of MB per step) streams through the same cache. The limit is a per-device setting.
+        if (!st->l2_limit_set) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)32 << 20); st->l2_limit_set = true; }
         cudaStreamAttrValue attr;
         memset(&attr, 0, sizeof(attr));
         attr.accessPolicyWindow.base_ptr = (void*)st->SinvP;
-        attr.accessPolicyWindow.num_bytes = (size_t)st->n_top_pad * st->n_top_pad * sizeof(double);
+        attr.accessPolicyWindow.num_bytes = (size_t)st->n_tt_pad * st->n_tt_pad * sizeof(double);
         attr.accessPolicyWindow.hitRatio = 1.0f;
         attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
         attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
@@ -1551,21 +1504,20 @@ int subdomain_prepare(JJHandle* h) {
     st->state_bytes = (size_t)st->n_chunks * h->cir.Nj * PC * sizeof(double);
     st->z_bytes = (size_t)st->n_chunks * st->P * std::max(st->n_loc_max, 1) * PC * sizeof(double);
     st->c_bytes = (size_t)st->n_chunks * std::max(st->n_slots, 1) * PC * sizeof(double);
-    st->t_bytes = (size_t)st->n_chunks * std::max(st->n_top_pad, 32) * PC * sizeof(double);
+    st->u_bytes = (size_t)3 * st->n_chunks * std::max(st->n_up_pad, 32) * PC * sizeof(double);
     int rc;
     if ((rc = dev_alloc(h, (void**)&st->rth, st->state_bytes))) return rc;
     if ((rc = dev_alloc(h, (void**)&st->rx, st->state_bytes))) return rc;
     if ((rc = dev_alloc(h, (void**)&st->zloc, st->z_bytes))) return rc;
     if ((rc = dev_alloc(h, (void**)&st->ctop, st->c_bytes))) return rc;
-    if ((rc = dev_alloc(h, (void**)&st->rtop, st->t_bytes))) return rc;
-    if ((rc = dev_alloc(h, (void**)&st->jtop, st->t_bytes))) return rc;
+    if ((rc = dev_alloc(h, (void**)&st->U, st->u_bytes))) return rc;
+    st->rtop = st->U; st->jtop = st->U + st->u_bytes / sizeof(double) / 3 * 2;
     if ((rc = dev_alloc(h, (void**)&st->bar, BAR_BYTES))) return rc;
     SCK(cudaMemsetAsync(st->rth, 0, st->state_bytes, h->stream));
     SCK(cudaMemsetAsync(st->rx, 0, st->state_bytes, h->stream));
     SCK(cudaMemsetAsync(st->zloc, 0, st->z_bytes, h->stream));
     SCK(cudaMemsetAsync(st->ctop, 0, st->c_bytes, h->stream));
-    SCK(cudaMemsetAsync(st->rtop, 0, st->t_bytes, h->stream));
-    SCK(cudaMemsetAsync(st->jtop, 0, st->t_bytes, h->stream));
+    SCK(cudaMemsetAsync(st->U, 0, st->u_bytes, h->stream));
     st->prepared = true;
     return JJ_OK;
 }
@@ -1598,7 +1550,7 @@ int subdomain_run(JJHandle* h, long long i0, int n, const long long* th_plane, c
     SubArgs a;
     fill_args(h, st, a);
     a.i0 = i0; a.n = n; a.th_plane = st->plane_d; a.I_plane = st->plane_d + n;
-    if (!getenv("JJ_SUB_PROF")) return launch(h, st, a);
+    if (!st->prof) return launch(h, st, a);
     // debugging aid: per-phase cycle counts of every block, printed as averages per time step
     const size_t nb = 1024;
     long long* prof = nullptr;
@@ -1653,3 +1605,5 @@ void subdomain_get_config(JJHandle* h, int* P, int* PC) {
 }
 
 }  // namespace jj
+
+#endif  // JJ_SUB_NG

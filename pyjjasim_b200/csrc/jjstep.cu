@@ -5,8 +5,8 @@
 //   k_step   fused "finish step n-1 / start step n" per junction  (reference: time_evolution.py:533-558,570-580)
 //   k_face   b = A (x/c0 - theta_s) - 2 pi f per face              (reference: time_evolution.py:560-569)
 //   k_solve  one launch per level of the compiled solve program    (reference: time_evolution.py:506,562-569)
-// It handles every input form and any circuit size; the resident engine (jj_resident.cu) is the fast
-// path for problems whose right-hand sides fit in a cluster's shared memory.
+// It handles every input form (dense per-step tables, dense voltage sources) and any circuit size; the subdomain
+// engine (jj_subdomain.cu) is the fast path for everything else.
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -384,7 +384,6 @@ static void free_problem(JJHandle* h) {
     dev_free(h, h->noise_buf, h->noise_cap); h->noise_buf = nullptr; h->noise_cap = 0; h->noise_K = 0;
     dev_free(h, h->th_out, (size_t)h->th_cap_planes * nj); dev_free(h, h->I_out, (size_t)h->I_cap_planes * nj);
     h->th_out = h->I_out = nullptr; h->n_th_planes = h->n_I_planes = 0; h->th_cap_planes = h->I_cap_planes = 0;
-    resident_free(h);
     subdomain_free_problem(h);
     h->have_problem = h->have_state = false;
 }
@@ -402,7 +401,6 @@ void jj_destroy(JJHandle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     free_problem(h);
-    resident_drop_plan(h);
     subdomain_drop_plan(h);
     free_sweep(h, h->fwd); free_sweep(h, h->bwd);
     free_circuit(h);
@@ -418,7 +416,6 @@ int jj_set_circuit(JJHandle* h, const JJCircuit* c) {
     REQUIRE(c && c->Nj > 0 && c->Nf >= 0, JJ_EINVAL, "circuit: bad sizes");
     REQUIRE(c->cpr_harmonics >= 1 && c->cpr_harmonics <= 16, JJ_EINVAL, "circuit: cpr_harmonics must be 1..16");
     if (h->have_problem) free_problem(h);
-    resident_drop_plan(h);
     subdomain_drop_plan(h);
     free_circuit(h);
     CircuitDev& d = h->cir;
@@ -451,8 +448,6 @@ int jj_set_solver(JJHandle* h, const JJSweep* fwd, const JJSweep* bwd) {
     CK(cudaSetDevice(h->device));
     REQUIRE(fwd && bwd, JJ_EINVAL, "solver: null sweep");
     if (h->have_problem) free_problem(h);
-    resident_drop_plan(h);
-    subdomain_drop_plan(h);
     int rc;
     if ((rc = upload_sweep(h, h->fwd, fwd))) return rc;
     if ((rc = upload_sweep(h, h->bwd, bwd))) return rc;
@@ -465,7 +460,7 @@ int jj_set_problem(JJHandle* h, int32_t W, double dt, uint64_t seed, int64_t pro
     REQUIRE(h->have_circuit && h->have_solver, JJ_ESTATE, "set_problem: circuit and solver must be set first");
     REQUIRE(W > 0 && dt > 0, JJ_EINVAL, "set_problem: W and dt must be positive");
     REQUIRE(problem_offset % 4 == 0, JJ_EINVAL, "set_problem: problem_offset must be a multiple of 4");
-    REQUIRE(engine >= 0 && engine <= 3, JJ_EINVAL, "set_problem: unknown engine");
+    REQUIRE(engine == JJ_ENGINE_AUTO || engine == JJ_ENGINE_STREAMING || engine == JJ_ENGINE_SUBDOMAIN, JJ_EINVAL, "set_problem: unknown engine");
     // same problem count as before (annealing loops, repeated compute() calls on a cached engine): keep the state
     // arrays of all engines and only reset them; cudaMalloc/cudaFree of ~10 large arrays costs tens of milliseconds
     const bool same = h->have_problem && h->W == W && h->th1 && h->th2 && h->x && !h->thetas;
@@ -704,25 +699,23 @@ int jj_run(JJHandle* h, int64_t i0, int32_t n, const int64_t* th_plane, const in
     int want = h->engine_req;
     std::string why;
     if (want == JJ_ENGINE_AUTO)
-        want = (!h->thetas && subdomain_supported(h, why)) ? JJ_ENGINE_SUBDOMAIN
-               : (!h->thetas && resident_supported(h, why)) ? JJ_ENGINE_RESIDENT : JJ_ENGINE_STREAMING;
-    if (want == JJ_ENGINE_RESIDENT) {
-        if (!resident_supported(h, why)) { h->err = "resident engine not applicable: " + why; return JJ_EINVAL; }
-        if (!h->resident) { if ((rc = resident_prepare(h))) return rc; }
-    }
+        want = (!h->thetas && subdomain_supported(h, why)) ? JJ_ENGINE_SUBDOMAIN : JJ_ENGINE_STREAMING;
     if (want == JJ_ENGINE_SUBDOMAIN) {
         if (!subdomain_supported(h, why)) { h->err = "subdomain engine not applicable: " + why; return JJ_EINVAL; }
         if (!subdomain_prepared(h)) { if ((rc = subdomain_prepare(h))) return rc; }
     }
-    if ((want == JJ_ENGINE_RESIDENT || want == JJ_ENGINE_SUBDOMAIN) && h->thetas) {
-        h->err = "the shared-memory engines do not support dense voltage sources";
+    if (want == JJ_ENGINE_SUBDOMAIN && h->thetas) {
+        h->err = "the subdomain engine does not support dense voltage sources";
         return JJ_EINVAL;
     }
     h->engine = want;
     CK(cudaEventRecord(h->ev0, h->stream));
-    if (want == JJ_ENGINE_RESIDENT) rc = resident_run(h, i0, n, (const long long*)th_plane, (const long long*)I_plane);
-    else if (want == JJ_ENGINE_SUBDOMAIN) rc = subdomain_run(h, i0, n, (const long long*)th_plane, (const long long*)I_plane);
-    else rc = streaming_run(h, i0, n, (const long long*)th_plane, (const long long*)I_plane);
+    if (want == JJ_ENGINE_SUBDOMAIN) rc = subdomain_run(h, i0, n, (const long long*)th_plane, (const long long*)I_plane);
+    else {
+        REQUIRE(h->cir.Nf == 0 || h->fwd.n_levels > 0, JJ_ESTATE,
+                "run: the streaming engine needs a solve program (jj_set_solver was given empty sweeps)");
+        rc = streaming_run(h, i0, n, (const long long*)th_plane, (const long long*)I_plane);
+    }
     if (rc) return rc;
     CK(cudaEventRecord(h->ev1, h->stream));
     CK(cudaEventSynchronize(h->ev1));
@@ -788,16 +781,9 @@ int jj_debug_solve(JJHandle* h, const double* b, double* J) {
     return JJ_OK;
 }
 
-int jj_set_resident_plan(JJHandle* h, const JJResidentPlan* plan) {
-    CK(cudaSetDevice(h->device));
-    REQUIRE(h->have_circuit && h->have_solver, JJ_ESTATE, "set_resident_plan: circuit and solver must be set first");
-    if (h->have_problem) free_problem(h);
-    return resident_set_plan(h, plan);
-}
-
 int jj_set_subdomain_plan(JJHandle* h, const JJSubdomainPlan* plan) {
     CK(cudaSetDevice(h->device));
-    REQUIRE(h->have_circuit && h->have_solver, JJ_ESTATE, "set_subdomain_plan: circuit and solver must be set first");
+    REQUIRE(h->have_circuit, JJ_ESTATE, "set_subdomain_plan: the circuit must be set first");
     if (h->have_problem) free_problem(h);
     return subdomain_set_plan(h, plan);
 }
@@ -819,23 +805,6 @@ int jj_debug_subdomain_solve(JJHandle* h, const double* b, double* J) {
     return rc;
 }
 
-int jj_debug_resident_solve(JJHandle* h, const double* b, double* J) {
-    CK(cudaSetDevice(h->device));
-    REQUIRE(h->have_problem && h->cir.Nf > 0, JJ_ESTATE, "debug_resident_solve: problem not set");
-    double* tmp = nullptr;
-    size_t bytes = (size_t)h->cir.Nf * h->Wp * sizeof(double);
-    int rc = dev_alloc(h, (void**)&tmp, bytes);
-    if (rc) return rc;
-    CK(cudaMemsetAsync(tmp, 0, bytes, h->stream));
-    CK(cudaMemsetAsync(h->v, 0, bytes, h->stream));
-    if ((rc = h2d_padded(h, h->v, b, h->cir.Nf)) == 0 && (rc = resident_debug_solve(h, h->v, tmp)) == 0)
-        rc = d2h_padded(h, J, tmp, h->cir.Nf);
-    cudaError_t e = cudaStreamSynchronize(h->stream);
-    dev_free(h, tmp, bytes);
-    if (rc == 0 && e != cudaSuccess) { h->err = std::string("debug_resident_solve: ") + cudaGetErrorString(e); rc = JJ_ECUDA; }
-    return rc;
-}
-
 int jj_stats(JJHandle* h, JJStats* out) {
     memset(out, 0, sizeof(*out));
     out->engine = h->engine;
@@ -845,7 +814,6 @@ int jj_stats(JJHandle* h, JJStats* out) {
     out->device_bytes = h->device_bytes;
     out->non_finite = h->non_finite;
     out->cluster_size = 1; out->tile_problems = h->Wp;
-    if (h->engine == JJ_ENGINE_RESIDENT) { int c, w; resident_get_config(h, &c, &w); out->cluster_size = c; out->tile_problems = w; }
     if (h->engine == JJ_ENGINE_SUBDOMAIN) { int c, w; subdomain_get_config(h, &c, &w); out->cluster_size = c; out->tile_problems = w; }
     return JJ_OK;
 }

@@ -68,8 +68,11 @@ def compute_sharded(problem, device=None, group=None, core=None):
         if core is not None:
             th, I = core(prob, th_mask, I_mask, w0, w1)
         else:
-            from .engine import device_time_evolution_core
-            th, I = device_time_evolution_core(prob, th_mask, I_mask, shard=(w0, w1), device=device)
+            from .engine import device_time_evolution_core, resolve_noise_seed
+            # one Philox seed for the whole job: rank 0 resolves it (explicit noise_seed, or a fresh draw), all use it
+            box = [resolve_noise_seed(prob) if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0, group=group)
+            th, I = device_time_evolution_core(prob, th_mask, I_mask, shard=(w0, w1), device=device, noise_seed=box[0])
         return gather_problem_axis(th, W, group), gather_problem_axis(I, W, group)
 
     return _time_evolution(problem, core=sharded_core)

@@ -24,7 +24,7 @@ import scipy.sparse
 
 from . import _lib
 from .current_phase_relation import harmonics
-from .factor import factorize, streaming_program, resident_plan, system_matrix
+from .factor import factorize, streaming_program, system_matrix
 from .subdomain import subdomain_plan, face_tables
 from .sources import classify_source, nonnegative_factors, ZERO, RANK1, DENSE
 
@@ -132,13 +132,20 @@ class CircuitTables:
             self.factor = factorize(S, cx, cy, leaf_size=leaf_size, n_parts=n_parts)
             if n_parts is not None and n_parts > 1 and os.environ.get("JJ_SUB_BALANCE", "1") != "0":
                 self.factor = self._balance_parts(A, S, cx, cy, leaf_size, n_parts, self.factor)
-            self.program = streaming_program(self.factor)
-            perm = self.program.perm.astype(np.int64)
+            self._program = None
+            perm = self.factor.perm.astype(np.int64)
         else:
-            self.program = None
+            self._program = None
             self.factor = None
             perm = np.zeros(0, dtype=np.int64)
         self._finish_tables(A, perm)
+
+    @property
+    def program(self):
+        """Solve program of the streaming engine (built on first use: only dense per-step inputs need it)."""
+        if self._program is None and self.factor is not None:
+            self._program = streaming_program(self.factor)
+        return self._program
 
     def _balance_parts(self, A, S, cx, cy, leaf_size, n_parts, F, rounds=2):
         """Re-run the dissection with part weights so that the WORK of the subdomains (sweep stream steps, junctions,
@@ -194,10 +201,11 @@ class CircuitTables:
         jf[rows, slot] = inv[At.indices]
         js[rows, slot] = At.data
         self.junc_face, self.junc_sign = jf, js
-        self._resident = {}
         self._subdomain = {}
 
     # ------------------------------------------------------------------ subdomain engine plan
+    SMEM_LIMIT = 227 * 1024
+
     def subdomain_smem_bytes(self, plan):
         PC = plan.PC
         aux = 3 * max(ps["n_levels"] * ps["n_warps"] + 1 for ps in plan.prog) + max(ps["n_levels"] for ps in plan.prog) \
@@ -205,7 +213,7 @@ class CircuitTables:
         return (plan.n_rows * PC + plan.stage_rows * (PC + 2)) * 8 + 64 * PC + 4 * aux
 
     def subdomain_plan(self, d, NG):
-        key = (d, NG)
+        key = (d, NG, os.environ.get("JJ_TT_MAX", ""))
         if key not in self._subdomain:
             plan = subdomain_plan(self.factor, self.junc_face, d, NG)
             face_tables(plan, self.face_ptr, self.face_junc, self.face_sign, self.junc_sign, self.c0)
@@ -240,92 +248,6 @@ class CircuitTables:
                 return d, NG
         return None
 
-    # ------------------------------------------------------------------ resident engine plan
-    SMEM_LIMIT = 227 * 1024
-
-    def resident_smem_bytes(self, plan, Wt):
-        aux = max(2 * (ps["n_levels"] * ps["n_warps"] + 1) + 6 + 2 * len(ps["thdr"]) for ps in plan.prog) + 4 * plan.ops.shape[1] + 140
-        return ((plan.n_rows + plan.allreduce_rows + 8 * plan.C) * Wt + plan.stage_rows * (Wt + 2)) * 8 + 4 * aux
-
-    def choose_resident(self, W):
-        """Pick (cluster size, problems per tile) for the resident engine, or None if the right-hand sides
-        do not fit in a cluster's shared memory. JJ_RESIDENT="C,Wt" overrides."""
-        if self.factor is None:
-            return None
-        env = os.environ.get("JJ_RESIDENT")
-        if env:
-            C, Wt = (int(v) for v in env.split(","))
-            return C, Wt
-        for limit in (110 * 1024, self.SMEM_LIMIT):
-            for C in (1, 2, 4, 8):
-                try:
-                    plan = self.resident_plan(C)
-                except ValueError:
-                    continue
-                if self.resident_smem_bytes(plan, 8) <= limit:
-                    return C, 8
-        return None
-
-    def resident_plan(self, C):
-        if C not in self._resident:
-            self._resident[C] = _ResidentTables(self, resident_plan(self.factor, C))
-        return self._resident[C].plan
-
-    def resident_tables(self, C):
-        self.resident_plan(C)
-        return self._resident[C]
-
-
-class _ResidentTables:
-    """Junction / face tables of a resident plan (device junction order, per-rank face lists)."""
-
-    def __init__(self, tab, plan):
-        self.plan = plan
-        C, Nj, Nf = plan.C, tab.Nj, tab.Nf
-        smem = np.stack(plan.smem_index)                      # (C, Nf)
-        jf = tab.junc_face.astype(np.int64)                   # permuted faces, -1 none
-        has = jf >= 0
-        rr = np.where(has, plan.row_rank[np.maximum(jf, 0)], -1)          # rank of each face, -1 replicated / none
-        co = np.where(has, plan.col_owner[np.maximum(jf, 0)], -1)
-        owner = np.where(rr[:, 0] >= 0, rr[:, 0], rr[:, 1])
-        both = (rr[:, 0] >= 0) & (rr[:, 1] >= 0)
-        assert np.all(rr[both, 0] == rr[both, 1]), "faces sharing a junction ended up in different subtrees"
-        shared_only = owner < 0
-        fallback = np.where(co[:, 0] >= 0, co[:, 0], np.where(co[:, 1] >= 0, co[:, 1], np.arange(Nj) % C))
-        owner = np.where(shared_only, fallback, owner).astype(np.int64)
-        order = np.lexsort((np.arange(Nj), owner))            # device junction order
-        self.junc_orig = order.astype(np.int32)
-        jdev = np.empty(Nj, dtype=np.int64)
-        jdev[order] = np.arange(Nj)
-        self.junc_ptr = np.searchsorted(owner[order], np.arange(C + 1)).astype(np.int32)
-        rows = np.where(has, smem[owner[:, None], np.maximum(jf, 0)], -1)
-        self.junc_row = np.ascontiguousarray(rows[order].astype(np.int32))
-        self.junc_sign = np.ascontiguousarray(tab.junc_sign[order].astype(np.int8))
-        # per-rank face lists: entry (g, j) goes to the rank owning j, at that rank's row of face g
-        g_of = np.repeat(np.arange(Nf), np.diff(tab.face_ptr))
-        j_of = tab.face_junc.astype(np.int64)
-        r_of = owner[j_of]
-        row_of = smem[r_of, g_of]
-        assert np.all(row_of >= 0)
-        key = np.lexsort((j_of, row_of, r_of))
-        n_rows = plan.n_rows
-        flat = r_of[key] * n_rows + row_of[key]
-        counts = np.bincount(flat, minlength=C * n_rows)
-        ptr_all = np.concatenate(([0], np.cumsum(counts)))
-        fp = np.zeros((C, n_rows + 1), dtype=np.int32)
-        for r in range(C):
-            fp[r] = ptr_all[r * n_rows: (r + 1) * n_rows + 1]
-        self.face_ptr = fp
-        self.face_junc = jdev[j_of[key]].astype(np.int32)
-        self.face_sign = tab.face_sign[key].astype(np.int8)
-        # which rank adds the flux term of a face / is authoritative for its row
-        fidx = np.full((C, n_rows), -1, dtype=np.int32)
-        for r in range(C):
-            mine = (plan.row_rank == r) | ((plan.row_rank < 0) & (plan.col_owner == r))
-            g = np.flatnonzero(mine)
-            fidx[r, smem[r, g]] = g
-        self.face_fidx = fidx
-
 
 _ROWS_FIT = 560               # local rows of a subdomain that still fit in 227 KB at 32 problems with a ~15 % halo
 _ROWS_PER_SUBDOMAIN = 450     # target when a circuit has to be cut finer than one subdomain per (SM, chunk) anyway
@@ -348,11 +270,10 @@ def subdomain_layout(Nf, W, n_sm=148):
         pass                                        # one item per block and the subdomains fit (cfg2: 545 rows each)
     elif need > n_parts and need <= n_sm:
         n_parts = n_sm // max(1, n_sm // need)
-    elif need > 4 * n_sm:
-        pass                                        # the dense top cannot follow (n_top grows like sqrt(parts * Nf)): streaming engine
     elif need > n_sm:
         half = max(1, n_sm // 2)
-        n_parts = -(-need // half) * half           # the dense top limits how far this goes (subdomain_plan raises)
+        n_parts = -(-need // half) * half           # cfg5: 2 220 subdomains; the separators above them (10^5 rows) are
+                                                    # swept by the upper program, only the last tree levels are dense
     return NG, chunks, n_parts
 
 
@@ -374,7 +295,7 @@ def _tables_for(circuit, dt, n_parts=None):
     L = circuit._L()
     key = (id(circuit), float(dt), hash(np.asarray(circuit._R()).tobytes()), hash(np.asarray(circuit._C()).tobytes()),
            hash(np.asarray(circuit._Ic()).tobytes()), hash(L.data.tobytes()) ^ hash(L.indices.tobytes()),
-           os.environ.get("JJ_LEAF_SIZE", ""), n_parts)
+           os.environ.get("JJ_LEAF_SIZE", ""), os.environ.get("JJ_TT_MAX", ""), n_parts)
     with _engine_lock:
         hit = _tables_cache.get(key)
         if hit is not None and hit[0]() is circuit:       # id() values are reused after garbage collection
@@ -423,7 +344,7 @@ class DeviceEngine:
             raise (ValueError if rc == -2 else RuntimeError)(f"libjjstep error {rc}: {msg}")
 
     # --- setup -----------------------------------------------------------------------------
-    def set_circuit(self, tab: CircuitTables, cpr):
+    def set_circuit(self, tab: CircuitTables, cpr, with_program=True):
         a, b = harmonics(cpr)
         a, b = _lib.c_f64(a), _lib.c_f64(b)
         c = _lib.JJCircuit()
@@ -437,11 +358,19 @@ class DeviceEngine:
         c.cpr_harmonics = len(a) - 1
         c.cpr_a, c.cpr_b = _lib.f64(a), _lib.f64(b)
         self._ck(self.lib.jj_set_circuit(self.h, C.byref(c)))
-        sweeps = [self._sweep_struct(tab.program.sweeps[name] if tab.program is not None else _empty_sweep())
+        self.tab = tab
+        self.has_streaming_program = False
+        self.set_streaming_program(with_program)
+
+    def set_streaming_program(self, with_program=True):
+        """Upload the solve program of the streaming engine (with_program=False: empty sweeps, for engines that only
+        ever run the subdomain kernel; the program of a large circuit takes long to build and is rarely needed)."""
+        tab = self.tab
+        prog = tab.program if (with_program and tab.factor is not None) else None
+        sweeps = [self._sweep_struct(prog.sweeps[name] if prog is not None else _empty_sweep())
                   for name in ("fwd", "bwd")]
         self._ck(self.lib.jj_set_solver(self.h, C.byref(sweeps[0]), C.byref(sweeps[1])))
-        self.tab = tab
-        self.resident_config = None
+        self.has_streaming_program = prog is not None or tab.factor is None
 
     @staticmethod
     def _sweep_struct(sw):
@@ -459,40 +388,14 @@ class DeviceEngine:
         s.tile_stage_off = _lib.i32(sw["tile_stage_off"])
         return s
 
-    def set_resident(self, Ccl, Wt):
-        """Upload the resident-engine plan for cluster size Ccl and Wt problems per tile."""
-        rt = self.tab.resident_tables(Ccl)
-        plan = rt.plan
-        p = _lib.JJResidentPlan()
-        p.C, p.tile_problems, p.n_rows = Ccl, Wt, plan.n_rows
-        p.stage_rows, p.allreduce_rows = plan.stage_rows, plan.allreduce_rows
-        ops = np.ascontiguousarray(plan.ops, dtype=np.int32)
-        p.n_ops, p.n_fwd_ops, p.ops = ops.shape[1], plan.n_fwd_ops, _lib.i32(ops)
-        def rank_stream(ps):
-            r = _lib.JJRankStream()
-            r.n_levels, r.n_warps, r.n_tiles = ps["n_levels"], ps["n_warps"], len(ps["thdr"])
-            r.wt_ptr, r.ws_ptr = _lib.i32(ps["wt_ptr"]), _lib.i32(ps["ws_ptr"])
-            ps["_thdr_c"] = np.ascontiguousarray(ps["thdr"], dtype=np.int32)
-            r.thdr = _lib.i32(ps["_thdr_c"])
-            r.n_steps = ps["n_steps"]
-            r.stream = ps["stream"].ctypes.data_as(C.POINTER(C.c_uint8))
-            return r
-        progs = (_lib.JJRankStream * Ccl)(*[rank_stream(ps) for ps in plan.prog])
-        p.prog = progs
-        fp = np.ascontiguousarray(rt.face_ptr); ff = np.ascontiguousarray(rt.face_fidx)
-        p.junc_ptr, p.junc_orig = _lib.i32(rt.junc_ptr), _lib.i32(rt.junc_orig)
-        p.junc_row, p.junc_sign = _lib.i32(rt.junc_row), _lib.i8(rt.junc_sign)
-        p.face_ptr, p.face_junc, p.face_sign, p.face_fidx = _lib.i32(fp), _lib.i32(rt.face_junc), _lib.i8(rt.face_sign), _lib.i32(ff)
-        self._ck(self.lib.jj_set_resident_plan(self.h, C.byref(p)))
-        self.resident_config = (Ccl, Wt)
-
     def set_subdomain(self, d, NG):
         """Upload the subdomain-engine plan for cut depth d (None: the n_parts subtrees of the ordering) and NG
         groups of 8 problems per chunk."""
         plan = self.tab.subdomain_plan(d, NG)
         p = _lib.JJSubdomainPlan()
         p.P, p.NG, p.n_rows, p.n_loc_max, p.stage_rows = plan.P, plan.NG, plan.n_rows, plan.n_loc_max, plan.stage_rows
-        p.n_top, p.n_top_pad, p.n_slots = plan.n_top, plan.n_top_pad, plan.n_slots
+        p.n_top, p.n_up_pad, p.n_slots = plan.n_top, plan.n_up_pad, plan.n_slots
+        p.tt0, p.n_tt, p.n_tt_pad = plan.tt0, plan.n_tt, plan.n_tt_pad
         keep = []
 
         def a32(x):
@@ -511,6 +414,15 @@ class DeviceEngine:
         p.n_loc, p.n_halo, p.hptr, p.halo_top = a32(plan.n_loc), a32(plan.n_halo), a32(plan.hptr), a32(plan.halo_top)
         p.tptr, p.tslot, p.top_face = a32(plan.tptr), a32(plan.tslot), a32(plan.top_rows)
         p.Sinv_packed = a64f(plan.Sinv_packed)
+        up = plan.upper
+        p.up_RB, p.up_KB, p.n_up_fwd, p.n_up_bwd = up["RB"], up["KB"], up["n_fwd"], up["n_bwd"]
+        p.n_up_tasks = len(up["task"])
+        p.up_phase_ptr, p.up_task = a32(up["phase_ptr"]), a32(up["task"])
+        aoff = np.ascontiguousarray(up["task_aoff"] if len(up["task_aoff"]) else np.zeros(1), dtype=np.int64)
+        keep.append(aoff)
+        p.up_task_aoff = _lib.i64(aoff)
+        p.n_up_cols, p.up_cols = up["cols"].size, a32(up["cols"])
+        p.n_up_vals, p.up_A = up["A"].size, a64f(up["A"])
 
         def sub_prog(ps, n_bwd):
             r = _lib.JJSubProgram()
@@ -536,14 +448,6 @@ class DeviceEngine:
         bp = _lib.c_f64(np.asarray(b)[self.tab.perm])
         Jp = np.empty_like(bp)
         self._ck(self.lib.jj_debug_subdomain_solve(self.h, _lib.f64(bp), _lib.f64(Jp)))
-        J = np.empty_like(Jp)
-        J[self.tab.perm] = Jp
-        return J
-
-    def debug_resident_solve(self, b):
-        bp = _lib.c_f64(np.asarray(b)[self.tab.perm])
-        Jp = np.empty_like(bp)
-        self._ck(self.lib.jj_debug_resident_solve(self.h, _lib.f64(bp), _lib.f64(Jp)))
         J = np.empty_like(Jp)
         J[self.tab.perm] = Jp
         return J
@@ -694,6 +598,20 @@ def _classify_all(problem, tab):
     return specs
 
 
+def resolve_noise_seed(problem, noisy=True):
+    """Philox seed of one compute() call. An explicit ``noise_seed`` is used as it is (reproducible runs); without
+    one every call draws a fresh 64-bit seed from numpy's global generator - like the reference, whose draws advance
+    ``np.random`` from call to call (time_evolution.py:533-538), so repeated runs, runs continued in segments and
+    annealing intervals see independent noise, and ``np.random.seed`` still makes a script reproducible. Nothing is
+    drawn when the temperature is zero (the reference draws nothing then either)."""
+    seed = getattr(problem, "noise_seed", None)
+    if seed is not None:
+        return int(seed)
+    if not noisy:
+        return 0
+    return int(np.random.randint(0, np.iinfo(np.int64).max, dtype=np.int64))
+
+
 def _chunk_length(specs, tab, W, Nt, has_replay):
     K = Nt
     for name, s in specs.items():
@@ -714,35 +632,37 @@ _engine_cache = {}           # device -> [(key, DeviceEngine)]: circuit, solver 
 _ENGINES_PER_DEVICE = 2
 
 
-def _engine_for(tab, cpr, dev, W, engine_kind):
-    """A DeviceEngine with the circuit tables (and the plan of the shared-memory engine that applies) uploaded.
-    Repeated compute() calls on the same circuit (annealing loops, parameter sweeps) reuse it: only the problem
-    state is re-created."""
+def _engine_for(tab, cpr, dev, W, engine_kind, dense_inputs=False):
+    """(key, DeviceEngine, engine kind to run) with the circuit tables and the plan of the engine that applies
+    uploaded. Repeated compute() calls on the same circuit (annealing loops, parameter sweeps) reuse it: only the
+    problem state is re-created. The subdomain engine runs whenever a plan fits and no input is a dense per-step
+    table; the streaming engine (and its solve program, built on first use) covers the rest."""
     _lib.load()              # fails loudly when the CUDA library is missing, cached engine or not
     a, b = harmonics(cpr)
-    sub_cfg = res_cfg = None
-    if engine_kind in (_lib.JJ_ENGINE_AUTO, _lib.JJ_ENGINE_SUBDOMAIN):
+    sub_cfg = None
+    if engine_kind in (_lib.JJ_ENGINE_AUTO, _lib.JJ_ENGINE_SUBDOMAIN) and not dense_inputs:
         sub_cfg = tab.choose_subdomain(W)
-        if sub_cfg is None and engine_kind == _lib.JJ_ENGINE_SUBDOMAIN:
-            raise ValueError("subdomain engine requested but no plan fits in shared memory")
-    if engine_kind == _lib.JJ_ENGINE_RESIDENT or (engine_kind == _lib.JJ_ENGINE_AUTO and sub_cfg is None):
-        res_cfg = tab.choose_resident(W)
-        if res_cfg is None and engine_kind == _lib.JJ_ENGINE_RESIDENT:
-            raise ValueError("resident engine requested but the circuit does not fit in shared memory")
-    key = (id(tab), tuple(a), tuple(b), sub_cfg, res_cfg)
+    if sub_cfg is None and engine_kind == _lib.JJ_ENGINE_SUBDOMAIN:
+        raise ValueError("subdomain engine requested but " + ("an input is a dense per-step table" if dense_inputs
+                                                              else "no plan fits in shared memory"))
+    run_kind = _lib.JJ_ENGINE_SUBDOMAIN if sub_cfg is not None else _lib.JJ_ENGINE_STREAMING
+    key = (id(tab), tuple(a), tuple(b), sub_cfg)
+    eng = None
     with _engine_lock:
         entries = _engine_cache.setdefault(dev, [])
         for i, (k, e) in enumerate(entries):
             if k == key:
                 del entries[i]
-                return key, e
-    eng = DeviceEngine(dev)
-    eng.set_circuit(tab, cpr)
-    if sub_cfg is not None:
-        eng.set_subdomain(*sub_cfg)
-    if res_cfg is not None:
-        eng.set_resident(*res_cfg)
-    return key, eng
+                eng = e
+                break
+    if eng is None:
+        eng = DeviceEngine(dev)
+        eng.set_circuit(tab, cpr, with_program=sub_cfg is None)
+        if sub_cfg is not None:
+            eng.set_subdomain(*sub_cfg)
+    elif run_kind == _lib.JJ_ENGINE_STREAMING and not eng.has_streaming_program:
+        eng.set_streaming_program(True)
+    return key, eng, run_kind
 
 
 def _release_engine(dev, key, eng, ok):
@@ -782,15 +702,15 @@ def _setup_sources(eng, specs, sh, tab):
                 eng.upload_source(which, 0, _dense_for_device(name, sh.dense(name, 0, 1), tab))
 
 
-def _run_shard(problem, tab, specs, dev, w0, w1, th_mask, I_mask, th_host, I_host, engine_kind, stats_out):
+def _run_shard(problem, tab, specs, dev, w0, w1, th_mask, I_mask, th_host, I_host, engine_kind, stats_out, seed=0):
     """Integrate problems [w0, w1) on one device and write stored planes into th_host / I_host
     (plane-major (n_planes + 2, Nj, W) arrays, planes 0 and 1 are the initial conditions)."""
     Nj, Nf, Nt, dt = tab.Nj, tab.Nf, problem._Nt(), problem._dt()
     W = w1 - w0
-    key, eng = _engine_for(tab, problem.current_phase_relation, dev, W, engine_kind)
+    dense = any(s.kind == DENSE for s in specs.values())
+    key, eng, engine_kind = _engine_for(tab, problem.current_phase_relation, dev, W, engine_kind, dense)
     ok = False
     try:
-        seed = problem.noise_seed if getattr(problem, "noise_seed", None) is not None else 0
         eng.set_problem(W, dt, seed=seed, problem_offset=w0, engine=engine_kind)
         eng.set_state(problem.config_at_minus_1[:, w0:w1], problem.config_at_minus_2[:, w0:w1])
         sh = _ShardInputs(specs, w0, w1)
@@ -860,7 +780,7 @@ def _dense_for_device(name, table, tab):
 
 
 def device_time_evolution_core(problem, th_store_mask, I_store_mask, engine=None, shard=None, device=None,
-                               initial_planes=True):
+                               initial_planes=True, noise_seed=None):
     """
     Device replacement of time_evolution_core (reference: time_evolution.py:461-582), stencil width 3.
     Returns th_out, I_out of shape (Nj, W, n_stored + 2).
@@ -868,7 +788,7 @@ def device_time_evolution_core(problem, th_store_mask, I_store_mask, engine=None
     supercurrents) are left unwritten; time_evolution() asks for that when it is going to drop them unread
     (no voltage requested), which saves two passes over (Nj, W) arrays per plane on the host.
     shard=(w0, w1), device=d: integrate only problems [w0, w1) on GPU d and return (Nj, w1 - w0, .) arrays
-    (used by distributed.compute_sharded, one process per GPU).
+    (used by distributed.compute_sharded, one process per GPU, which also passes the job-wide noise_seed).
     """
     if getattr(problem, "stencil_width", 3) != 3:
         raise NotImplementedError("only stencil_width=3 is supported")
@@ -907,10 +827,10 @@ def device_time_evolution_core(problem, th_store_mask, I_store_mask, engine=None
         I_host[:2] = 0.0
     if engine is None:
         engine = {"auto": _lib.JJ_ENGINE_AUTO, "streaming": _lib.JJ_ENGINE_STREAMING,
-                  "resident": _lib.JJ_ENGINE_RESIDENT,
                   "subdomain": _lib.JJ_ENGINE_SUBDOMAIN}[os.environ.get("JJ_ENGINE", "auto")]
     bounds = shard_bounds(W, len(devices))
     stats = {}
+    seed = resolve_noise_seed(problem, specs["T"].kind != ZERO) if noise_seed is None else int(noise_seed)
     jobs = [(dev, bounds[k], bounds[k + 1]) for k, dev in enumerate(devices) if bounds[k + 1] > bounds[k]]
     if shard is not None:
         jobs = [(devices[0] if device is None else device, shard[0], shard[1])] if shard[1] > shard[0] else []
@@ -918,13 +838,13 @@ def device_time_evolution_core(problem, th_store_mask, I_store_mask, engine=None
         pass
     elif len(jobs) == 1:
         dev, w0, w1 = jobs[0]
-        _run_shard(problem, tab, specs, dev, w0, w1, th_mask, I_mask, th_host, I_host, engine, stats)
+        _run_shard(problem, tab, specs, dev, w0, w1, th_mask, I_mask, th_host, I_host, engine, stats, seed)
     else:
         errors = []
 
         def work(dev, w0, w1):
             try:
-                _run_shard(problem, tab, specs, dev, w0, w1, th_mask, I_mask, th_host, I_host, engine, stats)
+                _run_shard(problem, tab, specs, dev, w0, w1, th_mask, I_mask, th_host, I_host, engine, stats, seed)
             except Exception as e:      # surfaced after join
                 errors.append(e)
         threads = [threading.Thread(target=work, args=j) for j in jobs]
@@ -945,7 +865,6 @@ def device_time_evolution_core(problem, th_store_mask, I_store_mask, engine=None
 def _engine_kind(engine):
     if engine is None:
         engine = {"auto": _lib.JJ_ENGINE_AUTO, "streaming": _lib.JJ_ENGINE_STREAMING,
-                  "resident": _lib.JJ_ENGINE_RESIDENT,
                   "subdomain": _lib.JJ_ENGINE_SUBDOMAIN}[os.environ.get("JJ_ENGINE", "auto")]
     return engine
 
@@ -969,10 +888,11 @@ def _anneal_shard(problem, tab, tab2, specs, dev, w0, w1, ann, adjust, out, engi
     planes = np.arange(steps, dtype=np.int64)
     total_ms = 0.0
     launches = 0
-    key, eng = _engine_for(tab, cpr, dev, W, engine_kind)
+    dense = any(s.kind == DENSE for s in specs.values())
+    key, eng, run_kind = _engine_for(tab, cpr, dev, W, engine_kind, dense)
     ok = False
     try:
-        eng.set_problem(W, dt, seed=seed, problem_offset=w0, engine=engine_kind)     # theta(-1) = theta(-2) = 0
+        eng.set_problem(W, dt, seed=seed, problem_offset=w0, engine=run_kind)     # theta(-1) = theta(-2) = 0
         _setup_sources(eng, specs, sh, tab)
         eng.set_source(_lib.JJ_SRC_T, _lib.JJ_KIND_RANK1, True, np.sqrt(2.0 * tab.Rv))
         eng.alloc_outputs(steps, 0)
@@ -997,10 +917,10 @@ def _anneal_shard(problem, tab, tab2, specs, dev, w0, w1, ann, adjust, out, engi
     finally:
         _release_engine(dev, key, eng, ok)
     # closing runs at T = 0 with half the time step (reference: time_evolution.py:1176-1183)
-    key, eng = _engine_for(tab2, cpr, dev, W, engine_kind)
+    key, eng, run_kind = _engine_for(tab2, cpr, dev, W, engine_kind, dense)
     ok = False
     try:
-        eng.set_problem(W, dt / 2, seed=seed, problem_offset=w0, engine=engine_kind)
+        eng.set_problem(W, dt / 2, seed=seed, problem_offset=w0, engine=run_kind)
         eng.set_state(th, th)
         _setup_sources(eng, specs, sh, tab2)
         eng.set_source(_lib.JJ_SRC_T, _lib.JJ_KIND_ZERO, True)
@@ -1052,7 +972,7 @@ def device_annealing(problem, T0, adjust, interval_count, final_runs=5, engine=N
     out = dict(T=np.array(T0, dtype=np.double).reshape(W).copy(), profiles=np.zeros((interval_count, W)),
                theta=np.zeros((tab.Nj, W)), n=np.zeros((tab.Nf, W), dtype=int))
     ann = dict(dt=dt, interval_count=int(interval_count), interval_steps=problem._Nt(), final_runs=int(final_runs),
-               seed=problem.noise_seed if getattr(problem, "noise_seed", None) is not None else 0,
+               seed=resolve_noise_seed(problem),
                noise_replay=getattr(problem, "noise_replay", None))
     bounds = shard_bounds(W, len(devices))
     jobs = [(dev, bounds[k], bounds[k + 1]) for k, dev in enumerate(devices) if bounds[k + 1] > bounds[k]]

@@ -22,12 +22,9 @@ Here (all on the host, once per problem):
      + sum_c V[i, c] * src[cols[c]]. Values are stored in the order a warp consumes them
      ([step][lane], lane = i * lanes_per_row + c % lanes_per_row), so device loads are coalesced.
 
-Two packings of the same tiles exist:
-  * ``streaming_program``  - rows are permuted face indices (streaming engine, any size);
-  * ``resident_plan``      - the elimination tree is cut at depth log2(C); each of the C thread blocks
-    of a cluster owns one subtree (its rows live in that block's shared memory), the separators above
-    the cut are replicated in every block and combined with an all-reduce over distributed shared
-    memory in the forward sweep (resident engine).
+``streaming_program`` packs these tiles with permuted face indices as rows (streaming engine, any size, any
+input form); the fast path (subdomain engine) has its own plan builder in subdomain.py, which reads the
+factor ``Lc`` and the dissection tree kept in ``Factor``.
 """
 import numpy as np
 import scipy.linalg
@@ -36,13 +33,12 @@ import scipy.sparse.linalg
 
 from .ordering import nested_dissection
 
-__all__ = ["Factor", "factorize", "streaming_program", "resident_plan", "system_matrix", "apply_program_host",
+__all__ = ["Factor", "factorize", "streaming_program", "system_matrix", "apply_program_host",
            "build_solve_program"]
 
 TILE_SELF = 1        # add src[row] to the dot product (phase a)
 TILE_STAGED = 2      # block spans several tiles: results must not overwrite src before the level is complete
 
-OP_LEVEL, OP_ALLREDUCE = 0, 1
 
 
 def system_matrix(A, Lmat, Rv, Cv):
@@ -104,11 +100,7 @@ def factorize(S, cx, cy, leaf_size=8, n_parts=None, part_weights=None):
     F.nnz_L = int(Lc.nnz)
     F.Lc = Lc
     nb = F.nb
-    F.dinv = []
-    for b in range(nb):
-        r0, r1 = bptr[b], bptr[b + 1]
-        D = Lc[r0:r1, r0:r1].toarray()
-        F.dinv.append(scipy.linalg.solve_triangular(D, np.eye(r1 - r0), lower=True))
+    F.dinv = None              # inverses of the diagonal blocks: only the streaming program needs them (block_inverses)
     blk_of = np.repeat(np.arange(nb), np.diff(bptr))
     coo = scipy.sparse.tril(Lc, k=-1).tocoo()
     keep = blk_of[coo.row] != blk_of[coo.col]
@@ -117,6 +109,17 @@ def factorize(S, cx, cy, leaf_size=8, n_parts=None, part_weights=None):
     F.LoffT = F.Loff.T.tocsr()
     F.LoffT.sort_indices()
     return F
+
+
+def block_inverses(F):
+    """Explicit inverses of the diagonal blocks of the factor (computed on first use)."""
+    if F.dinv is None:
+        F.dinv = []
+        for b in range(F.nb):
+            r0, r1 = F.bptr[b], F.bptr[b + 1]
+            D = F.Lc[r0:r1, r0:r1].toarray()
+            F.dinv.append(scipy.linalg.solve_triangular(D, np.eye(r1 - r0), lower=True))
+    return F.dinv
 
 
 # ----------------------------------------------------------------------------------------------
@@ -231,24 +234,9 @@ def pack_levels(levels, row_map=None, col_map=None):
                 stage_rows=int(stage_rows), nnz=int(nnz))
 
 
-RES_WARPS = 16          # warps per thread block of the resident kernel
-RES_WT = 8              # problems per tile of the resident engine (= N of the m8n8k4 FP64 MMA)
+RES_WARPS = 16          # warps per thread block of the subdomain kernel
 STEP_BYTES = 320        # one stream step: 32 float64 values + 32 uint16 shared-memory element codes
 CHAIN_ROWS = 32         # diagonal blocks up to this many rows are updated in place by a single warp
-
-
-def a_rows(F, blocks, M, col_mask=None):
-    """Phase-a tasks of the given blocks: per block (first permuted row, CSR rows of M restricted to col_mask)."""
-    out = []
-    for b in blocks:
-        r0, r1 = int(F.bptr[b]), int(F.bptr[b + 1])
-        out.append((r0, r1, M, col_mask))
-    return out
-
-
-def b_blocks(F, blocks, transpose):
-    """Phase-b block tasks: (first permuted row, dense triangular matrix to apply to the block's own rows)."""
-    return [(int(F.bptr[b]), F.dinv[b].T if transpose else F.dinv[b]) for b in blocks]
 
 
 def _lpt(costs, n_warps):
@@ -260,154 +248,6 @@ def _lpt(costs, n_warps):
         assign[w].append(int(i))
         load[w] += costs[i]
     return assign
-
-
-def _mma_tiles_a(items):
-    """8-row tiles of phase a: out = src[row] - M[row, cols] src[cols]; one unit per tile."""
-    units = []
-    for (r0, r1, M, col_mask) in items:
-        for t0 in range(r0, r1, 8):
-            t1 = min(r1, t0 + 8)
-            sub = M[t0:t1]
-            cols = np.unique(sub.indices)
-            if col_mask is not None:
-                cols = cols[col_mask[cols]]
-            if cols.size == 0:
-                continue
-            units.append([dict(row0=t0, V=-sub[:, cols].toarray(), cols=cols.astype(np.int64), flags=TILE_SELF)])
-    return units
-
-
-def _mma_tiles_b(blocks, transpose):
-    """8-row tiles of phase b. A block of at most CHAIN_ROWS rows is one unit: its tiles are processed by one
-    warp in an order that makes the in-place update safe; larger blocks write through the staging buffer."""
-    units = []
-    for (r0, D) in blocks:
-        k = D.shape[0]
-        starts = list(range(0, k, 8))
-        if not transpose:
-            starts.reverse()          # lower triangular: a row group reads the rows above it -> last group first
-        tiles = []
-        for t0 in starts:
-            t1 = min(k, t0 + 8)
-            c0, c1 = (t0, k) if transpose else (0, t1)
-            tiles.append(dict(row0=r0 + t0, V=D[t0:t1, c0:c1], cols=np.arange(r0 + c0, r0 + c1, dtype=np.int64), flags=0))
-        if k <= CHAIN_ROWS:
-            units.append(tiles)
-        else:
-            for t in tiles:
-                t["flags"] = TILE_STAGED
-                units.append([t])
-    return units
-
-
-def smem_code(col):
-    """Element offset (in float64) of problem n = 0..7 of shared-memory row `col` in the swizzled layout:
-    16-byte chunk c of row r lives at chunk position c ^ ((r >> 1) & 3)."""
-    col = np.asarray(col, dtype=np.int64)[..., None]
-    n = np.arange(8)
-    return col * 8 + (((n >> 1) ^ ((col >> 1) & 3)) << 1) + (n & 1)
-
-
-def pack_mma_streams(level_specs, row_map, col_map, n_warps=RES_WARPS):
-    """
-    Resident-engine packing for the FP64 tensor-core sweep. level_specs: list of (kind 'a'|'b', items,
-    transpose) per level. A tile is 8 output rows x K columns (K a multiple of 4) of a dense matrix V; the
-    device computes C(8 rows x 8 problems) += V(8x4) . S(4x8) per stream step with mma.m8n8k4, S gathered from
-    the shared-memory vector. Every (level, warp) pair owns a contiguous stream of 320-byte steps:
-      32 float64: lane = row*4 + kk holds V[row, 4*step + kk]          (the A fragment)
-      32 uint16 : lane = n*4 + kk holds the element code of src[col(4*step + kk)], problem n   (the B fragment)
-    Header (two int32): row0 | (nrows-1) << 16 | flags << 19 ;  nsteps | stage_off << 16.
-    """
-    n_levels = len(level_specs)
-    wt_ptr = np.zeros(n_levels * n_warps + 1, dtype=np.int32)
-    ws_ptr = np.zeros(n_levels * n_warps + 1, dtype=np.int32)
-    hdr, chunks = [], []
-    n_steps = stage_rows = n_vals = 0
-    staged_rows = []
-    lane = np.arange(32)
-    for li, (kind, items, transpose) in enumerate(level_specs):
-        units = (_mma_tiles_a(items) if kind == "a" else _mma_tiles_b(items, transpose)) if items else []
-        costs = [sum((t["V"].shape[1] + 3) // 4 + 5 for t in u) for u in units]
-        assign = _lpt(costs, n_warps)
-        staged = 0
-        for u in units:
-            for t in u:
-                if t["flags"] & TILE_STAGED:
-                    t["stage_off"] = staged
-                    staged += t["V"].shape[0]
-        stage_rows = max(stage_rows, staged)
-        staged_rows.append(int(staged))
-        for w in range(n_warps):
-            for ui in assign[w]:
-                for t in units[ui]:
-                    V = t["V"]
-                    nr, nc = V.shape
-                    st = (nc + 3) // 4
-                    Vp = np.zeros((8, st * 4))
-                    Vp[:nr, :nc] = V
-                    cm = col_map[t["cols"]]
-                    assert np.all(cm >= 0) and np.all(cm < 8192)
-                    cp = np.full(st * 4, cm[-1], dtype=np.int64)
-                    cp[:nc] = cm
-                    vals = Vp.reshape(8, st, 4).transpose(1, 0, 2).reshape(st, 32)       # lane = row*4 + kk
-                    codes = smem_code(cp.reshape(st, 4))                                  # (st, 4, 8): [kk][n]
-                    codes = codes.transpose(0, 2, 1).reshape(st, 32).astype(np.uint16)    # lane = n*4 + kk
-                    rec = np.zeros((st, STEP_BYTES), dtype=np.uint8)
-                    rec[:, :256] = np.ascontiguousarray(vals).view(np.uint8).reshape(st, 256)
-                    rec[:, 256:] = np.ascontiguousarray(codes).view(np.uint8).reshape(st, 64)
-                    chunks.append(rec)
-                    row = int(row_map[t["row0"]])
-                    assert 0 <= row < 65536 and st < 65536
-                    hdr.append((row | ((nr - 1) << 16) | (t["flags"] << 19), st | (t.get("stage_off", 0) << 16)))
-                    n_steps += st
-                    n_vals += nr * nc
-            wt_ptr[li * n_warps + w + 1] = len(hdr)
-            ws_ptr[li * n_warps + w + 1] = n_steps
-    stream = np.concatenate(chunks).ravel() if chunks else np.zeros(0, dtype=np.uint8)
-    return dict(n_levels=n_levels, n_warps=n_warps, wt_ptr=wt_ptr, ws_ptr=ws_ptr,
-                thdr=np.asarray(hdr, dtype=np.int32).reshape(-1, 2), stream=stream, n_steps=n_steps,
-                stage_rows=int(stage_rows), vals=int(n_vals), staged_rows=staged_rows)
-
-
-def _run_stream_level(ps, v, level):
-    """Host interpreter of one level of an MMA stream program (mirrors the device kernel, including the
-    sequential in-place semantics of the tiles of one warp). v: (rows, 8) float64."""
-    assert v.ndim == 2 and v.shape[1] == 8
-    nw = ps["n_warps"]
-    rec = ps["stream"].reshape(-1, STEP_BYTES)
-    flat = v.reshape(-1)
-    # swizzled view of v: the codes address the physical layout, so build it once per tile
-    def physical(vv):
-        rows = np.arange(vv.shape[0])
-        ph = np.empty_like(vv).reshape(vv.shape[0], 4, 2)
-        lg = vv.reshape(vv.shape[0], 4, 2)
-        for c in range(4):
-            ph[rows, c ^ ((rows >> 1) & 3)] = lg[rows, c]
-        return ph.reshape(-1)
-    staged = []
-    for w in range(nw):
-        idx = level * nw + w
-        s = ps["ws_ptr"][idx]
-        for t in range(ps["wt_ptr"][idx], ps["wt_ptr"][idx + 1]):
-            h0, h1 = int(ps["thdr"][t, 0]), int(ps["thdr"][t, 1])
-            row0, nr, fl = h0 & 0xffff, ((h0 >> 16) & 7) + 1, (h0 >> 19) & 3
-            st = h1 & 0xffff
-            vals = rec[s:s + st, :256].copy().view(np.float64).reshape(st, 8, 4)          # [step][row][kk]
-            codes = rec[s:s + st, 256:].copy().view(np.uint16).reshape(st, 8, 4).astype(np.int64)   # [step][n][kk]
-            s += st
-            ph = physical(v)
-            S = ph[codes]                                                                  # [step][n][kk]
-            acc = np.einsum("srk,snk->rn", vals, S)[:nr]
-            if fl & TILE_SELF:
-                acc = acc + v[row0:row0 + nr]
-            if fl & TILE_STAGED:
-                staged.append((row0, nr, acc))
-            else:
-                v[row0:row0 + nr] = acc            # in place, in the warp's program order
-        assert s == ps["ws_ptr"][idx + 1]
-    for (row0, nr, acc) in staged:
-        v[row0:row0 + nr] = acc
 
 
 class SolveProgram:
@@ -424,6 +264,7 @@ class SolveProgram:
 def streaming_program(F):
     prog = SolveProgram()
     prog.n, prog.perm, prog.factor = F.n, F.perm.astype(np.int32), F
+    block_inverses(F)
     H = F.H
     by_height = [np.flatnonzero(F.height == h) for h in range(H + 1)]
     rows_at = [int(sum(F.bptr[b + 1] - F.bptr[b] for b in by_height[h])) for h in range(H + 1)]
@@ -487,157 +328,3 @@ def _run_packed(sw, v, levels=None):
             out.append((r0, nr, acc))
         for (r0, nr, acc) in out:
             v[r0:r0 + nr] = acc
-
-
-# ----------------------------------------------------------------------------------------------
-# resident plan
-# ----------------------------------------------------------------------------------------------
-class ResidentPlan:
-    """
-    Per-rank programs for a cluster of C thread blocks (see module docstring).
-
-    C, n_rows            : cluster size, rows of each block's shared-memory vector (local + replicated)
-    n_local_max, n_shared
-    smem_index[r]        : (Nf,) shared-memory row of permuted face g on rank r, or -1
-    owner_rank           : (Nf,) rank whose vector holds the authoritative copy of face g (-1: replicated)
-    prog[r]              : pack_levels(...) result in rank r's index space; one level per OP_LEVEL op
-    ops                  : (n_ops, 4) int32, identical structure on every rank:
-                           (OP_LEVEL, level index, staged?, 0) or (OP_ALLREDUCE, row_lo, row_hi, 0)
-    n_fwd_ops            : ops[:n_fwd_ops] form the forward sweep, the rest the backward sweep
-    """
-
-
-def resident_plan(F, C, want_tasks=16):
-    assert C in (1, 2, 4, 8, 16)
-    d = int(np.log2(C))
-    nb, n = F.nb, F.n
-    shared_blk = F.depth < d
-    blk_rank = np.where(shared_blk, -1, F.dom >> np.maximum(F.depth - d, 0))
-    sizes = np.diff(F.bptr)
-    blk_of = np.repeat(np.arange(nb), sizes)
-    row_rank = blk_rank[blk_of]                                   # -1: replicated
-    n_local = np.array([int(np.sum(row_rank == r)) for r in range(C)])
-    n_local_max = int(n_local.max()) if C else 0
-    # replicated rows: ordered by (height, row) so that one all-reduce covers a contiguous range
-    sh_blocks = np.flatnonzero(shared_blk)
-    sh_blocks = sh_blocks[np.lexsort((sh_blocks, F.height[sh_blocks]))]
-    sh_index = np.full(n, -1, dtype=np.int64)
-    pos = 0
-    sh_range = {}
-    for b in sh_blocks:
-        k = int(sizes[b])
-        sh_index[F.bptr[b]:F.bptr[b + 1]] = n_local_max + pos + np.arange(k)
-        h = int(F.height[b])
-        lo, hi = sh_range.get(h, (n_local_max + pos, n_local_max + pos))
-        sh_range[h] = (lo, n_local_max + pos + k)
-        pos += k
-    n_shared = pos
-    smem_index = []
-    for r in range(C):
-        m = sh_index.copy()
-        rows = np.flatnonzero(row_rank == r)
-        m[rows] = np.arange(rows.size)
-        smem_index.append(m)
-    # columns of replicated blocks are contributed by the lowest rank below the block
-    col_owner = np.where(row_rank >= 0, row_rank,
-                         (F.dom[blk_of] << np.maximum(d - F.depth[blk_of], 0)))
-    col_owner = np.minimum(col_owner, C - 1)
-
-    local_blocks = [np.flatnonzero(blk_rank == r) for r in range(C)]
-    Hloc = max([int(F.height[lb].max()) if lb.size else 0 for lb in local_blocks] + [0])
-    sh_heights = sorted(sh_range)
-
-    def tr_for(blocks):
-        return _tile_rows_for(int(sum(sizes[b] for b in blocks)), want_tasks)
-
-    if n_local_max + n_shared > 8192:
-        raise ValueError("resident plan: %d rows per block exceed the 16-bit element codes" % (n_local_max + n_shared))
-    plan = ResidentPlan()
-    plan.C, plan.n_local_max, plan.n_shared, plan.n_rows = C, n_local_max, n_shared, n_local_max + n_shared
-    plan.smem_index, plan.row_rank, plan.col_owner = smem_index, row_rank, col_owner
-    plan.prog, ops = [], None
-    for r in range(C):
-        specs, rops = [], []
-
-        def level(kind, items, transpose=False):
-            specs.append((kind, items, transpose))
-            rops.append([OP_LEVEL, len(specs) - 1, 0, 0])
-
-        # ---- forward: local subtree bottom-up
-        for h in range(Hloc + 1):
-            blocks = [b for b in local_blocks[r] if F.height[b] == h]
-            if h > 0:
-                level("a", a_rows(F, blocks, F.Loff))
-            level("b", b_blocks(F, blocks, False), False)
-        # ---- forward: replicated separators bottom-up, partial sums + all-reduce
-        for h in sh_heights:
-            blocks = [b for b in sh_blocks if F.height[b] == h]
-            level("a", a_rows(F, blocks, F.Loff, col_mask=(col_owner == r)))
-            rops.append([OP_ALLREDUCE, sh_range[h][0], sh_range[h][1], 0])
-            level("b", b_blocks(F, blocks, False), False)
-        n_fwd = len(rops)
-        # ---- backward: replicated separators top-down (computed redundantly by every rank)
-        for h in reversed(sh_heights):
-            blocks = [b for b in sh_blocks if F.height[b] == h]
-            level("a", a_rows(F, blocks, F.LoffT))
-            level("b", b_blocks(F, blocks, True), True)
-        # ---- backward: local subtree top-down
-        for h in range(Hloc, -1, -1):
-            blocks = [b for b in local_blocks[r] if F.height[b] == h]
-            level("a", a_rows(F, blocks, F.LoffT))
-            level("b", b_blocks(F, blocks, True), True)
-        ps = pack_mma_streams(specs, row_map=smem_index[r], col_map=smem_index[r])
-        plan.prog.append(ps)
-        for op in rops:
-            if op[0] == OP_LEVEL:
-                op[2] = ps["staged_rows"][op[1]]        # number of staged rows of the level (0: none)
-        rops = np.array(rops, dtype=np.int32).reshape(-1, 4)
-        if ops is None:
-            ops, plan.n_fwd_ops = rops, n_fwd
-        else:
-            # identical structure on every rank; the staged-row count of a level is per rank
-            assert np.array_equal(ops[:, [0, 1]], rops[:, [0, 1]])
-            assert np.array_equal(ops[ops[:, 0] == OP_ALLREDUCE], rops[rops[:, 0] == OP_ALLREDUCE])
-        plan.rank_ops = getattr(plan, "rank_ops", []) + [rops]
-    plan.ops = np.stack(plan.rank_ops)            # (C, n_ops, 4)
-    plan.stage_rows = max(p["stage_rows"] for p in plan.prog)
-    plan.allreduce_rows = max([hi - lo for (lo, hi) in sh_range.values()] + [0])
-    plan.vals = [int(p["vals"]) for p in plan.prog]
-    return plan
-
-
-def apply_resident_plan_host(F, plan, b_perm):
-    """Host interpreter of a resident plan (CPU test of the plan; mirrors the device kernel's data flow).
-    b_perm: (Nf, ...) right-hand side in PERMUTED numbering. Returns J in permuted numbering."""
-    C = plan.C
-    shape_tail = b_perm.shape[1:]
-    vec = [np.zeros((plan.n_rows,) + shape_tail) for _ in range(C)]
-    # every rank holds its local rows; replicated rows start as PARTIAL right-hand sides: put everything on rank 0
-    for r in range(C):
-        loc = np.flatnonzero(plan.row_rank == r)
-        vec[r][plan.smem_index[r][loc]] = b_perm[loc]
-    sh = np.flatnonzero(plan.row_rank < 0)
-    if sh.size:
-        # split the replicated right-hand side unevenly over the ranks to exercise the reduction
-        w = np.linspace(1.0, 2.0, C)
-        w = w / w.sum()
-        for r in range(C):
-            vec[r][plan.smem_index[r][sh]] = w[r] * b_perm[sh]
-    for op in plan.ops[0]:
-        if op[0] == OP_LEVEL:
-            for r in range(C):
-                _run_stream_level(plan.prog[r], vec[r], int(op[1]))
-        else:
-            lo, hi = op[1], op[2]
-            tot = sum(vec[r][lo:hi] for r in range(C))
-            for r in range(C):
-                vec[r][lo:hi] = tot
-    out = np.zeros_like(b_perm)
-    for r in range(C):
-        loc = np.flatnonzero(plan.row_rank == r)
-        out[loc] = vec[r][plan.smem_index[r][loc]]
-    if sh.size:
-        out[sh] = vec[0][plan.smem_index[0][sh]]
-        for r in range(1, C):
-            assert np.allclose(vec[r][plan.smem_index[r][sh]], out[sh], rtol=1e-12, atol=1e-13)
-    return out

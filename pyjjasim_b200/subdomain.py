@@ -26,6 +26,8 @@ A subdomain's shared-memory vector has rows [0, n_loc) = its local faces (ascend
 rows [n_loc, n_loc + n_halo) = its halo rows (ascending top index); a row holds PC float64 as 32-byte chunks
 of 4 problems, chunk c of row r is stored at chunk position c ^ (r & 3) (bank-conflict-free tensor-core gathers).
 """
+import os
+
 import numpy as np
 import scipy.linalg
 import scipy.sparse
@@ -271,17 +273,180 @@ def _auto_groups(L0, hrow, stage_cap):
     return [best] if best >= 0 else []
 
 
-def subdomain_plan(F, junc_face, d, NG, n_warps=RES_WARPS, groups=None):
+UP_PLANE_SHIFT = 28                     # row code of the upper program: plane << 28 | row
+PLANE_R, PLANE_Z, PLANE_J = 0, 1, 2     # right-hand side / forward result / solution of the separator rows
+UP_KM = 2                               # k-steps per warp and pipeline stage of the upper phases
+
+
+def _up_code(plane, rows):
+    return (np.asarray(rows, dtype=np.int64) | (plane << UP_PLANE_SHIFT)).astype(np.int32)
+
+
+class _UpperBuilder:
+    """Collects the tasks of the upper program phase by phase (see JJSubdomainPlan in include/jjstep.h).
+    A task computes  out[rows] = V . X[cols]  for at most 8 * RB consecutive rows of one plane; its A fragments are
+    stored per 8-row tile as [k-step][lane = row * 4 + kk] = V[row, 4 k + kk]."""
+
+    def __init__(self, RB, KB, pad_code):
+        self.RB, self.KB, self.pad_code = RB, KB, pad_code
+        self.phases = []                 # list of lists of (cost, out code, rows, nk, cols, A)
+        self.cur = None
+
+    def begin_phase(self):
+        self.cur = []
+
+    def end_phase(self):
+        if self.cur:
+            self.phases.append(self.cur)
+        self.cur = None
+
+    def task(self, out_plane, row0, V, col_codes):
+        nr, K = V.shape
+        assert 1 <= nr <= 8 * self.RB and K == len(col_codes) and K > 0
+        nk = -(-K // (4 * self.KB)) * self.KB
+        tiles = -(-nr // 8)
+        A = np.zeros((tiles * 8, nk * 4))
+        A[:nr, :K] = V
+        A = np.ascontiguousarray(A.reshape(tiles, 8, nk, 4).transpose(0, 2, 1, 3)).ravel()
+        cols = np.full(nk * 4, self.pad_code, dtype=np.int32)
+        cols[:K] = col_codes
+        self.cur.append((tiles * nk, int(_up_code(out_plane, row0)), nr, nk, cols, A))
+
+    def finish(self, n_fwd):
+        """-> dict of flat arrays; tasks of a phase sorted by decreasing cost (the device deals them out round-robin)."""
+        phase_ptr, hdr, aoff, cols, vals = [0], [], [], [], []
+        co = vo = 0
+        for ph in self.phases:
+            for (cost, out, nr, nk, c, A) in sorted(ph, key=lambda t: -t[0]):
+                hdr.append((out, nr, nk, co))
+                aoff.append(vo)
+                cols.append(c)
+                vals.append(A)
+                co += c.size
+                vo += A.size
+            phase_ptr.append(len(hdr))
+        assert co < 2 ** 31
+        return dict(RB=self.RB, KB=self.KB, n_fwd=n_fwd, n_bwd=len(self.phases) - n_fwd,
+                    phase_ptr=np.asarray(phase_ptr, dtype=np.int32),
+                    task=np.asarray(hdr, dtype=np.int32).reshape(-1, 4),
+                    task_aoff=np.asarray(aoff, dtype=np.int64),
+                    cols=np.concatenate(cols) if cols else np.zeros(0, dtype=np.int32),
+                    A=np.concatenate(vals) if vals else np.zeros(0))
+
+
+def _upper_program(F, top_rows, tt0, blk_of, RB, KB, n_up_pad):
+    """
+    Sweep program of the UPPER separators (top rows [0, tt0) in the top numbering) and the elimination of the dense
+    top of the top (rows [tt0, n_top)) from them. Separator blocks of one tree depth are mutually independent, so a
+    sweep takes two phases per depth, every phase a list of independent gathered dense products:
+
+      forward, deepest first    a)  t_B = r_B - L[B, below] z          (r plane, in place)
+                                b)  z_B = inv(L[B, B]) t_B             (r -> z plane)
+      then                          r_tt -= L[tt, upper] z             (r plane, in place; the dense inverse follows)
+      backward, shallowest first a) t_B = z_B - L[above, B]^T J        (z plane, in place)
+                                b)  J_B = inv(L[B, B])^T t_B           (z -> J plane)
+    """
+    n_top = top_rows.size
+    ub = _UpperBuilder(RB, KB, int(_up_code(PLANE_R, n_up_pad - 1)))
+    if tt0 == 0:
+        return ub.finish(0)
+    Lt = F.Lc[top_rows][:, top_rows].tocsr()
+    Lt.sort_indices()
+    assert scipy.sparse.triu(Lt, k=1).nnz == 0
+    LtT = Lt.T.tocsr()
+    LtT.sort_indices()
+    bu = blk_of[top_rows[:tt0]]
+    starts = np.flatnonzero(np.concatenate(([True], bu[1:] != bu[:-1])))
+    ends = np.concatenate((starts[1:], [tt0]))
+    bdepth = F.depth[bu[starts]].astype(np.int64)
+    depths = np.unique(bdepth)
+    RT = 8 * RB
+    dinv = {}
+
+    def block_inv(b0, b1):
+        if b0 not in dinv:
+            dinv[b0] = scipy.linalg.solve_triangular(Lt[b0:b1, b0:b1].toarray(), np.eye(b1 - b0), lower=True)
+        return dinv[b0]
+
+    def phase_a(M, plane_self, plane_cols, row_ranges, col_lo, col_hi):
+        """out[rows] = self[rows] - M[rows, col_lo:col_hi] X[cols], in place in plane_self."""
+        ub.begin_phase()
+        for (r0, r1) in row_ranges:
+            sub = M[r0:r1]
+            idx = sub.indices
+            cols = np.unique(idx[(idx >= col_lo) & (idx < col_hi)])
+            if cols.size == 0:
+                continue
+            V = np.concatenate((-sub[:, cols].toarray(), np.eye(r1 - r0)), axis=1)
+            codes = np.concatenate((_up_code(plane_cols, cols), _up_code(plane_self, np.arange(r0, r1))))
+            ub.task(plane_self, r0, V, codes)
+        ub.end_phase()
+
+    def groups_of(blocks):
+        return [(r0, min(b1, r0 + RT), b0, b1) for (b0, b1) in blocks for r0 in range(b0, b1, RT)]
+
+    # ---- forward
+    for dd in depths[::-1]:
+        blocks = [(int(starts[i]), int(ends[i])) for i in np.flatnonzero(bdepth == dd)]
+        grp = groups_of(blocks)
+        ub.begin_phase()
+        for (r0, r1, b0, b1) in grp:
+            sub = Lt[r0:r1]
+            idx = sub.indices
+            cols = np.unique(idx[idx < b0])
+            if cols.size == 0:
+                continue
+            V = np.concatenate((-sub[:, cols].toarray(), np.eye(r1 - r0)), axis=1)
+            codes = np.concatenate((_up_code(PLANE_Z, cols), _up_code(PLANE_R, np.arange(r0, r1))))
+            ub.task(PLANE_R, r0, V, codes)
+        ub.end_phase()
+        ub.begin_phase()
+        for (r0, r1, b0, b1) in grp:
+            Di = block_inv(b0, b1)
+            ub.task(PLANE_Z, r0, Di[r0 - b0:r1 - b0, :r1 - b0], _up_code(PLANE_R, np.arange(b0, r1)))
+        ub.end_phase()
+    if n_top > tt0:
+        phase_a(Lt, PLANE_R, PLANE_Z, [(r0, min(n_top, r0 + RT)) for r0 in range(tt0, n_top, RT)], 0, tt0)
+    n_fwd = len(ub.phases)
+    # ---- backward
+    for dd in depths:
+        blocks = [(int(starts[i]), int(ends[i])) for i in np.flatnonzero(bdepth == dd)]
+        grp = groups_of(blocks)
+        ub.begin_phase()
+        for (r0, r1, b0, b1) in grp:
+            sub = LtT[r0:r1]
+            idx = sub.indices
+            cols = np.unique(idx[idx >= b1])
+            if cols.size == 0:
+                continue
+            V = np.concatenate((-sub[:, cols].toarray(), np.eye(r1 - r0)), axis=1)
+            codes = np.concatenate((_up_code(PLANE_J, cols), _up_code(PLANE_Z, np.arange(r0, r1))))
+            ub.task(PLANE_Z, r0, V, codes)
+        ub.end_phase()
+        ub.begin_phase()
+        for (r0, r1, b0, b1) in grp:
+            Di = block_inv(b0, b1)
+            ub.task(PLANE_J, r0, Di.T[r0 - b0:r1 - b0, r0 - b0:], _up_code(PLANE_Z, np.arange(r0, b1)))
+        ub.end_phase()
+    return ub.finish(n_fwd)
+
+
+def subdomain_plan(F, junc_face, d, NG, n_warps=RES_WARPS, groups=None, tt_max=None, up_rb=4):
     """
     F         : factor.Factor of the permuted cycle-space system
     junc_face : (Nj, 2) permuted faces of every junction, -1 none (CircuitTables.junc_face)
     d         : cut depth, P = 2^d subdomains; None: the subtrees of an ordering made with n_parts (F.blk_part)
     NG        : problem groups of 8 per chunk (PC = 8 * NG problems share one pass over the factor)
     groups    : tree heights after which a new level group starts (see _subdomain_levels); None = automatic
+    tt_max    : the tree levels nearest the root whose rows number at most this many are solved by ONE dense inverse
+                (the top of the top); the separators between them and the subdomains get the upper program
+    up_rb     : 8-row tiles per task of the upper program
     """
     assert NG in (1, 2, 4, 8)
     n, nb = F.n, F.nb
     PC = 8 * NG
+    if tt_max is None:
+        tt_max = int(os.environ.get("JJ_TT_MAX", "1024"))
     sizes = np.diff(F.bptr)
     blk_of = np.repeat(np.arange(nb), sizes)
     if d is None:
@@ -294,24 +459,33 @@ def subdomain_plan(F, junc_face, d, NG, n_warps=RES_WARPS, groups=None):
         top_blk = F.depth < d
         blk_sub = np.where(top_blk, -1, F.dom >> np.maximum(F.depth - d, 0)).astype(np.int64)
     row_sub = blk_sub[blk_of]
-    top_rows = np.flatnonzero(row_sub < 0)
-    n_top = int(top_rows.size)
+    # the top of the top: all separator blocks of depth < d_tt (an ancestor-closed set: it can be eliminated last)
+    tb = np.flatnonzero(blk_sub < 0)
+    d_tt = 0
+    if tb.size:
+        rows_at = np.bincount(F.depth[tb], weights=sizes[tb], minlength=int(F.depth[tb].max()) + 1)
+        d_tt = int(np.searchsorted(np.cumsum(rows_at), tt_max, side="right"))
+    row_tt = ((blk_sub < 0) & (F.depth < d_tt))[blk_of]
+    su_rows = np.flatnonzero((row_sub < 0) & ~row_tt)
+    tt_rows = np.flatnonzero(row_tt)
+    top_rows = np.concatenate((su_rows, tt_rows))
+    n_top, tt0, n_tt = int(top_rows.size), int(su_rows.size), int(tt_rows.size)
     tix = np.full(n, -1, dtype=np.int64)
     tix[top_rows] = np.arange(n_top)
 
     # (subdomain, top row) couplings through the factor
     coo = F.Loff.tocoo()
-    m = (row_sub[coo.row] < 0) & (row_sub[coo.col] >= 0)
-    assert not np.any((row_sub[coo.row] >= 0) & (row_sub[coo.col] < 0)), "a local row precedes one of its separators"
-    assert not np.any((row_sub[coo.row] >= 0) & (row_sub[coo.col] >= 0) & (row_sub[coo.row] != row_sub[coo.col])), \
-        "two subdomains are coupled"
-    coupled = [set() for _ in range(P)]
-    subs_of_top = [[] for _ in range(n_top)]
-    if m.any():
-        pairs = np.unique(np.stack((row_sub[coo.col[m]], tix[coo.row[m]]), axis=1), axis=0)
-        for s, k in pairs:
-            coupled[int(s)].add(int(k))
-            subs_of_top[int(k)].append(int(s))
+    rs_r, rs_c = row_sub[coo.row], row_sub[coo.col]
+    assert not np.any((rs_r >= 0) & (rs_c < 0)), "a local row precedes one of its separators"
+    assert not np.any((rs_r >= 0) & (rs_c >= 0) & (rs_r != rs_c)), "two subdomains are coupled"
+    m = (rs_r < 0) & (rs_c >= 0)
+    nt1 = max(n_top, 1)
+    lkeys = np.unique(rs_c[m] * nt1 + tix[coo.row[m]])
+    # subdomains coupled to each top row (CSR), for the junctions that lie between two top faces
+    lk_s, lk_k = lkeys // nt1, lkeys % nt1
+    o = np.argsort(lk_k, kind="stable")
+    sot_ptr = np.searchsorted(lk_k[o], np.arange(n_top + 1))
+    sot = lk_s[o]
 
     # junction ownership: the subdomain of its local face; junctions between top faces go to a coupled
     # subdomain with the fewest junctions so far
@@ -327,42 +501,49 @@ def subdomain_plan(F, junc_face, d, NG, n_warps=RES_WARPS, groups=None):
         cand = set()
         for k in range(2):
             if has[j, k]:
-                cand.update(subs_of_top[tix[jf[j, k]]])
+                t = tix[jf[j, k]]
+                cand.update(sot[sot_ptr[t]:sot_ptr[t + 1]].tolist())
         cand = sorted(cand) if cand else list(range(P))
         s = min(cand, key=lambda q: (load[q], q))
         owner[j] = s
         load[s] += 1
-    for j in np.flatnonzero(has.any(axis=1)):
-        for k in range(2):
-            if has[j, k] and row_sub[jf[j, k]] < 0:
-                coupled[int(owner[j])].add(int(tix[jf[j, k]]))
+    # a subdomain also carries the top faces of the junctions it owns (partial face sums, back-projection)
+    jt = has & (np.where(has, row_sub[np.maximum(jf, 0)], 0) < 0)
+    jkeys = (np.repeat(owner[:, None], 2, axis=1)[jt]) * nt1 + tix[jf[jt]]
+    keys = np.unique(np.concatenate((lkeys, jkeys)))            # sorted by (subdomain, top row)
+    key_s, key_k = keys // nt1, keys % nt1
 
     plan = SubdomainPlan()
     plan.P, plan.NG, plan.PC, plan.d = P, NG, PC, d
     plan.n_top, plan.top_rows = n_top, top_rows.astype(np.int32)
-    plan.n_top_pad = (n_top + 31) // 32 * 32
-    if plan.n_top_pad > 8192:
-        # the separators above the cut are solved by a DENSE inverse: 8192^2 float64 is 0.5 GB and 67 M multiply-adds
-        # per problem and time step; beyond that the circuit needs a multi-level top (not built) and runs on the
-        # streaming engine
-        raise ValueError("subdomain plan: %d top rows are too many for the dense top product" % n_top)
-    loc = [np.flatnonzero(row_sub == s) for s in range(P)]
-    halo = [np.array(sorted(coupled[s]), dtype=np.int64) for s in range(P)]
-    plan.n_loc = np.array([l.size for l in loc], dtype=np.int32)
-    plan.n_halo = np.array([h.size for h in halo], dtype=np.int32)
+    plan.tt0, plan.n_tt = tt0, n_tt
+    plan.n_tt_pad = (n_tt + 31) // 32 * 32
+    plan.n_up_pad = (max(n_top + 1, tt0 + plan.n_tt_pad) + 31) // 32 * 32
+    if plan.n_tt_pad > 8192:
+        raise ValueError("subdomain plan: %d rows are too many for the dense top product" % n_tt)
+    if plan.n_up_pad >= (1 << UP_PLANE_SHIFT):
+        raise ValueError("subdomain plan: %d separator rows exceed the row codes of the upper program" % n_top)
+    order_l = np.argsort(row_sub, kind="stable")
+    lptr = np.searchsorted(row_sub[order_l], np.arange(P + 1))
+    loc = [order_l[lptr[s]:lptr[s + 1]] for s in range(P)]
+    plan.hptr = np.searchsorted(key_s, np.arange(P + 1)).astype(np.int32)
+    halo = [key_k[plan.hptr[s]:plan.hptr[s + 1]] for s in range(P)]
+    plan.n_loc = np.diff(lptr).astype(np.int32)
+    plan.n_halo = np.diff(plan.hptr).astype(np.int32)
     plan.n_loc_max = int(plan.n_loc.max())
     plan.n_rows = (int((plan.n_loc + plan.n_halo).max()) + 7) // 8 * 8 + 8
     if plan.n_rows * PC > 65536:
         raise ValueError("subdomain plan: %d rows x %d problems exceed the 16-bit element codes" % (plan.n_rows, PC))
-    plan.hptr = np.concatenate(([0], np.cumsum(plan.n_halo))).astype(np.int32)
     plan.n_slots = int(plan.hptr[-1])
-    plan.halo_top = (np.concatenate(halo) if plan.n_slots else np.zeros(0)).astype(np.int32)
-    vrow = np.full((P, n), -1, dtype=np.int64)
-    for s in range(P):
-        vrow[s, loc[s]] = np.arange(loc[s].size)
-        vrow[s, top_rows[halo[s]]] = loc[s].size + np.arange(halo[s].size)
-    plan.vrow = vrow
+    plan.halo_top = key_k.astype(np.int32)
     plan.row_sub = row_sub
+
+    def halo_row(s, k):
+        """shared-memory row of top row k in subdomain s (vectorised)."""
+        pos = np.searchsorted(keys, s * nt1 + k)
+        assert np.all(keys[np.minimum(pos, keys.size - 1)] == s * nt1 + k)
+        return plan.n_loc[s] + (pos - plan.hptr[s])
+    plan.halo_row = halo_row
 
     # ---- per-subdomain sweep programs: backward levels first (they open a time step), then forward
     plan.prog, plan.n_bwd = [], []
@@ -372,35 +553,41 @@ def subdomain_plan(F, junc_face, d, NG, n_warps=RES_WARPS, groups=None):
     if stage_cap < 8:
         raise ValueError("subdomain plan: the right-hand sides leave no room for the staging rows")
     stage_cap = min(stage_cap, 4096)
+    vrow_loc = np.full(n, -1, dtype=np.int64)            # shared-memory row of every local face in its subdomain
     for s in range(P):
         levels, n_bwd, order, gb = _subdomain_levels(F, loc[s], top_rows[halo[s]], blk_of, stage_cap, groups)
-        vrow[s, loc[s][order]] = np.arange(loc[s].size)
+        vrow_loc[loc[s][order]] = np.arange(loc[s].size)
         plan.prog.append(_pack_levels(levels, NG, n_warps, n_bwd))
         plan.n_bwd.append(n_bwd)
         plan.group_bounds.append(gb)
+    plan.vrow_loc = vrow_loc
     plan.n_bwd = np.asarray(plan.n_bwd, dtype=np.int32)
     plan.stage_rows = max(p["stage_rows"] for p in plan.prog)
     if n_top:
-        # the staged top product keeps a ring of 4 stages x 8 KB (or 4 KB, 2 KB) in the staging rows
+        # the top product and the upper phases keep a ring of 4 stages x 8 KB (or 4 KB, 2 KB) in the staging rows
         for ring in (32768, 16384, 8192):
             need = -(-ring // ((PC + 2) * 8))
             if need <= stage_cap:
                 plan.stage_rows = max(plan.stage_rows, need)
                 break
 
-    # ---- top: explicit inverse of the Schur complement, packed as FP64 MMA A fragments
-    nTp = plan.n_top_pad
-    if n_top:
-        LTT = F.Lc[top_rows][:, top_rows].toarray()
-        Linv = scipy.linalg.solve_triangular(LTT, np.eye(n_top), lower=True)
+    # ---- top of the top: explicit inverse of its Schur complement, packed as FP64 MMA A fragments
+    nTp = plan.n_tt_pad
+    if n_tt:
+        LTT = F.Lc[tt_rows][:, tt_rows].toarray()
+        Linv = scipy.linalg.solve_triangular(LTT, np.eye(n_tt), lower=True)
         Sinv = Linv.T @ Linv
         SP = np.zeros((nTp, nTp))
-        SP[:n_top, :n_top] = Sinv
+        SP[:n_tt, :n_tt] = Sinv
         plan.Sinv = Sinv
         plan.Sinv_packed = np.ascontiguousarray(SP.reshape(nTp // 8, 8, nTp // 4, 4).transpose(0, 2, 1, 3)).ravel()
     else:
         plan.Sinv = np.zeros((0, 0))
         plan.Sinv_packed = np.zeros(0)
+    # ---- upper separators between the subdomains and the top of the top
+    RB = int(up_rb)
+    assert RB in (1, 2, 4, 8, 16)
+    plan.upper = _upper_program(F, top_rows, tt0, blk_of, RB, (16 // RB) * UP_KM, plan.n_up_pad)
     # assembly of r_top: slots (subdomain halo rows) of every top row
     order = np.argsort(plan.halo_top, kind="stable")
     plan.tslot = order.astype(np.int32)
@@ -414,10 +601,28 @@ def subdomain_plan(F, junc_face, d, NG, n_warps=RES_WARPS, groups=None):
     jdev[jorder] = np.arange(Nj)
     plan.jdev = jdev
     plan.junc_ptr = np.searchsorted(owner[jorder], np.arange(P + 1)).astype(np.int32)
-    rows = np.where(has, vrow[owner[:, None], np.maximum(jf, 0)], -1)
-    assert np.all(rows[has] >= 0)
-    plan.junc_row = np.ascontiguousarray(rows[jorder].astype(np.int32))
+    plan.junc_row = np.ascontiguousarray(plan.rows_of(np.repeat(owner[:, None], 2, axis=1), jf)[jorder].astype(np.int32))
     return plan
+
+
+def _rows_of(plan, s, g):
+    """Shared-memory row of permuted face g in subdomain s (arrays of equal shape; g = -1 gives -1)."""
+    s, g = np.asarray(s, dtype=np.int64), np.asarray(g, dtype=np.int64)
+    out = np.full(g.shape, -1, dtype=np.int64)
+    ok = g >= 0
+    gs = plan.row_sub[np.maximum(g, 0)]
+    is_loc = ok & (gs >= 0)
+    assert np.all(gs[is_loc] == s[is_loc]), "a face is used by a subdomain that does not own it"
+    out[is_loc] = plan.vrow_loc[g[is_loc]]
+    is_top = ok & (gs < 0)
+    if is_top.any():
+        tix = np.full(plan.row_sub.size, -1, dtype=np.int64)
+        tix[plan.top_rows] = np.arange(plan.n_top)
+        out[is_top] = plan.halo_row(s[is_top], tix[g[is_top]])
+    return out
+
+
+SubdomainPlan.rows_of = _rows_of
 
 
 def face_tables(plan, face_ptr, face_junc, face_sign, junc_sign, c0):
@@ -429,7 +634,7 @@ def face_tables(plan, face_ptr, face_junc, face_sign, junc_sign, c0):
     g_of = np.repeat(np.arange(Nf), np.diff(face_ptr))
     j_of = np.asarray(face_junc, dtype=np.int64)
     r_of = plan.owner[j_of]
-    row_of = plan.vrow[r_of, g_of]
+    row_of = plan.rows_of(r_of, g_of)
     assert np.all(row_of >= 0)
     key = np.lexsort((j_of, row_of, r_of))
     flat = (r_of * n_rows + row_of)[key]
@@ -442,9 +647,8 @@ def face_tables(plan, face_ptr, face_junc, face_sign, junc_sign, c0):
     ell_j[flat, pos] = plan.jdev[j_of[key]]
     ell_c[flat, pos] = np.asarray(face_sign, dtype=np.double)[key] / c0[j_of[key]]
     fidx = np.full((P, n_rows), -1, dtype=np.int32)
-    for s in range(P):
-        g = np.flatnonzero(plan.row_sub == s)
-        fidx[s, plan.vrow[s, g]] = g
+    g = np.flatnonzero(plan.row_sub >= 0)
+    fidx[plan.row_sub[g], plan.vrow_loc[g]] = g
     plan.face_K = K
     plan.face_ell_j = ell_j.reshape(P, n_rows, K)
     plan.face_ell_c = ell_c.reshape(P, n_rows, K)
@@ -486,26 +690,53 @@ def _run_level_host(ps, v, level, NG):
         v[row0:row0 + nr, pcols] = acc
 
 
+def _run_upper_phase_host(up, U, ph):
+    """One phase of the upper program on the host; U is (3, n_up_pad, PC). Tasks of a phase are independent: all
+    products are formed before any row is written, as on the device (where a grid barrier ends the phase)."""
+    res = []
+    mask = (1 << UP_PLANE_SHIFT) - 1
+    for t in range(up["phase_ptr"][ph], up["phase_ptr"][ph + 1]):
+        out, nr, nk, co = (int(v) for v in up["task"][t])
+        tiles = -(-nr // 8)
+        ao = int(up["task_aoff"][t])
+        A = up["A"][ao:ao + tiles * nk * 32].reshape(tiles, nk, 8, 4).transpose(0, 2, 1, 3).reshape(tiles * 8, nk * 4)
+        cols = up["cols"][co:co + nk * 4].astype(np.int64)
+        X = U[cols >> UP_PLANE_SHIFT, cols & mask]
+        res.append((out >> UP_PLANE_SHIFT, out & mask, (A @ X)[:nr]))
+    for (pl, r0, val) in res:
+        U[pl, r0:r0 + val.shape[0]] = val
+
+
 def apply_subdomain_plan_host(plan, b_perm):
     """Solve through the plan on the host. b_perm: (Nf, PC) right-hand side in PERMUTED numbering."""
     P, NG = plan.P, plan.NG
     assert b_perm.shape[1] == plan.PC
-    vec, z = [], []
+    vec = []
     ctop = np.zeros((plan.n_slots, plan.PC))
+    row_of = np.where(plan.row_sub >= 0, plan.vrow_loc, -1)
     for s in range(P):
         v = np.zeros((plan.n_rows, plan.PC))
         loc = np.flatnonzero(plan.row_sub == s)
-        v[plan.vrow[s, loc]] = b_perm[loc]
+        v[row_of[loc]] = b_perm[loc]
         ps = plan.prog[s]
         for l in range(plan.n_bwd[s], ps["n_levels"]):
             _run_level_host(ps, v, l, NG)
         ctop[plan.hptr[s]:plan.hptr[s + 1]] = v[plan.n_loc[s]: plan.n_loc[s] + plan.n_halo[s]]
         vec.append(v)
-    rtop = b_perm[plan.top_rows].copy()
+    U = np.zeros((3, plan.n_up_pad, plan.PC))
+    U[PLANE_R, :plan.n_top] = b_perm[plan.top_rows]
     for k in range(plan.n_top):
         for sl in plan.tslot[plan.tptr[k]:plan.tptr[k + 1]]:
-            rtop[k] += ctop[sl]
-    jtop = plan.Sinv @ rtop
+            U[PLANE_R, k] += ctop[sl]
+    up = plan.upper
+    for ph in range(up["n_fwd"]):
+        _run_upper_phase_host(up, U, ph)
+    t0, t1 = plan.tt0, plan.tt0 + plan.n_tt
+    U[PLANE_J, t0:t1] = plan.Sinv @ U[PLANE_R, t0:t1]
+    for ph in range(up["n_fwd"], up["n_fwd"] + up["n_bwd"]):
+        _run_upper_phase_host(up, U, ph)
+    assert not np.any(U[PLANE_R, plan.n_top:]), "the zero rows of the r plane were written"
+    jtop = U[PLANE_J, :plan.n_top]
     out = np.zeros_like(b_perm)
     out[plan.top_rows] = jtop
     for s in range(P):
@@ -515,5 +746,5 @@ def apply_subdomain_plan_host(plan, b_perm):
         for l in range(plan.n_bwd[s]):
             _run_level_host(ps, v, l, NG)
         loc = np.flatnonzero(plan.row_sub == s)
-        out[loc] = v[plan.vrow[s, loc]]
+        out[loc] = v[row_of[loc]]
     return out

@@ -118,65 +118,6 @@ def test_missing_gpu_library_fails_loudly(monkeypatch):
         pj.TimeEvolutionProblem(**kw).compute()
 
 
-# ------------------------------------------------------------------------------------------------
-# resident engine (cluster kernel): every cluster size / tile width against the golden vectors
-# ------------------------------------------------------------------------------------------------
-RESIDENT_CONFIGS = ["1,8", "2,8", "4,8", "8,8"]
-
-
-@pytest.mark.parametrize("cfg", RESIDENT_CONFIGS)
-def test_resident_solve_matches_direct_solve(cfg, monkeypatch):
-    import scipy.sparse.linalg
-    from pyjjasim_b200 import engine
-    from pyjjasim_b200.factor import system_matrix
-    Ccl, Wt = (int(v) for v in cfg.split(","))
-    a = pj.SquareArray(40, 37)
-    rng = np.random.RandomState(2)
-    a.set_resistance(0.5 + rng.rand(a._Nj()))
-    a.set_inductance(0.1)
-    tab = engine.CircuitTables(a, 0.05)
-    eng = engine.DeviceEngine(0)
-    eng.set_circuit(tab, pj.DefaultCPR())
-    eng.set_resident(Ccl, Wt)
-    W = 13
-    eng.set_problem(W, 0.05)
-    b = rng.randn(a._Nf(), W)
-    J = eng.debug_resident_solve(b)
-    S = system_matrix(a.get_cycle_matrix(), a._L(), tab.Rv, tab.Cv)
-    Jref = scipy.sparse.linalg.spsolve(S.tocsc(), b)
-    eng.close()
-    assert np.max(np.abs(J - Jref)) <= 1e-12 * np.max(np.abs(Jref))
-
-
-@pytest.mark.parametrize("cfg", RESIDENT_CONFIGS)
-@pytest.mark.parametrize("name", ["sq_mixed", "sq_frustrated", "honeycomb", "noise_recycled", "custom_cpr", "sq_iv"])
-def test_resident_engine_matches_reference_golden(name, cfg, golden_dir, monkeypatch):
-    monkeypatch.setenv("JJ_RESIDENT", cfg)
-    g = np.load(os.path.join(golden_dir, name + ".npz"))
-    kw, prob, res = run_device(name, "resident")
-    from pyjjasim_b200 import engine
-    st = engine.last_run_stats[0]
-    assert st["engine"] == 2 and (st["cluster_size"], st["tile_problems"]) == tuple(int(v) for v in cfg.split(","))
-    tol = cases.TOL[name]
-    assert np.max(np.abs(res.theta - g["theta"])) <= tol
-    if "current" in g.files:
-        assert np.max(np.abs(res.current - g["current"])) <= 10 * tol
-    if "voltage" in g.files:
-        assert np.max(np.abs(res.voltage - g["voltage"])) <= 10 * tol / kw.get("time_step", 0.05)
-
-
-def test_resident_and_streaming_agree_on_device_noise(monkeypatch):
-    # same Philox stream in both engines: identical draws -> trajectories agree to round-off over a short horizon
-    kw, _ = cases.build("noise_small", pj)
-    kw["noise_seed"] = 99
-    out = {}
-    for eng_name in ("streaming", "resident"):
-        monkeypatch.setenv("JJ_ENGINE", eng_name)
-        out[eng_name] = pj.TimeEvolutionProblem(**kw).compute().theta
-    assert np.max(np.abs(out["streaming"] - out["resident"])) <= 1e-9
-    assert np.std(out["resident"][:, -1, -1]) > 1e-3      # noise actually acted
-
-
 def test_device_noise_statistics_and_shard_invariance():
     from pyjjasim_b200 import engine
     a = pj.SquareArray(12, 12)
@@ -204,18 +145,36 @@ SUBDOMAIN_CONFIGS = ["0,1", "1,2", "2,4", "3,4", "2,8", "4,1"]
 @pytest.mark.parametrize("W", [13, 70])
 @pytest.mark.parametrize("cfg", SUBDOMAIN_CONFIGS)
 def test_subdomain_solve_matches_direct_solve(cfg, W):
+    _subdomain_solve_check(cfg, W)
+
+
+@pytest.mark.parametrize("tt_max", ["0", "40", "150"])
+@pytest.mark.parametrize("cfg,W", [("3,4", 70), ("4,1", 13), ("4,2", 40), ("5,4", 33), ("p24,4", 100), ("p7,8", 64)])
+def test_subdomain_solve_through_upper_phases(cfg, W, tt_max, monkeypatch):
+    # the separators between the subdomains and the dense top of the top are swept by the upper program (gathered
+    # dense products, two phases per tree depth); tt_max = 0: no dense part at all
+    monkeypatch.setenv("JJ_TT_MAX", tt_max)
+    _subdomain_solve_check(cfg, W, upper=True)
+
+
+def _subdomain_solve_check(cfg, W, upper=False):
     import scipy.sparse.linalg
     from pyjjasim_b200 import engine
     from pyjjasim_b200.factor import system_matrix
-    d, NG = (int(v) for v in cfg.split(","))
-    a = pj.SquareArray(40, 37)
+    d, NG = cfg.split(",")
+    n_parts = int(d[1:]) if d.startswith("p") else None
+    d, NG = (None if n_parts else int(d)), int(NG)
+    a = pj.SquareArray(40, 37) if not upper else pj.SquareArray(61, 53)
     rng = np.random.RandomState(2)
     a.set_resistance(0.5 + rng.rand(a._Nj()))
     a.set_inductance(0.1)
-    tab = engine.CircuitTables(a, 0.05)
+    tab = engine.CircuitTables(a, 0.05, n_parts=n_parts)
     eng = engine.DeviceEngine(0)
-    eng.set_circuit(tab, pj.DefaultCPR())
+    eng.set_circuit(tab, pj.DefaultCPR(), with_program=False)
     eng.set_subdomain(d, NG)
+    plan = tab.subdomain_plan(d, NG)
+    if upper:
+        assert plan.upper["n_fwd"] > 0 and plan.upper["n_bwd"] > 0 and plan.tt0 > 0
     eng.set_problem(W, 0.05)
     b = rng.randn(a._Nf(), W)
     J = eng.debug_subdomain_solve(b)
@@ -225,9 +184,12 @@ def test_subdomain_solve_matches_direct_solve(cfg, W):
     assert np.max(np.abs(J - Jref)) <= 1e-12 * np.max(np.abs(Jref))
 
 
-@pytest.mark.parametrize("cfg", ["0,1", "1,2", "2,4", "3,1"])
+@pytest.mark.parametrize("cfg", ["0,1", "1,2", "2,4", "3,1", "3,4,tt0", "4,2,tt12"])
 @pytest.mark.parametrize("name", ["sq_mixed", "sq_frustrated", "honeycomb", "noise_recycled", "custom_cpr", "sq_iv"])
 def test_subdomain_engine_matches_reference_golden(name, cfg, golden_dir, monkeypatch):
+    if "tt" in cfg:          # run the upper program inside the time loop (tt0: no dense top at all)
+        cfg, tt = cfg.rsplit(",tt", 1)
+        monkeypatch.setenv("JJ_TT_MAX", tt)
     monkeypatch.setenv("JJ_SUBDOMAIN", cfg)
     g = np.load(os.path.join(golden_dir, name + ".npz"))
     kw, prob, res = run_device(name, "subdomain")
@@ -334,8 +296,8 @@ def test_device_vortex_observables_are_exact(engine):
     os.environ["JJ_ENGINE"] = engine
     try:
         tab = eng_mod._tables_for(c, 0.05)
-        key, e = eng_mod._engine_for(tab, pj.DefaultCPR(), 0, W, eng_mod._engine_kind(None))
-        e.set_problem(W, 0.05, engine=eng_mod._engine_kind(None))
+        key, e, kind = eng_mod._engine_for(tab, pj.DefaultCPR(), 0, W, eng_mod._engine_kind(None))
+        e.set_problem(W, 0.05, engine=kind)
         e.alloc_outputs(Nt, 0)
         specs = eng_mod._classify_all(prob, tab)
         eng_mod._setup_sources(e, specs, eng_mod._ShardInputs(specs, 0, W), tab)

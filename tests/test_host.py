@@ -270,13 +270,12 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     # struct layouts of the ctypes mirror equal the C compiler's
     import subprocess, tempfile
-    src = '#include <stdio.h>\n#include "jjstep.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu", sizeof(JJSweep), sizeof(JJCircuit), sizeof(JJStats), sizeof(JJRankStream), sizeof(JJResidentPlan), sizeof(JJSubProgram), sizeof(JJSubdomainPlan));return 0;}'
+    src = '#include <stdio.h>\n#include "jjstep.h"\nint main(){printf("%zu %zu %zu %zu %zu", sizeof(JJSweep), sizeof(JJCircuit), sizeof(JJStats), sizeof(JJSubProgram), sizeof(JJSubdomainPlan));return 0;}'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "s.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o", os.path.join(d, "s")])
         sizes = [int(v) for v in subprocess.check_output([os.path.join(d, "s")]).split()]
     assert sizes == [ctypes.sizeof(_lib.JJSweep), ctypes.sizeof(_lib.JJCircuit), ctypes.sizeof(_lib.JJStats),
-                     ctypes.sizeof(_lib.JJRankStream), ctypes.sizeof(_lib.JJResidentPlan),
                      ctypes.sizeof(_lib.JJSubProgram), ctypes.sizeof(_lib.JJSubdomainPlan)]
 
 
@@ -339,7 +338,7 @@ def test_subdomain_layout_rules():
     assert (NG, chunks, P) == (4, 16, 148) and 65025 / P <= 450
     NG, chunks, P = subdomain_layout(79401, 512)              # cfg3: more subdomains than SMs, in units of half the SM count
     assert P == 222 and 79401 / P <= 450
-    assert subdomain_layout(998001, 64)[2] == 74              # cfg5: the dense top cannot follow; classic rule, streaming engine
+    assert subdomain_layout(998001, 64) == (4, 2, 2220)       # cfg5: 30 items per block; 10^5 separator rows above them
     assert subdomain_layout(100, 8) == (1, 1, 2)
 
 

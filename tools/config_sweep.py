@@ -62,7 +62,7 @@ def main():
         st = list(engine.last_run_stats.values())[0]
         W = prob.get_problem_count()
         out = dict(config=name, Nj=a._Nj(), Nf=a._Nf(), W=W, time_steps=Nt,
-                   engine={1: "streaming", 2: "resident", 3: "subdomain"}.get(st["engine"]),
+                   engine={1: "streaming", 3: "subdomain"}.get(st["engine"]),
                    setup_s=round(t2 - t1 - (t3 - t2), 2), device_us_per_time_step=round(st["total_ms"] * 1e3 / Nt, 1),
                    junction_steps_per_s_device=a._Nj() * W * Nt / (st["total_ms"] * 1e-3),
                    junction_steps_per_s_e2e=a._Nj() * W * Nt / (t3 - t2), finite=bool(np.all(np.isfinite(res.theta))),
