@@ -130,7 +130,10 @@ class CircuitTables:
             else:
                 cx, cy = _centroids_from_matrix(circuit, A)
             self.factor = factorize(S, cx, cy, leaf_size=leaf_size, n_parts=n_parts)
-            if n_parts is not None and n_parts > 1 and os.environ.get("JJ_SUB_BALANCE", "1") != "0":
+            # work balancing pays when a block owns ONE subdomain for the whole run and waits for the slowest block at
+            # every step (cfg2: 18 subdomains); with many subdomains the blocks' items average out and every
+            # balancing round would cost a full plan build
+            if n_parts is not None and 1 < n_parts <= _BALANCE_MAX_PARTS and os.environ.get("JJ_SUB_BALANCE", "1") != "0":
                 self.factor = self._balance_parts(A, S, cx, cy, leaf_size, n_parts, self.factor)
             self._program = None
             perm = self.factor.perm.astype(np.int64)
@@ -249,6 +252,7 @@ class CircuitTables:
         return None
 
 
+_BALANCE_MAX_PARTS = 64
 _ROWS_FIT = 560               # local rows of a subdomain that still fit in 227 KB at 32 problems with a ~15 % halo
 _ROWS_PER_SUBDOMAIN = 450     # target when a circuit has to be cut finer than one subdomain per (SM, chunk) anyway
 

@@ -54,22 +54,9 @@ class SubdomainPlan:
     """See module docstring. Attributes are plain numpy arrays ready for the C ABI (JJSubdomainPlan)."""
 
 
-def _tile_record(V, cols, NG):
-    """320-byte stream steps of one tile: A fragment (lane = row*4 + kk) and element codes (lane = n*4 + kk)."""
-    nr, nc = V.shape
-    st = ((nc + 3) // 4 + RING_STEPS - 1) // RING_STEPS * RING_STEPS      # whole ring blocks (zero steps at the end)
-    Vp = np.zeros((8, st * 4))
-    Vp[:nr, :nc] = V
-    cp = np.full(st * 4, cols[-1], dtype=np.int64)
-    cp[:nc] = cols
-    vals = Vp.reshape(8, st, 4).transpose(1, 0, 2).reshape(st, 32)
-    codes = elem_code(cp.reshape(st, 4), NG)                       # (st, kk, n)
-    assert codes.max() < 65536
-    codes = codes.transpose(0, 2, 1).reshape(st, 32).astype(np.uint16)
-    rec = np.zeros((st, STEP_BYTES), dtype=np.uint8)
-    rec[:, :256] = np.ascontiguousarray(vals).view(np.uint8).reshape(st, 256)
-    rec[:, 256:] = np.ascontiguousarray(codes).view(np.uint8).reshape(st, 64)
-    return rec
+def _tile_steps(nc):
+    """stream steps of a tile with nc columns: whole ring blocks (zero steps at the end)"""
+    return ((nc + 3) // 4 + RING_STEPS - 1) // RING_STEPS * RING_STEPS
 
 
 def _pack_levels(levels, NG, n_warps, n_bwd=0):
@@ -78,24 +65,26 @@ def _pack_levels(levels, NG, n_warps, n_bwd=0):
     level (and units of levels with fewer units than warps) are split over problem groups: a warp then handles
     ng < NG groups of the unit; the copies re-read the unit's (small) stream but run concurrently.
     Tiles and stream steps are emitted warp-major inside each sweep (levels [0, n_bwd) and [n_bwd, ...)), so the
-    stream of a warp is contiguous across the levels of a sweep and its prefetch ring never drains."""
+    stream of a warp is contiguous across the levels of a sweep and its prefetch ring never drains.
+    A stream step is 320 bytes: the A fragment (32 float64, lane = row*4 + kk) and the shared-memory element codes of
+    the B fragment (32 uint16, lane = n*4 + kk)."""
     n_levels = len(levels)
     wt_ptr = np.zeros((n_levels * n_warps, 2), dtype=np.int32)
     ws_ptr = np.zeros(n_levels * n_warps, dtype=np.int32)
-    hdr, chunks, lstaged = [], [], []
+    hdr, emitted, lstaged = [], [], []
     n_steps = n_vals = 0
     assigned = []                      # per level: per warp list of (unit index, g0, ng)
     for li, units in enumerate(levels):
         staged = 0
         for u in units:
             for t in u:
-                t["rec"] = _tile_record(t["V"], t["cols"], NG)
+                t["st"] = _tile_steps(t["V"].shape[1])
                 t["stage_off"] = 0
                 if t["flags"] & TILE_STAGED:
                     t["stage_off"] = staged
                     staged += t["V"].shape[0]
         lstaged.append(staged)
-        ucost = [sum(t["rec"].shape[0] for t in u) for u in units]
+        ucost = [sum(t["st"] for t in u) for u in units]
         split = [1] * len(units)
         while True:
             share = sum(c * NG + 6 * sp for c, sp in zip(ucost, split)) / float(n_warps)
@@ -118,32 +107,54 @@ def _pack_levels(levels, NG, n_warps, n_bwd=0):
                 for (ui, g0, ng) in assigned[li][w]:
                     for t in levels[li][ui]:
                         nr, nc = t["V"].shape
-                        st = t["rec"].shape[0]
+                        st = t["st"]
                         assert 0 <= t["row0"] < 65536 and st < 65536 and t["stage_off"] < 32768
                         hdr.append((t["row0"] | ((nr - 1) << 16) | (t["flags"] << 19) | (g0 << 21) | ((ng - 1) << 25),
                                     st | (t["stage_off"] << 16)))
-                        chunks.append(t["rec"])
+                        emitted.append((n_steps, t))
                         n_steps += st
                         if g0 == 0:
                             n_vals += nr * nc
                 wt_ptr[li * n_warps + w, 1] = len(hdr)
-    stream = np.concatenate(chunks).ravel() if chunks else np.zeros(0, dtype=np.uint8)
+    # all records at once: values as (8 rows, all columns), column rows as one list, one transposition at the end
+    VA = np.zeros((8, n_steps * 4))
+    CA = np.zeros(n_steps * 4, dtype=np.int64)
+    for (s0, t) in emitted:
+        nr, nc = t["V"].shape
+        VA[:nr, 4 * s0:4 * s0 + nc] = t["V"]
+        CA[4 * s0:4 * s0 + nc] = t["cols"]
+        CA[4 * s0 + nc:4 * (s0 + t["st"])] = t["cols"][-1]
+    stream = np.zeros((n_steps, STEP_BYTES), dtype=np.uint8)
+    if n_steps:
+        vals = np.ascontiguousarray(VA.reshape(8, n_steps, 4).transpose(1, 0, 2))            # [step][row][kk]
+        codes = elem_code(CA.reshape(n_steps, 4), NG)                                        # [step][kk][n]
+        assert codes.max() < 65536
+        codes = np.ascontiguousarray(codes.transpose(0, 2, 1)).astype(np.uint16)             # [step][n][kk]
+        stream[:, :256] = vals.view(np.uint8).reshape(n_steps, 256)
+        stream[:, 256:] = codes.view(np.uint8).reshape(n_steps, 64)
     return dict(n_levels=n_levels, n_warps=n_warps, wt_ptr=wt_ptr, ws_ptr=ws_ptr,
-                thdr=np.asarray(hdr, dtype=np.int32).reshape(-1, 2), stream=stream, n_steps=int(n_steps),
+                thdr=np.asarray(hdr, dtype=np.int32).reshape(-1, 2), stream=stream.ravel(), n_steps=int(n_steps),
                 lstaged=np.asarray(lstaged, dtype=np.int32), stage_rows=int(max(lstaged) if lstaged else 0),
                 vals=int(n_vals))
 
 
-def _tiles_sparse(M, row0, col_index, flags=TILE_SELF):
-    """8-row tiles of out[row0 + i] (+)= -M[i, :] src: M is CSR, col_index maps its columns to vector rows."""
+def _tri_inverse(L):
+    """inverse of a dense lower-triangular matrix (LAPACK dtrtri)"""
+    inv, info = scipy.linalg.lapack.dtrtri(np.asfortranarray(L), lower=1)
+    if info != 0:
+        raise np.linalg.LinAlgError("singular diagonal block in the factor")
+    return np.tril(inv)
+
+
+def _tiles_dense(M, row0, col_index, flags=TILE_SELF):
+    """8-row tiles of out[row0 + i] (+)= -M[i, :] src: M is a dense array, col_index maps its columns to vector rows."""
     units = []
-    M = scipy.sparse.csr_matrix(M)
+    nz = M != 0
     for t0 in range(0, M.shape[0], 8):
-        sub = M[t0:t0 + 8]
-        cols = np.unique(sub.indices[sub.data != 0]) if sub.nnz else np.zeros(0, dtype=np.int64)
+        cols = np.flatnonzero(nz[t0:t0 + 8].any(axis=0))
         if cols.size == 0:
             continue
-        units.append([dict(row0=int(row0 + t0), V=-sub[:, cols].toarray(), cols=col_index[cols], flags=flags)])
+        units.append([dict(row0=int(row0 + t0), V=-M[t0:t0 + 8, cols], cols=col_index[cols], flags=flags)])
     return units
 
 
@@ -171,7 +182,9 @@ def _subdomain_levels(F, loc, hrows, blk_of, stage_cap, groups=None):
         return [], 0, np.zeros(0, dtype=np.int64), []
     hrow = F.height[blk_of[loc]].astype(np.int64)
     H = int(hrow.max())
-    L0 = scipy.sparse.csr_matrix(F.Lc[loc][:, loc])
+    lo, hi = int(loc[0]), int(loc[-1]) + 1
+    contiguous = hi - lo == n            # a subtree of the dissection is a contiguous range of the post-order
+    L0 = scipy.sparse.csr_matrix(F.Lc[lo:hi, lo:hi] if contiguous else F.Lc[loc][:, loc])
     if groups is None:
         groups = _auto_groups(L0, hrow, stage_cap)
     cuts = sorted(set(int(g) for g in groups if 0 <= int(g) < H))
@@ -189,10 +202,14 @@ def _subdomain_levels(F, loc, hrows, blk_of, stage_cap, groups=None):
         np.minimum.at(first, lab, R)
         comp[R] = first[lab]
     order = np.lexsort((np.arange(n), comp, gid))
-    Lp = L0[order][:, order].tocsr()
-    assert scipy.sparse.triu(Lp, k=1).nnz == 0
+    Lp = L0.toarray()[np.ix_(order, order)]                  # dense from here on: a few hundred rows
+    assert not np.any(np.triu(Lp, k=1))
     gid_p, comp_p = gid[order], comp[order]
-    Lh = scipy.sparse.csr_matrix(F.Loff[hrows][:, loc[order]]) if hrows.size else scipy.sparse.csr_matrix((0, n))
+    if hrows.size:
+        Lh = F.Loff[hrows]
+        Lh = (Lh[:, lo:hi] if contiguous else Lh[:, loc]).toarray()[:, order]
+    else:
+        Lh = np.zeros((0, n))
     ident = np.arange(n + hrows.size, dtype=np.int64)
     gstart = np.searchsorted(gid_p, np.arange(n_groups + 1))
     fwd, bwd = [], []
@@ -200,7 +217,7 @@ def _subdomain_levels(F, loc, hrows, blk_of, stage_cap, groups=None):
         a, b = int(gstart[g]), int(gstart[g + 1])
         if a == b:
             continue
-        Linv = scipy.linalg.solve_triangular(Lp[a:b, a:b].toarray(), np.eye(b - a), lower=True)
+        Linv = _tri_inverse(Lp[a:b, a:b])
         cstart = np.flatnonzero(np.concatenate(([True], comp_p[a + 1:b] != comp_p[a:b - 1], [True])))
         chains_f, chains_b, staged_f, staged_b = [], [], [], []
         for ci in range(cstart.size - 1):
@@ -239,9 +256,9 @@ def _subdomain_levels(F, loc, hrows, blk_of, stage_cap, groups=None):
         pf, pb = passes(staged_f, True), passes(staged_b, False)
         inv_f = [chains_f + (pf[0] if pf else [])] + pf[1:]
         inv_b = [chains_b + (pb[0] if pb else [])] + pb[1:]
-        fwd.append((_tiles_sparse(Lp[a:b, :a], a, ident) if a > 0 else [], inv_f))
-        above = scipy.sparse.hstack([Lp[b:, a:b].T, Lh[:, a:b].T]).tocsr() if (b < n or hrows.size) else None
-        bwd.append((_tiles_sparse(above, a, ident[b:]) if above is not None else [], inv_b))
+        fwd.append((_tiles_dense(Lp[a:b, :a], a, ident) if a > 0 else [], inv_f))
+        above = np.concatenate((Lp[b:, a:b].T, Lh[:, a:b].T), axis=1) if (b < n or hrows.size) else None
+        bwd.append((_tiles_dense(above, a, ident[b:]) if above is not None else [], inv_b))
     levels = []
     for (ta, inv) in reversed(bwd):
         levels.append(ta)
@@ -252,7 +269,7 @@ def _subdomain_levels(F, loc, hrows, blk_of, stage_cap, groups=None):
         levels.append(ta)
         levels.extend(inv)
     if hrows.size:
-        levels.append(_tiles_sparse(Lh, n, ident))
+        levels.append(_tiles_dense(Lh, n, ident))
     levels = levels[:n_bwd] + [u for u in levels[n_bwd:] if u]
     return levels, n_bwd, order, cuts
 
@@ -365,7 +382,7 @@ def _upper_program(F, top_rows, tt0, blk_of, RB, KB, n_up_pad):
 
     def block_inv(b0, b1):
         if b0 not in dinv:
-            dinv[b0] = scipy.linalg.solve_triangular(Lt[b0:b1, b0:b1].toarray(), np.eye(b1 - b0), lower=True)
+            dinv[b0] = _tri_inverse(Lt[b0:b1, b0:b1].toarray())
         return dinv[b0]
 
     def phase_a(M, plane_self, plane_cols, row_ranges, col_lo, col_hi):
@@ -575,7 +592,7 @@ def subdomain_plan(F, junc_face, d, NG, n_warps=RES_WARPS, groups=None, tt_max=N
     nTp = plan.n_tt_pad
     if n_tt:
         LTT = F.Lc[tt_rows][:, tt_rows].toarray()
-        Linv = scipy.linalg.solve_triangular(LTT, np.eye(n_tt), lower=True)
+        Linv = _tri_inverse(LTT)
         Sinv = Linv.T @ Linv
         SP = np.zeros((nTp, nTp))
         SP[:n_tt, :n_tt] = Sinv
