@@ -27,6 +27,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 
 #include "jj_host.h"
 
@@ -844,120 +845,101 @@ __device__ void top_product_areg(const SubArgs& a, double* buf, int RB, int KQ, 
 }
 
 // One phase of the upper program (the separators between the subdomains and the dense top of the top): every task is
-// a gathered dense product  out[rows] = V . X[cols]  over the r / z / J planes of the separator rows, for up_RB 8-row
-// tiles and one problem chunk. It is the dense top product with two differences: the B fragments are gathered row by
-// row through the task's column list (row codes plane << 28 | row, prefetched one stage ahead), and the A fragments
-// are the task's own. Tasks of a phase are independent (a grid barrier ends the phase); they are sorted by
-// decreasing cost on the host and dealt to the blocks round-robin, chunk-minor: the blocks that run at the same time
-// apply the SAME A fragments to different problem chunks, so these come from HBM once and hit in L2 afterwards.
+// a gathered dense product  out[rows] = V . X[cols]  over the r / z / J planes of the separator rows, for up to 16
+// 8-row tiles and one problem chunk. The X rows named by the task's column list (row codes plane << 28 | row) are
+// gathered into shared memory in PANELS (cp.async, two buffers: the next panel lands while this one is multiplied),
+// in the swizzled row layout of the local sweeps; warp = (row tile, K slot): a task with T tiles splits the k-steps of
+// a panel over KQ = 16 / pow2ceil(T) warps per tile, the A fragments come straight from global memory (each is used
+// by exactly one warp), and the KQ partial sums of a tile meet in shared memory in a fixed order. Tasks of a phase are
+// independent (a grid barrier ends the phase); they are sorted by decreasing cost on the host and dealt to the
+// blocks round-robin, chunk-minor: the blocks that run at the same time apply the SAME A fragments to different
+// problem chunks, so these come from HBM once and hit in L2 afterwards.
+// buf: the whole dynamic shared memory in front of the amplitude cache (the local vector is idle: with upper phases z
+// always goes through global memory), buf_rows: rows of PC float64 per panel buffer (a multiple of 64).
 template <int NG>
-__device__ void upper_phase(const SubArgs& a, double* buf, int phase) {
+__device__ void upper_phase(const SubArgs& a, double* buf, int buf_rows, int phase) {
     constexpr int PC = 8 * NG;
-    constexpr int GW = NG < 4 ? NG : 4;
-    constexpr int GP = (NG + 3) / 4;
-    constexpr int KM = 2;                              // k-steps per warp and stage (host: subdomain.UP_KM)
-    const int RB = a.up_RB, KB = a.up_KB, KQ = NWARPS / RB;
+    constexpr int PPR = PC / 2;                        // 16-byte pieces per row
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int rtl = warp / KQ, kq = warp % KQ;
-    const int stage_doubles = GW * KB * 32;
-    const int pieces = stage_doubles / 2;              // <= NT: one 16-byte piece per thread and stage
-    const int stage_bytes = a.stage_rows * (PC + 2) * 8;
-    const int S = min(4, stage_bytes / (stage_doubles * 8));
     const int t_lo = __ldg(a.up_phase_ptr + phase), n_t = __ldg(a.up_phase_ptr + phase + 1) - t_lo;
-    const long long n_pairs = (long long)n_t * a.n_chunks * GP;
+    const long long n_pairs = (long long)n_t * a.n_chunks;
     const size_t plane_elems = (size_t)a.n_chunks * a.n_up_pad * PC;
     const unsigned long long pol = policy_evict_last();
+    const int KP = buf_rows / 4;                       // k-steps per panel (a multiple of 16)
+    const int n = lane >> 2, kk = lane & 3;
     for (long long p = blockIdx.x; p < n_pairs; p += gridDim.x) {
-        const int c = (int)(p % a.n_chunks), t = t_lo + (int)((p / a.n_chunks) % n_t), gp = (int)(p / ((long long)a.n_chunks * n_t));
+        const int c = (int)(p % a.n_chunks), t = t_lo + (int)(p / a.n_chunks);
         const int4 hd = __ldg(a.up_task + t);          // out code, rows, k-steps, first column
         const int tiles = (hd.y + 7) >> 3, nk = hd.z;
-        const int nkb = nk / KB;
+        int rbt = 1;
+        while (rbt < tiles) rbt <<= 1;
+        const int KQ = NWARPS / rbt;
+        const int rtl = warp / KQ, kq = warp % KQ;
         const bool active = rtl < tiles;
-        const int i = threadIdx.x;
-        const bool have = i < pieces;
-        const int frag = i / 16, piece = i % 16, gsel = frag / KB, kl = frag % KB;
-        const int gg = min(4 * gp + gsel, NG - 1), kk = piece >> 2, n2 = (piece & 3) * 2;
-        const int* cp = a.up_cols + hd.w + 4 * kl + kk;
-        const double* ubase = a.U + (size_t)c * a.n_up_pad * PC + 8 * gg + n2;
-        const int dofs = frag * 32 + kk * 8 + (n2 ^ ((kk >> 1) << 2));
-        int cnext = have ? __ldg(cp) : 0;
-        int issued = 0, islot = 0;
-        auto issue = [&]() {
-            if (issued < nkb) {
-                const int code = cnext;
-                cp += 4 * KB;
-                ++issued;
-                if (have && issued < nkb) cnext = __ldg(cp);
-                if (have) cp_async16(buf + (size_t)islot * stage_doubles + dofs,
-                                     ubase + (size_t)(code >> 28) * plane_elems + (size_t)(code & 0xfffffff) * PC);
-                if (++islot == S) islot = 0;
+        const int n_panels = (nk + KP - 1) / KP;
+        const int* cols = a.up_cols + hd.w;
+        const double* ubase = a.U + (size_t)c * a.n_up_pad * PC;
+        auto issue_panel = [&](int pp) {
+            const int r0 = pp * buf_rows, nr = min(nk * 4 - r0, buf_rows);
+            double* dst = buf + (size_t)(pp & 1) * buf_rows * PC;
+            for (int e = threadIdx.x; e < nr * PPR; e += NT) {
+                const int r = e / PPR, q = (e % PPR) * 2;
+                const int code = __ldg(cols + r0 + r);
+                cp_async16(dst + velem<NG>(r, q), ubase + (size_t)(code >> 28) * plane_elems + (size_t)(code & 0xfffffff) * PC + q);
             }
             asm volatile("cp.async.commit_group;");
         };
+        __syncthreads();                               // the buffers are free (previous task / phase done)
+        issue_panel(0);
+        double acc[NG][2];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) { acc[g][0] = 0.0; acc[g][1] = 0.0; }
+        // this warp's A fragments: k-steps kq, kq + KQ, ... of row tile rtl
         const double* ap = a.up_A + __ldg(a.up_task_aoff + t) + ((size_t)min(rtl, tiles - 1) * nk + kq) * 32 + lane;
-        double an[KM];
-#pragma unroll
-        for (int m = 0; m < KM; ++m) {
-            asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(an[m]) : "l"(ap + (size_t)m * KQ * 32), "l"(pol));
-        }
-        __syncthreads();                           // the ring is free (previous task / phase done)
-        for (int k = 0; k < S - 1; ++k) issue();
-        double acc[GW][2];
-#pragma unroll
-        for (int g = 0; g < GW; ++g) { acc[g][0] = 0.0; acc[g][1] = 0.0; }
-        const int b_off = kq * 32 + (lane & 3) * 8 + ((lane >> 2) ^ (((lane & 3) >> 1) << 2));   // group g: + g*KB*32
-        const double* st = buf;
-        int cslot = 0;
-        for (int kb = 0; kb < nkb; ++kb) {
-            if (S >= 4) asm volatile("cp.async.wait_group 2;");
-            else if (S == 3) asm volatile("cp.async.wait_group 1;");
+        const size_t astep = (size_t)KQ * 32;
+        for (int pp = 0; pp < n_panels; ++pp) {
+            if (pp + 1 < n_panels) { issue_panel(pp + 1); asm volatile("cp.async.wait_group 1;"); }
             else asm volatile("cp.async.wait_group 0;");
-            __syncthreads();
-            issue();
-            double av[KM];
-#pragma unroll
-            for (int m = 0; m < KM; ++m) av[m] = an[m];
-            ap += (size_t)KB * 32;
-            if (kb + 1 < nkb) {
-#pragma unroll
-                for (int m = 0; m < KM; ++m)
-                    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(an[m]) : "l"(ap + (size_t)m * KQ * 32), "l"(pol));
-            }
+            __syncthreads();                           // panel pp has landed for everyone
             if (active) {
+                const int own = min(nk - pp * KP, KP) / KQ;          // k-steps of this warp in the panel (nk % 16 == 0)
+                const unsigned vb = (unsigned)__cvta_generic_to_shared(buf + (size_t)(pp & 1) * buf_rows * PC);
+                // B fragment of local k-step j: rows 4 j + kk (row & 3 == kk), problems 8 g + n
+                unsigned baddr = vb + (unsigned)(velem<NG>(4 * kq + kk, n) * 8);
+                const unsigned bstep = (unsigned)(4 * KQ * PC * 8);
+#pragma unroll 4
+                for (int j = 0; j < own; ++j) {
+                    double av;
+                    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(av) : "l"(ap), "l"(pol));
+                    ap += astep;
+                    double bv[NG];
 #pragma unroll
-                for (int m = 0; m < KM; ++m) {
-                    double bv[GW];
+                    for (int g = 0; g < NG; ++g) bv[g] = lds_f64(baddr ^ (unsigned)(g << 6));
 #pragma unroll
-                    for (int g = 0; g < GW; ++g) bv[g] = st[b_off + m * KQ * 32 + g * KB * 32];
-#pragma unroll
-                    for (int g = 0; g < GW; ++g) dmma884(acc[g][0], acc[g][1], av[m], bv[g]);
+                    for (int g = 0; g < NG; ++g) dmma884(acc[g][0], acc[g][1], av, bv[g]);
+                    baddr += bstep;
                 }
             }
-            st += stage_doubles;
-            if (++cslot == S) { cslot = 0; st = buf; }
+            __syncthreads();                           // everyone is done with buffer pp & 1
         }
-        asm volatile("cp.async.wait_group 0;");
-        __syncthreads();                           // everyone is done with the ring: reuse it for the partial sums
-        if (active) {
+        // partial sums of the K slots meet in shared memory (buffer 0 is free), fixed order
+        if (active && KQ > 1) {
 #pragma unroll
-            for (int g = 0; g < GW; ++g)
-                *reinterpret_cast<double2*>(buf + ((size_t)(warp * GW + g) * 32 + lane) * 2) = make_double2(acc[g][0], acc[g][1]);
+            for (int g = 0; g < NG; ++g)
+                *reinterpret_cast<double2*>(buf + ((size_t)(warp * NG + g) * 32 + lane) * 2) = make_double2(acc[g][0], acc[g][1]);
         }
-        __syncthreads();
-        const int row = 8 * rtl + (lane >> 2);
+        if (KQ > 1) __syncthreads();
+        const int row = 8 * rtl + n;
         if (active && kq == 0 && row < hd.y) {
             double* obase = a.U + (size_t)(hd.x >> 28) * plane_elems + ((size_t)c * a.n_up_pad + (hd.x & 0xfffffff) + row) * PC;
 #pragma unroll
-            for (int g = 0; g < GW; ++g) {
-                const int gg2 = 4 * gp + g;
-                if (gg2 < NG) {
-                    double2 sum = make_double2(0.0, 0.0);
-                    for (int k2 = 0; k2 < KQ; ++k2) {
-                        const double2 part = *reinterpret_cast<const double2*>(buf + ((size_t)((warp + k2) * GW + g) * 32 + lane) * 2);
-                        sum.x += part.x; sum.y += part.y;
-                    }
-                    *reinterpret_cast<double2*>(obase + 8 * gg2 + 2 * (lane & 3)) = sum;
+            for (int g = 0; g < NG; ++g) {
+                double2 sum = make_double2(acc[g][0], acc[g][1]);
+                for (int k2 = 1; k2 < KQ; ++k2) {
+                    const double2 part = *reinterpret_cast<const double2*>(buf + ((size_t)((warp + k2) * NG + g) * 32 + lane) * 2);
+                    sum.x += part.x; sum.y += part.y;
                 }
+                *reinterpret_cast<double2*>(obase + 8 * g + 2 * kk) = sum;
             }
         }
     }
@@ -998,7 +980,17 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
     int* aux = reinterpret_cast<int*>(ac + 1);
     ProgSmem ps;
     const int n_items = a.P * a.n_chunks;
-    const bool keep_z = n_items <= (int)gridDim.x;     // every block has at most one item: z stays in shared memory
+    // More items than blocks: a block takes a contiguous range of the subdomain-major item list, so its consecutive items
+    // are chunks of the SAME subdomain (its program stays loaded, its factor stream is hot in L2, and the neighbouring
+    // blocks stream the same factor at the same time). Otherwise block b owns item b = (chunk b / P, subdomain b % P).
+    const bool multi = n_items > (int)gridDim.x;
+    const int it_lo = multi ? (int)((long long)blockIdx.x * n_items / gridDim.x) : (int)blockIdx.x;
+    const int it_hi = multi ? (int)((long long)(blockIdx.x + 1) * n_items / gridDim.x) : min(n_items, (int)blockIdx.x + 1);
+    const int n_up = a.n_up_fwd + a.n_up_bwd;
+    // every block has at most one item: z stays in shared memory - unless upper phases run between the sweeps, which
+    // gather their operands into the whole shared memory (two panel buffers of up_rows rows)
+    const bool keep_z = n_items <= (int)gridDim.x && n_up == 0;
+    const int up_rows = (int)((((size_t)a.n_rows * PC + (size_t)a.stage_rows * (PC + 2)) / (2 * PC)) / 64 * 64);
     unsigned bar_target = 0;
     int cur_s = -1;
     // dense top product (top_product_areg): RB row tiles per block so that one round of blocks covers it, the K range
@@ -1006,7 +998,6 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
     // a ring of S stages in the staging rows. Without upper phases and with exactly one item per block the whole top
     // phase is CHUNK-LOCAL: the top rows of a problem chunk are assembled and multiplied by the P blocks of that
     // chunk, and the barriers only join those blocks.
-    const int n_up = a.n_up_fwd + a.n_up_bwd;
     int top_rb = 0, ar_kq = 1, top_ar = 0, ar_s = 0;
     bool chunk_local = false;
     if (a.n_tt > 0) {
@@ -1049,20 +1040,20 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
         if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 4] += tn - tq; tq = tn; }
         top_assemble<NG>(a, n, 0, a.n_chunks, blockIdx.x, gridDim.x);
         grid_barrier(a.bar, bar_target);
-        for (int ph = 0; ph < a.n_up_fwd; ++ph) { upper_phase<NG>(a, stage, ph); grid_barrier(a.bar, bar_target); }
+        for (int ph = 0; ph < a.n_up_fwd; ++ph) { upper_phase<NG>(a, smem, up_rows, ph); grid_barrier(a.bar, bar_target); }
         if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 5] += tn - tq; tq = tn; }
         if (a.n_tt > 0) {
             dense_top(0, a.n_chunks, blockIdx.x, gridDim.x);
             if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 6] += tn - tq; tq = tn; }
             grid_barrier(a.bar, bar_target);
         }
-        for (int ph = a.n_up_fwd; ph < n_up; ++ph) { upper_phase<NG>(a, stage, ph); grid_barrier(a.bar, bar_target); }
+        for (int ph = a.n_up_fwd; ph < n_up; ++ph) { upper_phase<NG>(a, smem, up_rows, ph); grid_barrier(a.bar, bar_target); }
         if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 7] += tn - tq; tq = tn; }
     };
     if (a.dbg_b) {
         // ---- debug: one solve J = S^-1 b through the plan
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const int s = item % a.P, c = item / a.P;
+        for (int item = it_lo; item < it_hi; ++item) {
+            const int s = multi ? item / a.n_chunks : item % a.P, c = multi ? item % a.n_chunks : item / a.P;
             __syncthreads();
             load_prog<NG>(a, s, ps, aux);
             const int nl = a.n_loc[s], nh = a.n_halo[s];
@@ -1079,8 +1070,8 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
             rows_to_global<NG>(v, 0, nl, a.zloc + ((size_t)item * a.n_loc_max) * PC);
         }
         { long long tq = 0; top_phase_grid(0, tq); }
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const int s = item % a.P, c = item / a.P;
+        for (int item = it_lo; item < it_hi; ++item) {
+            const int s = multi ? item / a.n_chunks : item % a.P, c = multi ? item % a.n_chunks : item / a.P;
             __syncthreads();
             load_prog<NG>(a, s, ps, aux);
             const int nl = a.n_loc[s], nh = a.n_halo[s];
@@ -1111,8 +1102,8 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
     for (long long k = 0; k <= a.n; ++k) {
         const long long n = a.i0 + k;
         long long tq = a.prof ? clock64() : 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const int s = item % a.P, c = item / a.P;
+        for (int item = it_lo; item < it_hi; ++item) {
+            const int s = multi ? item / a.n_chunks : item % a.P, c = multi ? item % a.n_chunks : item / a.P;
             if (s != cur_s) { __syncthreads(); load_prog<NG>(a, s, ps, aux); cur_s = s; }
             const int nl = a.n_loc[s], nh = a.n_halo[s];
             amp_fill<PC>(a, ac, c, n - 1);
@@ -1301,9 +1292,8 @@ int subdomain_set_plan(JJHandle* h, const JJSubdomainPlan* pl) {
                  "tt0 + n_tt == n_top < n_up_pad and tt0 + n_tt_pad <= n_up_pad";
         return JJ_EINVAL;
     }
-    if (pl->n_up_fwd + pl->n_up_bwd > 0 &&
-        !((pl->up_RB == 4 || pl->up_RB == 8 || pl->up_RB == 16) && pl->up_KB == 2 * (NWARPS / pl->up_RB))) {
-        h->err = "subdomain plan: upper program needs up_RB in {4, 8, 16} and up_KB == 2 * (16 / up_RB)";
+    if (pl->n_up_fwd + pl->n_up_bwd > 0 && !(pl->up_RB == NWARPS && pl->up_KB == 16)) {
+        h->err = "subdomain plan: upper program must be packed for up_RB == 16 row tiles per task, up_KB == 16";
         return JJ_EINVAL;
     }
     SubState* st = new SubState();
@@ -1325,9 +1315,22 @@ int subdomain_set_plan(JJHandle* h, const JJSubdomainPlan* pl) {
     const int Nj = h->cir.Nj, P = pl->P;
     int rc;
     std::vector<SubProgDev> progs(P);
+    std::map<const void*, int> seen;          // host stream pointer -> first subdomain with that program
     for (int s = 0; s < P; ++s) {
         const JJSubProgram& ps = pl->prog[s];
         if (ps.n_warps != NWARPS) { h->err = "subdomain plan: program packed for a different warp count"; return JJ_EINVAL; }
+        // congruent subdomains (translated copies on a regular lattice) come with the SAME host arrays: one device
+        // copy serves them all, and the shared factor stream stays in L2
+        if (ps.n_steps > 0) {
+            auto it = seen.find((const void*)ps.stream);
+            if (it != seen.end() && pl->prog[it->second].wt_ptr == ps.wt_ptr && pl->prog[it->second].thdr == ps.thdr &&
+                pl->prog[it->second].n_steps == ps.n_steps) {
+                progs[s] = progs[it->second];
+                progs[s].n_bwd = ps.n_bwd;
+                continue;
+            }
+            seen[(const void*)ps.stream] = s;
+        }
         const size_t np = (size_t)ps.n_levels * NWARPS;
         int *wt, *ws, *th, *ls; unsigned char* sb;
         if ((rc = up(h, st, &wt, ps.wt_ptr, 2 * np))) return rc;
@@ -1388,8 +1391,7 @@ int subdomain_set_plan(JJHandle* h, const JJSubdomainPlan* pl) {
         if ((rc = up(h, st, (int**)&st->up_task, pl->up_task, (size_t)pl->n_up_tasks * 4))) return rc;
         if ((rc = up(h, st, (long long**)&st->up_task_aoff, (const long long*)pl->up_task_aoff, (size_t)pl->n_up_tasks))) return rc;
         if ((rc = up(h, st, &st->up_cols, pl->up_cols, (size_t)pl->n_up_cols))) return rc;
-        // the kernel prefetches the A fragments of one stage past the end of a task: pad by one stage
-        if ((rc = up(h, st, &st->up_A, pl->up_A, (size_t)pl->n_up_vals, (size_t)(pl->up_KB + 2) * 32 * sizeof(double)))) return rc;
+        if ((rc = up(h, st, &st->up_A, pl->up_A, (size_t)pl->n_up_vals, (size_t)64 * 32 * sizeof(double)))) return rc;
     }
     if ((rc = up(h, st, &st->junc_ptr, pl->junc_ptr, (size_t)P + 1))) return rc;
     if ((rc = up(h, st, &st->junc_orig, pl->junc_orig, (size_t)Nj))) return rc;

@@ -215,16 +215,16 @@ class CircuitTables:
             + 2 * max(len(ps["thdr"]) for ps in plan.prog) + 10
         return (plan.n_rows * PC + plan.stage_rows * (PC + 2)) * 8 + 64 * PC + 4 * aux
 
-    def subdomain_plan(self, d, NG):
-        key = (d, NG, os.environ.get("JJ_TT_MAX", ""))
+    def subdomain_plan(self, d, NG, n_chunks=1):
+        key = (d, NG, n_chunks, os.environ.get("JJ_TT_MAX", ""))
         if key not in self._subdomain:
-            plan = subdomain_plan(self.factor, self.junc_face, d, NG)
+            plan = subdomain_plan(self.factor, self.junc_face, d, NG, n_chunks=n_chunks)
             face_tables(plan, self.face_ptr, self.face_junc, self.face_sign, self.junc_sign, self.c0)
             self._subdomain[key] = plan
         return self._subdomain[key]
 
     def choose_subdomain(self, W, n_sm=148):
-        """Pick (cut, problem groups NG) for the subdomain engine, or None. cut = None uses the n_parts subtrees
+        """Pick (cut, problem groups NG, problem chunks) for the subdomain engine, or None. cut = None uses the n_parts subtrees
         this ordering was made with (see subdomain_layout); otherwise cut is a tree depth (2^cut subdomains).
         JJ_SUBDOMAIN="cut,NG" overrides ("p,NG" selects the parts)."""
         if self.factor is None:
@@ -232,7 +232,8 @@ class CircuitTables:
         env = os.environ.get("JJ_SUBDOMAIN")
         if env:
             d, NG = env.split(",")
-            return (None if d.strip().startswith("p") else int(d)), int(NG)
+            NG = int(NG)
+            return (None if d.strip().startswith("p") else int(d)), NG, -(-((W + 3) // 4 * 4) // (8 * NG))
         NG, chunks, _ = subdomain_layout(self.Nf, W, n_sm)
         if self.n_parts is not None and self.factor.blk_part is not None:
             cands = [None]
@@ -244,17 +245,17 @@ class CircuitTables:
             cands = [d for d in range(d_hi, 7) if d <= max(max_d - 1, 0)]
         for d in cands:
             try:
-                plan = self.subdomain_plan(d, NG)
+                plan = self.subdomain_plan(d, NG, chunks)
             except ValueError:
                 continue
             if self.subdomain_smem_bytes(plan) <= self.SMEM_LIMIT:
-                return d, NG
+                return d, NG, chunks
         return None
 
 
 _BALANCE_MAX_PARTS = 64
 _ROWS_FIT = 560               # local rows of a subdomain that still fit in 227 KB at 32 problems with a ~15 % halo
-_ROWS_PER_SUBDOMAIN = 450     # target when a circuit has to be cut finer than one subdomain per (SM, chunk) anyway
+_ROWS_MULTI = 520             # most local rows of a subdomain when a block works through several items per time step
 
 
 def subdomain_layout(Nf, W, n_sm=148):
@@ -267,17 +268,14 @@ def subdomain_layout(Nf, W, n_sm=148):
     chunks = (Wp + 8 * NG - 1) // (8 * NG)
     n_parts = max(1, min(n_sm // chunks, Nf // 45))
     # larger circuits: the rows of a subdomain (local + halo) must fit in a block's shared memory, so there are more
-    # (subdomain, chunk) items than SMs and every block loops over several items per time step. With n_sm // k
-    # subdomains the items spread evenly when the chunk count is a multiple of k; k = 1 pins one subdomain to each block.
-    need = -(-Nf // _ROWS_PER_SUBDOMAIN)
-    if Nf <= _ROWS_FIT * n_parts:
-        pass                                        # one item per block and the subdomains fit (cfg2: 545 rows each)
-    elif need > n_parts and need <= n_sm:
-        n_parts = n_sm // max(1, n_sm // need)
-    elif need > n_sm:
-        half = max(1, n_sm // 2)
-        n_parts = -(-need // half) * half           # cfg5: 2 220 subdomains; the separators above them (10^5 rows) are
-                                                    # swept by the upper program, only the last tree levels are dense
+    # (subdomain, chunk) items than SMs and every block loops over several items per time step
+    if Nf > _ROWS_FIT * n_parts:
+        # a power of two: every cut of the dissection is then a median cut, so a regular lattice falls into a handful
+        # of congruent subdomain shapes whose sweep programs are shared (subdomain._subdomain_inputs): less host
+        # setup, and the shared factor streams stay in L2
+        n_parts = 1
+        while Nf > _ROWS_MULTI * n_parts:
+            n_parts *= 2
     return NG, chunks, n_parts
 
 
@@ -392,10 +390,10 @@ class DeviceEngine:
         s.tile_stage_off = _lib.i32(sw["tile_stage_off"])
         return s
 
-    def set_subdomain(self, d, NG):
+    def set_subdomain(self, d, NG, n_chunks=1):
         """Upload the subdomain-engine plan for cut depth d (None: the n_parts subtrees of the ordering) and NG
-        groups of 8 problems per chunk."""
-        plan = self.tab.subdomain_plan(d, NG)
+        groups of 8 problems per chunk (n_chunks: the chunk count the upper program is sized for)."""
+        plan = self.tab.subdomain_plan(d, NG, n_chunks)
         p = _lib.JJSubdomainPlan()
         p.P, p.NG, p.n_rows, p.n_loc_max, p.stage_rows = plan.P, plan.NG, plan.n_rows, plan.n_loc_max, plan.stage_rows
         p.n_top, p.n_up_pad, p.n_slots = plan.n_top, plan.n_up_pad, plan.n_slots
@@ -428,8 +426,13 @@ class DeviceEngine:
         p.n_up_cols, p.up_cols = up["cols"].size, a32(up["cols"])
         p.n_up_vals, p.up_A = up["A"].size, a64f(up["A"])
 
+        memo = {}
+
         def sub_prog(ps, n_bwd):
-            r = _lib.JJSubProgram()
+            # congruent subdomains share one program object: hand the library the same host pointers, it uploads them once
+            if id(ps) in memo:
+                return memo[id(ps)]
+            r = memo[id(ps)] = _lib.JJSubProgram()
             r.n_levels, r.n_bwd, r.n_warps, r.n_tiles = ps["n_levels"], int(n_bwd), ps["n_warps"], len(ps["thdr"])
             r.wt_ptr, r.ws_ptr, r.thdr, r.lstaged = a32(ps["wt_ptr"]), a32(ps["ws_ptr"]), a32(ps["thdr"]), a32(ps["lstaged"])
             r.n_steps = ps["n_steps"]
@@ -446,7 +449,7 @@ class DeviceEngine:
         p.face_K = plan.face_K
         p.face_ell_j, p.face_ell_c, p.face_fidx = a32(plan.face_ell_j), a64f(plan.face_ell_c), a32(plan.face_fidx)
         self._ck(self.lib.jj_set_subdomain_plan(self.h, C.byref(p)))
-        self.subdomain_config = (d, NG)
+        self.subdomain_config = (d, NG, n_chunks)
 
     def debug_subdomain_solve(self, b):
         bp = _lib.c_f64(np.asarray(b)[self.tab.perm])

@@ -59,11 +59,29 @@ class Factor:
         self.depth = None         # cut-tree depth of the block
         self.dom = None           # cut-tree path of the block
         self.dinv = None          # list: inverse of the diagonal block (dense lower triangular)
-        self.Loff = None          # CSR: Lc without the diagonal blocks  (row i: couplings to earlier blocks)
-        self.LoffT = None         # CSR: its transpose                   (row j: couplings to later blocks)
+        self._Loff = None         # CSR: Lc without the diagonal blocks  (row i: couplings to earlier blocks)
+        self._LoffT = None        # CSR: its transpose                   (row j: couplings to later blocks)
         self.nnz_L = 0
         self.blk_part = None      # part (subtree) of each block when the ordering was made with n_parts
         self.Lc = None            # CSR: the full Cholesky factor (subdomain engine: Schur complement of the top separators)
+        self.Sp = None            # CSR: the permuted system matrix
+
+    @property
+    def Loff(self):
+        if self._Loff is None:
+            blk_of = np.repeat(np.arange(self.nb), np.diff(self.bptr))
+            coo = scipy.sparse.tril(self.Lc, k=-1).tocoo()
+            keep = blk_of[coo.row] != blk_of[coo.col]
+            self._Loff = scipy.sparse.csr_matrix((coo.data[keep], (coo.row[keep], coo.col[keep])), shape=(self.n, self.n))
+            self._Loff.sort_indices()
+        return self._Loff
+
+    @property
+    def LoffT(self):
+        if self._LoffT is None:
+            self._LoffT = self.Loff.T.tocsr()
+            self._LoffT.sort_indices()
+        return self._LoffT
 
     @property
     def nb(self):
@@ -95,19 +113,17 @@ def factorize(S, cx, cy, leaf_size=8, n_parts=None, part_weights=None):
     d = lu.U.diagonal()
     if not np.all(d > 0):
         raise RuntimeError("system matrix is not positive definite")
-    Lc = (lu.L @ scipy.sparse.diags(np.sqrt(d))).tocsr()       # Cholesky factor
+    # Cholesky factor Lc = L diag(sqrt(d)): scale the columns of the unit lower factor in place, then one CSC -> CSR
+    Lcsc = lu.L.tocsc()
+    Lcsc.data *= np.repeat(np.sqrt(d), np.diff(Lcsc.indptr))
+    Lc = Lcsc.tocsr()
     Lc.sort_indices()
     F.nnz_L = int(Lc.nnz)
     F.Lc = Lc
-    nb = F.nb
+    F.Sp = Sp.tocsr()          # the permuted system matrix (subdomain.py recognises congruent subdomains by it)
+    F.Sp.sort_indices()
     F.dinv = None              # inverses of the diagonal blocks: only the streaming program needs them (block_inverses)
-    blk_of = np.repeat(np.arange(nb), np.diff(bptr))
-    coo = scipy.sparse.tril(Lc, k=-1).tocoo()
-    keep = blk_of[coo.row] != blk_of[coo.col]
-    F.Loff = scipy.sparse.csr_matrix((coo.data[keep], (coo.row[keep], coo.col[keep])), shape=(n, n))
-    F.Loff.sort_indices()
-    F.LoffT = F.Loff.T.tocsr()
-    F.LoffT.sort_indices()
+    F._Loff = F._LoffT = None  # Lc without its diagonal blocks: built on first use (streaming program)
     return F
 
 

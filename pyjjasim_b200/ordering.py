@@ -98,7 +98,15 @@ def nested_dissection(S, cx, cy, leaf_size=24, return_tree=False, n_parts=None, 
         p_lo = parts // 2
         frac = (wcum[pos0 + p_lo] - wcum[pos0]) / np.maximum(wcum[pos0 + parts] - wcum[pos0], 1e-300)
         lo_count = np.where(parts > 1, np.rint(size * frac).astype(np.int64), (size + 1) // 2)
-        half[idx] = rank >= lo_count[d]
+        # cut at a coordinate VALUE (that of the first unknown of the upper half): unknowns that share it stay on one
+        # side, so on a lattice the cut runs along a lattice line, separators are straight and congruent regions get
+        # congruent orderings; a domain whose lower half would end up empty is cut by rank instead
+        first_hi = order[np.minimum(start + np.minimum(lo_count, np.maximum(size - 1, 0)), idx.size - 1)]
+        cut_val = coord[first_hi]
+        by_val = coord >= cut_val[d]
+        n_lo = np.bincount(d, weights=~by_val, minlength=n_dom)
+        use_val = (n_lo > 0)[d]
+        half[idx] = np.where(use_val, by_val, rank >= lo_count[d])
         # separator: unknowns of the lower half coupled to the upper half of the same subdomain
         both = active[ei] & active[ej]
         e1, e2 = ei[both], ej[both]

@@ -26,6 +26,7 @@ A subdomain's shared-memory vector has rows [0, n_loc) = its local faces (ascend
 rows [n_loc, n_loc + n_halo) = its halo rows (ascending top index); a row holds PC float64 as 32-byte chunks
 of 4 problems, chunk c of row r is stored at chunk position c ^ (r & 3) (bank-conflict-free tensor-core gathers).
 """
+import hashlib
 import os
 
 import numpy as np
@@ -158,9 +159,42 @@ def _tiles_dense(M, row0, col_index, flags=TILE_SELF):
     return units
 
 
-def _subdomain_levels(F, loc, hrows, blk_of, stage_cap, groups=None):
+def _subdomain_inputs(F, loc, hrows, blk_of):
+    """What the sweep program of a subdomain depends on: tree heights of its rows, its block of the factor (CSR) and
+    the factor rows of its halo (dense, local columns in the order of loc), plus a digest of all three. Two subdomains
+    with equal digests (the translated copies of a regular lattice) share one program - on the host and on the
+    device, where the shared stream stays in L2."""
+    n = loc.size
+    hrow = F.height[blk_of[loc]].astype(np.int64)
+    lo, hi = int(loc[0]), int(loc[-1]) + 1
+    contiguous = hi - lo == n            # a subtree of the dissection is a contiguous range of the post-order
+    L0 = scipy.sparse.csr_matrix(F.Lc[lo:hi, lo:hi] if contiguous else F.Lc[loc][:, loc])
+    if hrows.size:
+        Lh = F.Lc[hrows]                 # separator rows: their local columns are off-block entries of the factor
+        Lh = (Lh[:, lo:hi] if contiguous else Lh[:, loc]).toarray()
+    else:
+        Lh = np.zeros((0, n))
+    # digest of the SYSTEM matrix blocks that determine (L0, Lh) - L0 is the Cholesky factor of S[loc, loc] and
+    # Lh = S[halo, loc] L0^-T, a leaf subtree being eliminated before everything it touches - and of the row heights.
+    # The factor values themselves differ in the last bit between congruent subdomains (summation orders inside the
+    # supernodal factorisation), the matrix entries do not.
+    S0 = F.Sp[lo:hi, lo:hi] if contiguous else F.Sp[loc][:, loc]
+    h = hashlib.blake2b(digest_size=16)
+    for arr in (hrow, S0.indptr, S0.indices, S0.data, L0.indptr, L0.indices, Lh != 0):
+        h.update(np.ascontiguousarray(arr).view(np.uint8).data)
+    if hrows.size:
+        Sh = F.Sp[hrows]
+        Sh = Sh[:, lo:hi] if contiguous else Sh[:, loc]
+        for arr in (Sh.indptr, Sh.indices, Sh.data):
+            h.update(np.ascontiguousarray(arr).view(np.uint8).data)
+    h.update(np.array(Lh.shape, dtype=np.int64).tobytes())
+    return hrow, L0, Lh, h.digest()
+
+
+def _subdomain_levels(hrow, L0, Lh, stage_cap, groups=None):
     """
-    Sweep program of one subdomain as a list of levels (each a list of units of 8-row tiles).
+    Sweep program of one subdomain as a list of levels (each a list of units of 8-row tiles); the arguments come
+    from _subdomain_inputs.
 
     The local tree levels are collected into a few GROUPS of consecutive heights. Inside a group the
     triangular solve is replaced by the explicit inverse of the group's diagonal part (a block-diagonal matrix:
@@ -177,14 +211,11 @@ def _subdomain_levels(F, loc, hrows, blk_of, stage_cap, groups=None):
     The local rows are renumbered: by group, then by block of the group's inverse, so every dense block is a
     contiguous row range. Returns (levels, n_bwd, order, group_bounds); order[i] = index into loc of local row i.
     """
-    n = loc.size
+    n = hrow.size
     if n == 0:
         return [], 0, np.zeros(0, dtype=np.int64), []
-    hrow = F.height[blk_of[loc]].astype(np.int64)
+    n_halo = Lh.shape[0]
     H = int(hrow.max())
-    lo, hi = int(loc[0]), int(loc[-1]) + 1
-    contiguous = hi - lo == n            # a subtree of the dissection is a contiguous range of the post-order
-    L0 = scipy.sparse.csr_matrix(F.Lc[lo:hi, lo:hi] if contiguous else F.Lc[loc][:, loc])
     if groups is None:
         groups = _auto_groups(L0, hrow, stage_cap)
     cuts = sorted(set(int(g) for g in groups if 0 <= int(g) < H))
@@ -205,12 +236,8 @@ def _subdomain_levels(F, loc, hrows, blk_of, stage_cap, groups=None):
     Lp = L0.toarray()[np.ix_(order, order)]                  # dense from here on: a few hundred rows
     assert not np.any(np.triu(Lp, k=1))
     gid_p, comp_p = gid[order], comp[order]
-    if hrows.size:
-        Lh = F.Loff[hrows]
-        Lh = (Lh[:, lo:hi] if contiguous else Lh[:, loc]).toarray()[:, order]
-    else:
-        Lh = np.zeros((0, n))
-    ident = np.arange(n + hrows.size, dtype=np.int64)
+    Lh = Lh[:, order]
+    ident = np.arange(n + n_halo, dtype=np.int64)
     gstart = np.searchsorted(gid_p, np.arange(n_groups + 1))
     fwd, bwd = [], []
     for g in range(n_groups):
@@ -257,7 +284,7 @@ def _subdomain_levels(F, loc, hrows, blk_of, stage_cap, groups=None):
         inv_f = [chains_f + (pf[0] if pf else [])] + pf[1:]
         inv_b = [chains_b + (pb[0] if pb else [])] + pb[1:]
         fwd.append((_tiles_dense(Lp[a:b, :a], a, ident) if a > 0 else [], inv_f))
-        above = np.concatenate((Lp[b:, a:b].T, Lh[:, a:b].T), axis=1) if (b < n or hrows.size) else None
+        above = np.concatenate((Lp[b:, a:b].T, Lh[:, a:b].T), axis=1) if (b < n or n_halo) else None
         bwd.append((_tiles_dense(above, a, ident[b:]) if above is not None else [], inv_b))
     levels = []
     for (ta, inv) in reversed(bwd):
@@ -268,7 +295,7 @@ def _subdomain_levels(F, loc, hrows, blk_of, stage_cap, groups=None):
     for (ta, inv) in fwd:
         levels.append(ta)
         levels.extend(inv)
-    if hrows.size:
+    if n_halo:
         levels.append(_tiles_dense(Lh, n, ident))
     levels = levels[:n_bwd] + [u for u in levels[n_bwd:] if u]
     return levels, n_bwd, order, cuts
@@ -292,7 +319,8 @@ def _auto_groups(L0, hrow, stage_cap):
 
 UP_PLANE_SHIFT = 28                     # row code of the upper program: plane << 28 | row
 PLANE_R, PLANE_Z, PLANE_J = 0, 1, 2     # right-hand side / forward result / solution of the separator rows
-UP_KM = 2                               # k-steps per warp and pipeline stage of the upper phases
+UP_TILES = 16                           # most 8-row tiles of a task of the upper program (one warp each)
+UP_KSTEPS = 16                          # k-steps of a task are padded to a multiple of this (any K split 16 / 2^i works)
 
 
 def _up_code(plane, rows):
@@ -304,10 +332,11 @@ class _UpperBuilder:
     A task computes  out[rows] = V . X[cols]  for at most 8 * RB consecutive rows of one plane; its A fragments are
     stored per 8-row tile as [k-step][lane = row * 4 + kk] = V[row, 4 k + kk]."""
 
-    def __init__(self, RB, KB, pad_code):
-        self.RB, self.KB, self.pad_code = RB, KB, pad_code
+    def __init__(self, pad_code):
+        self.RB, self.KB, self.pad_code = UP_TILES, UP_KSTEPS, pad_code
         self.phases = []                 # list of lists of (cost, out code, rows, nk, cols, A)
         self.cur = None
+        self.nnz = self.stored = 0       # factor entries applied / values stored (padding, unions of column sets)
 
     def begin_phase(self):
         self.cur = []
@@ -322,6 +351,8 @@ class _UpperBuilder:
         assert 1 <= nr <= 8 * self.RB and K == len(col_codes) and K > 0
         nk = -(-K // (4 * self.KB)) * self.KB
         tiles = -(-nr // 8)
+        self.nnz += int(np.count_nonzero(V))
+        self.stored += tiles * 8 * nk * 4
         A = np.zeros((tiles * 8, nk * 4))
         A[:nr, :K] = V
         A = np.ascontiguousarray(A.reshape(tiles, 8, nk, 4).transpose(0, 2, 1, 3)).ravel()
@@ -343,7 +374,7 @@ class _UpperBuilder:
                 vo += A.size
             phase_ptr.append(len(hdr))
         assert co < 2 ** 31
-        return dict(RB=self.RB, KB=self.KB, n_fwd=n_fwd, n_bwd=len(self.phases) - n_fwd,
+        return dict(RB=self.RB, KB=self.KB, n_fwd=n_fwd, n_bwd=len(self.phases) - n_fwd, nnz=self.nnz, stored=self.stored,
                     phase_ptr=np.asarray(phase_ptr, dtype=np.int32),
                     task=np.asarray(hdr, dtype=np.int32).reshape(-1, 4),
                     task_aoff=np.asarray(aoff, dtype=np.int64),
@@ -351,7 +382,16 @@ class _UpperBuilder:
                     A=np.concatenate(vals) if vals else np.zeros(0))
 
 
-def _upper_program(F, top_rows, tt0, blk_of, RB, KB, n_up_pad):
+def _phase_rows(blocks, n_chunks, n_sm=148):
+    """Rows per task for the separator blocks of one tree depth: as many as 16 warps can take (128), fewer when that
+    would leave SMs without a (task, chunk) pair - near the root there are few, large blocks."""
+    for rb in (16, 8, 4):
+        if sum(-(-(b1 - b0) // (8 * rb)) for (b0, b1) in blocks) * n_chunks >= 2 * n_sm:
+            return 8 * rb
+    return 16
+
+
+def _upper_program(F, top_rows, tt0, blk_of, n_chunks, n_up_pad):
     """
     Sweep program of the UPPER separators (top rows [0, tt0) in the top numbering) and the elimination of the dense
     top of the top (rows [tt0, n_top)) from them. Separator blocks of one tree depth are mutually independent, so a
@@ -364,7 +404,7 @@ def _upper_program(F, top_rows, tt0, blk_of, RB, KB, n_up_pad):
                                 b)  J_B = inv(L[B, B])^T t_B           (z -> J plane)
     """
     n_top = top_rows.size
-    ub = _UpperBuilder(RB, KB, int(_up_code(PLANE_R, n_up_pad - 1)))
+    ub = _UpperBuilder(int(_up_code(PLANE_R, n_up_pad - 1)))
     if tt0 == 0:
         return ub.finish(0)
     Lt = F.Lc[top_rows][:, top_rows].tocsr()
@@ -377,7 +417,6 @@ def _upper_program(F, top_rows, tt0, blk_of, RB, KB, n_up_pad):
     ends = np.concatenate((starts[1:], [tt0]))
     bdepth = F.depth[bu[starts]].astype(np.int64)
     depths = np.unique(bdepth)
-    RT = 8 * RB
     dinv = {}
 
     def block_inv(b0, b1):
@@ -400,6 +439,7 @@ def _upper_program(F, top_rows, tt0, blk_of, RB, KB, n_up_pad):
         ub.end_phase()
 
     def groups_of(blocks):
+        RT = _phase_rows(blocks, n_chunks)
         return [(r0, min(b1, r0 + RT), b0, b1) for (b0, b1) in blocks for r0 in range(b0, b1, RT)]
 
     # ---- forward
@@ -423,6 +463,7 @@ def _upper_program(F, top_rows, tt0, blk_of, RB, KB, n_up_pad):
             ub.task(PLANE_Z, r0, Di[r0 - b0:r1 - b0, :r1 - b0], _up_code(PLANE_R, np.arange(b0, r1)))
         ub.end_phase()
     if n_top > tt0:
+        RT = _phase_rows([(tt0, n_top)], n_chunks)
         phase_a(Lt, PLANE_R, PLANE_Z, [(r0, min(n_top, r0 + RT)) for r0 in range(tt0, n_top, RT)], 0, tt0)
     n_fwd = len(ub.phases)
     # ---- backward
@@ -448,7 +489,7 @@ def _upper_program(F, top_rows, tt0, blk_of, RB, KB, n_up_pad):
     return ub.finish(n_fwd)
 
 
-def subdomain_plan(F, junc_face, d, NG, n_warps=RES_WARPS, groups=None, tt_max=None, up_rb=4):
+def subdomain_plan(F, junc_face, d, NG, n_warps=RES_WARPS, groups=None, tt_max=None, n_chunks=1):
     """
     F         : factor.Factor of the permuted cycle-space system
     junc_face : (Nj, 2) permuted faces of every junction, -1 none (CircuitTables.junc_face)
@@ -457,7 +498,8 @@ def subdomain_plan(F, junc_face, d, NG, n_warps=RES_WARPS, groups=None, tt_max=N
     groups    : tree heights after which a new level group starts (see _subdomain_levels); None = automatic
     tt_max    : the tree levels nearest the root whose rows number at most this many are solved by ONE dense inverse
                 (the top of the top); the separators between them and the subdomains get the upper program
-    up_rb     : 8-row tiles per task of the upper program
+    n_chunks  : problem chunks the plan will run with (sizes the tasks of the upper program: a phase wants at least
+                two (task, chunk) pairs per SM)
     """
     assert NG in (1, 2, 4, 8)
     n, nb = F.n, F.nb
@@ -490,14 +532,15 @@ def subdomain_plan(F, junc_face, d, NG, n_warps=RES_WARPS, groups=None, tt_max=N
     tix = np.full(n, -1, dtype=np.int64)
     tix[top_rows] = np.arange(n_top)
 
-    # (subdomain, top row) couplings through the factor
-    coo = F.Loff.tocoo()
-    rs_r, rs_c = row_sub[coo.row], row_sub[coo.col]
-    assert not np.any((rs_r >= 0) & (rs_c < 0)), "a local row precedes one of its separators"
-    assert not np.any((rs_r >= 0) & (rs_c >= 0) & (rs_r != rs_c)), "two subdomains are coupled"
-    m = (rs_r < 0) & (rs_c >= 0)
+    # (subdomain, top row) couplings through the factor: entries of the top rows of Lc in local columns
+    # (local rows only ever couple to their own subdomain: every subdomain is a subtree of the elimination tree)
+    Ltr = F.Lc[top_rows]
+    tr_row = np.repeat(np.arange(n_top), np.diff(Ltr.indptr))
+    rs_c = row_sub[Ltr.indices]
+    m = rs_c >= 0
     nt1 = max(n_top, 1)
-    lkeys = np.unique(rs_c[m] * nt1 + tix[coo.row[m]])
+    lkeys = np.unique(rs_c[m] * nt1 + tr_row[m])
+    del Ltr, tr_row, rs_c, m
     # subdomains coupled to each top row (CSR), for the junctions that lie between two top faces
     lk_s, lk_k = lkeys // nt1, lkeys % nt1
     o = np.argsort(lk_k, kind="stable")
@@ -571,12 +614,24 @@ def subdomain_plan(F, junc_face, d, NG, n_warps=RES_WARPS, groups=None, tt_max=N
         raise ValueError("subdomain plan: the right-hand sides leave no room for the staging rows")
     stage_cap = min(stage_cap, 4096)
     vrow_loc = np.full(n, -1, dtype=np.int64)            # shared-memory row of every local face in its subdomain
+    cache = {}                                           # digest of a subdomain's inputs -> its program
     for s in range(P):
-        levels, n_bwd, order, gb = _subdomain_levels(F, loc[s], top_rows[halo[s]], blk_of, stage_cap, groups)
+        hrow, L0, Lh, digest = _subdomain_inputs(F, loc[s], top_rows[halo[s]], blk_of)
+        hit = cache.get(digest)
+        if hit is not None:
+            # congruent to an earlier subdomain: its factor blocks must agree to rounding (guards the digest)
+            scale = 1e-12 * float(np.max(np.abs(L0.data)))
+            if np.max(np.abs(hit[4] - L0.data)) > scale or (Lh.size and np.max(np.abs(hit[5] - Lh)) > scale):
+                hit = None
+        if hit is None:
+            levels, n_bwd, order, gb = _subdomain_levels(hrow, L0, Lh, stage_cap, groups)
+            hit = cache[digest] = (_pack_levels(levels, NG, n_warps, n_bwd), n_bwd, order, gb, L0.data, Lh)
+        prog, n_bwd, order, gb = hit[:4]
         vrow_loc[loc[s][order]] = np.arange(loc[s].size)
-        plan.prog.append(_pack_levels(levels, NG, n_warps, n_bwd))
+        plan.prog.append(prog)
         plan.n_bwd.append(n_bwd)
         plan.group_bounds.append(gb)
+    plan.n_distinct_programs = len(cache)
     plan.vrow_loc = vrow_loc
     plan.n_bwd = np.asarray(plan.n_bwd, dtype=np.int32)
     plan.stage_rows = max(p["stage_rows"] for p in plan.prog)
@@ -602,9 +657,11 @@ def subdomain_plan(F, junc_face, d, NG, n_warps=RES_WARPS, groups=None, tt_max=N
         plan.Sinv = np.zeros((0, 0))
         plan.Sinv_packed = np.zeros(0)
     # ---- upper separators between the subdomains and the top of the top
-    RB = int(up_rb)
-    assert RB in (1, 2, 4, 8, 16)
-    plan.upper = _upper_program(F, top_rows, tt0, blk_of, RB, (16 // RB) * UP_KM, plan.n_up_pad)
+    plan.upper = _upper_program(F, top_rows, tt0, blk_of, max(1, int(n_chunks)), plan.n_up_pad)
+    if plan.upper["n_fwd"] + plan.upper["n_bwd"] > 0:
+        # the upper phases gather into two panel buffers of at least 64 rows and reduce over 16 warps in shared memory
+        need = max(2 * 64 * PC, 16 * NG * 64) - plan.n_rows * PC
+        plan.stage_rows = max(plan.stage_rows, -(-need // (PC + 2)))
     # assembly of r_top: slots (subdomain halo rows) of every top row
     order = np.argsort(plan.halo_top, kind="stable")
     plan.tslot = order.astype(np.int32)

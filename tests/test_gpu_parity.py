@@ -149,7 +149,7 @@ def test_subdomain_solve_matches_direct_solve(cfg, W):
 
 
 @pytest.mark.parametrize("tt_max", ["0", "40", "150"])
-@pytest.mark.parametrize("cfg,W", [("3,4", 70), ("4,1", 13), ("4,2", 40), ("5,4", 33), ("p24,4", 100), ("p7,8", 64)])
+@pytest.mark.parametrize("cfg,W", [("3,4", 70), ("4,1", 13), ("4,2", 40), ("5,4", 33), ("p24,4", 100), ("p7,2", 64), ("5,8", 64)])
 def test_subdomain_solve_through_upper_phases(cfg, W, tt_max, monkeypatch):
     # the separators between the subdomains and the dense top of the top are swept by the upper program (gathered
     # dense products, two phases per tree depth); tt_max = 0: no dense part at all
@@ -374,7 +374,8 @@ def test_full_size_cfg2_invariants_and_chunking():
 
 def test_full_size_cfg4_share_invariants():
     # BASELINE config 4 (SquareArray(256,256) with capacitance, DC + AC drive) with one GPU's share of 512 problems:
-    # 148 subdomains, 16 items per block, dense top of ~5 800 rows; a few steps, then the invariants
+    # 128 subdomains, ~14 items per block, ~5 500 separator rows above them (upper program + dense top of the top);
+    # a few steps, then the invariants
     a = pj.SquareArray(256, 256)
     a.set_capacitance(1.0)
     W, Nt, dt = 512, 6, 0.05
@@ -386,7 +387,7 @@ def test_full_size_cfg4_share_invariants():
                                   store_voltage=False).compute()
     from pyjjasim_b200 import engine
     st = engine.last_run_stats[0]
-    assert st["engine"] == 3 and st["cluster_size"] == 148
+    assert st["engine"] == 3 and st["cluster_size"] == engine.subdomain_layout(a._Nf(), W, engine._sm_count(0))[2]
     flux, kcl = _flux_and_kcl(a, res, 0.05, Is(Nt - 1))
     assert flux < 1e-10 and kcl < 1e-9
 

@@ -131,9 +131,11 @@ def test_subdomain_plan_with_uneven_dissection(ctor, args, n_parts, NG):
     part = np.asarray(tab.factor.blk_part)
     sizes = np.diff(tab.factor.bptr)
     rows = np.array([sizes[part == k].sum() for k in range(part.max() + 1)])
-    assert part.max() + 1 == n_parts and (a._Nf() < 500 or rows.min() >= 0.6 * rows.max())
+    # (cuts run along lattice lines: on a tiny lattice a domain can get too small to be cut into all its parts)
+    n_got = part.max() + 1
+    assert (n_got == n_parts or (a._Nf() < 200 and n_parts - 1 <= n_got <= n_parts)) and (a._Nf() < 500 or rows.min() >= 0.6 * rows.max())
     plan = tab.subdomain_plan(None, NG)
-    assert plan.P == n_parts
+    assert plan.P == n_got
     S = system_matrix(a.get_cycle_matrix(), a._L(), tab.Rv, tab.Cv)
     b = rng.randn(a._Nf(), plan.PC)
     Jp = apply_subdomain_plan_host(plan, b[tab.perm])
@@ -334,11 +336,10 @@ def test_subdomain_layout_rules():
     from pyjjasim_b200.engine import subdomain_layout
     assert subdomain_layout(9801, 256) == (4, 8, 18)          # cfg2: one (subdomain, chunk) item per block, 144 blocks
     assert subdomain_layout(361, 32) == (4, 1, 8)             # cfg1: no subdomain smaller than ~45 faces
-    NG, chunks, P = subdomain_layout(65025, 512)              # cfg4 per GPU: cut finer than one item per block
-    assert (NG, chunks, P) == (4, 16, 148) and 65025 / P <= 450
-    NG, chunks, P = subdomain_layout(79401, 512)              # cfg3: more subdomains than SMs, in units of half the SM count
-    assert P == 222 and 79401 / P <= 450
-    assert subdomain_layout(998001, 64) == (4, 2, 2220)       # cfg5: 30 items per block; 10^5 separator rows above them
+    # larger circuits: several items per block, a power of two of subdomains (median cuts: congruent shapes share programs)
+    assert subdomain_layout(65025, 512) == (4, 16, 128)       # cfg4 per GPU
+    assert subdomain_layout(79401, 512) == (4, 16, 256)       # cfg3
+    assert subdomain_layout(998001, 64) == (4, 2, 2048)       # cfg5: 28 items per block; 10^5 separator rows above them
     assert subdomain_layout(100, 8) == (1, 1, 2)
 
 
