@@ -100,12 +100,15 @@ typedef struct {
     const double  *Sinv_packed;      /* [n_tt_pad/8][n_tt_pad/4][8][4] MMA A fragments of the inverse Schur complement */
     /* upper program: phases [0, n_up_fwd) run after the top assembly, phases [n_up_fwd, n_up_fwd + n_up_bwd) after the
      * dense product; a grid barrier separates phases. A task computes out[rows] = V . X[cols] for up_RB 8-row tiles. */
-    int32_t up_RB, up_KB;            /* row tiles per task; k-steps (of 4 columns) per pipeline stage: nk % up_KB == 0 */
+    int32_t up_RB, up_KB;            /* most 8-row tiles of a task (16); the k-steps nk of a task are a multiple of up_KB (16) */
     int32_t n_up_fwd, n_up_bwd, n_up_tasks;
-    const int32_t *up_phase_ptr;     /* [n_up_fwd + n_up_bwd + 1] first task of each phase (tasks sorted by cost) */
+    const int32_t *up_phase_ptr;     /* [n_up_fwd + n_up_bwd + 1] first task of each phase */
+    const int32_t *up_phase_split;   /* [n_up_fwd + n_up_bwd + 1] tasks [ptr, split) of a phase are run by whole thread blocks
+                                        (sorted by decreasing cost), tasks [split, next ptr) by single warps (<= 4 tiles) */
     const int32_t *up_task;          /* [n_up_tasks][4]: out code, rows (1..8*up_RB), nk, first column (index into up_cols) */
     const int64_t *up_task_aoff;     /* [n_up_tasks] offset of the task's A fragments in up_A (float64 units) */
-    int64_t n_up_cols; const int32_t *up_cols;   /* row codes: plane << 28 | row, plane 0 = r, 1 = z, 2 = J */
+    int64_t n_up_cols; const int32_t *up_cols;   /* row codes: plane << 28 | row, plane 0 = r, 1 = z, 2 = J, 3 = scratch (partial
+                                                    products of column-split tasks, summed by a phase of their own) */
     int64_t n_up_vals; const double *up_A;       /* per task [row tile][nk][32]: lane = row*4 + kk holds V[row][4k + kk] */
     const JJSubProgram *prog;        /* [P] */
     const int32_t *junc_ptr;         /* [P+1] subdomain s owns device junctions junc_ptr[s]:junc_ptr[s+1] */
@@ -148,6 +151,9 @@ int jj_set_subdomain_plan(JJHandle *h, const JJSubdomainPlan *plan);
 /* W problems, time step dt, Philox seed, index of this shard's first problem in the global batch
  * (keeps noise identical however the batch is sharded over GPUs; must be a multiple of 4) */
 int jj_set_problem(JJHandle *h, int32_t W, double dt, uint64_t seed, int64_t problem_offset, int32_t engine);
+/* change the step engine of the current problem between two jj_run calls; the state is handed over on the device
+ * (the host does this when a callable input stops being of the form base x amplitude and must be uploaded densely) */
+int jj_set_engine(JJHandle *h, int32_t engine);
 /* theta(-1), theta(-2): (Nj, W) host arrays (reference: time_evolution.py:480,490; config_at_minus_1/2) */
 int jj_set_state(JJHandle *h, const double *theta_m1, const double *theta_m2);
 int jj_get_state(JJHandle *h, double *theta_m1, double *theta_m2);

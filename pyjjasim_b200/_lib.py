@@ -17,7 +17,7 @@ JJ_KIND_ZERO, JJ_KIND_RANK1, JJ_KIND_DENSE = 0, 1, 2
 JJ_ENGINE_AUTO, JJ_ENGINE_STREAMING, JJ_ENGINE_SUBDOMAIN = 0, 1, 3
 JJ_ENONFINITE = -5
 
-EXPORTS = ["jj_create", "jj_destroy", "jj_last_error", "jj_set_circuit", "jj_set_solver", "jj_set_problem",
+EXPORTS = ["jj_create", "jj_destroy", "jj_last_error", "jj_set_circuit", "jj_set_solver", "jj_set_problem", "jj_set_engine",
            "jj_set_state", "jj_get_state", "jj_set_source", "jj_upload_source", "jj_upload_noise",
            "jj_alloc_outputs", "jj_run", "jj_fetch_theta", "jj_fetch_current", "jj_debug_noise",
            "jj_debug_solve", "jj_stats", "jj_set_subdomain_plan", "jj_debug_subdomain_solve", "jj_sm_count",
@@ -52,7 +52,7 @@ class JJSubdomainPlan(C.Structure):
                 ("n_loc", _i32p), ("n_halo", _i32p), ("hptr", _i32p), ("halo_top", _i32p), ("tptr", _i32p),
                 ("tslot", _i32p), ("top_face", _i32p), ("Sinv_packed", _f64p),
                 ("up_RB", C.c_int32), ("up_KB", C.c_int32), ("n_up_fwd", C.c_int32), ("n_up_bwd", C.c_int32),
-                ("n_up_tasks", C.c_int32), ("up_phase_ptr", _i32p), ("up_task", _i32p), ("up_task_aoff", _i64p),
+                ("n_up_tasks", C.c_int32), ("up_phase_ptr", _i32p), ("up_phase_split", _i32p), ("up_task", _i32p), ("up_task_aoff", _i64p),
                 ("n_up_cols", C.c_int64), ("up_cols", _i32p), ("n_up_vals", C.c_int64), ("up_A", _f64p),
                 ("prog", C.POINTER(JJSubProgram)),
                 ("junc_ptr", _i32p), ("junc_orig", _i32p), ("junc_row", _i32p), ("junc_sign", _i8p),
@@ -92,6 +92,7 @@ def load():
     lib.jj_set_circuit.argtypes = [_p, C.POINTER(JJCircuit)]
     lib.jj_set_solver.argtypes = [_p, C.POINTER(JJSweep), C.POINTER(JJSweep)]
     lib.jj_set_problem.argtypes = [_p, C.c_int32, C.c_double, C.c_uint64, C.c_int64, C.c_int32]
+    lib.jj_set_engine.argtypes = [_p, C.c_int32]
     lib.jj_set_state.argtypes = [_p, _f64p, _f64p]
     lib.jj_get_state.argtypes = [_p, _f64p, _f64p]
     lib.jj_set_source.argtypes = [_p, C.c_int32, C.c_int32, C.c_int32, _f64p]

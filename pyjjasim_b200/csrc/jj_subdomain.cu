@@ -49,9 +49,10 @@ struct SubArgs {
     int max_np, max_levels, max_tiles;
     // upper program (see JJSubdomainPlan): phases of tasks out[rows] = V . X[cols] over the r / z / J planes
     int up_RB, up_KB, n_up_fwd, n_up_bwd;
-    const int* up_phase_ptr; const int4* up_task; const long long* up_task_aoff;
+    const int* up_phase_ptr; const int* up_phase_split; const int4* up_task; const long long* up_task_aoff;
+    unsigned* up_ctr;               // [phases] monotonic work counters of the block tasks (zeroed per launch)
     const int* up_cols; const double* up_A;
-    double* U;                      // [3 planes][chunk][n_up_pad][PC]; rtop = plane 0, jtop = plane 2
+    double* U;                      // [4 planes: r, z, J, scratch][chunk][n_up_pad][PC]; rtop = plane 0, jtop = plane 2
     const SubProgDev* prog;
     const int *n_loc, *n_halo, *hptr, *halo_top, *tptr, *tslot, *top_face;
     const int4* tslot4;             // [n_top] the (at most four) slots of a top row, -1 padded; null when a row has more
@@ -97,12 +98,15 @@ constexpr int NWARPS = NT / 32;
 constexpr int RING = 4;            // stream steps per ring block; every tile is padded to a multiple of it
 constexpr int STEP_BYTES = 320;
 constexpr double TWO_PI = 6.283185307179586;
-constexpr int PROF_SLOTS = 8 + 48;     // phase counters + per-level counters of the sweeps (JJ_SUB_PROF)
+constexpr int PROF_UP = 48;             // upper phases with their own counters
+constexpr int PROF_STAMPS = 8;          // time stamps inside the first warp task of block 0 (latency chain of a small task)
+constexpr int PROF_SLOTS = 8 + 48 + 2 * PROF_UP + PROF_STAMPS;     // phase counters + per-level counters of the sweeps + (work, wait) per upper phase (JJ_SUB_PROF)
 
 struct SubState {
     int P = 1, NG = 4, PC = 32, n_rows = 0, n_loc_max = 0, stage_rows = 0, n_top = 0, n_up_pad = 0, n_slots = 0;
     int tt0 = 0, n_tt = 0, n_tt_pad = 0, up_RB = 4, up_KB = 8, n_up_fwd = 0, n_up_bwd = 0;
-    int* up_phase_ptr = nullptr; int4* up_task = nullptr; long long* up_task_aoff = nullptr;
+    int* up_phase_ptr = nullptr; int* up_phase_split = nullptr; int4* up_task = nullptr; long long* up_task_aoff = nullptr;
+    unsigned* up_ctr = nullptr;
     int* up_cols = nullptr; double* up_A = nullptr;
     double* U = nullptr; size_t u_bytes = 0;
     int dbg = 0; bool prof = false, no_tslot4 = false, no_l2_window = false, l2_limit_set = false; int grid_env = 0;
@@ -844,34 +848,129 @@ __device__ void top_product_areg(const SubArgs& a, double* buf, int RB, int KQ, 
     __syncthreads();
 }
 
+// A task small enough for one warp (at most 4 tiles, a few hundred A fragments): no shared memory, no block barrier.
+// The B fragments come straight from L2 (ld.global.cg: the rows were written by other blocks in earlier phases), two
+// row tiles per pass; the warps of a block work on different (task, chunk) pairs at the same time, which hides the
+// dependent loads (column code -> row address -> fragment) that dominate tasks of this size.
+template <int NG>
+__device__ void upper_warp_task(const SubArgs& a, int t, int c, int half, long long* stamp) {
+    constexpr int PC = 8 * NG;
+    const int lane = threadIdx.x & 31, n = lane >> 2, kk = lane & 3;
+    const long long ts0 = stamp ? clock64() : 0;
+    const int4 hd = __ldg(a.up_task + t);
+    const int tiles = (hd.y + 7) >> 3, nk = hd.z;
+    if (stamp && nk > 0 && lane == 0) stamp[0] += clock64() - ts0;          // header arrived
+    const size_t plane_elems = (size_t)a.n_chunks * a.n_up_pad * PC;
+    const int* cols = a.up_cols + hd.w;
+    const double* ubase = a.U + (size_t)c * a.n_up_pad * PC + n;
+    const double* abase = a.up_A + __ldg(a.up_task_aoff + t) + lane;
+    double* obase = a.U + (size_t)(hd.x >> 28) * plane_elems + ((size_t)c * a.n_up_pad + (hd.x & 0xfffffff)) * PC;
+    // pull the item's A fragments and column codes into L2 now (one memory latency for all of them): the loop below
+    // is a chain of dependent loads, and everything outside the r / z / J planes was evicted by the state streams
+    {
+        const int t0p = min(2 * half, tiles - 1);
+        const char* pa = reinterpret_cast<const char*>(abase - lane + (size_t)t0p * nk * 32);
+        const int a_bytes = min(2, tiles - t0p) * nk * 256;
+        for (int o = lane * 128; o < a_bytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + o));
+        const char* pc = reinterpret_cast<const char*>(cols);
+        for (int o = lane * 128; o < nk * 16; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + o));
+    }
+    // a warp takes ONE pair of row tiles (half = 0: tiles 0, 1; half = 1: tiles 2, 3); the two halves of a task run in
+    // different warps at the same time (in an in-place phase a half may read rows the other half is rewriting, but
+    // only with coefficients that are exactly zero)
+    {
+        const int t0 = 2 * half;
+        if (t0 >= tiles) return;
+        const bool two = t0 + 1 < tiles;
+        const double* a0 = abase + (size_t)t0 * nk * 32;
+        const double* a1 = abase + (size_t)(two ? t0 + 1 : t0) * nk * 32;
+        double acc0[NG][2], acc1[NG][2];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) { acc0[g][0] = acc0[g][1] = acc1[g][0] = acc1[g][1] = 0.0; }
+        // the column codes of 8 k-steps arrive in one coalesced load (nk is a multiple of 16) and are handed to the
+        // lanes by shuffles; the codes of the next 8 k-steps are in flight meanwhile. Four k-steps of fragments are
+        // fetched before their MMAs issue: the task is a chain of dependent latencies, not of arithmetic.
+        int code_next = __ldg(cols + lane);
+        if (stamp && code_next != 0x7fffffff && lane == 0) stamp[1] += clock64() - ts0;     // first column codes arrived
+        for (int k0 = 0; k0 < nk; k0 += 8) {
+            const int code32 = code_next;
+            if (k0 + 8 < nk) code_next = __ldg(cols + 4 * (k0 + 8) + lane);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                double av0[4], av1[4], bv[4][NG];
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    const int k = k0 + 4 * h + m;
+                    const int code = __shfl_sync(0xffffffffu, code32, 4 * (4 * h + m) + kk);
+                    const double* bp = ubase + (size_t)(code >> 28) * plane_elems + (size_t)(code & 0xfffffff) * PC;
+                    av0[m] = __ldg(a0 + (size_t)k * 32);
+                    av1[m] = __ldg(a1 + (size_t)k * 32);
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) bv[m][g] = __ldcg(bp + 8 * g);
+                }
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) { dmma884(acc0[g][0], acc0[g][1], av0[m], bv[m][g]); dmma884(acc1[g][0], acc1[g][1], av1[m], bv[m][g]); }
+                }
+            }
+        }
+        if (stamp && acc0[0][0] != 1.2345e300 && lane == 0) stamp[2] += clock64() - ts0;  // all products done
+        __syncwarp();            // all fragments of this pass are read before rows of the task are rewritten (in-place phases)
+        const int row = 8 * t0 + n;
+        if (row < hd.y) {
+#pragma unroll
+            for (int g = 0; g < NG; ++g) *reinterpret_cast<double2*>(obase + (size_t)row * PC + 8 * g + 2 * kk) = make_double2(acc0[g][0], acc0[g][1]);
+        }
+        if (two && row + 8 < hd.y) {
+#pragma unroll
+            for (int g = 0; g < NG; ++g) *reinterpret_cast<double2*>(obase + (size_t)(row + 8) * PC + 8 * g + 2 * kk) = make_double2(acc1[g][0], acc1[g][1]);
+        }
+    }
+}
+
 // One phase of the upper program (the separators between the subdomains and the dense top of the top): every task is
 // a gathered dense product  out[rows] = V . X[cols]  over the r / z / J planes of the separator rows, for up to 16
-// 8-row tiles and one problem chunk. The X rows named by the task's column list (row codes plane << 28 | row) are
+// 8-row tiles and one problem chunk. Tasks of a phase are independent (a grid barrier ends the phase).
+//
+// BLOCK tasks [phase_ptr, phase_split): the X rows named by the task's column list (row codes plane << 28 | row) are
 // gathered into shared memory in PANELS (cp.async, two buffers: the next panel lands while this one is multiplied),
 // in the swizzled row layout of the local sweeps; warp = (row tile, K slot): a task with T tiles splits the k-steps of
 // a panel over KQ = 16 / pow2ceil(T) warps per tile, the A fragments come straight from global memory (each is used
-// by exactly one warp), and the KQ partial sums of a tile meet in shared memory in a fixed order. Tasks of a phase are
-// independent (a grid barrier ends the phase); they are sorted by decreasing cost on the host and dealt to the
-// blocks round-robin, chunk-minor: the blocks that run at the same time apply the SAME A fragments to different
-// problem chunks, so these come from HBM once and hit in L2 afterwards.
+// by exactly one warp), and the KQ partial sums of a tile meet in shared memory in a fixed order. (task, chunk) pairs
+// are handed out by a work counter in decreasing order of cost (the host sorts them), chunk-minor: the blocks that run
+// at the same time apply the SAME A fragments to different problem chunks, so these come from HBM once and hit in
+// L2 afterwards. Which block runs a pair does not change its arithmetic: results do not depend on the schedule.
+// WARP tasks [phase_split, phase_ptr next): see upper_warp_task; dealt to the warps of the grid round-robin.
 // buf: the whole dynamic shared memory in front of the amplitude cache (the local vector is idle: with upper phases z
-// always goes through global memory), buf_rows: rows of PC float64 per panel buffer (a multiple of 64).
+// always goes through global memory), buf_rows: rows of PC float64 per panel buffer (a multiple of 256).
 template <int NG>
-__device__ void upper_phase(const SubArgs& a, double* buf, int buf_rows, int phase) {
+__device__ void upper_phase(const SubArgs& a, double* buf, int buf_rows, int phase, long long step) {
     constexpr int PC = 8 * NG;
     constexpr int PPR = PC / 2;                        // 16-byte pieces per row
+    __shared__ int s_pair;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t_lo = __ldg(a.up_phase_ptr + phase), n_t = __ldg(a.up_phase_ptr + phase + 1) - t_lo;
-    const long long n_pairs = (long long)n_t * a.n_chunks;
+    const long long tph0 = a.prof ? clock64() : 0;
+    const int t_lo = __ldg(a.up_phase_ptr + phase), t_split = __ldg(a.up_phase_split + phase), t_hi = __ldg(a.up_phase_ptr + phase + 1);
+    const int n_pairs = (t_split - t_lo) * a.n_chunks;
     const size_t plane_elems = (size_t)a.n_chunks * a.n_up_pad * PC;
     const unsigned long long pol = policy_evict_last();
     const int KP = buf_rows / 4;                       // k-steps per panel (a multiple of 16)
     const int n = lane >> 2, kk = lane & 3;
-    for (long long p = blockIdx.x; p < n_pairs; p += gridDim.x) {
-        const int c = (int)(p % a.n_chunks), t = t_lo + (int)(p / a.n_chunks);
+    // every block draws pairs until it draws one past the end: n_pairs + gridDim.x draws per time step
+    const unsigned base = (unsigned)(step * (long long)(n_pairs + (int)gridDim.x));
+    unsigned drawn = 0;
+    if (n_pairs > 0 && threadIdx.x == 0) drawn = atomicAdd(a.up_ctr + phase, 1u) - base;
+    while (n_pairs > 0) {
+        if (threadIdx.x == 0) s_pair = (int)drawn;
+        __syncthreads();                               // the pair is known; the buffers are free (previous task done)
+        const int p = s_pair;
+        if (p >= n_pairs) break;
+        if (threadIdx.x == 0) drawn = atomicAdd(a.up_ctr + phase, 1u) - base;       // the next pair, while this one runs
+        const int c = p % a.n_chunks, t = t_lo + p / a.n_chunks;
         const int4 hd = __ldg(a.up_task + t);          // out code, rows, k-steps, first column
         const int tiles = (hd.y + 7) >> 3, nk = hd.z;
-        int rbt = 1;
+        int rbt = NG >= 8 ? 2 : 1;                     // (64 problems per chunk: panels of 128 rows, at most 8 K slots)
         while (rbt < tiles) rbt <<= 1;
         const int KQ = NWARPS / rbt;
         const int rtl = warp / KQ, kq = warp % KQ;
@@ -882,42 +981,62 @@ __device__ void upper_phase(const SubArgs& a, double* buf, int buf_rows, int pha
         auto issue_panel = [&](int pp) {
             const int r0 = pp * buf_rows, nr = min(nk * 4 - r0, buf_rows);
             double* dst = buf + (size_t)(pp & 1) * buf_rows * PC;
-            for (int e = threadIdx.x; e < nr * PPR; e += NT) {
-                const int r = e / PPR, q = (e % PPR) * 2;
-                const int code = __ldg(cols + r0 + r);
-                cp_async16(dst + velem<NG>(r, q), ubase + (size_t)(code >> 28) * plane_elems + (size_t)(code & 0xfffffff) * PC + q);
+            // a thread copies at most 8 pieces of a panel (buf_rows * PPR <= 8 * NT): all its row codes are fetched first
+            // (independent loads, one memory latency), then the copies are issued
+            constexpr int MAXP = 8;
+            int code[MAXP];
+#pragma unroll
+            for (int i = 0; i < MAXP; ++i) {
+                const int e = threadIdx.x + i * NT;
+                code[i] = e < nr * PPR ? __ldg(cols + r0 + e / PPR) : 0;
+            }
+#pragma unroll
+            for (int i = 0; i < MAXP; ++i) {
+                const int e = threadIdx.x + i * NT;
+                if (e < nr * PPR) {
+                    const int r = e / PPR, q = (e % PPR) * 2;
+                    cp_async16(dst + velem<NG>(r, q), ubase + (size_t)(code[i] >> 28) * plane_elems + (size_t)(code[i] & 0xfffffff) * PC + q);
+                }
             }
             asm volatile("cp.async.commit_group;");
         };
-        __syncthreads();                               // the buffers are free (previous task / phase done)
         issue_panel(0);
         double acc[NG][2];
 #pragma unroll
         for (int g = 0; g < NG; ++g) { acc[g][0] = 0.0; acc[g][1] = 0.0; }
-        // this warp's A fragments: k-steps kq, kq + KQ, ... of row tile rtl
+        // this warp's A fragments: k-steps kq, kq + KQ, ... of row tile rtl, through a register ring that stays UPR
+        // k-steps ahead across panel boundaries (nk is a multiple of 64 and a panel holds a multiple of 64 k-steps, so
+        // a warp's share of a panel is a whole number of ring turns; reading past the task's end is harmless: the
+        // array is padded and the values are never used)
+        constexpr int UPR = 4;
         const double* ap = a.up_A + __ldg(a.up_task_aoff + t) + ((size_t)min(rtl, tiles - 1) * nk + kq) * 32 + lane;
         const size_t astep = (size_t)KQ * 32;
+        double ra[UPR];
+#pragma unroll
+        for (int u = 0; u < UPR; ++u)
+            asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(ra[u]) : "l"(ap + (size_t)u * astep), "l"(pol));
         for (int pp = 0; pp < n_panels; ++pp) {
             if (pp + 1 < n_panels) { issue_panel(pp + 1); asm volatile("cp.async.wait_group 1;"); }
             else asm volatile("cp.async.wait_group 0;");
             __syncthreads();                           // panel pp has landed for everyone
             if (active) {
-                const int own = min(nk - pp * KP, KP) / KQ;          // k-steps of this warp in the panel (nk % 16 == 0)
+                const int own = min(nk - pp * KP, KP) / KQ;          // k-steps of this warp in the panel
                 const unsigned vb = (unsigned)__cvta_generic_to_shared(buf + (size_t)(pp & 1) * buf_rows * PC);
                 // B fragment of local k-step j: rows 4 j + kk (row & 3 == kk), problems 8 g + n
                 unsigned baddr = vb + (unsigned)(velem<NG>(4 * kq + kk, n) * 8);
                 const unsigned bstep = (unsigned)(4 * KQ * PC * 8);
-#pragma unroll 4
-                for (int j = 0; j < own; ++j) {
-                    double av;
-                    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(av) : "l"(ap), "l"(pol));
-                    ap += astep;
-                    double bv[NG];
+                for (int j = 0; j < own; j += UPR) {
 #pragma unroll
-                    for (int g = 0; g < NG; ++g) bv[g] = lds_f64(baddr ^ (unsigned)(g << 6));
+                    for (int u = 0; u < UPR; ++u) {
+                        double bv[NG];
 #pragma unroll
-                    for (int g = 0; g < NG; ++g) dmma884(acc[g][0], acc[g][1], av, bv[g]);
-                    baddr += bstep;
+                        for (int g = 0; g < NG; ++g) bv[g] = lds_f64(baddr ^ (unsigned)(g << 6));
+#pragma unroll
+                        for (int g = 0; g < NG; ++g) dmma884(acc[g][0], acc[g][1], ra[u], bv[g]);
+                        asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(ra[u]) : "l"(ap + (size_t)(UPR + u) * astep), "l"(pol));
+                        baddr += bstep;
+                    }
+                    ap += UPR * astep;
                 }
             }
             __syncthreads();                           // everyone is done with buffer pp & 1
@@ -943,6 +1062,16 @@ __device__ void upper_phase(const SubArgs& a, double* buf, int buf_rows, int pha
             }
         }
     }
+    // warp tasks: (task, chunk, pair of row tiles) items; consecutive items go to different BLOCKS (all SMs busy even
+    // when there are fewer items than warps)
+    const long long n_witems = (long long)(t_hi - t_split) * a.n_chunks * 2;
+    for (long long p = (long long)warp * gridDim.x + blockIdx.x; p < n_witems; p += (long long)gridDim.x * NWARPS) {
+        const long long q = p >> 1;
+        long long* stamp = (a.prof && blockIdx.x == 0 && warp == 0 && phase == 0) ? a.prof + 8 + 48 + 2 * PROF_UP : nullptr;
+        upper_warp_task<NG>(a, t_split + (int)(q / a.n_chunks), (int)(q % a.n_chunks), (int)(p & 1), stamp);
+        if (stamp && lane == 0) stamp[3] += clock64() - tph0;
+    }
+    if (a.prof && blockIdx.x == 0 && threadIdx.x == 0 && phase == 0) a.prof[8 + 48 + 2 * PROF_UP + 4] += clock64() - tph0;
     __syncthreads();
 }
 
@@ -970,7 +1099,9 @@ __device__ __forceinline__ void rows_to_global(const double* v, int row0, int nr
     }
 }
 
-template <int NG, bool DEF>
+// UPPER: the plan has upper phases (compiled out otherwise: their registers and code must not weigh on the kernel of
+// circuits whose separators all fit the dense top product, whose time step is a tenth as long)
+template <int NG, bool DEF, bool UPPER>
 __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
     constexpr int PC = 8 * NG;
     extern __shared__ __align__(1024) double smem[];
@@ -986,11 +1117,12 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
     const bool multi = n_items > (int)gridDim.x;
     const int it_lo = multi ? (int)((long long)blockIdx.x * n_items / gridDim.x) : (int)blockIdx.x;
     const int it_hi = multi ? (int)((long long)(blockIdx.x + 1) * n_items / gridDim.x) : min(n_items, (int)blockIdx.x + 1);
-    const int n_up = a.n_up_fwd + a.n_up_bwd;
+    const int n_up = UPPER ? a.n_up_fwd + a.n_up_bwd : 0;
     // every block has at most one item: z stays in shared memory - unless upper phases run between the sweeps, which
     // gather their operands into the whole shared memory (two panel buffers of up_rows rows)
     const bool keep_z = n_items <= (int)gridDim.x && n_up == 0;
-    const int up_rows = (int)((((size_t)a.n_rows * PC + (size_t)a.stage_rows * (PC + 2)) / (2 * PC)) / 64 * 64);
+    constexpr int UP_GRAN = NG >= 8 ? 128 : 256;     // panel rows: whole ring turns for every K split (upper_phase)
+    const int up_rows = (int)((((size_t)a.n_rows * PC + (size_t)a.stage_rows * (PC + 2)) / (2 * PC)) / UP_GRAN * UP_GRAN);
     unsigned bar_target = 0;
     int cur_s = -1;
     // dense top product (top_product_areg): RB row tiles per block so that one round of blocks covers it, the K range
@@ -1034,20 +1166,34 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
         else if (top_ar == 1) top_product_areg<NG, 1>(a, stage, top_rb, ar_kq, ar_s, c0, nc, worker, n_workers);
         else top_product_direct<NG>(a);
     };
+    long long up_step = 0;               // time steps done: the work counters of the upper phases only ever grow
+    auto up_phase_timed = [&](int ph) {
+        if (!UPPER) return;
+        const bool pr = a.prof && threadIdx.x == 0 && ph < PROF_UP;
+        const long long t0 = pr ? clock64() : 0;
+        upper_phase<NG>(a, smem, up_rows, ph, up_step);
+        const long long t1 = pr ? clock64() : 0;
+        grid_barrier(a.bar, bar_target);
+        if (pr) {
+            a.prof[(size_t)blockIdx.x * PROF_SLOTS + 56 + 2 * ph] += t1 - t0;
+            a.prof[(size_t)blockIdx.x * PROF_SLOTS + 57 + 2 * ph] += clock64() - t1;
+        }
+    };
     // the solve of the separator rows for all chunks, between the forward and the backward local sweeps
     auto top_phase_grid = [&](long long n, long long& tq) {
         grid_barrier(a.bar, bar_target);
         if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 4] += tn - tq; tq = tn; }
         top_assemble<NG>(a, n, 0, a.n_chunks, blockIdx.x, gridDim.x);
         grid_barrier(a.bar, bar_target);
-        for (int ph = 0; ph < a.n_up_fwd; ++ph) { upper_phase<NG>(a, smem, up_rows, ph); grid_barrier(a.bar, bar_target); }
+        if (UPPER) for (int ph = 0; ph < a.n_up_fwd; ++ph) up_phase_timed(ph);
         if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 5] += tn - tq; tq = tn; }
         if (a.n_tt > 0) {
             dense_top(0, a.n_chunks, blockIdx.x, gridDim.x);
             if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 6] += tn - tq; tq = tn; }
             grid_barrier(a.bar, bar_target);
         }
-        for (int ph = a.n_up_fwd; ph < n_up; ++ph) { upper_phase<NG>(a, smem, up_rows, ph); grid_barrier(a.bar, bar_target); }
+        if (UPPER) for (int ph = a.n_up_fwd; ph < n_up; ++ph) up_phase_timed(ph);
+        ++up_step;
         if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 7] += tn - tq; tq = tn; }
     };
     if (a.dbg_b) {
@@ -1179,30 +1325,31 @@ typedef void (*KernelPtr)(const SubArgs);
 // The step kernel is compiled once per chunk width in its own translation unit (build.sh compiles this file with
 // -DJJ_SUB_NG=1|2|4|8 in parallel; without the macro only the host side below is compiled).
 namespace jj {
-KernelPtr subdomain_kernel_ng1(bool def);
-KernelPtr subdomain_kernel_ng2(bool def);
-KernelPtr subdomain_kernel_ng4(bool def);
-KernelPtr subdomain_kernel_ng8(bool def);
+KernelPtr subdomain_kernel_ng1(bool def, bool upper);
+KernelPtr subdomain_kernel_ng2(bool def, bool upper);
+KernelPtr subdomain_kernel_ng4(bool def, bool upper);
+KernelPtr subdomain_kernel_ng8(bool def, bool upper);
 }
 
 #ifdef JJ_SUB_NG
 #define JJ_SUB_CAT2(a, b) a##b
 #define JJ_SUB_CAT(a, b) JJ_SUB_CAT2(a, b)
 namespace jj {
-KernelPtr JJ_SUB_CAT(subdomain_kernel_ng, JJ_SUB_NG)(bool def) {
-    return def ? k_subdomain<JJ_SUB_NG, true> : k_subdomain<JJ_SUB_NG, false>;
+KernelPtr JJ_SUB_CAT(subdomain_kernel_ng, JJ_SUB_NG)(bool def, bool upper) {
+    if (upper) return def ? k_subdomain<JJ_SUB_NG, true, true> : k_subdomain<JJ_SUB_NG, false, true>;
+    return def ? k_subdomain<JJ_SUB_NG, true, false> : k_subdomain<JJ_SUB_NG, false, false>;
 }
 }
 #else
 
 namespace {
 
-KernelPtr pick_kernel(int NG, bool def) {
+KernelPtr pick_kernel(int NG, bool def, bool upper) {
     switch (NG) {
-        case 1: return subdomain_kernel_ng1(def);
-        case 2: return subdomain_kernel_ng2(def);
-        case 4: return subdomain_kernel_ng4(def);
-        default: return subdomain_kernel_ng8(def);
+        case 1: return subdomain_kernel_ng1(def, upper);
+        case 2: return subdomain_kernel_ng2(def, upper);
+        case 4: return subdomain_kernel_ng4(def, upper);
+        default: return subdomain_kernel_ng8(def, upper);
     }
 }
 
@@ -1380,7 +1527,9 @@ int subdomain_set_plan(JJHandle* h, const JJSubdomainPlan* pl) {
             for (int t = 0; t < pl->n_up_tasks; ++t) {
                 const int32_t* hd = pl->up_task + 4 * (size_t)t;
                 const int64_t tiles = (hd[1] + 7) / 8;
-                if (hd[1] < 1 || hd[1] > 8 * pl->up_RB || hd[2] < pl->up_KB || hd[2] % pl->up_KB != 0 || hd[3] < 0 ||
+                const bool block_task = t < pl->up_phase_split[std::upper_bound(pl->up_phase_ptr, pl->up_phase_ptr + n_ph + 1, t) - pl->up_phase_ptr - 1];
+                if (hd[1] < 1 || hd[1] > 8 * pl->up_RB || hd[2] < pl->up_KB || hd[2] % (block_task ? 64 : pl->up_KB) != 0 || hd[3] < 0 ||
+                    (!block_task && hd[1] > 32) ||
                     (int64_t)hd[3] + 4 * (int64_t)hd[2] > pl->n_up_cols ||
                     pl->up_task_aoff[t] < 0 || pl->up_task_aoff[t] + tiles * hd[2] * 32 > pl->n_up_vals) {
                     h->err = "subdomain plan: malformed task in the upper program"; return JJ_EINVAL;
@@ -1388,10 +1537,16 @@ int subdomain_set_plan(JJHandle* h, const JJSubdomainPlan* pl) {
             }
         }
         if ((rc = up(h, st, &st->up_phase_ptr, pl->up_phase_ptr, (size_t)n_ph + 1))) return rc;
+        for (int ph = 0; ph < n_ph; ++ph)
+            if (pl->up_phase_split[ph] < pl->up_phase_ptr[ph] || pl->up_phase_split[ph] > pl->up_phase_ptr[ph + 1]) {
+                h->err = "subdomain plan: up_phase_split outside its phase"; return JJ_EINVAL;
+            }
+        if ((rc = up(h, st, &st->up_phase_split, pl->up_phase_split, (size_t)n_ph + 1))) return rc;
+        if ((rc = up(h, st, &st->up_ctr, (const unsigned*)nullptr, 0, ((size_t)n_ph + 1) * sizeof(unsigned)))) return rc;
         if ((rc = up(h, st, (int**)&st->up_task, pl->up_task, (size_t)pl->n_up_tasks * 4))) return rc;
         if ((rc = up(h, st, (long long**)&st->up_task_aoff, (const long long*)pl->up_task_aoff, (size_t)pl->n_up_tasks))) return rc;
         if ((rc = up(h, st, &st->up_cols, pl->up_cols, (size_t)pl->n_up_cols))) return rc;
-        if ((rc = up(h, st, &st->up_A, pl->up_A, (size_t)pl->n_up_vals, (size_t)64 * 32 * sizeof(double)))) return rc;
+        if ((rc = up(h, st, &st->up_A, pl->up_A, (size_t)pl->n_up_vals, (size_t)8 * 16 * 32 * sizeof(double)))) return rc;
     }
     if ((rc = up(h, st, &st->junc_ptr, pl->junc_ptr, (size_t)P + 1))) return rc;
     if ((rc = up(h, st, &st->junc_orig, pl->junc_orig, (size_t)Nj))) return rc;
@@ -1410,7 +1565,7 @@ int subdomain_set_plan(JJHandle* h, const JJSubdomainPlan* pl) {
     }
     SCK(cudaStreamSynchronize(h->stream));
     st->smem_bytes = smem_for(st);
-    if (st->smem_bytes > 227 * 1024) { h->err = "subdomain plan: shared memory per block exceeds 227 KB"; return JJ_EINVAL; }
+    if (st->smem_bytes + 1024 > 227 * 1024) { h->err = "subdomain plan: shared memory per block exceeds 226 KB (+ 1 KB static)"; return JJ_EINVAL; }
     return JJ_OK;
 }
 
@@ -1429,7 +1584,8 @@ static void fill_args(JJHandle* h, SubState* st, SubArgs& a) {
     a.n_top = st->n_top; a.n_up_pad = st->n_up_pad; a.n_slots = st->n_slots;
     a.tt0 = st->tt0; a.n_tt = st->n_tt; a.n_tt_pad = st->n_tt_pad;
     a.up_RB = st->up_RB; a.up_KB = st->up_KB; a.n_up_fwd = st->n_up_fwd; a.n_up_bwd = st->n_up_bwd;
-    a.up_phase_ptr = st->up_phase_ptr; a.up_task = st->up_task; a.up_task_aoff = st->up_task_aoff;
+    a.up_phase_ptr = st->up_phase_ptr; a.up_phase_split = st->up_phase_split; a.up_task = st->up_task; a.up_task_aoff = st->up_task_aoff;
+    a.up_ctr = st->up_ctr;
     a.up_cols = st->up_cols; a.up_A = st->up_A; a.U = st->U;
     a.max_np = st->max_np; a.max_levels = st->max_levels; a.max_tiles = st->max_tiles;
     a.prog = st->prog; a.n_loc = st->n_loc; a.n_halo = st->n_halo; a.hptr = st->hptr; a.halo_top = st->halo_top;
@@ -1449,7 +1605,7 @@ static void fill_args(JJHandle* h, SubState* st, SubArgs& a) {
 }
 
 static int launch(JJHandle* h, SubState* st, SubArgs& a) {
-    KernelPtr k = pick_kernel(st->NG, h->cir.default_cpr);
+    KernelPtr k = pick_kernel(st->NG, h->cir.default_cpr, st->n_up_fwd + st->n_up_bwd > 0);
     {
         const Source &is = h->src[JJ_SRC_IS].dev, &t = h->src[JJ_SRC_T].dev, &vs = h->src[JJ_SRC_VS].dev;
         k_sub_gather_params<<<(h->cir.Nj + 255) / 256, 256, 0, h->stream>>>(
@@ -1477,6 +1633,7 @@ static int launch(JJHandle* h, SubState* st, SubArgs& a) {
     int grid = std::min(st->grid, std::max(1, want));
     if (st->grid_env > 0) grid = std::min(st->grid, st->grid_env);
     SCK(cudaMemsetAsync(st->bar, 0, BAR_BYTES, h->stream));
+    if (st->up_ctr) SCK(cudaMemsetAsync(st->up_ctr, 0, ((size_t)st->n_up_fwd + st->n_up_bwd + 1) * sizeof(unsigned), h->stream));
     if (st->n_tt > 0 && !st->no_l2_window) {
         // keep the packed Schur inverse resident in L2: it is re-read by every block once per time step while
         // the state (hundreds of MB per step) streams through the same cache. The limit is a per-device setting.
@@ -1506,14 +1663,14 @@ int subdomain_prepare(JJHandle* h) {
     st->state_bytes = (size_t)st->n_chunks * h->cir.Nj * PC * sizeof(double);
     st->z_bytes = (size_t)st->n_chunks * st->P * std::max(st->n_loc_max, 1) * PC * sizeof(double);
     st->c_bytes = (size_t)st->n_chunks * std::max(st->n_slots, 1) * PC * sizeof(double);
-    st->u_bytes = (size_t)3 * st->n_chunks * std::max(st->n_up_pad, 32) * PC * sizeof(double);
+    st->u_bytes = (size_t)4 * st->n_chunks * std::max(st->n_up_pad, 32) * PC * sizeof(double);     // planes r, z, J, scratch
     int rc;
     if ((rc = dev_alloc(h, (void**)&st->rth, st->state_bytes))) return rc;
     if ((rc = dev_alloc(h, (void**)&st->rx, st->state_bytes))) return rc;
     if ((rc = dev_alloc(h, (void**)&st->zloc, st->z_bytes))) return rc;
     if ((rc = dev_alloc(h, (void**)&st->ctop, st->c_bytes))) return rc;
     if ((rc = dev_alloc(h, (void**)&st->U, st->u_bytes))) return rc;
-    st->rtop = st->U; st->jtop = st->U + st->u_bytes / sizeof(double) / 3 * 2;
+    st->rtop = st->U; st->jtop = st->U + st->u_bytes / sizeof(double) / 4 * 2;
     if ((rc = dev_alloc(h, (void**)&st->bar, BAR_BYTES))) return rc;
     SCK(cudaMemsetAsync(st->rth, 0, st->state_bytes, h->stream));
     SCK(cudaMemsetAsync(st->rx, 0, st->state_bytes, h->stream));
@@ -1574,12 +1731,14 @@ int subdomain_run(JJHandle* h, long long i0, int n, const long long* th_plane, c
         for (size_t b = 0; b < nb; ++b) { double v = (double)hp[b * PROF_SLOTS + sl] / n; if (v > 0) { sum += v; ++cnt; } mx = std::max(mx, v); }
         double avg = cnt ? sum / cnt : 0;
         if (sl < 8) { tot += avg; fprintf(stderr, "  %-26s avg %9.0f max %9.0f (blocks %d)\n", names[sl], avg, mx, cnt); }
-        else if (cnt) fprintf(stderr, "    sweep level %2d           avg %9.0f max %9.0f\n", sl - 8, avg, mx);
+        else if (sl < 56) { if (cnt) fprintf(stderr, "    sweep level %2d           avg %9.0f max %9.0f\n", sl - 8, avg, mx); }
+        else if (sl < 56 + 2 * PROF_UP) { if (cnt) fprintf(stderr, "    upper phase %2d %s        avg %9.0f max %9.0f (blocks %d)\n", (sl - 56) / 2, (sl & 1) ? "wait" : "work", avg, mx, cnt); }
+        else if (cnt) fprintf(stderr, "    stamp %d (phase 0, block 0, warp 0: header / codes / products / item end / before final sync)  %9.0f\n", sl - 56 - 2 * PROF_UP, avg);
     }
     fprintf(stderr, "  total avg cycles per time step %.0f\n", tot);
     // local work (sweeps + junction + face pass) per subdomain, averaged over its chunks: what the dissection balances
     fprintf(stderr, "  local cycles per subdomain:");
-    for (int s = 0; s < st->P; ++s) {
+    for (int s = 0; s < std::min(st->P, 64); ++s) {
         double sum = 0; int cnt = 0;
         for (size_t b = s; b < nb && b < (size_t)st->P * st->n_chunks; b += st->P) {
             double v = 0; for (int sl = 0; sl < 4; ++sl) v += (double)hp[b * PROF_SLOTS + sl] / n;

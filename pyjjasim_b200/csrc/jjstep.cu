@@ -447,7 +447,7 @@ int jj_set_circuit(JJHandle* h, const JJCircuit* c) {
 int jj_set_solver(JJHandle* h, const JJSweep* fwd, const JJSweep* bwd) {
     CK(cudaSetDevice(h->device));
     REQUIRE(fwd && bwd, JJ_EINVAL, "solver: null sweep");
-    if (h->have_problem) free_problem(h);
+    CK(cudaStreamSynchronize(h->stream));      // the program may be replaced between runs of a live problem
     int rc;
     if ((rc = upload_sweep(h, h->fwd, fwd))) return rc;
     if ((rc = upload_sweep(h, h->bwd, bwd))) return rc;
@@ -492,6 +492,14 @@ int jj_set_problem(JJHandle* h, int32_t W, double dt, uint64_t seed, int64_t pro
     h->steps_done = 0; h->launches = 0; h->non_finite = 0; h->last_ms = 0.0;
     h->engine = JJ_ENGINE_STREAMING;
     h->have_problem = true; h->have_state = true;   // zero initial conditions are valid
+    return JJ_OK;
+}
+
+int jj_set_engine(JJHandle* h, int32_t engine) {
+    REQUIRE(h->have_problem, JJ_ESTATE, "set_engine: problem not set");
+    REQUIRE(engine == JJ_ENGINE_AUTO || engine == JJ_ENGINE_STREAMING || engine == JJ_ENGINE_SUBDOMAIN, JJ_EINVAL,
+            "set_engine: unknown engine");
+    h->engine_req = engine;
     return JJ_OK;
 }
 

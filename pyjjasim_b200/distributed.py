@@ -11,11 +11,15 @@ identical however the batch is sharded.
 Single-process alternative: ``TimeEvolutionProblem(..., devices=[0, 1, ...])`` drives several GPUs from host
 threads (engine.device_time_evolution_core).
 """
+import time
+
 import numpy as np
 
 from .engine import shard_bounds
 
-__all__ = ["shard_for_rank", "gather_problem_axis", "compute_sharded"]
+__all__ = ["shard_for_rank", "gather_problem_axis", "compute_sharded", "last_gather_seconds"]
+
+last_gather_seconds = None      # wall time of the final gather of the last compute_sharded call on this rank
 
 
 def shard_for_rank(W, rank, world_size):
@@ -73,6 +77,10 @@ def compute_sharded(problem, device=None, group=None, core=None):
             box = [resolve_noise_seed(prob) if rank == 0 else None]
             dist.broadcast_object_list(box, src=0, group=group)
             th, I = device_time_evolution_core(prob, th_mask, I_mask, shard=(w0, w1), device=device, noise_seed=box[0])
-        return gather_problem_axis(th, W, group), gather_problem_axis(I, W, group)
+        global last_gather_seconds
+        t0 = time.perf_counter()
+        out = gather_problem_axis(th, W, group), gather_problem_axis(I, W, group)
+        last_gather_seconds = time.perf_counter() - t0
+        return out
 
     return _time_evolution(problem, core=sharded_core)

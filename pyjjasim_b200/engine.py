@@ -26,7 +26,7 @@ from . import _lib
 from .current_phase_relation import harmonics
 from .factor import factorize, streaming_program, system_matrix
 from .subdomain import subdomain_plan, face_tables
-from .sources import classify_source, nonnegative_factors, ZERO, RANK1, DENSE
+from .sources import classify_source, nonnegative_factors, NotRankOne, ZERO, RANK1, DENSE
 
 __all__ = ["device_time_evolution_core", "CircuitTables", "DeviceEngine", "last_run_stats"]
 
@@ -207,7 +207,7 @@ class CircuitTables:
         self._subdomain = {}
 
     # ------------------------------------------------------------------ subdomain engine plan
-    SMEM_LIMIT = 227 * 1024
+    SMEM_LIMIT = 226 * 1024          # dynamic shared memory of the step kernel (it has 1 KB of static shared memory)
 
     def subdomain_smem_bytes(self, plan):
         PC = plan.PC
@@ -419,7 +419,7 @@ class DeviceEngine:
         up = plan.upper
         p.up_RB, p.up_KB, p.n_up_fwd, p.n_up_bwd = up["RB"], up["KB"], up["n_fwd"], up["n_bwd"]
         p.n_up_tasks = len(up["task"])
-        p.up_phase_ptr, p.up_task = a32(up["phase_ptr"]), a32(up["task"])
+        p.up_phase_ptr, p.up_phase_split, p.up_task = a32(up["phase_ptr"]), a32(up["phase_split"]), a32(up["task"])
         aoff = np.ascontiguousarray(up["task_aoff"] if len(up["task_aoff"]) else np.zeros(1), dtype=np.int64)
         keep.append(aoff)
         p.up_task_aoff = _lib.i64(aoff)
@@ -462,6 +462,10 @@ class DeviceEngine:
     def set_problem(self, W, dt, seed=0, problem_offset=0, engine=_lib.JJ_ENGINE_AUTO):
         self.W = W
         self._ck(self.lib.jj_set_problem(self.h, W, float(dt), int(seed) & (2 ** 64 - 1), int(problem_offset), engine))
+
+    def set_engine(self, engine):
+        """Switch the step engine of the current problem (the state stays on the device)."""
+        self._ck(self.lib.jj_set_engine(self.h, int(engine)))
 
     def set_state(self, th_m1, th_m2):
         a, b = _lib.c_f64(th_m1), _lib.c_f64(th_m2)
@@ -583,9 +587,17 @@ class _ShardInputs:
 def _classify_all(problem, tab):
     Nj, Nf, W, Nt = tab.Nj, tab.Nf, problem.get_problem_count(), problem._Nt()
     raw = getattr(problem, "_raw_sources", None)
-    if raw is None:       # a reference-style problem object: use its stored inputs
-        raw = dict(f=problem.external_flux, Is=problem.current_sources, Vs=problem.voltage_sources,
-                   T=problem.temperature)
+    if raw is None:
+        # a reference-style problem object (the reference's own TimeEvolutionProblem bound to this core):
+        # its inputs are callables or (N, W, Nt) broadcast views, with the time-dependence flags frozen at construction;
+        # an input that is not time dependent is read at step 0 only (reference: time_evolution.py:509-531)
+        raw = {}
+        for name, attr, flag in (("f", "external_flux", "_f_is_timedep"), ("Is", "current_sources", "_Is_is_timedep"),
+                                 ("Vs", "voltage_sources", "_Vs_is_timedep"), ("T", "temperature", "_T_is_timedep")):
+            cur = getattr(problem, attr)
+            if not getattr(problem, flag, True):
+                cur = np.asarray(cur(0))[..., None] if callable(cur) else np.asarray(cur)[:, :, 0:1]
+            raw[name] = cur
     else:
         # an input attribute replaced after construction (the reference's annealing loop assigns prob.temperature
         # between compute() calls, time_evolution.py:1166): the reference reads the new attribute, with the
@@ -729,26 +741,50 @@ def _run_shard(problem, tab, specs, dev, w0, w1, th_mask, I_mask, th_host, I_hos
         th_idx = np.cumsum(th_mask) - 1      # plane index (without the +2 offset) of each stored step
         I_idx = np.cumsum(I_mask) - 1
         total_ms = 0.0
-        for i0 in range(0, Nt, K):
+        i0 = 0
+        while i0 < Nt:
             i1 = min(Nt, i0 + K)
             n = i1 - i0
-            for name, s in specs.items():
-                which = _WHICH[name]
-                if s.kind == ZERO:
-                    continue
-                if s.kind == RANK1:
-                    if name == "Vs":
-                        amp = sh.amp(name, i0, i1)
-                        if s.static:
-                            amp = np.broadcast_to(amp, (n, W))
-                        cum = vs_cum[None, :] + np.concatenate((np.zeros((1, W)), np.cumsum(amp * dt, axis=0)[:-1]), axis=0)
-                        vs_cum = vs_cum + np.sum(amp * dt, axis=0)
-                        eng.upload_source(which, i0, cum)
+            try:
+                tables = []
+                for name, s in specs.items():
+                    if s.kind == ZERO:
+                        continue
+                    if s.kind == RANK1:
+                        if name == "Vs":
+                            amp = sh.amp(name, i0, i1)
+                            if s.static:
+                                amp = np.broadcast_to(amp, (n, W))
+                            cum = vs_cum[None, :] + np.concatenate((np.zeros((1, W)), np.cumsum(amp * dt, axis=0)[:-1]), axis=0)
+                            tables.append((name, cum, np.sum(amp * dt, axis=0)))
+                        elif not s.static:
+                            amp = sh.amp(name, i0, i1)
+                            tables.append((name, np.sqrt(amp) if name == "T" else amp, None))
                     elif not s.static:
-                        amp = sh.amp(name, i0, i1)
-                        eng.upload_source(which, i0, np.sqrt(amp) if name == "T" else amp)
-                elif not s.static:
-                    eng.upload_source(which, i0, _dense_for_device(name, sh.dense(name, i0, i1), tab))
+                        tables.append((name, _dense_for_device(name, sh.dense(name, i0, i1), tab), None))
+            except NotRankOne:
+                # a callable that was base[e] * amp(i)[w] at the probed steps is not any more: from this chunk of steps
+                # on it is uploaded as dense per-step tables, which only the streaming engine reads (the state stays
+                # where it is: both engines hand it over through the canonical arrays)
+                name = _first_not_rank_one(specs, sh, i0, i1)
+                if name == "Vs":
+                    raise NotImplementedError("a callable voltage source stopped being base[e] * amp(i)[w] during the "
+                                              "run; pass it as an array") from None
+                specs = dict(specs)
+                specs[name] = specs[name].as_dense()
+                sh = _ShardInputs(specs, w0, w1)
+                if engine_kind != _lib.JJ_ENGINE_STREAMING:
+                    engine_kind = _lib.JJ_ENGINE_STREAMING
+                    if not eng.has_streaming_program:
+                        eng.set_streaming_program(True)
+                    eng.set_engine(engine_kind)
+                eng.set_source(_WHICH[name], _lib.JJ_KIND_DENSE, False)
+                K = _chunk_length(specs, tab, W, Nt, replay is not None)
+                continue
+            for name, table, vs_add in tables:
+                eng.upload_source(_WHICH[name], i0, table)
+                if vs_add is not None:
+                    vs_cum = vs_cum + vs_add
             if replay is not None and specs["T"].kind != ZERO:
                 if callable(replay):
                     Z = np.stack([np.asarray(replay(i))[:, w0:w1] for i in range(i0, i1)])
@@ -768,6 +804,7 @@ def _run_shard(problem, tab, specs, dev, w0, w1, th_mask, I_mask, th_host, I_hos
             if n_I:
                 first = I_idx[i0:i1][im][0]
                 eng.fetch_current(0, n_I, out=I_host[2 + first: 2 + first + n_I, :, w0:w1])
+            i0 = i1
         st = eng.stats()
         st["total_ms"] = total_ms
         st["problems"] = W
@@ -775,6 +812,16 @@ def _run_shard(problem, tab, specs, dev, w0, w1, th_mask, I_mask, th_host, I_hos
         ok = True
     finally:
         _release_engine(dev, key, eng, ok)
+
+
+def _first_not_rank_one(specs, sh, i0, i1):
+    for name, s in specs.items():
+        if s.kind == RANK1 and not s.static:
+            try:
+                sh.amp(name, i0, i1)
+            except NotRankOne:
+                return name
+    raise RuntimeError("no input failed the rank-one check on re-evaluation")
 
 
 def _dense_for_device(name, table, tab):

@@ -79,6 +79,17 @@ class SourceSpec:
         return np.ascontiguousarray(np.stack(
             [np.broadcast_to(np.asarray(self._dense_fn(i), dtype=np.double), (self.N, self.W)) for i in steps]))
 
+    def as_dense(self):
+        """The same input as per-step dense tables (for a callable that stopped being rank one)."""
+        if self.kind == DENSE:
+            return self
+        fn = self._dense_fn
+        if fn is None:
+            base, amp_fn = self.base, self._amp_fn
+            fn = (lambda i: base[:, None] * np.asarray(amp_fn(i), dtype=np.double)[None, :]) if self.kind == RANK1 \
+                else (lambda i: np.zeros((self.N, self.W)))
+        return SourceSpec(DENSE, self.N, self.W, self.Nt, static=self.static, dense_fn=fn)
+
     def value(self, i):
         """Dense (N, W) value at step i (host; used for stored currents and tests)."""
         if self.kind == ZERO:
@@ -103,6 +114,29 @@ def _rank_one_factor(a2, rtol=_RANK1_RTOL):
     return None
 
 
+def _collapse_broadcast(arr):
+    """(a, b, c) view of an array of at most three dimensions with every zero-stride axis (np.broadcast_to views, as
+    a reference-style problem object stores its inputs: time_evolution.py:119-130) reduced to length one."""
+    a3 = arr.reshape((1,) * (3 - arr.ndim) + arr.shape)
+    index = tuple(slice(0, 1) if (a3.strides[k] == 0 and a3.shape[k] > 1) else slice(None) for k in range(3))
+    return a3[index]
+
+
+_CHECK_ELEMS = 1 << 24          # elements per block when a time-dependent array is verified to be rank one
+
+
+def _rank_one_over_time(a3, base, j0, N, W, Nt):
+    """Is a3 (N, W, Nt) == base[:, None, None] * (a3[j0] / base[j0]) everywhere? Checked in blocks of time steps, so
+    that no copy of the whole array is ever made."""
+    step = max(1, _CHECK_ELEMS // max(1, N * W))
+    for i0 in range(0, Nt, step):
+        blk = a3[:, :, i0:i0 + step]
+        tab = blk[j0] / base[j0]
+        if not np.allclose(base[:, None, None] * tab[None, :, :], blk, rtol=_RANK1_RTOL, atol=0.0):
+            return False
+    return True
+
+
 def classify_source(x, N, W, Nt, zero_if_allclose=True):
     """
     Build a SourceSpec from a reference-style input: scalar / array broadcastable to (N, W, Nt) /
@@ -125,23 +159,25 @@ def classify_source(x, N, W, Nt, zero_if_allclose=True):
                 v = np.broadcast_to(np.asarray(_x(i), dtype=np.double), (N, W))
                 amp = v[_j0, :] / _base[_j0]
                 if not np.allclose(_base[:, None] * amp[None, :], v, rtol=_RANK1_RTOL, atol=0.0):
-                    raise _NotRankOne()
+                    raise NotRankOne()
                 return amp
-            # probe a few steps: a callable whose structure changes over time is handled densely
+            # probe a few steps: a callable whose structure changes over time is handled densely (and one that
+            # changes later in the run makes the engine switch to the dense form from that chunk of steps on)
             try:
                 for i in sorted(set([0, 1, Nt // 3, Nt // 2, Nt - 1])):
                     if 0 <= i < Nt:
                         amp_fn(i)
                 return SourceSpec(RANK1, N, W, Nt, base=base, static=False, amp_fn=amp_fn, dense_fn=x)
-            except _NotRankOne:
+            except NotRankOne:
                 pass
         return SourceSpec(DENSE, N, W, Nt, static=False, dense_fn=x)
     arr = np.asarray(x, dtype=np.double)
-    full = np.broadcast_to(arr, (N, W, Nt))      # raises like the reference on bad shapes
-    a3 = arr.reshape((1,) * (3 - arr.ndim) + arr.shape) if arr.ndim <= 3 else None
-    if a3 is None:
+    np.broadcast_to(arr, (N, W, Nt))             # raises like the reference on bad shapes
+    if arr.ndim > 3:
         raise ValueError("input must be broadcastable to (N, W, Nt)")
-    timedep = arr.ndim > 0 and arr.shape[-1] > 1     # reference: _is_timedep
+    a3 = _collapse_broadcast(arr)                # zero-stride axes (broadcast views) count as length one
+    full = np.broadcast_to(a3, (N, W, Nt))
+    timedep = a3.shape[-1] > 1                   # reference: _is_timedep; a constant stored as a broadcast view is constant
     if not timedep:
         s0 = full[:, :, 0]
         if zero_if_allclose and np.allclose(a3[:, :, 0], 0):      # same values as s0, without the broadcast copies
@@ -170,16 +206,18 @@ def classify_source(x, N, W, Nt, zero_if_allclose=True):
     if rf is not None and np.any(rf[0] != 0.0):
         base = rf[0]
         j0 = int(np.argmax(np.abs(base)))
-        tab = full[j0, :, :] / base[j0]
-        if np.allclose(base[:, None, None] * tab[None, :, :], full, rtol=_RANK1_RTOL, atol=0.0):
+        if _rank_one_over_time(full, base, j0, N, W, Nt):
+            tab = full[j0, :, :] / base[j0]
             return SourceSpec(RANK1, N, W, Nt, base=base, static=False, amp_fn=lambda i, t=tab: t[:, i])
     return SourceSpec(DENSE, N, W, Nt, static=False, dense_fn=lambda i, f=full: f[:, :, i])
 
 
-class _NotRankOne(ValueError):
+class NotRankOne(ValueError):
+    """A callable input stopped being of the form base[e] * amp(i)[w]; the engine catches this and continues with the
+    dense form of that input (SourceSpec.as_dense)."""
+
     def __init__(self):
-        super().__init__("a callable input stopped being of the form base[e] * amp(i)[w] during the run; "
-                         "wrap it so that it is, or pass it as an array")
+        super().__init__("a callable input stopped being of the form base[e] * amp(i)[w] during the run")
 
 
 def nonnegative_factors(spec):

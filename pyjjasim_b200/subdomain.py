@@ -318,8 +318,12 @@ def _auto_groups(L0, hrow, stage_cap):
 
 
 UP_PLANE_SHIFT = 28                     # row code of the upper program: plane << 28 | row
-PLANE_R, PLANE_Z, PLANE_J = 0, 1, 2     # right-hand side / forward result / solution of the separator rows
+PLANE_R, PLANE_Z, PLANE_J, PLANE_S = 0, 1, 2, 3     # right-hand side / forward result / solution of the separator rows; scratch
+UP_SPLIT_MIN_COLS = 128                 # fewest columns of a column group of a split product
 UP_TILES = 16                           # most 8-row tiles of a task of the upper program (one warp each)
+UP_MERGE_ROWS = 96                      # separator blocks up to this size get one merged phase per depth and sweep
+UP_WARP_COST = 512                      # tasks of at most this many A fragments (and 4 tiles) are run by single warps
+UP_BLOCK_KSTEPS = 64                    # k-steps of a block task are a multiple of this (4 ring turns x up to 16 K slots)
 UP_KSTEPS = 16                          # k-steps of a task are padded to a multiple of this (any K split 16 / 2^i works)
 
 
@@ -332,25 +336,65 @@ class _UpperBuilder:
     A task computes  out[rows] = V . X[cols]  for at most 8 * RB consecutive rows of one plane; its A fragments are
     stored per 8-row tile as [k-step][lane = row * 4 + kk] = V[row, 4 k + kk]."""
 
-    def __init__(self, pad_code):
+    def __init__(self, pad_code, scratch_rows=0):
         self.RB, self.KB, self.pad_code = UP_TILES, UP_KSTEPS, pad_code
+        self.scratch_rows, self.scratch_next, self.pending = scratch_rows, 0, []
         self.phases = []                 # list of lists of (cost, out code, rows, nk, cols, A)
         self.cur = None
         self.nnz = self.stored = 0       # factor entries applied / values stored (padding, unions of column sets)
 
     def begin_phase(self):
         self.cur = []
+        self.scratch_next, self.pending = 0, []
 
     def end_phase(self):
         if self.cur:
             self.phases.append(self.cur)
-        self.cur = None
+        if self.pending:
+            # the column groups of the split products of this phase are summed in a phase of their own
+            self.cur = []
+            for args in self.pending:
+                self.task(*args)
+            self.phases.append(self.cur)
+        self.cur, self.pending = None, []
+
+    def product(self, out_plane, row0, V, col_codes, self_plane=None, n_split=1):
+        """out[rows] = V . X[cols] (+ self[rows]). n_split > 1 cuts the columns into that many groups whose partial
+        products go to the scratch plane, one (task, chunk) pair each, and are summed - in a fixed order - by 8-row
+        tasks of the phase that end_phase appends: parallelism for a few large separator blocks times a few problem
+        chunks without shrinking the row blocks (which would gather every operand row for two row tiles only)."""
+        nr, K = V.shape
+        n_split = max(1, min(int(n_split), K // UP_SPLIT_MIN_COLS))
+        if n_split > 1 and self.scratch_next + n_split * nr > self.scratch_rows:
+            n_split = 1
+        if n_split == 1:
+            if self_plane is not None:
+                V = np.concatenate((V, np.eye(nr)), axis=1)
+                col_codes = np.concatenate((col_codes, _up_code(self_plane, np.arange(row0, row0 + nr))))
+            self.task(out_plane, row0, V, col_codes)
+            return
+        edges = (np.linspace(0, K, n_split + 1) // 4 * 4).astype(int)
+        edges[-1] = K
+        srow = []
+        for c in range(n_split):
+            srow.append(self.scratch_next)
+            self.task(PLANE_S, self.scratch_next, V[:, edges[c]:edges[c + 1]], col_codes[edges[c]:edges[c + 1]])
+            self.scratch_next += nr
+        for i0 in range(0, nr, 8):
+            m = min(8, nr - i0)
+            codes = [_up_code(PLANE_S, np.arange(s0 + i0, s0 + i0 + m)) for s0 in srow]
+            if self_plane is not None:
+                codes.append(_up_code(self_plane, np.arange(row0 + i0, row0 + i0 + m)))
+            self.pending.append((out_plane, row0 + i0, np.tile(np.eye(m), (1, len(codes))), np.concatenate(codes)))
 
     def task(self, out_plane, row0, V, col_codes):
         nr, K = V.shape
         assert 1 <= nr <= 8 * self.RB and K == len(col_codes) and K > 0
-        nk = -(-K // (4 * self.KB)) * self.KB
         tiles = -(-nr // 8)
+        nk = -(-K // (4 * self.KB)) * self.KB
+        warp = tiles * nk <= UP_WARP_COST and nr <= 32
+        if not warp:
+            nk = -(-K // (4 * UP_BLOCK_KSTEPS)) * UP_BLOCK_KSTEPS      # a block task: whole turns of the A ring per warp
         self.nnz += int(np.count_nonzero(V))
         self.stored += tiles * 8 * nk * 4
         A = np.zeros((tiles * 8, nk * 4))
@@ -358,14 +402,18 @@ class _UpperBuilder:
         A = np.ascontiguousarray(A.reshape(tiles, 8, nk, 4).transpose(0, 2, 1, 3)).ravel()
         cols = np.full(nk * 4, self.pad_code, dtype=np.int32)
         cols[:K] = col_codes
-        self.cur.append((tiles * nk, int(_up_code(out_plane, row0)), nr, nk, cols, A))
+        self.cur.append((tiles * nk, int(_up_code(out_plane, row0)), nr, nk, cols, A, warp))
 
     def finish(self, n_fwd):
         """-> dict of flat arrays; tasks of a phase sorted by decreasing cost (the device deals them out round-robin)."""
-        phase_ptr, hdr, aoff, cols, vals = [0], [], [], [], []
+        phase_ptr, phase_split, hdr, aoff, cols, vals = [0], [], [], [], [], []
         co = vo = 0
         for ph in self.phases:
-            for (cost, out, nr, nk, c, A) in sorted(ph, key=lambda t: -t[0]):
+            # block tasks (panels in shared memory, 16 warps) first, then the tasks small enough for a single warp
+            ordered = sorted((t for t in ph if not t[6]), key=lambda t: -t[0])
+            phase_split.append(len(hdr) + len(ordered))
+            ordered += sorted((t for t in ph if t[6]), key=lambda t: -t[0])
+            for (cost, out, nr, nk, c, A, _) in ordered:
                 hdr.append((out, nr, nk, co))
                 aoff.append(vo)
                 cols.append(c)
@@ -376,6 +424,7 @@ class _UpperBuilder:
         assert co < 2 ** 31
         return dict(RB=self.RB, KB=self.KB, n_fwd=n_fwd, n_bwd=len(self.phases) - n_fwd, nnz=self.nnz, stored=self.stored,
                     phase_ptr=np.asarray(phase_ptr, dtype=np.int32),
+                    phase_split=np.asarray(phase_split + [0], dtype=np.int32),
                     task=np.asarray(hdr, dtype=np.int32).reshape(-1, 4),
                     task_aoff=np.asarray(aoff, dtype=np.int64),
                     cols=np.concatenate(cols) if cols else np.zeros(0, dtype=np.int32),
@@ -402,9 +451,12 @@ def _upper_program(F, top_rows, tt0, blk_of, n_chunks, n_up_pad):
       then                          r_tt -= L[tt, upper] z             (r plane, in place; the dense inverse follows)
       backward, shallowest first a) t_B = z_B - L[above, B]^T J        (z plane, in place)
                                 b)  J_B = inv(L[B, B])^T t_B           (z -> J plane)
+
+    Depths whose blocks are all small are done in ONE phase per sweep (a and b multiplied out on the host), and
+    small tasks are marked for single warps: a phase lists its block tasks first, then its warp tasks.
     """
     n_top = top_rows.size
-    ub = _UpperBuilder(int(_up_code(PLANE_R, n_up_pad - 1)))
+    ub = _UpperBuilder(int(_up_code(PLANE_R, n_up_pad - 1)), scratch_rows=n_up_pad)
     if tt0 == 0:
         return ub.finish(0)
     Lt = F.Lc[top_rows][:, top_rows].tocsr()
@@ -424,67 +476,87 @@ def _upper_program(F, top_rows, tt0, blk_of, n_chunks, n_up_pad):
             dinv[b0] = _tri_inverse(Lt[b0:b1, b0:b1].toarray())
         return dinv[b0]
 
-    def phase_a(M, plane_self, plane_cols, row_ranges, col_lo, col_hi):
-        """out[rows] = self[rows] - M[rows, col_lo:col_hi] X[cols], in place in plane_self."""
-        ub.begin_phase()
-        for (r0, r1) in row_ranges:
-            sub = M[r0:r1]
-            idx = sub.indices
-            cols = np.unique(idx[(idx >= col_lo) & (idx < col_hi)])
-            if cols.size == 0:
-                continue
-            V = np.concatenate((-sub[:, cols].toarray(), np.eye(r1 - r0)), axis=1)
-            codes = np.concatenate((_up_code(plane_cols, cols), _up_code(plane_self, np.arange(r0, r1))))
-            ub.task(plane_self, r0, V, codes)
-        ub.end_phase()
-
-    def groups_of(blocks):
+    def groups_of(blocks, splittable=False):
+        """row groups (r0, r1, b0, b1) of the tasks of a phase and the number of column groups of each product"""
         RT = _phase_rows(blocks, n_chunks)
-        return [(r0, min(b1, r0 + RT), b0, b1) for (b0, b1) in blocks for r0 in range(b0, b1, RT)]
+        n_split = 1
+        if splittable and RT < 64:
+            # a few large blocks and a few problem chunks: keep 128-row tasks and split their columns instead
+            RT = 128
+            n_groups = sum(-(-(b1 - b0) // RT) for (b0, b1) in blocks)
+            n_split = -(-2 * 148 // (n_groups * n_chunks))
+        return [(r0, min(b1, r0 + RT), b0, b1) for (b0, b1) in blocks for r0 in range(b0, b1, RT)], n_split
+
+    def dense_cols(M, r0, r1, lo, hi):
+        """columns in [lo, hi) that rows r0:r1 of the CSR matrix M touch, and the dense block over them"""
+        sub = M[r0:r1]
+        idx = sub.indices
+        cols = np.unique(idx[(idx >= lo) & (idx < hi)])
+        return cols, (sub[:, cols].toarray() if cols.size else np.zeros((r1 - r0, 0)))
+
+    def merged(blocks):
+        """small separators: one phase per depth, z_B = inv(L_BB) r_B - (inv(L_BB) L[B, below]) z (the product is as
+        dense as L[B, below] itself when the block is a few tiles), instead of two phases with a barrier between"""
+        return max(b1 - b0 for (b0, b1) in blocks) <= UP_MERGE_ROWS
 
     # ---- forward
     for dd in depths[::-1]:
         blocks = [(int(starts[i]), int(ends[i])) for i in np.flatnonzero(bdepth == dd)]
-        grp = groups_of(blocks)
+        if merged(blocks):
+            grp, _ = groups_of(blocks)
+            ub.begin_phase()
+            for (r0, r1, b0, b1) in grp:
+                Di = block_inv(b0, b1)[r0 - b0:r1 - b0]
+                cols, Lb = dense_cols(Lt, b0, b1, 0, b0)            # all rows of the block: Di couples them
+                V = np.concatenate((Di[:, :r1 - b0], -(Di @ Lb)), axis=1)
+                ub.task(PLANE_Z, r0, V, np.concatenate((_up_code(PLANE_R, np.arange(b0, r1)), _up_code(PLANE_Z, cols))))
+            ub.end_phase()
+            continue
+        grp, n_split = groups_of(blocks, splittable=True)
         ub.begin_phase()
         for (r0, r1, b0, b1) in grp:
-            sub = Lt[r0:r1]
-            idx = sub.indices
-            cols = np.unique(idx[idx < b0])
-            if cols.size == 0:
-                continue
-            V = np.concatenate((-sub[:, cols].toarray(), np.eye(r1 - r0)), axis=1)
-            codes = np.concatenate((_up_code(PLANE_Z, cols), _up_code(PLANE_R, np.arange(r0, r1))))
-            ub.task(PLANE_R, r0, V, codes)
+            cols, Lb = dense_cols(Lt, r0, r1, 0, b0)
+            if cols.size:
+                ub.product(PLANE_R, r0, -Lb, _up_code(PLANE_Z, cols), self_plane=PLANE_R, n_split=n_split)
         ub.end_phase()
         ub.begin_phase()
         for (r0, r1, b0, b1) in grp:
             Di = block_inv(b0, b1)
-            ub.task(PLANE_Z, r0, Di[r0 - b0:r1 - b0, :r1 - b0], _up_code(PLANE_R, np.arange(b0, r1)))
+            ub.product(PLANE_Z, r0, Di[r0 - b0:r1 - b0, :r1 - b0], _up_code(PLANE_R, np.arange(b0, r1)), n_split=n_split)
         ub.end_phase()
     if n_top > tt0:
-        RT = _phase_rows([(tt0, n_top)], n_chunks)
-        phase_a(Lt, PLANE_R, PLANE_Z, [(r0, min(n_top, r0 + RT)) for r0 in range(tt0, n_top, RT)], 0, tt0)
+        grp, n_split = groups_of([(tt0, n_top)], splittable=True)
+        ub.begin_phase()
+        for (r0, r1, _b0, _b1) in grp:
+            cols, Lb = dense_cols(Lt, r0, r1, 0, tt0)
+            if cols.size:
+                ub.product(PLANE_R, r0, -Lb, _up_code(PLANE_Z, cols), self_plane=PLANE_R, n_split=n_split)
+        ub.end_phase()
     n_fwd = len(ub.phases)
     # ---- backward
     for dd in depths:
         blocks = [(int(starts[i]), int(ends[i])) for i in np.flatnonzero(bdepth == dd)]
-        grp = groups_of(blocks)
+        if merged(blocks):
+            grp, _ = groups_of(blocks)
+            ub.begin_phase()
+            for (r0, r1, b0, b1) in grp:
+                DiT = block_inv(b0, b1).T[r0 - b0:r1 - b0]          # rows r0:r1 of inv(L_BB)^T, columns = block rows
+                cols, Lb = dense_cols(LtT, b0, b1, b1, n_top)
+                V = np.concatenate((DiT[:, r0 - b0:], -(DiT @ Lb)), axis=1)
+                ub.task(PLANE_J, r0, V, np.concatenate((_up_code(PLANE_Z, np.arange(r0, b1)), _up_code(PLANE_J, cols))))
+            ub.end_phase()
+            continue
+        grp, n_split = groups_of(blocks, splittable=True)
         ub.begin_phase()
         for (r0, r1, b0, b1) in grp:
-            sub = LtT[r0:r1]
-            idx = sub.indices
-            cols = np.unique(idx[idx >= b1])
-            if cols.size == 0:
-                continue
-            V = np.concatenate((-sub[:, cols].toarray(), np.eye(r1 - r0)), axis=1)
-            codes = np.concatenate((_up_code(PLANE_J, cols), _up_code(PLANE_Z, np.arange(r0, r1))))
-            ub.task(PLANE_Z, r0, V, codes)
+            cols, Lb = dense_cols(LtT, r0, r1, b1, n_top)
+            if cols.size:
+                ub.product(PLANE_Z, r0, -Lb, _up_code(PLANE_J, cols), self_plane=PLANE_Z, n_split=n_split)
         ub.end_phase()
         ub.begin_phase()
         for (r0, r1, b0, b1) in grp:
             Di = block_inv(b0, b1)
-            ub.task(PLANE_J, r0, Di.T[r0 - b0:r1 - b0, r0 - b0:], _up_code(PLANE_Z, np.arange(r0, b1)))
+            ub.product(PLANE_J, r0, Di.T[r0 - b0:r1 - b0, r0 - b0:], _up_code(PLANE_Z, np.arange(r0, b1)), n_split=n_split)
         ub.end_phase()
     return ub.finish(n_fwd)
 
@@ -616,6 +688,13 @@ def subdomain_plan(F, junc_face, d, NG, n_warps=RES_WARPS, groups=None, tt_max=N
     vrow_loc = np.full(n, -1, dtype=np.int64)            # shared-memory row of every local face in its subdomain
     cache = {}                                           # digest of a subdomain's inputs -> its program
     for s in range(P):
+        if loc[s].size == 0:             # a cut deeper than a small circuit's tree leaves subtrees without rows
+            hit = cache.setdefault(b"empty", (_pack_levels([], NG, n_warps, 0), 0, np.zeros(0, dtype=np.int64), [],
+                                              np.zeros(0), np.zeros((0, 0))))
+            plan.prog.append(hit[0])
+            plan.n_bwd.append(0)
+            plan.group_bounds.append([])
+            continue
         hrow, L0, Lh, digest = _subdomain_inputs(F, loc[s], top_rows[halo[s]], blk_of)
         hit = cache.get(digest)
         if hit is not None:
@@ -659,8 +738,8 @@ def subdomain_plan(F, junc_face, d, NG, n_warps=RES_WARPS, groups=None, tt_max=N
     # ---- upper separators between the subdomains and the top of the top
     plan.upper = _upper_program(F, top_rows, tt0, blk_of, max(1, int(n_chunks)), plan.n_up_pad)
     if plan.upper["n_fwd"] + plan.upper["n_bwd"] > 0:
-        # the upper phases gather into two panel buffers of at least 64 rows and reduce over 16 warps in shared memory
-        need = max(2 * 64 * PC, 16 * NG * 64) - plan.n_rows * PC
+        # the upper phases gather into two panel buffers of at least 256 rows and reduce over 16 warps in shared memory
+        need = max(2 * (128 if NG >= 8 else 256) * PC, 16 * NG * 64) - plan.n_rows * PC
         plan.stage_rows = max(plan.stage_rows, -(-need // (PC + 2)))
     # assembly of r_top: slots (subdomain halo rows) of every top row
     order = np.argsort(plan.halo_top, kind="stable")
@@ -765,7 +844,7 @@ def _run_level_host(ps, v, level, NG):
 
 
 def _run_upper_phase_host(up, U, ph):
-    """One phase of the upper program on the host; U is (3, n_up_pad, PC). Tasks of a phase are independent: all
+    """One phase of the upper program on the host; U is (4, n_up_pad, PC). Tasks of a phase are independent: all
     products are formed before any row is written, as on the device (where a grid barrier ends the phase)."""
     res = []
     mask = (1 << UP_PLANE_SHIFT) - 1
@@ -797,7 +876,7 @@ def apply_subdomain_plan_host(plan, b_perm):
             _run_level_host(ps, v, l, NG)
         ctop[plan.hptr[s]:plan.hptr[s + 1]] = v[plan.n_loc[s]: plan.n_loc[s] + plan.n_halo[s]]
         vec.append(v)
-    U = np.zeros((3, plan.n_up_pad, plan.PC))
+    U = np.zeros((4, plan.n_up_pad, plan.PC))
     U[PLANE_R, :plan.n_top] = b_perm[plan.top_rows]
     for k in range(plan.n_top):
         for sl in plan.tslot[plan.tptr[k]:plan.tptr[k + 1]]:

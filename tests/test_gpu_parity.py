@@ -139,7 +139,7 @@ def test_device_noise_statistics_and_shard_invariance():
 # ------------------------------------------------------------------------------------------------
 # subdomain engine (cooperative kernel): cut depths / chunk widths against a direct solve and the golden vectors
 # ------------------------------------------------------------------------------------------------
-SUBDOMAIN_CONFIGS = ["0,1", "1,2", "2,4", "3,4", "2,8", "4,1"]
+SUBDOMAIN_CONFIGS = ["0,1", "1,2", "2,4", "3,4", "3,8", "4,1"]
 
 
 @pytest.mark.parametrize("W", [13, 70])
@@ -320,11 +320,15 @@ def test_device_vortex_observables_are_exact(engine):
         os.environ.pop("JJ_ENGINE", None)
 
 
-def test_larger_circuit_runs_on_subdomain_engine_with_several_items_per_block():
+@pytest.mark.parametrize("tt_max", [None, "120", "0"])
+def test_larger_circuit_runs_on_subdomain_engine_with_several_items_per_block(tt_max, monkeypatch):
     # a circuit too large for one subdomain per (SM, chunk) pair (the cfg3 / cfg4 regime, scaled down): the layout cuts
-    # it finer, every block loops over several (subdomain, chunk) items per time step, the top product takes the
-    # grid-wide register-A path; per-step parity with the oracle
+    # it finer, every block loops over several (subdomain, chunk) items per time step; with a small dense top of the top
+    # (tt_max) the separators above the subdomains go through the upper program (block and warp tasks) every time step;
+    # per-step parity with the oracle
     from pyjjasim_b200 import engine
+    if tt_max is not None:
+        monkeypatch.setenv("JJ_TT_MAX", tt_max)
     a = pj.SquareArray(80, 80)
     W, Nt = 512, 12
     NG, chunks, n_parts = engine.subdomain_layout(a._Nf(), W, engine._sm_count(0))
@@ -336,6 +340,9 @@ def test_larger_circuit_runs_on_subdomain_engine_with_several_items_per_block():
     res = prob.compute()
     st = engine.last_run_stats[0]
     assert st["engine"] == 3 and st["cluster_size"] == n_parts
+    if tt_max is not None:
+        up = engine._tables_for(a, 0.05, n_parts).subdomain_plan(None, NG, chunks).upper
+        assert up["n_fwd"] > 0 and up["n_bwd"] > 0
     kw["current_sources"] = (a.current_base(angle=0)[:, None] * np.linspace(0.2, 1.8, W)[None, :])[:, :, None]
     args, extra = cases.oracle_inputs(kw)
     with warnings.catch_warnings():
