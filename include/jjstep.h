@@ -195,6 +195,24 @@ int jj_vortex_configuration(JJHandle *h, int64_t plane, int32_t *dst);
  * reference's vortex mobility (reference: time_evolution.py:1128-1133, get_vortex_mobility); exact integers */
 int jj_vortex_mobility(JJHandle *h, int64_t plane0, int64_t n_planes, int64_t *dst /* [W] */);
 
+/* all stored theta planes [plane0, plane0 + n_planes) at once: dst is (n_planes, Nf, W) int32, permuted faces. With it the
+ * vortex configurations of the stored steps leave the device as integers and the theta planes never have to
+ * (reference: time_evolution.py:734-755 evaluated on host copies of theta) */
+int jj_vortex_configurations(JJHandle *h, int64_t plane0, int64_t n_planes, int32_t *dst);
+
+/* ---- running observables: accumulated on the device WHILE stepping, no theta plane stored or copied ----
+ * Steps first_step + m * interval (m = 0, 1, ...) are OBSERVATIONS. At every observation the step kernel itself adds
+ * the vortex configuration n = -A round(theta / 2 pi) of that step into a per-(face, problem) integer sum and keeps
+ * theta of the first and of the latest observation, from which the host forms the quantities the reference's users
+ * average over stored planes (reference: time_evolution.py:734-755 and :422-458 over all stored steps):
+ *   time-averaged vortex configuration = nsum / count                     (exact integers)
+ *   DC junction voltage = (theta_latest - theta_first) / ((count - 1) interval dt)   (the stencil sum telescopes)
+ * The accumulators belong to the problem: they survive chunked jj_run calls and are cleared by jj_observe_begin
+ * (interval = 0 switches observation off). first_step must not lie before the steps already run. */
+int jj_observe_begin(JJHandle *h, int64_t first_step, int32_t interval);
+/* count = observations so far; nsum (Nf, W) int32, permuted faces; theta_first / theta_latest (Nj, W); any pointer may be NULL */
+int jj_observe_fetch(JJHandle *h, int64_t *count, int32_t *nsum, double *theta_first, double *theta_latest);
+
 /* Page-locked host memory for result planes: jj_fetch_* into such a buffer is a single DMA at PCIe speed instead of
  * a staged copy into pageable memory. The Python wrapper pools these blocks and hands them out as numpy arrays. */
 int jj_host_alloc(int device, uint64_t bytes, void **out);   /* device: whose context pins the block (portable) */

@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libjjstep.so")
+# JJ_LIB_PATH: an alternative build of the same library (build variants measured side by side, e.g. -DJJ_NOISE_F64)
+LIB_PATH = os.environ.get("JJ_LIB_PATH") or os.path.join(_HERE, "libjjstep.so")
 
 JJ_SRC_IS, JJ_SRC_F, JJ_SRC_VS, JJ_SRC_T = 0, 1, 2, 3
 JJ_KIND_ZERO, JJ_KIND_RANK1, JJ_KIND_DENSE = 0, 1, 2
@@ -21,7 +22,7 @@ EXPORTS = ["jj_create", "jj_destroy", "jj_last_error", "jj_set_circuit", "jj_set
            "jj_set_state", "jj_get_state", "jj_set_source", "jj_upload_source", "jj_upload_noise",
            "jj_alloc_outputs", "jj_run", "jj_fetch_theta", "jj_fetch_current", "jj_debug_noise",
            "jj_debug_solve", "jj_stats", "jj_set_subdomain_plan", "jj_debug_subdomain_solve", "jj_sm_count",
-           "jj_restart_at_rest", "jj_vortex_configuration", "jj_vortex_mobility",
+           "jj_restart_at_rest", "jj_vortex_configuration", "jj_vortex_mobility", "jj_vortex_configurations", "jj_observe_begin", "jj_observe_fetch",
            "jj_host_alloc", "jj_host_free"]
 
 _p = C.c_void_p
@@ -111,6 +112,9 @@ def load():
     lib.jj_restart_at_rest.argtypes = [_p]
     lib.jj_vortex_configuration.argtypes = [_p, C.c_int64, _i32p]
     lib.jj_vortex_mobility.argtypes = [_p, C.c_int64, C.c_int64, _i64p]
+    lib.jj_vortex_configurations.argtypes = [_p, C.c_int64, C.c_int64, _i32p]
+    lib.jj_observe_begin.argtypes = [_p, C.c_int64, C.c_int32]
+    lib.jj_observe_fetch.argtypes = [_p, C.POINTER(C.c_int64), _i32p, _f64p, _f64p]
     lib.jj_host_alloc.argtypes = [C.c_int, C.c_uint64, C.POINTER(_p)]
     lib.jj_host_free.argtypes = [_p]
     for name in EXPORTS:

@@ -1,0 +1,140 @@
+"""
+``AnnealingProblem``: the annealing caller of the stepping loop (reference: time_evolution.py:1070-1191, same
+constructor, same schedule), run as ONE device-resident schedule instead of one compute() per interval.
+"""
+import numpy as np
+
+from .josephson_circuit import Circuit
+
+__all__ = ["AnnealingProblem", "AnnealedConfiguration"]
+
+
+class AnnealedConfiguration:
+    """
+    One annealed problem: phases after the closing T = 0 runs and the vortex configuration the reference hands to
+    its static solver (reference: time_evolution.py:1185-1188). The reference then polishes the phases with
+    StaticProblem.compute() (static_problem.py) - a Newton solve outside the time-evolution path that this package
+    does not provide; the object therefore carries the un-polished state, and ``AnnealingProblem.compute`` reports
+    status 2 ("indeterminate") for it.
+    """
+
+    def __init__(self, circuit, theta, n, external_flux, current_sources):
+        self.circuit, self.theta, self.n = circuit, theta, n
+        self.external_flux, self.current_sources = external_flux, current_sources
+
+    def get_circuit(self):
+        return self.circuit
+
+    def get_theta(self):
+        return self.theta
+
+    def get_n(self):
+        return self.n
+
+    def get_vortex_configuration(self):
+        return self.n
+
+
+class AnnealingProblem:
+    """
+    Anneals a circuit by gradually lowering the temperature; the temperature profile follows the measured vortex
+    mobility (reference: time_evolution.py:1070-1191, same constructor, same schedule):
+
+     - interval_count iterations of interval_steps time steps, the first at T = start_T; every iteration restarts
+       from rest (theta(-2) = theta(-1));
+     - after each iteration the vortex mobility sum |n(i+1) - n(i)| / (Nf dt (interval_count - 1)) per problem is
+       compared with the target v (N - i)/N)^1.5 (or vortex_mobility[i]): above -> T /= T_factor, else T *= T_factor;
+     - five closing runs at T = 0 with half the time step.
+
+    The whole schedule runs on the GPU through ``engine.device_annealing``: state, factor and theta planes stay in
+    HBM, per iteration one integer per problem comes back and one temperature per problem goes out. The reference
+    re-enters compute() per iteration (refactorising, re-uploading and pulling interval_steps theta planes to the host).
+
+    Extra keyword arguments: noise_seed, noise_replay ((interval_count, interval_steps, Nj, W) array or callable
+    k -> (interval_steps, Nj, W)), devices.
+    """
+
+    def __init__(self, circuit: Circuit, time_step=0.5, interval_steps=10,
+                 external_flux=0.0, current_sources=0, problem_count=1,
+                 interval_count=1000, vortex_mobility=0.001,
+                 start_T=1.0, T_factor=1.03, *, noise_seed=None, noise_replay=None, devices=None):
+        self.circuit = circuit
+        self.time_step = time_step
+        self.interval_steps = interval_steps
+        self.interval_count = interval_count
+        self.vortex_mobility = vortex_mobility
+        self.current_sources = current_sources
+        self.external_flux = external_flux
+        self.problem_count = problem_count
+        self.T = start_T * np.ones((1, self.problem_count, 1))
+        self.T_factor = T_factor
+        self.noise_seed, self.noise_replay, self.devices = noise_seed, noise_replay, devices
+
+    def get_vortex_mobility(self, n):
+        """Vortex mobility of consecutive vortex configurations n (Nf, W, K) (reference: time_evolution.py:1128-1133)."""
+        Nf = self.circuit.face_count()
+        return np.sum(np.sum(np.abs(np.diff(n, axis=2)), axis=2), axis=0) / (Nf * self.time_step * (self.interval_count - 1))
+
+    def _temperature_adjustment(self, vortex_mobility, iteration):
+        # reference: time_evolution.py:1135-1140
+        v = self.vortex_mobility
+        upper = v[iteration] if (np.array(v)).size == self.interval_count else \
+            v * ((self.interval_count - iteration) / self.interval_count) ** 1.5
+        factor = (vortex_mobility > upper) * (1 / self.T_factor) + (vortex_mobility <= upper) * self.T_factor
+        self.T *= factor[..., None]
+
+    def _problem(self):
+        # the problem the reference's loop re-runs (reference: time_evolution.py:1159-1162); constructing it validates
+        # the inputs exactly as the reference does
+        f = np.atleast_1d(self.external_flux)[:, None, None]
+        from .time_evolution import TimeEvolutionProblem
+        return TimeEvolutionProblem(self.circuit, time_step_count=self.interval_steps, time_step=self.time_step,
+                                    external_flux=f, current_sources=self.current_sources, temperature=self.T,
+                                    store_current=False, store_voltage=False, stencil_width=3,
+                                    noise_seed=self.noise_seed, noise_replay=self.noise_replay, devices=self.devices)
+
+    def anneal(self):
+        """
+        The device part of compute(): the temperature schedule and the closing T = 0 runs.
+
+        Returns
+        -------
+        theta : (Nj, problem_count) phases after the closing runs
+        vortex_configuration : (Nf, problem_count) int array, n = -A round(theta / 2 pi)
+        temperature_profiles : (interval_count, problem_count)
+        """
+        from .engine import device_annealing
+        prob = self._problem()
+        Nf, dt, N = self.circuit.face_count(), self.time_step, self.interval_count
+        v, T_factor = self.vortex_mobility, self.T_factor
+
+        def adjust(sums, i, T):
+            # get_vortex_mobility + _temperature_adjustment on the exact integer sums of interval i
+            mob = sums / (Nf * dt * (N - 1))
+            upper = v[i] if (np.array(v)).size == N else v * ((N - i) / N) ** 1.5
+            factor = (mob > upper) * (1 / T_factor) + (mob <= upper) * T_factor
+            return T * factor
+
+        out = device_annealing(prob, self.T[0, :, 0], adjust, N)
+        self.T[0, :, 0] = out["T"]
+        self.last_stats = out["stats"]
+        return out["theta"], out["n"], out["profiles"]
+
+    def compute(self):
+        """
+        Executes the annealing procedure (reference: time_evolution.py:1142-1191).
+
+        Returns
+        -------
+        status : (problem_count,) int array; 2 (indeterminate) for every problem, because the static Newton solve
+            with which the reference decides between 0 (converged) and 1 (diverged) is outside this package
+        configurations : (problem_count,) list of AnnealedConfiguration (phases and vortex configuration of the
+            annealed state, before the reference's static polish)
+        temperature_profiles : (interval_count, problem_count) array
+        """
+        theta, n, profiles = self.anneal()
+        f = np.atleast_1d(self.external_flux)
+        configurations = [AnnealedConfiguration(self.circuit, theta[:, p].copy(), n[:, p].copy(), f, self.current_sources)
+                          for p in range(self.problem_count)]
+        status = np.full(self.problem_count, 2, dtype=int)
+        return status, configurations, profiles

@@ -81,14 +81,32 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, fl
     z1 = r * s;
 }
 
+// Double-precision variant (build with -DJJ_NOISE_F64): the same uniforms through log / sqrt / sincospi in float64. Kept
+// as a compile-time alternative so that its cost and its effect on the statistics can be measured
+// (profiles/r02_noise_precision.md); the shipped build uses the single-precision transform above.
+__device__ __forceinline__ void box_muller_f64(uint32_t a, uint32_t b, double& z0, double& z1) {
+    const double u = ((double)a + 0.5) * 2.3283064365386963e-10;      // (0, 1)
+    const double v = ((double)b + 0.5) * 2.3283064365386963e-10;
+    const double r = sqrt(-2.0 * log(u));
+    double s, c;
+    sincospi(2.0 * v, &s, &c);
+    z0 = r * c;
+    z1 = r * s;
+}
+
 __device__ __forceinline__ void normal4(uint64_t seed, int junction, long long group, long long step, double z[4]) {
     uint32_t o[4];
     philox4x32_10((uint32_t)junction, (uint32_t)group, (uint32_t)step, (uint32_t)((unsigned long long)step >> 32),
                   (uint32_t)seed, (uint32_t)(seed >> 32), o);
+#ifdef JJ_NOISE_F64
+    box_muller_f64(o[0], o[1], z[0], z[1]);
+    box_muller_f64(o[2], o[3], z[2], z[3]);
+#else
     float a, b, c, d;
     box_muller(o[0], o[1], a, b);
     box_muller(o[2], o[3], c, d);
     z[0] = a; z[1] = b; z[2] = c; z[3] = d;
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -75,6 +75,11 @@ struct JJHandle {
     long long th_cap_planes = 0, I_cap_planes = 0;   // allocated planes (kept across jj_set_problem calls of equal W)
     int *flag_d = nullptr;
     void *scratch = nullptr; size_t scratch_cap = 0;     // grow-only device scratch of the observable kernels (jj_observe.cu)
+    // running observables (jj_observe_begin): observations at steps obs_first + m * obs_interval
+    long long obs_first = 0, obs_count = 0; int obs_interval = 0;
+    int *obs_nsum = nullptr;                                  // [Nf][Wp] permuted faces
+    double *obs_th_first = nullptr, *obs_th_last = nullptr;   // canonical [Nj][Wp]
+    size_t obs_n_bytes = 0, obs_th_bytes = 0;
     // subdomain engine (see jj_subdomain.cu)
     void *subdomain_plan = nullptr;
     // stats
@@ -94,6 +99,11 @@ int subdomain_set_plan(JJHandle* h, const JJSubdomainPlan* plan);
 void subdomain_drop_plan(JJHandle* h);
 int subdomain_debug_solve(JJHandle* h, const double* b_d, double* J_d);
 void subdomain_get_config(JJHandle* h, int* P, int* PC);
+// implemented in jj_observe.cu
+void observe_free(JJHandle* h);
+bool observed_step(const JJHandle* h, long long step);
+long long observations_in(const JJHandle* h, long long i0, long long n);      // observations among steps [i0, i0 + n)
+int observe_streaming(JJHandle* h, long long step, const double* theta);      // streaming engine: one observation
 int dev_alloc(JJHandle* h, void** p, size_t bytes);
 void dev_free(JJHandle* h, void* p, size_t bytes);
 }

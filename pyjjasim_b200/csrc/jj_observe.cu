@@ -4,6 +4,7 @@
 //   vortex mobility sums  sum_f sum_t |n_f(t+1) - n_f(t)| per problem        (reference: time_evolution.py:1128-1133)
 //   restart at rest       theta(-2) := theta(-1)                            (reference: time_evolution.py:1169-1171)
 // Everything here is integer arithmetic on rounded phases: results are exact, not approximate.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -82,6 +83,16 @@ __global__ void __launch_bounds__(LANES * ROWS) k_vortex_mobility(const FaceView
     }
 }
 
+// nsum[f][w] += n_f(theta): one observation of the streaming engine (the subdomain engine accumulates inside its step
+// kernel, jj_subdomain.cu: vortex_pass)
+__global__ void __launch_bounds__(LANES * ROWS) k_vortex_accumulate(const FaceView c, const double* __restrict__ plane,
+                                                                     int* __restrict__ nsum) {
+    const int w = blockIdx.x * LANES + threadIdx.x;
+    const int f = blockIdx.y * ROWS + threadIdx.y;
+    if (w >= c.Wp || f >= c.Nf) return;
+    nsum[(size_t)f * c.Wp + w] += vorticity(c, plane, c.face_ptr[f], c.face_ptr[f + 1], w);
+}
+
 // device scratch kept in the handle: an annealing schedule calls jj_vortex_mobility once per interval, and a
 // cudaMalloc / cudaFree pair per call costs more than the kernel
 int scratch(JJHandle* h, size_t bytes, void** out) {
@@ -106,7 +117,106 @@ FaceView view(const JJHandle* h) {
 
 }  // namespace
 
+namespace jj {
+
+void observe_free(JJHandle* h) {
+    dev_free(h, h->obs_nsum, h->obs_n_bytes);
+    dev_free(h, h->obs_th_first, h->obs_th_bytes); dev_free(h, h->obs_th_last, h->obs_th_bytes);
+    h->obs_nsum = nullptr; h->obs_th_first = h->obs_th_last = nullptr; h->obs_n_bytes = h->obs_th_bytes = 0;
+    h->obs_interval = 0; h->obs_first = 0; h->obs_count = 0;
+}
+
+bool observed_step(const JJHandle* h, long long step) {
+    return h->obs_interval > 0 && step >= h->obs_first && (step - h->obs_first) % h->obs_interval == 0;
+}
+
+long long observations_in(const JJHandle* h, long long i0, long long n) {
+    if (h->obs_interval <= 0 || n <= 0) return 0;
+    const long long last = i0 + n - 1;
+    if (last < h->obs_first) return 0;
+    // m ranges over first + m * interval in [max(i0, first), last]
+    const long long lo = i0 <= h->obs_first ? 0 : (i0 - h->obs_first + h->obs_interval - 1) / h->obs_interval;
+    const long long hi = (last - h->obs_first) / h->obs_interval;
+    return hi >= lo ? hi - lo + 1 : 0;
+}
+
+int observe_streaming(JJHandle* h, long long step, const double* theta) {
+    const FaceView c = view(h);
+    if (c.Nf > 0) {
+        dim3 grid((c.Wp + LANES - 1) / LANES, (c.Nf + ROWS - 1) / ROWS), block(LANES, ROWS);
+        k_vortex_accumulate<<<grid, block, 0, h->stream>>>(c, theta, h->obs_nsum);
+        h->launches++;
+    }
+    if (step == h->obs_first) CK(cudaMemcpyAsync(h->obs_th_first, theta, h->obs_th_bytes, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->obs_th_last, theta, h->obs_th_bytes, cudaMemcpyDeviceToDevice, h->stream));
+    h->obs_count++;
+    return JJ_OK;
+}
+
+}  // namespace jj
+
 extern "C" {
+
+int jj_observe_begin(JJHandle* h, int64_t first_step, int32_t interval) {
+    CK(cudaSetDevice(h->device));
+    REQUIRE(h->have_problem, JJ_ESTATE, "observe_begin: problem not set");
+    REQUIRE(interval >= 0, JJ_EINVAL, "observe_begin: negative interval");
+    CK(cudaStreamSynchronize(h->stream));
+    if (interval == 0) { observe_free(h); return JJ_OK; }
+    REQUIRE(first_step >= h->steps_done, JJ_EINVAL, "observe_begin: first_step lies before the steps already run");
+    const size_t nb = (size_t)std::max(h->cir.Nf, 1) * h->Wp * sizeof(int), tb = (size_t)h->cir.Nj * h->Wp * sizeof(double);
+    if (nb != h->obs_n_bytes || tb != h->obs_th_bytes) {
+        observe_free(h);
+        int rc;
+        if ((rc = dev_alloc(h, (void**)&h->obs_nsum, nb))) return rc;
+        h->obs_n_bytes = nb;
+        if ((rc = dev_alloc(h, (void**)&h->obs_th_first, tb))) return rc;
+        h->obs_th_bytes = tb;
+        if ((rc = dev_alloc(h, (void**)&h->obs_th_last, tb))) { h->obs_th_bytes = 0; return rc; }
+    }
+    CK(cudaMemsetAsync(h->obs_nsum, 0, nb, h->stream));
+    CK(cudaMemsetAsync(h->obs_th_first, 0, tb, h->stream));
+    CK(cudaMemsetAsync(h->obs_th_last, 0, tb, h->stream));
+    h->obs_first = first_step; h->obs_interval = interval; h->obs_count = 0;
+    return JJ_OK;
+}
+
+int jj_observe_fetch(JJHandle* h, int64_t* count, int32_t* nsum, double* theta_first, double* theta_latest) {
+    CK(cudaSetDevice(h->device));
+    REQUIRE(h->have_problem && h->obs_interval > 0, JJ_ESTATE, "observe_fetch: no observation in progress");
+    if (count) *count = h->obs_count;
+    const size_t wi = (size_t)h->W * sizeof(int), wpi = (size_t)h->Wp * sizeof(int);
+    const size_t wd = (size_t)h->W * sizeof(double), wpd = (size_t)h->Wp * sizeof(double);
+    if (nsum && h->cir.Nf > 0) CK(cudaMemcpy2DAsync(nsum, wi, h->obs_nsum, wpi, wi, h->cir.Nf, cudaMemcpyDeviceToHost, h->stream));
+    if (theta_first) CK(cudaMemcpy2DAsync(theta_first, wd, h->obs_th_first, wpd, wd, h->cir.Nj, cudaMemcpyDeviceToHost, h->stream));
+    if (theta_latest) CK(cudaMemcpy2DAsync(theta_latest, wd, h->obs_th_last, wpd, wd, h->cir.Nj, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return JJ_OK;
+}
+
+int jj_vortex_configurations(JJHandle* h, int64_t plane0, int64_t n_planes, int32_t* dst) {
+    CK(cudaSetDevice(h->device));
+    REQUIRE(h->have_problem, JJ_ESTATE, "vortex_configurations: problem not set");
+    REQUIRE(plane0 >= 0 && n_planes >= 0 && plane0 + n_planes <= h->n_th_planes, JJ_EINVAL,
+            "vortex_configurations: theta plane range out of bounds");
+    if (h->cir.Nf == 0 || n_planes == 0) return JJ_OK;
+    const FaceView c = view(h);
+    // two scratch planes: the kernel of plane p + 1 runs while plane p is copied out
+    int* buf = nullptr;
+    const size_t pe = (size_t)c.Nf * c.Wp;
+    int rc = scratch(h, 2 * pe * sizeof(int), (void**)&buf);
+    if (rc) return rc;
+    dim3 grid((c.Wp + LANES - 1) / LANES, (c.Nf + ROWS - 1) / ROWS), block(LANES, ROWS);
+    const size_t wi = (size_t)h->W * sizeof(int), wpi = (size_t)c.Wp * sizeof(int);
+    for (int64_t p = 0; p < n_planes; ++p) {
+        int* b = buf + (size_t)(p & 1) * pe;
+        k_vortex_configuration<<<grid, block, 0, h->stream>>>(c, h->th_out + (size_t)(plane0 + p) * c.Nj * c.Wp, b);
+        h->launches++;
+        CK(cudaMemcpy2DAsync(dst + (size_t)p * c.Nf * h->W, wi, b, wpi, wi, c.Nf, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return JJ_OK;
+}
 
 int jj_restart_at_rest(JJHandle* h) {
     CK(cudaSetDevice(h->device));

@@ -81,6 +81,10 @@ struct SubArgs {
     const long long* th_plane; const long long* I_plane;
     double *snap_th, *snap_I;
     int* flag;
+    // running observables (jj_observe_begin): steps obs_first + m * obs_interval add their vortex configuration to
+    // obs_nsum [Nf][Wp] (permuted faces) and leave their phases in obs_th_last (the first one also in obs_th_first)
+    long long obs_first; int obs_interval;
+    int* obs_nsum; double *obs_th_first, *obs_th_last;
     const double* dbg_b; double* dbg_J;   // debug solve: canonical [Nf][Wp], permuted faces
     long long* prof;                       // optional per-block cycle counters [block][8]
     int dbg;                               // JJ_SUB_DEBUG (read once per plan): 4 no chunk-local top phase, 64 direct top
@@ -447,6 +451,8 @@ __device__ __forceinline__ void junction_item(const SubArgs& a, const AmpCache<8
             double2* o2 = reinterpret_cast<double2*>(a.th2 + cidx);
             o1[0] = make_double2(th1[0], th1[1]); o1[1] = make_double2(th1[2], th1[3]);
             o2[0] = t0; o2[1] = t1;
+            // (the state slab is only read again by the vortex pass of an observed last step)
+            stg256_hint(a.rth + sidx, make_double2(th1[0], th1[1]), make_double2(th1[2], th1[3]), pol_first);
             return;
         }
     }
@@ -622,6 +628,68 @@ __device__ void face_pass(const SubArgs& a, const AmpCache<8 * NG>* ac, int s, i
             dst[0] = make_double2(acc[u][0], acc[u][1]);
             dst[1] = make_double2(acc[u][2], acc[u][3]);
         }
+    }
+}
+
+// One OBSERVATION (running observables, jj_observe_begin): add n = -A round(theta / 2 pi) of the step just finished
+// into the per-(face, problem) sums and leave its phases in the mark planes, straight from the state slab this block
+// has just written - no theta plane is stored. Same row lists as the face pass (the coefficient's sign is the cycle
+// matrix entry); local rows belong to this block alone (plain read-modify-write, 16 bytes per thread), halo rows
+// receive one partial sum per subdomain that owns junctions of the face (integer atomics: exact in any order). True
+// division and round-to-nearest-even, like np.round(theta / (2 pi)) (reference: time_evolution.py:734-755).
+// (not inlined, and called with plain values instead of the argument block: its registers must not weigh on the step
+// kernel, which runs it only at observed steps)
+struct VortexView {
+    const int* fj; const double* fc; const int* fidx; const int* ht; const int* top_face;
+    const double* th; const double* jrec;
+    int* nsum; double* th_last; double* th_first;       // th_first: null except at the first observation
+    int K, rows, nl, jlo, jhi, c, Wp;
+};
+
+template <int NG>
+__device__ __noinline__ void vortex_pass(const VortexView o) {
+    constexpr int PC = 8 * NG, G = PC / 4;
+    for (int idx = threadIdx.x; idx < o.rows * G; idx += NT) {
+        const int row = idx / G, q = (idx % G) * 4, w = o.c * PC + q;
+        if (w >= o.Wp) continue;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int k0 = 0; k0 < o.K; k0 += 4) {
+            const int4 j4 = __ldg(reinterpret_cast<const int4*>(o.fj + (size_t)row * o.K + k0));
+            const double2 ca = __ldg(reinterpret_cast<const double2*>(o.fc + (size_t)row * o.K + k0));
+            const double2 cb = __ldg(reinterpret_cast<const double2*>(o.fc + (size_t)row * o.K + k0) + 1);
+            const int jp[4] = {j4.x, j4.y, j4.z, j4.w};
+            const double cf[4] = {ca.x, ca.y, cb.x, cb.y};
+            double4v t[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) t[k] = ldg256(o.th + (size_t)max(jp[k], 0) * PC + q);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (jp[k] < 0) continue;
+                const double sg = cf[k] > 0.0 ? 1.0 : -1.0;
+                acc[0] -= sg * rint(t[k].lo.x / TWO_PI); acc[1] -= sg * rint(t[k].lo.y / TWO_PI);
+                acc[2] -= sg * rint(t[k].hi.x / TWO_PI); acc[3] -= sg * rint(t[k].hi.y / TWO_PI);
+            }
+        }
+        if (row < o.nl) {
+            int4* dst = reinterpret_cast<int4*>(o.nsum + (size_t)__ldg(o.fidx + row) * o.Wp + w);
+            int4 v4 = *dst;
+            v4.x += (int)acc[0]; v4.y += (int)acc[1]; v4.z += (int)acc[2]; v4.w += (int)acc[3];
+            *dst = v4;
+        } else {
+            int* dst = o.nsum + (size_t)__ldg(o.top_face + __ldg(o.ht + (row - o.nl))) * o.Wp + w;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if ((int)acc[e] != 0) atomicAdd(dst + e, (int)acc[e]);
+        }
+    }
+    // phase marks of the junctions this subdomain owns, canonical [Nj][Wp] by original junction index
+    for (int idx = threadIdx.x; idx < (o.jhi - o.jlo) * G; idx += NT) {
+        const int jp = o.jlo + idx / G, q = (idx % G) * 4, w = o.c * PC + q;
+        if (w >= o.Wp) continue;
+        const int jo = __ldg(reinterpret_cast<const int4*>(o.jrec + 8 * (size_t)jp + 6)).z;
+        const double4v t = ldg256(o.th + (size_t)jp * PC + q);
+        stg256(o.th_last + (size_t)jo * o.Wp + w, t.lo, t.hi);
+        if (o.th_first) stg256(o.th_first + (size_t)jo * o.Wp + w, t.lo, t.hi);
     }
 }
 
@@ -1274,6 +1342,16 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
             }
             if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 0] += tn - tq; tq = tn; }
             junction_pass<NG, DEF>(a, ac, s, c, n, k > 0, k < a.n, v);
+            if (k > 0 && a.obs_interval > 0 && n - 1 >= a.obs_first && (n - 1 - a.obs_first) % a.obs_interval == 0) {
+                __syncthreads();                 // the phases of step n - 1 are in the state slab
+                VortexView o;
+                o.fj = a.face_ell_j + (size_t)s * a.n_rows * a.face_K; o.fc = a.face_ell_c + (size_t)s * a.n_rows * a.face_K;
+                o.fidx = a.face_fidx + (size_t)s * a.n_rows; o.ht = a.halo_top + a.hptr[s]; o.top_face = a.top_face;
+                o.th = a.rth + (size_t)c * a.Nj * PC; o.jrec = a.jrec;
+                o.nsum = a.obs_nsum; o.th_last = a.obs_th_last; o.th_first = (n - 1 == a.obs_first) ? a.obs_th_first : nullptr;
+                o.K = a.face_K; o.rows = nl + nh; o.nl = nl; o.jlo = a.junc_ptr[s]; o.jhi = a.junc_ptr[s + 1]; o.c = c; o.Wp = a.Wp;
+                vortex_pass<NG>(o);
+            }
             if (k == a.n) { __syncthreads(); continue; }
             __syncthreads();
             if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 1] += tn - tq; tq = tn; }
@@ -1601,6 +1679,8 @@ static void fill_args(JJHandle* h, SubState* st, SubArgs& a) {
     a.rth = st->rth; a.rx = st->rx; a.th1 = h->th1; a.th2 = h->th2;
     a.zloc = st->zloc; a.ctop = st->ctop; a.rtop = st->rtop; a.jtop = st->jtop; a.bar = st->bar;
     a.snap_th = h->th_out; a.snap_I = h->I_out; a.flag = h->flag_d;
+    a.obs_first = h->obs_first; a.obs_interval = h->obs_interval;
+    a.obs_nsum = h->obs_nsum; a.obs_th_first = h->obs_th_first; a.obs_th_last = h->obs_th_last;
     a.dbg = st->dbg;
 }
 

@@ -385,6 +385,7 @@ static void free_problem(JJHandle* h) {
     dev_free(h, h->th_out, (size_t)h->th_cap_planes * nj); dev_free(h, h->I_out, (size_t)h->I_cap_planes * nj);
     h->th_out = h->I_out = nullptr; h->n_th_planes = h->n_I_planes = 0; h->th_cap_planes = h->I_cap_planes = 0;
     subdomain_free_problem(h);
+    observe_free(h);
     h->have_problem = h->have_state = false;
 }
 
@@ -472,6 +473,7 @@ int jj_set_problem(JJHandle* h, int32_t W, double dt, uint64_t seed, int64_t pro
         // the output planes stay allocated (jj_alloc_outputs reuses them when they are large enough): cudaFree and
         // cudaMalloc of ~100 MB cost tens of milliseconds per compute() call
         h->n_th_planes = h->n_I_planes = 0;
+        observe_free(h);
     } else {
         free_problem(h);
     }
@@ -680,6 +682,10 @@ static int streaming_run(JJHandle* h, long long i0, int n, const long long* th_p
         if (c.default_cpr) k_step<true><<<sblocks, 256, 0, h->stream>>>(a);
         else k_step<false><<<sblocks, 256, 0, h->stream>>>(a);
         h->launches++;
+        if (k > 0 && observed_step(h, nn - 1)) {
+            int rc = observe_streaming(h, nn - 1, a.th_out);
+            if (rc) return rc;
+        }
         if (k == n) break;
         if (c.Nf > 0) {
             fa.n = nn;
@@ -730,6 +736,7 @@ int jj_run(JJHandle* h, int64_t i0, int32_t n, const int64_t* th_plane, const in
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->last_ms = ms;
+    if (want == JJ_ENGINE_SUBDOMAIN) h->obs_count += observations_in(h, i0, n);
     h->steps_done += n;
     int flag = 0;
     CK(cudaMemcpy(&flag, h->flag_d, sizeof(int), cudaMemcpyDeviceToHost));

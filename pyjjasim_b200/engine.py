@@ -32,6 +32,7 @@ __all__ = ["device_time_evolution_core", "CircuitTables", "DeviceEngine", "last_
 
 _TABLE_BYTES = 64 << 20      # budget for one chunk of rank-one amplitude tables
 _DENSE_BYTES = 256 << 20     # budget for one chunk of dense tables / injected noise
+_PLANE_BYTES = 48 << 30      # budget for the theta / current planes one jj_run call keeps on the device (180 GB HBM3e)
 last_run_stats = {}          # filled by device_time_evolution_core (per device), for benchmarks and tests
 
 
@@ -550,6 +551,34 @@ class DeviceEngine:
         n[self.tab.perm] = out
         return n.astype(int)
 
+    def vortex_configurations(self, plane0, n_planes):
+        """n of the stored theta planes [plane0, plane0 + n_planes) in one call: (n_planes, Nf, W) int32, ORIGINAL face
+        numbering; the theta planes themselves stay on the device."""
+        out = np.zeros((int(n_planes), self.tab.Nf, self.W), dtype=np.int32)
+        if n_planes and self.tab.Nf:
+            self._ck(self.lib.jj_vortex_configurations(self.h, int(plane0), int(n_planes), _lib.i32(out)))
+        n = np.empty_like(out)
+        n[:, self.tab.perm] = out
+        return n
+
+    def observe_begin(self, first_step, interval):
+        """Running observables: every ``interval``-th step from ``first_step`` on, the step kernel adds the vortex
+        configuration into per-(face, problem) sums and keeps the phases of the first and the latest observation
+        (0 switches it off)."""
+        self._ck(self.lib.jj_observe_begin(self.h, int(first_step), int(interval)))
+
+    def observe_fetch(self, marks=True):
+        """-> (count, nsum (Nf, W) int32 in the ORIGINAL face numbering, theta_first, theta_latest ((Nj, W) or None))"""
+        cnt = C.c_int64(0)
+        ns = np.zeros((self.tab.Nf, self.W), dtype=np.int32)
+        t0 = np.empty((self.tab.Nj, self.W)) if marks else None
+        t1 = np.empty((self.tab.Nj, self.W)) if marks else None
+        self._ck(self.lib.jj_observe_fetch(self.h, C.byref(cnt), _lib.i32(ns), _lib.f64(t0) if marks else None,
+                                           _lib.f64(t1) if marks else None))
+        n = np.empty_like(ns)
+        n[self.tab.perm] = ns
+        return int(cnt.value), n, t0, t1
+
     def vortex_mobility_sums(self, plane0, n_planes):
         """(W,) integer sums over faces and consecutive stored planes of |n(t+1) - n(t)|
         (numerator of the reference's get_vortex_mobility, time_evolution.py:1128-1133)."""
@@ -721,7 +750,8 @@ def _setup_sources(eng, specs, sh, tab):
                 eng.upload_source(which, 0, _dense_for_device(name, sh.dense(name, 0, 1), tab))
 
 
-def _run_shard(problem, tab, specs, dev, w0, w1, th_mask, I_mask, th_host, I_host, engine_kind, stats_out, seed=0):
+def _run_shard(problem, tab, specs, dev, w0, w1, th_mask, I_mask, th_host, I_host, engine_kind, stats_out, seed=0,
+               extras=None):
     """Integrate problems [w0, w1) on one device and write stored planes into th_host / I_host
     (plane-major (n_planes + 2, Nj, W) arrays, planes 0 and 1 are the initial conditions)."""
     Nj, Nf, Nt, dt = tab.Nj, tab.Nf, problem._Nt(), problem._dt()
@@ -731,7 +761,13 @@ def _run_shard(problem, tab, specs, dev, w0, w1, th_mask, I_mask, th_host, I_hos
     ok = False
     try:
         eng.set_problem(W, dt, seed=seed, problem_offset=w0, engine=engine_kind)
-        eng.set_state(problem.config_at_minus_1[:, w0:w1], problem.config_at_minus_2[:, w0:w1])
+        at_rest = getattr(problem, "starts_at_rest_with_zero_phases", None)
+        if not (at_rest is not None and at_rest()):       # (jj_set_problem has cleared the state: nothing to upload)
+            eng.set_state(problem.config_at_minus_1[:, w0:w1], problem.config_at_minus_2[:, w0:w1])
+        ex = extras or {}
+        if ex.get("interval"):
+            eng.observe_begin(ex.get("first", 0), ex["interval"])
+        fetch_theta = ex.get("fetch_theta", True)
         sh = _ShardInputs(specs, w0, w1)
         replay = getattr(problem, "noise_replay", None)
         # static parts
@@ -742,8 +778,13 @@ def _run_shard(problem, tab, specs, dev, w0, w1, th_mask, I_mask, th_host, I_hos
         I_idx = np.cumsum(I_mask) - 1
         total_ms = 0.0
         i0 = 0
+        # planes kept on the device per jj_run call: a chunk of steps ends before its stored planes outgrow the budget
+        kept = np.concatenate(([0], np.cumsum(th_mask.astype(np.int64) + I_mask.astype(np.int64))))
+        plane_budget = max(1, int(_PLANE_BYTES // (Nj * W * 8)))
         while i0 < Nt:
             i1 = min(Nt, i0 + K)
+            if kept[i1] - kept[i0] > plane_budget:
+                i1 = max(i0 + 1, int(np.searchsorted(kept, kept[i0] + plane_budget, side="right")) - 1)
             n = i1 - i0
             try:
                 tables = []
@@ -798,13 +839,27 @@ def _run_shard(problem, tab, specs, dev, w0, w1, th_mask, I_mask, th_host, I_hos
             ip = np.where(im, np.cumsum(im) - 1, -1)
             eng.run(i0, n, tp, ip)
             total_ms += eng.stats()["step_ms"]
-            if n_th:
+            if n_th and ex.get("vortex_planes"):
+                # vortex configurations of the steps the caller asked for, computed where the phases are
+                wanted = np.flatnonzero(ex["wanted"][i0:i1][tm])
+                if wanted.size:
+                    n_all = eng.vortex_configurations(int(wanted[0]), int(wanted[-1] - wanted[0] + 1))
+                    dst0 = int(np.count_nonzero(ex["wanted"][:i0]))
+                    ex["n_planes"][dst0:dst0 + wanted.size, :, w0:w1] = n_all[wanted - wanted[0]]
+            if n_th and fetch_theta:
                 first = th_idx[i0:i1][tm][0]
                 eng.fetch_theta(0, n_th, out=th_host[2 + first: 2 + first + n_th, :, w0:w1])
             if n_I:
                 first = I_idx[i0:i1][im][0]
                 eng.fetch_current(0, n_I, out=I_host[2 + first: 2 + first + n_I, :, w0:w1])
             i0 = i1
+        if ex.get("interval"):
+            cnt, nsum, t_first, t_last = eng.observe_fetch()
+            ex["count"] = cnt
+            ex["nsum"][:, w0:w1] = nsum
+            ex["theta_first"][:, w0:w1] = t_first
+            ex["theta_latest"][:, w0:w1] = t_last
+            eng.observe_begin(0, 0)
         st = eng.stats()
         st["total_ms"] = total_ms
         st["problems"] = W
@@ -834,7 +889,7 @@ def _dense_for_device(name, table, tab):
 
 
 def device_time_evolution_core(problem, th_store_mask, I_store_mask, engine=None, shard=None, device=None,
-                               initial_planes=True, noise_seed=None):
+                               initial_planes=True, noise_seed=None, extras=None):
     """
     Device replacement of time_evolution_core (reference: time_evolution.py:461-582), stencil width 3.
     Returns th_out, I_out of shape (Nj, W, n_stored + 2).
@@ -843,6 +898,10 @@ def device_time_evolution_core(problem, th_store_mask, I_store_mask, engine=None
     (no voltage requested), which saves two passes over (Nj, W) arrays per plane on the host.
     shard=(w0, w1), device=d: integrate only problems [w0, w1) on GPU d and return (Nj, w1 - w0, .) arrays
     (used by distributed.compute_sharded, one process per GPU, which also passes the job-wide noise_seed).
+    extras: dict describing what else the device should produce beside the planes; filled in place:
+      interval, first       running observables (jj_observe_begin) -> count, nsum (Nf, W) int32, theta_first, theta_latest
+      vortex_planes, wanted vortex configurations of the wanted stored steps -> n_planes (n_wanted, Nf, W) int32
+      fetch_theta           False: the kept theta planes stay on the device (only the two initial planes are returned)
     """
     if getattr(problem, "stencil_width", 3) != 3:
         raise NotImplementedError("only stencil_width=3 is supported")
@@ -865,18 +924,34 @@ def device_time_evolution_core(problem, th_store_mask, I_store_mask, engine=None
     specs = _classify_all(problem, tab)
     # every plane is written below: the two initial conditions here, the stored steps by the shards
     pin_dev = devices[0] if device is None else device
-    th_host = _pinned.empty((int(th_mask.sum()) + 2, Nj, W), pin_dev) if th_mask.any() else np.empty((2, Nj, W))
+    ex = extras if extras is not None else {}
+    if ex.get("interval"):
+        ex["nsum"] = np.zeros((tab.Nf, W), dtype=np.int32)
+        ex["theta_first"], ex["theta_latest"], ex["count"] = np.zeros((Nj, W)), np.zeros((Nj, W)), 0
+    if ex.get("vortex_planes"):
+        ex["wanted"] = np.asarray(ex.get("wanted", th_mask), dtype=bool) & th_mask
+        ex["n_planes"] = np.zeros((int(ex["wanted"].sum()), tab.Nf, W), dtype=np.int32)
+    keep_theta = th_mask.any() and ex.get("fetch_theta", True)
+    th_host = _pinned.empty((int(th_mask.sum()) + 2, Nj, W), pin_dev) if keep_theta else np.empty((2, Nj, W))
     I_host = _pinned.empty((int(I_mask.sum()) + 2, Nj, W), pin_dev) if I_mask.any() else np.empty((2, Nj, W))
+    at_rest = getattr(problem, "starts_at_rest_with_zero_phases", None)
+    at_rest = at_rest is not None and at_rest()          # no initial condition given: nothing is materialised for it
     if initial_planes:
-        th_host[1] = problem.config_at_minus_1
-        th_host[0] = problem.config_at_minus_2
+        if at_rest:
+            th_host[:2] = 0.0
+        else:
+            th_host[1] = problem.config_at_minus_1
+            th_host[0] = problem.config_at_minus_2
     if not initial_planes:
         pass
     elif I_mask.any():
         # supercurrent of the initial conditions (reference: time_evolution.py:487); only read when currents
         # are stored or differentiated, so the two full-size sin passes are skipped otherwise
-        I_host[1] = problem._cp(problem.config_at_minus_1)
-        I_host[0] = problem._cp(problem.config_at_minus_2)
+        if at_rest:
+            I_host[:2] = problem._cp(np.zeros((Nj, 1)))
+        else:
+            I_host[1] = problem._cp(problem.config_at_minus_1)
+            I_host[0] = problem._cp(problem.config_at_minus_2)
     else:
         I_host[:2] = 0.0
     if engine is None:
@@ -892,13 +967,13 @@ def device_time_evolution_core(problem, th_store_mask, I_store_mask, engine=None
         pass
     elif len(jobs) == 1:
         dev, w0, w1 = jobs[0]
-        _run_shard(problem, tab, specs, dev, w0, w1, th_mask, I_mask, th_host, I_host, engine, stats, seed)
+        _run_shard(problem, tab, specs, dev, w0, w1, th_mask, I_mask, th_host, I_host, engine, stats, seed, ex)
     else:
         errors = []
 
         def work(dev, w0, w1):
             try:
-                _run_shard(problem, tab, specs, dev, w0, w1, th_mask, I_mask, th_host, I_host, engine, stats, seed)
+                _run_shard(problem, tab, specs, dev, w0, w1, th_mask, I_mask, th_host, I_host, engine, stats, seed, ex)
             except Exception as e:      # surfaced after join
                 errors.append(e)
         threads = [threading.Thread(target=work, args=j) for j in jobs]

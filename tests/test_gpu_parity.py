@@ -86,6 +86,36 @@ def test_device_solve_matches_direct_solve():
     assert np.max(np.abs(J - Jref)) <= 1e-12 * np.max(np.abs(Jref))
 
 
+@pytest.mark.parametrize("engine", ENGINES)
+def test_reference_style_problem_object_through_the_device_core(engine, monkeypatch):
+    # INTEGRATION.md's binding: the reference's own TimeEvolutionProblem (no _raw_sources, inputs as (N, W, Nt) broadcast
+    # views or callables, time-dependence flags frozen at construction) and a circuit offering only the reference's
+    # getters go through device_time_evolution_core; per-step parity with the oracle, and the fast engine must be the
+    # one that ran (constants held as broadcast views are not "dense time-dependent tables")
+    from pyjjasim_b200 import engine as eng_mod
+    from tests.refstyle import RefStyleProblem, RefStyleCircuit
+    monkeypatch.setenv("JJ_ENGINE", engine)
+    a = pj.SquareArray(14, 12)
+    a.set_inductance(0.05)
+    W, Nt, dt = 10, 60, 0.05
+    base, amps = a.current_base(angle=0), np.linspace(0.3, 1.6, W)
+    Is = lambda i: base[:, None] * (amps + 0.2 * np.sin(0.4 * i * dt))[None, :]
+    Vs = np.zeros((a._Nj(), 1, 1)); Vs[3] = 0.02
+    kw = dict(time_step=dt, time_step_count=Nt, external_flux=0.1, current_sources=Is, voltage_sources=Vs)
+    prob = RefStyleProblem(RefStyleCircuit(a), current_phase_relation=pj.DefaultCPR(), **kw)
+    mask = np.zeros(Nt, dtype=bool); mask[[5, 30, Nt - 1]] = True
+    th, I = eng_mod.device_time_evolution_core(prob, mask, mask)
+    assert th.shape == (a._Nj(), W, 5) and I.shape == th.shape
+    if engine == "auto":
+        assert eng_mod.last_run_stats[0]["engine"] == 3
+    args, extra = cases.oracle_inputs(dict(kw, circuit=a, store_time_steps=[5, 30, Nt - 1], store_voltage=False))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        th_o, I_o, _ = oracle.time_evolution(*args, W, **extra)
+    assert np.max(np.abs(th[:, :, 2:] - th_o)) <= 1e-9 and np.max(np.abs(I[:, :, 2:] - I_o)) <= 1e-9
+    assert np.array_equal(th[:, :, 1], prob.config_at_minus_1) and np.array_equal(th[:, :, 0], prob.config_at_minus_2)
+
+
 def test_chunked_run_equals_single_run(monkeypatch):
     # time-dependent tables uploaded chunk by chunk give the same result as one chunk
     from pyjjasim_b200 import engine
@@ -134,6 +164,44 @@ def test_device_noise_statistics_and_shard_invariance():
     assert abs(z.mean()) < 5 / np.sqrt(n) and abs(z.var() - 1) < 5 * np.sqrt(2 / n)
     assert abs(np.mean(z ** 4) - 3) < 0.1 and np.max(np.abs(z)) < 7
     assert abs(np.corrcoef(z[:-1].ravel(), z[1:].ravel())[0, 1]) < 5 / np.sqrt(n)
+
+
+def test_device_normals_distribution_and_tails():
+    # the device draws (Philox4x32-10 + single-precision Box-Muller) as a distribution: Kolmogorov-Smirnov distance
+    # from the standard normal on 1.2e7 draws, tail mass beyond 3 / 4 / 5 sigma against the exact values within their
+    # Poisson noise, per-junction and per-problem means (no structure along either counter axis), and the largest
+    # |z| (32-bit uniforms: the transform reaches 6.66 sigma, P(|z| > 6.66) = 2.7e-11 of the mass is cut)
+    import scipy.stats
+    from pyjjasim_b200 import engine
+    a = pj.SquareArray(40, 40)
+    tab = engine.CircuitTables(a, 0.05)
+    eng = engine.DeviceEngine(0)
+    eng.set_circuit(tab, pj.DefaultCPR())
+    W, steps = 128, 30
+    eng.set_problem(W, 0.05, seed=20261018)
+    z = np.stack([eng.debug_noise(s) for s in range(steps)])           # (steps, Nj, W)
+    eng.close()
+    n = z.size
+    assert n >= 1.1e7
+    flat = np.sort(z.ravel())
+    cdf = scipy.stats.norm.cdf(flat)
+    grid = np.arange(1, n + 1) / n
+    D = max(np.max(grid - cdf), np.max(cdf - (grid - 1.0 / n)))
+    assert D < 1.63 / np.sqrt(n), D                                      # KS critical value at alpha = 0.01
+    for k in (3.0, 4.0, 5.0):
+        expect = 2 * scipy.stats.norm.sf(k) * n
+        got = float(np.count_nonzero(np.abs(flat) > k))
+        assert abs(got - expect) <= 5 * np.sqrt(expect) + 3, (k, got, expect)
+    assert 4.8 < np.max(np.abs(flat)) < 6.7
+    assert abs(scipy.stats.skew(flat)) < 5 * np.sqrt(6 / n) and abs(scipy.stats.kurtosis(flat)) < 5 * np.sqrt(24 / n)
+    # independence across the counter axes: means per junction / per problem / per step are those of white noise
+    for axis_keep, cnt in ((1, steps * W), (2, steps * a._Nj()), (0, a._Nj() * W)):
+        m = z.mean(axis=tuple(i for i in range(3) if i != axis_keep))
+        assert np.max(np.abs(m)) < 5.5 / np.sqrt(cnt)
+        assert abs(m.var() * cnt - 1.0) < 6 * np.sqrt(2.0 / m.size)
+    # neighbouring problems / junctions / steps are uncorrelated
+    for u, v in ((z[:, :, :-1], z[:, :, 1:]), (z[:, :-1], z[:, 1:]), (z[:-1], z[1:])):
+        assert abs(np.mean(u * v)) < 5 / np.sqrt(u.size)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -397,6 +465,191 @@ def test_full_size_cfg4_share_invariants():
     assert st["engine"] == 3 and st["cluster_size"] == engine.subdomain_layout(a._Nf(), W, engine._sm_count(0))[2]
     flux, kcl = _flux_and_kcl(a, res, 0.05, Is(Nt - 1))
     assert flux < 1e-10 and kcl < 1e-9
+
+
+# ---------------------------------------------------------------- running observables (north star (3))
+def _observer_case(a, W, Nt, **extra):
+    base = a.current_base(angle=0)
+    amps = np.linspace(0.4, 2.2, W)                       # from pinned to running problems: vortices move, phases wind
+    return dict(circuit=a, time_step=0.1, time_step_count=Nt, external_flux=0.15,
+                current_sources=pj.RankOneSource(base, amps), store_current=False, store_voltage=False, **extra), base, amps
+
+
+def _check_observers(res, a, theta_all, first, k, Nt, dt):
+    steps = np.arange(first, Nt, k)
+    assert res.get_observation_count() == steps.size and np.array_equal(res.get_observed_steps(), steps)
+    n_all = oracle.vortex_configuration(a.get_cycle_matrix(), theta_all[:, :, steps])
+    assert np.abs(n_all).sum() > 0 and np.abs(np.diff(n_all, axis=2)).sum() > 0       # vortices are there and move
+    assert np.array_equal(res.get_vortex_sum(), n_all.sum(axis=2))
+    assert np.allclose(res.get_mean_vortex_configuration(), n_all.mean(axis=2), rtol=0, atol=1e-15)
+    span = (steps[-1] - steps[0]) * dt
+    assert np.array_equal(res.get_dc_voltage(), (theta_all[:, :, steps[-1]] - theta_all[:, :, steps[0]]) / span)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_running_observables_equal_what_the_stored_planes_give(engine, monkeypatch):
+    # vortex sums and phase marks accumulated inside the step kernel (no plane stored) against the same quantities
+    # formed on the host from ALL phase planes of the same run (exact: integers and the same two phases), including
+    # ragged problem counts, an offset first observation, and chunked jj_run calls
+    from pyjjasim_b200 import engine as eng_mod
+    monkeypatch.setenv("JJ_ENGINE", engine)
+    a = pj.SquareArray(13, 11)
+    W, Nt, first, k = 10, 90, 7, 4
+    kw, base, amps = _observer_case(a, W, Nt)
+    full = pj.TimeEvolutionProblem(**kw).compute()
+    res = pj.TimeEvolutionProblem(observe_interval=k, observe_first=first, **dict(kw, store_theta=False)).compute()
+    assert res.theta is None
+    _check_observers(res, a, full.theta, first, k, Nt, 0.1)
+    # together with stored planes and time-dependent tables uploaded in chunks of 7 steps
+    monkeypatch.setattr(eng_mod, "_TABLE_BYTES", W * 8 * 7)
+    f_t = 0.15 + 0.01 * np.sin(0.3 * np.arange(Nt))[None, None, :] * np.ones((1, W, 1))
+    kw2 = dict(kw, external_flux=f_t, store_time_steps=[5, 50])
+    full2 = pj.TimeEvolutionProblem(**dict(kw2, store_time_steps=None)).compute()
+    res2 = pj.TimeEvolutionProblem(observe_interval=k, observe_first=first, **kw2).compute()
+    assert np.array_equal(res2.theta, full2.theta[:, :, [5, 50]])
+    _check_observers(res2, a, full2.theta, first, k, Nt, 0.1)
+    # against the oracle (non-chaotic over this horizon): same integers
+    args, extra = cases.oracle_inputs(dict(kw, current_sources=(base[:, None] * amps[None, :])[:, :, None]))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        th, _, _ = oracle.time_evolution(*args, W, **extra)
+    steps = np.arange(first, Nt, k)
+    assert np.array_equal(res.get_vortex_sum(), oracle.vortex_configuration(a.get_cycle_matrix(), th[:, :, steps]).sum(axis=2))
+    assert np.max(np.abs(res.get_dc_voltage() - (th[:, :, steps[-1]] - th[:, :, steps[0]]) / ((steps[-1] - steps[0]) * 0.1))) < 1e-9
+
+
+def test_running_observables_with_several_items_per_block_and_upper_phases(monkeypatch):
+    # the cfg3 / cfg4 / cfg5 regime scaled down: several (subdomain, chunk) items per block, halo rows shared by
+    # subdomains (integer atomics), observation at the last step of the run
+    from pyjjasim_b200 import engine as eng_mod
+    monkeypatch.setenv("JJ_TT_MAX", "120")
+    a = pj.SquareArray(80, 80)
+    W, Nt, first, k = 512, 13, 0, 3
+    kw, base, amps = _observer_case(a, W, Nt)
+    full = pj.TimeEvolutionProblem(**kw).compute()
+    assert eng_mod.last_run_stats[0]["engine"] == 3
+    res = pj.TimeEvolutionProblem(observe_interval=k, observe_first=first, **dict(kw, store_theta=False)).compute()
+    _check_observers(res, a, full.theta, first, k, Nt, 0.1)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_vortex_configurations_of_the_stored_steps_without_the_phases_leaving_the_device(engine, monkeypatch):
+    from pyjjasim_b200 import engine as eng_mod
+    monkeypatch.setenv("JJ_ENGINE", engine)
+    a = pj.HoneycombArray(6, 7)
+    W, Nt = 9, 60
+    kw, base, amps = _observer_case(a, W, Nt, store_time_steps=[0, 11, 12, 40, 59])
+    want = pj.TimeEvolutionProblem(**kw).compute().get_vortex_configuration()
+    assert np.abs(want).sum() > 0
+    res = pj.TimeEvolutionProblem(store_vortex_configuration=True, **dict(kw, store_theta=False)).compute()
+    assert res.theta is None and np.array_equal(res.get_vortex_configuration(), want)
+    assert np.array_equal(res.get_vortex_configuration([12, 59]), want[:, :, [2, 4]])
+    with pytest.raises(pj.ThetaNotStored):
+        res.get_theta()
+    # the planes one jj_run call keeps on the device are bounded: a tiny budget forces one call per stored plane
+    monkeypatch.setattr(eng_mod, "_PLANE_BYTES", a._Nj() * W * 8)
+    res2 = pj.TimeEvolutionProblem(store_vortex_configuration=True, **kw).compute()
+    assert np.array_equal(res2.get_vortex_configuration(), want)
+    assert np.array_equal(res2.theta, pj.TimeEvolutionProblem(**kw).compute().theta)
+
+
+def _oracle_sub_batch(a, kw, base, amps, sel, **oracle_extra):
+    """oracle.time_evolution on the problems `sel` of a rank-one current sweep base[e] * amps[w] (the oracle's cost is
+    per problem: a sub-batch of a full-size device run is compared, the device run itself uses the full batch and
+    therefore the plan, chunking and item schedule of the named configuration)"""
+    kw = dict(kw)
+    kw["current_sources"] = (base[:, None] * amps[sel][None, :])[:, :, None]
+    args, extra = cases.oracle_inputs(kw)
+    extra.update(oracle_extra)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        th, _, _ = oracle.time_evolution(*args, len(sel), **extra)
+    return th
+
+
+def test_full_size_cfg3_per_step_against_oracle():
+    # BASELINE config 3 at full size: HoneycombArray(200,200) (239 400 junctions), f = 0.1, DC bias sweep, 512 problems:
+    # 256 subdomains, upper program + dense top of the top. Per-step parity with the oracle on problems from both ends
+    # and the middle of the sweep, over a short horizon (frustrated: 1e-8)
+    from pyjjasim_b200 import engine
+    a = pj.HoneycombArray(200, 200)
+    W, Nt, dt = 512, 12, 0.05
+    base, amps = a.current_base(angle=0), np.linspace(0.1, 1.5, W)
+    kw = dict(circuit=a, time_step=dt, time_step_count=Nt, external_flux=0.1, store_time_steps=[4, Nt - 1],
+              store_current=False, store_voltage=False)
+    res = pj.TimeEvolutionProblem(current_sources=pj.RankOneSource(base, amps), **kw).compute()
+    st = engine.last_run_stats[0]
+    assert st["engine"] == 3 and st["cluster_size"] == engine.subdomain_layout(a._Nf(), W, engine._sm_count(0))[2]
+    sel = np.array([0, 1, 255, 256, 257, 509, 510, 511])
+    th = _oracle_sub_batch(a, kw, base, amps, sel)
+    assert np.max(np.abs(th)) > 0.5
+    assert np.max(np.abs(res.theta[:, sel, :] - th)) <= 1e-8
+
+
+def test_full_size_cfg4_per_step_against_oracle():
+    # BASELINE config 4: SquareArray(256,256) with capacitance, DC + AC drive, one GPU's share of 512 problems
+    # (T = 0 here: trajectories with device noise cannot be compared step by step; the noisy variant is covered by the
+    # invariants above)
+    from pyjjasim_b200 import engine
+    a = pj.SquareArray(256, 256)
+    a.set_capacitance(1.0)
+    W, Nt, dt = 512, 16, 0.05
+    base = a.current_base(angle=0)
+    IDC, IA = np.linspace(0, 2, W), np.linspace(0, 3, W)
+    Is = pj.RankOneSource(base, lambda i: IDC + IA * np.sin(0.25 * i * dt), problem_count=W)
+    kw = dict(circuit=a, time_step=dt, time_step_count=Nt, external_flux=0.05, store_time_steps=[5, Nt - 1],
+              store_current=False, store_voltage=False)
+    res = pj.TimeEvolutionProblem(current_sources=Is, **kw).compute()
+    assert engine.last_run_stats[0]["engine"] == 3
+    sel = np.array([0, 100, 255, 256, 400, 511])
+    kw_o = dict(kw, current_sources=lambda i: base[:, None] * (IDC[sel] + IA[sel] * np.sin(0.25 * i * dt))[None, :])
+    args, extra = cases.oracle_inputs(kw_o)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        th, _, _ = oracle.time_evolution(*args, len(sel), **extra)
+    assert np.max(np.abs(th)) > 0.5
+    assert np.max(np.abs(res.theta[:, sel, :] - th)) <= 1e-8
+
+
+def test_full_size_cfg5_per_step_against_oracle():
+    # BASELINE config 5 at full size: SquareArray(1000,1000) (1 998 000 junctions, 998 001 faces) with self-inductance
+    # and capacitance, 64 problems: 2 048 subdomains, ~30 upper phases. Per-step parity with the oracle (whose SuperLU
+    # factorisation of the 10^6-row system takes ~20 s) on four problems of the sweep
+    from pyjjasim_b200 import engine
+    a = pj.SquareArray(1000, 1000)
+    a.set_inductance(1.0)
+    a.set_capacitance(1.0)
+    W, Nt, dt = 64, 8, 0.05
+    base, amps = a.current_base(angle=0), np.linspace(0.5, 1.5, W)
+    kw = dict(circuit=a, time_step=dt, time_step_count=Nt, external_flux=0.05, store_time_steps=[2, Nt - 1],
+              store_current=False, store_voltage=False)
+    res = pj.TimeEvolutionProblem(current_sources=pj.RankOneSource(base, amps), **kw).compute()
+    st = engine.last_run_stats[0]
+    assert st["engine"] == 3 and st["cluster_size"] == engine.subdomain_layout(a._Nf(), W, engine._sm_count(0))[2]
+    sel = np.array([0, 31, 32, 63])
+    th = _oracle_sub_batch(a, kw, base, amps, sel)
+    assert np.max(np.abs(th)) > 0.05
+    assert np.max(np.abs(res.theta[:, sel, :] - th)) <= 1e-8
+    engine._tables_cache.clear()
+
+
+def test_full_size_cfg2_per_step_against_oracle_with_reference_draws():
+    # BASELINE config 2 at full size with the reference's own Gaussian draws injected (Nj > 500: the recycling branch of
+    # time_evolution.py:533-537), all 256 temperatures, per-step parity over a short horizon
+    from pyjjasim_b200 import engine
+    a = pj.SquareArray(100, 100)
+    W, Nt, dt = 256, 9, 0.5
+    T = np.geomspace(1e-2, 1.0, W)[None, :, None]
+    kw = dict(circuit=a, time_step=dt, time_step_count=Nt, external_flux=0.1, temperature=T,
+              store_time_steps=[3, Nt - 1], store_current=False, store_voltage=False)
+    Z = cases.replay_noise(a._Nj(), W, Nt, 11)
+    res = pj.TimeEvolutionProblem(noise_replay=Z, **kw).compute()
+    assert engine.last_run_stats[0]["engine"] == 3
+    args, extra = cases.oracle_inputs(kw)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        th, _, _ = oracle.time_evolution(*args, W, rng=np.random.RandomState(11), **extra)
+    assert np.max(np.abs(res.theta - th)) <= 1e-8
 
 
 def test_annealing_shards_over_devices():

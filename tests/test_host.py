@@ -196,6 +196,66 @@ def test_source_classification():
         sources.classify_source(np.zeros((N, W)), N, W, Nt)                        # quirk Q6: 2-D input is misread
 
 
+def _refstyle_cases(pkg, mk_problem):
+    """(problem, expected kinds) for reference-style problem objects: constants must not look time dependent just because
+    the reference holds them as (N, W, Nt) broadcast views (time_evolution.py:117-131)"""
+    a = pkg.SquareArray(9, 8)
+    W, Nt = 6, 400
+    base = a.current_base(angle=0)
+    amps = np.linspace(0.2, 1.4, W)
+    T = np.linspace(0.0, 0.3, W)[None, :, None]
+    p1 = mk_problem(a, time_step=0.05, time_step_count=Nt, external_flux=0.1, temperature=T,
+                    current_sources=base[:, None, None] * amps[None, :, None])
+    p2 = mk_problem(a, time_step=0.05, time_step_count=Nt, current_sources=lambda i: base[:, None] * (amps + 0.1 * np.sin(0.3 * i)),
+                    voltage_sources=0.0, external_flux=np.linspace(0, 0.2, Nt)[None, None, :] * np.ones((1, W, 1)))
+    return a, (p1, dict(Is=(sources.RANK1, True), f=(sources.RANK1, True), Vs=(sources.ZERO, True), T=(sources.RANK1, True))), \
+              (p2, dict(Is=(sources.RANK1, False), f=(sources.RANK1, False), Vs=(sources.ZERO, True), T=(sources.ZERO, True)))
+
+
+def _check_refstyle_classification(pkg, mk_problem, wrap):
+    import tracemalloc
+    from pyjjasim_b200 import engine
+    a, *probs = _refstyle_cases(pkg, mk_problem)
+    for prob, expect in probs:
+        assert not hasattr(prob, "_raw_sources")
+        tab = engine.CircuitTables(wrap(a), 0.05)
+        tracemalloc.start()
+        specs = engine._classify_all(prob, tab)
+        peak = tracemalloc.get_traced_memory()[1]
+        tracemalloc.stop()
+        for name, (kind, static) in expect.items():
+            assert specs[name].kind == kind and bool(specs[name].static) == static, (name, specs[name].kind, specs[name].static)
+        # nothing of size N x W x Nt is materialised to classify a broadcast view (advice r1: ~1 TB on cfg2 at Nt = 1e5)
+        assert peak < 0.25 * a._Nj() * prob.get_problem_count() * prob._Nt() * 8, peak
+
+
+def test_reference_style_problem_objects_are_classified_by_their_frozen_flags():
+    from tests.refstyle import RefStyleProblem, RefStyleCircuit
+    mk = lambda a, **kw: RefStyleProblem(RefStyleCircuit(a), current_phase_relation=pj.DefaultCPR(), **kw)
+    _check_refstyle_classification(pj, mk, RefStyleCircuit)
+
+
+def test_the_reference_own_problem_class_binds_to_the_device_core_classification():
+    # the real thing, where the reference tree exists (build container): the unmodified reference's
+    # TimeEvolutionProblem / SquareArray objects, as INTEGRATION.md binds them
+    from oracle.ref_harness import reference_available, import_reference
+    if not reference_available():
+        pytest.skip("reference tree not present")
+    ref = import_reference()
+    from tests.refstyle import RefStyleProblem, RefStyleCircuit
+    _check_refstyle_classification(ref, lambda a, **kw: ref.TimeEvolutionProblem(a, **kw), lambda a: a)
+    # and the stand-in used on the GPU box holds its inputs in the same form as the real class
+    a = ref.SquareArray(5, 4)
+    kw = dict(time_step=0.1, time_step_count=7, external_flux=0.2, temperature=np.ones((1, 3, 1)))
+    real, fake = ref.TimeEvolutionProblem(a, **kw), RefStyleProblem(RefStyleCircuit(a), **kw)
+    for attr in ("external_flux", "current_sources", "voltage_sources", "temperature", "config_at_minus_1", "config_at_minus_2"):
+        x, y = getattr(real, attr), getattr(fake, attr)
+        assert x.shape == y.shape and x.strides == y.strides and np.array_equal(x, y), attr
+    for flag in ("_f_is_timedep", "_Is_is_timedep", "_Vs_is_timedep", "_T_is_timedep"):
+        assert getattr(real, flag) == getattr(fake, flag)
+    assert real.get_problem_count() == fake.get_problem_count() and real._Nt() == fake._Nt() and real._dt() == fake._dt()
+
+
 def test_cpr_harmonics():
     a, b = harmonics(pj.DefaultCPR())
     assert list(a) == [0, 0] and list(b) == [0, 1]
@@ -251,6 +311,63 @@ def test_result_container_semantics():
     n = r.get_vortex_configuration()
     assert n.shape == (a._Nf(), 1, 2) and n.dtype.kind == "i"
     assert r.get_phase().shape == (a._Nn(), 1, 2)
+
+
+def test_derived_quantities_are_batched_over_time_points_and_match_the_per_step_formulas():
+    # every getter evaluates all selected time points in one batched operation; compare with the formulas of the
+    # reference written out per time point (time_evolution.py:692-983)
+    a = pj.SquareArray(5, 4)
+    a.set_inductance(0.3)
+    a.set_capacitance(0.7)
+    Nj, Nf, Nn, W, Nt = a._Nj(), a._Nf(), a._Nn(), 3, 8
+    rng = np.random.RandomState(3)
+    Is = rng.randn(Nj, W, Nt)
+    f = rng.rand(Nf, W, 1)
+    p = pj.TimeEvolutionProblem(a, time_step_count=Nt, store_time_steps=[1, 4, 6], current_sources=Is, external_flux=f)
+    th, I, V = 7 * rng.randn(Nj, W, 3), rng.randn(Nj, W, 3), rng.randn(Nj, W, 3)
+    r = pj.TimeEvolutionResult(p, th, I, V)
+    A, M, L, C, Ic = a.get_cycle_matrix(), a.get_cut_matrix(), a._L(), a._C(), a._Ic()
+    for sel, planes in ((None, [0, 1, 2]), ([6, 1], [0, 2]), ([4], [1])):
+        steps = [1, 4, 6] if sel is None else sorted(sel)
+        want = {
+            "phase": [a.Msq_solve(M @ th[:, :, k]) for k in planes],
+            "vortex_configuration": [-A @ np.round(th[:, :, k] / (2 * np.pi)) for k in planes],
+            "josephson_energy": [Ic[:, None] * (1 - np.cos(th[:, :, k])) for k in planes],
+            "supercurrent": [Ic[:, None] * np.sin(th[:, :, k]) for k in planes],
+            "cycle_current": [a.Asq_solve(A @ (I[:, :, k] - Is[:, :, t])) for k, t in zip(planes, steps)],
+            "flux": [f[:, :, 0] + A @ (L @ I[:, :, k]) / (2 * np.pi) for k in planes],
+            "magnetic_energy": [0.5 * L @ I[:, :, k] ** 2 for k in planes],
+            "potential": [a.Msq_solve(M @ V[:, :, k]) for k in planes],
+            "capacitive_energy": [0.5 * C[:, None] * V[:, :, k] ** 2 for k in planes],
+        }
+        for name, per_step in want.items():
+            got = getattr(r, "get_" + name)(sel)
+            assert got.shape == (per_step[0].shape[0], W, len(planes)), name
+            assert np.allclose(got, np.stack(per_step, axis=2), rtol=1e-13, atol=1e-13), name
+        assert np.allclose(r.get_energy(sel), r.get_josephson_energy(sel) + r.get_magnetic_energy(sel) + r.get_capacitive_energy(sel))
+    b = pj.SquareArray(3, 3)
+    r0 = pj.TimeEvolutionResult(pj.TimeEvolutionProblem(b, time_step_count=2), *(np.ones((b._Nj(), 1, 2)),) * 3)
+    assert not r0.get_magnetic_energy().any() and not r0.get_capacitive_energy().any()      # no L, no C: zero
+    with pytest.raises(ValueError, match="no running observables"):
+        r0.get_vortex_sum()
+
+
+def test_store_plan_keeps_the_helper_planes_of_the_voltage_difference():
+    a = pj.SquareArray(3, 3)
+    p = pj.TimeEvolutionProblem(a, time_step_count=9, store_time_steps=[0, 3, 4, 8])
+    plan = pj.StorePlan(p)
+    assert list(np.flatnonzero(plan.theta_mask)) == [0, 2, 3, 4, 7, 8]
+    assert list(np.flatnonzero(plan.current_mask)) == [0, 3, 4, 8]        # no inductance: no helper planes for currents
+    at = pj.StorePlan.positions(plan.theta_mask, plan.requested)
+    assert list(at) == [2, 4, 5, 7] and list(at - 1) == [1, 3, 4, 6]       # step 0 differences against theta(-1)
+    a.set_inductance(0.2)
+    assert list(np.flatnonzero(pj.StorePlan(p).current_mask)) == [0, 2, 3, 4, 7, 8]
+    q = pj.TimeEvolutionProblem(a, time_step_count=9, store_time_steps=[5], store_voltage=False, store_theta=False)
+    plan = pj.StorePlan(q)
+    assert not plan.theta_mask.any() and list(np.flatnonzero(plan.current_mask)) == [5] and not plan.fetch_theta
+    o = pj.TimeEvolutionProblem(a, time_step_count=9, store_theta=False, store_voltage=False, store_current=False, observe_interval=2)
+    assert not pj.StorePlan(o).theta_mask.any() and o.starts_at_rest_with_zero_phases()
+    assert o.config_at_minus_2.shape == (a._Nj(), 1) and not o.config_at_minus_2.any()
 
 
 def test_shard_bounds():
