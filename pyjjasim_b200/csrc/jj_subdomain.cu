@@ -687,9 +687,15 @@ __device__ __noinline__ void vortex_pass(const VortexView o) {
         const int jp = o.jlo + idx / G, q = (idx % G) * 4, w = o.c * PC + q;
         if (w >= o.Wp) continue;
         const int jo = __ldg(reinterpret_cast<const int4*>(o.jrec + 8 * (size_t)jp + 6)).z;
-        const double4v t = ldg256(o.th + (size_t)jp * PC + q);
-        stg256(o.th_last + (size_t)jo * o.Wp + w, t.lo, t.hi);
-        if (o.th_first) stg256(o.th_first + (size_t)jo * o.Wp + w, t.lo, t.hi);
+        // (plain 16-byte accesses: ptxas 12.9 narrows a 256-bit load/store pair that only copies to its first 8 bytes)
+        const double2* src = reinterpret_cast<const double2*>(o.th + (size_t)jp * PC + q);
+        const double2 lo = src[0], hi = src[1];
+        double2* dl = reinterpret_cast<double2*>(o.th_last + (size_t)jo * o.Wp + w);
+        dl[0] = lo; dl[1] = hi;
+        if (o.th_first) {
+            double2* df = reinterpret_cast<double2*>(o.th_first + (size_t)jo * o.Wp + w);
+            df[0] = lo; df[1] = hi;
+        }
     }
 }
 

@@ -483,6 +483,9 @@ def _check_observers(res, a, theta_all, first, k, Nt, dt):
     assert np.array_equal(res.get_vortex_sum(), n_all.sum(axis=2))
     assert np.allclose(res.get_mean_vortex_configuration(), n_all.mean(axis=2), rtol=0, atol=1e-15)
     span = (steps[-1] - steps[0]) * dt
+    ob = res.observed
+    assert np.array_equal(ob["theta_first"], theta_all[:, :, steps[0]]), np.argwhere(ob["theta_first"] != theta_all[:, :, steps[0]])[:8]
+    assert np.array_equal(ob["theta_latest"], theta_all[:, :, steps[-1]]), np.argwhere(ob["theta_latest"] != theta_all[:, :, steps[-1]])[:8]
     assert np.array_equal(res.get_dc_voltage(), (theta_all[:, :, steps[-1]] - theta_all[:, :, steps[0]]) / span)
 
 
