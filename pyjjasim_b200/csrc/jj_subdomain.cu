@@ -87,6 +87,7 @@ struct SubArgs {
     int* obs_nsum; double *obs_th_first, *obs_th_last;
     const double* dbg_b; double* dbg_J;   // debug solve: canonical [Nf][Wp], permuted faces
     long long* prof;                       // optional per-block cycle counters [block][8]
+    int stagger;                           // cycles by which consecutive problem chunks start apart (chunk-local top phase only)
     int dbg;                               // JJ_SUB_DEBUG (read once per plan): 4 no chunk-local top phase, 64 direct top
                                            // product; the physics-altering timing experiments (128, 256) exist only in
                                            // builds with -DJJ_EXPERIMENTS
@@ -96,8 +97,15 @@ struct SubArgs {
 
 namespace {
 
-constexpr int NT = 512;
-constexpr size_t BAR_BYTES = 8192;      // grid barrier counter + one counter per problem chunk, 128 bytes apart
+// threads per block: 512 (one block per SM) or, compiled with -DJJ_SUB_NT=256, half blocks of 8 warps that run two to
+// an SM on different (subdomain, chunk) items: the latency-bound phases of one overlap the pipe-bound phases of the other
+#ifndef JJ_SUB_NT
+#define JJ_SUB_NT 512
+#endif
+constexpr int NT = JJ_SUB_NT;
+constexpr int BLOCKS_PER_SM = NT == 256 ? 2 : 1;
+constexpr size_t BAR_COUNTERS = 8192;   // grid barrier counter + one counter per problem chunk, 128 bytes apart
+constexpr size_t BAR_BYTES = BAR_COUNTERS + 128;     // ... + the 64-bit work counter of the item scheduler
 constexpr int NWARPS = NT / 32;
 constexpr int RING = 4;            // stream steps per ring block; every tile is padded to a multiple of it
 constexpr int STEP_BYTES = 320;
@@ -107,12 +115,14 @@ constexpr int PROF_STAMPS = 8;          // time stamps inside the first warp tas
 constexpr int PROF_SLOTS = 8 + 48 + 2 * PROF_UP + PROF_STAMPS;     // phase counters + per-level counters of the sweeps + (work, wait) per upper phase (JJ_SUB_PROF)
 
 struct SubState {
+    int threads = 512;      // block size the plan was packed for (16 or 8 warps)
     int P = 1, NG = 4, PC = 32, n_rows = 0, n_loc_max = 0, stage_rows = 0, n_top = 0, n_up_pad = 0, n_slots = 0;
     int tt0 = 0, n_tt = 0, n_tt_pad = 0, up_RB = 4, up_KB = 8, n_up_fwd = 0, n_up_bwd = 0;
     int* up_phase_ptr = nullptr; int* up_phase_split = nullptr; int4* up_task = nullptr; long long* up_task_aoff = nullptr;
     unsigned* up_ctr = nullptr;
     int* up_cols = nullptr; double* up_A = nullptr;
     double* U = nullptr; size_t u_bytes = 0;
+    int stagger = -1;       // JJ_SUB_STAGGER (cycles per chunk; -1: derived from the measured step time)
     int dbg = 0; bool prof = false, no_tslot4 = false, no_l2_window = false, l2_limit_set = false; int grid_env = 0;
     int max_np = 0, max_levels = 0, max_tiles = 0, face_K = 0;
     SubProgDev* prog = nullptr;
@@ -804,6 +814,42 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc));
 }
 
+// ---- bulk copies through the TMA unit (cp.async.bulk, 1-D): one thread moves a whole contiguous block between global
+// and shared memory; the other threads only wait on an mbarrier (loads) or carry on (stores). Used for the solve
+// vector of the local rows, which passes through global memory between the forward and the backward sweep whenever a
+// block works through several (subdomain, chunk) items per time step.
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// global -> shared, completion counted in bytes on the mbarrier (bytes: multiple of 16, below 2^20)
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar), d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(b), "r"(parity) : "memory");
+}
+// shared -> global
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, unsigned bytes) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_src);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(sa), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // J_tt = S_tt^-1 r_tt (dense top of the top) with the A fragments (the packed inverse) read straight from L2 into
 // registers: a fragment is used by exactly one warp, so staging it in shared memory only costs shared-memory bandwidth.
 // Only the B fragments (r_tt, shared by all row tiles of the block) go through a cp.async ring in the staging rows
@@ -1173,10 +1219,13 @@ __device__ __forceinline__ void rows_to_global(const double* v, int row0, int nr
     }
 }
 
+// UPPER = false is the LEAN kernel: at most one (subdomain, chunk) item per block and no upper phases, z stays in shared
+// memory; UPPER = true is the general one (several items per block handed out by the work counter, z through global
+// memory by bulk copies, upper phases - possibly none).
 // UPPER: the plan has upper phases (compiled out otherwise: their registers and code must not weigh on the kernel of
 // circuits whose separators all fit the dense top product, whose time step is a tenth as long)
 template <int NG, bool DEF, bool UPPER>
-__global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
+__global__ void __launch_bounds__(NT, BLOCKS_PER_SM) k_subdomain(const SubArgs a) {
     constexpr int PC = 8 * NG;
     extern __shared__ __align__(1024) double smem[];
     double* v = smem;
@@ -1188,17 +1237,30 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
     // More items than blocks: a block takes a contiguous range of the subdomain-major item list, so its consecutive items
     // are chunks of the SAME subdomain (its program stays loaded, its factor stream is hot in L2, and the neighbouring
     // blocks stream the same factor at the same time). Otherwise block b owns item b = (chunk b / P, subdomain b % P).
-    const bool multi = n_items > (int)gridDim.x;
+    const bool multi = UPPER && n_items > (int)gridDim.x;
     const int it_lo = multi ? (int)((long long)blockIdx.x * n_items / gridDim.x) : (int)blockIdx.x;
     const int it_hi = multi ? (int)((long long)(blockIdx.x + 1) * n_items / gridDim.x) : min(n_items, (int)blockIdx.x + 1);
     const int n_up = UPPER ? a.n_up_fwd + a.n_up_bwd : 0;
     // every block has at most one item: z stays in shared memory - unless upper phases run between the sweeps, which
     // gather their operands into the whole shared memory (two panel buffers of up_rows rows)
-    const bool keep_z = n_items <= (int)gridDim.x && n_up == 0;
+    const bool keep_z = !UPPER || (n_items <= (int)gridDim.x && n_up == 0);
     constexpr int UP_GRAN = NG >= 8 ? 128 : 256;     // panel rows: whole ring turns for every K split (upper_phase)
     const int up_rows = (int)((((size_t)a.n_rows * PC + (size_t)a.stage_rows * (PC + 2)) / (2 * PC)) / UP_GRAN * UP_GRAN);
     unsigned bar_target = 0;
     int cur_s = -1;
+    __shared__ unsigned long long s_zbar;      // mbarrier of the bulk loads of z
+    __shared__ int s_item;
+    if (UPPER && threadIdx.x == 0) mbar_init(&s_zbar, 1);
+    unsigned zphase = 0;
+    __syncthreads();
+    // More items than blocks: items are handed out by a work counter, one draw per item and time step (subdomain-major
+    // order: the blocks that run at the same time work on chunks of the same few subdomains, whose factor streams stay
+    // hot in L2). A static split leaves every block waiting for the one with the most expensive items at every time
+    // step (boundary subdomains are cheaper, 2048 items do not divide by 148 blocks); with the counter the spread is
+    // at most one item. Which block runs an item does not change its arithmetic. Needs the grid barriers of the top
+    // phase between the time steps (the counter only ever grows: step k draws from k * (n_items + gridDim.x) on).
+    unsigned long long* item_ctr = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(a.bar) + BAR_COUNTERS);
+    const bool dyn = UPPER && n_items > (int)gridDim.x && a.n_top > 0 && !a.dbg_b && !(a.dbg & 8);
     // dense top product (top_product_areg): RB row tiles per block so that one round of blocks covers it, the K range
     // of a stage split over KQ = 16 / RB warps (KQ must divide the number of k-steps), KM k-steps per warp and stage,
     // a ring of S stages in the staging rows. Without upper phases and with exactly one item per block the whole top
@@ -1225,7 +1287,7 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
             const int rb = min(NWARPS, (RT * GPr + a.P - 1) / a.P);
             int kq, km, ss = 0;
             pick(rb, kq, km, ss);
-            if (kq >= 2 && km > 0) { chunk_local = true; top_rb = rb; ar_kq = kq; top_ar = km; ar_s = ss; }
+            if (kq >= (NWARPS >= 16 ? 2 : 1) && km > 0) { chunk_local = true; top_rb = rb; ar_kq = kq; top_ar = km; ar_s = ss; }
         }
         if (!chunk_local) {
             const int per_chunk = max(1, (int)gridDim.x / (a.n_chunks * GPr));
@@ -1319,28 +1381,50 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
         return;
     }
 
+    if (chunk_local && a.stagger > 0) {
+        // Problem chunks are independent pipelines with the same period. Started together they stay in lockstep: every
+        // SM streams the state through HBM during the same third of the time step (the junction pass then runs at
+        // the HBM limit) and leaves it idle for the rest. Started apart, the chunks are in different phases at any
+        // moment: the HBM load is even over the time step and the pass is no longer bandwidth-bound.
+        const long long t0 = clock64(), wait = (long long)(blockIdx.x / a.P) * a.stagger;
+        while (clock64() - t0 < wait) __nanosleep(256);
+    }
     for (long long k = 0; k <= a.n; ++k) {
         const long long n = a.i0 + k;
         long long tq = a.prof ? clock64() : 0;
-        for (int item = it_lo; item < it_hi; ++item) {
+        const unsigned long long draw_base = (unsigned long long)k * (unsigned long long)(n_items + (int)gridDim.x);
+        unsigned long long drawn = 0;
+        if (dyn && threadIdx.x == 0) drawn = atomicAdd(item_ctr, 1ull) - draw_base;
+        int item = it_lo - 1;
+        auto next_item = [&]() -> bool {
+            if (!dyn) return ++item < it_hi;
+            if (threadIdx.x == 0) s_item = drawn < (unsigned long long)n_items ? (int)drawn : n_items;
+            __syncthreads();                 // (every item body has block barriers: s_item was read by all before this)
+            item = s_item;
+            if (item >= n_items) return false;
+            if (threadIdx.x == 0) drawn = atomicAdd(item_ctr, 1ull) - draw_base;    // the next draw, while this item runs
+            return true;
+        };
+        while (next_item()) {
             const int s = multi ? item / a.n_chunks : item % a.P, c = multi ? item % a.n_chunks : item / a.P;
             if (s != cur_s) { __syncthreads(); load_prog<NG>(a, s, ps, aux); cur_s = s; }
             const int nl = a.n_loc[s], nh = a.n_halo[s];
             amp_fill<PC>(a, ac, c, n - 1);
             amp_fill<PC>(a, ac, c, n);
             if (k > 0) {
-                // J_top of the halo rows and z of the local rows, then the backward sweep
+                // z of the local rows (one bulk copy, in flight while the halo rows are gathered) and J_top of the halo
+                // rows, then the backward sweep
+                if (UPPER && !keep_z && nl > 0 && threadIdx.x == 0) {
+                    fence_proxy_async();     // the vector was last touched through the generic proxy (barrier at the item's end)
+                    bulk_load(v, a.zloc + ((size_t)item * a.n_loc_max) * PC, (unsigned)(nl * PC * sizeof(double)), &s_zbar);
+                }
                 const int* ht = a.halo_top + a.hptr[s];
                 for (int e = threadIdx.x; e < nh * (PC / 2); e += NT) {
                     const int r = e / (PC / 2), q = (e % (PC / 2)) * 2;
                     const double2 val = __ldcg(reinterpret_cast<const double2*>(a.jtop + ((size_t)c * a.n_up_pad + ht[r]) * PC + q));
                     *reinterpret_cast<double2*>(v + velem<NG>(nl + r, q)) = val;
                 }
-                if (!keep_z) {
-                    const double2* src = reinterpret_cast<const double2*>(a.zloc + ((size_t)item * a.n_loc_max) * PC);
-                    double2* dst = reinterpret_cast<double2*>(v);
-                    for (int e = threadIdx.x; e < nl * (PC / 2); e += NT) dst[e] = src[e];
-                }
+                if (UPPER && !keep_z && nl > 0) { mbar_wait(&s_zbar, zphase); zphase ^= 1u; }
                 __syncthreads();
                 run_levels<NG>(ps, 0, ps.n_bwd, v, stage, a.prof);
             } else {
@@ -1365,11 +1449,15 @@ __global__ void __launch_bounds__(NT, 1) k_subdomain(const SubArgs a) {
             __syncthreads();
             if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 2] += tn - tq; tq = tn; }
             run_levels<NG>(ps, ps.n_bwd, ps.n_levels, v, stage, a.prof);
+            if (UPPER && !keep_z && nl > 0 && threadIdx.x == 0) {
+                // z of the local rows leaves as one bulk copy while the block writes out the halo contributions
+                fence_proxy_async();         // the sweep's shared-memory writes (all before its closing barrier) -> async proxy
+                bulk_store(a.zloc + ((size_t)item * a.n_loc_max) * PC, v, (unsigned)(nl * PC * sizeof(double)));
+            }
             rows_to_global<NG>(v, nl, nh, a.ctop + ((size_t)c * a.n_slots + a.hptr[s]) * PC);
-            if (!keep_z) {
-                const double2* src = reinterpret_cast<const double2*>(v);
-                double2* dst = reinterpret_cast<double2*>(a.zloc + ((size_t)item * a.n_loc_max) * PC);
-                for (int e = threadIdx.x; e < nl * (PC / 2); e += NT) dst[e] = src[e];
+            if (UPPER && !keep_z && nl > 0 && threadIdx.x == 0) {
+                bulk_store_wait();           // complete (not only read): the next reader is another block, after a grid barrier
+                fence_proxy_async();
             }
             __syncthreads();     // the vector is reused by the next item / the next step
             if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 3] += tn - tq; tq = tn; }
@@ -1413,22 +1501,41 @@ KernelPtr subdomain_kernel_ng1(bool def, bool upper);
 KernelPtr subdomain_kernel_ng2(bool def, bool upper);
 KernelPtr subdomain_kernel_ng4(bool def, bool upper);
 KernelPtr subdomain_kernel_ng8(bool def, bool upper);
+// half blocks (256 threads, two per SM); no upper program
+KernelPtr subdomain_kernel_h_ng1(bool def, bool upper);
+KernelPtr subdomain_kernel_h_ng2(bool def, bool upper);
+KernelPtr subdomain_kernel_h_ng4(bool def, bool upper);
 }
 
 #ifdef JJ_SUB_NG
 #define JJ_SUB_CAT2(a, b) a##b
 #define JJ_SUB_CAT(a, b) JJ_SUB_CAT2(a, b)
 namespace jj {
+#if JJ_SUB_NT == 256
+KernelPtr JJ_SUB_CAT(subdomain_kernel_h_ng, JJ_SUB_NG)(bool def, bool upper) {
+    if (upper) return nullptr;           // the upper phases are written for 16 warps
+    return def ? k_subdomain<JJ_SUB_NG, true, false> : k_subdomain<JJ_SUB_NG, false, false>;
+}
+#else
 KernelPtr JJ_SUB_CAT(subdomain_kernel_ng, JJ_SUB_NG)(bool def, bool upper) {
     if (upper) return def ? k_subdomain<JJ_SUB_NG, true, true> : k_subdomain<JJ_SUB_NG, false, true>;
     return def ? k_subdomain<JJ_SUB_NG, true, false> : k_subdomain<JJ_SUB_NG, false, false>;
 }
+#endif
 }
 #else
 
 namespace {
 
-KernelPtr pick_kernel(int NG, bool def, bool upper) {
+KernelPtr pick_kernel(int threads, int NG, bool def, bool upper) {
+    if (threads == 256) {
+        switch (NG) {
+            case 1: return subdomain_kernel_h_ng1(def, upper);
+            case 2: return subdomain_kernel_h_ng2(def, upper);
+            case 4: return subdomain_kernel_h_ng4(def, upper);
+            default: return nullptr;
+        }
+    }
     switch (NG) {
         case 1: return subdomain_kernel_ng1(def, upper);
         case 2: return subdomain_kernel_ng2(def, upper);
@@ -1523,7 +1630,7 @@ int subdomain_set_plan(JJHandle* h, const JJSubdomainPlan* pl) {
                  "tt0 + n_tt == n_top < n_up_pad and tt0 + n_tt_pad <= n_up_pad";
         return JJ_EINVAL;
     }
-    if (pl->n_up_fwd + pl->n_up_bwd > 0 && !(pl->up_RB == NWARPS && pl->up_KB == 16)) {
+    if (pl->n_up_fwd + pl->n_up_bwd > 0 && !(pl->up_RB == 16 && pl->up_KB == 16)) {
         h->err = "subdomain plan: upper program must be packed for up_RB == 16 row tiles per task, up_KB == 16";
         return JJ_EINVAL;
     }
@@ -1541,6 +1648,7 @@ int subdomain_set_plan(JJHandle* h, const JJSubdomainPlan* pl) {
         st->no_tslot4 = getenv("JJ_SUB_NO_TSLOT4") != nullptr;
         st->no_l2_window = getenv("JJ_SUB_NO_L2_WINDOW") != nullptr;
         st->grid_env = (e = getenv("JJ_SUB_GRID")) ? atoi(e) : 0;
+        st->stagger = (e = getenv("JJ_SUB_STAGGER")) ? atoi(e) : -1;
     }
     if ((size_t)st->n_rows * st->PC > 65536) { h->err = "subdomain plan: shared-memory vector exceeds the 16-bit element codes"; return JJ_EINVAL; }
     const int Nj = h->cir.Nj, P = pl->P;
@@ -1549,7 +1657,12 @@ int subdomain_set_plan(JJHandle* h, const JJSubdomainPlan* pl) {
     std::map<const void*, int> seen;          // host stream pointer -> first subdomain with that program
     for (int s = 0; s < P; ++s) {
         const JJSubProgram& ps = pl->prog[s];
-        if (ps.n_warps != NWARPS) { h->err = "subdomain plan: program packed for a different warp count"; return JJ_EINVAL; }
+        if (s == 0) st->threads = 32 * ps.n_warps;
+        if ((ps.n_warps != 16 && ps.n_warps != 8) || 32 * ps.n_warps != st->threads ||
+            (ps.n_warps == 8 && (pl->n_up_fwd + pl->n_up_bwd > 0 || pl->NG == 8))) {
+            h->err = "subdomain plan: programs must all be packed for 16 warps, or for 8 warps (half blocks: no upper program, NG <= 4)";
+            return JJ_EINVAL;
+        }
         // congruent subdomains (translated copies on a regular lattice) come with the SAME host arrays: one device
         // copy serves them all, and the shared factor stream stays in L2
         if (ps.n_steps > 0) {
@@ -1562,7 +1675,7 @@ int subdomain_set_plan(JJHandle* h, const JJSubdomainPlan* pl) {
             }
             seen[(const void*)ps.stream] = s;
         }
-        const size_t np = (size_t)ps.n_levels * NWARPS;
+        const size_t np = (size_t)ps.n_levels * ps.n_warps;
         int *wt, *ws, *th, *ls; unsigned char* sb;
         if ((rc = up(h, st, &wt, ps.wt_ptr, 2 * np))) return rc;
         if ((rc = up(h, st, &ws, ps.ws_ptr, np))) return rc;
@@ -1649,7 +1762,9 @@ int subdomain_set_plan(JJHandle* h, const JJSubdomainPlan* pl) {
     }
     SCK(cudaStreamSynchronize(h->stream));
     st->smem_bytes = smem_for(st);
-    if (st->smem_bytes + 1024 > 227 * 1024) { h->err = "subdomain plan: shared memory per block exceeds 226 KB (+ 1 KB static)"; return JJ_EINVAL; }
+    // 228 KB per SM, 1 KB reserved per resident block (+ the kernel's own static shared memory)
+    const size_t smem_cap = st->threads == 256 ? (size_t)112 * 1024 : (size_t)226 * 1024;
+    if (st->smem_bytes > smem_cap) { h->err = "subdomain plan: shared memory per block exceeds 226 KB (112 KB for half blocks)"; return JJ_EINVAL; }
     return JJ_OK;
 }
 
@@ -1688,10 +1803,19 @@ static void fill_args(JJHandle* h, SubState* st, SubArgs& a) {
     a.obs_first = h->obs_first; a.obs_interval = h->obs_interval;
     a.obs_nsum = h->obs_nsum; a.obs_th_first = h->obs_th_first; a.obs_th_last = h->obs_th_last;
     a.dbg = st->dbg;
+    a.stagger = st->stagger > 0 ? st->stagger : 0;
 }
 
 static int launch(JJHandle* h, SubState* st, SubArgs& a) {
-    KernelPtr k = pick_kernel(st->NG, h->cir.default_cpr, st->n_up_fwd + st->n_up_bwd > 0);
+    // the lean kernel when every block has at most one item and there are no upper phases, else the general one
+    // (both are limited to one block per SM by their shared memory - two for half blocks -, so the capacity is known)
+    int sms = 0;
+    SCK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    int cap = sms * (st->threads == 256 ? 2 : 1);
+    if (st->grid_env > 0) cap = std::min(cap, st->grid_env);
+    const bool general = st->n_up_fwd + st->n_up_bwd > 0 || st->P * st->n_chunks > cap;
+    KernelPtr k = pick_kernel(st->threads, st->NG, h->cir.default_cpr, general);
+    if (!k) { h->err = "subdomain: no kernel for this block size / chunk width / item count"; return JJ_EINVAL; }
     {
         const Source &is = h->src[JJ_SRC_IS].dev, &t = h->src[JJ_SRC_T].dev, &vs = h->src[JJ_SRC_VS].dev;
         k_sub_gather_params<<<(h->cir.Nj + 255) / 256, 256, 0, h->stream>>>(
@@ -1706,11 +1830,10 @@ static int launch(JJHandle* h, SubState* st, SubArgs& a) {
     }
     SCK(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem_bytes));
     if (st->grid == 0) {
-        int per_sm = 0, sms = 0;
-        SCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, NT, st->smem_bytes));
-        SCK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+        int per_sm = 0;
+        SCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, st->threads, st->smem_bytes));
         if (per_sm <= 0) { h->err = "subdomain: kernel does not fit on the device"; return JJ_EINVAL; }
-        st->grid = sms * std::min(per_sm, 1);
+        st->grid = sms * std::min(per_sm, st->threads == 256 ? 2 : 1);
     }
     // the staged top product sizes its row blocks to the grid: give it up to 18 blocks per chunk and group pass
     const int top_tasks = st->n_chunks * ((st->NG + 3) / 4) * std::min(18, (st->n_tt + 7) / 8);
@@ -1735,7 +1858,7 @@ static int launch(JJHandle* h, SubState* st, SubArgs& a) {
         cudaGetLastError();
     }
     void* params[] = {(void*)&a};
-    SCK(cudaLaunchCooperativeKernel((const void*)k, dim3(grid), dim3(NT), params, st->smem_bytes, h->stream));
+    SCK(cudaLaunchCooperativeKernel((const void*)k, dim3(grid), dim3(st->threads), params, st->smem_bytes, h->stream));
     h->launches++;
     return JJ_OK;
 }

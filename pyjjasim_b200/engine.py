@@ -209,6 +209,7 @@ class CircuitTables:
 
     # ------------------------------------------------------------------ subdomain engine plan
     SMEM_LIMIT = 226 * 1024          # dynamic shared memory of the step kernel (it has 1 KB of static shared memory)
+    SMEM_LIMIT_HALF = 112 * 1024     # half blocks (8 warps), two to an SM
 
     def subdomain_smem_bytes(self, plan):
         PC = plan.PC
@@ -217,9 +218,10 @@ class CircuitTables:
         return (plan.n_rows * PC + plan.stage_rows * (PC + 2)) * 8 + 64 * PC + 4 * aux
 
     def subdomain_plan(self, d, NG, n_chunks=1):
-        key = (d, NG, n_chunks, os.environ.get("JJ_TT_MAX", ""))
+        n_warps = 8 if half_blocks() else 16
+        key = (d, NG, n_chunks, os.environ.get("JJ_TT_MAX", ""), n_warps)
         if key not in self._subdomain:
-            plan = subdomain_plan(self.factor, self.junc_face, d, NG, n_chunks=n_chunks)
+            plan = subdomain_plan(self.factor, self.junc_face, d, NG, n_warps=n_warps, n_chunks=n_chunks)
             face_tables(plan, self.face_ptr, self.face_junc, self.face_sign, self.junc_sign, self.c0)
             self._subdomain[key] = plan
         return self._subdomain[key]
@@ -249,7 +251,9 @@ class CircuitTables:
                 plan = self.subdomain_plan(d, NG, chunks)
             except ValueError:
                 continue
-            if self.subdomain_smem_bytes(plan) <= self.SMEM_LIMIT:
+            if plan.prog[0]["n_warps"] == 8 and (plan.upper["n_fwd"] + plan.upper["n_bwd"] > 0):
+                continue                     # half blocks have no upper program
+            if self.subdomain_smem_bytes(plan) <= (self.SMEM_LIMIT_HALF if plan.prog[0]["n_warps"] == 8 else self.SMEM_LIMIT):
                 return d, NG, chunks
         return None
 
@@ -259,6 +263,11 @@ _ROWS_FIT = 560               # local rows of a subdomain that still fit in 227 
 _ROWS_MULTI = 520             # most local rows of a subdomain when a block works through several items per time step
 
 
+def half_blocks():
+    """JJ_SUB_HALF=1: blocks of 8 warps, two to an SM, each on its own (subdomain, chunk of 16 problems) item"""
+    return os.environ.get("JJ_SUB_HALF", "0") == "1"
+
+
 def subdomain_layout(Nf, W, n_sm=148):
     """(NG, chunks, n_parts) of the subdomain engine for W problems on a circuit with Nf faces: chunks of 8*NG
     problems, and as many subdomains as fill the SMs with (subdomain, chunk) thread blocks - but none smaller
@@ -266,6 +275,13 @@ def subdomain_layout(Nf, W, n_sm=148):
     faces run 6 % faster than 5 x 72)."""
     Wp = (W + 3) // 4 * 4
     NG = 4 if Wp > 16 else 2 if Wp > 8 else 1
+    if half_blocks():
+        # two resident blocks per SM: half the problems per chunk, twice the blocks
+        NG = min(NG, 2)
+        chunks = (Wp + 8 * NG - 1) // (8 * NG)
+        n_parts = max(1, min(2 * n_sm // chunks, Nf // 45))
+        if Nf <= _ROWS_FIT * n_parts:
+            return NG, chunks, n_parts
     chunks = (Wp + 8 * NG - 1) // (8 * NG)
     n_parts = max(1, min(n_sm // chunks, Nf // 45))
     # larger circuits: the rows of a subdomain (local + halo) must fit in a block's shared memory, so there are more

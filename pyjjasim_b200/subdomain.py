@@ -680,7 +680,8 @@ def subdomain_plan(F, junc_face, d, NG, n_warps=RES_WARPS, groups=None, tt_max=N
     # ---- per-subdomain sweep programs: backward levels first (they open a time step), then forward
     plan.prog, plan.n_bwd = [], []
     plan.group_bounds = []
-    smem_limit = 227 * 1024 - 20 * 1024                 # room for headers, cursors and the amplitude cache
+    # room for headers, cursors and the amplitude cache; half blocks (8 warps, two to an SM) have 112 KB each
+    smem_limit = (227 * 1024 - 20 * 1024) if n_warps >= 16 else (112 * 1024 - 8 * 1024)
     stage_cap = (smem_limit // 8 - plan.n_rows * PC) // (PC + 2)
     if stage_cap < 8:
         raise ValueError("subdomain plan: the right-hand sides leave no room for the staging rows")
