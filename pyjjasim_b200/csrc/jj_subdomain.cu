@@ -57,6 +57,7 @@ struct SubArgs {
     const int *n_loc, *n_halo, *hptr, *halo_top, *tptr, *tslot, *top_face;
     const int4* tslot4;             // [n_top] the (at most four) slots of a top row, -1 padded; null when a row has more
     const double* topF;             // [n_top] flux base of each top row (gathered per launch), null without rank-one flux
+    const double* rowF;             // [P][n_rows] flux base of each local row, 0 for halo rows (gathered per launch), null without rank-one flux
     const double* SinvP;
     const int* junc_ptr; const int* junc_orig; const int2* junc_row; const char2* junc_sign;
     int face_K; const int* face_ell_j; const double* face_ell_c; const int* face_fidx;
@@ -128,7 +129,7 @@ struct SubState {
     SubProgDev* prog = nullptr;
     int *n_loc = nullptr, *n_halo = nullptr, *hptr = nullptr, *halo_top = nullptr, *tptr = nullptr, *tslot = nullptr, *top_face = nullptr;
     double* SinvP = nullptr;
-    int4* tslot4 = nullptr; double* topF = nullptr;
+    int4* tslot4 = nullptr; double* topF = nullptr; double* rowF = nullptr;
     int *junc_ptr = nullptr, *junc_orig = nullptr; int2* junc_row = nullptr; char2* junc_sign = nullptr;
     int* face_ell_j = nullptr; double* face_ell_c = nullptr; int* face_fidx = nullptr;
     double *P0 = nullptr, *P1 = nullptr, *jrec = nullptr;
@@ -381,7 +382,7 @@ __device__ __forceinline__ void amp_fill(const SubArgs& a, AmpCache<PC>* ac, int
 }
 
 // x' = (noise - Is) + Ic cpr(2 theta_n - theta_{n-1}) + c1 theta_n + c2 theta_{n-1} for four problems
-// (reference: time_evolution.py:533-558)
+// (reference: time_evolution.py:533-558); called with the coefficients divided by c0 it returns x'/c0
 template <bool DEF>
 __device__ __forceinline__ void next_x(const SubArgs& a, double Ic, double c1, double c2, double isb, double nb,
                                        const double* ampT, const double* ampIs, int jo, int w, long long n,
@@ -438,8 +439,9 @@ __device__ __forceinline__ void junction_item(const SubArgs& a, const AmpCache<8
     const double2* jb = reinterpret_cast<const double2*>(v + velem<NG>(ri.y, q));
     const double2 a0 = ja[0], a1 = ja[1], b0 = jb[0], b1 = jb[1];
     const double y[4] = {fma(s1, b0.x, s0 * a0.x), fma(s1, b0.y, s0 * a0.y), fma(s1, b1.x, s0 * a1.x), fma(s1, b1.y, s0 * a1.y)};
+    // the x stream holds x'/c0 (what the face pass sums): theta_n = y/c0 - x'/c0
     const double ic0 = rIc.y;
-    const double th1[4] = {(y[0] - x0.x) * ic0, (y[1] - x0.y) * ic0, (y[2] - x1.x) * ic0, (y[3] - x1.y) * ic0};
+    const double th1[4] = {fma(y[0], ic0, -x0.x), fma(y[1], ic0, -x0.y), fma(y[2], ic0, -x1.x), fma(y[3], ic0, -x1.y)};
     const double th2[4] = {t0.x, t0.y, t1.x, t1.y};
     // one finiteness test for the four phases (a NaN or Inf in any of them poisons the sum)
     if (!(fabs((th1[0] + th1[1]) + (th1[2] + th1[3])) < 1.0e300)) atomicOr(a.flag, 1);
@@ -451,9 +453,10 @@ __device__ __forceinline__ void junction_item(const SubArgs& a, const AmpCache<8
         }
         if (snap_I) {
             const double* am = ac->Is[(n - 1) & 1] + q;
+            const double isb = __ldg(a.P1 + 4 * (size_t)(jlo + idx / G));       // (the record holds Is base / c0)
             double2* sp = reinterpret_cast<double2*>(snap_I + cidx);
-            sp[0] = make_double2(y[0] + rb.x * am[0], y[1] + rb.x * am[1]);
-            sp[1] = make_double2(y[2] + rb.x * am[2], y[3] + rb.x * am[3]);
+            sp[0] = make_double2(y[0] + isb * am[0], y[1] + isb * am[1]);
+            sp[1] = make_double2(y[2] + isb * am[2], y[3] + isb * am[3]);
         }
         if (!do_pre) {
             // end of the run: hand theta_last and theta_{last-1} back in the canonical layout
@@ -553,49 +556,50 @@ __device__ void junction_pass(const SubArgs& a, const AmpCache<8 * NG>* ac, int 
 }
 
 // b = A (x'/c0 - theta_s) - 2 pi f into shared memory (reference: time_evolution.py:560-569). Every row has a
-// fixed-width list of (device junction, +-1/c0) pairs; halo rows hold the partial sum over the junctions this
-// subdomain owns (their flux term is added by the top assembly).
+// fixed-width list of signed junction entries (2 * device junction + (sign < 0), -1 = absent) and the x stream holds
+// x'/c0, so a row is a signed sum of gathered values; halo rows hold the partial sum over the junctions this subdomain
+// owns (their flux term is added by the top assembly).
+// The pass is a chain of dependent L2 round trips (row list -> gathers), not bandwidth (a lone SM streams L2 at
+// 80 B/clk, tools/mb_l2stream.cu; the pass moves 30): no coefficient loads travel with the gathers, and the flux base
+// of a row comes from a per-row table gathered once per launch (rowF) instead of two dependent loads behind them.
+// (Fetching the row lists one chunk ahead brought the pass from 24 k to 16 k cycles per time step on cfg2, but its 12
+// extra registers pushed loop invariants of the junction pass into local memory: +11 k cycles there. Not kept.)
 template <int NG>
 __device__ void face_pass(const SubArgs& a, const AmpCache<8 * NG>* ac, int s, int c, long long n, int rows_used,
                           double* __restrict__ v) {
     constexpr int PC = 8 * NG, G = PC / 4;
-    constexpr int U = 2;                  // rows per thread and iteration: 16 independent 16-byte loads in flight
+    constexpr int U = 2;                  // rows per thread and iteration: 8 independent 32-byte gathers in flight
     const int K = a.face_K;
     const int* fj = a.face_ell_j + (size_t)s * a.n_rows * K;
-    const double* fc = a.face_ell_c + (size_t)s * a.n_rows * K;
-    const int* fidx = a.face_fidx + (size_t)s * a.n_rows;
+    const double* rowF = a.rowF ? a.rowF + (size_t)s * a.n_rows : nullptr;
     const int total = rows_used * G;
-    const bool has_vs = a.Vs.kind == KIND_RANK1, has_f = a.F.kind == KIND_RANK1;
+    const bool has_vs = a.Vs.kind == KIND_RANK1;
+    const double* xbase = a.rx + (size_t)c * a.Nj * PC;
     for (int idx0 = threadIdx.x; idx0 < total; idx0 += U * NT) {
         double acc[U][4];
+        double fv[U];
         int row[U], q[U];
-        bool live[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int idx = idx0 + u * NT;
-            live[u] = idx < total;
-            row[u] = live[u] ? idx / G : 0;
+            row[u] = idx < total ? idx / G : 0;
             q[u] = (idx % G) * 4;
             acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.0;
-            live[u] = live[u] && (c * PC + q[u] < a.Wp);
+            fv[u] = rowF ? __ldg(rowF + row[u]) : 0.0;        // (independent of the gathers: in flight with them)
         }
         for (int k0 = 0; k0 < K; k0 += 4) {
-            int jp[U][4]; double cf[U][4]; double2 xa[U][4], xb[U][4];
+            int je[U][4]; double2 xa[U][4], xb[U][4];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int4 j4 = __ldg(reinterpret_cast<const int4*>(fj + (size_t)row[u] * K + k0));
-                jp[u][0] = j4.x; jp[u][1] = j4.y; jp[u][2] = j4.z; jp[u][3] = j4.w;
-                const double2 ca = __ldg(reinterpret_cast<const double2*>(fc + (size_t)row[u] * K + k0));
-                const double2 cb = __ldg(reinterpret_cast<const double2*>(fc + (size_t)row[u] * K + k0) + 1);
-                cf[u][0] = ca.x; cf[u][1] = ca.y; cf[u][2] = cb.x; cf[u][3] = cb.y;
+                je[u][0] = j4.x; je[u][1] = j4.y; je[u][2] = j4.z; je[u][3] = j4.w;
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const size_t tbase = (size_t)c * a.Nj * PC + q[u];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    // absent entries (-1) read junction 0 with coefficient 0; x' was written by this block (plain loads)
-                    const double4v xv = ldg256(a.rx + tbase + (size_t)max(jp[u][k], 0) * PC);
+                    // absent entries (-1) read junction 0 and are not added; x'/c0 was written by this block (plain loads)
+                    const double4v xv = ldg256(xbase + q[u] + (size_t)(max(je[u][k], 0) >> 1) * PC);
                     xa[u][k] = xv.lo; xb[u][k] = xv.hi;
                 }
             }
@@ -603,17 +607,21 @@ __device__ void face_pass(const SubArgs& a, const AmpCache<8 * NG>* ac, int s, i
             for (int u = 0; u < U; ++u) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    acc[u][0] = fma(cf[u][k], xa[u][k].x, acc[u][0]); acc[u][1] = fma(cf[u][k], xa[u][k].y, acc[u][1]);
-                    acc[u][2] = fma(cf[u][k], xb[u][k].x, acc[u][2]); acc[u][3] = fma(cf[u][k], xb[u][k].y, acc[u][3]);
+                    if (je[u][k] < 0) continue;
+                    if (je[u][k] & 1) {
+                        acc[u][0] -= xa[u][k].x; acc[u][1] -= xa[u][k].y; acc[u][2] -= xb[u][k].x; acc[u][3] -= xb[u][k].y;
+                    } else {
+                        acc[u][0] += xa[u][k].x; acc[u][1] += xa[u][k].y; acc[u][2] += xb[u][k].x; acc[u][3] += xb[u][k].y;
+                    }
                 }
                 if (has_vs) {
                     const double* cum = ac->Vs[n & 1] + q[u];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        if (jp[u][k] >= 0) {
-                            // coefficient = sign / c0: recover sign * Vs base from the per-junction records
-                            const double ic0 = __ldg(a.P0 + 4 * (size_t)jp[u][k] + 1), vb = __ldg(a.P1 + 4 * (size_t)jp[u][k] + 2);
-                            const double sv = (cf[u][k] / ic0) * vb;
+                        if (je[u][k] >= 0) {
+                            // - sign * (Vs base) * (running sum of the Vs amplitude)
+                            const double vb = __ldg(a.P1 + 4 * (size_t)(je[u][k] >> 1) + 2);
+                            const double sv = (je[u][k] & 1) ? -vb : vb;
                             for (int e = 0; e < 4; ++e) acc[u][e] -= sv * cum[e];
                         }
                     }
@@ -623,14 +631,10 @@ __device__ void face_pass(const SubArgs& a, const AmpCache<8 * NG>* ac, int s, i
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (idx0 + u * NT >= total) continue;
-            if (live[u]) {
-                const int g = __ldg(fidx + row[u]);
-                if (g >= 0 && has_f) {
-                    const double* am = ac->F[n & 1] + q[u];
-                    const double b = __ldg(a.F.base + g);
+            if (c * PC + q[u] < a.Wp) {
+                const double* am = ac->F[n & 1] + q[u];            // (zeros unless the flux is rank one; fv is 0 for halo rows)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) acc[u][k] -= TWO_PI * (b * am[k]);
-                }
+                for (int k = 0; k < 4; ++k) acc[u][k] -= TWO_PI * (fv[u] * am[k]);
             } else {
                 acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.0;
             }
@@ -650,7 +654,7 @@ __device__ void face_pass(const SubArgs& a, const AmpCache<8 * NG>* ac, int s, i
 // (not inlined, and called with plain values instead of the argument block: its registers must not weigh on the step
 // kernel, which runs it only at observed steps)
 struct VortexView {
-    const int* fj; const double* fc; const int* fidx; const int* ht; const int* top_face;
+    const int* fj; const int* fidx; const int* ht; const int* top_face;
     const double* th; const double* jrec;
     int* nsum; double* th_last; double* th_first;       // th_first: null except at the first observation
     int K, rows, nl, jlo, jhi, c, Wp;
@@ -665,17 +669,14 @@ __device__ __noinline__ void vortex_pass(const VortexView o) {
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
         for (int k0 = 0; k0 < o.K; k0 += 4) {
             const int4 j4 = __ldg(reinterpret_cast<const int4*>(o.fj + (size_t)row * o.K + k0));
-            const double2 ca = __ldg(reinterpret_cast<const double2*>(o.fc + (size_t)row * o.K + k0));
-            const double2 cb = __ldg(reinterpret_cast<const double2*>(o.fc + (size_t)row * o.K + k0) + 1);
-            const int jp[4] = {j4.x, j4.y, j4.z, j4.w};
-            const double cf[4] = {ca.x, ca.y, cb.x, cb.y};
+            const int je[4] = {j4.x, j4.y, j4.z, j4.w};
             double4v t[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) t[k] = ldg256(o.th + (size_t)max(jp[k], 0) * PC + q);
+            for (int k = 0; k < 4; ++k) t[k] = ldg256(o.th + (size_t)(max(je[k], 0) >> 1) * PC + q);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                if (jp[k] < 0) continue;
-                const double sg = cf[k] > 0.0 ? 1.0 : -1.0;
+                if (je[k] < 0) continue;
+                const double sg = (je[k] & 1) ? -1.0 : 1.0;
                 acc[0] -= sg * rint(t[k].lo.x / TWO_PI); acc[1] -= sg * rint(t[k].lo.y / TWO_PI);
                 acc[2] -= sg * rint(t[k].hi.x / TWO_PI); acc[3] -= sg * rint(t[k].hi.y / TWO_PI);
             }
@@ -1233,6 +1234,7 @@ __global__ void __launch_bounds__(NT, BLOCKS_PER_SM) k_subdomain(const SubArgs a
     AmpCache<PC>* ac = reinterpret_cast<AmpCache<PC>*>(stage + (size_t)a.stage_rows * (PC + 2));
     int* aux = reinterpret_cast<int*>(ac + 1);
     ProgSmem ps;
+    long long* const prof_p = a.prof;       // in-kernel phase counters (JJ_SUB_PROF), null in normal runs
     const int n_items = a.P * a.n_chunks;
     // More items than blocks: a block takes a contiguous range of the subdomain-major item list, so its consecutive items
     // are chunks of the SAME subdomain (its program stays loaded, its factor stream is hot in L2, and the neighbouring
@@ -1305,35 +1307,35 @@ __global__ void __launch_bounds__(NT, BLOCKS_PER_SM) k_subdomain(const SubArgs a
     long long up_step = 0;               // time steps done: the work counters of the upper phases only ever grow
     auto up_phase_timed = [&](int ph) {
         if (!UPPER) return;
-        const bool pr = a.prof && threadIdx.x == 0 && ph < PROF_UP;
+        const bool pr = prof_p && threadIdx.x == 0 && ph < PROF_UP;
         const long long t0 = pr ? clock64() : 0;
         upper_phase<NG>(a, smem, up_rows, ph, up_step);
         const long long t1 = pr ? clock64() : 0;
         grid_barrier(a.bar, bar_target);
         if (pr) {
-            a.prof[(size_t)blockIdx.x * PROF_SLOTS + 56 + 2 * ph] += t1 - t0;
-            a.prof[(size_t)blockIdx.x * PROF_SLOTS + 57 + 2 * ph] += clock64() - t1;
+            prof_p[(size_t)blockIdx.x * PROF_SLOTS + 56 + 2 * ph] += t1 - t0;
+            prof_p[(size_t)blockIdx.x * PROF_SLOTS + 57 + 2 * ph] += clock64() - t1;
         }
     };
     // the solve of the separator rows for all chunks, between the forward and the backward local sweeps
     auto top_phase_grid = [&](long long n, long long& tq) {
         grid_barrier(a.bar, bar_target);
-        if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 4] += tn - tq; tq = tn; }
+        if (prof_p && threadIdx.x == 0) { const long long tn = clock64(); prof_p[(size_t)blockIdx.x * PROF_SLOTS + 4] += tn - tq; tq = tn; }
         top_assemble<NG>(a, n, 0, a.n_chunks, blockIdx.x, gridDim.x);
         grid_barrier(a.bar, bar_target);
         if (UPPER) for (int ph = 0; ph < a.n_up_fwd; ++ph) up_phase_timed(ph);
-        if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 5] += tn - tq; tq = tn; }
+        if (prof_p && threadIdx.x == 0) { const long long tn = clock64(); prof_p[(size_t)blockIdx.x * PROF_SLOTS + 5] += tn - tq; tq = tn; }
         if (a.n_tt > 0) {
             dense_top(0, a.n_chunks, blockIdx.x, gridDim.x);
-            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 6] += tn - tq; tq = tn; }
+            if (prof_p && threadIdx.x == 0) { const long long tn = clock64(); prof_p[(size_t)blockIdx.x * PROF_SLOTS + 6] += tn - tq; tq = tn; }
             grid_barrier(a.bar, bar_target);
         }
         if (UPPER) for (int ph = a.n_up_fwd; ph < n_up; ++ph) up_phase_timed(ph);
         ++up_step;
-        if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 7] += tn - tq; tq = tn; }
+        if (prof_p && threadIdx.x == 0) { const long long tn = clock64(); prof_p[(size_t)blockIdx.x * PROF_SLOTS + 7] += tn - tq; tq = tn; }
     };
-    if (a.dbg_b) {
-        // ---- debug: one solve J = S^-1 b through the plan
+    if (UPPER && a.dbg_b) {
+        // ---- debug: one solve J = S^-1 b through the plan (general kernel only: the host launches that one for it)
         for (int item = it_lo; item < it_hi; ++item) {
             const int s = multi ? item / a.n_chunks : item % a.P, c = multi ? item % a.n_chunks : item / a.P;
             __syncthreads();
@@ -1347,7 +1349,7 @@ __global__ void __launch_bounds__(NT, BLOCKS_PER_SM) k_subdomain(const SubArgs a
                 v[velem<NG>(row, q)] = val;
             }
             __syncthreads();
-            run_levels<NG>(ps, ps.n_bwd, ps.n_levels, v, stage, a.prof);
+            run_levels<NG>(ps, ps.n_bwd, ps.n_levels, v, stage, prof_p);
             rows_to_global<NG>(v, nl, nh, a.ctop + ((size_t)c * a.n_slots + a.hptr[s]) * PC);
             rows_to_global<NG>(v, 0, nl, a.zloc + ((size_t)item * a.n_loc_max) * PC);
         }
@@ -1367,7 +1369,7 @@ __global__ void __launch_bounds__(NT, BLOCKS_PER_SM) k_subdomain(const SubArgs a
                 v[velem<NG>(row, q)] = val;
             }
             __syncthreads();
-            run_levels<NG>(ps, 0, ps.n_bwd, v, stage, a.prof);
+            run_levels<NG>(ps, 0, ps.n_bwd, v, stage, prof_p);
             for (int e = threadIdx.x; e < nl * PC; e += NT) {
                 const int row = e / PC, q = e % PC, w = c * PC + q;
                 if (w < a.Wp) a.dbg_J[(size_t)fidx[row] * a.Wp + w] = v[velem<NG>(row, q)];
@@ -1391,7 +1393,7 @@ __global__ void __launch_bounds__(NT, BLOCKS_PER_SM) k_subdomain(const SubArgs a
     }
     for (long long k = 0; k <= a.n; ++k) {
         const long long n = a.i0 + k;
-        long long tq = a.prof ? clock64() : 0;
+        long long tq = prof_p ? clock64() : 0;
         const unsigned long long draw_base = (unsigned long long)k * (unsigned long long)(n_items + (int)gridDim.x);
         unsigned long long drawn = 0;
         if (dyn && threadIdx.x == 0) drawn = atomicAdd(item_ctr, 1ull) - draw_base;
@@ -1426,16 +1428,16 @@ __global__ void __launch_bounds__(NT, BLOCKS_PER_SM) k_subdomain(const SubArgs a
                 }
                 if (UPPER && !keep_z && nl > 0) { mbar_wait(&s_zbar, zphase); zphase ^= 1u; }
                 __syncthreads();
-                run_levels<NG>(ps, 0, ps.n_bwd, v, stage, a.prof);
+                run_levels<NG>(ps, 0, ps.n_bwd, v, stage, prof_p);
             } else {
                 __syncthreads();
             }
-            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 0] += tn - tq; tq = tn; }
+            if (prof_p && threadIdx.x == 0) { const long long tn = clock64(); prof_p[(size_t)blockIdx.x * PROF_SLOTS + 0] += tn - tq; tq = tn; }
             junction_pass<NG, DEF>(a, ac, s, c, n, k > 0, k < a.n, v);
             if (k > 0 && a.obs_interval > 0 && n - 1 >= a.obs_first && (n - 1 - a.obs_first) % a.obs_interval == 0) {
                 __syncthreads();                 // the phases of step n - 1 are in the state slab
                 VortexView o;
-                o.fj = a.face_ell_j + (size_t)s * a.n_rows * a.face_K; o.fc = a.face_ell_c + (size_t)s * a.n_rows * a.face_K;
+                o.fj = a.face_ell_j + (size_t)s * a.n_rows * a.face_K;
                 o.fidx = a.face_fidx + (size_t)s * a.n_rows; o.ht = a.halo_top + a.hptr[s]; o.top_face = a.top_face;
                 o.th = a.rth + (size_t)c * a.Nj * PC; o.jrec = a.jrec;
                 o.nsum = a.obs_nsum; o.th_last = a.obs_th_last; o.th_first = (n - 1 == a.obs_first) ? a.obs_th_first : nullptr;
@@ -1444,11 +1446,11 @@ __global__ void __launch_bounds__(NT, BLOCKS_PER_SM) k_subdomain(const SubArgs a
             }
             if (k == a.n) { __syncthreads(); continue; }
             __syncthreads();
-            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 1] += tn - tq; tq = tn; }
+            if (prof_p && threadIdx.x == 0) { const long long tn = clock64(); prof_p[(size_t)blockIdx.x * PROF_SLOTS + 1] += tn - tq; tq = tn; }
             face_pass<NG>(a, ac, s, c, n, nl + nh, v);
             __syncthreads();
-            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 2] += tn - tq; tq = tn; }
-            run_levels<NG>(ps, ps.n_bwd, ps.n_levels, v, stage, a.prof);
+            if (prof_p && threadIdx.x == 0) { const long long tn = clock64(); prof_p[(size_t)blockIdx.x * PROF_SLOTS + 2] += tn - tq; tq = tn; }
+            run_levels<NG>(ps, ps.n_bwd, ps.n_levels, v, stage, prof_p);
             if (UPPER && !keep_z && nl > 0 && threadIdx.x == 0) {
                 // z of the local rows leaves as one bulk copy while the block writes out the halo contributions
                 fence_proxy_async();         // the sweep's shared-memory writes (all before its closing barrier) -> async proxy
@@ -1460,7 +1462,7 @@ __global__ void __launch_bounds__(NT, BLOCKS_PER_SM) k_subdomain(const SubArgs a
                 fence_proxy_async();
             }
             __syncthreads();     // the vector is reused by the next item / the next step
-            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 3] += tn - tq; tq = tn; }
+            if (prof_p && threadIdx.x == 0) { const long long tn = clock64(); prof_p[(size_t)blockIdx.x * PROF_SLOTS + 3] += tn - tq; tq = tn; }
         }
         if (k == a.n) break;
         if (a.n_top > 0 && chunk_local) {
@@ -1470,14 +1472,14 @@ __global__ void __launch_bounds__(NT, BLOCKS_PER_SM) k_subdomain(const SubArgs a
             const int c = blockIdx.x / a.P, s = blockIdx.x % a.P;
             unsigned* ctr = a.bar + 32 * (1 + c);
             group_barrier(ctr, bar_target, a.P);
-            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 4] += tn - tq; tq = tn; }
+            if (prof_p && threadIdx.x == 0) { const long long tn = clock64(); prof_p[(size_t)blockIdx.x * PROF_SLOTS + 4] += tn - tq; tq = tn; }
             top_assemble<NG>(a, n, c, 1, s, a.P);
             group_barrier(ctr, bar_target, a.P);
-            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 5] += tn - tq; tq = tn; }
+            if (prof_p && threadIdx.x == 0) { const long long tn = clock64(); prof_p[(size_t)blockIdx.x * PROF_SLOTS + 5] += tn - tq; tq = tn; }
             dense_top(c, 1, s, a.P);
-            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 6] += tn - tq; tq = tn; }
+            if (prof_p && threadIdx.x == 0) { const long long tn = clock64(); prof_p[(size_t)blockIdx.x * PROF_SLOTS + 6] += tn - tq; tq = tn; }
             group_barrier(ctr, bar_target, a.P);
-            if (a.prof && threadIdx.x == 0) { const long long tn = clock64(); a.prof[(size_t)blockIdx.x * PROF_SLOTS + 7] += tn - tq; tq = tn; }
+            if (prof_p && threadIdx.x == 0) { const long long tn = clock64(); prof_p[(size_t)blockIdx.x * PROF_SLOTS + 7] += tn - tq; tq = tn; }
         } else if (a.n_top > 0) {
             top_phase_grid(n, tq);
         }
@@ -1488,6 +1490,12 @@ __global__ void __launch_bounds__(NT, BLOCKS_PER_SM) k_subdomain(const SubArgs a
 __global__ void k_sub_gather_top(int n_top, const int* top_face, const double* fbase, double* topF) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < n_top) topF[k] = fbase[top_face[k]];
+}
+
+// flux base of the local rows of every subdomain (0 for halo rows), gathered once per launch
+__global__ void k_sub_gather_rows(long long n, const int* fidx, const double* fbase, double* rowF) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) { const int g = fidx[k]; rowF[k] = g >= 0 ? fbase[g] : 0.0; }
 }
 
 typedef void (*KernelPtr)(const SubArgs);
@@ -1554,9 +1562,12 @@ __global__ void k_sub_gather_params(int n, const int* orig, const double* Ic, co
     P0[4 * jp + 0] = Ic[jo]; P0[4 * jp + 1] = 1.0 / c0[jo]; P0[4 * jp + 2] = c1[jo]; P0[4 * jp + 3] = c2[jo];
     P1[4 * jp + 0] = isb ? isb[jo] : 0.0; P1[4 * jp + 1] = tb ? tb[jo] : 0.0; P1[4 * jp + 2] = vsb ? vsb[jo] : 0.0;
     P1[4 * jp + 3] = 0.0;
+    // the junction record holds the coefficients of x'/c0 (the x stream is kept divided by c0: it is what the face
+    // pass sums and what theta_n = y/c0 - x'/c0 subtracts), so 1/c0 itself is only needed for y
     double* r = jrec + 8 * (size_t)jp;
-    r[0] = Ic[jo]; r[1] = 1.0 / c0[jo]; r[2] = c1[jo]; r[3] = c2[jo];
-    r[4] = isb ? isb[jo] : 0.0; r[5] = tb ? tb[jo] : 0.0;
+    const double ic0 = 1.0 / c0[jo];
+    r[0] = Ic[jo] * ic0; r[1] = ic0; r[2] = c1[jo] * ic0; r[3] = c2[jo] * ic0;
+    r[4] = (isb ? isb[jo] : 0.0) * ic0; r[5] = (tb ? tb[jo] : 0.0) * ic0;
     const int2 rw = rows[jp];
     const char2 sg = sign[jp];
     const int s0 = rw.x >= 0 ? (int)sg.x : 0, s1 = rw.y >= 0 ? (int)sg.y : 0;
@@ -1715,6 +1726,11 @@ int subdomain_set_plan(JJHandle* h, const JJSubdomainPlan* pl) {
         if ((rc = dev_alloc(h, &p, bytes))) return rc;
         st->allocs.push_back(p); st->alloc_bytes.push_back(bytes);
         st->topF = (double*)p;
+        void* p2 = nullptr;
+        const size_t bytes2 = (size_t)std::max(pl->P * pl->n_rows, 1) * sizeof(double);
+        if ((rc = dev_alloc(h, &p2, bytes2))) return rc;
+        st->allocs.push_back(p2); st->alloc_bytes.push_back(bytes2);
+        st->rowF = (double*)p2;
     }
     if ((rc = up(h, st, &st->SinvP, pl->Sinv_packed, (size_t)pl->n_tt_pad * pl->n_tt_pad))) return rc;
     {
@@ -1750,8 +1766,15 @@ int subdomain_set_plan(JJHandle* h, const JJSubdomainPlan* pl) {
     if ((rc = up(h, st, (int**)&st->junc_row, pl->junc_row, (size_t)Nj * 2))) return rc;
     if ((rc = up(h, st, (signed char**)&st->junc_sign, (const signed char*)pl->junc_sign, (size_t)Nj * 2))) return rc;
     const size_t nell = (size_t)P * pl->n_rows * pl->face_K;
-    if ((rc = up(h, st, &st->face_ell_j, pl->face_ell_j, nell))) return rc;
-    if ((rc = up(h, st, &st->face_ell_c, pl->face_ell_c, nell))) return rc;
+    {
+        // device form of the row lists: 2 * junction + (coefficient < 0), -1 = absent (the magnitude 1/c0 of the plan's
+        // coefficients is applied by the junction pass, which stores x'/c0)
+        std::vector<int> packed(std::max<size_t>(nell, 1), -1);
+        for (size_t e = 0; e < nell; ++e)
+            if (pl->face_ell_j[e] >= 0) packed[e] = 2 * pl->face_ell_j[e] + (pl->face_ell_c[e] < 0.0 ? 1 : 0);
+        if ((rc = up(h, st, &st->face_ell_j, packed.data(), nell))) return rc;
+        SCK(cudaStreamSynchronize(h->stream));       // `packed` goes out of scope
+    }
     if ((rc = up(h, st, &st->face_fidx, pl->face_fidx, (size_t)P * pl->n_rows))) return rc;
     for (double** pp : {&st->P0, &st->P1, &st->jrec}) {
         void* p = nullptr;
@@ -1791,6 +1814,7 @@ static void fill_args(JJHandle* h, SubState* st, SubArgs& a) {
     a.tptr = st->tptr; a.tslot = st->tslot; a.top_face = st->top_face; a.SinvP = st->SinvP;
     a.tslot4 = st->no_tslot4 ? nullptr : st->tslot4;
     a.topF = (h->src[JJ_SRC_F].dev.kind == KIND_RANK1 && st->n_top > 0) ? st->topF : nullptr;
+    a.rowF = h->src[JJ_SRC_F].dev.kind == KIND_RANK1 ? st->rowF : nullptr;
     a.junc_ptr = st->junc_ptr; a.junc_orig = st->junc_orig; a.junc_row = st->junc_row; a.junc_sign = st->junc_sign;
     a.face_K = st->face_K; a.face_ell_j = st->face_ell_j; a.face_ell_c = st->face_ell_c; a.face_fidx = st->face_fidx;
     a.Nj = h->cir.Nj; a.Nf = h->cir.Nf; a.P0 = st->P0; a.P1 = st->P1; a.jrec = st->jrec; a.cpr = h->cir.cpr;
@@ -1813,7 +1837,7 @@ static int launch(JJHandle* h, SubState* st, SubArgs& a) {
     SCK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
     int cap = sms * (st->threads == 256 ? 2 : 1);
     if (st->grid_env > 0) cap = std::min(cap, st->grid_env);
-    const bool general = st->n_up_fwd + st->n_up_bwd > 0 || st->P * st->n_chunks > cap;
+    const bool general = st->n_up_fwd + st->n_up_bwd > 0 || st->P * st->n_chunks > cap || a.dbg_b != nullptr;
     KernelPtr k = pick_kernel(st->threads, st->NG, h->cir.default_cpr, general);
     if (!k) { h->err = "subdomain: no kernel for this block size / chunk width / item count"; return JJ_EINVAL; }
     {
@@ -1826,6 +1850,11 @@ static int launch(JJHandle* h, SubState* st, SubArgs& a) {
     }
     if (a.topF) {
         k_sub_gather_top<<<(st->n_top + 255) / 256, 256, 0, h->stream>>>(st->n_top, st->top_face, h->src[JJ_SRC_F].dev.base, st->topF);
+        h->launches++;
+    }
+    if (a.rowF) {
+        const long long nr = (long long)st->P * st->n_rows;
+        k_sub_gather_rows<<<(unsigned)((nr + 255) / 256), 256, 0, h->stream>>>(nr, st->face_fidx, h->src[JJ_SRC_F].dev.base, st->rowF);
         h->launches++;
     }
     SCK(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem_bytes));
