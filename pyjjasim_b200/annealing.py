@@ -115,7 +115,10 @@ class AnnealingProblem:
             factor = (mob > upper) * (1 / T_factor) + (mob <= upper) * T_factor
             return T * factor
 
-        out = device_annealing(prob, self.T[0, :, 0], adjust, N)
+        # the same rule as data, for the device-side schedule
+        upper_all = np.array([float(v[i]) if (np.array(v)).size == N else float(v * ((N - i) / N) ** 1.5) for i in range(N)])
+        rule = dict(upper=upper_all, T_factor=float(T_factor), norm=float(Nf * dt * (N - 1))) if N > 1 else None
+        out = device_annealing(prob, self.T[0, :, 0], adjust, N, rule=rule)
         self.T[0, :, 0] = out["T"]
         self.last_stats = out["stats"]
         return out["theta"], out["n"], out["profiles"]

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 #include "jj_host.h"
 
@@ -91,6 +92,31 @@ __global__ void __launch_bounds__(LANES * ROWS) k_vortex_accumulate(const FaceVi
     const int f = blockIdx.y * ROWS + threadIdx.y;
     if (w >= c.Wp || f >= c.Nf) return;
     nsum[(size_t)f * c.Wp + w] += vorticity(c, plane, c.face_ptr[f], c.face_ptr[f + 1], w);
+}
+
+// ---- the annealing schedule's per-interval bookkeeping on the device (reference: time_evolution.py:1128-1140, 1164-1174)
+// noise amplitudes of the next interval: sqrt(T) - or zero for everybody once every temperature is numerically zero,
+// which is when the reference stops drawing noise (np.allclose(T, 0), time_evolution.py:512). One block.
+__global__ void __launch_bounds__(256) k_anneal_amp(int W, int Wp, const double* __restrict__ T, double* __restrict__ amp) {
+    int hot = 0;
+    for (int w = threadIdx.x; w < W; w += blockDim.x) hot |= fabs(T[w]) > 1.0e-8;
+    hot = __syncthreads_or(hot);
+    for (int w = threadIdx.x; w < Wp; w += blockDim.x) amp[w] = (hot && w < W) ? sqrt(T[w]) : 0.0;
+}
+
+// the temperature rule on the exact integer mobility sums of the interval just run: mobility = sum / norm, compared with
+// this interval's target; T *= 1/T_factor above it, T *= T_factor otherwise (the reference's expression
+// (m > u) * (1 / f) + (m <= u) * f evaluates to exactly one of the two factors); the new temperatures are the
+// interval's row of the temperature profiles
+__global__ void k_anneal_rule(int W, const unsigned long long* __restrict__ sums, double norm, double upper, double f,
+                              double inv_f, double* __restrict__ T, double* __restrict__ profile) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    const double m = (double)(long long)sums[w] / norm;
+    const double factor = (m > upper ? inv_f : 0.0) + (m <= upper ? f : 0.0);
+    const double t = T[w] * factor;
+    T[w] = t;
+    profile[w] = t;
 }
 
 // device scratch kept in the handle: an annealing schedule calls jj_vortex_mobility once per interval, and a
@@ -271,6 +297,64 @@ int jj_vortex_mobility(JJHandle* h, int64_t plane0, int64_t n_planes, int64_t* d
     if (e == cudaSuccess) e = cudaMemcpyAsync(dst, buf, (size_t)h->W * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) { h->err = std::string("vortex_mobility: ") + cudaGetErrorString(e); return JJ_ECUDA; }
+    return JJ_OK;
+}
+
+int jj_anneal(JJHandle* h, int64_t first_interval, int32_t n_intervals, int32_t steps, const double* upper,
+              double T_factor, double inv_T_factor, double norm, double* T, double* profiles, double* device_ms) {
+    CK(cudaSetDevice(h->device));
+    REQUIRE(h->have_problem && h->have_state, JJ_ESTATE, "anneal: problem/state not set");
+    REQUIRE(n_intervals >= 0 && steps >= 1 && upper && T && profiles, JJ_EINVAL, "anneal: bad arguments");
+    REQUIRE(h->n_th_planes >= steps, JJ_ESTATE, "anneal: jj_alloc_outputs must provide one theta plane per interval step");
+    const Source& ts = h->src[JJ_SRC_T].dev;
+    REQUIRE(ts.kind == KIND_RANK1 && ts.is_static && h->src[JJ_SRC_T].table_buf, JJ_ESTATE,
+            "anneal: the temperature must be declared as a static base x amplitude input with an uploaded amplitude row");
+    REQUIRE(!h->thetas, JJ_EINVAL, "anneal: not available with dense voltage sources");
+    if (device_ms) *device_ms = 0.0;
+    if (n_intervals == 0) return JJ_OK;
+    const int W = h->W, Wp = h->Wp;
+    const FaceView c = view(h);
+    double *Td = nullptr, *prof = nullptr;
+    unsigned long long* sums = nullptr;
+    const size_t tb = (size_t)Wp * sizeof(double), pb = (size_t)n_intervals * W * sizeof(double);
+    int rc;
+    if ((rc = dev_alloc(h, (void**)&Td, tb))) return rc;
+    if ((rc = dev_alloc(h, (void**)&prof, pb))) { dev_free(h, Td, tb); return rc; }
+    std::vector<long long> planes(steps);
+    for (int k = 0; k < steps; ++k) planes[k] = k;
+    cudaError_t e = cudaMemsetAsync(Td, 0, tb, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(Td, T, (size_t)W * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    const int strips = (Wp + LANES - 1) / LANES;
+    int slices = (c.Nf + ROWS - 1) / ROWS;
+    slices = std::max(1, std::min(slices, (148 * 8 + strips - 1) / strips));
+    double ms = 0.0;
+    rc = JJ_OK;
+    for (int i = 0; i < n_intervals && rc == JJ_OK && e == cudaSuccess; ++i) {
+        k_anneal_amp<<<1, 256, 0, h->stream>>>(W, Wp, Td, h->src[JJ_SRC_T].table_buf);
+        h->launches++;
+        if (first_interval + i > 0)      // zero-velocity restart of every interval but the first (time_evolution.py:1169-1171)
+            e = cudaMemcpyAsync(h->th2, h->th1, (size_t)c.Nj * Wp * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
+        if (e != cudaSuccess) break;
+        rc = jj_run(h, (first_interval + i) * (int64_t)steps, steps, (const int64_t*)planes.data(), nullptr);
+        if (rc) break;
+        ms += h->last_ms;
+        if ((rc = scratch(h, (size_t)Wp * sizeof(unsigned long long), (void**)&sums))) break;
+        e = cudaMemsetAsync(sums, 0, (size_t)Wp * sizeof(unsigned long long), h->stream);
+        if (c.Nf > 0 && steps >= 2) {
+            k_vortex_mobility<<<dim3(strips, slices), dim3(LANES, ROWS), 0, h->stream>>>(c, h->th_out, steps, sums);
+            h->launches++;
+        }
+        k_anneal_rule<<<(W + 255) / 256, 256, 0, h->stream>>>(W, sums, norm, upper[i], T_factor, inv_T_factor, Td, prof + (size_t)i * W);
+        h->launches++;
+    }
+    if (rc == JJ_OK && e == cudaSuccess) e = cudaMemcpyAsync(T, Td, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (rc == JJ_OK && e == cudaSuccess) e = cudaMemcpyAsync(profiles, prof, pb, cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t e2 = cudaStreamSynchronize(h->stream);
+    dev_free(h, Td, tb); dev_free(h, prof, pb);
+    if (rc) return rc;
+    if (e == cudaSuccess) e = e2;
+    if (e != cudaSuccess) { h->err = std::string("anneal: ") + cudaGetErrorString(e); return JJ_ECUDA; }
+    if (device_ms) *device_ms = ms;
     return JJ_OK;
 }
 

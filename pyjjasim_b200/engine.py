@@ -595,6 +595,18 @@ class DeviceEngine:
         n[self.tab.perm] = ns
         return int(cnt.value), n, t0, t1
 
+    def anneal(self, first_interval, n_intervals, steps, upper, T_factor, norm, T):
+        """The temperature schedule of n_intervals intervals on the device (jj_anneal): -> (T after the last interval,
+        profiles (n_intervals, W), device milliseconds). upper: the mobility target of every interval."""
+        T = np.ascontiguousarray(T, dtype=np.double).copy()
+        up = np.ascontiguousarray(upper, dtype=np.double)
+        assert up.shape == (n_intervals,) and T.shape == (self.W,)
+        prof = np.zeros((n_intervals, self.W))
+        ms = C.c_double(0.0)
+        self._ck(self.lib.jj_anneal(self.h, int(first_interval), int(n_intervals), int(steps), _lib.f64(up), float(T_factor),
+                                    1 / T_factor, float(norm), _lib.f64(T), _lib.f64(prof), C.byref(ms)))
+        return T, prof, float(ms.value)
+
     def vortex_mobility_sums(self, plane0, n_planes):
         """(W,) integer sums over faces and consecutive stored planes of |n(t+1) - n(t)|
         (numerator of the reference's get_vortex_mobility, time_evolution.py:1128-1133)."""
@@ -779,7 +791,9 @@ def _run_shard(problem, tab, specs, dev, w0, w1, th_mask, I_mask, th_host, I_hos
         eng.set_problem(W, dt, seed=seed, problem_offset=w0, engine=engine_kind)
         at_rest = getattr(problem, "starts_at_rest_with_zero_phases", None)
         if not (at_rest is not None and at_rest()):       # (jj_set_problem has cleared the state: nothing to upload)
-            eng.set_state(problem.config_at_minus_1[:, w0:w1], problem.config_at_minus_2[:, w0:w1])
+            pair = getattr(problem, "initial_phases", None)
+            m1, m2 = pair() if pair is not None else (problem.config_at_minus_1, problem.config_at_minus_2)
+            eng.set_state(m1[:, w0:w1], m2[:, w0:w1])
         ex = extras or {}
         if ex.get("interval"):
             eng.observe_begin(ex.get("first", 0), ex["interval"])
@@ -1041,6 +1055,16 @@ def _anneal_shard(problem, tab, tab2, specs, dev, w0, w1, ann, adjust, out, engi
         _setup_sources(eng, specs, sh, tab)
         eng.set_source(_lib.JJ_SRC_T, _lib.JJ_KIND_RANK1, True, np.sqrt(2.0 * tab.Rv))
         eng.alloc_outputs(steps, 0)
+        rule = ann.get("rule")
+        if rule is not None and replay is None and os.environ.get("JJ_ANNEAL_HOST", "0") != "1":
+            # the whole schedule in one call: amplitudes, restarts, mobility sums and the temperature rule stay on the
+            # device (same arithmetic on the same integers as `adjust`, so the profiles are bit-identical)
+            eng.upload_source(_lib.JJ_SRC_T, 0, np.zeros((1, W)))
+            T_new, prof, ms = eng.anneal(0, n_int, steps, rule["upper"], rule["T_factor"], rule["norm"], out["T"][w0:w1])
+            out["T"][w0:w1] = T_new
+            out["profiles"][:, w0:w1] = prof
+            total_ms += ms
+            n_int = 0
         for i in range(n_int):
             T = out["T"][w0:w1]
             # the reference stops drawing noise once every temperature is numerically zero (time_evolution.py:512)
@@ -1088,13 +1112,16 @@ def _anneal_shard(problem, tab, tab2, specs, dev, w0, w1, ann, adjust, out, engi
         _release_engine(dev, key, eng, ok)
 
 
-def device_annealing(problem, T0, adjust, interval_count, final_runs=5, engine=None):
+def device_annealing(problem, T0, adjust, interval_count, final_runs=5, engine=None, rule=None):
     """
     Device-resident annealing schedule around the stepping loop (reference: time_evolution.py:1142-1191).
 
     problem : the TimeEvolutionProblem the reference's loop would re-run (circuit, dt, interval_steps steps, flux,
               current sources; its temperature is ignored). T0 : (W,) start temperatures.
     adjust(sums, i, T) -> new T : the temperature rule, given the exact integer mobility sums of interval i.
+    rule : the same rule as data, dict(upper (interval_count,), T_factor, norm): new T = T / T_factor where
+           sums / norm > upper[i], else T * T_factor. When given (and no noise is replayed) the schedule runs in one
+           device call per shard (jj_anneal) instead of one host round trip per interval.
     Returns dict(profiles (interval_count, W), theta (Nj, W), n (Nf, W), stats).
     """
     if getattr(problem, "stencil_width", 3) != 3:
@@ -1118,7 +1145,7 @@ def device_annealing(problem, T0, adjust, interval_count, final_runs=5, engine=N
                theta=np.zeros((tab.Nj, W)), n=np.zeros((tab.Nf, W), dtype=int))
     ann = dict(dt=dt, interval_count=int(interval_count), interval_steps=problem._Nt(), final_runs=int(final_runs),
                seed=resolve_noise_seed(problem),
-               noise_replay=getattr(problem, "noise_replay", None))
+               noise_replay=getattr(problem, "noise_replay", None), rule=rule)
     bounds = shard_bounds(W, len(devices))
     jobs = [(dev, bounds[k], bounds[k + 1]) for k, dev in enumerate(devices) if bounds[k + 1] > bounds[k]]
     stats, errors = {}, []

@@ -141,6 +141,12 @@ class TimeEvolutionProblem:
         """True when neither initial condition was given: the device state is simply cleared"""
         return self._m1 is None and self._m2 is None
 
+    def initial_phases(self):
+        """(theta(-1), theta(-2)) for the device upload, without materialising the copy that stands for an omitted
+        theta(-2) (a problem that starts at rest)"""
+        m1 = self.config_at_minus_1
+        return m1, (m1 if self._m2 is None else self._m2)
+
     @property
     def config_at_minus_1(self):
         if self._m1 is None:

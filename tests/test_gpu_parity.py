@@ -328,6 +328,30 @@ def test_annealing_matches_reference_golden(name, engine, golden_dir):
     assert np.array_equal(configs[1].get_vortex_configuration(), n[:, 1])
 
 
+@pytest.mark.parametrize("engine", ENGINES)
+def test_device_side_temperature_schedule_equals_the_host_rule_bit_for_bit(engine, monkeypatch):
+    # jj_anneal keeps amplitudes, restarts, mobility sums and the temperature rule on the device; the same schedule with
+    # one host round trip per interval (the reference's expressions in numpy on the same integer sums) must give the
+    # same temperature profiles and phases exactly - both directions of the rule, per-interval targets, a cold start
+    monkeypatch.setenv("JJ_ENGINE", engine)
+    a = pj.SquareArray(14, 13)
+    for kw in (dict(vortex_mobility=0.02, start_T=0.4, T_factor=1.25, interval_count=16),
+               dict(vortex_mobility=np.linspace(0.05, 0.001, 9), start_T=0.15, T_factor=1.5, interval_count=9),
+               dict(vortex_mobility=0.01, start_T=0.0, T_factor=1.1, interval_count=3)):
+        args = dict(circuit=a, time_step=0.5, interval_steps=10, external_flux=0.2, current_sources=0, problem_count=10,
+                    noise_seed=99, **kw)
+        monkeypatch.setenv("JJ_ANNEAL_HOST", "1")
+        th_h, n_h, prof_h = pj.AnnealingProblem(**args).anneal()
+        monkeypatch.setenv("JJ_ANNEAL_HOST", "0")
+        ap = pj.AnnealingProblem(**args)
+        th_d, n_d, prof_d = ap.anneal()
+        assert np.array_equal(prof_d, prof_h) and np.array_equal(th_d, th_h) and np.array_equal(n_d, n_h)
+        assert np.array_equal(ap.T[0, :, 0], prof_h[-1])
+        if kw["start_T"] > 0:
+            ratio = prof_h[1:] / prof_h[:-1]
+            assert np.any(ratio > 1) and (np.any(ratio < 1) or kw["interval_count"] < 10)
+
+
 def test_annealing_equals_reference_style_loop():
     # the loop exactly as the reference writes it (re-entering compute(), assigning prob.temperature and the
     # initial conditions, vortex configurations on the host) gives the same schedule as the device-resident path
