@@ -17,7 +17,7 @@ evaluates it on the device:
 """
 import numpy as np
 
-__all__ = ["RankOneSource", "SourceSpec", "classify_source"]
+__all__ = ["RankOneSource", "SourceSpec", "classify_source", "AmplitudeModel"]
 
 ZERO, RANK1, DENSE = 0, 1, 2
 # an input counts as base[e] * amp[w] when that product reproduces it to a few units in the last place
@@ -55,11 +55,113 @@ class RankOneSource:
         return self.base[:, None] * self.amp(i)[None, :]
 
 
+class AmplitudeModel:
+    """
+    amp(i)[w] = c[w] + l[w] i + a[w] cos(omega i) + b[w] sin(omega i): the closed forms the reference's example scripts
+    drive their circuits with (a constant, a ramp, DC + AC: examples/time_evolution_example_5_giant_shapiro_steps.py:33),
+    recovered from a plain callable ``Is(i) -> (N, W)`` so that the callable - which materialises an (N, W) array per
+    call, 535 MB for SquareArray(256,256) x 512 problems - is evaluated at a few dozen steps instead of at every step.
+
+    ``fit(sample)`` takes ``sample(i) -> (W,)`` (the amplitude of the rank-one input at step i), samples the first
+    steps and a few far ones, and returns a model that reproduces all of them to ``RTOL`` of the amplitude scale, or
+    None. While the run goes on the model is re-verified against the callable every ``check_every`` steps - an interval
+    chosen from the measured cost of one call so that verification costs ~50 us per time step, between 16 and 4096
+    steps - and from the first chunk of steps in which a check fails the callable is evaluated at every step again.
+    What this cannot see is a transient that begins and ends between two checks (a pulse shorter than the interval on
+    top of an otherwise closed-form drive): pass such inputs as arrays or RankOneSource, or set JJ_SOURCE_MODEL=0,
+    which keeps the per-step evaluation. The model reproduces the callable to ~1e-10 of the amplitude scale.
+    """
+    RTOL = 1e-11
+    NEAR = 10                # consecutive steps sampled at the start
+
+    def __init__(self, c, l, a, b, omega, check_every=2048):
+        self.c, self.l, self.a, self.b, self.omega = c, l, a, b, float(omega)
+        self.check_every = int(check_every)
+
+    def table(self, steps):
+        i = np.asarray(steps, dtype=np.double)[:, None]
+        out = self.c[None, :] + self.l[None, :] * i
+        if self.omega != 0.0:
+            out = out + self.a[None, :] * np.cos(self.omega * i) + self.b[None, :] * np.sin(self.omega * i)
+        return out
+
+    @staticmethod
+    def _design(steps, omega):
+        i = np.asarray(steps, dtype=np.double)
+        cols = [np.ones_like(i), i]
+        if omega != 0.0:
+            cols += [np.cos(omega * i), np.sin(omega * i)]
+        return np.stack(cols, axis=1)
+
+    @classmethod
+    def _solve(cls, steps, X, omega):
+        M = cls._design(steps, omega)
+        coef, *_ = np.linalg.lstsq(M, X, rcond=None)
+        return coef, X - M @ coef
+
+    @classmethod
+    def fit(cls, sample, Nt):
+        near = list(range(min(cls.NEAR, Nt)))
+        if len(near) < 6:
+            return None
+        far = sorted(set(int(round(f * (Nt - 1))) for f in (0.25, 0.5, 0.75, 1.0)) - set(near))
+        steps = near + far
+        import time
+        t0 = time.perf_counter()
+        X = np.stack([np.asarray(sample(i), dtype=np.double) for i in steps])        # (S, W)
+        per_call = (time.perf_counter() - t0) / len(steps)
+        check_every = int(min(4096, max(16, round(per_call / 50e-6))))
+        scale = float(np.max(np.abs(X)))
+        if scale == 0.0 or not np.all(np.isfinite(X)):
+            return None
+        tol = cls.RTOL * scale
+        # second differences of the consecutive samples remove constant and ramp; what is left is the oscillation
+        Xn = X[:len(near)]
+        e = Xn[2:] - 2.0 * Xn[1:-1] + Xn[:-2]
+        omega = 0.0
+        if np.max(np.abs(e)) > tol:
+            # a sinusoid obeys e[i+1] + e[i-1] = 2 cos(omega) e[i]
+            den = float(np.sum(e[1:-1] ** 2))
+            if den == 0.0:
+                return None
+            g = float(np.sum(e[1:-1] * (e[2:] + e[:-2]))) / den
+            if not -2.0 < g < 2.0:
+                return None
+            omega = float(np.arccos(0.5 * g))
+            # the frequency from ten neighbouring samples is good to ~1e-13; the far samples pin it (Gauss-Newton on omega,
+            # a few steps, each bounded so that the phase at the far samples never slips by a cycle)
+            i_all = np.asarray(steps, dtype=np.double)
+            for _ in range(12):
+                coef, r = cls._solve(steps, X, omega)
+                if np.max(np.abs(r)) <= tol:
+                    break
+                dM = (-coef[2][None, :] * np.sin(omega * i_all)[:, None] + coef[3][None, :] * np.cos(omega * i_all)[:, None]) \
+                    * i_all[:, None]
+                # variable projection: the coefficients are re-fitted at every frequency, so only the part of the
+                # derivative outside the span of the design columns moves the residual
+                Q, _ = np.linalg.qr(cls._design(steps, omega))
+                dM = dM - Q @ (Q.T @ dM)
+                den = float(np.sum(dM * dM))
+                if den == 0.0:
+                    break
+                step = float(np.sum(dM * r)) / den
+                omega += float(np.clip(step, -0.25 / max(i_all[-1], 1.0), 0.25 / max(i_all[-1], 1.0)))
+        coef, r = cls._solve(steps, X, omega)
+        if np.max(np.abs(r)) > tol:
+            return None
+        W = X.shape[1]
+        a, b = (coef[2], coef[3]) if omega != 0.0 else (np.zeros(W), np.zeros(W))
+        l = np.where(np.abs(coef[1]) * max(Nt, 1) <= tol, 0.0, coef[1])
+        return cls(coef[0], l, a, b, omega, check_every)
+
+
 class SourceSpec:
     """Device-facing description of one input; ``chunk(i0, i1)`` yields the tables for steps [i0, i1)."""
 
-    def __init__(self, kind, N, W, Nt, base=None, static=True, amp_fn=None, dense_fn=None):
+    def __init__(self, kind, N, W, Nt, base=None, static=True, amp_fn=None, dense_fn=None, model=None):
         self.kind, self.N, self.W, self.Nt = kind, N, W, Nt
+        self.model = model          # AmplitudeModel standing in for amp_fn between its checks, or None
+        self.model_checks = 0       # how often the callable was evaluated to re-verify the model
         self.base = base            # (N,) for RANK1
         self.static = static        # True: a single table row is valid for every step
         self._amp_fn = amp_fn       # i -> (W,)
@@ -71,6 +173,20 @@ class SourceSpec:
     def amp_chunk(self, i0, i1):
         """(K, W) float64 amplitudes for RANK1; K == 1 when static."""
         steps = [i0] if self.static else range(i0, i1)
+        if self.model is not None and not self.static:
+            tab = self.model.table(steps)
+            # re-verify against the callable at the multiples of check_every that fall into this chunk (and at its
+            # first step); a miss retires the model for the rest of the run
+            every = self.model.check_every
+            checks = sorted(set([i0] + list(range(-(-i0 // every) * every, i1, every))))
+            scale = max(float(np.max(np.abs(tab))), 1e-300)
+            for i in checks:
+                self.model_checks += 1
+                if np.max(np.abs(np.asarray(self._amp_fn(i), dtype=np.double) - tab[i - i0])) > 10 * self.model.RTOL * scale:
+                    self.model = None
+                    break
+            else:
+                return np.ascontiguousarray(tab)
         return np.ascontiguousarray(np.stack([np.asarray(self._amp_fn(i), dtype=np.double) for i in steps]))
 
     def dense_chunk(self, i0, i1):
@@ -167,7 +283,10 @@ def classify_source(x, N, W, Nt, zero_if_allclose=True):
                 for i in sorted(set([0, 1, Nt // 3, Nt // 2, Nt - 1])):
                     if 0 <= i < Nt:
                         amp_fn(i)
-                return SourceSpec(RANK1, N, W, Nt, base=base, static=False, amp_fn=amp_fn, dense_fn=x)
+                import os
+                use_model = Nt > 4 * AmplitudeModel.NEAR and os.environ.get("JJ_SOURCE_MODEL", "1") != "0"
+                model = AmplitudeModel.fit(amp_fn, Nt) if use_model else None
+                return SourceSpec(RANK1, N, W, Nt, base=base, static=False, amp_fn=amp_fn, dense_fn=x, model=model)
             except NotRankOne:
                 pass
         return SourceSpec(DENSE, N, W, Nt, static=False, dense_fn=x)

@@ -116,6 +116,26 @@ def test_reference_style_problem_object_through_the_device_core(engine, monkeypa
     assert np.array_equal(th[:, :, 1], prob.config_at_minus_1) and np.array_equal(th[:, :, 0], prob.config_at_minus_2)
 
 
+def test_reference_example_callable_runs_through_its_closed_form():
+    # examples/time_evolution_example_5_giant_shapiro_steps.py drives the array with a plain callable
+    # Is(i) = base[:, None] * (IDC + IAmp sin(f i dt)): its closed form is recovered from a few evaluations, the run
+    # evaluates it a few dozen times instead of once per step, and the phases equal those of the exact rank-one input
+    a = pj.SquareArray(20, 20)
+    W, Nt, dt = 101, 3000, 0.05
+    base, IDC = a.current_base(angle=0), np.linspace(0, 2, W)
+    calls = [0]
+
+    def Is(i):
+        calls[0] += 1
+        return base[:, None] * (IDC + 1.0 * np.sin(0.25 * i * dt))
+    kw = dict(time_step=dt, time_step_count=Nt, store_time_steps=[Nt // 3, Nt - 1], store_current=False, store_voltage=False)
+    res = pj.TimeEvolutionProblem(a, current_sources=Is, **kw).compute()
+    assert calls[0] < 400                      # (constructor + classification + fit + sparse checks)
+    exact = pj.TimeEvolutionProblem(a, current_sources=pj.RankOneSource(base, lambda i: IDC + 1.0 * np.sin(0.25 * i * dt)), **kw).compute()
+    scale = max(1.0, float(np.max(np.abs(exact.theta))))
+    assert scale > 10.0 and np.max(np.abs(res.theta - exact.theta)) <= 1e-8 * scale
+
+
 def test_chunked_run_equals_single_run(monkeypatch):
     # time-dependent tables uploaded chunk by chunk give the same result as one chunk
     from pyjjasim_b200 import engine

@@ -256,6 +256,51 @@ def test_the_reference_own_problem_class_binds_to_the_device_core_classification
     assert real.get_problem_count() == fake.get_problem_count() and real._Nt() == fake._Nt() and real._dt() == fake._dt()
 
 
+def test_closed_form_amplitudes_are_recovered_from_plain_callables(monkeypatch):
+    # a reference-style callable Is(i) -> (N, W) of the form base x (constant + ramp + DC/AC drive) is evaluated at a few
+    # dozen steps instead of at every step; anything else keeps the per-step evaluation; a model that stops holding is
+    # retired at the next check and the chunk is evaluated exactly
+    N, W, Nt = 30, 17, 60000
+    rng = np.random.RandomState(1)
+    base, IDC = rng.randn(N), np.linspace(0, 2, W)
+    j0 = int(np.argmax(np.abs(base)))
+    calls = [0]
+
+    def counted(f):
+        def g(i):
+            calls[0] += 1
+            return f(i)
+        return g
+    for amp in (lambda i: IDC + np.sin(0.0125 * i), lambda i: 0.3 * IDC + (1 + IDC) * np.cos(2.9 * i + 0.3) + 1e-5 * i,
+                lambda i: 0.5 + 1e-4 * i * np.ones(W), lambda i: IDC + 0.0 * i):
+        calls[0] = 0
+        s = sources.classify_source(counted(lambda i, a=amp: base[:, None] * a(i)[None, :]), N, W, Nt)
+        assert s.kind == sources.RANK1 and s.model is not None
+        for i0 in (0, 31000, Nt - 500):
+            tab = s.amp_chunk(i0, i0 + 500) * s.base[j0]
+            want = np.stack([amp(i) for i in range(i0, i0 + 500)]) * base[j0]
+            assert np.max(np.abs(tab - want)) <= 1e-9 * np.max(np.abs(want))
+        assert s.model is not None and calls[0] < 120            # not 1500 evaluations
+    # a chirp is not one of the closed forms: evaluated per step
+    s = sources.classify_source(lambda i: base[:, None] * (1 + np.sin(1e-6 * i * i)) * np.ones((1, W)), N, W, Nt)
+    assert s.kind == sources.RANK1 and s.model is None
+    # a change that the far samples of the fit see: no model
+    late = lambda i: base[:, None] * (IDC + np.sin(0.01 * i) * (1.0 if i < 30000 else 1.5))[None, :]
+    assert sources.classify_source(late, N, W, Nt).model is None
+    # the closed form stops holding between steps 20 000 and 26 000 (none of the fit's samples falls there): the model is
+    # retired at the next check and the chunk is evaluated exactly
+    late = lambda i: base[:, None] * (IDC + np.sin(0.01 * i) * (1.5 if 20000 <= i < 26000 else 1.0))[None, :]
+    s = sources.classify_source(late, N, W, Nt)
+    assert s.model is not None
+    s.model.check_every = 256
+    assert np.allclose(s.amp_chunk(19000, 19900)[5] * s.base[j0], (IDC + np.sin(0.01 * 19005)) * base[j0], rtol=0, atol=1e-9)
+    tab = s.amp_chunk(19900, 20600)
+    assert s.model is None
+    assert np.allclose(tab[400] * s.base[j0], (IDC + 1.5 * np.sin(0.01 * 20300)) * base[j0], rtol=1e-14)
+    monkeypatch.setenv("JJ_SOURCE_MODEL", "0")
+    assert sources.classify_source(lambda i: base[:, None] * (IDC + np.sin(0.0125 * i))[None, :], N, W, Nt).model is None
+
+
 def test_cpr_harmonics():
     a, b = harmonics(pj.DefaultCPR())
     assert list(a) == [0, 0] and list(b) == [0, 1]
