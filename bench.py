@@ -259,7 +259,7 @@ def named_config(pj, name, rank, world):
         W = 512 * world
         w0 = 512 * rank
         Is = pj.RankOneSource(a.current_base(angle=0), np.linspace(0.1, 1.5, W)[w0:w0 + 512])
-        return a, dict(time_step=0.05, external_flux=0.1, current_sources=Is), 40, (w0, w0 + 512), W, "512 problems per GPU"
+        return a, dict(time_step=0.05, external_flux=0.1, current_sources=Is), 100, (w0, w0 + 512), W, "512 problems per GPU"
     if name == "cfg4":
         a = pj.SquareArray(256, 256)
         a.set_capacitance(1.0)
@@ -271,7 +271,7 @@ def named_config(pj, name, rank, world):
         idc, ia = IDC[w0:w0 + per], IA[w0:w0 + per]
         Is = pj.RankOneSource(a.current_base(angle=0), lambda i: idc + ia * np.sin(0.25 * i * 0.05), problem_count=per)
         note = "one GPU's share (512) of the 4096-problem sweep" if world == 1 else f"4096 problems in shards of {per}"
-        return a, dict(time_step=0.05, current_sources=Is, temperature=0.01 * np.ones((1, per, 1)), noise_seed=SEED), 40, (w0, w0 + per), W, note
+        return a, dict(time_step=0.05, current_sources=Is, temperature=0.01 * np.ones((1, per, 1)), noise_seed=SEED), 100, (w0, w0 + per), W, note
     if name == "cfg5":
         a = pj.SquareArray(1000, 1000)
         a.set_inductance(1.0)
@@ -280,7 +280,7 @@ def named_config(pj, name, rank, world):
         per = W // world
         w0 = per * rank
         Is = pj.RankOneSource(a.current_base(angle=0), np.linspace(0.5, 1.5, W)[w0:w0 + per])
-        return a, dict(time_step=0.05, external_flux=0.05, current_sources=Is), 12, (w0, w0 + per), W, f"64 problems in shards of {per}"
+        return a, dict(time_step=0.05, external_flux=0.05, current_sources=Is), 20, (w0, w0 + per), W, f"64 problems in shards of {per}"
     raise KeyError(name)
 
 
@@ -304,14 +304,18 @@ def per_config(rank, world, local_rank, dist, peak):
                                                store_voltage=False, **kw)
                 res = prob.compute()               # first call: ordering, factorisation, plans, upload
                 t1 = time.perf_counter()
-                res = prob.compute()
+                del res
+                res = prob.compute()               # warm: result block pinned and pooled, engine cached
+                del res
+                t1b = time.perf_counter()
+                res = prob.compute()               # the timed call (steady state of repeated calls, like the cfg2 e2e leg)
                 t2 = time.perf_counter()
                 st = list(engine.last_run_stats.values())[0]
                 assert np.all(np.isfinite(res.theta))
-                dev_s, wall = st["total_ms"] * 1e-3, t2 - t1
+                dev_s, wall = st["total_ms"] * 1e-3, t2 - t1b
                 tab = engine._tables_for(a, kw["time_step"], engine._n_parts_for(a, w1 - w0, local_rank, None))
                 rec.update(engine={1: "streaming", 3: "subdomain"}.get(st["engine"]), subdomains=st["cluster_size"],
-                           setup_s=round((t1 - t0) - (t2 - t1), 2), device_us_per_time_step=round(dev_s * 1e6 / Nt, 1),
+                           setup_s=round((t1 - t0) - (t2 - t1b), 2), device_us_per_time_step=round(dev_s * 1e6 / Nt, 1),
                            roofline_frac=algorithmic_bytes_per_time_step(tab, w1 - w0) * Nt / dev_s / 1e9 / peak)
                 del res, prob
         except Exception as e:

@@ -9,30 +9,7 @@ from .josephson_circuit import Circuit
 __all__ = ["AnnealingProblem", "AnnealedConfiguration"]
 
 
-class AnnealedConfiguration:
-    """
-    One annealed problem: phases after the closing T = 0 runs and the vortex configuration the reference hands to
-    its static solver (reference: time_evolution.py:1185-1188). The reference then polishes the phases with
-    StaticProblem.compute() (static_problem.py) - a Newton solve outside the time-evolution path that this package
-    does not provide; the object therefore carries the un-polished state, and ``AnnealingProblem.compute`` reports
-    status 2 ("indeterminate") for it.
-    """
-
-    def __init__(self, circuit, theta, n, external_flux, current_sources):
-        self.circuit, self.theta, self.n = circuit, theta, n
-        self.external_flux, self.current_sources = external_flux, current_sources
-
-    def get_circuit(self):
-        return self.circuit
-
-    def get_theta(self):
-        return self.theta
-
-    def get_n(self):
-        return self.n
-
-    def get_vortex_configuration(self):
-        return self.n
+from .static_polish import AnnealedConfiguration, london_approximation, newton_stationary_states, _CircuitOps   # noqa: E402
 
 
 class AnnealingProblem:
@@ -123,21 +100,33 @@ class AnnealingProblem:
         self.last_stats = out["stats"]
         return out["theta"], out["n"], out["profiles"]
 
-    def compute(self):
+    def compute(self, polish=True):
         """
-        Executes the annealing procedure (reference: time_evolution.py:1142-1191).
+        Executes the annealing procedure (reference: time_evolution.py:1142-1191): the temperature schedule and the
+        closing T = 0 runs on the GPU (``anneal``), then - like the reference - one stationary-state solve per problem
+        for the annealed vortex configuration, started from the London approximation (host, static_polish.py).
 
         Returns
         -------
-        status : (problem_count,) int array; 2 (indeterminate) for every problem, because the static Newton solve
-            with which the reference decides between 0 (converged) and 1 (diverged) is outside this package
-        configurations : (problem_count,) list of AnnealedConfiguration (phases and vortex configuration of the
-            annealed state, before the reference's static polish)
+        status : (problem_count,) int array: 0 converged onto the annealed vortex configuration, 1 diverged or
+            converged onto another one, 2 iteration limit (polish=False: 2 for every problem, nothing is solved)
+        configurations : (problem_count,) list of AnnealedConfiguration (stationary phases, vortex configuration,
+            getters of the reference's StaticConfiguration; ``annealed_theta`` holds the phases the anneal ended with)
         temperature_profiles : (interval_count, problem_count) array
         """
         theta, n, profiles = self.anneal()
-        f = np.atleast_1d(self.external_flux)
-        configurations = [AnnealedConfiguration(self.circuit, theta[:, p].copy(), n[:, p].copy(), f, self.current_sources)
-                          for p in range(self.problem_count)]
-        status = np.full(self.problem_count, 2, dtype=int)
+        prob = self._problem()
+        W, cpr = self.problem_count, prob.current_phase_relation
+        f = np.array(np.broadcast_to(prob._f(0), (self.circuit._Nf(), W)), dtype=np.double)
+        Is = np.array(np.broadcast_to(prob._Is(0), (self.circuit._Nj(), W)), dtype=np.double)
+        if polish:
+            ops = _CircuitOps(self.circuit)
+            theta0 = london_approximation(self.circuit, f, n, Is, ops)
+            theta_s, status, info = newton_stationary_states(self.circuit, theta0, Is, f, n, cpr, ops=ops)
+            self.last_polish = info
+        else:
+            theta_s, status, info = theta, np.full(W, 2, dtype=int), dict(error=np.full(W, np.nan))
+        configurations = [AnnealedConfiguration(self.circuit, theta_s[:, p].copy(), n[:, p].copy(), f[:, p], Is[:, p], cpr,
+                                                annealed_theta=theta[:, p].copy(), error=float(info["error"][p]))
+                          for p in range(W)]
         return status, configurations, profiles

@@ -55,9 +55,10 @@ class _PinnedPool:
     """Result planes in page-locked memory (device -> host at PCIe speed, no page faults on fresh numpy pages). Blocks
     are reused across compute() calls of the same result size; pinning is slow, so only a few sizes are kept."""
 
-    MAX_BLOCK = 2 << 30
-    MAX_CACHED = 2 << 30
-    MAX_PINNED = 6 << 30          # in use + cached; results beyond that are ordinary numpy arrays
+    # JJ_PINNED_MAX_GB (default 16): page-locked memory in use + cached; results beyond that are ordinary numpy arrays
+    MAX_PINNED = int(float(os.environ.get("JJ_PINNED_MAX_GB", "16")) * (1 << 30))
+    MAX_BLOCK = MAX_PINNED // 2
+    MAX_CACHED = MAX_PINNED // 2
 
     def __init__(self):
         self._free, self._cached, self._in_use, self._lock = {}, 0, 0, threading.Lock()
@@ -795,6 +796,7 @@ def _run_shard(problem, tab, specs, dev, w0, w1, th_mask, I_mask, th_host, I_hos
             m1, m2 = pair() if pair is not None else (problem.config_at_minus_1, problem.config_at_minus_2)
             eng.set_state(m1[:, w0:w1], m2[:, w0:w1])
         ex = extras or {}
+        lead = ex.get("lead", 2)
         if ex.get("interval"):
             eng.observe_begin(ex.get("first", 0), ex["interval"])
         fetch_theta = ex.get("fetch_theta", True)
@@ -878,10 +880,10 @@ def _run_shard(problem, tab, specs, dev, w0, w1, th_mask, I_mask, th_host, I_hos
                     ex["n_planes"][dst0:dst0 + wanted.size, :, w0:w1] = n_all[wanted - wanted[0]]
             if n_th and fetch_theta:
                 first = th_idx[i0:i1][tm][0]
-                eng.fetch_theta(0, n_th, out=th_host[2 + first: 2 + first + n_th, :, w0:w1])
+                eng.fetch_theta(0, n_th, out=th_host[lead + first: lead + first + n_th, :, w0:w1])
             if n_I:
                 first = I_idx[i0:i1][im][0]
-                eng.fetch_current(0, n_I, out=I_host[2 + first: 2 + first + n_I, :, w0:w1])
+                eng.fetch_current(0, n_I, out=I_host[lead + first: lead + first + n_I, :, w0:w1])
             i0 = i1
         if ex.get("interval"):
             cnt, nsum, t_first, t_last = eng.observe_fetch()
@@ -962,8 +964,12 @@ def device_time_evolution_core(problem, th_store_mask, I_store_mask, engine=None
         ex["wanted"] = np.asarray(ex.get("wanted", th_mask), dtype=bool) & th_mask
         ex["n_planes"] = np.zeros((int(ex["wanted"].sum()), tab.Nf, W), dtype=np.int32)
     keep_theta = th_mask.any() and ex.get("fetch_theta", True)
-    th_host = _pinned.empty((int(th_mask.sum()) + 2, Nj, W), pin_dev) if keep_theta else np.empty((2, Nj, W))
-    I_host = _pinned.empty((int(I_mask.sum()) + 2, Nj, W), pin_dev) if I_mask.any() else np.empty((2, Nj, W))
+    # a caller that passes `extras` and does not want the initial planes gets arrays WITHOUT the two leading planes
+    # (extras["lead"] = 0): 2 (Nj, W) planes less to pin and to allocate per output
+    lead = 0 if (extras is not None and not initial_planes) else 2
+    ex["lead"] = lead
+    th_host = _pinned.empty((int(th_mask.sum()) + lead, Nj, W), pin_dev) if keep_theta else np.empty((lead, Nj, W))
+    I_host = _pinned.empty((int(I_mask.sum()) + lead, Nj, W), pin_dev) if I_mask.any() else np.empty((lead, Nj, W))
     at_rest = getattr(problem, "starts_at_rest_with_zero_phases", None)
     at_rest = at_rest is not None and at_rest()          # no initial condition given: nothing is materialised for it
     if initial_planes:

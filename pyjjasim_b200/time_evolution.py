@@ -316,6 +316,7 @@ def time_evolution(problem: TimeEvolutionProblem, core=None):
         th, I = core(problem, plan.theta_mask, plan.current_mask)
 
     dt = problem._dt()
+    lead = extras.get("lead", 2) if extras is not None else 2       # the device core drops the two initial planes when unread
     V = None
     if plan.want_V:
         at = StorePlan.positions(plan.theta_mask, plan.requested)
@@ -326,17 +327,18 @@ def time_evolution(problem: TimeEvolutionProblem, core=None):
             V += (problem.circuit.get_inductance() @ dI.reshape(dI.shape[0], -1)).reshape(V.shape)
     theta = current = None
     if problem.store_theta:
-        theta = _planes(th, plan.theta_mask, plan.theta_public)
+        theta = _planes(th, plan.theta_mask, plan.theta_public, lead)
     if problem.store_current:
-        current = _planes(I, plan.current_mask, plan.current_public)
+        current = _planes(I, plan.current_mask, plan.current_public, lead)
     return TimeEvolutionResult(problem, theta, current, V if problem.store_voltage else None, observed=extras)
 
 
-def _planes(arr, kept_mask, wanted_mask):
-    """the wanted steps out of the kept planes; a plain slice (no copy) when every kept plane is wanted"""
+def _planes(arr, kept_mask, wanted_mask, lead=2):
+    """the wanted steps out of the kept planes (behind `lead` initial planes); a plain slice (no copy) when every kept
+    plane is wanted"""
     if np.array_equal(kept_mask, wanted_mask):
-        return arr[:, :, 2:]
-    return arr[:, :, StorePlan.positions(kept_mask, wanted_mask)]
+        return arr[:, :, lead:]
+    return arr[:, :, StorePlan.positions(kept_mask, wanted_mask) - (2 - lead)]
 
 
 from .result import TimeEvolutionResult                               # noqa: E402

@@ -228,3 +228,21 @@ def anneal_oracle_inputs(kw):
                                 "interval_count", "start_T", "T_factor") if k in kw}
     extra["vortex_mobility_target"] = kw.get("vortex_mobility", 0.001)
     return args, extra
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Static polish cases (reference: static_problem.py:550-610): lattice, inductance, flux, vortex configurations, bias.
+def static_cases(pkg):
+    out = {}
+    for name, ctor, args, L in (("square", "SquareArray", (9, 8), 0.05), ("honeycomb", "HoneycombArray", (4, 5), 0.0)):
+        a = getattr(pkg, ctor)(*args)
+        Nf, W = a._Nf(), 6
+        rng = np.random.RandomState(0)
+        f = 0.06 * np.ones((Nf, W))
+        n = np.zeros((Nf, W), dtype=int)
+        for w in range(1, W):
+            n[rng.choice(Nf, size=w, replace=False), w] = 1
+        n[rng.choice(Nf), 5] = -1
+        Is = a.current_base(angle=0)[:, None] * np.linspace(0, 0.2, W)[None, :]
+        out[name] = (ctor, args, L, f, n, Is)
+    return out

@@ -343,9 +343,19 @@ def test_annealing_matches_reference_golden(name, engine, golden_dir):
         prof_o, th_o, n_o = oracle.annealing(*args, noise=lambda k, s: Z[k, s], **extra)
     assert np.max(np.abs(theta - th_o)) <= 1e-7          # ~150 noisy steps; tolerance stated in SURVEY.md section 8c
     assert np.array_equal(ap.T[0, :, 0], profiles[-1])
+    # compute(): the anneal, then the reference's closing step - one stationary-state solve per annealed configuration
     status, configs, prof2 = pj.AnnealingProblem(noise_replay=Z, **kw).compute()
-    assert np.array_equal(prof2, profiles) and np.all(status == 2) and len(configs) == kw["problem_count"]
+    assert np.array_equal(prof2, profiles) and len(configs) == kw["problem_count"] and set(status) <= {0, 1, 2}
     assert np.array_equal(configs[1].get_vortex_configuration(), n[:, 1])
+    A, M = kw["circuit"].get_cycle_matrix(), kw["circuit"].get_cut_matrix()
+    assert np.any(status == 0)
+    for p in np.flatnonzero(status == 0):
+        th_p = configs[p].get_theta()                      # a stationary state carrying the annealed vortices
+        assert np.array_equal(-(A @ np.round(th_p / (2 * np.pi))).astype(int), n[:, p])
+        assert np.max(np.abs(M @ (configs[p].get_current() - np.broadcast_to(configs[p].current_sources, th_p.shape)))) < 1e-8
+        assert np.array_equal(configs[p].annealed_theta, theta[:, p])
+    st2, cf2, _ = pj.AnnealingProblem(noise_replay=Z, **kw).compute(polish=False)
+    assert np.all(st2 == 2) and np.array_equal(cf2[0].get_theta(), theta[:, 0])
 
 
 @pytest.mark.parametrize("engine", ENGINES)

@@ -301,6 +301,34 @@ def test_closed_form_amplitudes_are_recovered_from_plain_callables(monkeypatch):
     assert sources.classify_source(lambda i: base[:, None] * (IDC + np.sin(0.0125 * i))[None, :], N, W, Nt).model is None
 
 
+@pytest.mark.parametrize("name", ["square", "honeycomb"])
+def test_static_polish_matches_the_reference_static_solver(name, golden_dir):
+    # London approximation in phase zone 0 and the Newton iteration against StaticProblem.approximate() / .compute() of
+    # the unmodified reference (tests/golden/make_golden_static.py): same status, same iteration count, same phases up
+    # to integer multiples of 2 pi (any integral solution of A Z = n moves between phase zones)
+    from tests import cases
+    from pyjjasim_b200.static_polish import london_approximation, newton_stationary_states, integral_cycle_solve
+    ctor, args, L, f, n, Is = cases.static_cases(pj)[name]
+    g = np.load(os.path.join(golden_dir, f"static_{name}.npz"))
+    a = getattr(pj, ctor)(*args)
+    if L:
+        a.set_inductance(L)
+    A = a.get_cycle_matrix()
+    assert np.array_equal(A @ integral_cycle_solve(A, n), n)
+    pv = lambda x: x - 2 * np.pi * np.round(x / (2 * np.pi))
+    th0 = london_approximation(a, f, n, Is)
+    assert np.max(np.abs(pv(th0 - g["theta0"]))) < 1e-13
+    th, status, info = newton_stationary_states(a, th0, Is, f, n, pj.DefaultCPR())
+    assert np.array_equal(status, g["status"]) and np.array_equal(info["iterations"], g["iterations"])
+    ok = status == 0
+    assert ok.sum() >= 3 and (~ok).sum() >= 1
+    assert np.max(np.abs(pv(th[:, ok] - g["theta"][:, ok]))) < 1e-12
+    # a converged state is a stationary state with the requested vortices
+    I = np.sin(th[:, ok])
+    assert np.max(np.abs(a.get_cut_matrix() @ (I - Is[:, ok]))) < 1e-9
+    assert np.array_equal(-(A @ np.round(th[:, ok] / (2 * np.pi))), n[:, ok])
+
+
 def test_cpr_harmonics():
     a, b = harmonics(pj.DefaultCPR())
     assert list(a) == [0, 0] and list(b) == [0, 1]

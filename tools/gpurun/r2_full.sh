@@ -1,0 +1,12 @@
+mkdir -p gpurun_out
+timeout 1800 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/r2_pytest_full2.txt 2>&1
+tail -6 gpurun_out/r2_pytest_full2.txt | cut -c1-200
+( time timeout 900 python bench.py ) > gpurun_out/r2_bench_full2.json 2> gpurun_out/r2_bench_full2.err
+tail -4 gpurun_out/r2_bench_full2.err
+python -c "
+import json
+d=json.load(open('gpurun_out/r2_bench_full2.json'))
+print('cfg2 us/timestep %.2f  %.2f Gjs/s frac %.3f e2e %.2f G'%(d['ms_per_step']*1e3/d['config']['time_steps_per_step'], d['value']/1e9, d['roofline']['frac'], d['e2e']['value']/1e9))
+for k,v in d['per_config'].items(): print(k, {a: (round(b,3) if isinstance(b,float) else b) for a,b in v.items() if a in ('value','e2e','roofline_frac','device_us_per_time_step','setup_s','error')})
+print(d['cpu_baseline']['value'])
+"
