@@ -353,9 +353,9 @@ def test_annealing_matches_reference_golden(name, engine, golden_dir):
         th_p = configs[p].get_theta()                      # a stationary state carrying the annealed vortices
         assert np.array_equal(-(A @ np.round(th_p / (2 * np.pi))).astype(int), n[:, p])
         assert np.max(np.abs(M @ (configs[p].get_current() - np.broadcast_to(configs[p].current_sources, th_p.shape)))) < 1e-8
-        assert np.array_equal(configs[p].annealed_theta, theta[:, p])
+        assert np.max(np.abs(configs[p].annealed_theta - theta[:, p])) <= 1e-7      # (this run used the default engine)
     st2, cf2, _ = pj.AnnealingProblem(noise_replay=Z, **kw).compute(polish=False)
-    assert np.all(st2 == 2) and np.array_equal(cf2[0].get_theta(), theta[:, 0])
+    assert np.all(st2 == 2) and np.max(np.abs(cf2[0].get_theta() - theta[:, 0])) <= 1e-7
 
 
 @pytest.mark.parametrize("engine", ENGINES)
