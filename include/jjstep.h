@@ -156,7 +156,7 @@ int jj_set_problem(JJHandle *h, int32_t W, double dt, uint64_t seed, int64_t pro
 int jj_set_engine(JJHandle *h, int32_t engine);
 /* theta(-1), theta(-2): (Nj, W) host arrays (reference: time_evolution.py:480,490; config_at_minus_1/2) */
 int jj_set_state(JJHandle *h, const double *theta_m1, const double *theta_m2);
-int jj_get_state(JJHandle *h, double *theta_m1, double *theta_m2);
+int jj_get_state(JJHandle *h, double *theta_m1, double *theta_m2);   /* either output may be NULL */
 
 /* per-step inputs (reference: time_evolution.py:342-356, :524-531).
  * RANK1: value(e,w,i) = base[e] * amp[i - i0][w];  DENSE: value = table[i - i0][e][w].

@@ -424,7 +424,7 @@ __device__ __forceinline__ void next_x(const SubArgs& a, double Ic, double c1, d
 template <int NG, bool DEF>
 __device__ __forceinline__ void junction_item(const SubArgs& a, const AmpCache<8 * NG>* ac, int c, long long n, int idx,
                                               int jlo, bool do_pre, const double* __restrict__ v,
-                                              double* snap_th, double* snap_I, const double2 x0, const double2 x1,
+                                              int plane_th, int plane_I, const double2 x0, const double2 x1,
                                               const double2 t0, const double2 t1, const double2 rIc, const double2 rc,
                                               const double2 rb, const int4 ri) {
     constexpr int PC = 8 * NG, G = PC / 4;
@@ -445,16 +445,17 @@ __device__ __forceinline__ void junction_item(const SubArgs& a, const AmpCache<8
     const double th2[4] = {t0.x, t0.y, t1.x, t1.y};
     // one finiteness test for the four phases (a NaN or Inf in any of them poisons the sum)
     if (!(fabs((th1[0] + th1[1]) + (th1[2] + th1[3])) < 1.0e300)) atomicOr(a.flag, 1);
-    if (snap_th || snap_I || !do_pre) {
+    // (the snapshot planes travel as two plane numbers, -1 = none, not as two pointers: two registers less in the loop)
+    if (plane_th >= 0 || plane_I >= 0 || !do_pre) {
         const size_t cidx = (size_t)ri.z * a.Wp + w;
-        if (snap_th) {
-            double2* sp = reinterpret_cast<double2*>(snap_th + cidx);
+        if (plane_th >= 0) {
+            double2* sp = reinterpret_cast<double2*>(a.snap_th + (size_t)plane_th * a.Nj * a.Wp + cidx);
             sp[0] = make_double2(th1[0], th1[1]); sp[1] = make_double2(th1[2], th1[3]);
         }
-        if (snap_I) {
+        if (plane_I >= 0) {
             const double* am = ac->Is[(n - 1) & 1] + q;
             const double isb = __ldg(a.P1 + 4 * (size_t)(jlo + idx / G));       // (the record holds Is base / c0)
-            double2* sp = reinterpret_cast<double2*>(snap_I + cidx);
+            double2* sp = reinterpret_cast<double2*>(a.snap_I + (size_t)plane_I * a.Nj * a.Wp + cidx);
             sp[0] = make_double2(y[0] + isb * am[0], y[1] + isb * am[1]);
             sp[1] = make_double2(y[2] + isb * am[2], y[3] + isb * am[3]);
         }
@@ -510,12 +511,11 @@ __device__ void junction_pass(const SubArgs& a, const AmpCache<8 * NG>* ac, int 
         }
         return;
     }
-    double* snap_th = nullptr; double* snap_I = nullptr;
+    int plane_th = -1, plane_I = -1;
     {
         const long long k = n - 1 - a.i0;
-        const long long pt = a.th_plane ? a.th_plane[k] : -1, pi = a.I_plane ? a.I_plane[k] : -1;
-        if (pt >= 0) snap_th = a.snap_th + (size_t)pt * a.Nj * a.Wp;
-        if (pi >= 0) snap_I = a.snap_I + (size_t)pi * a.Nj * a.Wp;
+        if (a.th_plane) plane_th = (int)a.th_plane[k];
+        if (a.I_plane) plane_I = (int)a.I_plane[k];
     }
     const size_t sbase = ((size_t)c * a.Nj + jlo) * PC;
     // software pipeline: the state of the next item is in flight (registers) while this one is computed, and the
@@ -550,7 +550,7 @@ __device__ void junction_pass(const SubArgs& a, const AmpCache<8 * NG>* ac, int 
             const double2* rec = reinterpret_cast<const double2*>(a.jrec + 8 * (size_t)(jlo + (idx + NT) / G));
             nIc = __ldg(rec); nc = __ldg(rec + 1); nb = __ldg(rec + 2); ni = __ldg(reinterpret_cast<const int4*>(rec + 3));
         }
-        junction_item<NG, DEF>(a, ac, c, n, idx, jlo, do_pre, v, snap_th, snap_I, x0, x1, t0, t1, rIc, rc, rb, ri);
+        junction_item<NG, DEF>(a, ac, c, n, idx, jlo, do_pre, v, plane_th, plane_I, x0, x1, t0, t1, rIc, rc, rb, ri);
         x0 = nx0; x1 = nx1; t0 = nt0; t1 = nt1; rIc = nIc; rc = nc; rb = nb; ri = ni;
     }
 }
@@ -1391,7 +1391,7 @@ __global__ void __launch_bounds__(NT, BLOCKS_PER_SM) k_subdomain(const SubArgs a
         const long long t0 = clock64(), wait = (long long)(blockIdx.x / a.P) * a.stagger;
         while (clock64() - t0 < wait) __nanosleep(256);
     }
-    for (long long k = 0; k <= a.n; ++k) {
+    for (int k = 0; k <= a.n; ++k) {          // (a 32-bit counter: it stays live through every loop of the time step)
         const long long n = a.i0 + k;
         long long tq = prof_p ? clock64() : 0;
         const unsigned long long draw_base = (unsigned long long)k * (unsigned long long)(n_items + (int)gridDim.x);

@@ -532,8 +532,8 @@ int jj_get_state(JJHandle* h, double* t1, double* t2) {
     CK(cudaSetDevice(h->device));
     REQUIRE(h->have_problem, JJ_ESTATE, "get_state: problem not set");
     int rc;     // both engines keep theta(-1), theta(-2) in the canonical arrays between runs
-    if ((rc = d2h_padded(h, t1, h->th1, h->cir.Nj))) return rc;
-    if ((rc = d2h_padded(h, t2, h->th2, h->cir.Nj))) return rc;
+    if (t1 && (rc = d2h_padded(h, t1, h->th1, h->cir.Nj))) return rc;       // either pointer may be NULL
+    if (t2 && (rc = d2h_padded(h, t2, h->th2, h->cir.Nj))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     return JJ_OK;
 }

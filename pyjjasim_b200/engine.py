@@ -387,9 +387,11 @@ class DeviceEngine:
         ever run the subdomain kernel; the program of a large circuit takes long to build and is rarely needed)."""
         tab = self.tab
         prog = tab.program if (with_program and tab.factor is not None) else None
-        sweeps = [self._sweep_struct(prog.sweeps[name] if prog is not None else _empty_sweep())
-                  for name in ("fwd", "bwd")]
+        # (the structs hold raw pointers into these arrays: the dictionaries must outlive the call)
+        held = [prog.sweeps[name] if prog is not None else _empty_sweep() for name in ("fwd", "bwd")]
+        sweeps = [self._sweep_struct(sw) for sw in held]
         self._ck(self.lib.jj_set_solver(self.h, C.byref(sweeps[0]), C.byref(sweeps[1])))
+        del held
         self.has_streaming_program = prog is not None or tab.factor is None
 
     @staticmethod
@@ -490,9 +492,11 @@ class DeviceEngine:
         assert a.shape == (self.tab.Nj, self.W) and b.shape == (self.tab.Nj, self.W)
         self._ck(self.lib.jj_set_state(self.h, _lib.f64(a), _lib.f64(b)))
 
-    def get_state(self):
-        a = np.empty((self.tab.Nj, self.W)); b = np.empty((self.tab.Nj, self.W))
-        self._ck(self.lib.jj_get_state(self.h, _lib.f64(a), _lib.f64(b)))
+    def get_state(self, previous=True):
+        """(theta(-1), theta(-2)) of the device state; previous=False fetches theta(-1) only (-> (theta(-1), None))"""
+        a = np.empty((self.tab.Nj, self.W))
+        b = np.empty((self.tab.Nj, self.W)) if previous else None
+        self._ck(self.lib.jj_get_state(self.h, _lib.f64(a), _lib.f64(b) if previous else None))
         return a, b
 
     def set_source(self, which, kind, is_static, base=None):
@@ -1086,7 +1090,7 @@ def _anneal_shard(problem, tab, tab2, specs, dev, w0, w1, ann, adjust, out, engi
             sums = eng.vortex_mobility_sums(0, steps)
             out["T"][w0:w1] = adjust(sums, i, T)
             out["profiles"][i, w0:w1] = out["T"][w0:w1]
-        th, _ = eng.get_state()
+        th, _ = eng.get_state(previous=False)
         launches += eng.stats()["kernel_launches"]
         ok = True
     finally:
@@ -1105,7 +1109,7 @@ def _anneal_shard(problem, tab, tab2, specs, dev, w0, w1, ann, adjust, out, engi
                 eng.restart_at_rest()
             eng.run(r * steps, steps, None, None)
             total_ms += eng.stats()["step_ms"]
-        th, _ = eng.get_state()
+        th, _ = eng.get_state(previous=False)
         out["theta"][:, w0:w1] = th
         out["n"][:, w0:w1] = eng.vortex_configuration(-1)
         st = eng.stats()
