@@ -99,6 +99,8 @@ int subdomain_set_plan(JJHandle* h, const JJSubdomainPlan* plan);
 void subdomain_drop_plan(JJHandle* h);
 int subdomain_debug_solve(JJHandle* h, const double* b_d, double* J_d);
 void subdomain_get_config(JJHandle* h, int* P, int* PC);
+// implemented in jjstep.cu: enqueue steps on the stream, no wait (see jj_run)
+int run_enqueue(JJHandle* h, long long i0, int n, const long long* th_plane, const long long* I_plane);
 // implemented in jj_observe.cu
 void observe_free(JJHandle* h);
 bool observed_step(const JJHandle* h, long long step);

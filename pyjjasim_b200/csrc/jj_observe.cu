@@ -327,7 +327,9 @@ int jj_anneal(JJHandle* h, int64_t first_interval, int32_t n_intervals, int32_t 
     const int strips = (Wp + LANES - 1) / LANES;
     int slices = (c.Nf + ROWS - 1) / ROWS;
     slices = std::max(1, std::min(slices, (148 * 8 + strips - 1) / strips));
-    double ms = 0.0;
+    // the whole schedule is enqueued back to back; one wait, one timing, one non-finite check at the end
+    if ((rc = scratch(h, (size_t)Wp * sizeof(unsigned long long), (void**)&sums))) { dev_free(h, Td, tb); dev_free(h, prof, pb); return rc; }
+    if (e == cudaSuccess) e = cudaEventRecord(h->ev0, h->stream);
     rc = JJ_OK;
     for (int i = 0; i < n_intervals && rc == JJ_OK && e == cudaSuccess; ++i) {
         k_anneal_amp<<<1, 256, 0, h->stream>>>(W, Wp, Td, h->src[JJ_SRC_T].table_buf);
@@ -335,10 +337,8 @@ int jj_anneal(JJHandle* h, int64_t first_interval, int32_t n_intervals, int32_t 
         if (first_interval + i > 0)      // zero-velocity restart of every interval but the first (time_evolution.py:1169-1171)
             e = cudaMemcpyAsync(h->th2, h->th1, (size_t)c.Nj * Wp * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
         if (e != cudaSuccess) break;
-        rc = jj_run(h, (first_interval + i) * (int64_t)steps, steps, (const int64_t*)planes.data(), nullptr);
+        rc = run_enqueue(h, (first_interval + i) * (long long)steps, steps, planes.data(), nullptr);
         if (rc) break;
-        ms += h->last_ms;
-        if ((rc = scratch(h, (size_t)Wp * sizeof(unsigned long long), (void**)&sums))) break;
         e = cudaMemsetAsync(sums, 0, (size_t)Wp * sizeof(unsigned long long), h->stream);
         if (c.Nf > 0 && steps >= 2) {
             k_vortex_mobility<<<dim3(strips, slices), dim3(LANES, ROWS), 0, h->stream>>>(c, h->th_out, steps, sums);
@@ -347,14 +347,25 @@ int jj_anneal(JJHandle* h, int64_t first_interval, int32_t n_intervals, int32_t 
         k_anneal_rule<<<(W + 255) / 256, 256, 0, h->stream>>>(W, sums, norm, upper[i], T_factor, inv_T_factor, Td, prof + (size_t)i * W);
         h->launches++;
     }
+    if (rc == JJ_OK && e == cudaSuccess) e = cudaEventRecord(h->ev1, h->stream);
     if (rc == JJ_OK && e == cudaSuccess) e = cudaMemcpyAsync(T, Td, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
     if (rc == JJ_OK && e == cudaSuccess) e = cudaMemcpyAsync(profiles, prof, pb, cudaMemcpyDeviceToHost, h->stream);
+    int flag = 0;
+    if (rc == JJ_OK && e == cudaSuccess) e = cudaMemcpyAsync(&flag, h->flag_d, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
     cudaError_t e2 = cudaStreamSynchronize(h->stream);
     dev_free(h, Td, tb); dev_free(h, prof, pb);
     if (rc) return rc;
     if (e == cudaSuccess) e = e2;
     if (e != cudaSuccess) { h->err = std::string("anneal: ") + cudaGetErrorString(e); return JJ_ECUDA; }
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_ms = ms;
     if (device_ms) *device_ms = ms;
+    if (flag) {
+        h->non_finite = 1;
+        h->err = "non-finite phase encountered during time evolution";
+        return JJ_ENONFINITE;
+    }
     return JJ_OK;
 }
 

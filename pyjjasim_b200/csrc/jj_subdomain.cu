@@ -138,7 +138,7 @@ struct SubState {
     double *rth = nullptr, *rx = nullptr, *zloc = nullptr, *ctop = nullptr, *rtop = nullptr, *jtop = nullptr;
     size_t state_bytes = 0, z_bytes = 0, c_bytes = 0;
     unsigned* bar = nullptr;
-    long long* plane_d = nullptr; size_t plane_cap = 0;
+    long long* plane_d = nullptr; size_t plane_cap = 0; std::vector<long long> plane_h;   // device plane table and what it holds
     int n_chunks = 0, grid = 0;
     size_t smem_bytes = 0;
     bool prepared = false;
@@ -1618,7 +1618,7 @@ void subdomain_free_problem(JJHandle* h) {
     dev_free(h, st->bar, BAR_BYTES);
     dev_free(h, st->plane_d, st->plane_cap);
     st->rth = st->rx = st->zloc = st->ctop = st->rtop = st->jtop = st->U = nullptr; st->bar = nullptr;
-    st->plane_d = nullptr; st->plane_cap = 0; st->state_bytes = st->z_bytes = st->c_bytes = st->u_bytes = 0;
+    st->plane_d = nullptr; st->plane_cap = 0; st->plane_h.clear(); st->state_bytes = st->z_bytes = st->c_bytes = st->u_bytes = 0;
     st->prepared = false;
 }
 
@@ -1931,7 +1931,7 @@ int subdomain_run(JJHandle* h, long long i0, int n, const long long* th_plane, c
     if (need > st->plane_cap) {
         SCK(cudaStreamSynchronize(h->stream));
         dev_free(h, st->plane_d, st->plane_cap);
-        st->plane_d = nullptr; st->plane_cap = 0;
+        st->plane_d = nullptr; st->plane_cap = 0; st->plane_h.clear();
         int rc = dev_alloc(h, (void**)&st->plane_d, need);
         if (rc) return rc;
         st->plane_cap = need;
@@ -1942,8 +1942,12 @@ int subdomain_run(JJHandle* h, long long i0, int n, const long long* th_plane, c
         if (I_plane) pl[n + k] = I_plane[k];
         if (pl[k] >= h->n_th_planes || pl[n + k] >= h->n_I_planes) { h->err = "run: plane index out of range"; return JJ_EINVAL; }
     }
-    SCK(cudaMemcpyAsync(st->plane_d, pl.data(), need, cudaMemcpyHostToDevice, h->stream));
-    SCK(cudaStreamSynchronize(h->stream));     // pl goes out of scope
+    if (pl != st->plane_h) {
+        // (an annealing schedule asks for the same planes every interval: uploaded once. The host copy lives in the
+        // plan state, so nothing has to wait for the transfer.)
+        st->plane_h.swap(pl);
+        SCK(cudaMemcpyAsync(st->plane_d, st->plane_h.data(), need, cudaMemcpyHostToDevice, h->stream));
+    }
     SubArgs a;
     fill_args(h, st, a);
     a.i0 = i0; a.n = n; a.th_plane = st->plane_d; a.I_plane = st->plane_d + n;

@@ -702,11 +702,11 @@ static int streaming_run(JJHandle* h, long long i0, int n, const long long* th_p
     return JJ_OK;
 }
 
-int jj_run(JJHandle* h, int64_t i0, int32_t n, const int64_t* th_plane, const int64_t* I_plane) {
-    CK(cudaSetDevice(h->device));
-    REQUIRE(h->have_problem && h->have_state, JJ_ESTATE, "run: problem/state not set");
-    REQUIRE(n >= 0, JJ_EINVAL, "run: negative step count");
-    if (n == 0) return JJ_OK;
+}  // extern "C" (run_enqueue has C++ linkage)
+
+// Enqueue steps [i0, i0 + n) on the handle's stream without waiting for them (jj_run adds the timing events, the wait
+// and the non-finite check; jj_anneal enqueues a whole schedule of intervals back to back and waits once).
+int jj::run_enqueue(JJHandle* h, long long i0, int n, const long long* th_plane, const long long* I_plane) {
     int rc = check_sources(h, i0, n);
     if (rc) return rc;
     // engine choice
@@ -723,21 +723,33 @@ int jj_run(JJHandle* h, int64_t i0, int32_t n, const int64_t* th_plane, const in
         return JJ_EINVAL;
     }
     h->engine = want;
-    CK(cudaEventRecord(h->ev0, h->stream));
-    if (want == JJ_ENGINE_SUBDOMAIN) rc = subdomain_run(h, i0, n, (const long long*)th_plane, (const long long*)I_plane);
+    if (want == JJ_ENGINE_SUBDOMAIN) rc = subdomain_run(h, i0, n, th_plane, I_plane);
     else {
         REQUIRE(h->cir.Nf == 0 || h->fwd.n_levels > 0, JJ_ESTATE,
                 "run: the streaming engine needs a solve program (jj_set_solver was given empty sweeps)");
-        rc = streaming_run(h, i0, n, (const long long*)th_plane, (const long long*)I_plane);
+        rc = streaming_run(h, i0, n, th_plane, I_plane);
     }
+    if (rc) return rc;
+    if (want == JJ_ENGINE_SUBDOMAIN) h->obs_count += observations_in(h, i0, n);
+    h->steps_done += n;
+    return JJ_OK;
+}
+
+extern "C" {
+
+int jj_run(JJHandle* h, int64_t i0, int32_t n, const int64_t* th_plane, const int64_t* I_plane) {
+    CK(cudaSetDevice(h->device));
+    REQUIRE(h->have_problem && h->have_state, JJ_ESTATE, "run: problem/state not set");
+    REQUIRE(n >= 0, JJ_EINVAL, "run: negative step count");
+    if (n == 0) return JJ_OK;
+    CK(cudaEventRecord(h->ev0, h->stream));
+    int rc = run_enqueue(h, i0, n, (const long long*)th_plane, (const long long*)I_plane);
     if (rc) return rc;
     CK(cudaEventRecord(h->ev1, h->stream));
     CK(cudaEventSynchronize(h->ev1));
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->last_ms = ms;
-    if (want == JJ_ENGINE_SUBDOMAIN) h->obs_count += observations_in(h, i0, n);
-    h->steps_done += n;
     int flag = 0;
     CK(cudaMemcpy(&flag, h->flag_d, sizeof(int), cudaMemcpyDeviceToHost));
     if (flag) {
