@@ -55,8 +55,8 @@ class _PinnedPool:
     """Result planes in page-locked memory (device -> host at PCIe speed, no page faults on fresh numpy pages). Blocks
     are reused across compute() calls of the same result size; pinning is slow, so only a few sizes are kept."""
 
-    # JJ_PINNED_MAX_GB (default 16): page-locked memory in use + cached; results beyond that are ordinary numpy arrays
-    MAX_PINNED = int(float(os.environ.get("JJ_PINNED_MAX_GB", "16")) * (1 << 30))
+    # JJ_PINNED_MAX_GB (default 8): page-locked memory in use + cached; results beyond that are ordinary numpy arrays
+    MAX_PINNED = int(float(os.environ.get("JJ_PINNED_MAX_GB", "8")) * (1 << 30))
     MAX_BLOCK = MAX_PINNED // 2
     MAX_CACHED = MAX_PINNED // 2
 
