@@ -577,7 +577,10 @@ def subdomain_plan(F, junc_face, d, NG, n_warps=RES_WARPS, groups=None, tt_max=N
     n, nb = F.n, F.nb
     PC = 8 * NG
     if tt_max is None:
-        tt_max = int(os.environ.get("JJ_TT_MAX", "1024"))
+        # measured on B200: 1024 for wide batches (cfg3 / cfg4 at 512 problems lose 3 % at 2048 and 25 % at 4096: the dense
+        # product costs n_tt^2 per problem), 4096 for narrow ones (cfg5 at 64 problems gains 4 %: the inverse streams from
+        # HBM once per step whatever the width, and replaces the most serial upper phases)
+        tt_max = int(os.environ.get("JJ_TT_MAX", "4096" if n_chunks * 8 * NG <= 128 else "1024"))
     sizes = np.diff(F.bptr)
     blk_of = np.repeat(np.arange(nb), sizes)
     if d is None:
