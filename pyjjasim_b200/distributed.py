@@ -68,7 +68,7 @@ def compute_sharded(problem, device=None, group=None, core=None):
     if device is None:
         device = int(os.environ.get("LOCAL_RANK", "0"))
 
-    def sharded_core(prob, th_mask, I_mask):
+    def sharded_core(prob, th_mask, I_mask, extras=None):
         if core is not None:
             th, I = core(prob, th_mask, I_mask, w0, w1)
         else:
@@ -76,11 +76,24 @@ def compute_sharded(problem, device=None, group=None, core=None):
             # one Philox seed for the whole job: rank 0 resolves it (explicit noise_seed, or a fresh draw), all use it
             box = [resolve_noise_seed(prob) if rank == 0 else None]
             dist.broadcast_object_list(box, src=0, group=group)
-            th, I = device_time_evolution_core(prob, th_mask, I_mask, shard=(w0, w1), device=device, noise_seed=box[0])
+            th, I = device_time_evolution_core(prob, th_mask, I_mask, shard=(w0, w1), device=device, noise_seed=box[0],
+                                               initial_planes=True if extras is None else bool(extras.get("initial_planes", True)),
+                                               extras=extras)
         global last_gather_seconds
         t0 = time.perf_counter()
         out = gather_problem_axis(th, W, group), gather_problem_axis(I, W, group)
+        if extras is not None:
+            # what the device produced beside the planes, gathered along the problem axis as well (every rank filled
+            # the columns of its shard): vortex sums and phase marks of the running observables, device-side vortex planes
+            for key in ("nsum", "theta_first", "theta_latest"):
+                if key in extras:
+                    full = gather_problem_axis(np.asarray(extras[key][:, w0:w1, None], dtype=np.double), W, group)[:, :, 0]
+                    extras[key] = full.astype(extras[key].dtype)
+            if extras.get("n_planes") is not None:
+                loc = np.moveaxis(extras["n_planes"][:, :, w0:w1], 0, 2).astype(np.double)        # (Nf, w, K)
+                extras["n_planes"] = np.moveaxis(gather_problem_axis(loc, W, group), 2, 0).astype(np.int32)
         last_gather_seconds = time.perf_counter() - t0
         return out
 
+    sharded_core.accepts_extras = core is None
     return _time_evolution(problem, core=sharded_core)

@@ -304,15 +304,23 @@ def time_evolution(problem: TimeEvolutionProblem, core=None):
     """
     plan = StorePlan(problem)
     extras = None
-    if core is None:
-        from .engine import device_time_evolution_core
+    wants_extras = bool(getattr(problem, "observe_interval", 0)) or bool(getattr(problem, "store_vortex_configuration", False))
+    if core is None or getattr(core, "accepts_extras", False):
         extras = dict(interval=getattr(problem, "observe_interval", 0), first=getattr(problem, "observe_first", 0),
                       vortex_planes=bool(getattr(problem, "store_vortex_configuration", False)),
                       fetch_theta=plan.fetch_theta, wanted=plan.requested)
+    if core is None:
+        from .engine import device_time_evolution_core
         # the initial-condition planes are only read by the voltage difference of step 0
         th, I = device_time_evolution_core(problem, plan.theta_mask, plan.current_mask,
                                            initial_planes=plan.want_V, extras=extras)
+    elif extras is not None:
+        extras["initial_planes"] = plan.want_V
+        th, I = core(problem, plan.theta_mask, plan.current_mask, extras=extras)
     else:
+        if wants_extras:
+            raise NotImplementedError("running observables and device-side vortex planes need the device core; the core "
+                                      "passed to time_evolution() does not produce them")
         th, I = core(problem, plan.theta_mask, plan.current_mask)
 
     dt = problem._dt()

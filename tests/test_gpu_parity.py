@@ -709,6 +709,27 @@ def test_full_size_cfg2_per_step_against_oracle_with_reference_draws():
     assert np.max(np.abs(res.theta - th)) <= 1e-8
 
 
+def test_running_observables_and_vortex_planes_shard_over_devices():
+    # host threads, one per GPU, fill the columns of their shards (needs two devices)
+    import ctypes
+    from pyjjasim_b200 import _lib
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    if lib.jj_create(1, ctypes.byref(h)) != 0:
+        pytest.skip("needs two CUDA devices")
+    lib.jj_destroy(h)
+    a = pj.SquareArray(13, 11)
+    W, Nt, first, k = 24, 60, 4, 5
+    kw, base, amps = _observer_case(a, W, Nt)
+    one = pj.TimeEvolutionProblem(observe_interval=k, observe_first=first, store_vortex_configuration=True,
+                                  store_time_steps=[10, 59], **kw).compute()
+    two = pj.TimeEvolutionProblem(observe_interval=k, observe_first=first, store_vortex_configuration=True,
+                                  store_time_steps=[10, 59], devices=[0, 1], **kw).compute()
+    assert np.array_equal(one.get_vortex_sum(), two.get_vortex_sum())
+    assert np.array_equal(one.get_vortex_configuration(), two.get_vortex_configuration())
+    assert np.max(np.abs(one.get_dc_voltage() - two.get_dc_voltage())) <= 1e-9
+
+
 def test_annealing_shards_over_devices():
     # two GPUs: problems never interact and the temperatures are per problem, so the sharded schedule equals the
     # single-device one exactly
