@@ -5,7 +5,10 @@
 set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xptxas -v $JJ_NVCC_EXTRA"
+# --register-usage-level=2: ptxas holds back the optimisations that trade registers for speed; the step kernel lives at
+# its 128-register cap, and this takes the lean kernel from 112 to 12 bytes of spills (cfg2 +0.2 %, cfg3 +1.1 %, cfg4
+# +1.6 %, measured A/B on one B200, profiles/r02_experiments.md)
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xptxas -v -Xptxas --register-usage-level=2 $JJ_NVCC_EXTRA"
 mkdir -p obj
 pids=()
 names=()
