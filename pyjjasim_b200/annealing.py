@@ -35,39 +35,46 @@ class AnnealingProblem:
                  external_flux=0.0, current_sources=0, problem_count=1,
                  interval_count=1000, vortex_mobility=0.001,
                  start_T=1.0, T_factor=1.03, *, noise_seed=None, noise_replay=None, devices=None):
-        self.circuit = circuit
-        self.time_step = time_step
-        self.interval_steps = interval_steps
-        self.interval_count = interval_count
-        self.vortex_mobility = vortex_mobility
-        self.current_sources = current_sources
-        self.external_flux = external_flux
-        self.problem_count = problem_count
-        self.T = start_T * np.ones((1, self.problem_count, 1))
-        self.T_factor = T_factor
-        self.noise_seed, self.noise_replay, self.devices = noise_seed, noise_replay, devices
+        settings = dict(circuit=circuit, time_step=time_step, interval_steps=interval_steps, external_flux=external_flux,
+                        current_sources=current_sources, problem_count=problem_count, interval_count=interval_count,
+                        vortex_mobility=vortex_mobility, T_factor=T_factor, noise_seed=noise_seed,
+                        noise_replay=noise_replay, devices=devices)
+        for name, value in settings.items():
+            setattr(self, name, value)
+        self.T = np.full((1, problem_count, 1), float(start_T))        # one temperature per problem, (1, W, 1) like the reference's
+
+    def mobility_targets(self):
+        """(interval_count,) mobility target of every interval: vortex_mobility[i] when one value per interval is given,
+        else vortex_mobility ((N - i) / N)^1.5 (reference: time_evolution.py:1136-1138)"""
+        N, v = self.interval_count, self.vortex_mobility
+        if np.array(v).size == N:
+            return np.array([float(v[i]) for i in range(N)])
+        return np.array([float(v * ((N - i) / N) ** 1.5) for i in range(N)])
+
+    def mobility_norm(self):
+        """what the integer mobility sums are divided by: Nf dt (interval_count - 1) (reference: time_evolution.py:1133)"""
+        return self.circuit.face_count() * self.time_step * (self.interval_count - 1)
 
     def get_vortex_mobility(self, n):
-        """Vortex mobility of consecutive vortex configurations n (Nf, W, K) (reference: time_evolution.py:1128-1133)."""
-        Nf = self.circuit.face_count()
-        return np.sum(np.sum(np.abs(np.diff(n, axis=2)), axis=2), axis=0) / (Nf * self.time_step * (self.interval_count - 1))
+        """Vortex mobility of consecutive vortex configurations n (Nf, W, K): the number of vortex moves per face and
+        unit time (reference: time_evolution.py:1128-1133)."""
+        moves = np.abs(n[:, :, 1:] - n[:, :, :-1]).sum(axis=2).sum(axis=0)
+        return moves / self.mobility_norm()
 
     def _temperature_adjustment(self, vortex_mobility, iteration):
-        # reference: time_evolution.py:1135-1140
-        v = self.vortex_mobility
-        upper = v[iteration] if (np.array(v)).size == self.interval_count else \
-            v * ((self.interval_count - iteration) / self.interval_count) ** 1.5
-        factor = (vortex_mobility > upper) * (1 / self.T_factor) + (vortex_mobility <= upper) * self.T_factor
-        self.T *= factor[..., None]
+        """T /= T_factor for the problems whose mobility exceeds this interval's target, T *= T_factor for the others
+        (reference: time_evolution.py:1135-1140)"""
+        too_mobile = vortex_mobility > self.mobility_targets()[iteration]
+        self.T *= np.where(too_mobile, 1 / self.T_factor, self.T_factor)[..., None]
 
     def _problem(self):
         # the problem the reference's loop re-runs (reference: time_evolution.py:1159-1162); constructing it validates
         # the inputs exactly as the reference does
-        f = np.atleast_1d(self.external_flux)[:, None, None]
         from .time_evolution import TimeEvolutionProblem
-        return TimeEvolutionProblem(self.circuit, time_step_count=self.interval_steps, time_step=self.time_step,
-                                    external_flux=f, current_sources=self.current_sources, temperature=self.T,
-                                    store_current=False, store_voltage=False, stencil_width=3,
+        return TimeEvolutionProblem(self.circuit, time_step=self.time_step, time_step_count=self.interval_steps,
+                                    external_flux=np.atleast_1d(self.external_flux)[:, None, None],
+                                    current_sources=self.current_sources, temperature=self.T, stencil_width=3,
+                                    store_current=False, store_voltage=False,
                                     noise_seed=self.noise_seed, noise_replay=self.noise_replay, devices=self.devices)
 
     def anneal(self):
@@ -82,19 +89,15 @@ class AnnealingProblem:
         """
         from .engine import device_annealing
         prob = self._problem()
-        Nf, dt, N = self.circuit.face_count(), self.time_step, self.interval_count
-        v, T_factor = self.vortex_mobility, self.T_factor
+        N, T_factor = self.interval_count, self.T_factor
+        targets, norm = self.mobility_targets(), self.mobility_norm()
 
         def adjust(sums, i, T):
-            # get_vortex_mobility + _temperature_adjustment on the exact integer sums of interval i
-            mob = sums / (Nf * dt * (N - 1))
-            upper = v[i] if (np.array(v)).size == N else v * ((N - i) / N) ** 1.5
-            factor = (mob > upper) * (1 / T_factor) + (mob <= upper) * T_factor
-            return T * factor
+            # the rule of _temperature_adjustment on the exact integer sums of interval i (host path: replayed noise)
+            return T * np.where(sums / norm > targets[i], 1 / T_factor, T_factor)
 
-        # the same rule as data, for the device-side schedule
-        upper_all = np.array([float(v[i]) if (np.array(v)).size == N else float(v * ((N - i) / N) ** 1.5) for i in range(N)])
-        rule = dict(upper=upper_all, T_factor=float(T_factor), norm=float(Nf * dt * (N - 1))) if N > 1 else None
+        # the same rule as data, for the device-side schedule (jj_anneal)
+        rule = dict(upper=targets, T_factor=float(T_factor), norm=float(norm)) if N > 1 else None
         out = device_annealing(prob, self.T[0, :, 0], adjust, N, rule=rule)
         self.T[0, :, 0] = out["T"]
         self.last_stats = out["stats"]
