@@ -207,7 +207,8 @@ int jj_anneal(JJHandle *h, int64_t first_interval, int32_t n_intervals, int32_t 
 /* all stored theta planes [plane0, plane0 + n_planes) at once: dst is (n_planes, Nf, W) int32, permuted faces. With it the
  * vortex configurations of the stored steps leave the device as integers and the theta planes never have to
  * (reference: time_evolution.py:734-755 evaluated on host copies of theta) */
-int jj_vortex_configurations(JJHandle *h, int64_t plane0, int64_t n_planes, int32_t *dst);
+int jj_vortex_configurations(JJHandle *h, int64_t plane0, int64_t n_planes, int32_t *dst,
+                             const int32_t *face_order /* [Nf] output row of each permuted face, or NULL: permuted order */);
 
 /* ---- running observables: accumulated on the device WHILE stepping, no theta plane stored or copied ----
  * Steps first_step + m * interval (m = 0, 1, ...) are OBSERVATIONS. At every observation the step kernel itself adds
@@ -219,8 +220,9 @@ int jj_vortex_configurations(JJHandle *h, int64_t plane0, int64_t n_planes, int3
  * The accumulators belong to the problem: they survive chunked jj_run calls and are cleared by jj_observe_begin
  * (interval = 0 switches observation off). first_step must not lie before the steps already run. */
 int jj_observe_begin(JJHandle *h, int64_t first_step, int32_t interval);
-/* count = observations so far; nsum (Nf, W) int32, permuted faces; theta_first / theta_latest (Nj, W); any pointer may be NULL */
-int jj_observe_fetch(JJHandle *h, int64_t *count, int32_t *nsum, double *theta_first, double *theta_latest);
+/* count = observations so far; nsum (Nf, W) int32; theta_first / theta_latest (Nj, W); any pointer may be NULL */
+int jj_observe_fetch(JJHandle *h, int64_t *count, int32_t *nsum, double *theta_first, double *theta_latest,
+                     const int32_t *face_order /* as for jj_vortex_configurations */);
 
 /* Page-locked host memory for result planes: jj_fetch_* into such a buffer is a single DMA at PCIe speed instead of
  * a staged copy into pageable memory. The Python wrapper pools these blocks and hands them out as numpy arrays. */

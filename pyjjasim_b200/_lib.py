@@ -112,11 +112,11 @@ def load():
     lib.jj_restart_at_rest.argtypes = [_p]
     lib.jj_vortex_configuration.argtypes = [_p, C.c_int64, _i32p]
     lib.jj_vortex_mobility.argtypes = [_p, C.c_int64, C.c_int64, _i64p]
-    lib.jj_vortex_configurations.argtypes = [_p, C.c_int64, C.c_int64, _i32p]
+    lib.jj_vortex_configurations.argtypes = [_p, C.c_int64, C.c_int64, _i32p, _i32p]
     lib.jj_anneal.argtypes = [_p, C.c_int64, C.c_int32, C.c_int32, _f64p, C.c_double, C.c_double, C.c_double, _f64p, _f64p,
                               C.POINTER(C.c_double)]
     lib.jj_observe_begin.argtypes = [_p, C.c_int64, C.c_int32]
-    lib.jj_observe_fetch.argtypes = [_p, C.POINTER(C.c_int64), _i32p, _f64p, _f64p]
+    lib.jj_observe_fetch.argtypes = [_p, C.POINTER(C.c_int64), _i32p, _f64p, _f64p, _i32p]
     lib.jj_host_alloc.argtypes = [C.c_int, C.c_uint64, C.POINTER(_p)]
     lib.jj_host_free.argtypes = [_p]
     for name in EXPORTS:

@@ -48,12 +48,22 @@ __device__ __forceinline__ int vorticity(const FaceView& c, const double* __rest
     return (int)acc;
 }
 
+// dst_row: row of each (permuted) face in the output, or null for the permuted order itself - callers that want the
+// circuit's own face numbering get it from the device instead of permuting hundreds of MB on the host
 __global__ void __launch_bounds__(LANES * ROWS) k_vortex_configuration(const FaceView c, const double* __restrict__ plane,
-                                                                        int* __restrict__ out) {
+                                                                        int* __restrict__ out, const int* __restrict__ dst_row) {
     const int w = blockIdx.x * LANES + threadIdx.x;
     const int f = blockIdx.y * ROWS + threadIdx.y;
     if (w >= c.Wp || f >= c.Nf) return;
-    out[(size_t)f * c.Wp + w] = vorticity(c, plane, c.face_ptr[f], c.face_ptr[f + 1], w);
+    const int row = dst_row ? dst_row[f] : f;
+    out[(size_t)row * c.Wp + w] = vorticity(c, plane, c.face_ptr[f], c.face_ptr[f + 1], w);
+}
+
+__global__ void k_permute_rows_i32(int Nf, int Wp, const int* __restrict__ src, int* __restrict__ dst, const int* __restrict__ dst_row) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)Nf * Wp) return;
+    const int f = (int)(idx / Wp), w = (int)(idx % Wp);
+    dst[(size_t)dst_row[f] * Wp + w] = src[idx];
 }
 
 // out[w] += sum over this block's faces and over consecutive planes of |n(t+1) - n(t)|
@@ -207,36 +217,55 @@ int jj_observe_begin(JJHandle* h, int64_t first_step, int32_t interval) {
     return JJ_OK;
 }
 
-int jj_observe_fetch(JJHandle* h, int64_t* count, int32_t* nsum, double* theta_first, double* theta_latest) {
+int jj_observe_fetch(JJHandle* h, int64_t* count, int32_t* nsum, double* theta_first, double* theta_latest,
+                     const int32_t* face_order) {
     CK(cudaSetDevice(h->device));
     REQUIRE(h->have_problem && h->obs_interval > 0, JJ_ESTATE, "observe_fetch: no observation in progress");
     if (count) *count = h->obs_count;
     const size_t wi = (size_t)h->W * sizeof(int), wpi = (size_t)h->Wp * sizeof(int);
     const size_t wd = (size_t)h->W * sizeof(double), wpd = (size_t)h->Wp * sizeof(double);
-    if (nsum && h->cir.Nf > 0) CK(cudaMemcpy2DAsync(nsum, wi, h->obs_nsum, wpi, wi, h->cir.Nf, cudaMemcpyDeviceToHost, h->stream));
+    if (nsum && h->cir.Nf > 0) {
+        const int* src = h->obs_nsum;
+        if (face_order) {
+            int* buf = nullptr;
+            const size_t pe = (size_t)h->cir.Nf * h->Wp;
+            int rc = scratch(h, (pe + (size_t)h->cir.Nf) * sizeof(int), (void**)&buf);
+            if (rc) return rc;
+            CK(cudaMemcpyAsync(buf + pe, face_order, (size_t)h->cir.Nf * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+            k_permute_rows_i32<<<(unsigned)((pe + 255) / 256), 256, 0, h->stream>>>(h->cir.Nf, h->Wp, h->obs_nsum, buf, buf + pe);
+            h->launches++;
+            src = buf;
+        }
+        CK(cudaMemcpy2DAsync(nsum, wi, src, wpi, wi, h->cir.Nf, cudaMemcpyDeviceToHost, h->stream));
+    }
     if (theta_first) CK(cudaMemcpy2DAsync(theta_first, wd, h->obs_th_first, wpd, wd, h->cir.Nj, cudaMemcpyDeviceToHost, h->stream));
     if (theta_latest) CK(cudaMemcpy2DAsync(theta_latest, wd, h->obs_th_last, wpd, wd, h->cir.Nj, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return JJ_OK;
 }
 
-int jj_vortex_configurations(JJHandle* h, int64_t plane0, int64_t n_planes, int32_t* dst) {
+int jj_vortex_configurations(JJHandle* h, int64_t plane0, int64_t n_planes, int32_t* dst, const int32_t* face_order) {
     CK(cudaSetDevice(h->device));
     REQUIRE(h->have_problem, JJ_ESTATE, "vortex_configurations: problem not set");
     REQUIRE(plane0 >= 0 && n_planes >= 0 && plane0 + n_planes <= h->n_th_planes, JJ_EINVAL,
             "vortex_configurations: theta plane range out of bounds");
     if (h->cir.Nf == 0 || n_planes == 0) return JJ_OK;
     const FaceView c = view(h);
-    // two scratch planes: the kernel of plane p + 1 runs while plane p is copied out
+    // two scratch planes: the kernel of plane p + 1 runs while plane p is copied out (+ the output order of the faces)
     int* buf = nullptr;
     const size_t pe = (size_t)c.Nf * c.Wp;
-    int rc = scratch(h, 2 * pe * sizeof(int), (void**)&buf);
+    int rc = scratch(h, (2 * pe + (size_t)c.Nf) * sizeof(int), (void**)&buf);
     if (rc) return rc;
+    int* order_d = nullptr;
+    if (face_order) {
+        order_d = buf + 2 * pe;
+        CK(cudaMemcpyAsync(order_d, face_order, (size_t)c.Nf * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    }
     dim3 grid((c.Wp + LANES - 1) / LANES, (c.Nf + ROWS - 1) / ROWS), block(LANES, ROWS);
     const size_t wi = (size_t)h->W * sizeof(int), wpi = (size_t)c.Wp * sizeof(int);
     for (int64_t p = 0; p < n_planes; ++p) {
         int* b = buf + (size_t)(p & 1) * pe;
-        k_vortex_configuration<<<grid, block, 0, h->stream>>>(c, h->th_out + (size_t)(plane0 + p) * c.Nj * c.Wp, b);
+        k_vortex_configuration<<<grid, block, 0, h->stream>>>(c, h->th_out + (size_t)(plane0 + p) * c.Nj * c.Wp, b, order_d);
         h->launches++;
         CK(cudaMemcpy2DAsync(dst + (size_t)p * c.Nf * h->W, wi, b, wpi, wi, c.Nf, cudaMemcpyDeviceToHost, h->stream));
     }
@@ -265,7 +294,7 @@ int jj_vortex_configuration(JJHandle* h, int64_t plane, int32_t* dst) {
     int rc = scratch(h, bytes, (void**)&buf);
     if (rc) return rc;
     dim3 grid((c.Wp + LANES - 1) / LANES, (c.Nf + ROWS - 1) / ROWS), block(LANES, ROWS);
-    k_vortex_configuration<<<grid, block, 0, h->stream>>>(c, src, buf);
+    k_vortex_configuration<<<grid, block, 0, h->stream>>>(c, src, buf, nullptr);
     h->launches++;
     cudaError_t e = cudaMemcpy2DAsync(dst, (size_t)h->W * sizeof(int), buf, (size_t)c.Wp * sizeof(int),
                                       (size_t)h->W * sizeof(int), c.Nf, cudaMemcpyDeviceToHost, h->stream);

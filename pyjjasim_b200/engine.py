@@ -97,6 +97,12 @@ class _PinnedPool:
 _pinned = _PinnedPool()
 
 
+def _pinned_i32(shape, device=0):
+    """int32 array of this shape in a pooled page-locked block (the pool hands out float64 blocks)"""
+    n = int(np.prod(shape))
+    return _pinned.empty(((n + 1) // 2,), device).view(np.int32)[:n].reshape(shape)
+
+
 class CircuitTables:
     """
     Everything the device needs that depends only on (circuit, dt): coefficient vectors
@@ -575,12 +581,13 @@ class DeviceEngine:
     def vortex_configurations(self, plane0, n_planes):
         """n of the stored theta planes [plane0, plane0 + n_planes) in one call: (n_planes, Nf, W) int32, ORIGINAL face
         numbering; the theta planes themselves stay on the device."""
-        out = np.zeros((int(n_planes), self.tab.Nf, self.W), dtype=np.int32)
+        out = _pinned_i32((int(n_planes), self.tab.Nf, self.W), self.device)
         if n_planes and self.tab.Nf:
-            self._ck(self.lib.jj_vortex_configurations(self.h, int(plane0), int(n_planes), _lib.i32(out)))
-        n = np.empty_like(out)
-        n[:, self.tab.perm] = out
-        return n
+            order = np.ascontiguousarray(self.tab.perm, dtype=np.int32)     # permuted face p is face perm[p] of the circuit
+            self._ck(self.lib.jj_vortex_configurations(self.h, int(plane0), int(n_planes), _lib.i32(out), _lib.i32(order)))
+        else:
+            out[...] = 0
+        return out
 
     def observe_begin(self, first_step, interval):
         """Running observables: every ``interval``-th step from ``first_step`` on, the step kernel adds the vortex
@@ -591,14 +598,15 @@ class DeviceEngine:
     def observe_fetch(self, marks=True):
         """-> (count, nsum (Nf, W) int32 in the ORIGINAL face numbering, theta_first, theta_latest ((Nj, W) or None))"""
         cnt = C.c_int64(0)
-        ns = np.zeros((self.tab.Nf, self.W), dtype=np.int32)
-        t0 = np.empty((self.tab.Nj, self.W)) if marks else None
-        t1 = np.empty((self.tab.Nj, self.W)) if marks else None
+        ns = _pinned_i32((self.tab.Nf, self.W), self.device)
+        if self.tab.Nf == 0:
+            ns[...] = 0
+        t0 = _pinned.empty((self.tab.Nj, self.W), self.device) if marks else None
+        t1 = _pinned.empty((self.tab.Nj, self.W), self.device) if marks else None
+        order = np.ascontiguousarray(self.tab.perm, dtype=np.int32)
         self._ck(self.lib.jj_observe_fetch(self.h, C.byref(cnt), _lib.i32(ns), _lib.f64(t0) if marks else None,
-                                           _lib.f64(t1) if marks else None))
-        n = np.empty_like(ns)
-        n[self.tab.perm] = ns
-        return int(cnt.value), n, t0, t1
+                                           _lib.f64(t1) if marks else None, _lib.i32(order)))
+        return int(cnt.value), ns, t0, t1
 
     def anneal(self, first_interval, n_intervals, steps, upper, T_factor, norm, T):
         """The temperature schedule of n_intervals intervals on the device (jj_anneal): -> (T after the last interval,
@@ -892,9 +900,13 @@ def _run_shard(problem, tab, specs, dev, w0, w1, th_mask, I_mask, th_host, I_hos
         if ex.get("interval"):
             cnt, nsum, t_first, t_last = eng.observe_fetch()
             ex["count"] = cnt
-            ex["nsum"][:, w0:w1] = nsum
-            ex["theta_first"][:, w0:w1] = t_first
-            ex["theta_latest"][:, w0:w1] = t_last
+            if w0 == 0 and w1 == ex["nsum"].shape[1]:
+                # one shard holds every problem: hand the fetched (page-locked) arrays over as they are
+                ex["nsum"], ex["theta_first"], ex["theta_latest"] = nsum, t_first, t_last
+            else:
+                ex["nsum"][:, w0:w1] = nsum
+                ex["theta_first"][:, w0:w1] = t_first
+                ex["theta_latest"][:, w0:w1] = t_last
             eng.observe_begin(0, 0)
         st = eng.stats()
         st["total_ms"] = total_ms
@@ -962,8 +974,10 @@ def device_time_evolution_core(problem, th_store_mask, I_store_mask, engine=None
     pin_dev = devices[0] if device is None else device
     ex = extras if extras is not None else {}
     if ex.get("interval"):
+        single = len(devices) == 1 and shard is None
         ex["nsum"] = np.zeros((tab.Nf, W), dtype=np.int32)
-        ex["theta_first"], ex["theta_latest"], ex["count"] = np.zeros((Nj, W)), np.zeros((Nj, W)), 0
+        # (np.zeros pages are only touched when several shards fill their columns)
+        ex["theta_first"], ex["theta_latest"], ex["count"] = (None, None, 0) if single else (np.zeros((Nj, W)), np.zeros((Nj, W)), 0)
     if ex.get("vortex_planes"):
         ex["wanted"] = np.asarray(ex.get("wanted", th_mask), dtype=bool) & th_mask
         ex["n_planes"] = np.zeros((int(ex["wanted"].sum()), tab.Nf, W), dtype=np.int32)
