@@ -67,14 +67,27 @@ class _PinnedPool:
         nbytes = int(np.prod(shape)) * 8
         if os.environ.get("JJ_PINNED_RESULTS", "1") == "0" or nbytes == 0 or nbytes > self.MAX_BLOCK:
             return np.empty(shape)
+        evict = []
         with self._lock:
             lst = self._free.get(nbytes)
             ptr = lst.pop() if lst else None
             if ptr is not None:
                 self._cached -= nbytes
-            elif self._in_use + self._cached + nbytes > self.MAX_PINNED:
-                return np.empty(shape)
-            self._in_use += nbytes
+            else:
+                # no cached block of this size: cached blocks of other sizes give way before the result falls back to
+                # pageable memory (a different problem size after a few others used to do that, at a fifth of the speed)
+                for size in sorted(self._free, reverse=True):
+                    while self._free[size] and self._in_use + self._cached + nbytes > self.MAX_PINNED:
+                        evict.append(self._free[size].pop())
+                        self._cached -= size
+                if self._in_use + self._cached + nbytes > self.MAX_PINNED:
+                    ptr = False
+            if ptr is not False:
+                self._in_use += nbytes
+        for old in evict:
+            _lib.load().jj_host_free(C.c_void_p(old))
+        if ptr is False:
+            return np.empty(shape)
         if ptr is None:
             out = C.c_void_p()
             if _lib.load().jj_host_alloc(int(device), nbytes, C.byref(out)) != 0 or not out.value:
@@ -128,9 +141,10 @@ class CircuitTables:
         self.n_parts = n_parts
         if leaf_size is None:
             # the subdomain engine applies explicit inverses of level groups: larger leaves give it fewer, fatter
-            # tiles and better balanced items (measured on cfg2: 24 beats 8 by 4 %, 32 - the largest block a single
-            # warp applies in place - beats 24 by another 2 %; 40 is 25 % slower; cfg1 / cfg3 / cfg4 do not care)
-            leaf_size = int(os.environ.get("JJ_LEAF_SIZE", "32" if n_parts is not None else "8"))
+            # tiles (8 is 4 % slower on cfg2, 36 and more 25 % slower: blocks beyond the 32 rows a single warp applies in
+            # place). Re-measured on the round-2 kernel (profiles/r02_experiments.md): 16 beats the 32 of round 1 on
+            # every named configuration (cfg2 88.8 vs 90.7 us per time step, cfg3 2300 vs 2326, cfg4 1490 vs 1526)
+            leaf_size = int(os.environ.get("JJ_LEAF_SIZE", "16" if n_parts is not None else "8"))
         if Nf > 0:
             S = system_matrix(A, circuit._L(), self.Rv, self.Cv)
             if hasattr(circuit, "get_face_centroids"):
