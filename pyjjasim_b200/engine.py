@@ -172,10 +172,12 @@ class CircuitTables:
             self._program = streaming_program(self.factor)
         return self._program
 
-    def _balance_parts(self, A, S, cx, cy, leaf_size, n_parts, F, rounds=2):
+    def _balance_parts(self, A, S, cx, cy, leaf_size, n_parts, F, rounds=None):
         """Re-run the dissection with part weights so that the WORK of the subdomains (sweep stream steps, junctions,
         rows; per-unit costs measured on B200) is even: every thread block waits for the slowest one at the grid
         barrier of each time step."""
+        if rounds is None:
+            rounds = int(os.environ.get("JJ_BAL_ROUNDS", "2"))
         weights = np.ones(n_parts)
         best, best_spread = F, None
         if A.shape[0] > 30000:
@@ -191,7 +193,8 @@ class CircuitTables:
                 # streaming engine will run this circuit
                 return best
             steps = np.array([p["n_steps"] for p in plan.prog], dtype=np.double)
-            cost = 41.0 * steps + 52.0 * np.diff(plan.junc_ptr) + 42.0 * (plan.n_loc + plan.n_halo)
+            w_steps, w_junc, w_rows = (float(x) for x in os.environ.get("JJ_BAL_W", "41,52,42").split(","))
+            cost = w_steps * steps + w_junc * np.diff(plan.junc_ptr) + w_rows * (plan.n_loc + plan.n_halo)
             spread = float(cost.max() / cost.mean())
             if best_spread is None or spread < best_spread:
                 best, best_spread = F, spread
