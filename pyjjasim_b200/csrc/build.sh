@@ -22,6 +22,7 @@ run jj_observe jj_observe.cu
 run jj_subdomain jj_subdomain.cu
 for ng in 1 2 4 8; do run jj_subdomain_ng$ng -DJJ_SUB_NG=$ng jj_subdomain.cu; done
 for ng in 1 2 4; do run jj_subdomain_h_ng$ng -DJJ_SUB_NG=$ng -DJJ_SUB_NT=256 jj_subdomain.cu; done
+for ng in 1 2 4 8; do run jj_subdomain_m_ng$ng -DJJ_SUB_NG=$ng -DJJ_SUB_MOB=1 jj_subdomain.cu; done
 fail=0
 for i in "${!pids[@]}"; do
     if ! wait ${pids[$i]}; then echo "== ${names[$i]} failed"; cat obj/${names[$i]}.log; fail=1; fi

@@ -80,6 +80,8 @@ struct JJHandle {
     int *obs_nsum = nullptr;                                  // [Nf][Wp] permuted faces
     double *obs_th_first = nullptr, *obs_th_last = nullptr;   // canonical [Nj][Wp]
     size_t obs_n_bytes = 0, obs_th_bytes = 0;
+    // annealing (jj_anneal): the subdomain engine stores phase zones (one byte each) instead of phases, [planes][Nj][Wp]
+    unsigned char* zone8 = nullptr;
     // subdomain engine (see jj_subdomain.cu)
     void *subdomain_plan = nullptr;
     // stats
@@ -93,6 +95,7 @@ namespace jj {
 int subdomain_supported(JJHandle* h, std::string& why_not);
 int subdomain_prepare(JJHandle* h);
 bool subdomain_prepared(JJHandle* h);
+bool subdomain_stores_zones(JJHandle* h);
 int subdomain_run(JJHandle* h, long long i0, int n, const long long* th_plane, const long long* I_plane);
 void subdomain_free_problem(JJHandle* h);
 int subdomain_set_plan(JJHandle* h, const JJSubdomainPlan* plan);

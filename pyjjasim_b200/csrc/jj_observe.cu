@@ -43,7 +43,7 @@ __device__ __forceinline__ int vorticity(const FaceView& c, const double* __rest
     double acc = 0.0;
     for (int p = p0; p < p1; ++p) {
         const double th = plane[(size_t)c.face_junc[p] * c.Wp + w];
-        acc -= (double)c.face_sign[p] * rint(th / 6.283185307179586);
+        acc -= (double)c.face_sign[p] * phase_zone(th);
     }
     return (int)acc;
 }
@@ -67,15 +67,57 @@ __global__ void k_permute_rows_i32(int Nf, int Wp, const int* __restrict__ src, 
 }
 
 // out[w] += sum over this block's faces and over consecutive planes of |n(t+1) - n(t)|
+// The kernel is bound by the latency of its gathers (one 256-byte row segment per junction, plane and warp): a face's
+// junction list is read once, and the loads of all its junctions in two planes are issued before any is used.
+constexpr int MOB_K = 8;      // junctions per face on the fast path (longer faces take the general loop)
+
+template <int KU>
+__device__ __forceinline__ int vorticity_k(const double* __restrict__ col, int Wp, const int (&j)[MOB_K], unsigned neg, int k_used) {
+    double th[KU];
+#pragma unroll
+    for (int k = 0; k < KU; ++k) th[k] = k < k_used ? __ldg(col + (size_t)j[k] * Wp) : 0.0;
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < KU; ++k) {
+        const double z = phase_zone(th[k]);            // (0 for the unused slots)
+        acc += ((neg >> k) & 1u) ? z : -z;
+    }
+    return (int)acc;
+}
+
 __global__ void __launch_bounds__(LANES * ROWS) k_vortex_mobility(const FaceView c, const double* __restrict__ planes,
                                                                    long long n_planes, unsigned long long* __restrict__ out) {
-    __shared__ unsigned long long part[ROWS][LANES];
-    const int w = blockIdx.x * LANES + threadIdx.x;
+    // block shape (bx, by), bx * by = 256: bx problems (up to 256: the warps of a block then read one contiguous
+    // 2 KB row of a plane together, which HBM serves better than 256-byte pieces at different times) x by faces
+    __shared__ unsigned long long part[LANES * ROWS];
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
     const size_t plane = (size_t)c.Nj * c.Wp;
     unsigned long long acc = 0;
     if (w < c.Wp) {
-        for (int f = blockIdx.y * ROWS + threadIdx.y; f < c.Nf; f += gridDim.y * ROWS) {
+        for (int f = blockIdx.y * blockDim.y + threadIdx.y; f < c.Nf; f += gridDim.y * blockDim.y) {
             const int p0 = c.face_ptr[f], p1 = c.face_ptr[f + 1];
+            if (p1 - p0 <= MOB_K) {
+                int j[MOB_K]; unsigned neg = 0u;          // junction rows and the bits of the negative cycle-matrix entries
+                const int ku = p1 - p0;
+#pragma unroll
+                for (int k = 0; k < MOB_K; ++k) {
+                    const int p = min(p0 + k, p1 - 1);
+                    j[k] = c.face_junc[p];
+                    if (c.face_sign[p] < 0) neg |= 1u << k;
+                }
+                const double* col = planes + w;
+                auto n_of = [&](const double* pl) { return ku <= 4 ? vorticity_k<4>(pl, c.Wp, j, neg, ku) : vorticity_k<MOB_K>(pl, c.Wp, j, neg, ku); };
+                int prev = n_of(col);
+                long long t = 1;
+                for (; t + 1 < n_planes; t += 2) {        // two planes per round: twice the loads in flight
+                    const double* pa = col + (size_t)t * plane;
+                    const int ca = n_of(pa), cb = n_of(pa + plane);
+                    acc += (unsigned long long)(abs(ca - prev) + abs(cb - ca));
+                    prev = cb;
+                }
+                if (t < n_planes) acc += (unsigned long long)abs(n_of(col + (size_t)t * plane) - prev);
+                continue;
+            }
             int prev = vorticity(c, planes, p0, p1, w);
             for (long long t = 1; t < n_planes; ++t) {
                 const int cur = vorticity(c, planes + (size_t)t * plane, p0, p1, w);
@@ -84,14 +126,102 @@ __global__ void __launch_bounds__(LANES * ROWS) k_vortex_mobility(const FaceView
             }
         }
     }
-    part[threadIdx.y][threadIdx.x] = acc;
+    part[threadIdx.y * blockDim.x + threadIdx.x] = acc;
     __syncthreads();
     if (threadIdx.y == 0 && w < c.Wp) {
         unsigned long long s = 0;
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r) s += part[r][threadIdx.x];
+        for (int r = 0; r < (int)blockDim.y; ++r) s += part[r * blockDim.x + threadIdx.x];
         if (s) atomicAdd(out + w, s);       // integer sum: independent of the order of arrival
     }
+}
+
+// launch shape of k_vortex_mobility: enough blocks to fill the machine, problem strips x face slices
+static void mobility_shape(int Wp, int Nf, dim3& grid, dim3& block) {
+    const int bx = std::min(LANES * ROWS, (Wp + 31) / 32 * 32), by = LANES * ROWS / bx;
+    const int strips = (Wp + bx - 1) / bx;
+    int slices = (Nf + by - 1) / by;
+    slices = std::max(1, std::min(slices, (148 * 8 + strips - 1) / strips));
+    grid = dim3(strips, slices); block = dim3(bx, by);
+}
+
+// The same sums from PHASE ZONE planes (jj_anneal on the subdomain engine): zones[t][j][w] is the low byte of
+// round(theta / 2 pi). A thread takes four problems (one 32-bit word per junction) and works bytewise modulo 256:
+// n_t = -A zones_t and d = n_t - n_(t-1) as signed bytes - exact while a face's vorticity moves by less than 128 per step.
+__device__ __forceinline__ unsigned zone_vorticity4(const unsigned char* __restrict__ col, int Wp, const int (&j)[MOB_K], unsigned neg, int k_used) {
+    unsigned z[MOB_K];
+#pragma unroll
+    for (int k = 0; k < MOB_K; ++k) z[k] = k < k_used ? __ldg(reinterpret_cast<const unsigned*>(col + (size_t)j[k] * Wp)) : 0u;
+    unsigned n = 0u;
+#pragma unroll
+    for (int k = 0; k < MOB_K; ++k) n = ((neg >> k) & 1u) ? __vadd4(n, z[k]) : __vsub4(n, z[k]);
+    return n;
+}
+
+__global__ void __launch_bounds__(LANES * ROWS) k_zone_mobility(const FaceView c, const unsigned char* __restrict__ zones,
+                                                                 long long n_planes, unsigned long long* __restrict__ out) {
+    __shared__ unsigned part[LANES * ROWS][4];
+    const int w = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+    const size_t plane = (size_t)c.Nj * c.Wp;
+    unsigned acc[4] = {0u, 0u, 0u, 0u};
+    if (w < c.Wp) {
+        for (int f = blockIdx.y * blockDim.y + threadIdx.y; f < c.Nf; f += gridDim.y * blockDim.y) {
+            const int p0 = c.face_ptr[f], p1 = c.face_ptr[f + 1];
+            if (p1 - p0 <= MOB_K) {
+                int j[MOB_K]; unsigned neg = 0u;          // junction rows and the bits of the negative cycle-matrix entries
+                const int ku = p1 - p0;
+#pragma unroll
+                for (int k = 0; k < MOB_K; ++k) {
+                    const int p = min(p0 + k, max(p1 - 1, p0));
+                    j[k] = ku > 0 ? c.face_junc[p] : 0;
+                    if (ku > 0 && c.face_sign[p] < 0) neg |= 1u << k;
+                }
+                const unsigned char* col = zones + w;
+                unsigned prev = zone_vorticity4(col, c.Wp, j, neg, ku);
+                for (long long t = 1; t < n_planes; ++t) {
+                    const unsigned cur = zone_vorticity4(col + (size_t)t * plane, c.Wp, j, neg, ku);
+                    const unsigned d = __vabs4(__vsub4(cur, prev));
+                    acc[0] += d & 0xffu; acc[1] += (d >> 8) & 0xffu; acc[2] += (d >> 16) & 0xffu; acc[3] += d >> 24;
+                    prev = cur;
+                }
+            } else {
+                unsigned prev = 0u;
+                for (long long t = 0; t < n_planes; ++t) {
+                    const unsigned char* col = zones + (size_t)t * plane + w;
+                    unsigned cur = 0u;
+                    for (int p = p0; p < p1; ++p) {
+                        const unsigned z = __ldg(reinterpret_cast<const unsigned*>(col + (size_t)c.face_junc[p] * c.Wp));
+                        cur = c.face_sign[p] < 0 ? __vadd4(cur, z) : __vsub4(cur, z);
+                    }
+                    if (t > 0) {
+                        const unsigned d = __vabs4(__vsub4(cur, prev));
+                        acc[0] += d & 0xffu; acc[1] += (d >> 8) & 0xffu; acc[2] += (d >> 16) & 0xffu; acc[3] += d >> 24;
+                    }
+                    prev = cur;
+                }
+            }
+        }
+    }
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) part[tid][e] = acc[e];
+    __syncthreads();
+    if (threadIdx.y == 0 && w < c.Wp) {
+        for (int e = 0; e < 4; ++e) {
+            unsigned long long s = 0;
+            for (int r = 0; r < (int)blockDim.y; ++r) s += part[r * blockDim.x + threadIdx.x][e];
+            if (s && w + e < c.Wp) atomicAdd(out + w + e, s);
+        }
+    }
+}
+
+// launch shape of k_zone_mobility: bx threads x 4 problems across, by faces down
+static void zone_mobility_shape(int Wp, int Nf, dim3& grid, dim3& block) {
+    const int words = (Wp + 3) / 4;
+    const int bx = std::min(LANES * ROWS, (words + 31) / 32 * 32), by = LANES * ROWS / bx;
+    const int strips = (words + bx - 1) / bx;
+    int slices = (Nf + by - 1) / by;
+    slices = std::max(1, std::min(slices, (148 * 8 + strips - 1) / strips));
+    grid = dim3(strips, slices); block = dim3(bx, by);
 }
 
 // nsum[f][w] += n_f(theta): one observation of the streaming engine (the subdomain engine accumulates inside its step
@@ -315,12 +445,8 @@ int jj_vortex_mobility(JJHandle* h, int64_t plane0, int64_t n_planes, int64_t* d
     int rc = scratch(h, bytes, (void**)&buf);
     if (rc) return rc;
     cudaError_t e = cudaMemsetAsync(buf, 0, bytes, h->stream);
-    // enough blocks to fill the machine: problem strips x face slices
-    const int strips = (c.Wp + LANES - 1) / LANES;
-    int slices = (c.Nf + ROWS - 1) / ROWS;
-    const int want = (148 * 8 + strips - 1) / strips;
-    if (slices > want) slices = want;
-    dim3 grid(strips, slices), block(LANES, ROWS);
+    dim3 grid, block;
+    mobility_shape(c.Wp, c.Nf, grid, block);
     k_vortex_mobility<<<grid, block, 0, h->stream>>>(c, h->th_out + (size_t)plane0 * c.Nj * c.Wp, n_planes, buf);
     h->launches++;
     if (e == cudaSuccess) e = cudaMemcpyAsync(dst, buf, (size_t)h->W * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream);
@@ -351,11 +477,22 @@ int jj_anneal(JJHandle* h, int64_t first_interval, int32_t n_intervals, int32_t 
     if ((rc = dev_alloc(h, (void**)&prof, pb))) { dev_free(h, Td, tb); return rc; }
     std::vector<long long> planes(steps);
     for (int k = 0; k < steps; ++k) planes[k] = k;
+    // On the subdomain engine the interval's planes hold PHASE ZONES - the low byte of round(theta / 2 pi) per junction
+    // and problem, written by the annealing variant of the step kernel into the theta plane buffer (an eighth of it) -
+    // and k_zone_mobility takes the mobility from them: 4 bytes instead of 32 per junction and four problems leave the
+    // step kernel, and the mobility kernel gathers bytes that are still in L2. JJ_ANNEAL_ZONES=0 (and the streaming
+    // engine) store the phases themselves and run k_vortex_mobility on them.
+    std::string why;
+    const bool sub = h->engine_req == JJ_ENGINE_SUBDOMAIN || (h->engine_req == JJ_ENGINE_AUTO && subdomain_supported(h, why));
+    const char* ze = getenv("JJ_ANNEAL_ZONES");
+    bool zones = sub && !(ze && atoi(ze) == 0) && c.Nf > 0 && steps >= 2;
+    if (zones && !subdomain_prepared(h) && (rc = subdomain_prepare(h))) { dev_free(h, Td, tb); dev_free(h, prof, pb); return rc; }
+    zones = zones && subdomain_stores_zones(h);
     cudaError_t e = cudaMemsetAsync(Td, 0, tb, h->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(Td, T, (size_t)W * sizeof(double), cudaMemcpyHostToDevice, h->stream);
-    const int strips = (Wp + LANES - 1) / LANES;
-    int slices = (c.Nf + ROWS - 1) / ROWS;
-    slices = std::max(1, std::min(slices, (148 * 8 + strips - 1) / strips));
+    dim3 mgrid, mblock, zgrid, zblock;
+    mobility_shape(Wp, c.Nf, mgrid, mblock);
+    zone_mobility_shape(Wp, c.Nf, zgrid, zblock);
     // the whole schedule is enqueued back to back; one wait, one timing, one non-finite check at the end
     if ((rc = scratch(h, (size_t)Wp * sizeof(unsigned long long), (void**)&sums))) { dev_free(h, Td, tb); dev_free(h, prof, pb); return rc; }
     if (e == cudaSuccess) e = cudaEventRecord(h->ev0, h->stream);
@@ -366,11 +503,16 @@ int jj_anneal(JJHandle* h, int64_t first_interval, int32_t n_intervals, int32_t 
         if (first_interval + i > 0)      // zero-velocity restart of every interval but the first (time_evolution.py:1169-1171)
             e = cudaMemcpyAsync(h->th2, h->th1, (size_t)c.Nj * Wp * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
         if (e != cudaSuccess) break;
+        h->zone8 = zones ? reinterpret_cast<unsigned char*>(h->th_out) : nullptr;
         rc = run_enqueue(h, (first_interval + i) * (long long)steps, steps, planes.data(), nullptr);
+        h->zone8 = nullptr;
         if (rc) break;
         e = cudaMemsetAsync(sums, 0, (size_t)Wp * sizeof(unsigned long long), h->stream);
-        if (c.Nf > 0 && steps >= 2) {
-            k_vortex_mobility<<<dim3(strips, slices), dim3(LANES, ROWS), 0, h->stream>>>(c, h->th_out, steps, sums);
+        if (zones) {
+            k_zone_mobility<<<zgrid, zblock, 0, h->stream>>>(c, reinterpret_cast<const unsigned char*>(h->th_out), steps, sums);
+            h->launches++;
+        } else if (c.Nf > 0 && steps >= 2) {
+            k_vortex_mobility<<<mgrid, mblock, 0, h->stream>>>(c, h->th_out, steps, sums);
             h->launches++;
         }
         k_anneal_rule<<<(W + 255) / 256, 256, 0, h->stream>>>(W, sums, norm, upper[i], T_factor, inv_T_factor, Td, prof + (size_t)i * W);

@@ -86,6 +86,9 @@ struct SubArgs {
     // obs_nsum [Nf][Wp] (permuted faces) and leave their phases in obs_th_last (the first one also in obs_th_first)
     long long obs_first; int obs_interval;
     int* obs_nsum; double *obs_th_first, *obs_th_last;
+    // vortex mobility of an annealing interval (jj_anneal): the steps with a theta plane number p >= 0 store the low byte
+    // of round(theta / 2 pi) to zone8[p][Nj][Wp] (original junction order) instead of theta; null = off
+    unsigned char* zone8;
     const double* dbg_b; double* dbg_J;   // debug solve: canonical [Nf][Wp], permuted faces
     long long* prof;                       // optional per-block cycle counters [block][8]
     int stagger;                           // cycles by which consecutive problem chunks start apart (chunk-local top phase only)
@@ -108,6 +111,14 @@ constexpr int BLOCKS_PER_SM = NT == 256 ? 2 : 1;
 constexpr size_t BAR_COUNTERS = 8192;   // grid barrier counter + one counter per problem chunk, 128 bytes apart
 constexpr size_t BAR_BYTES = BAR_COUNTERS + 128;     // ... + the 64-bit work counter of the item scheduler
 constexpr int NWARPS = NT / 32;
+// The annealing schedule's kernels (build.sh: units jj_subdomain_m_ng*, -DJJ_SUB_MOB=1) store the PHASE ZONES of the
+// requested steps (one byte per junction and problem, SubArgs::zone8) instead of the phases; the code is compiled out of
+// the ordinary step kernels, whose register allocation at the 128-register cap does not tolerate passengers
+// (profiles/r02_experiments.md).
+#ifndef JJ_SUB_MOB
+#define JJ_SUB_MOB 0
+#endif
+constexpr bool MOB = JJ_SUB_MOB != 0;
 constexpr int RING = 4;            // stream steps per ring block; every tile is padded to a multiple of it
 constexpr int STEP_BYTES = 320;
 constexpr double TWO_PI = 6.283185307179586;
@@ -448,7 +459,13 @@ __device__ __forceinline__ void junction_item(const SubArgs& a, const AmpCache<8
     // (the snapshot planes travel as two plane numbers, -1 = none, not as two pointers: two registers less in the loop)
     if (plane_th >= 0 || plane_I >= 0 || !do_pre) {
         const size_t cidx = (size_t)ri.z * a.Wp + w;
-        if (plane_th >= 0) {
+        if (MOB && a.zone8 && plane_th >= 0) {
+            // the vortex configuration n = -A round(theta / 2 pi) moves by a few units per step at most: its changes are
+            // exact from the zones modulo 256 (k_zone_mobility), 4 bytes per thread instead of 32
+            const unsigned z = ((unsigned)(int)phase_zone(th1[0]) & 0xffu) | (((unsigned)(int)phase_zone(th1[1]) & 0xffu) << 8) |
+                               (((unsigned)(int)phase_zone(th1[2]) & 0xffu) << 16) | (((unsigned)(int)phase_zone(th1[3]) & 0xffu) << 24);
+            *reinterpret_cast<unsigned*>(a.zone8 + (size_t)plane_th * a.Nj * a.Wp + cidx) = z;
+        } else if (plane_th >= 0) {
             double2* sp = reinterpret_cast<double2*>(a.snap_th + (size_t)plane_th * a.Nj * a.Wp + cidx);
             sp[0] = make_double2(th1[0], th1[1]); sp[1] = make_double2(th1[2], th1[3]);
         }
@@ -677,8 +694,8 @@ __device__ __noinline__ void vortex_pass(const VortexView o) {
             for (int k = 0; k < 4; ++k) {
                 if (je[k] < 0) continue;
                 const double sg = (je[k] & 1) ? -1.0 : 1.0;
-                acc[0] -= sg * rint(t[k].lo.x / TWO_PI); acc[1] -= sg * rint(t[k].lo.y / TWO_PI);
-                acc[2] -= sg * rint(t[k].hi.x / TWO_PI); acc[3] -= sg * rint(t[k].hi.y / TWO_PI);
+                acc[0] -= sg * phase_zone(t[k].lo.x); acc[1] -= sg * phase_zone(t[k].lo.y);
+                acc[2] -= sg * phase_zone(t[k].hi.x); acc[3] -= sg * phase_zone(t[k].hi.y);
             }
         }
         if (row < o.nl) {
@@ -1509,6 +1526,11 @@ KernelPtr subdomain_kernel_ng1(bool def, bool upper);
 KernelPtr subdomain_kernel_ng2(bool def, bool upper);
 KernelPtr subdomain_kernel_ng4(bool def, bool upper);
 KernelPtr subdomain_kernel_ng8(bool def, bool upper);
+// the annealing schedule's variant (full blocks): phase zones instead of phases in the stored planes
+KernelPtr subdomain_kernel_m_ng1(bool def, bool upper);
+KernelPtr subdomain_kernel_m_ng2(bool def, bool upper);
+KernelPtr subdomain_kernel_m_ng4(bool def, bool upper);
+KernelPtr subdomain_kernel_m_ng8(bool def, bool upper);
 // half blocks (256 threads, two per SM); no upper program
 KernelPtr subdomain_kernel_h_ng1(bool def, bool upper);
 KernelPtr subdomain_kernel_h_ng2(bool def, bool upper);
@@ -1524,6 +1546,11 @@ KernelPtr JJ_SUB_CAT(subdomain_kernel_h_ng, JJ_SUB_NG)(bool def, bool upper) {
     if (upper) return nullptr;           // the upper phases are written for 16 warps
     return def ? k_subdomain<JJ_SUB_NG, true, false> : k_subdomain<JJ_SUB_NG, false, false>;
 }
+#elif JJ_SUB_MOB
+KernelPtr JJ_SUB_CAT(subdomain_kernel_m_ng, JJ_SUB_NG)(bool def, bool upper) {
+    if (upper) return def ? k_subdomain<JJ_SUB_NG, true, true> : k_subdomain<JJ_SUB_NG, false, true>;
+    return def ? k_subdomain<JJ_SUB_NG, true, false> : k_subdomain<JJ_SUB_NG, false, false>;
+}
 #else
 KernelPtr JJ_SUB_CAT(subdomain_kernel_ng, JJ_SUB_NG)(bool def, bool upper) {
     if (upper) return def ? k_subdomain<JJ_SUB_NG, true, true> : k_subdomain<JJ_SUB_NG, false, true>;
@@ -1535,7 +1562,16 @@ KernelPtr JJ_SUB_CAT(subdomain_kernel_ng, JJ_SUB_NG)(bool def, bool upper) {
 
 namespace {
 
-KernelPtr pick_kernel(int threads, int NG, bool def, bool upper) {
+KernelPtr pick_kernel(int threads, int NG, bool def, bool upper, bool zones) {
+    if (zones) {
+        if (threads != NT) return nullptr;
+        switch (NG) {
+            case 1: return subdomain_kernel_m_ng1(def, upper);
+            case 2: return subdomain_kernel_m_ng2(def, upper);
+            case 4: return subdomain_kernel_m_ng4(def, upper);
+            default: return subdomain_kernel_m_ng8(def, upper);
+        }
+    }
     if (threads == 256) {
         switch (NG) {
             case 1: return subdomain_kernel_h_ng1(def, upper);
@@ -1826,6 +1862,7 @@ static void fill_args(JJHandle* h, SubState* st, SubArgs& a) {
     a.snap_th = h->th_out; a.snap_I = h->I_out; a.flag = h->flag_d;
     a.obs_first = h->obs_first; a.obs_interval = h->obs_interval;
     a.obs_nsum = h->obs_nsum; a.obs_th_first = h->obs_th_first; a.obs_th_last = h->obs_th_last;
+    a.zone8 = h->zone8;
     a.dbg = st->dbg;
     a.stagger = st->stagger > 0 ? st->stagger : 0;
 }
@@ -1838,7 +1875,7 @@ static int launch(JJHandle* h, SubState* st, SubArgs& a) {
     int cap = sms * (st->threads == 256 ? 2 : 1);
     if (st->grid_env > 0) cap = std::min(cap, st->grid_env);
     const bool general = st->n_up_fwd + st->n_up_bwd > 0 || st->P * st->n_chunks > cap || a.dbg_b != nullptr;
-    KernelPtr k = pick_kernel(st->threads, st->NG, h->cir.default_cpr, general);
+    KernelPtr k = pick_kernel(st->threads, st->NG, h->cir.default_cpr, general, a.zone8 != nullptr);
     if (!k) { h->err = "subdomain: no kernel for this block size / chunk width / item count"; return JJ_EINVAL; }
     {
         const Source &is = h->src[JJ_SRC_IS].dev, &t = h->src[JJ_SRC_T].dev, &vs = h->src[JJ_SRC_VS].dev;
@@ -2000,6 +2037,12 @@ int subdomain_debug_solve(JJHandle* h, const double* b_d, double* J_d) {
     fill_args(h, st, a);
     a.dbg_b = b_d; a.dbg_J = J_d;
     return launch(h, st, a);
+}
+
+// whether runs of this plan can store phase zones instead of phases (jj_anneal)
+bool subdomain_stores_zones(JJHandle* h) {
+    SubState* st = (SubState*)h->subdomain_plan;
+    return st && st->prepared && st->threads == NT;
 }
 
 void subdomain_get_config(JJHandle* h, int* P, int* PC) {

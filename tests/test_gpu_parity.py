@@ -382,6 +382,65 @@ def test_device_side_temperature_schedule_equals_the_host_rule_bit_for_bit(engin
             assert np.any(ratio > 1) and (np.any(ratio < 1) or kw["interval_count"] < 10)
 
 
+@pytest.mark.parametrize("cfg", [
+    dict(array=(14, 13), W=10, env={}),                                            # one block per item, few subdomains
+    dict(array=(40, 37), W=40, env={"JJ_SUBDOMAIN": "3,1"}),                       # lean kernel, 8 subdomains, chunk-local barriers
+    dict(array=(40, 37), W=70, env={"JJ_SUBDOMAIN": "3,2", "JJ_SUB_GRID": "5"}),   # several items per block (work counter)
+    dict(array=(61, 53), W=33, env={"JJ_SUBDOMAIN": "5,4", "JJ_TT_MAX": "40"}),    # upper phases inside the time loop
+    dict(array=(61, 53), W=20, env={"JJ_SUBDOMAIN": "4,1", "JJ_TT_MAX": "0"}),     # no dense top at all
+    dict(array=(14, 13), W=12, env={}, Is="drive"),                                 # driven far above Ic: zones wrap past 127
+])
+def test_mobility_from_phase_zone_planes_equals_the_mobility_from_phase_planes(cfg, monkeypatch):
+    # on the subdomain engine jj_anneal lets the step kernel store the phase zones round(theta / 2 pi) of the interval's
+    # steps as bytes and k_zone_mobility works on them modulo 256; with JJ_ANNEAL_ZONES=0 it stores the phases themselves
+    # and k_vortex_mobility reads them back. Integer sums: the temperature profiles and the phases must be identical.
+    from pyjjasim_b200 import engine as eng_mod
+    monkeypatch.setenv("JJ_ENGINE", "subdomain")
+    for k, v in cfg["env"].items():
+        monkeypatch.setenv(k, v)
+    a = pj.SquareArray(*cfg["array"])
+    if cfg.get("Is") == "drive":
+        cfg = dict(cfg, Is=30.0 * a.current_base(angle=0)[:, None, None])        # ~30 rad per unit time: > 128 zones within the schedule
+    args = dict(circuit=a, time_step=0.5, interval_steps=7, external_flux=0.2, current_sources=cfg.get("Is", 0), problem_count=cfg["W"],
+                noise_seed=5, vortex_mobility=0.02, start_T=0.4, T_factor=1.25, interval_count=12)
+    out = {}
+    for zones in ("0", "1"):
+        monkeypatch.setenv("JJ_ANNEAL_ZONES", zones)
+        out[zones] = pj.AnnealingProblem(**args).anneal()
+        assert eng_mod.last_run_stats[0]["engine"] == 3
+    (th_p, n_p, prof_p), (th_k, n_k, prof_k) = out["0"], out["1"]
+    ratio = prof_p[1:] / prof_p[:-1]
+    if np.ndim(cfg.get("Is", 0)) == 0:
+        assert np.any(ratio > 1) and np.any(ratio < 1)            # both directions of the rule were exercised
+    else:
+        assert np.abs(th_p).max() > 2 * np.pi * 200               # the driven junctions wound through > 128 zones
+    assert np.array_equal(prof_k, prof_p) and np.array_equal(th_k, th_p) and np.array_equal(n_k, n_p)
+
+
+def test_phase_zones_at_the_rounding_ties():
+    # the device takes round(theta / 2 pi) from a reciprocal product when that is safely away from a tie and from the
+    # true division otherwise: phases placed on and next to the half-integers must give numpy's integers
+    from pyjjasim_b200 import engine as eng_mod
+    a = pj.SquareArray(3, 3)
+    Nj, W = a.junction_count(), 64
+    rng = np.random.RandomState(0)
+    k = rng.randint(-2000, 2000, size=(Nj, W)).astype(np.double)
+    th = (k + 0.5) * (2 * np.pi)
+    for _ in range(3):                                   # a few ulps to either side of the tie, and the tie itself
+        step = rng.randint(-3, 4, size=th.shape)
+        th = np.where(step > 0, np.nextafter(th, np.inf), np.where(step < 0, np.nextafter(th, -np.inf), th))
+    th[:, ::7] = rng.randn(Nj, th[:, ::7].shape[1]) * 1e7      # huge phases: always the division
+    tab = eng_mod._tables_for(a, 0.05)
+    key, e, kind = eng_mod._engine_for(tab, pj.DefaultCPR(), 0, W, eng_mod._engine_kind(None))
+    try:
+        e.set_problem(W, 0.05, engine=kind)
+        e.set_state(th, th)
+        want = -(a.get_cycle_matrix() @ np.round(th / (2.0 * np.pi))).astype(int)
+        assert np.array_equal(e.vortex_configuration(-1), want)
+    finally:
+        eng_mod._release_engine(0, key, e, True)
+
+
 def test_annealing_equals_reference_style_loop():
     # the loop exactly as the reference writes it (re-entering compute(), assigning prob.temperature and the
     # initial conditions, vortex configurations on the host) gives the same schedule as the device-resident path

@@ -39,6 +39,9 @@ def main():
     dev_ms = sum(s["total_ms"] for s in ap.last_stats.values())
     out["device"] = dict(wall_s=t1 - t0, device_ms=dev_ms, junction_steps_per_s=total / (t1 - t0),
                          final_T_median=float(np.median(prof[-1])), vortices_mean=float(np.abs(n).sum(axis=0).mean()))
+    if os.environ.get("ANNEAL_LOOP", "1") == "0":
+        print(json.dumps(out))
+        return
     # reference-style loop through compute()
     cnt2 = max(3, count // 10)
     f = np.atleast_1d(0.1)[:, None, None]

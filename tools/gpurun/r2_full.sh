@@ -10,3 +10,5 @@ print('cfg2 us/timestep %.2f  %.2f Gjs/s frac %.3f e2e %.2f G'%(d['ms_per_step']
 for k,v in d['per_config'].items(): print(k, {a: (round(b,3) if isinstance(b,float) else b) for a,b in v.items() if a in ('value','e2e','roofline_frac','device_us_per_time_step','setup_s','error')})
 print(d['cpu_baseline']['value'])
 "
+timeout 600 python tools/anneal_bench.py > gpurun_out/r2_anneal_bench.json 2> gpurun_out/r2_anneal_bench.err; tail -2 gpurun_out/r2_anneal_bench.err; head -c 500 gpurun_out/r2_anneal_bench.json; echo
+timeout 300 python __graft_entry__.py > gpurun_out/r2_smoke.txt 2>&1; tail -2 gpurun_out/r2_smoke.txt
