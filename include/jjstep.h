@@ -188,6 +188,10 @@ int jj_debug_subdomain_solve(JJHandle *h, const double *b, double *J);
  * keep the state and the stored planes on the device between intervals. */
 /* zero-velocity restart: theta(-2) := theta(-1) on the device (reference: time_evolution.py:1169-1171) */
 int jj_restart_at_rest(JJHandle *h);
+/* the closing runs of the schedule use another time step, i.e. another handle (its own factor): theta(-1) = theta(-2)
+ * := theta(-1) of `from`, device to device (same device, same junction and problem counts)
+ * (reference: time_evolution.py:1176-1183 hands the phases over through the host) */
+int jj_adopt_state_at_rest(JJHandle *h, JJHandle *from);
 /* n = -A round(theta / 2 pi) of stored theta plane `plane` (-1: the current state theta(-1)); dst is (Nf, W) int32,
  * faces in the PERMUTED order (reference: time_evolution.py:734-755, get_vortex_configuration) */
 int jj_vortex_configuration(JJHandle *h, int64_t plane, int32_t *dst);

@@ -22,7 +22,7 @@ EXPORTS = ["jj_create", "jj_destroy", "jj_last_error", "jj_set_circuit", "jj_set
            "jj_set_state", "jj_get_state", "jj_set_source", "jj_upload_source", "jj_upload_noise",
            "jj_alloc_outputs", "jj_run", "jj_fetch_theta", "jj_fetch_current", "jj_debug_noise",
            "jj_debug_solve", "jj_stats", "jj_set_subdomain_plan", "jj_debug_subdomain_solve", "jj_sm_count",
-           "jj_restart_at_rest", "jj_vortex_configuration", "jj_vortex_mobility", "jj_vortex_configurations", "jj_observe_begin", "jj_observe_fetch", "jj_anneal",
+           "jj_restart_at_rest", "jj_adopt_state_at_rest", "jj_vortex_configuration", "jj_vortex_mobility", "jj_vortex_configurations", "jj_observe_begin", "jj_observe_fetch", "jj_anneal",
            "jj_host_alloc", "jj_host_free"]
 
 _p = C.c_void_p
@@ -110,6 +110,7 @@ def load():
     lib.jj_debug_subdomain_solve.argtypes = [_p, _f64p, _f64p]
     lib.jj_sm_count.argtypes = [C.c_int]
     lib.jj_restart_at_rest.argtypes = [_p]
+    lib.jj_adopt_state_at_rest.argtypes = [_p, _p]
     lib.jj_vortex_configuration.argtypes = [_p, C.c_int64, _i32p]
     lib.jj_vortex_mobility.argtypes = [_p, C.c_int64, C.c_int64, _i64p]
     lib.jj_vortex_configurations.argtypes = [_p, C.c_int64, C.c_int64, _i32p, _i32p]

@@ -412,6 +412,23 @@ int jj_restart_at_rest(JJHandle* h) {
     return JJ_OK;
 }
 
+int jj_adopt_state_at_rest(JJHandle* h, JJHandle* from) {
+    REQUIRE(from && from != h, JJ_EINVAL, "adopt_state_at_rest: needs another handle");
+    CK(cudaSetDevice(h->device));
+    REQUIRE(from->device == h->device, JJ_EINVAL, "adopt_state_at_rest: the handles live on different devices");
+    REQUIRE(h->have_problem && from->have_problem && from->have_state, JJ_ESTATE, "adopt_state_at_rest: problem/state not set");
+    REQUIRE(h->cir.Nj == from->cir.Nj && h->W == from->W && h->Wp == from->Wp, JJ_EINVAL,
+            "adopt_state_at_rest: the handles differ in junction or problem count");
+    REQUIRE(!h->thetas && !from->thetas, JJ_EINVAL, "adopt_state_at_rest: not available with dense voltage sources");
+    CK(cudaStreamSynchronize(from->stream));          // (the state of `from` is final)
+    const size_t bytes = (size_t)h->cir.Nj * h->Wp * sizeof(double);
+    CK(cudaMemcpyAsync(h->th1, from->th1, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->th2, from->th1, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->have_state = true;
+    return JJ_OK;
+}
+
 int jj_vortex_configuration(JJHandle* h, int64_t plane, int32_t* dst) {
     CK(cudaSetDevice(h->device));
     REQUIRE(h->have_problem, JJ_ESTATE, "vortex_configuration: problem not set");

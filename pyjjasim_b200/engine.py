@@ -515,9 +515,11 @@ class DeviceEngine:
         assert a.shape == (self.tab.Nj, self.W) and b.shape == (self.tab.Nj, self.W)
         self._ck(self.lib.jj_set_state(self.h, _lib.f64(a), _lib.f64(b)))
 
-    def get_state(self, previous=True):
-        """(theta(-1), theta(-2)) of the device state; previous=False fetches theta(-1) only (-> (theta(-1), None))"""
-        a = np.empty((self.tab.Nj, self.W))
+    def get_state(self, previous=True, out=None):
+        """(theta(-1), theta(-2)) of the device state; previous=False fetches theta(-1) only (-> (theta(-1), None));
+        out: a C-contiguous (Nj, W) float64 array to receive theta(-1) (e.g. page-locked)"""
+        ok = out is not None and out.shape == (self.tab.Nj, self.W) and out.dtype == np.double and out.flags.c_contiguous
+        a = out if ok else np.empty((self.tab.Nj, self.W))
         b = np.empty((self.tab.Nj, self.W)) if previous else None
         self._ck(self.lib.jj_get_state(self.h, _lib.f64(a), _lib.f64(b) if previous else None))
         return a, b
@@ -585,6 +587,10 @@ class DeviceEngine:
     def restart_at_rest(self):
         """theta(-2) := theta(-1) on the device (reference: time_evolution.py:1169-1171)."""
         self._ck(self.lib.jj_restart_at_rest(self.h))
+
+    def adopt_state_at_rest(self, other):
+        """theta(-1) = theta(-2) := theta(-1) of another engine on the same device, device to device."""
+        self._ck(self.lib.jj_adopt_state_at_rest(self.h, other.h))
 
     def vortex_configuration(self, plane=-1):
         """n = -A round(theta / 2 pi) of a stored theta plane (-1: the current state), (Nf, W) int array in the
@@ -1121,17 +1127,22 @@ def _anneal_shard(problem, tab, tab2, specs, dev, w0, w1, ann, adjust, out, engi
             sums = eng.vortex_mobility_sums(0, steps)
             out["T"][w0:w1] = adjust(sums, i, T)
             out["profiles"][i, w0:w1] = out["T"][w0:w1]
-        th, _ = eng.get_state(previous=False)
         launches += eng.stats()["kernel_launches"]
+        # closing runs at T = 0 with half the time step (reference: time_evolution.py:1176-1183): another factor, i.e.
+        # another engine; the phases go over device to device
+        key2, eng2, run_kind2 = _engine_for(tab2, cpr, dev, W, engine_kind, dense)
+        try:
+            eng2.set_problem(W, dt / 2, seed=seed, problem_offset=w0, engine=run_kind2)
+            eng2.adopt_state_at_rest(eng)
+        except BaseException:
+            _release_engine(dev, key2, eng2, False)
+            raise
         ok = True
     finally:
         _release_engine(dev, key, eng, ok)
-    # closing runs at T = 0 with half the time step (reference: time_evolution.py:1176-1183)
-    key, eng, run_kind = _engine_for(tab2, cpr, dev, W, engine_kind, dense)
+    key, eng, run_kind = key2, eng2, run_kind2
     ok = False
     try:
-        eng.set_problem(W, dt / 2, seed=seed, problem_offset=w0, engine=run_kind)
-        eng.set_state(th, th)
         _setup_sources(eng, specs, sh, tab2)
         eng.set_source(_lib.JJ_SRC_T, _lib.JJ_KIND_ZERO, True)
         eng.alloc_outputs(0, 0)
@@ -1140,8 +1151,10 @@ def _anneal_shard(problem, tab, tab2, specs, dev, w0, w1, ann, adjust, out, engi
                 eng.restart_at_rest()
             eng.run(r * steps, steps, None, None)
             total_ms += eng.stats()["step_ms"]
-        th, _ = eng.get_state(previous=False)
-        out["theta"][:, w0:w1] = th
+        whole = w0 == 0 and w1 == out["theta"].shape[1]          # one shard: the phases land in the result array itself
+        th, _ = eng.get_state(previous=False, out=out["theta"] if whole else None)
+        if th is not out["theta"]:
+            out["theta"][:, w0:w1] = th
         out["n"][:, w0:w1] = eng.vortex_configuration(-1)
         st = eng.stats()
         st["total_ms"] = total_ms
@@ -1183,7 +1196,7 @@ def device_annealing(problem, T0, adjust, interval_count, final_runs=5, engine=N
     if specs["Vs"].kind == DENSE:
         raise NotImplementedError("annealing with dense voltage sources is not supported")
     out = dict(T=np.array(T0, dtype=np.double).reshape(W).copy(), profiles=np.zeros((interval_count, W)),
-               theta=np.zeros((tab.Nj, W)), n=np.zeros((tab.Nf, W), dtype=int))
+               theta=_pinned.empty((tab.Nj, W), devices[0]), n=np.zeros((tab.Nf, W), dtype=int))
     ann = dict(dt=dt, interval_count=int(interval_count), interval_steps=problem._Nt(), final_runs=int(final_runs),
                seed=resolve_noise_seed(problem),
                noise_replay=getattr(problem, "noise_replay", None), rule=rule)
