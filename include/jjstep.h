@@ -201,11 +201,14 @@ int jj_vortex_mobility(JJHandle *h, int64_t plane0, int64_t n_planes, int64_t *d
 
 /* The whole temperature schedule without host round trips: for interval i = first_interval .. + n_intervals - 1
  *   noise amplitude := sqrt(T) (zero for all once every T is numerically zero, time_evolution.py:512); theta(-2) := theta(-1)
- *   (not before interval 0); `steps` time steps with every theta plane kept; the interval's exact integer mobility sums;
+ *   (not before interval 0); `steps` time steps; the interval's exact integer mobility sums;
  *   T *= (sum / norm > upper[i]) ? inv_T_factor : T_factor; profiles[i] := T        (reference: time_evolution.py:1128-1140)
  * The temperature must have been declared jj_set_source(JJ_SRC_T, JJ_KIND_RANK1, static) with one amplitude row uploaded,
- * and jj_alloc_outputs must provide `steps` theta planes. T: (W,) in/out; profiles: (n_intervals, W) out; the arithmetic
- * is the reference's on the same integers, so the schedule is bit-identical to one evaluated on the host. */
+ * and jj_alloc_outputs must provide `steps` theta planes: they are SCRATCH of the schedule (the streaming engine keeps the
+ * interval's phases there; the subdomain engine keeps one byte per junction and problem, round(theta / 2 pi) mod 256, from
+ * which the mobility sums are exact) - their contents are unspecified afterwards. T: (W,) in/out; profiles:
+ * (n_intervals, W) out; the arithmetic is the reference's on the same integers, so the schedule is bit-identical to one
+ * evaluated on the host. */
 int jj_anneal(JJHandle *h, int64_t first_interval, int32_t n_intervals, int32_t steps, const double *upper,
               double T_factor, double inv_T_factor, double norm, double *T, double *profiles, double *device_ms);
 /* all stored theta planes [plane0, plane0 + n_planes) at once: dst is (n_planes, Nf, W) int32, permuted faces. With it the

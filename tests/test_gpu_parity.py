@@ -417,6 +417,52 @@ def test_mobility_from_phase_zone_planes_equals_the_mobility_from_phase_planes(c
     assert np.array_equal(prof_k, prof_p) and np.array_equal(th_k, th_p) and np.array_equal(n_k, n_p)
 
 
+@pytest.mark.parametrize("engine", ENGINES)
+def test_mobility_kernels_on_faces_longer_than_their_fast_path(engine, monkeypatch):
+    # two faces of 11 junctions each (a ring of 20 with one chord): the mobility kernels keep up to 8 junction rows of a face
+    # in registers and take a general loop beyond; the schedule must equal the host rule on the same integer sums, with
+    # phase-zone bytes (subdomain engine) and with phase planes
+    from pyjjasim_b200 import engine as eng_mod
+    monkeypatch.setenv("JJ_ENGINE", engine)
+    N = 20
+    ang = 2 * np.pi * np.arange(N) / N
+    n1 = np.concatenate([np.arange(N), [0]])
+    n2 = np.concatenate([(np.arange(N) + 1) % N, [N // 2]])
+    c = pj.Circuit(pj.EmbeddedGraph(np.cos(ang), np.sin(ang), n1, n2))
+    assert np.all(np.diff(c.get_cycle_matrix().tocsr().indptr) == 11)
+    args = dict(circuit=c, time_step=0.5, interval_steps=9, external_flux=0.4, current_sources=0, problem_count=7,
+                noise_seed=11, vortex_mobility=0.05, start_T=1.5, T_factor=1.2, interval_count=14)
+    monkeypatch.setenv("JJ_ANNEAL_HOST", "1")
+    th_h, n_h, prof_h = pj.AnnealingProblem(**args).anneal()
+    monkeypatch.setenv("JJ_ANNEAL_HOST", "0")
+    for zones in ("1", "0"):
+        monkeypatch.setenv("JJ_ANNEAL_ZONES", zones)
+        th_d, n_d, prof_d = pj.AnnealingProblem(**args).anneal()
+        assert np.array_equal(prof_d, prof_h) and np.array_equal(th_d, th_h) and np.array_equal(n_d, n_h)
+        assert eng_mod.last_run_stats[0]["engine"] == (3 if engine == "auto" else 1)      # (zone bytes: subdomain engine only)
+    ratio = prof_h[1:] / prof_h[:-1]
+    assert np.any(ratio < 1)                                  # the hot start did move vortices
+    # and k_vortex_mobility itself against numpy on host copies of the phases: the same draws replayed through the
+    # device loop and through the loop as the reference writes it (compute() per interval, mobility on the host)
+    Z = np.random.RandomState(3).randn(args["interval_count"], args["interval_steps"], c.junction_count(), args["problem_count"])
+    kw = {k: v for k, v in args.items() if k != "noise_seed"}
+    _, _, prof_r = pj.AnnealingProblem(noise_replay=Z, **kw).anneal()
+    ref_style = pj.AnnealingProblem(**kw)
+    th = np.zeros((c.junction_count(), kw["problem_count"]))
+    prob = pj.TimeEvolutionProblem(c, time_step_count=kw["interval_steps"], time_step=kw["time_step"],
+                                   external_flux=np.atleast_1d(kw["external_flux"])[:, None, None], current_sources=0,
+                                   temperature=ref_style.T, store_current=False, store_voltage=False, stencil_width=3)
+    prof = np.zeros_like(prof_r)
+    for i in range(kw["interval_count"]):
+        prob.temperature = ref_style.T * np.ones((1, 1, kw["interval_steps"]))
+        prob.config_at_minus_1, prob.config_at_minus_2, prob.noise_replay = th, th.copy(), Z[i]
+        out = prob.compute()
+        ref_style._temperature_adjustment(ref_style.get_vortex_mobility(out.get_vortex_configuration()), i)
+        th = out.get_theta()[..., -1]
+        prof[i, :] = ref_style.T[0, :, 0]
+    assert np.array_equal(prof, prof_r)
+
+
 def test_phase_zones_at_the_rounding_ties():
     # the device takes round(theta / 2 pi) from a reciprocal product when that is safely away from a tie and from the
     # true division otherwise: phases placed on and next to the half-integers must give numpy's integers
