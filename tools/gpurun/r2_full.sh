@@ -12,3 +12,5 @@ print(d['cpu_baseline']['value'])
 "
 timeout 600 python tools/anneal_bench.py > gpurun_out/r2_anneal_bench.json 2> gpurun_out/r2_anneal_bench.err; tail -2 gpurun_out/r2_anneal_bench.err; head -c 500 gpurun_out/r2_anneal_bench.json; echo
 timeout 300 python __graft_entry__.py > gpurun_out/r2_smoke.txt 2>&1; tail -2 gpurun_out/r2_smoke.txt
+JJ_ANNEAL_INTERVALS=6 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/anneal_launches.csv python tools/anneal_launches.py > gpurun_out/anneal_launches.log 2>&1
+tail -1 gpurun_out/anneal_launches.log
