@@ -9,6 +9,14 @@ which = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
 if which == "cfg2":
     a = pj.SquareArray(100, 100); W = 256
     kw = dict(time_step=0.5, external_flux=0.1, temperature=np.geomspace(1e-2, 1, W)[None, :, None], noise_seed=1)
+elif which == "anneal":
+    # the annealing schedule: zone-byte variant of the step kernel, k_zone_mobility, amplitude / rule kernels, hand-over
+    # of the state to the half-step engine
+    a = pj.SquareArray(40, 37)
+    th, n, prof = pj.AnnealingProblem(a, time_step=0.5, interval_steps=5, external_flux=0.2, problem_count=40, interval_count=4,
+                                      vortex_mobility=0.02, start_T=0.4, T_factor=1.25, noise_seed=3).anneal()
+    print(which, "engine", engine.last_run_stats[0]["engine"], "finite", bool(np.all(np.isfinite(th))), "T", float(prof[-1].mean()))
+    sys.exit(0)
 else:
     # several items per block + upper program (the cfg3 / cfg4 / cfg5 regime, scaled down)
     os.environ["JJ_TT_MAX"] = "120"
