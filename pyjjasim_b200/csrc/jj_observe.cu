@@ -517,12 +517,17 @@ int jj_anneal(JJHandle* h, int64_t first_interval, int32_t n_intervals, int32_t 
     for (int i = 0; i < n_intervals && rc == JJ_OK && e == cudaSuccess; ++i) {
         k_anneal_amp<<<1, 256, 0, h->stream>>>(W, Wp, Td, h->src[JJ_SRC_T].table_buf);
         h->launches++;
-        if (first_interval + i > 0)      // zero-velocity restart of every interval but the first (time_evolution.py:1169-1171)
+        // zero-velocity restart of every interval but the first (time_evolution.py:1169-1171): the subdomain engine's
+        // first iteration reads theta(-2) from theta(-1) (it writes both back at the end of the run), the streaming
+        // engine gets a device copy
+        const bool restart = first_interval + i > 0;
+        if (restart && !sub)
             e = cudaMemcpyAsync(h->th2, h->th1, (size_t)c.Nj * Wp * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
         if (e != cudaSuccess) break;
         h->zone8 = zones ? reinterpret_cast<unsigned char*>(h->th_out) : nullptr;
+        h->start_at_rest = restart && sub;
         rc = run_enqueue(h, (first_interval + i) * (long long)steps, steps, planes.data(), nullptr);
-        h->zone8 = nullptr;
+        h->zone8 = nullptr; h->start_at_rest = false;
         if (rc) break;
         e = cudaMemsetAsync(sums, 0, (size_t)Wp * sizeof(unsigned long long), h->stream);
         if (zones) {

@@ -75,6 +75,7 @@ struct SubArgs {
     // state
     double *rth, *rx;               // [chunk][Nj'][PC]
     double *th1, *th2;              // canonical [Nj][Wp]
+    const double* th2_in;           // theta(-2) the run starts from: th2, or th1 for a start at rest (no copy needed)
     double *zloc, *ctop, *rtop, *jtop;
     unsigned* bar;
     // run
@@ -516,7 +517,7 @@ __device__ void junction_pass(const SubArgs& a, const AmpCache<8 * NG>* ac, int 
             const size_t sidx = ((size_t)c * a.Nj + jlo) * PC + (size_t)idx * 4;
             const size_t cidx = (size_t)jo * a.Wp + w;
             const double2* p1 = reinterpret_cast<const double2*>(a.th1 + cidx);
-            const double2* p2 = reinterpret_cast<const double2*>(a.th2 + cidx);
+            const double2* p2 = reinterpret_cast<const double2*>(a.th2_in + cidx);
             const double2 u0 = p1[0], u1 = p1[1], v0 = p2[0], v1 = p2[1];
             double2* op = reinterpret_cast<double2*>(a.rth + sidx);
             op[0] = u0; op[1] = u1;
@@ -1857,7 +1858,7 @@ static void fill_args(JJHandle* h, SubState* st, SubArgs& a) {
     a.Wp = h->Wp; a.n_chunks = st->n_chunks; a.dt = h->dt; a.seed = h->seed; a.group_offset = h->problem_offset / 4;
     a.Is = h->src[JJ_SRC_IS].dev; a.Vs = h->src[JJ_SRC_VS].dev; a.T = h->src[JJ_SRC_T].dev; a.F = h->src[JJ_SRC_F].dev;
     a.noise = h->noise_buf; a.noise_i0 = h->noise_i0; a.noise_K = h->noise_K;
-    a.rth = st->rth; a.rx = st->rx; a.th1 = h->th1; a.th2 = h->th2;
+    a.rth = st->rth; a.rx = st->rx; a.th1 = h->th1; a.th2 = h->th2; a.th2_in = h->start_at_rest ? h->th1 : h->th2;
     a.zloc = st->zloc; a.ctop = st->ctop; a.rtop = st->rtop; a.jtop = st->jtop; a.bar = st->bar;
     a.snap_th = h->th_out; a.snap_I = h->I_out; a.flag = h->flag_d;
     a.obs_first = h->obs_first; a.obs_interval = h->obs_interval;
