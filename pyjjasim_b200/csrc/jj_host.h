@@ -82,6 +82,7 @@ struct JJHandle {
     size_t obs_n_bytes = 0, obs_th_bytes = 0;
     // annealing (jj_anneal): the subdomain engine stores phase zones (one byte each) instead of phases, [planes][Nj][Wp]
     unsigned char* zone8 = nullptr;
+    unsigned long long src_gen = 1;   // bumped by jj_set_source: the subdomain engine re-gathers its per-junction / per-row constants
     bool start_at_rest = false;       // the next subdomain run reads theta(-2) from theta(-1) (jj_anneal: no restart copy)
     // subdomain engine (see jj_subdomain.cu)
     void *subdomain_plan = nullptr;

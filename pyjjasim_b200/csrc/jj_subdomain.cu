@@ -154,6 +154,7 @@ struct SubState {
     int n_chunks = 0, grid = 0;
     size_t smem_bytes = 0;
     bool prepared = false;
+    unsigned long long gather_gen = 0;     // JJHandle::src_gen the gathered constants (jrec, P0, P1, topF, rowF) were made for
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1878,7 +1879,11 @@ static int launch(JJHandle* h, SubState* st, SubArgs& a) {
     const bool general = st->n_up_fwd + st->n_up_bwd > 0 || st->P * st->n_chunks > cap || a.dbg_b != nullptr;
     KernelPtr k = pick_kernel(st->threads, st->NG, h->cir.default_cpr, general, a.zone8 != nullptr);
     if (!k) { h->err = "subdomain: no kernel for this block size / chunk width / item count"; return JJ_EINVAL; }
-    {
+    // per-junction records and per-row flux bases in device order: gathered again only after an input was redeclared
+    // (an annealing schedule launches the kernel hundreds of times on the same inputs)
+    const bool regather = st->gather_gen != h->src_gen;
+    st->gather_gen = h->src_gen;
+    if (regather) {
         const Source &is = h->src[JJ_SRC_IS].dev, &t = h->src[JJ_SRC_T].dev, &vs = h->src[JJ_SRC_VS].dev;
         k_sub_gather_params<<<(h->cir.Nj + 255) / 256, 256, 0, h->stream>>>(
             h->cir.Nj, st->junc_orig, h->cir.Ic, h->cir.c0, h->cir.c1, h->cir.c2,
@@ -1886,11 +1891,11 @@ static int launch(JJHandle* h, SubState* st, SubArgs& a) {
             vs.kind == KIND_RANK1 ? vs.base : nullptr, st->junc_row, st->junc_sign, st->P0, st->P1, st->jrec);
         h->launches++;
     }
-    if (a.topF) {
+    if (regather && a.topF) {
         k_sub_gather_top<<<(st->n_top + 255) / 256, 256, 0, h->stream>>>(st->n_top, st->top_face, h->src[JJ_SRC_F].dev.base, st->topF);
         h->launches++;
     }
-    if (a.rowF) {
+    if (regather && a.rowF) {
         const long long nr = (long long)st->P * st->n_rows;
         k_sub_gather_rows<<<(unsigned)((nr + 255) / 256), 256, 0, h->stream>>>(nr, st->face_fidx, h->src[JJ_SRC_F].dev.base, st->rowF);
         h->launches++;
@@ -1954,6 +1959,7 @@ int subdomain_prepare(JJHandle* h) {
     SCK(cudaMemsetAsync(st->ctop, 0, st->c_bytes, h->stream));
     SCK(cudaMemsetAsync(st->U, 0, st->u_bytes, h->stream));
     st->prepared = true;
+    st->gather_gen = 0;
     return JJ_OK;
 }
 

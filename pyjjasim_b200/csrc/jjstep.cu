@@ -370,6 +370,7 @@ int jj_create(int device, JJHandle** out) {
 const char* jj_last_error(const JJHandle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
 
 static void free_source(JJHandle* h, SourceHost& s) {
+    h->src_gen++;          // whatever the subdomain engine gathered from this input's base is stale
     dev_free(h, s.base_buf, s.N * sizeof(double));
     dev_free(h, s.table_buf, s.table_cap);
     s = SourceHost();
