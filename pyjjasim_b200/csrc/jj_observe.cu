@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(LANES * ROWS) k_vortex_mobility(const FaceView
     if (w < c.Wp) {
         for (int f = blockIdx.y * blockDim.y + threadIdx.y; f < c.Nf; f += gridDim.y * blockDim.y) {
             const int p0 = c.face_ptr[f], p1 = c.face_ptr[f + 1];
+            if (p1 == p0) continue;                       // (an empty row of the cycle matrix has no vorticity)
             if (p1 - p0 <= MOB_K) {
                 int j[MOB_K]; unsigned neg = 0u;          // junction rows and the bits of the negative cycle-matrix entries
                 const int ku = p1 - p0;
