@@ -108,6 +108,7 @@ void subdomain_get_config(JJHandle* h, int* P, int* PC);
 int run_enqueue(JJHandle* h, long long i0, int n, const long long* th_plane, const long long* I_plane);
 // implemented in jj_observe.cu
 void observe_free(JJHandle* h);
+void observe_off(JJHandle* h);
 bool observed_step(const JJHandle* h, long long step);
 long long observations_in(const JJHandle* h, long long i0, long long n);      // observations among steps [i0, i0 + n)
 int observe_streaming(JJHandle* h, long long step, const double* theta);      // streaming engine: one observation

@@ -474,7 +474,7 @@ int jj_set_problem(JJHandle* h, int32_t W, double dt, uint64_t seed, int64_t pro
         // the output planes stay allocated (jj_alloc_outputs reuses them when they are large enough): cudaFree and
         // cudaMalloc of ~100 MB cost tens of milliseconds per compute() call
         h->n_th_planes = h->n_I_planes = 0;
-        observe_free(h);
+        observe_off(h);           // (same problem size: the accumulators fit the next observation)
     } else {
         free_problem(h);
     }

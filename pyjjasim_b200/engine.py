@@ -912,7 +912,11 @@ def _run_shard(problem, tab, specs, dev, w0, w1, th_mask, I_mask, th_host, I_hos
                 if wanted.size:
                     n_all = eng.vortex_configurations(int(wanted[0]), int(wanted[-1] - wanted[0] + 1))
                     dst0 = int(np.count_nonzero(ex["wanted"][:i0]))
-                    ex["n_planes"][dst0:dst0 + wanted.size, :, w0:w1] = n_all[wanted - wanted[0]]
+                    sel = n_all if wanted[-1] - wanted[0] + 1 == wanted.size else n_all[wanted - wanted[0]]
+                    if dst0 == 0 and sel.shape == ex["n_planes"].shape:
+                        ex["n_planes"] = sel          # one shard, one chunk: the page-locked block itself, no second copy
+                    else:
+                        ex["n_planes"][dst0:dst0 + wanted.size, :, w0:w1] = sel
             if n_th and fetch_theta:
                 first = th_idx[i0:i1][tm][0]
                 eng.fetch_theta(0, n_th, out=th_host[lead + first: lead + first + n_th, :, w0:w1])

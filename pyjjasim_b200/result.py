@@ -173,7 +173,11 @@ class TimeEvolutionResult:
         planes = self.observed.get("n_planes")
         if planes is not None:
             steps = self._steps(select_time_points)
-            return np.moveaxis(planes[self.time_point_indices[steps]], 0, 2).astype(int)
+            idx = self.time_point_indices[steps]
+            if not (idx.size == planes.shape[0] and np.array_equal(idx, np.arange(idx.size))):
+                planes = planes[idx]
+            # (widened plane by plane in memory order, then viewed in the reference's (Nf, W, K) layout like the phases)
+            return np.moveaxis(planes.astype(int), 0, 2)
         return self._derive("vortex_configuration", select_time_points).astype(int)
 
     def get_energy(self, select_time_points=None):
