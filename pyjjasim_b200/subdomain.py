@@ -488,11 +488,22 @@ def _upper_program(F, top_rows, tt0, blk_of, n_chunks, n_up_pad):
         return [(r0, min(b1, r0 + RT), b0, b1) for (b0, b1) in blocks for r0 in range(b0, b1, RT)], n_split
 
     def dense_cols(M, r0, r1, lo, hi):
-        """columns in [lo, hi) that rows r0:r1 of the CSR matrix M touch, and the dense block over them"""
-        sub = M[r0:r1]
-        idx = sub.indices
-        cols = np.unique(idx[(idx >= lo) & (idx < hi)])
-        return cols, (sub[:, cols].toarray() if cols.size else np.zeros((r1 - r0, 0)))
+        """columns in [lo, hi) that rows r0:r1 of the CSR matrix M touch, and the dense block over them (straight from
+        the CSR arrays: thousands of these per plan, scipy's fancy indexing costs more than the work)"""
+        ptr = M.indptr[r0:r1 + 1]
+        idx, val = M.indices[ptr[0]:ptr[-1]], M.data[ptr[0]:ptr[-1]]
+        keep = np.flatnonzero((idx >= lo) & (idx < hi))
+        if keep.size == 0:
+            return np.zeros(0, dtype=idx.dtype), np.zeros((r1 - r0, 0))
+        rel = idx[keep] - lo
+        mark = np.zeros(hi - lo, dtype=bool)         # (a bitmap of the column window instead of a sort of the entries)
+        mark[rel] = True
+        cols = (np.flatnonzero(mark) + lo).astype(idx.dtype)
+        pos = (np.cumsum(mark) - 1)[rel]
+        rows = np.searchsorted(ptr, keep + ptr[0], side="right") - 1
+        D = np.zeros((r1 - r0, cols.size))
+        D[rows, pos] = val[keep]                     # (canonical CSR: one entry per position)
+        return cols, D
 
     def merged(blocks):
         """small separators: one phase per depth, z_B = inv(L_BB) r_B - (inv(L_BB) L[B, below]) z (the product is as
