@@ -386,6 +386,31 @@ def test_result_container_semantics():
     assert r.get_phase().shape == (a._Nn(), 1, 2)
 
 
+def test_vortex_configuration_from_device_planes_selects_and_widens_like_the_host_path():
+    # store_vortex_configuration: the result holds (K, Nf, W) int32 planes from the device (a page-locked block); the
+    # getter returns the reference's (Nf, W, K) int layout for all stored steps, a subset, and a reordered subset
+    a = pj.SquareArray(4, 5)
+    Nj, Nf, W = a._Nj(), a._Nf(), 3
+    stored = [1, 4, 5, 8]
+    p = pj.TimeEvolutionProblem(a, time_step_count=10, store_time_steps=stored, store_voltage=False, store_current=False,
+                                current_sources=np.zeros((Nj, W, 1)))
+    rng = np.random.RandomState(4)
+    th = 9.0 * rng.randn(Nj, W, len(stored))
+    A = a.get_cycle_matrix()
+    want = np.stack([-(A @ np.round(th[:, :, k] / (2 * np.pi))) for k in range(len(stored))], axis=2).astype(int)
+    planes = np.ascontiguousarray(np.moveaxis(want, 2, 0)).astype(np.int32)
+    r = pj.TimeEvolutionResult(p, th, None, None, observed=dict(n_planes=planes))
+    n = r.get_vortex_configuration()
+    assert n.shape == (Nf, W, len(stored)) and n.dtype == np.dtype(int) and np.array_equal(n, want)
+    assert np.array_equal(r.get_vortex_configuration([4, 8]), want[:, :, [1, 3]])
+    assert np.array_equal(np.reshape(r.get_vortex_configuration(5), (Nf, W)), want[:, :, 2])
+    # and it agrees with the host derivation from the phases
+    r_host = pj.TimeEvolutionResult(p, th, None, None)
+    assert np.array_equal(r_host.get_vortex_configuration(), want)
+    with pytest.raises(pj.DataAtTimepointNotStored):
+        r.get_vortex_configuration([2])
+
+
 def test_derived_quantities_are_batched_over_time_points_and_match_the_per_step_formulas():
     # every getter evaluates all selected time points in one batched operation; compare with the formulas of the
     # reference written out per time point (time_evolution.py:692-983)
