@@ -495,12 +495,14 @@ def _upper_program(F, top_rows, tt0, blk_of, n_chunks, n_up_pad):
         keep = np.flatnonzero((idx >= lo) & (idx < hi))
         if keep.size == 0:
             return np.zeros(0, dtype=idx.dtype), np.zeros((r1 - r0, 0))
-        rel = idx[keep] - lo
-        mark = np.zeros(hi - lo, dtype=bool)         # (a bitmap of the column window instead of a sort of the entries)
+        kept = idx[keep]
+        lo = int(kept.min())                         # (the touched columns usually span a small part of the window)
+        rel = kept - lo
+        mark = np.zeros(int(kept.max()) - lo + 1, dtype=bool)     # a bitmap of the column span instead of a sort of the entries
         mark[rel] = True
         cols = (np.flatnonzero(mark) + lo).astype(idx.dtype)
         pos = (np.cumsum(mark) - 1)[rel]
-        rows = np.searchsorted(ptr, keep + ptr[0], side="right") - 1
+        rows = np.repeat(np.arange(r1 - r0), np.diff(ptr))[keep]
         D = np.zeros((r1 - r0, cols.size))
         D[rows, pos] = val[keep]                     # (canonical CSR: one entry per position)
         return cols, D
