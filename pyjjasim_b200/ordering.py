@@ -50,6 +50,9 @@ def nested_dissection(S, cx, cy, leaf_size=24, return_tree=False, n_parts=None, 
     Sc = scipy.sparse.coo_matrix(S)
     off = Sc.row != Sc.col
     ei, ej = Sc.row[off].astype(np.int64), Sc.col[off].astype(np.int64)
+    xrank = np.unique(cx, return_inverse=True)[1].astype(np.int64)      # dense ranks of the coordinates
+    yrank = np.unique(cy, return_inverse=True)[1].astype(np.int64)
+    n_rank = int(max(xrank.max(initial=0), yrank.max(initial=0))) + 1
     dom = np.zeros(n, dtype=np.int64)          # subdomain id (path in the cut tree) of each unknown
     active = np.ones(n, dtype=bool)            # not yet placed in a block
     blk_depth = np.zeros(n, dtype=np.int64)    # (depth, dom) of the block each unknown ends up in
@@ -89,7 +92,12 @@ def nested_dissection(S, cx, cy, leaf_size=24, return_tree=False, n_parts=None, 
         cut_x = (hi_x - lo_x) >= (hi_y - lo_y)          # cut across the longer extent
         coord = np.where(cut_x[d], x, y)
         other = np.where(cut_x[d], y, x)
-        order = np.lexsort((other, coord, d))
+        # (d, coord, other) lexicographically, as ONE integer sort: the coordinates enter through their dense ranks
+        # (ties keep equal ranks, the sort is stable), which is several times faster than a three-key lexsort
+        rc_ = np.where(cut_x[d], xrank[idx], yrank[idx])
+        ro_ = np.where(cut_x[d], yrank[idx], xrank[idx])
+        order = np.argsort((d * n_rank + rc_) * n_rank + ro_, kind="stable") if n_dom * n_rank * n_rank < 2 ** 62 \
+            else np.lexsort((other, coord, d))
         sd = d[order]
         start = np.searchsorted(sd, np.arange(n_dom))
         rank = np.empty(idx.size, dtype=np.int64)
