@@ -139,6 +139,27 @@ def _pack_levels(levels, NG, n_warps, n_bwd=0):
                 vals=int(n_vals))
 
 
+def _background(fn, *args):
+    """start fn(*args) on a thread; the returned callable waits for it and returns its result (or re-raises)"""
+    import threading
+    box = {}
+
+    def run():
+        try:
+            box["value"] = fn(*args)
+        except BaseException as e:        # handed to the caller
+            box["error"] = e
+    t = threading.Thread(target=run, daemon=True)
+    t.start()
+
+    def result():
+        t.join()
+        if "error" in box:
+            raise box["error"]
+        return box["value"]
+    return result
+
+
 def _tri_inverse(L):
     """inverse of a dense lower-triangular matrix (LAPACK dtrtri)"""
     inv, info = scipy.linalg.lapack.dtrtri(np.asfortranarray(L), lower=1)
@@ -704,6 +725,9 @@ def subdomain_plan(F, junc_face, d, NG, n_warps=RES_WARPS, groups=None, tt_max=N
     stage_cap = min(stage_cap, 4096)
     vrow_loc = np.full(n, -1, dtype=np.int64)            # shared-memory row of every local face in its subdomain
     cache = {}                                           # digest of a subdomain's inputs -> its program
+    # the program of the upper separators depends on the factor and the cut only: it is built on a second thread while
+    # this one goes through the subdomains (numpy / scipy / LAPACK release the interpreter lock in their kernels)
+    upper_job = _background(_upper_program, F, top_rows, tt0, blk_of, max(1, int(n_chunks)), plan.n_up_pad)
     for s in range(P):
         if loc[s].size == 0:             # a cut deeper than a small circuit's tree leaves subtrees without rows
             hit = cache.setdefault(b"empty", (_pack_levels([], NG, n_warps, 0), 0, np.zeros(0, dtype=np.int64), [],
@@ -753,7 +777,7 @@ def subdomain_plan(F, junc_face, d, NG, n_warps=RES_WARPS, groups=None, tt_max=N
         plan.Sinv = np.zeros((0, 0))
         plan.Sinv_packed = np.zeros(0)
     # ---- upper separators between the subdomains and the top of the top
-    plan.upper = _upper_program(F, top_rows, tt0, blk_of, max(1, int(n_chunks)), plan.n_up_pad)
+    plan.upper = upper_job()
     if plan.upper["n_fwd"] + plan.upper["n_bwd"] > 0:
         # the upper phases gather into two panel buffers of at least 256 rows and reduce over 16 warps in shared memory
         need = max(2 * (128 if NG >= 8 else 256) * PC, 16 * NG * 64) - plan.n_rows * PC
